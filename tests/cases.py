@@ -1,0 +1,53 @@
+"""Golden-fixture case table shared by tests/golden/make_golden.py (which runs the reference) and
+the parity tests (which regenerate the same seeded inputs and compare with the stored outputs)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from veto_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = {
+    # BASELINE.json configs[0]: 1 image 592x800, 20 GT boxes -> 380 pairs, VG 151/51, PredCls
+    "cfg1_predcls_vg": dict(predictor="VETOPredictor", mode="predcls", dataset="VG", n_boxes=[20],
+                            batch_seed=1, weight_seed=11, spread=True, tokens=[0, 57, 379]),
+    # same inputs, torch-default-like init (every pair gets the same label: vacuous for argmax but
+    # pins the un-spread numerics)
+    "cfg1_default_init": dict(predictor="VETOPredictor", mode="predcls", dataset="VG", n_boxes=[20],
+                              batch_seed=1, weight_seed=12, spread=False),
+    # ragged multi-image batch incl. the degenerate sizes: 1 box (0 pairs -> [[0,0]] placeholder), 2 boxes
+    "ragged_predcls": dict(predictor="VETOPredictor", mode="predcls", dataset="VG", n_boxes=[1, 2, 7, 3],
+                           batch_seed=2, weight_seed=11, spread=True, H=320, W=416, tokens=[0, 1, 2]),
+    # SGDet-shaped: soft class embedding (softmax @ obj_embed), pair cap hit (12*11=132 > 100)
+    "sgdet_cap": dict(predictor="VETOPredictor", mode="sgdet", dataset="VG", n_boxes=[12, 9],
+                      batch_seed=3, weight_seed=13, spread=True, max_pairs=100, H=320, W=416),
+    # SGDet with TEST.RELATION.REQUIRE_OVERLAP (sampling.py:38-39)
+    "sgdet_overlap": dict(predictor="VETOPredictor", mode="sgdet", dataset="VG", n_boxes=[10],
+                          batch_seed=4, weight_seed=13, spread=True, require_overlap=True, H=320, W=416),
+    # BASELINE.json configs[3] (reduced batch): MEET group heads, GQA 201/101, divide4
+    "meet_gqa": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="GQA", n_boxes=[20, 9],
+                     batch_seed=5, weight_seed=14, spread=True),
+    "meet_vg": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", n_boxes=[10],
+                    batch_seed=6, weight_seed=15, spread=True, H=320, W=416),
+}
+
+
+def case_batch(c, features=True):
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    return synth.make_batch(c["batch_seed"], c["n_boxes"], H=c.get("H", 592), W=c.get("W", 800),
+                            num_obj=ds["num_obj"], mode=c["mode"], features=features)
+
+
+def case_state(c):
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    if c["predictor"].endswith("MEET"):
+        return synth.meet_state(c["weight_seed"], ds["num_obj"], synth.GROUP_SPLITS[(c["dataset"], "divide4")],
+                                spread=c["spread"])
+    return synth.predictor_state(c["weight_seed"], ds["num_obj"], ds["num_rel"], spread=c["spread"])
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))

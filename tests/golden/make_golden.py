@@ -1,0 +1,106 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:  python tests/golden/make_golden.py
+Inputs and weights are regenerated from seeds by veto_b200.synth at test time (they are too large
+to commit: 43 MB of feature maps per image, 70 MB of weights); the fixtures hold the reference's
+OUTPUTS plus sha256 digests of the inputs/weights they were computed from.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from veto_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# name -> case description; shared with tests/cases.py
+from tests.cases import CASES, case_batch, case_state  # noqa: E402
+
+
+def digest(arrs) -> str:
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def run_case(ns, name, c):
+    import torch
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    meet = c["predictor"].endswith("MEET")
+    cfg = ref_shim.make_cfg(ns, predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"],
+                            max_pairs=c.get("max_pairs", 2048), require_overlap=c.get("require_overlap", False))
+    sd = case_state(c)
+    pred = ref_shim.build_predictor(ns, cfg, ds["num_obj"], ds["num_rel"], synth.to_torch_state(sd))
+    batch = case_batch(c)
+    bls = ref_shim.make_boxlists(ns, batch, ds["num_obj"])
+    fe = ns.make_extractor(cfg, 256, for_relation=True).eval()
+    samp, post = ns.make_sampler(cfg), ns.make_post(cfg)
+    out = {}
+    with torch.no_grad():
+        pairs = samp.prepare_test_pairs(torch.device("cpu"), bls)
+        feats = [torch.from_numpy(f) for f in batch["feats"]]
+        feats.append(torch.zeros(batch["B"], 256, 1, 1))            # P6: present in the reference, unused
+        x2d, d2d, _, _ = fe(feats, bls, depth_features=torch.from_numpy(batch["depth"]))
+        obj_d, rel_d, losses, incre, chosen, custom = pred(bls, pairs, None, None, roi_features=x2d,
+                                                          roi_depth_features=d2d)
+    out["input_digest"] = np.array(digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]))
+    out["weight_digest"] = np.array(digest([sd[k] for k in sorted(sd)]))
+    out["pairs"] = np.concatenate([p.numpy() for p in pairs])
+    out["pair_counts"] = np.array([len(p) for p in pairs])
+    out["x2d_sub"] = x2d.numpy()[:, ::16].copy()
+    out["d2d_sub"] = d2d.numpy()[:, ::16].copy()
+    out["x2d_sum"] = x2d.numpy().sum(axis=(1, 2, 3), dtype=np.float64)
+    out["d2d_sum"] = d2d.numpy().sum(axis=(1, 2, 3), dtype=np.float64)
+    out["obj_dists_argmax"] = np.concatenate([o.numpy().argmax(1) for o in obj_d])
+    if meet:
+        for k, v in rel_d.items():
+            out["logits_" + k] = v.numpy()
+        out["incre_idx_list"] = np.array(incre)
+    else:
+        out["logits"] = np.concatenate([r.numpy() for r in rel_d])
+        if c["mode"] == "predcls":
+            res = post((rel_d, [b.get_field("predict_logits") for b in bls]), pairs, bls)
+            out["post_pairs"] = np.concatenate([r.get_field("rel_pair_idxs").numpy() for r in res])
+            out["post_labels"] = np.concatenate([r.get_field("pred_rel_labels").numpy() for r in res])
+            out["post_scores"] = np.concatenate([r.get_field("pred_rel_scores").numpy()[:, 1:].max(1) for r in res])
+    if c.get("tokens"):
+        # token tensor of a few pairs, captured at the encoder input (model_veto.py:16)
+        keep = {}
+        tr = pred.fusion_transformer.transformer if not meet else pred.model.fusion_transformer.transformer
+        def _hook(m, i, o):
+            keep["tok"] = o.detach().numpy()
+        h = tr.register_forward_hook(_hook)
+        with torch.no_grad():
+            pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)
+        h.remove()
+        sel = np.array(c["tokens"])
+        out["token_rows"] = sel
+        out["tokens"] = keep["tok"][sel]
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KB)",
+          {k: v.shape for k, v in out.items() if hasattr(v, 'shape') and v.ndim})
+
+
+def main():
+    ns = ref_shim.load()
+    only = sys.argv[1:]
+    for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        run_case(ns, name, c)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""CPU tests: the oracle (oracle/veto_oracle.py + roialign_oracle.c) against the golden fixtures
+produced by the unmodified reference (tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import veto_oracle as O
+from tests.cases import CASES, case_batch, case_state, load_golden
+from tests.util import tie_groups_equal
+from veto_b200 import synth
+
+REL_TOL = 2e-5   # oracle (numpy fp32/OpenBLAS) vs reference (torch fp32/MKL): summation order only
+
+
+def _digest(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _pairs(c, batch):
+    return O.prepare_test_pairs(batch["n_boxes"], c.get("max_pairs", 2048),
+                                scores=batch.get("pred_scores"), boxes=batch["boxes"],
+                                require_overlap=c.get("require_overlap", False) and c["mode"] == "sgdet")
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    c = CASES[request.param]
+    g = load_golden(request.param)
+    batch = case_batch(c)
+    return request.param, c, g, batch
+
+
+def test_inputs_reproduce(case):
+    name, c, g, batch = case
+    assert _digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]) == str(g["input_digest"])
+    sd = case_state(c)
+    assert _digest([sd[k] for k in sorted(sd)]) == str(g["weight_digest"])
+
+
+def test_pairs_bit_exact(case):
+    name, c, g, batch = case
+    pairs = _pairs(c, batch)
+    assert [len(p) for p in pairs] == list(g["pair_counts"])
+    if "max_pairs" not in c:
+        assert np.array_equal(np.concatenate(pairs), g["pairs"])
+        return
+    # over the cap the order is (score desc) with the reference's unstable sort deciding ties
+    off = 0
+    for k, p in enumerate(pairs):
+        ref = g["pairs"][off:off + len(p)]
+        off += len(p)
+        s = batch["pred_scores"][k]
+        key = s[ref[:, 0]] * s[ref[:, 1]]
+        if len(p) == c["max_pairs"]:
+            assert np.all(np.diff(key) <= 0)
+            assert tie_groups_equal(p, ref, key)
+        else:
+            assert np.array_equal(p, ref)
+
+
+def test_gather_bit_exact(case):
+    name, c, g, batch = case
+    x2d, d2d = O.pooler_forward(batch["feats"], batch["depth"], batch["boxes"])
+    assert np.array_equal(x2d[:, ::16], g["x2d_sub"])
+    assert np.array_equal(d2d[:, ::16], g["d2d_sub"])
+    assert np.array_equal(x2d.sum(axis=(1, 2, 3), dtype=np.float64), g["x2d_sum"])
+    assert np.array_equal(d2d.sum(axis=(1, 2, 3), dtype=np.float64), g["d2d_sum"])
+
+
+def test_all_levels_populated():
+    b = case_batch(CASES["cfg1_predcls_vg"], features=False)
+    assert set(O.level_map(b["boxes"]).tolist()) == {0, 1, 2, 3}
+    assert np.array_equal(O.level_map(b["boxes"]), synth.box_levels(np.concatenate(b["boxes"])))
+
+
+def test_logits(case):
+    name, c, g, batch = case
+    sd = case_state(c)
+    pairs = _pairs(c, batch)
+    if "max_pairs" in c:      # row alignment with the golden logits: use the reference's tie order
+        pairs = np.split(g["pairs"], np.cumsum(g["pair_counts"])[:-1])
+    x2d, d2d = O.pooler_forward(batch["feats"], batch["depth"], batch["boxes"])
+    if c["predictor"].endswith("MEET"):
+        gs = synth.GROUP_SPLITS[(c["dataset"], "divide4")]
+        out = O.meet_forward(sd, batch, pairs, x2d, d2d, gs, c["mode"])
+        ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+        assert O.incre_idx_list(gs, ds["num_rel"]) == list(g["incre_idx_list"])
+        for k, v in out.items():
+            ref = g["logits_" + k]
+            assert v.shape == ref.shape
+            assert np.abs(v - ref).max() <= REL_TOL * np.abs(ref).max(), k
+            assert np.array_equal(v.argmax(1), ref.argmax(1))
+        return
+    logits = O.predictor_forward(sd, batch, pairs, x2d, d2d, c["mode"])
+    ref = g["logits"]
+    assert np.abs(logits - ref).max() <= REL_TOL * np.abs(ref).max()
+    assert np.array_equal(logits.argmax(1), ref.argmax(1))
+    if c["spread"] and len(ref) >= 300:
+        assert len(np.unique(ref[:, 1:].argmax(1))) >= 10      # the argmax check is not vacuous
+    if "tokens" in g.files:
+        tok = O.tokens_only(sd, batch, pairs, x2d, d2d, c["mode"])[g["token_rows"]]
+        assert np.abs(tok - g["tokens"]).max() <= REL_TOL * np.abs(g["tokens"]).max()
+    if "post_pairs" in g.files:
+        obj_logits, off = [], 0
+        for lab in batch["labels"]:
+            ol = np.full((len(lab), batch["num_obj"]), -1000.0, np.float32)    # to_onehot, model_kern.py:266-281
+            ol[np.arange(len(lab)), lab] = 1000.0
+            obj_logits.append(ol)
+        split = np.cumsum([len(p) for p in pairs])[:-1]
+        res = O.postprocess(np.split(ref, split), obj_logits, pairs)
+        # ranking parity is tie-aware: scores must agree, and wherever scores are distinct so must rows
+        s = np.concatenate([r["triple_scores"] for r in res])
+        assert np.allclose(s, g["post_scores"], rtol=1e-6, atol=0)
+        pp = np.concatenate([r["rel_pair_idxs"] for r in res])
+        distinct = np.ones(len(s), bool)
+        distinct[1:] &= s[1:] != s[:-1]
+        distinct[:-1] &= s[:-1] != s[1:]
+        assert np.array_equal(pp[distinct], g["post_pairs"][distinct])
+        assert np.array_equal(np.concatenate([r["pred_rel_labels"] for r in res])[distinct], g["post_labels"][distinct])
+
+
+def test_empty_and_degenerate_pairs():
+    p = O.prepare_test_pairs([1, 2, 0])
+    assert np.array_equal(p[0], [[0, 0]]) and np.array_equal(p[1], [[0, 1], [1, 0]]) and np.array_equal(p[2], [[0, 0]])
+    for n in (3, 20, 80):
+        q = O.prepare_test_pairs([n], max_pairs=10 ** 9)[0]
+        r = np.arange(n * (n - 1))
+        i, j = r // (n - 1), r % (n - 1)
+        j = j + (j >= i)
+        assert np.array_equal(q, np.stack([i, j], 1))          # closed form used by the CUDA kernel
+
+
+def _ref_lib():
+    import ctypes
+    import os
+    path = os.path.join(os.path.dirname(O.__file__), "_ref", "libref_roialign.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference: bash oracle/build_ref.sh)")
+    import torch  # noqa: F401  (libtorch must be resident before the reference .so is opened)
+    lib = ctypes.CDLL(path)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.ref_roi_align_forward.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int,
+                                          ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
+    return lib
+
+
+@pytest.mark.parametrize("scale,hw", [(0.25, (40, 52)), (0.125, (20, 26)), (0.0625, (10, 13)), (0.03125, (5, 7))])
+def test_roialign_c_oracle_equals_compiled_reference(scale, hw):
+    """oracle/roialign_oracle.c vs the unmodified reference ROIAlign_cpu.cpp (oracle/_ref): bit-exact,
+    including boxes hanging outside the map, degenerate (<1 px) boxes and sampling_ratio<=0."""
+    import ctypes
+    lib = _ref_lib()
+    rng = np.random.default_rng(int(scale * 1e5))
+    B, C = 2, 5
+    inp = rng.standard_normal((B, C) + hw, dtype=np.float32)
+    W, H = hw[1] / scale, hw[0] / scale
+    boxes = synth.make_boxes(rng, 12, int(W), int(H), max_side=min(W, H) * 0.9)
+    boxes = np.concatenate([boxes, np.array([[-30, -20, 40, 50], [W - 10, H - 10, W + 60, H + 40],
+                                             [10, 10, 10.2, 10.1], [W + 50, H + 50, W + 90, H + 90]], np.float32)])
+    rois = np.concatenate([rng.integers(0, B, (len(boxes), 1)).astype(np.float32), boxes], 1)
+    for sr in (2, 0, 3):
+        mine = O.roi_align(inp, rois, scale, 8, 8, sr)
+        ref = np.empty_like(mine)
+        fp = ctypes.POINTER(ctypes.c_float)
+        lib.ref_roi_align_forward(inp.ctypes.data_as(fp), B, C, hw[0], hw[1], rois.ctypes.data_as(fp), len(rois),
+                                  scale, 8, 8, sr, ref.ctypes.data_as(fp))
+        assert np.array_equal(mine, ref), sr
+
+
+def test_roialign_backward_matches_torchvision():
+    import torch
+    import torchvision
+    rng = np.random.default_rng(7)
+    inp_shape = (2, 3, 10, 13)
+    boxes = synth.make_boxes(rng, 9, 208, 160, max_side=140)
+    rois = np.concatenate([rng.integers(0, 2, (9, 1)).astype(np.float32), boxes], 1)
+    g = rng.standard_normal((9, 3, 8, 8), dtype=np.float32)
+    mine = O.roi_align_backward(g, rois, inp_shape, 0.0625, 2)
+    ref = torch.ops.torchvision._roi_align_backward(torch.from_numpy(g), torch.from_numpy(rois), 0.0625, 8, 8,
+                                                    2, 3, 10, 13, 2, False).numpy()
+    assert np.allclose(mine, ref, rtol=1e-5, atol=1e-6)
