@@ -1,0 +1,243 @@
+/*
+ * veto_b200.h — C ABI of libveto_b200.so: the B200 (sm_100a) implementation of the VETO
+ * relation-prediction hot path of visinf/veto (reference tree paths are relative to the reference
+ * repository root; see SURVEY.md §8 for the scope table this ABI covers).
+ *
+ * Conventions (SURVEY.md §8b "what a C-ABI replacement must export"):
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every *_dev pointer is device memory owned by the caller (PyTorch's caching allocator on the
+ *     reference side); the library never frees or retains caller buffers beyond the call — packed
+ *     weights and workspaces are caller-allocated too (sizes from the *_bytes functions);
+ *   - every entry point enqueues on the given stream (a cudaStream_t passed as void*) and returns
+ *     without synchronising, except where a host copy of a small table is documented;
+ *   - return value 0 = ok, < 0 = error; veto_last_error() gives the message (thread-local).
+ *     No C++ exception crosses the ABI (the reference raises RuntimeError from AT_ERROR /
+ *     AT_ASSERTM, pysgg/csrc/ROIAlign.h:11-44; the Python host turns a negative code into one).
+ */
+#ifndef VETO_B200_H
+#define VETO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VETO_ABI_VERSION 1
+
+enum {
+    VETO_OK = 0,
+    VETO_ERR_ARG = -1,          /* bad argument / shape */
+    VETO_ERR_CUDA = -2,         /* a CUDA runtime or driver call failed */
+    VETO_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels are built for */
+    VETO_ERR_WORKSPACE = -4     /* workspace / packed buffer too small */
+};
+
+/* Arithmetic of the token-wise GEMMs of the encoder (model_veto.py:15-26).
+ *   FP32   : fp32 SIMT FMA everywhere (the reference's own precision, DTYPE "float32").
+ *   BF16X3 : tcgen05 tensor cores, every operand split into bf16 hi+lo, 3 MMAs per product,
+ *            fp32 accumulate in TMEM — fp32-grade results (rel. error ~1e-5).
+ *   BF16   : tcgen05 tensor cores, single bf16 pass, fp32 accumulate (stated tolerance 2e-2). */
+enum { VETO_PREC_FP32 = 0, VETO_PREC_BF16X3 = 1, VETO_PREC_BF16 = 2 };
+
+typedef void* veto_stream_t; /* cudaStream_t */
+
+int veto_abi_version(void);
+const char* veto_last_error(void);
+/* 0 if the current device can run the sm_100a kernels, VETO_ERR_UNSUPPORTED otherwise. */
+int veto_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1. Candidate-pair enumeration.
+ * Replaces RelationSampling.prepare_test_pairs
+ * (pysgg/modeling/roi_heads/relation_head/sampling.py:31-52).
+ *
+ * For image b with n_b boxes: all ordered pairs (i,j), i != j, row-major (== torch.nonzero of
+ * ones-eye); if require_overlap, only pairs with boxlist_iou > 0 (structures/boxlist_ops.py:54-87,
+ * +1 convention); if more than max_pairs remain, the top max_pairs by scores[i]*scores[j] (fp32),
+ * ordered by (product descending, row-major index ascending) — the reference's torch.sort is
+ * unstable, this is the tie-break its CPU path shows; if none remain, the single placeholder
+ * pair (0,0) (sampling.py:47-51).
+ *
+ * n_boxes_host [n_images] (host).  Image b's pairs are written at row out_offset(b) =
+ * sum_{a<b} cap(a), cap(a) = max(1, min(n_a*(n_a-1), max_pairs)); counts_out_dev[b] = number of
+ * valid rows.  With require_overlap == 0 counts are known on the host (== cap) and
+ * counts_out_dev may be NULL.  scratch_dev: >= 3*(n_images+1) int32.
+ * boxes_dev [N,4] fp32 xyxy (needed iff require_overlap); scores_dev [N] fp32 (needed iff some
+ * image exceeds max_pairs).  The filtered / capped path holds one image's candidates in shared
+ * memory: n_b*(n_b-1) <= 16384 (n_b <= 128) there, else VETO_ERR_UNSUPPORTED.
+ * The small offset tables are copied host->device on `stream` before the kernel. */
+int veto_pairs_capacity(const int32_t* n_boxes_host, int n_images, int max_pairs, int64_t* total_rows);
+int veto_pairs_enumerate(const int32_t* n_boxes_host, int n_images,
+                         const float* boxes_dev, const float* scores_dev,
+                         int require_overlap, int max_pairs,
+                         int64_t* pairs_out_dev, int32_t* counts_out_dev,
+                         int32_t* scratch_dev, veto_stream_t stream);
+
+/* Per-image local pair indices -> global box indices (roi_relation_predictors.py:4104-4115,
+ * a host loop over CPU tensors in the reference).  pairs_dev int64 [R,2]; rel_offsets_dev /
+ * box_offsets_dev int32 [n_images+1] prefix sums; subj/obj out int32 [R]. */
+int veto_pairs_globalize(const int64_t* pairs_dev, int64_t n_pairs,
+                         const int32_t* rel_offsets_dev, const int32_t* box_offsets_dev, int n_images,
+                         int32_t* subj_out_dev, int32_t* obj_out_dev, veto_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3. ROIAlign.  veto_roi_align_forward is the one-for-one replacement of
+ * _C.roi_align_forward(input, rois, spatial_scale, ph, pw, sampling_ratio)
+ * (pysgg/csrc/vision.cpp:11, ROIAlign.h:11-24, cuda/ROIAlign_cuda.cu:65-122,257-299): legacy
+ * (non-aligned) ROIAlign, input NCHW fp32 [B,C,H,W], rois [N,5] fp32 (batch idx, x1,y1,x2,y2),
+ * out [N,C,ph,pw] fp32.  Bit-exact with the reference's CPU kernel (ROIAlign_cpu.cpp:114-219).
+ * sampling_ratio must be > 0 and ph*pw*sampling_ratio^2 <= 1024.
+ *
+ * veto_roi_align_backward replaces _C.roi_align_backward (ROIAlign_cuda.cu:178-254): scatters
+ * grad [N,C,ph,pw] into grad_input [B,C,H,W] (zero-initialised here) with fp32 atomics. */
+int veto_roi_align_forward(const float* input_dev, int batch, int channels, int height, int width,
+                           const float* rois_dev, int n_rois, float spatial_scale,
+                           int pooled_h, int pooled_w, int sampling_ratio,
+                           float* out_dev, veto_stream_t stream);
+int veto_roi_align_backward(const float* grad_dev, const float* rois_dev, int n_rois, float spatial_scale,
+                            int pooled_h, int pooled_w, int batch, int channels, int height, int width,
+                            int sampling_ratio, float* grad_input_dev, veto_stream_t stream);
+
+/* a2+a3 fused: Pooler.forward depth + RGB branch (pysgg/modeling/poolers.py:109-171) as used by
+ * VETOFeatureExtractor.forward (box_head/roi_box_feature_extractors.py:116-135) in ONE launch:
+ * rois from boxes + per-image box offsets (poolers.py:96-107), FPN level per box by LevelMapper
+ * (poolers.py:32-43; area with the +1 convention, bounding_box.py:249-253), RGB pooled from its
+ * level's map, depth always from `depth_dev` with `depth_scale` (poolers.py:144-153).
+ * feats_dev: n_levels (<= 4) device pointers (host array), each [B,C,feat_h[l],feat_w[l]].
+ * boxes_dev [N,4] fp32 xyxy; box_offsets_dev int32 [n_images+1].
+ * Outputs out_rgb_dev / out_depth_dev [N,C,pool,pool] fp32; levels_out_dev int32 [N] or NULL. */
+int veto_roi_gather_forward(const float* const* feats_dev, const int32_t* feat_h, const int32_t* feat_w,
+                            const float* scales, int n_levels, int k_min, int k_max,
+                            const float* depth_dev, int depth_h, int depth_w, float depth_scale,
+                            int batch, int channels,
+                            const float* boxes_dev, const int32_t* box_offsets_dev, int n_images, int n_boxes,
+                            int pool, int sampling_ratio,
+                            float* out_rgb_dev, float* out_depth_dev, int32_t* levels_out_dev,
+                            veto_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5-a10. The relation head proper: VETOPredictor.forward / Ensemble.forward
+ * (roi_relation_predictors.py:4074-4139, 3752-3853) with VETOTransformer (model_veto.py).
+ * The architecture constants of configs/VETO_final.yaml are compiled in (T_INPUT_DIM 576, 6 heads
+ * of 96, MLP 1152, PATCH_SIZE 2 on 8x8 maps -> 19 tokens, 256 ROI channels, proj_d 512 + proj_v 64,
+ * 128-d position and 200-d class embeddings); veto_config is validated against them. */
+typedef struct {
+    int32_t dim;        /* 576  MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER.T_INPUT_DIM */
+    int32_t layers;     /* 6    ENC_LAYERS (1..16) */
+    int32_t heads;      /* 6    NHEADS */
+    int32_t mlp_dim;    /* 1152 (model_veto.py:35) */
+    int32_t channels;   /* 256  ROI feature channels */
+    int32_t pool;       /* 8    POOLER_RESOLUTION */
+    int32_t patch;      /* 2    PATCH_SIZE */
+    int32_t num_obj;    /* 151 (VG) / 201 (GQA) */
+    int32_t num_out;    /* rel_out rows: 51 / 101, or for MEET the sum over heads of (n_k + 2) */
+    int32_t precision;  /* VETO_PREC_* */
+} veto_config;
+
+#define VETO_MAX_LAYERS 16
+
+/* Device pointers to the reference module's parameters, fp32, in state_dict layout
+ * (SURVEY.md §8a "State-dict keys"). */
+typedef struct {
+    const float* obj_embed;                 /* obj_embed.weight            [num_obj,200] */
+    const float* class_proj_w;              /* class_projection.0.weight   [576,400] */
+    const float* class_proj_b;              /* class_projection.0.bias     [576] */
+    const float* bn_weight;                 /* pos_embed.0.weight          [4] */
+    const float* bn_bias;                   /* pos_embed.0.bias            [4] */
+    const float* bn_mean;                   /* pos_embed.0.running_mean    [4] */
+    const float* bn_var;                    /* pos_embed.0.running_var     [4] */
+    const float* pos_w;                     /* pos_embed.1.weight          [128,4] */
+    const float* pos_b;                     /* pos_embed.1.bias            [128] */
+    const float* loc_proj_w;                /* location_projection.0.weight[576,256] */
+    const float* loc_proj_b;                /* location_projection.0.bias  [576] */
+    const float* cls_token;                 /* ...transformer.cls_token    [576] */
+    const float* pos_embedding;             /* ...transformer.pos_embedding[576] */
+    const float* proj_d_w;                  /* ...patch_embed.proj_d.weight[512,2048] */
+    const float* proj_d_b;                  /* ...patch_embed.proj_d.bias  [512] */
+    const float* proj_v_w;                  /* ...patch_embed.proj_v.weight[64,2048] */
+    const float* proj_v_b;                  /* ...patch_embed.proj_v.bias  [64] */
+    const float* ln1_w[VETO_MAX_LAYERS];    /* layers.i.0.norm.weight      [576] */
+    const float* ln1_b[VETO_MAX_LAYERS];    /* layers.i.0.norm.bias        [576] */
+    const float* qkv_w[VETO_MAX_LAYERS];    /* layers.i.0.fn.to_qkv.weight [1728,576] (no bias) */
+    const float* out_w[VETO_MAX_LAYERS];    /* layers.i.0.fn.to_out.0.weight [576,576] */
+    const float* out_b[VETO_MAX_LAYERS];    /* layers.i.0.fn.to_out.0.bias [576] */
+    const float* ln2_w[VETO_MAX_LAYERS];    /* layers.i.1.norm.weight      [576] */
+    const float* ln2_b[VETO_MAX_LAYERS];    /* layers.i.1.norm.bias        [576] */
+    const float* ff1_w[VETO_MAX_LAYERS];    /* layers.i.1.fn.net.0.weight  [1152,576] */
+    const float* ff1_b[VETO_MAX_LAYERS];    /* layers.i.1.fn.net.0.bias    [1152] */
+    const float* ff2_w[VETO_MAX_LAYERS];    /* layers.i.1.fn.net.3.weight  [576,1152] */
+    const float* ff2_b[VETO_MAX_LAYERS];    /* layers.i.1.fn.net.3.bias    [576] */
+    const float* rel_out_w;                 /* rel_out.weight [num_out,576] (MEET: heads concatenated) */
+    const float* rel_out_b;                 /* rel_out.bias   [num_out] */
+} veto_weights;
+
+/* Derived weights (subject/object-factored projections, bf16 hi/lo splits for the tensor-core
+ * modes).  The caller allocates veto_packed_bytes(cfg) of device memory, veto_pack_weights fills
+ * it; it must be re-packed whenever the source parameters change.  The source pointers in
+ * veto_weights must stay valid for every later forward call (they are read directly too). */
+size_t veto_packed_bytes(const veto_config* cfg);
+int veto_pack_weights(const veto_config* cfg, const veto_weights* w, void* packed_dev, size_t packed_bytes,
+                      veto_stream_t stream);
+
+typedef struct {
+    int32_t n_boxes;                /* N */
+    int64_t n_pairs;                /* R */
+    const float* boxes;             /* [N,4] fp32 xyxy pixels (BoxList.bbox) */
+    const int64_t* labels;          /* [N] hard class ids: predcls labels (…:4087) or MEET obj_preds
+                                       (…:3783); NULL => soft embedding from `obj_logits` */
+    const float* obj_logits;        /* [N,num_obj] predict_logits (softmax @ obj_embed, …:4095) or NULL */
+    const float* roi_rgb;           /* roi_features        [N,256,8,8] */
+    const float* roi_depth;         /* roi_depth_features  [N,256,8,8] */
+    const int32_t* subj;            /* [R] global subject box index */
+    const int32_t* obj;             /* [R] global object box index */
+    const float* freq_bias;         /* optional [num_obj*num_obj, num_out] table (model_motifs.py:29-38),
+                                       added as row labels[s]*num_obj+labels[o]; NULL = off (the
+                                       reference never applies it for VETO: SURVEY.md note A) */
+} veto_inputs;
+
+typedef struct {
+    float* rel_logits;              /* [R,num_out] */
+    float* rel_features;            /* optional [R,576]: encoder CLS output (x[:,0], model_veto.py:25) */
+    float* tokens;                  /* optional [R,19,576]: encoder input (debug / stage parity) */
+} veto_outputs;
+
+/* Pairs are processed in chunks of `chunk_pairs` (0 = library default) so that the activations of
+ * one chunk stay L2-resident; the workspace scales with N and the chunk, not with R. */
+size_t veto_workspace_bytes(const veto_config* cfg, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs);
+int veto_relation_forward(const veto_config* cfg, const veto_weights* w, const void* packed_dev,
+                          const veto_inputs* in, const veto_outputs* out,
+                          void* workspace_dev, size_t workspace_bytes, int32_t chunk_pairs,
+                          veto_stream_t stream);
+/* Number of kernel launches the last veto_relation_forward on this thread enqueued. */
+int64_t veto_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a12 (row f1). PostProcessor.forward, vanilla branch (relation_head/inference.py:398-453):
+ * softmax over rel logits, max over classes 1.., triple score rel*obj_s*obj_o, per-image sort
+ * descending (ties: original row ascending).  obj_scores [N] fp32; rel_offsets int32 [n_images+1]
+ * over rows of rel_logits; pairs int64 [R,2] local indices; box_offsets int32 [n_images+1].
+ * Outputs (all [R] rows, image-segmented like the input): sorted pairs int64 [R,2], class
+ * probabilities [R,num_rel], labels int64 [R], triple scores [R].  One image is sorted in
+ * shared memory: R_i <= 16384.  */
+int veto_postprocess(const float* rel_logits_dev, int num_rel, const int64_t* pairs_dev,
+                     const float* obj_scores_dev, const int32_t* rel_offsets_dev,
+                     const int32_t* box_offsets_dev, int n_images, int64_t n_pairs,
+                     int64_t* pairs_out_dev, float* probs_out_dev, int64_t* labels_out_dev,
+                     float* triple_out_dev, veto_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Test hooks (used by tests/ only): one GEMM  C[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual)
+ * through the SIMT or the tcgen05 kernel, fp32 in / fp32 out. scratch_dev: >= 4*(M*K + N*K) bytes. */
+int veto_test_gemm(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,
+                   float* c_dev, int M, int N, int K, int act, int precision,
+                   void* scratch_dev, size_t scratch_bytes, veto_stream_t stream);
+int veto_test_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
+                        int64_t rows, veto_stream_t stream);
+int veto_test_attention(const float* qkv_dev, float* out_dev, int64_t n_seq, veto_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VETO_B200_H */

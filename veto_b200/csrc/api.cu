@@ -1,0 +1,411 @@
+// C ABI of libveto_b200.so: error plumbing, weight packing, workspace planning and the orchestration of
+// VETOPredictor.forward / Ensemble.forward (roi_relation_predictors.py:4074-4139, 3752-3853) over the
+// stage kernels.  Declarations: include/veto_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "stages.cuh"
+
+namespace veto {
+
+static thread_local char g_err[768] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("%s: %s (%s) at %s:%d", what, cudaGetErrorString(e), cudaGetErrorName(e), file, line);
+    return VETO_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+namespace {
+
+constexpr size_t kAlign = 256;
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off += (bytes + kAlign - 1) / kAlign * kAlign;
+        return o;
+    }
+};
+
+int check_config(const veto_config* c) {
+    VETO_REQUIRE(c != nullptr, VETO_ERR_ARG, "veto_config is NULL");
+    VETO_REQUIRE(c->dim == kDim && c->heads == kHeads && c->mlp_dim == kMlp && c->channels == kChannels &&
+                     c->pool == kPool && c->patch == 2,
+                 VETO_ERR_UNSUPPORTED,
+                 "unsupported architecture (dim %d heads %d mlp %d channels %d pool %d patch %d): this library is built "
+                 "for configs/VETO_final.yaml (576/6/1152/256/8/2)",
+                 c->dim, c->heads, c->mlp_dim, c->channels, c->pool, c->patch);
+    VETO_REQUIRE(c->layers >= 1 && c->layers <= VETO_MAX_LAYERS, VETO_ERR_UNSUPPORTED, "layers=%d outside 1..%d", c->layers,
+                 VETO_MAX_LAYERS);
+    VETO_REQUIRE(c->num_obj >= 2 && c->num_obj <= 512 && c->num_out >= 1, VETO_ERR_ARG, "bad num_obj=%d / num_out=%d",
+                 c->num_obj, c->num_out);
+    VETO_REQUIRE(c->precision >= VETO_PREC_FP32 && c->precision <= VETO_PREC_BF16, VETO_ERR_ARG, "bad precision %d",
+                 c->precision);
+    return VETO_OK;
+}
+
+struct PackedLayout {
+    size_t w_loc2, b_loc2, w_cls2, b_cls2, w_d2, b_d2, w_v2, b_v2, clspos;
+    size_t d2_hi, d2_lo, v2_hi, v2_lo;
+    size_t qkv_hi[VETO_MAX_LAYERS], qkv_lo[VETO_MAX_LAYERS], out_hi[VETO_MAX_LAYERS], out_lo[VETO_MAX_LAYERS];
+    size_t ff1_hi[VETO_MAX_LAYERS], ff1_lo[VETO_MAX_LAYERS], ff2_hi[VETO_MAX_LAYERS], ff2_lo[VETO_MAX_LAYERS];
+    size_t total;
+};
+
+PackedLayout packed_layout(const veto_config& c) {
+    PackedLayout L{};
+    Carver k;
+    L.w_loc2 = k.take(sizeof(float) * 2 * kDim * kPosDim);
+    L.b_loc2 = k.take(sizeof(float) * 2 * kDim);
+    L.w_cls2 = k.take(sizeof(float) * 2 * kDim * kEmbDim);
+    L.b_cls2 = k.take(sizeof(float) * 2 * kDim);
+    L.w_d2 = k.take(sizeof(float) * 2 * kDimDepth * kPatchVec);
+    L.b_d2 = k.take(sizeof(float) * 2 * kDimDepth);
+    L.w_v2 = k.take(sizeof(float) * 2 * kDimRgb * kPatchVec);
+    L.b_v2 = k.take(sizeof(float) * 2 * kDimRgb);
+    L.clspos = k.take(sizeof(float) * kDim);
+    if (c.precision != VETO_PREC_FP32) {
+        const bool lo = c.precision == VETO_PREC_BF16X3;
+        const size_t e = sizeof(__nv_bfloat16);
+        L.d2_hi = k.take(e * 2 * kDimDepth * kPatchVec);
+        L.d2_lo = lo ? k.take(e * 2 * kDimDepth * kPatchVec) : 0;
+        L.v2_hi = k.take(e * 2 * kDimRgb * kPatchVec);
+        L.v2_lo = lo ? k.take(e * 2 * kDimRgb * kPatchVec) : 0;
+        for (int l = 0; l < c.layers; ++l) {
+            L.qkv_hi[l] = k.take(e * 3 * kDim * kDim);
+            L.qkv_lo[l] = lo ? k.take(e * 3 * kDim * kDim) : 0;
+            L.out_hi[l] = k.take(e * kDim * kDim);
+            L.out_lo[l] = lo ? k.take(e * kDim * kDim) : 0;
+            L.ff1_hi[l] = k.take(e * kMlp * kDim);
+            L.ff1_lo[l] = lo ? k.take(e * kMlp * kDim) : 0;
+            L.ff2_hi[l] = k.take(e * kDim * kMlp);
+            L.ff2_lo[l] = lo ? k.take(e * kDim * kMlp) : 0;
+        }
+    }
+    L.total = k.off;
+    return L;
+}
+
+// an activation buffer in the storage format of the precision mode
+struct ActBuf {
+    float* f32 = nullptr;
+    __nv_bfloat16* hi = nullptr;
+    __nv_bfloat16* lo = nullptr;
+    ActOut out() const { return ActOut{f32, hi, lo}; }
+};
+
+struct WorkLayout {
+    size_t pos, emb, lso, cso, pa_d, pa_v, so_d, so_v;  // box level
+    size_t x, xn, qkv, h;                               // chunk level
+    size_t total;
+    int32_t chunk;
+};
+
+size_t act_bytes(int precision, size_t elems) {
+    if (precision == VETO_PREC_FP32) return elems * sizeof(float);
+    if (precision == VETO_PREC_BF16X3) return elems * 2 * sizeof(__nv_bfloat16);
+    return elems * sizeof(__nv_bfloat16);
+}
+
+constexpr int32_t kDefaultChunk = 512;
+
+WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
+    WorkLayout W{};
+    Carver k;
+    int32_t chunk = chunk_pairs > 0 ? chunk_pairs : kDefaultChunk;
+    if (n_pairs > 0 && chunk > n_pairs) chunk = (int32_t)n_pairs;
+    if (chunk < 1) chunk = 1;
+    W.chunk = chunk;
+    const size_t N = (size_t)(n_boxes > 0 ? n_boxes : 1);
+    W.pos = k.take(sizeof(float) * N * kPosDim);
+    W.emb = k.take(sizeof(float) * N * kEmbDim);
+    W.lso = k.take(sizeof(float) * N * 2 * kDim);
+    W.cso = k.take(sizeof(float) * N * 2 * kDim);
+    W.pa_d = k.take(act_bytes(c.precision, N * kPatches * kPatchVec));
+    W.pa_v = k.take(act_bytes(c.precision, N * kPatches * kPatchVec));
+    W.so_d = k.take(sizeof(float) * N * kPatches * 2 * kDimDepth);
+    W.so_v = k.take(sizeof(float) * N * kPatches * 2 * kDimRgb);
+    const size_t M = (size_t)chunk * kTokens;
+    W.x = k.take(sizeof(float) * M * kDim);
+    W.xn = k.take(act_bytes(c.precision, M * kDim));
+    W.qkv = k.take(sizeof(float) * M * 3 * kDim);
+    W.h = k.take(act_bytes(c.precision, M * kMlp));
+    W.total = k.off;
+    return W;
+}
+
+ActBuf act_at(void* base, size_t off, int precision, size_t elems) {
+    ActBuf b;
+    char* p = (char*)base + off;
+    if (precision == VETO_PREC_FP32) b.f32 = (float*)p;
+    else {
+        b.hi = (__nv_bfloat16*)p;
+        if (precision == VETO_PREC_BF16X3) b.lo = b.hi + elems;
+    }
+    return b;
+}
+
+struct WRef {  // a Linear weight in the forms the two GEMM paths need
+    const float* f32;
+    const __nv_bfloat16* hi;
+    const __nv_bfloat16* lo;
+};
+
+int linear(int precision, const ActBuf& a, int lda, const WRef& w, int M, int N, int K, const GemmEpilogue& ep,
+           cudaStream_t s) {
+    if (precision == VETO_PREC_FP32) return gemm_simt(a.f32, lda, w.f32, M, N, K, ep, s);
+    VETO_REQUIRE(lda == K, VETO_ERR_ARG, "tensor-core GEMM needs a dense A (lda == K)");
+    GemmOperand A, W;
+    A.hi = a.hi; A.lo = a.lo;
+    W.hi = w.hi; W.lo = w.lo;
+    return gemm_tc(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+}
+
+const __nv_bfloat16* bf(const void* base, size_t off) { return off ? (const __nv_bfloat16*)((const char*)base + off) : nullptr; }
+
+}  // namespace
+}  // namespace veto
+
+using namespace veto;
+
+extern "C" int veto_abi_version(void) { return VETO_ABI_VERSION; }
+extern "C" const char* veto_last_error(void) { return g_err; }
+extern "C" int64_t veto_last_launch_count(void) { return g_launches; }
+
+extern "C" int veto_device_check(void) {
+    int dev = 0, major = 0, minor = 0;
+    VETO_CUDA(cudaGetDevice(&dev));
+    VETO_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    VETO_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    VETO_REQUIRE(major == 10 && minor == 0, VETO_ERR_UNSUPPORTED,
+                 "libveto_b200 is built for sm_100a only; the current device is sm_%d%d", major, minor);
+    return VETO_OK;
+}
+
+extern "C" size_t veto_packed_bytes(const veto_config* cfg) {
+    if (check_config(cfg)) return 0;
+    return packed_layout(*cfg).total;
+}
+
+extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, void* packed_dev, size_t packed_bytes,
+                                 veto_stream_t stream) {
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    VETO_REQUIRE(w && packed_dev, VETO_ERR_ARG, "veto_pack_weights: NULL argument");
+    const PackedLayout L = packed_layout(*cfg);
+    VETO_REQUIRE(packed_bytes >= L.total, VETO_ERR_WORKSPACE, "veto_pack_weights: packed buffer %zu < %zu bytes", packed_bytes,
+                 L.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    char* P = (char*)packed_dev;
+    if ((rc = pack_halves(w->loc_proj_w, (float*)(P + L.w_loc2), kDim, kPosDim, s))) return rc;
+    if ((rc = pack_bias2(w->loc_proj_b, (float*)(P + L.b_loc2), kDim, s))) return rc;
+    if ((rc = pack_halves(w->class_proj_w, (float*)(P + L.w_cls2), kDim, kEmbDim, s))) return rc;
+    if ((rc = pack_bias2(w->class_proj_b, (float*)(P + L.b_cls2), kDim, s))) return rc;
+    if ((rc = pack_patch(w->proj_d_w, (float*)(P + L.w_d2), kDimDepth, s))) return rc;
+    if ((rc = pack_bias2(w->proj_d_b, (float*)(P + L.b_d2), kDimDepth, s))) return rc;
+    if ((rc = pack_patch(w->proj_v_w, (float*)(P + L.w_v2), kDimRgb, s))) return rc;
+    if ((rc = pack_bias2(w->proj_v_b, (float*)(P + L.b_v2), kDimRgb, s))) return rc;
+    if ((rc = pack_add(w->cls_token, w->pos_embedding, (float*)(P + L.clspos), kDim, s))) return rc;
+    if (cfg->precision != VETO_PREC_FP32) {
+        auto split = [&](const float* src, size_t hi, size_t lo, size_t n) {
+            return pack_split_bf16(src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n, s);
+        };
+        if ((rc = split((const float*)(P + L.w_d2), L.d2_hi, L.d2_lo, (size_t)2 * kDimDepth * kPatchVec))) return rc;
+        if ((rc = split((const float*)(P + L.w_v2), L.v2_hi, L.v2_lo, (size_t)2 * kDimRgb * kPatchVec))) return rc;
+        for (int l = 0; l < cfg->layers; ++l) {
+            VETO_REQUIRE(w->qkv_w[l] && w->out_w[l] && w->ff1_w[l] && w->ff2_w[l], VETO_ERR_ARG, "layer %d weights missing", l);
+            if ((rc = split(w->qkv_w[l], L.qkv_hi[l], L.qkv_lo[l], (size_t)3 * kDim * kDim))) return rc;
+            if ((rc = split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim))) return rc;
+            if ((rc = split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim))) return rc;
+            if ((rc = split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp))) return rc;
+        }
+    }
+    return VETO_OK;
+}
+
+extern "C" size_t veto_workspace_bytes(const veto_config* cfg, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
+    if (check_config(cfg)) return 0;
+    return work_layout(*cfg, n_boxes, n_pairs, chunk_pairs).total;
+}
+
+extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights* w, const void* packed_dev,
+                                     const veto_inputs* in, const veto_outputs* out, void* workspace_dev,
+                                     size_t workspace_bytes, int32_t chunk_pairs, veto_stream_t stream) {
+    g_launches = 0;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    VETO_REQUIRE(w && packed_dev && in && out && workspace_dev, VETO_ERR_ARG, "veto_relation_forward: NULL argument");
+    VETO_REQUIRE(in->n_boxes >= 0 && in->n_pairs >= 0, VETO_ERR_ARG, "veto_relation_forward: negative sizes");
+    if (in->n_pairs == 0 || in->n_boxes == 0) return VETO_OK;
+    VETO_REQUIRE(in->boxes && in->roi_rgb && in->roi_depth && in->subj && in->obj && (in->labels || in->obj_logits),
+                 VETO_ERR_ARG, "veto_relation_forward: missing input pointer");
+    VETO_REQUIRE(out->rel_logits, VETO_ERR_ARG, "veto_relation_forward: rel_logits output missing");
+    VETO_REQUIRE(!in->freq_bias || in->labels, VETO_ERR_ARG, "frequency bias needs hard labels");
+    const int prec = cfg->precision;
+    const PackedLayout L = packed_layout(*cfg);
+    const WorkLayout W = work_layout(*cfg, in->n_boxes, in->n_pairs, chunk_pairs);
+    VETO_REQUIRE(workspace_bytes >= W.total, VETO_ERR_WORKSPACE, "veto_relation_forward: workspace %zu < %zu bytes",
+                 workspace_bytes, W.total);
+    VETO_REQUIRE(W.chunk <= 65536, VETO_ERR_UNSUPPORTED, "chunk_pairs=%d > 65536", W.chunk);
+    cudaStream_t s = (cudaStream_t)stream;
+    const char* P = (const char*)packed_dev;
+    char* B = (char*)workspace_dev;
+    const int N = in->n_boxes;
+
+    // ---------------- box stage: everything that depends on one box only ----------------
+    float* pos = (float*)(B + W.pos);
+    float* emb = (float*)(B + W.emb);
+    float* lso = (float*)(B + W.lso);
+    float* cso = (float*)(B + W.cso);
+    float* so_d = (float*)(B + W.so_d);
+    float* so_v = (float*)(B + W.so_v);
+    if ((rc = box_embed(in->boxes, in->labels, in->obj_logits, cfg->num_obj, N, *w, pos, emb, s))) return rc;
+    {
+        GemmEpilogue ep;
+        ep.bias = (const float*)(P + L.b_loc2);
+        ep.out.f32 = lso;
+        ep.ldc = 2 * kDim;
+        if ((rc = gemm_simt(pos, kPosDim, (const float*)(P + L.w_loc2), N, 2 * kDim, kPosDim, ep, s))) return rc;
+        ep.bias = (const float*)(P + L.b_cls2);
+        ep.out.f32 = cso;
+        if ((rc = gemm_simt(emb, kEmbDim, (const float*)(P + L.w_cls2), N, 2 * kDim, kEmbDim, ep, s))) return rc;
+    }
+    {
+        const size_t pe = (size_t)N * kPatches * kPatchVec;
+        ActBuf pa_d = act_at(B, W.pa_d, prec, pe), pa_v = act_at(B, W.pa_v, prec, pe);
+        if ((rc = patchify(in->roi_depth, N, pa_d.out(), s))) return rc;
+        if ((rc = patchify(in->roi_rgb, N, pa_v.out(), s))) return rc;
+        GemmEpilogue ep;
+        ep.bias = (const float*)(P + L.b_d2);
+        ep.out.f32 = so_d;
+        ep.ldc = 2 * kDimDepth;
+        WRef wd{(const float*)(P + L.w_d2), bf(P, L.d2_hi), bf(P, L.d2_lo)};
+        if ((rc = linear(prec, pa_d, kPatchVec, wd, N * kPatches, 2 * kDimDepth, kPatchVec, ep, s))) return rc;
+        ep.bias = (const float*)(P + L.b_v2);
+        ep.out.f32 = so_v;
+        ep.ldc = 2 * kDimRgb;
+        WRef wv{(const float*)(P + L.w_v2), bf(P, L.v2_hi), bf(P, L.v2_lo)};
+        if ((rc = linear(prec, pa_v, kPatchVec, wv, N * kPatches, 2 * kDimRgb, kPatchVec, ep, s))) return rc;
+    }
+
+    // ---------------- pair stage, chunk by chunk ----------------
+    TokenSources ts{so_d, so_v, lso, cso, (const float*)(P + L.clspos), w->pos_embedding};
+    float* x = (float*)(B + W.x);
+    float* qkv = (float*)(B + W.qkv);
+    for (int64_t r0 = 0; r0 < in->n_pairs; r0 += W.chunk) {
+        const int64_t rc_pairs = (in->n_pairs - r0 < W.chunk) ? (in->n_pairs - r0) : W.chunk;
+        const int M = (int)(rc_pairs * kTokens);
+        ActBuf xn = act_at(B, W.xn, prec, (size_t)M * kDim);
+        ActBuf hb = act_at(B, W.h, prec, (size_t)M * kMlp);
+        if ((rc = build_tokens(ts, in->subj + r0, in->obj + r0, rc_pairs, x, s))) return rc;
+        if (out->tokens)
+            VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
+                                      cudaMemcpyDeviceToDevice, s));
+        for (int l = 0; l < cfg->layers; ++l) {
+            // x = to_out(softmax(q k^T * scale) v) + x      (PreNorm + Attention, model_veto.py:18-19,86-96)
+            if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
+            GemmEpilogue e1;
+            e1.out.f32 = qkv;
+            e1.ldc = 3 * kDim;
+            WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+            if ((rc = linear(prec, xn, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
+            if ((rc = attention_seq(qkv, rc_pairs, xn.out(), s))) return rc;
+            GemmEpilogue e2;
+            e2.bias = w->out_b[l];
+            e2.residual = x;
+            e2.out.f32 = x;
+            e2.ldc = kDim;
+            WRef wo{w->out_w[l], bf(P, L.out_hi[l]), bf(P, L.out_lo[l])};
+            if ((rc = linear(prec, xn, kDim, wo, M, kDim, kDim, e2, s))) return rc;
+            // x = W2 gelu(W1 LN(x) + b1) + b2 + x           (PreNorm + FeedForward, model_veto.py:20,134-146)
+            if ((rc = layernorm_rows(x, kDim, w->ln2_w[l], w->ln2_b[l], M, xn.out(), s))) return rc;
+            GemmEpilogue e3;
+            e3.bias = w->ff1_b[l];
+            e3.act = ACT_GELU;
+            e3.out = hb.out();
+            e3.ldc = kMlp;
+            WRef w1{w->ff1_w[l], bf(P, L.ff1_hi[l]), bf(P, L.ff1_lo[l])};
+            if ((rc = linear(prec, xn, kDim, w1, M, kMlp, kDim, e3, s))) return rc;
+            GemmEpilogue e4;
+            e4.bias = w->ff2_b[l];
+            e4.residual = x;
+            e4.out.f32 = x;
+            e4.ldc = kDim;
+            WRef w2{w->ff2_w[l], bf(P, L.ff2_hi[l]), bf(P, L.ff2_lo[l])};
+            if ((rc = linear(prec, hb, kMlp, w2, M, kDim, kMlp, e4, s))) return rc;
+        }
+        // rel_out on the CLS row x[:,0] (model_veto.py:25; roi_relation_predictors.py:4125): always fp32 FMA
+        GemmEpilogue ec;
+        ec.bias = w->rel_out_b;
+        ec.out.f32 = out->rel_logits + (size_t)r0 * cfg->num_out;
+        ec.ldc = cfg->num_out;
+        if ((rc = gemm_simt(x, kTokens * kDim, w->rel_out_w, (int)rc_pairs, cfg->num_out, kDim, ec, s))) return rc;
+        if (out->rel_features)
+            VETO_CUDA(cudaMemcpy2DAsync(out->rel_features + (size_t)r0 * kDim, sizeof(float) * kDim, x,
+                                        sizeof(float) * kTokens * kDim, sizeof(float) * kDim, (size_t)rc_pairs,
+                                        cudaMemcpyDeviceToDevice, s));
+    }
+    if (in->freq_bias)
+        if ((rc = add_freq_bias(out->rel_logits, cfg->num_out, in->freq_bias, in->labels, cfg->num_obj, in->subj, in->obj,
+                                in->n_pairs, s)))
+            return rc;
+    return VETO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+extern "C" int veto_test_gemm(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,
+                              float* c_dev, int M, int N, int K, int act, int precision, void* scratch_dev,
+                              size_t scratch_bytes, veto_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmEpilogue ep;
+    ep.bias = bias_dev;
+    ep.residual = residual_dev;
+    ep.act = act;
+    ep.out.f32 = c_dev;
+    ep.ldc = N;
+    if (precision == VETO_PREC_FP32) return gemm_simt(a_dev, K, w_dev, M, N, K, ep, s);
+    const size_t ae = (size_t)M * K, we = (size_t)N * K;
+    VETO_REQUIRE(scratch_dev && scratch_bytes >= 4 * (ae + we), VETO_ERR_WORKSPACE, "veto_test_gemm: scratch too small");
+    __nv_bfloat16* a_hi = (__nv_bfloat16*)scratch_dev;
+    __nv_bfloat16* a_lo = a_hi + ae;
+    __nv_bfloat16* w_hi = a_lo + ae;
+    __nv_bfloat16* w_lo = w_hi + we;
+    int rc;
+    if ((rc = pack_split_bf16(a_dev, a_hi, a_lo, ae, s))) return rc;
+    if ((rc = pack_split_bf16(w_dev, w_hi, w_lo, we, s))) return rc;
+    GemmOperand A, W;
+    A.hi = a_hi; A.lo = a_lo;
+    W.hi = w_hi; W.lo = w_lo;
+    return gemm_tc(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+}
+
+extern "C" int veto_test_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev, int64_t rows,
+                                   veto_stream_t stream) {
+    ActOut o;
+    o.f32 = y_dev;
+    return layernorm_rows(x_dev, kDim, w_dev, b_dev, rows, o, (cudaStream_t)stream);
+}
+
+extern "C" int veto_test_attention(const float* qkv_dev, float* out_dev, int64_t n_seq, veto_stream_t stream) {
+    ActOut o;
+    o.f32 = out_dev;
+    return attention_seq(qkv_dev, n_seq, o, (cudaStream_t)stream);
+}

@@ -1,0 +1,114 @@
+// Shared declarations of libveto_b200.so (internal; the public surface is include/veto_b200.h).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/veto_b200.h"
+
+namespace veto {
+
+// ---- architecture constants of configs/VETO_final.yaml (validated against veto_config) ----
+constexpr int kDim = 576;        // T_INPUT_DIM
+constexpr int kHeads = 6;        // NHEADS
+constexpr int kHeadDim = 96;     // 576 / 6 (model_veto.py:70)
+constexpr int kMlp = 1152;       // mlp_dim = 2 * dim (model_veto.py:35)
+constexpr int kTokens = 19;      // 1 cls + 16 patches + location + class (model_veto.py:52-61)
+constexpr int kPatches = 16;     // (8/2)^2
+constexpr int kChannels = 256;   // ROI feature channels
+constexpr int kPool = 8;
+constexpr int kPatchVec = 1024;  // p1*p2*c for ONE box (the reference's 2048 = subject + object halves)
+constexpr int kDimDepth = 512;   // proj_d out (model_veto.py:105)
+constexpr int kDimRgb = 64;      // proj_v out (model_veto.py:106)
+constexpr int kPosDim = 128;     // pos_embed out (roi_relation_predictors.py:4042-4047)
+constexpr int kEmbDim = 200;     // obj_embed dim
+
+// ---- error plumbing ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define VETO_CUDA(expr)                                                               \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) return ::veto::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define VETO_LAUNCH_CHECK()                                                                  \
+    do {                                                                                     \
+        ::veto::count_launch();                                                              \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) return ::veto::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define VETO_REQUIRE(cond, code, ...)   \
+    do {                                \
+        if (!(cond)) {                  \
+            ::veto::set_error(__VA_ARGS__); \
+            return (code);              \
+        }                               \
+    } while (0)
+
+// ---- activation storage formats between kernels ----
+// F32     : one fp32 array
+// BF16    : one bf16 array
+// BF16X2  : bf16 hi array followed (at `lo`) by a bf16 lo array, value ~= hi + lo (16 mantissa bits)
+struct ActOut {
+    float* f32 = nullptr;
+    __nv_bfloat16* hi = nullptr;
+    __nv_bfloat16* lo = nullptr;
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(__nv_bfloat16 a, __nv_bfloat16 b, __nv_bfloat16 c, __nv_bfloat16 d) {
+    uint2 r;
+    r.x = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+    r.y = (uint32_t)__bfloat16_as_ushort(c) | ((uint32_t)__bfloat16_as_ushort(d) << 16);
+    return r;
+}
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // nn.GELU() exact (model_veto.py:139)
+    return v;
+}
+
+struct GemmEpilogue {
+    const float* bias = nullptr;      // [N]
+    const float* residual = nullptr;  // [M, ldc] fp32 (may alias out.f32)
+    int act = ACT_NONE;
+    ActOut out;                       // any subset of f32 / hi / lo; row stride ldc
+    int ldc = 0;
+};
+
+// A operand of a GEMM: fp32 (SIMT path) or bf16 hi[/lo] (tensor-core path); W likewise.
+struct GemmOperand {
+    const float* f32 = nullptr;
+    const __nv_bfloat16* hi = nullptr;
+    const __nv_bfloat16* lo = nullptr;
+};
+
+// C[M,N] = epi(A[M,K] @ W[N,K]^T).  A row stride lda (elements), W row stride K.
+int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s);
+// passes = 1 (bf16) or 3 (bf16x3: hi*hi + lo*hi + hi*lo). Requires K % 64 == 0, N % 16 == 0, lda == K.
+int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
+            const GemmEpilogue& ep, cudaStream_t s);
+int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
+
+// LayerNorm over rows of kDim (eps 1e-5, model_veto.py:128) -> out format(s)
+int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, int64_t rows, const ActOut& out,
+                   cudaStream_t s);
+// softmax(q k^T * 96^-0.5) v per (sequence, head); qkv fp32 [n_seq*19, 1728] -> out [n_seq*19, 576]
+int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
+
+int num_sms();
+
+}  // namespace veto

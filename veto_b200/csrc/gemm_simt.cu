@@ -1,0 +1,166 @@
+// fp32 SIMT GEMM:  C[M,N] = epilogue( A[M,K] @ W[N,K]^T ), every product an fp32 FMA.
+//
+// This is the reference-precision path (the reference runs DTYPE "float32", VETO_final.yaml:1) and the
+// GEMM used for the small box-level projections and the predicate classifier in every precision mode,
+// so that logits / argmax do not depend on tensor-core rounding.  128x128x16 tiles, 256 threads, 8x8
+// register micro-tiles, register-prefetched double buffering.
+#include "common.cuh"
+
+namespace veto {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int PAD = 4;
+
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int N, int K,
+                 const float* __restrict__ bias, const float* residual, int act, float* out_f32,
+                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    // global -> register staging: each thread moves two float4 of A and two of W per K step
+    const int lrow = tid >> 2;        // 0..63 (+64)
+    const int lk = (tid & 3) * 4;     // 0,4,8,12
+    const bool vec_ok = ((lda & 3) == 0) && ((K & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)W) & 15) == 0);
+
+    float4 ra[2], rb[2];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = m0 + lrow + h * 64;
+            const int k = k0 + lk;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < M) {
+                const float* p = A + (size_t)r * lda + k;
+                if (vec_ok && k + 3 < K) v = __ldg((const float4*)p);
+                else {
+                    if (k < K) v.x = __ldg(p);
+                    if (k + 1 < K) v.y = __ldg(p + 1);
+                    if (k + 2 < K) v.z = __ldg(p + 2);
+                    if (k + 3 < K) v.w = __ldg(p + 3);
+                }
+            }
+            ra[h] = v;
+            const int c = n0 + lrow + h * 64;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < N) {
+                const float* p = W + (size_t)c * K + k;
+                if (vec_ok && k + 3 < K) w = __ldg((const float4*)p);
+                else {
+                    if (k < K) w.x = __ldg(p);
+                    if (k + 1 < K) w.y = __ldg(p + 1);
+                    if (k + 2 < K) w.z = __ldg(p + 2);
+                    if (k + 3 < K) w.w = __ldg(p + 3);
+                }
+            }
+            rb[h] = w;
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lrow + h * 64;
+            As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y;
+            As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+            Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y;
+            Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int nk = (K + BK - 1) / BK;
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *(const float4*)&As[buf][k][ty * 4];
+            const float4 a1 = *(const float4*)&As[buf][k][64 + ty * 4];
+            const float4 b0 = *(const float4*)&Bs[buf][k][tx * 4];
+            const float4 b1 = *(const float4*)&Bs[buf][k][64 + tx * 4];
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store_tile(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    const bool vec_out = ((N & 3) == 0) && ((ldc & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = n0 + h * 64 + tx * 4;
+            if (c >= N) continue;
+            float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+            const size_t off = (size_t)r * ldc + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c + j < N) {
+                    if (bias) v[j] += __ldg(bias + c + j);
+                    v[j] = apply_act(v[j], act);
+                    if (residual) v[j] += residual[off + j];
+                }
+            }
+            if (vec_out && c + 3 < N) {
+                if (out_f32) *(float4*)(out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+                if (out_hi) {
+                    __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_bf16(v[j], hh[j], ll[j]);
+                    *(uint2*)(out_hi + off) = pack_bf16x4(hh[0], hh[1], hh[2], hh[3]);
+                    if (out_lo) *(uint2*)(out_lo + off) = pack_bf16x4(ll[0], ll[1], ll[2], ll[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c + j < N) {
+                        if (out_f32) out_f32[off + j] = v[j];
+                        if (out_hi) {
+                            __nv_bfloat16 hh, ll;
+                            split_bf16(v[j], hh, ll);
+                            out_hi[off + j] = hh;
+                            if (out_lo) out_lo[off + j] = ll;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return VETO_OK;
+    VETO_REQUIRE(K > 0 && A && W, VETO_ERR_ARG, "gemm_simt: bad operands");
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "gemm_simt: M=%d too large for one launch", M);
+    gemm_simt_kernel<<<grid, 256, 0, s>>>(A, lda, W, M, N, K, ep.bias, ep.residual, ep.act, ep.out.f32, ep.out.hi,
+                                          ep.out.lo, ep.ldc);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+}  // namespace veto

@@ -1,0 +1,421 @@
+// Token-wise GEMM of the relation encoder on the 5th-generation tensor cores (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] @ W[N,K]^T )       A, W bf16 (K-major), accumulate fp32 in TMEM
+//
+// This is the B200 replacement of the cuBLAS SGEMMs behind every nn.Linear of the reference
+// encoder (model_veto.py:70-96 to_qkv / to_out, :134-146 FeedForward, :105-106 patch projections).
+//
+// Layout: persistent CTAs (one per SM) walk 128 x BLOCK_N output tiles; warp 0 is the TMA producer
+// (cp.async.bulk.tensor, 128-byte swizzle, a 5-6 stage mbarrier ring), warp 1 issues tcgen05.mma
+// (M=128, N=BLOCK_N, K=16 per instruction) into one of two TMEM accumulator stages, warps 4-7 drain
+// the other stage with tcgen05.ld and apply bias / GELU / residual before storing.  With passes == 3
+// the K loop runs three times over (A_hi,W_hi), (A_lo,W_hi), (A_hi,W_lo): the bf16x3 split that gives
+// fp32-grade products on the bf16 pipe (every fp32 operand = hi + lo with 16 mantissa bits kept).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace veto {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B: one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 4;
+
+template <int BLOCK_N>
+struct TileCfg {
+    static constexpr int kBytesA = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBytesB = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStageBytes = kBytesA + kBytesB;
+    static constexpr int kStages = (BLOCK_N > 128) ? 5 : 6;
+    static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("veto gemm_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows
+// of 128 B) >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10), both K-major,
+// N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct EpiParams {
+    const float* bias;
+    const float* residual;
+    float* out_f32;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    int act;
+    int ldc;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+               int M, int N, int K, int passes, EpiParams ep) {
+    using C = TileCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::kStages * C::kBytesA;
+    uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + C::kStages;      // [kStages]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * C::kStages;  // [2]        MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]        epilogue -> MMA
+    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int kb_per_pass = K / BLOCK_K;
+    const int num_kb = kb_per_pass * passes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_w_hi);
+        if (passes > 1) {
+            tma_prefetch_desc(&tm_a_lo);
+            tma_prefetch_desc(&tm_w_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_base_slot, C::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BLOCK_M;
+                const int n0 = (tile % num_n) * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int pass = kb / kb_per_pass;
+                    const int k0 = (kb - pass * kb_per_pass) * BLOCK_K;
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    tma_load_2d(smem_a + stage * C::kBytesA, (pass == 1) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], k0, m0);
+                    tma_load_2d(smem_b + stage * C::kBytesB, (pass == 2) ? &tm_w_lo : &tm_w_hi, &full_bar[stage], k0, n0);
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * C::kBytesA);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * C::kBytesB);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
+                        const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
+                        umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+                    if (++stage == C::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / num_n) * BLOCK_M;
+            const int n0 = (tile % num_n) * BLOCK_N;
+            const int row = m0 + ew * 32 + lane;
+            mbar_wait(&tmem_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row < M && col0 < N) {
+                    const size_t off = (size_t)row * ep.ldc + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col0 + j < N) {  // N % 4 == 0 is enforced by the host
+                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            if (ep.bias) {
+                                const float4 b = __ldg((const float4*)(ep.bias + col0 + j));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            v.x = apply_act(v.x, ep.act); v.y = apply_act(v.y, ep.act);
+                            v.z = apply_act(v.z, ep.act); v.w = apply_act(v.w, ep.act);
+                            if (ep.residual) {
+                                const float4 q = *(const float4*)(ep.residual + off + j);
+                                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                            }
+                            if (ep.out_f32) *(float4*)(ep.out_f32 + off + j) = v;
+                            if (ep.out_hi) {
+                                __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                                split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+                                split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                                *(uint2*)(ep.out_hi + off + j) = pack_bf16x4(h0, h1, h2, h3);
+                                if (ep.out_lo) *(uint2*)(ep.out_lo + off + j) = pack_bf16x4(l0, l1, l2, l3);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_mu;
+bool g_inited = false;
+
+struct MapKey {
+    const void* p;
+    uint64_t rows, cols;
+    uint32_t box_rows;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ k.box_rows;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// bf16 row-major [rows, cols] -> tiled map with a {64, box_rows} box and 128-byte swizzle
+int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out) {
+    MapKey key{p, rows, cols, box_rows};
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+        *out = it->second;
+        return VETO_OK;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%llu,%llu] box %u at %p", (int)r, (unsigned long long)rows,
+                  (unsigned long long)cols, box_rows, (const void*)p);
+        return VETO_ERR_CUDA;
+    }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return VETO_OK;
+}
+
+template <int BLOCK_N>
+int launch(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+           cudaStream_t s) {
+    using C = TileCfg<BLOCK_N>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    int rc;
+    if ((rc = get_map(A.hi, M, K, BLOCK_M, &ta_hi))) return rc;
+    if ((rc = get_map(W.hi, N, K, BLOCK_N, &tw_hi))) return rc;
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (passes == 3) {
+        if ((rc = get_map(A.lo, M, K, BLOCK_M, &ta_lo))) return rc;
+        if ((rc = get_map(W.lo, N, K, BLOCK_N, &tw_lo))) return rc;
+    }
+    const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc};
+    gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return VETO_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
+                 "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<192>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
+    g_inited = true;
+    return VETO_OK;
+}
+
+int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+            cudaStream_t s) {
+    if (M <= 0 || N <= 0) return VETO_OK;
+    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tc: passes must be 1 or 3");
+    VETO_REQUIRE(K % BLOCK_K == 0 && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a positive multiple of %d", K, BLOCK_K);
+    VETO_REQUIRE(N % 4 == 0 && ep.ldc % 4 == 0, VETO_ERR_UNSUPPORTED, "gemm_tc: N=%d and ldc=%d must be multiples of 4", N, ep.ldc);
+    VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)), VETO_ERR_ARG, "gemm_tc: missing bf16 operand");
+    int rc = gemm_tc_init();
+    if (rc) return rc;
+    if (N % 192 == 0) return launch<192>(A, W, M, N, K, passes, ep, s);
+    return launch<128>(A, W, M, N, K, passes, ep, s);
+}
+
+}  // namespace veto

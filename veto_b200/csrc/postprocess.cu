@@ -1,0 +1,134 @@
+// PostProcessor.forward, vanilla branch (relation_head/inference.py:398-453), one CTA per image:
+//   rel_class_prob = softmax(rel_logit);  rel_scores, rel_class = rel_class_prob[:,1:].max(1) (+1)
+//   triple = rel_scores * obj_scores[s] * obj_scores[o];  sort descending; reorder pairs / probs / labels.
+// The reference sort is unstable; ties are broken here by the original row (ascending).  Warp per row for
+// the softmax (lanes over predicate classes, shuffle reductions), bitonic sort of 64-bit keys in shared
+// memory, then a second warp-per-row pass that writes the probability rows in ranked order.
+#include "common.cuh"
+
+namespace veto {
+namespace {
+
+constexpr int kMaxRows = 16384;
+
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+postprocess_kernel(const float* __restrict__ logits, int num_rel, const int64_t* __restrict__ pairs,
+                   const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off,
+                   const int32_t* __restrict__ box_off, int64_t* __restrict__ pairs_out, float* __restrict__ probs_out,
+                   int64_t* __restrict__ labels_out, float* __restrict__ triple_out) {
+    extern __shared__ unsigned long long keys[];  // [npow]
+    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
+    float* trip = (float*)(lab + kMaxRows);
+    const int b = blockIdx.x;
+    const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
+    if (rows <= 0) return;
+    if (rows > kMaxRows) {  // documented limit of the in-shared-memory sort (include/veto_b200.h)
+        if (threadIdx.x == 0) printf("veto_postprocess: image %d has %d rows > %d\n", b, rows, kMaxRows);
+        __trap();
+    }
+    const int boff = box_off[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int npow = 1;
+    while (npow < rows) npow <<= 1;
+
+    for (int q = wid; q < rows; q += nw) {
+        const float* lg = logits + (size_t)(r0 + q) * num_rel;
+        float m = -INFINITY;
+        for (int c = lane; c < num_rel; c += 32) m = fmaxf(m, lg[c]);
+        m = wmax(m);
+        float sum = 0.f, best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int c = lane; c < num_rel; c += 32) {
+            const float e = expf(lg[c] - m);
+            sum += e;
+            if (c >= 1 && e > best) { best = e; besti = c; }
+        }
+        sum = wsum(sum);
+        // arg max over classes 1.. of e/sum (monotone in e); first index on ties
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) {
+            const float score = best / sum;
+            const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + q));
+            const float t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
+            unsigned int u = __float_as_uint(t);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
+            lab[q] = (unsigned short)besti;
+            trip[q] = t;
+        }
+    }
+    for (int q = rows + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int q = threadIdx.x; q < npow; q += blockDim.x) {
+                const int p = q ^ j;
+                if (p > q) {
+                    const unsigned long long a = keys[q], c = keys[p];
+                    const bool up = ((q & k) == 0);
+                    if ((a > c) == up) { keys[q] = c; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int rank = wid; rank < rows; rank += nw) {
+        const int q = (int)(keys[rank] & 0xffffffffull);
+        const float* lg = logits + (size_t)(r0 + q) * num_rel;
+        float m = -INFINITY;
+        for (int c = lane; c < num_rel; c += 32) m = fmaxf(m, lg[c]);
+        m = wmax(m);
+        float sum = 0.f;
+        for (int c = lane; c < num_rel; c += 32) sum += expf(lg[c] - m);
+        sum = wsum(sum);
+        float* po = probs_out + (size_t)(r0 + rank) * num_rel;
+        for (int c = lane; c < num_rel; c += 32) po[c] = expf(lg[c] - m) / sum;
+        if (lane == 0) {
+            *(longlong2*)(pairs_out + 2 * (size_t)(r0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + q));
+            labels_out[r0 + rank] = lab[q];
+            triple_out[r0 + rank] = trip[q];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace veto
+
+using namespace veto;
+
+extern "C" int veto_postprocess(const float* rel_logits_dev, int num_rel, const int64_t* pairs_dev,
+                                const float* obj_scores_dev, const int32_t* rel_offsets_dev, const int32_t* box_offsets_dev,
+                                int n_images, int64_t n_pairs, int64_t* pairs_out_dev, float* probs_out_dev,
+                                int64_t* labels_out_dev, float* triple_out_dev, veto_stream_t stream) {
+    if (n_images <= 0 || n_pairs <= 0) return VETO_OK;
+    VETO_REQUIRE(rel_logits_dev && pairs_dev && obj_scores_dev && rel_offsets_dev && box_offsets_dev && pairs_out_dev &&
+                     probs_out_dev && labels_out_dev && triple_out_dev && num_rel >= 2 && num_rel < 65536,
+                 VETO_ERR_ARG, "veto_postprocess: bad argument");
+    static bool attr_set = false;
+    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
+    if (!attr_set) {
+        VETO_CUDA(cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(rel_logits_dev, num_rel, pairs_dev, obj_scores_dev,
+                                                                      rel_offsets_dev, box_offsets_dev, pairs_out_dev,
+                                                                      probs_out_dev, labels_out_dev, triple_out_dev);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}

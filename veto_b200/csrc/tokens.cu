@@ -1,0 +1,96 @@
+// Relation-token construction: the [R,19,576] encoder input of Transformer.forward (model_veto.py:52-64)
+// from the box-level projections (box_stage.cu).  Per pair (s,o):
+//   row 0      cls_token + pos_embedding
+//   rows 1..16 cat(proj_d(depth patches), proj_v(rgb patches)) + pos_embedding, with
+//              proj(cat(s,o)) = S[s] + O[o]                      (model_veto.py:105-113, call order
+//                                                                 roi_relation_predictors.py:4124)
+//   row 17     ReLU(location_projection(cat(pos[s],pos[o]))) + pos_embedding   (:4118-4119)
+//   row 18     ReLU(class_projection(cat(emb[s],emb[o]))) + pos_embedding      (:4120-4121)
+// pos_embedding is one [1,1,576] vector added to every token (model_veto.py:62).  Pure gather + add:
+// 144 threads, thread t owns float4 column t of all 19 rows; loads and stores are 128-bit and coalesced.
+#include "stages.cuh"
+
+namespace veto {
+namespace {
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 relu4(float4 a) {
+    return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+
+constexpr int kTokThreads = kDim / 4;  // 144
+
+__global__ void __launch_bounds__(kTokThreads)
+tokens_kernel(TokenSources src, const int32_t* __restrict__ subj, const int32_t* __restrict__ obj, int64_t n_pairs,
+              float* __restrict__ x) {
+    const int t = threadIdx.x;
+    const float4 pos = __ldg((const float4*)src.pos + t);
+    const float4 clspos = __ldg((const float4*)src.clspos + t);
+    const bool depth_part = t < kDimDepth / 4;
+    for (int64_t r = blockIdx.x; r < n_pairs; r += gridDim.x) {
+        const int s = subj[r], o = obj[r];
+        float4* xr = (float4*)(x + (size_t)r * kTokens * kDim) + t;
+        xr[0] = clspos;
+        if (depth_part) {
+            const float4* ps = (const float4*)(src.so_d + (size_t)s * kPatches * 2 * kDimDepth) + t;
+            const float4* po = (const float4*)(src.so_d + (size_t)o * kPatches * 2 * kDimDepth + kDimDepth) + t;
+#pragma unroll 4
+            for (int p = 0; p < kPatches; ++p)
+                xr[(size_t)(1 + p) * kTokThreads] =
+                    add4(add4(__ldg(ps + (size_t)p * (2 * kDimDepth / 4)), __ldg(po + (size_t)p * (2 * kDimDepth / 4))), pos);
+        } else {
+            const int tv = t - kDimDepth / 4;
+            const float4* ps = (const float4*)(src.so_v + (size_t)s * kPatches * 2 * kDimRgb) + tv;
+            const float4* po = (const float4*)(src.so_v + (size_t)o * kPatches * 2 * kDimRgb + kDimRgb) + tv;
+#pragma unroll 4
+            for (int p = 0; p < kPatches; ++p)
+                xr[(size_t)(1 + p) * kTokThreads] =
+                    add4(add4(__ldg(ps + (size_t)p * (2 * kDimRgb / 4)), __ldg(po + (size_t)p * (2 * kDimRgb / 4))), pos);
+        }
+        const float4 ls = __ldg((const float4*)(src.lso + (size_t)s * 2 * kDim) + t);
+        const float4 lo = __ldg((const float4*)(src.lso + (size_t)o * 2 * kDim + kDim) + t);
+        xr[(size_t)17 * kTokThreads] = add4(relu4(add4(ls, lo)), pos);
+        const float4 cs = __ldg((const float4*)(src.cso + (size_t)s * 2 * kDim) + t);
+        const float4 co = __ldg((const float4*)(src.cso + (size_t)o * 2 * kDim + kDim) + t);
+        xr[(size_t)18 * kTokThreads] = add4(relu4(add4(cs, co)), pos);
+    }
+}
+
+// rel_dists += freq_bias.index_with_labels(stack(obj_pred[s], obj_pred[o])) (model_motifs.py:29-38;
+// roi_relation_predictors.py:1134-1135 in the heads that use it) — optional, OFF for VETO parity.
+__global__ void freq_bias_kernel(float* __restrict__ logits, int num_out, const float* __restrict__ table,
+                                 const int64_t* __restrict__ labels, int num_obj, const int32_t* __restrict__ subj,
+                                 const int32_t* __restrict__ obj, int64_t n_pairs) {
+    const int64_t total = n_pairs * num_out;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / num_out;
+        const int c = (int)(e - r * num_out);
+        const int64_t row = labels[subj[r]] * num_obj + labels[obj[r]];
+        logits[e] += __ldg(table + row * num_out + c);
+    }
+}
+
+}  // namespace
+
+int build_tokens(const TokenSources& src, const int32_t* subj, const int32_t* obj, int64_t n_pairs, float* x,
+                 cudaStream_t s) {
+    if (n_pairs <= 0) return VETO_OK;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const int grid = (int)(n_pairs < cap ? n_pairs : cap);
+    tokens_kernel<<<grid, kTokThreads, 0, s>>>(src, subj, obj, n_pairs, x);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int add_freq_bias(float* logits, int num_out, const float* table, const int64_t* labels, int num_obj,
+                  const int32_t* subj, const int32_t* obj, int64_t n_pairs, cudaStream_t s) {
+    if (n_pairs <= 0) return VETO_OK;
+    const int64_t blocks = (n_pairs * num_out + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    freq_bias_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(logits, num_out, table, labels, num_obj, subj, obj,
+                                                                         n_pairs);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+}  // namespace veto

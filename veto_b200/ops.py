@@ -1,0 +1,345 @@
+"""Functional wrappers over the C ABI (include/veto_b200.h).  Inputs and outputs are CUDA tensors; the
+work is done by libveto_b200.so on the current stream.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+T_DIM, N_TOKENS = 576, 19
+
+
+def _i32(seq: Sequence[int]):
+    return (ctypes.c_int32 * len(seq))(*[int(v) for v in seq])
+
+
+def offsets_tensor(counts: Sequence[int], device) -> torch.Tensor:
+    """int32 prefix sums [len+1] on `device` (pinned staging, asynchronous copy)."""
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    t = torch.tensor(off, dtype=torch.int32)
+    if torch.device(device).type == "cuda":
+        t = t.pin_memory().to(device, non_blocking=True)
+    return t
+
+
+def _cuda_f32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("veto_b200: tensors must live on a CUDA device (no CPU fallback)")
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# a1: pair enumeration
+# --------------------------------------------------------------------------------------------
+def pair_capacities(n_boxes: Sequence[int], max_pairs: int) -> List[int]:
+    return [max(1, min(n * (n - 1), max_pairs)) for n in n_boxes]
+
+
+def enumerate_pairs(n_boxes: Sequence[int], device, max_pairs: int = 2048, boxes: Optional[torch.Tensor] = None,
+                    scores: Optional[torch.Tensor] = None, require_overlap: bool = False) -> List[torch.Tensor]:
+    """RelationSampling.prepare_test_pairs (sampling.py:31-52): list of int64 [R_i,2] per image.
+
+    `boxes` [N,4] xyxy / `scores` [N]: concatenated over images, needed for the IoU filter / the cap."""
+    L.require_device()
+    lib = L.load()
+    B = len(n_boxes)
+    if B == 0:
+        return []
+    caps = pair_capacities(n_boxes, max_pairs)
+    total = sum(caps)
+    pairs = torch.empty((total, 2), dtype=torch.int64, device=device)
+    scratch = torch.empty(3 * (B + 1), dtype=torch.int32, device=device)
+    counts = torch.empty(B, dtype=torch.int32, device=device) if require_overlap else None
+    if boxes is not None:
+        boxes = _cuda_f32(boxes)
+    if scores is not None:
+        scores = _cuda_f32(scores)
+    with torch.cuda.device(pairs.device):
+        L.check(lib.veto_pairs_enumerate(_i32(n_boxes), B, L.ptr(boxes), L.ptr(scores), int(bool(require_overlap)),
+                                         int(max_pairs), pairs.data_ptr(), L.ptr(counts), scratch.data_ptr(),
+                                         L.stream_ptr()), "veto_pairs_enumerate")
+    if counts is None:
+        n_valid = caps
+    else:
+        n_valid = counts.cpu().tolist()  # data-dependent sizes: the reference syncs here too (torch.nonzero)
+    out, off = [], 0
+    for cap, n in zip(caps, n_valid):
+        out.append(pairs[off:off + n])
+        off += cap
+    return out
+
+
+def globalize_pairs(rel_pair_idxs: Sequence[torch.Tensor], n_boxes: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """roi_relation_predictors.py:4104-4115 on the device: global (subject, object) box indices, int32 [R]."""
+    L.require_device()
+    lib = L.load()
+    device = rel_pair_idxs[0].device
+    counts = [int(p.shape[0]) for p in rel_pair_idxs]
+    R = sum(counts)
+    pairs = rel_pair_idxs[0] if len(rel_pair_idxs) == 1 else torch.cat(list(rel_pair_idxs), 0)
+    pairs = pairs.to(torch.int64).contiguous()
+    subj = torch.empty(R, dtype=torch.int32, device=device)
+    obj = torch.empty(R, dtype=torch.int32, device=device)
+    if R == 0:
+        return subj, obj
+    rel_off = offsets_tensor(counts, device)
+    box_off = offsets_tensor(n_boxes, device)
+    with torch.cuda.device(device):
+        L.check(lib.veto_pairs_globalize(pairs.data_ptr(), R, rel_off.data_ptr(), box_off.data_ptr(), len(counts),
+                                         subj.data_ptr(), obj.data_ptr(), L.stream_ptr()), "veto_pairs_globalize")
+    return subj, obj
+
+
+# --------------------------------------------------------------------------------------------
+# a3: ROIAlign
+# --------------------------------------------------------------------------------------------
+def roi_align_forward(inp: torch.Tensor, rois: torch.Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
+                      sampling_ratio: int) -> torch.Tensor:
+    """_C.roi_align_forward (pysgg/csrc/vision.cpp:11)."""
+    L.require_device()
+    inp, rois = _cuda_f32(inp), _cuda_f32(rois)
+    B, C, H, W = inp.shape
+    out = torch.empty((rois.shape[0], C, pooled_h, pooled_w), dtype=torch.float32, device=inp.device)
+    with torch.cuda.device(inp.device):
+        L.check(L.load().veto_roi_align_forward(inp.data_ptr(), B, C, H, W, rois.data_ptr(), rois.shape[0],
+                                                float(spatial_scale), pooled_h, pooled_w, sampling_ratio,
+                                                out.data_ptr(), L.stream_ptr()), "veto_roi_align_forward")
+    return out
+
+
+def roi_align_backward(grad: torch.Tensor, rois: torch.Tensor, spatial_scale: float, pooled_h: int, pooled_w: int,
+                       batch: int, channels: int, height: int, width: int, sampling_ratio: int) -> torch.Tensor:
+    """_C.roi_align_backward (pysgg/csrc/vision.cpp:12)."""
+    L.require_device()
+    grad, rois = _cuda_f32(grad), _cuda_f32(rois)
+    gi = torch.empty((batch, channels, height, width), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        L.check(L.load().veto_roi_align_backward(grad.data_ptr(), rois.data_ptr(), rois.shape[0], float(spatial_scale),
+                                                 pooled_h, pooled_w, batch, channels, height, width, sampling_ratio,
+                                                 gi.data_ptr(), L.stream_ptr()), "veto_roi_align_backward")
+    return gi
+
+
+def roi_gather(feats: Sequence[torch.Tensor], depth: torch.Tensor, boxes: torch.Tensor, n_boxes: Sequence[int],
+               scales: Sequence[float], depth_scale: float, pool: int = 8, sampling_ratio: int = 2,
+               k_min: int = 2, k_max: int = 5, return_levels: bool = False):
+    """Pooler.forward depth + RGB branch (poolers.py:109-171) in one launch: (x_2d, d_2d) [N,C,pool,pool]."""
+    L.require_device()
+    feats = [_cuda_f32(f) for f in feats]
+    depth, boxes = _cuda_f32(depth), _cuda_f32(boxes)
+    n_levels = len(feats)
+    Bt, C = feats[0].shape[:2]
+    N = boxes.shape[0]
+    dev = boxes.device
+    x2d = torch.empty((N, C, pool, pool), dtype=torch.float32, device=dev)
+    d2d = torch.empty((N, C, pool, pool), dtype=torch.float32, device=dev)
+    levels = torch.empty(N, dtype=torch.int32, device=dev) if return_levels else None
+    if N:
+        box_off = offsets_tensor(n_boxes, dev)
+        fp = (ctypes.c_void_p * n_levels)(*[f.data_ptr() for f in feats])
+        fh = _i32([f.shape[2] for f in feats])
+        fw = _i32([f.shape[3] for f in feats])
+        sc = (ctypes.c_float * n_levels)(*[float(s) for s in scales])
+        with torch.cuda.device(dev):
+            L.check(L.load().veto_roi_gather_forward(fp, fh, fw, sc, n_levels, k_min, k_max, depth.data_ptr(),
+                                                     depth.shape[2], depth.shape[3], float(depth_scale), Bt, C,
+                                                     boxes.data_ptr(), box_off.data_ptr(), len(n_boxes), N, pool,
+                                                     sampling_ratio, x2d.data_ptr(), d2d.data_ptr(), L.ptr(levels),
+                                                     L.stream_ptr()), "veto_roi_gather_forward")
+    return (x2d, d2d, levels) if return_levels else (x2d, d2d)
+
+
+# --------------------------------------------------------------------------------------------
+# a5-a10: relation head
+# --------------------------------------------------------------------------------------------
+def make_config(num_obj: int, num_out: int, precision: str = "bf16x3", layers: int = 6, dim: int = 576, heads: int = 6,
+                mlp_dim: int = 1152, channels: int = 256, pool: int = 8, patch: int = 2) -> L.VetoConfig:
+    if precision not in L.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(L.PRECISIONS)}, got {precision!r}")
+    return L.VetoConfig(dim, layers, heads, mlp_dim, channels, pool, patch, num_obj, num_out, L.PRECISIONS[precision])
+
+
+# state_dict key (relative to the predictor / Ensemble module) -> veto_weights field
+_SCALAR_KEYS = {
+    "obj_embed": "obj_embed.weight",
+    "class_proj_w": "class_projection.0.weight", "class_proj_b": "class_projection.0.bias",
+    "bn_weight": "pos_embed.0.weight", "bn_bias": "pos_embed.0.bias",
+    "bn_mean": "pos_embed.0.running_mean", "bn_var": "pos_embed.0.running_var",
+    "pos_w": "pos_embed.1.weight", "pos_b": "pos_embed.1.bias",
+    "loc_proj_w": "location_projection.0.weight", "loc_proj_b": "location_projection.0.bias",
+    "cls_token": "fusion_transformer.transformer.cls_token",
+    "pos_embedding": "fusion_transformer.transformer.pos_embedding",
+    "proj_d_w": "fusion_transformer.transformer.patch_embed.proj_d.weight",
+    "proj_d_b": "fusion_transformer.transformer.patch_embed.proj_d.bias",
+    "proj_v_w": "fusion_transformer.transformer.patch_embed.proj_v.weight",
+    "proj_v_b": "fusion_transformer.transformer.patch_embed.proj_v.bias",
+}
+_LAYER_KEYS = {
+    "ln1_w": "0.norm.weight", "ln1_b": "0.norm.bias", "qkv_w": "0.fn.to_qkv.weight",
+    "out_w": "0.fn.to_out.0.weight", "out_b": "0.fn.to_out.0.bias",
+    "ln2_w": "1.norm.weight", "ln2_b": "1.norm.bias",
+    "ff1_w": "1.fn.net.0.weight", "ff1_b": "1.fn.net.0.bias", "ff2_w": "1.fn.net.3.weight", "ff2_b": "1.fn.net.3.bias",
+}
+
+
+class PackedWeights:
+    """veto_weights + the packed device buffer for one (state, precision).  Keeps the source tensors alive."""
+
+    def __init__(self, cfg: L.VetoConfig, tensors: Dict[str, torch.Tensor], rel_out_w: torch.Tensor,
+                 rel_out_b: torch.Tensor):
+        L.require_device()
+        lib = L.load()
+        self.cfg = cfg
+        keep = []
+
+        def dev(t):
+            t = _cuda_f32(t.detach())
+            keep.append(t)
+            return t.data_ptr()
+
+        w = L.VetoWeights()
+        for field, key in _SCALAR_KEYS.items():
+            setattr(w, field, dev(tensors[key]))
+        for field, key in _LAYER_KEYS.items():
+            arr = getattr(w, field)
+            for i in range(cfg.layers):
+                arr[i] = dev(tensors[f"fusion_transformer.transformer.layers.{i}.{key}"])
+        w.rel_out_w = dev(rel_out_w)
+        w.rel_out_b = dev(rel_out_b)
+        self.struct = w
+        self._keep = keep
+        self.device = keep[0].device
+        nbytes = lib.veto_packed_bytes(ctypes.byref(cfg))
+        if nbytes == 0:
+            L.check(-3, "veto_packed_bytes")
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.veto_pack_weights(ctypes.byref(cfg), ctypes.byref(w), self.packed.data_ptr(), nbytes,
+                                          L.stream_ptr()), "veto_pack_weights")
+
+
+_workspaces: Dict[Tuple, torch.Tensor] = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (str(device),)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _workspaces.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+last_launch_count = 0
+
+
+def relation_forward(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.Tensor, roi_depth: torch.Tensor,
+                     subj: torch.Tensor, obj: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                     obj_logits: Optional[torch.Tensor] = None, freq_bias: Optional[torch.Tensor] = None,
+                     chunk_pairs: int = 0, return_features: bool = False, return_tokens: bool = False):
+    """Relation logits [R, num_out] of VETOPredictor / Ensemble (eval) for global pair indices subj/obj."""
+    global last_launch_count
+    lib = L.load()
+    cfg = pw.cfg
+    dev = pw.device
+    boxes, roi_rgb, roi_depth = _cuda_f32(boxes), _cuda_f32(roi_rgb), _cuda_f32(roi_depth)
+    N, R = boxes.shape[0], subj.shape[0]
+    if tuple(roi_rgb.shape) != (N, 256, 8, 8) or tuple(roi_depth.shape) != (N, 256, 8, 8):
+        raise RuntimeError(f"roi features must be [{N},256,8,8], got {tuple(roi_rgb.shape)} / {tuple(roi_depth.shape)}")
+    subj = subj.to(torch.int32).contiguous()
+    obj = obj.to(torch.int32).contiguous()
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    if obj_logits is not None:
+        obj_logits = _cuda_f32(obj_logits)
+    logits = torch.empty((R, cfg.num_out), dtype=torch.float32, device=dev)
+    feats = torch.empty((R, T_DIM), dtype=torch.float32, device=dev) if return_features else None
+    toks = torch.empty((R, N_TOKENS, T_DIM), dtype=torch.float32, device=dev) if return_tokens else None
+    if R and N:
+        nbytes = lib.veto_workspace_bytes(ctypes.byref(cfg), N, R, chunk_pairs)
+        ws = _workspace(dev, nbytes)
+        vin = L.VetoInputs(N, R, boxes.data_ptr(), L.ptr(labels), L.ptr(obj_logits), roi_rgb.data_ptr(),
+                           roi_depth.data_ptr(), subj.data_ptr(), obj.data_ptr(), L.ptr(freq_bias))
+        vout = L.VetoOutputs(logits.data_ptr(), L.ptr(feats), L.ptr(toks))
+        with torch.cuda.device(dev):
+            L.check(lib.veto_relation_forward(ctypes.byref(cfg), ctypes.byref(pw.struct), pw.packed.data_ptr(),
+                                              ctypes.byref(vin), ctypes.byref(vout), ws.data_ptr(), ws.numel(),
+                                              chunk_pairs, L.stream_ptr()), "veto_relation_forward")
+        last_launch_count = int(lib.veto_last_launch_count())
+    out = [logits]
+    if return_features:
+        out.append(feats)
+    if return_tokens:
+        out.append(toks)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+# --------------------------------------------------------------------------------------------
+# a12: post-processing
+# --------------------------------------------------------------------------------------------
+def postprocess(rel_logits: torch.Tensor, pairs: torch.Tensor, obj_scores: torch.Tensor, rel_counts: Sequence[int],
+                n_boxes: Sequence[int]):
+    """PostProcessor vanilla branch (inference.py:398-453) for a whole batch: returns image-segmented
+    (sorted pairs [R,2], class probabilities [R,C], labels [R], triple scores [R])."""
+    L.require_device()
+    rel_logits, obj_scores = _cuda_f32(rel_logits), _cuda_f32(obj_scores)
+    pairs = pairs.to(torch.int64).contiguous()
+    R, C = rel_logits.shape
+    dev = rel_logits.device
+    if max(rel_counts, default=0) > 16384:
+        raise RuntimeError("veto_postprocess sorts one image in shared memory: at most 16384 pairs per image")
+    pairs_o = torch.empty_like(pairs)
+    probs_o = torch.empty_like(rel_logits)
+    labels_o = torch.empty(R, dtype=torch.int64, device=dev)
+    triple_o = torch.empty(R, dtype=torch.float32, device=dev)
+    if R:
+        rel_off = offsets_tensor(rel_counts, dev)
+        box_off = offsets_tensor(n_boxes, dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().veto_postprocess(rel_logits.data_ptr(), C, pairs.data_ptr(), obj_scores.data_ptr(),
+                                              rel_off.data_ptr(), box_off.data_ptr(), len(rel_counts), R,
+                                              pairs_o.data_ptr(), probs_o.data_ptr(), labels_o.data_ptr(),
+                                              triple_o.data_ptr(), L.stream_ptr()), "veto_postprocess")
+    return pairs_o, probs_o, labels_o, triple_o
+
+
+# --------------------------------------------------------------------------------------------
+# test hooks
+# --------------------------------------------------------------------------------------------
+def test_gemm(a, w, bias=None, residual=None, act: int = 0, precision: str = "fp32"):
+    L.require_device()
+    a, w = _cuda_f32(a), _cuda_f32(w)
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    scratch = torch.empty(4 * (M * K + N * K) + 256, dtype=torch.uint8, device=a.device)
+    L.check(L.load().veto_test_gemm(a.data_ptr(), w.data_ptr(), L.ptr(bias), L.ptr(residual), c.data_ptr(), M, N, K, act,
+                                    L.PRECISIONS[precision], scratch.data_ptr(), scratch.numel(), L.stream_ptr()),
+            "veto_test_gemm")
+    return c
+
+
+def test_layernorm(x, w, b):
+    L.require_device()
+    x = _cuda_f32(x)
+    y = torch.empty_like(x)
+    L.check(L.load().veto_test_layernorm(x.data_ptr(), _cuda_f32(w).data_ptr(), _cuda_f32(b).data_ptr(), y.data_ptr(),
+                                         x.shape[0], L.stream_ptr()), "veto_test_layernorm")
+    return y
+
+
+def test_attention(qkv):
+    """qkv [n_seq*19, 1728] -> [n_seq*19, 576]"""
+    L.require_device()
+    qkv = _cuda_f32(qkv)
+    n_seq = qkv.shape[0] // N_TOKENS
+    out = torch.empty((qkv.shape[0], T_DIM), dtype=torch.float32, device=qkv.device)
+    L.check(L.load().veto_test_attention(qkv.data_ptr(), out.data_ptr(), n_seq, L.stream_ptr()), "veto_test_attention")
+    return out

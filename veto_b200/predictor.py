@@ -1,0 +1,312 @@
+"""Drop-ins for the registry-registered ``VETOPredictor`` / ``VETOPredictor_MEET``
+(pysgg/modeling/roi_heads/relation_head/roi_relation_predictors.py:3997-4139, 3876-3995, 3661-3874).
+
+Same registration names, constructor ``(config, in_channels)``, ``forward(proposals, rel_pair_idxs,
+rel_labels, logger, roi_features=, roi_depth_features=, rel_binarys=)`` signature, 6-tuple return and
+state_dict keys as the reference, so reference checkpoints load and ``ROIRelationHead.forward``
+(relation_head.py:195-203) can call them unchanged.  The modules hold parameters only; the forward
+computation is ``veto_relation_forward`` of libveto_b200.so (sm_100a kernels).  There is no PyTorch or
+CPU fallback: without the library or an sm_100 device, forward raises.
+
+Scope of this round: inference (``eval()``) forward.  The training branch (losses, dropout, BN batch
+statistics, backward) is the next row of SURVEY.md §8 and raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import config as C
+from . import ops
+from .registry import ROI_RELATION_PREDICTOR
+from .structures import xyxy_boxes
+
+
+# ---- hooks a harness may replace (the reference resolves these from the dataset / GloVe files) ----
+def get_dataset_statistics(config):
+    """obj / rel class name lists (reference: pysgg/data/build.py:27-53).  Uses pysgg when importable,
+    otherwise synthesises names from the configured class counts."""
+    try:
+        from pysgg.data import get_dataset_statistics as ref_stats
+        return ref_stats(config)
+    except Exception:
+        n_obj, n_rel = C.num_classes(config)
+        return {"obj_classes": ["__background__"] + [f"obj{i}" for i in range(1, n_obj)],
+                "rel_classes": ["__background__"] + [f"rel{i}" for i in range(1, n_rel)]}
+
+
+def obj_edge_vectors(names, wv_dir, wv_dim):
+    """GloVe rows for the class names (reference: relation_head/utils_motifs.py:151-171); random when the
+    reference / the GloVe files are not available (a checkpoint overwrites them anyway)."""
+    try:
+        from pysgg.modeling.roi_heads.relation_head.utils_motifs import obj_edge_vectors as ref_vecs
+        return ref_vecs(names, wv_dir=wv_dir, wv_dim=wv_dim)
+    except Exception:
+        return torch.randn(len(names), wv_dim)
+
+
+def xavier_init(m: nn.Linear) -> nn.Linear:
+    """pysgg/modeling/utils.py-style xavier_normal_ + zero bias is NOT what the reference uses for rel_out:
+    miscellaneous.py:85-93 applies xavier_normal_ to the weight only."""
+    nn.init.xavier_normal_(m.weight)
+    return m
+
+
+# ---- parameter containers with the reference's module tree (model_veto.py) ----
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, dropout):
+        super().__init__()
+        self.heads = heads
+        self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(dropout))
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.0), nn.Linear(hidden, dim),
+                                 nn.Dropout(0.0))
+
+
+class _PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, in_channels, patch):
+        super().__init__()
+        self.proj_d = nn.Linear(in_channels * 2 * patch ** 2, 512)
+        self.proj_v = nn.Linear(in_channels * 2 * patch ** 2, 64)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, config, in_channels):
+        super().__init__()
+        t = config.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER
+        dim = t.T_INPUT_DIM
+        self.patch_embed = _PatchEmbed(in_channels, t.PATCH_SIZE)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, 1, dim))
+        self.layers = nn.ModuleList([
+            nn.ModuleList([_PreNorm(dim, _Attention(dim, t.NHEADS, t.T_DROPOUT)),
+                           _PreNorm(dim, _FeedForward(dim, dim * 2))])
+            for _ in range(t.ENC_LAYERS)])
+
+
+class _VETOTransformer(nn.Module):
+    def __init__(self, config, in_channels=256):
+        super().__init__()
+        self.transformer = _Transformer(config, in_channels)
+
+
+class _Trunk(nn.Module):
+    """Everything VETOPredictor and Ensemble share (same parameter names in both)."""
+
+    def _build_trunk(self, config, obj_classes):
+        t = config.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER
+        dim = t.T_INPUT_DIM
+        if (dim, t.NHEADS, t.PATCH_SIZE, config.MODEL.ROI_RELATION_HEAD.POOLER_RESOLUTION) != (576, 6, 2, 8):
+            raise RuntimeError("veto_b200 kernels are built for T_INPUT_DIM 576 / NHEADS 6 / PATCH_SIZE 2 / "
+                               "POOLER_RESOLUTION 8 (configs/VETO_final.yaml)")
+        self.embed_dim = 200
+        self.obj_embed = nn.Embedding(len(obj_classes), self.embed_dim)
+        self.class_projection = nn.Sequential(nn.Linear(400, dim), nn.ReLU(inplace=True))
+        with torch.no_grad():
+            self.obj_embed.weight.copy_(obj_edge_vectors(obj_classes, config.GLOVE_DIR, self.embed_dim))
+        self.bbox_embed = nn.Sequential(nn.Linear(9, 32), nn.ReLU(inplace=True), nn.Dropout(0.1),
+                                        nn.Linear(32, 128), nn.ReLU(inplace=True), nn.Dropout(0.1))
+        self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.001), nn.Linear(4, 128), nn.ReLU(inplace=True),
+                                       nn.Dropout(0.1))
+        self.location_projection = nn.Sequential(nn.Linear(256, dim), nn.ReLU(inplace=True))
+        self.fusion_transformer = _VETOTransformer(config, in_channels=256)
+        self.n_layers = t.ENC_LAYERS
+        self.precision = C.get(config, "VETO_B200.PRECISION", "bf16x3")
+        self.chunk_pairs = int(C.get(config, "VETO_B200.CHUNK_PAIRS", 0) or 0)
+        self._packed = None
+        self._packed_key = None
+
+    def _trunk_tensors(self):
+        return {k: v for k, v in self.state_dict(keep_vars=True).items()}
+
+    def _pack(self, rel_w: torch.Tensor, rel_b: torch.Tensor) -> ops.PackedWeights:
+        tensors = self._trunk_tensors()
+        key = (self.precision, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()),
+               rel_w.data_ptr(), rel_w._version, rel_b._version)
+        if self._packed is None or self._packed_key != key:
+            cfg = ops.make_config(self.num_obj_cls, rel_w.shape[0], self.precision, layers=self.n_layers)
+            self._packed = ops.PackedWeights(cfg, tensors, rel_w, rel_b)
+            self._packed_key = key
+        return self._packed
+
+    def _relation_logits(self, proposals, rel_pair_idxs, roi_features, roi_depth_features, rel_w, rel_b,
+                         labels=None, obj_logits=None, freq_bias=None):
+        n_boxes = [len(p) for p in proposals]
+        boxes = torch.cat([xyxy_boxes(p) for p in proposals], 0)
+        subj, obj = ops.globalize_pairs(rel_pair_idxs, n_boxes)
+        pw = self._pack(rel_w, rel_b)
+        return ops.relation_forward(pw, boxes, roi_features, roi_depth_features, subj, obj, labels=labels,
+                                    obj_logits=obj_logits, freq_bias=freq_bias, chunk_pairs=self.chunk_pairs)
+
+
+def _mode(config) -> str:
+    if config.MODEL.ROI_RELATION_HEAD.USE_GT_BOX:
+        return "predcls" if config.MODEL.ROI_RELATION_HEAD.USE_GT_OBJECT_LABEL else "sgcls"
+    return "sgdet"
+
+
+@ROI_RELATION_PREDICTOR.register("VETOPredictor")
+class VETOPredictor(_Trunk):
+    """roi_relation_predictors.py:3997-4139."""
+
+    def __init__(self, config, in_channels):
+        super().__init__()
+        self.mode = _mode(config)
+        statistics = get_dataset_statistics(config)
+        self.obj_classes, self.rel_classes = statistics["obj_classes"], statistics["rel_classes"]
+        self.num_obj_cls, self.num_rel_cls = len(self.obj_classes), len(self.rel_classes)
+        self.obj_embed2 = nn.Embedding(self.num_obj_cls, 200)  # unused by forward, kept for checkpoint parity
+        self._build_trunk(config, self.obj_classes)
+        dim = config.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER.T_INPUT_DIM
+        self.rel_out = xavier_init(nn.Linear(dim, self.num_rel_cls, bias=True))
+        if config.GLOBAL_SETTING.BETA_LOSS:
+            raise NotImplementedError("GLOBAL_SETTING.BETA_LOSS needs the training branch (next round)")
+        self.criterion_loss_rel = nn.CrossEntropyLoss(weight=torch.ones(self.num_rel_cls))
+        self.criterion_loss = nn.CrossEntropyLoss()
+        self.use_freq_bias = bool(C.get(config, "VETO_B200.FREQ_BIAS", False))
+        self.freq_bias_table = None  # [num_obj^2, num_rel] fp32, set by the caller when use_freq_bias
+
+    def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
+                rel_binarys=None):
+        if self.training:
+            raise NotImplementedError("veto_b200.VETOPredictor: the training branch is not built yet (eval() only)")
+        if self.mode == "predcls":
+            obj_labels = torch.cat([p.get_field("labels") for p in proposals], 0).long()
+            hard, soft = obj_labels, None
+        else:
+            soft = torch.cat([p.get_field("predict_logits") for p in proposals], 0).detach()
+            obj_labels = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
+            hard = None
+        obj_dists = nn.functional.one_hot(obj_labels, self.num_obj_cls).float()
+        fb = None
+        if self.use_freq_bias:
+            if self.freq_bias_table is None or hard is None:
+                raise RuntimeError("FREQ_BIAS needs freq_bias_table and hard labels (predcls)")
+            fb = self.freq_bias_table
+        rel_dists = self._relation_logits(proposals, rel_pair_idxs, roi_features, roi_depth_features,
+                                          self.rel_out.weight, self.rel_out.bias, labels=hard, obj_logits=soft,
+                                          freq_bias=fb)
+        obj_dists = obj_dists.split([len(p) for p in proposals], dim=0)
+        rel_dists = rel_dists.split([len(r) for r in rel_pair_idxs], dim=0)
+        return obj_dists, rel_dists, {}, None, None, None
+
+
+def incre_idx_list(group_sizes: List[int], num_rel: int) -> List[int]:
+    """SHA_GCL_extra/extra_function_utils.py:39-52: predicate id -> 1-based group id (0 = background)."""
+    out = [0] * num_rel
+    c = 1
+    for g, n in enumerate(group_sizes):
+        for _ in range(n):
+            out[c] = g + 1
+            c += 1
+    return out
+
+
+class Ensemble(_Trunk):
+    """roi_relation_predictors.py:3661-3874 (ensemble_type 'group')."""
+
+    def __init__(self, config, mode, params, group_num, exp_per_group, group_element_number_list, idx_list):
+        super().__init__()
+        self.mode = mode
+        self.num_obj_cls = len(params["obj_classes"])
+        self.num_rel_cls = len(params["rel_classes"])
+        self.incre_idx_list = idx_list
+        self._build_trunk(config, params["obj_classes"])
+        dim = config.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER.T_INPUT_DIM
+        self.group_num = group_num
+        self.experts_per_group = exp_per_group
+        self.expert_group = bool(config.ENSEMBLE_LEARNING.EXPERT_GROUP)
+        self.group_outs = [n + 2 for n in group_element_number_list]
+        self.rel_out = nn.ModuleList([])
+        self.rel_out_group = nn.ModuleList([])
+        if self.expert_group:
+            for _ in range(exp_per_group):
+                self.rel_out = nn.ModuleList([xavier_init(nn.Linear(dim, n, bias=True)) for n in self.group_outs])
+                self.rel_out_group.append(self.rel_out)
+        else:
+            for n in self.group_outs:
+                self.rel_out.append(xavier_init(nn.Linear(dim, n, bias=True)))
+        self.CE_loss = nn.CrossEntropyLoss()
+        self.criterion_loss = nn.CrossEntropyLoss()
+        self.nms_thresh = config.TEST.RELATION.LATER_NMS_PREDICTION_THRES
+
+    def _head_sets(self):
+        if self.expert_group:
+            return [(f"group_%d%d" % (k, j + 1), self.rel_out_group[j][k]) for j in range(self.experts_per_group)
+                    for k in range(self.group_num)]
+        return [("group_%d" % k, self.rel_out[k]) for k in range(self.group_num)]
+
+    def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None):
+        if self.training:
+            raise NotImplementedError("veto_b200 Ensemble: the training branch is not built yet (eval() only)")
+        if self.mode == "predcls":
+            obj_preds = torch.cat([p.get_field("labels") for p in proposals], 0).long()
+            obj_dists = nn.functional.one_hot(obj_preds, self.num_obj_cls).float()
+        else:
+            obj_labels = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
+            obj_dists = nn.functional.one_hot(obj_labels, self.num_obj_cls).float()
+            if self.mode == "sgdet":
+                raise NotImplementedError("MEET sgdet test uses nms_per_cls (:3855-3874): not built yet")
+            obj_preds = obj_dists[:, 1:].max(1)[1] + 1  # :3783
+        heads = self._head_sets()
+        # all expert heads as ONE [sum(n_k+2), 576] classifier GEMM, split afterwards
+        w = torch.cat([m.weight for _, m in heads], 0)
+        b = torch.cat([m.bias for _, m in heads], 0)
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias._version) for _, m in heads)
+        if getattr(self, "_cat_key", None) != key:
+            self._cat_w, self._cat_b, self._cat_key = w.detach().contiguous(), b.detach().contiguous(), key
+        logits = self._relation_logits(proposals, rel_pair_idxs, roi_features, roi_depth_features, self._cat_w,
+                                       self._cat_b, labels=obj_preds)
+        rel_dists, off = {}, 0
+        for name, m in heads:
+            n = m.weight.shape[0]
+            rel_dists[name] = logits[:, off:off + n]
+            off += n
+        obj_dists = obj_dists.split([len(p) for p in proposals], dim=0)
+        return obj_dists, rel_dists, {}, None
+
+
+@ROI_RELATION_PREDICTOR.register("VETOPredictor_MEET")
+class VETOPredictor_MEET(nn.Module):
+    """roi_relation_predictors.py:3876-3995."""
+
+    def __init__(self, config, in_channels):
+        super().__init__()
+        self.mode = _mode(config)
+        stats = get_dataset_statistics(config)
+        self.params = {"statistics": stats, "obj_classes": stats["obj_classes"], "rel_classes": stats["rel_classes"]}
+        ds = config.GLOBAL_SETTING.DATASET_CHOICE
+        split = config.GCL_SETTING.GROUP_SPLIT_MODE
+        if (ds, split) not in C.GROUP_SPLITS:
+            raise KeyError(f"unknown group split {(ds, split)}")
+        self.max_group_element_number_list = list(C.GROUP_SPLITS[(ds, split)])
+        self.incre_idx_list = incre_idx_list(self.max_group_element_number_list, len(stats["rel_classes"]))
+        self.num_groups = len(self.max_group_element_number_list)
+        self.experts_per_group = 3 if config.ENSEMBLE_LEARNING.EXPERT_GROUP else 1
+        self.ensemble_type = config.ENSEMBLE_LEARNING.TYPE
+        self.model = Ensemble(config, self.mode, self.params, self.num_groups, self.experts_per_group,
+                              self.max_group_element_number_list, self.incre_idx_list)
+
+    def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
+                rel_binarys=None):
+        if self.training:
+            raise NotImplementedError("veto_b200.VETOPredictor_MEET: the training branch is not built yet")
+        obj_dists, rel_dists, add_losses, _ = self.model(proposals, rel_pair_idxs, rel_labels, logger,
+                                                         roi_features=roi_features,
+                                                         roi_depth_features=roi_depth_features)
+        return obj_dists, dict(rel_dists), dict(add_losses), self.incre_idx_list, None, {}
