@@ -210,8 +210,16 @@ int veto_relation_forward(const veto_config* cfg, const veto_weights* w, const v
                           const veto_inputs* in, const veto_outputs* out,
                           void* workspace_dev, size_t workspace_bytes, int32_t chunk_pairs,
                           veto_stream_t stream);
-/* Number of kernel launches the last veto_relation_forward on this thread enqueued. */
+/* Total number of kernel launches this thread has enqueued through the library so far (monotonic). */
 int64_t veto_last_launch_count(void);
+
+/* Per-stage device timing (used by bench.py for the roofline line; not a profiler): between begin and end every
+ * kernel launch of this thread is bracketed by CUDA events on `stream`; end synchronises and adds, per stage tag,
+ * the elapsed milliseconds and the launch count into the caller's host arrays of length VETO_PROFILE_TAGS. */
+#define VETO_PROFILE_TAGS 16
+int veto_profile_begin(veto_stream_t stream);
+int veto_profile_end(double* ms_by_tag_host, int64_t* launches_by_tag_host);
+const char* veto_profile_tag_name(int tag);
 
 /* ------------------------------------------------------------------------------------------
  * a12 (row f1). PostProcessor.forward, vanilla branch (relation_head/inference.py:398-453):

@@ -1,0 +1,381 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libveto_b200.so via the reference-shaped host API, and is compared with the CPU oracle (oracle/) and with the
+golden fixtures produced by the unmodified reference (tests/golden/make_golden.py).
+
+Bars (BASELINE.json north_star): rel_pair_idxs, ROI gather and argmax labels bit-exact; relation logits within
+1e-3 relative (max |diff| / max |ref|) for the fp32 and bf16x3 modes; the single-pass bf16 tensor-core mode has the
+stated tolerance BF16_TOL = 3e-2 and is not required to keep every argmax.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import veto_oracle as O
+from tests import harness as H
+from tests.cases import CASES, case_batch, case_state, load_golden
+from tests.util import rel_err, tie_groups_equal
+from veto_b200 import lib as L
+from veto_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3     # north_star: "relation logits must match within 1e-3 relative in fp32"
+BF16_TOL = 3e-2     # stated tolerance of the single-pass bf16 tensor-core mode
+TOL = {"fp32": FP32_TOL, "bf16x3": FP32_TOL, "bf16": BF16_TOL}
+DEV = torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("shape", [(300, 51, 576), (1000, 1152, 200), (77, 128, 128), (130, 60, 576)])
+def test_gemm_simt(shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(0)
+    a, w, b, r = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g), \
+        torch.randn(M, N, generator=g)
+    ref = a.double() @ w.double().T
+    assert rel_err(H.np_(ops.test_gemm(_t(a.numpy()), _t(w.numpy()))), ref.numpy()) < 5e-6
+    out = ops.test_gemm(_t(a.numpy()), _t(w.numpy()), bias=_t(b.numpy()), residual=_t(r.numpy()), act=2)
+    exp = torch.nn.functional.gelu(ref + b.double()) + r.double()
+    assert rel_err(H.np_(out), exp.numpy()) < 5e-6
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 5e-6), ("bf16x3", 3e-5)])
+@pytest.mark.parametrize("shape", [(128, 192, 64), (100, 128, 64), (333, 576, 1152), (1000, 1728, 576), (320, 1024, 1024),
+                                   (320, 128, 1024), (19456, 576, 576)])
+def test_gemm_tcgen05(shape, precision, tol):
+    """tcgen05/TMEM GEMM.  bf16: exact up to fp32 accumulation against the product of the bf16-rounded operands;
+    bf16x3: fp32-grade against the fp64 product of the fp32 operands."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(1)
+    a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    if precision == "bf16":
+        ref = a.bfloat16().double() @ w.bfloat16().double().T
+    else:
+        ref = a.double() @ w.double().T
+    assert rel_err(H.np_(ops.test_gemm(_t(a.numpy()), _t(w.numpy()), precision=precision)), ref.numpy()) < tol
+    out = ops.test_gemm(_t(a.numpy()), _t(w.numpy()), bias=_t(b.numpy()), act=1, precision=precision)
+    assert rel_err(H.np_(out), torch.relu(ref + b.double()).numpy()) < tol
+
+
+def test_layernorm_and_attention():
+    g = torch.Generator().manual_seed(2)
+    x, w, b = 3 * torch.randn(1000, 576, generator=g) + 0.5, torch.randn(576, generator=g), torch.randn(576, generator=g)
+    ref = torch.nn.functional.layer_norm(x.double(), (576,), w.double(), b.double(), 1e-5)
+    assert rel_err(H.np_(ops.test_layernorm(_t(x.numpy()), _t(w.numpy()), _t(b.numpy()))), ref.numpy()) < 2e-6
+    n_seq = 301
+    qkv = torch.randn(n_seq * 19, 1728, generator=g)
+    q, k, v = [t.reshape(n_seq, 19, 6, 96).permute(0, 2, 1, 3).double() for t in qkv.chunk(3, -1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) * (96 ** -0.5), -1) @ v
+    ref = att.permute(0, 2, 1, 3).reshape(n_seq * 19, 576)
+    assert rel_err(H.np_(ops.test_attention(_t(qkv.numpy()))), ref.numpy()) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------ a1 pairs
+def _pairs_gpu(c, batch):
+    boxes = _t(np.concatenate(batch["boxes"]))
+    scores = _t(np.concatenate(batch["pred_scores"])) if "pred_scores" in batch else None
+    return ops.enumerate_pairs(batch["n_boxes"], DEV, c.get("max_pairs", 2048), boxes=boxes, scores=scores,
+                               require_overlap=c.get("require_overlap", False) and c["mode"] == "sgdet")
+
+
+def _pairs_oracle(c, batch):
+    return O.prepare_test_pairs(batch["n_boxes"], c.get("max_pairs", 2048), scores=batch.get("pred_scores"),
+                                boxes=batch["boxes"],
+                                require_overlap=c.get("require_overlap", False) and c["mode"] == "sgdet")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_pairs_bit_exact(name):
+    c = CASES[name]
+    batch = case_batch(c, features=False)
+    g = load_golden(name)
+    got = [H.np_(p) for p in _pairs_gpu(c, batch)]
+    ref = _pairs_oracle(c, batch)
+    assert [len(p) for p in got] == list(g["pair_counts"])
+    for a, b in zip(got, ref):
+        assert a.dtype == np.int64 and np.array_equal(a, b)
+    if "max_pairs" not in c:
+        assert np.array_equal(np.concatenate(got), g["pairs"])
+    else:  # over the cap the reference's unstable sort decides ties: compare tie-aware against the golden rows
+        off = 0
+        for k, p in enumerate(got):
+            gp = g["pairs"][off:off + len(p)]
+            off += len(p)
+            s = batch["pred_scores"][k]
+            assert tie_groups_equal(p, gp, s[gp[:, 0]] * s[gp[:, 1]])
+
+
+def test_pairs_edge_cases():
+    # empty / single-box images give the [[0,0]] placeholder (sampling.py:47-51); large n uses the closed form
+    n_boxes = [0, 1, 2, 300, 5]
+    got = [H.np_(p) for p in ops.enumerate_pairs(n_boxes, DEV, max_pairs=10 ** 6)]
+    ref = O.prepare_test_pairs(n_boxes, max_pairs=10 ** 6)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    # cap + overlap on the largest supported filtered image (n = 128), ragged batch
+    rng = np.random.default_rng(5)
+    n_boxes = [128, 3, 40]
+    boxes = [synth.make_boxes(rng, n, 800, 592) for n in n_boxes]
+    scores = [rng.uniform(0.05, 1.0, n).astype(np.float32) for n in n_boxes]
+    for overlap in (False, True):
+        got = ops.enumerate_pairs(n_boxes, DEV, 2048, boxes=_t(np.concatenate(boxes)), scores=_t(np.concatenate(scores)),
+                                  require_overlap=overlap)
+        ref = O.prepare_test_pairs(n_boxes, 2048, scores=scores, boxes=boxes, require_overlap=overlap)
+        assert all(np.array_equal(H.np_(a), b) for a, b in zip(got, ref)), overlap
+    with pytest.raises(L.VetoError):
+        ops.enumerate_pairs([200], DEV, 2048, scores=torch.ones(200, device=DEV))
+    assert [tuple(p.shape) for p in ops.enumerate_pairs([], DEV)] == []
+
+
+def test_globalize_pairs():
+    n_boxes = [3, 1, 4]
+    pairs = ops.enumerate_pairs(n_boxes, DEV)
+    s, o = ops.globalize_pairs(pairs, n_boxes)
+    rs, ro = O.global_pair_indices([H.np_(p) for p in pairs], n_boxes)
+    assert np.array_equal(H.np_(s), rs) and np.array_equal(H.np_(o), ro)
+
+
+# ------------------------------------------------------------------------------------------ a2/a3 gather
+@pytest.mark.parametrize("name", ["cfg1_predcls_vg", "ragged_predcls", "sgdet_cap", "meet_gqa"])
+def test_gather_bit_exact(name):
+    c = CASES[name]
+    batch = case_batch(c)
+    g = load_golden(name)
+    x2d, d2d, lv = ops.roi_gather([_t(f) for f in batch["feats"]], _t(batch["depth"]), _t(np.concatenate(batch["boxes"])),
+                                  batch["n_boxes"], synth.POOLER_SCALES, synth.DEPTH_SCALE, return_levels=True)
+    rx, rd = O.pooler_forward(batch["feats"], batch["depth"], batch["boxes"])
+    x, d = H.np_(x2d), H.np_(d2d)
+    assert np.array_equal(H.np_(lv), O.level_map(batch["boxes"]))
+    assert np.array_equal(x, rx) and np.array_equal(d, rd)
+    assert np.array_equal(x[:, ::16], g["x2d_sub"]) and np.array_equal(d[:, ::16], g["d2d_sub"])
+    assert np.array_equal(x.sum(axis=(1, 2, 3), dtype=np.float64), g["x2d_sum"])
+
+
+def test_roi_align_generic_and_edges():
+    """The one-for-one _C.roi_align_forward replacement: boxes hanging outside the map, sub-pixel boxes, other
+    pooled sizes / sampling ratios; and the scatter backward against the serial oracle."""
+    rng = np.random.default_rng(9)
+    B, C, Hh, Ww, scale = 2, 37, 20, 26, 0.125
+    inp = rng.standard_normal((B, C, Hh, Ww), dtype=np.float32)
+    W, Himg = Ww / scale, Hh / scale
+    boxes = np.concatenate([synth.make_boxes(rng, 12, int(W), int(Himg), max_side=140.0),
+                            np.array([[-30, -20, 40, 50], [W - 10, Himg - 10, W + 60, Himg + 40], [10, 10, 10.2, 10.1],
+                                      [W + 50, Himg + 50, W + 90, Himg + 90]], np.float32)])
+    rois = np.concatenate([rng.integers(0, B, (len(boxes), 1)).astype(np.float32), boxes], 1)
+    for (ph, pw, sr) in [(8, 8, 2), (7, 7, 2), (4, 6, 3), (1, 1, 1)]:
+        got = H.np_(ops.roi_align_forward(_t(inp), _t(rois), scale, ph, pw, sr))
+        assert np.array_equal(got, O.roi_align(inp, rois, scale, ph, pw, sr)), (ph, pw, sr)
+    grad = rng.standard_normal((len(rois), C, 8, 8), dtype=np.float32)
+    gi = H.np_(ops.roi_align_backward(_t(grad), _t(rois), scale, 8, 8, B, C, Hh, Ww, 2))
+    ref = O.roi_align_backward(grad, rois, (B, C, Hh, Ww), scale, 2)
+    assert np.allclose(gi, ref, rtol=1e-4, atol=1e-5)   # fp32 atomics: summation order differs
+    with pytest.raises(L.VetoError):
+        ops.roi_align_forward(_t(inp), _t(rois), scale, 8, 8, 0)      # adaptive sampling is not on this path
+
+
+# ------------------------------------------------------------------------------------------ a5-a10 head
+def _golden_pairs(c, g, batch):
+    """Pair lists in the golden row order (the reference's tie order over the cap)."""
+    return [_t(p) for p in np.split(g["pairs"], np.cumsum(g["pair_counts"])[:-1])]
+
+
+def _run_predictor(name, precision, chunk=0, pairs=None):
+    c = CASES[name]
+    batch, state, g = case_batch(c), case_state(c), load_golden(name)
+    cfg = H.make_cfg(c["predictor"], c["mode"], c["dataset"], c.get("max_pairs", 2048), c.get("require_overlap", False),
+                     precision, chunk)
+    ds_obj = 151 if c["dataset"] == "VG" else 201
+    bls = H.boxlists(batch, DEV, ds_obj)
+    feats, depth = H.device_features(batch, DEV)
+    from veto_b200 import registry
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True)
+    pred = H.build_predictor(cfg, state, DEV)
+    pairs = pairs if pairs is not None else _golden_pairs(c, g, batch)
+    with torch.no_grad():
+        x2d, d2d, a, b = fe(feats, bls, depth_features=depth)
+        assert a is None and b is None
+        out = pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)
+    return c, batch, g, bls, pairs, pred, out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["cfg1_predcls_vg", "cfg1_default_init", "ragged_predcls", "sgdet_cap", "sgdet_overlap"])
+def test_relation_logits(name, precision):
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    assert len(out) == 6                                           # relation_head.py:196 unpacks exactly six
+    obj_dists, rel_dists, add_losses, incre, chosen, custom = out
+    assert add_losses == {} and incre is None and chosen is None and custom is None
+    assert [tuple(o.shape) for o in obj_dists] == [(n, 151) for n in batch["n_boxes"]]
+    assert np.array_equal(np.concatenate([H.np_(o).argmax(1) for o in obj_dists]), g["obj_dists_argmax"])
+    assert [r.shape[0] for r in rel_dists] == list(g["pair_counts"])
+    logits, ref = np.concatenate([H.np_(r) for r in rel_dists]), g["logits"]
+    assert rel_err(logits, ref) < TOL[precision]
+    if precision != "bf16":
+        assert np.array_equal(logits[:, 1:].argmax(1), ref[:, 1:].argmax(1))      # argmax predicate labels bit-exact
+        assert np.array_equal(logits.argmax(1), ref.argmax(1))
+    else:
+        assert (logits.argmax(1) == ref.argmax(1)).mean() > 0.97
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_tokens_match_reference(precision):
+    """Encoder input [R,19,576] (factored patch embedding + gather/add) against tokens captured from the reference."""
+    for name in ("cfg1_predcls_vg", "ragged_predcls"):
+        c = CASES[name]
+        batch, state, g = case_batch(c), case_state(c), load_golden(name)
+        pred = H.build_predictor(H.make_cfg(precision=precision), state, DEV)
+        x2d, d2d = ops.roi_gather([_t(f) for f in batch["feats"]], _t(batch["depth"]), _t(np.concatenate(batch["boxes"])),
+                                  batch["n_boxes"], synth.POOLER_SCALES, synth.DEPTH_SCALE)
+        pairs = _golden_pairs(c, g, batch)
+        subj, obj = ops.globalize_pairs(pairs, batch["n_boxes"])
+        pw = pred._pack(pred.rel_out.weight, pred.rel_out.bias)
+        logits, feats, toks = ops.relation_forward(pw, _t(np.concatenate(batch["boxes"])), x2d, d2d, subj, obj,
+                                                   labels=_t(np.concatenate(batch["labels"])), return_features=True,
+                                                   return_tokens=True)
+        tok = H.np_(toks)[g["token_rows"]]
+        assert rel_err(tok, g["tokens"]) < 2e-5
+        # rel_features is the CLS row the classifier consumed
+        w, b = H.np_(pred.rel_out.weight).astype(np.float64), H.np_(pred.rel_out.bias).astype(np.float64)
+        assert rel_err(H.np_(feats).astype(np.float64) @ w.T + b, H.np_(logits)) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["meet_gqa", "meet_vg"])
+def test_meet_group_heads(name, precision):
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    obj_dists, rel_dists, add_losses, incre, chosen, custom = out
+    assert isinstance(rel_dists, dict) and add_losses == {} and chosen is None and custom == {}
+    assert list(incre) == list(g["incre_idx_list"])
+    keys = [k[len("logits_"):] for k in g.files if k.startswith("logits_")]
+    assert sorted(rel_dists) == sorted(keys)
+    for k in keys:
+        got, ref = H.np_(rel_dists[k]), g["logits_" + k]
+        assert got.shape == ref.shape                           # un-split [R_total, n_k+2] (…:3843,3851-3853)
+        assert rel_err(got, ref) < TOL[precision]
+        if precision != "bf16":
+            assert np.array_equal(got.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_top50_ranking_and_postprocess(precision):
+    """PostProcessor parity: triple scores, and the top-50 triplet ranking of the reference (tie-aware)."""
+    name = "cfg1_predcls_vg"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    from veto_b200.postprocess import make_roi_relation_post_processor
+    cfg = H.make_cfg(precision=precision)
+    res = make_roi_relation_post_processor(cfg)((out[1], [b.get_field("predict_logits") for b in bls]), pairs, bls)
+    pp = np.concatenate([H.np_(r.get_field("rel_pair_idxs")) for r in res])
+    labels = np.concatenate([H.np_(r.get_field("pred_rel_labels")) for r in res])
+    probs = np.concatenate([H.np_(r.get_field("pred_rel_scores")) for r in res])
+    scores = probs[:, 1:].max(1)
+    assert pp.dtype == np.int64 and labels.dtype == np.int64
+    assert np.allclose(scores, g["post_scores"], rtol=5e-4)
+    assert np.all(np.diff(np.concatenate([H.np_(r.get_field("triple_scores")) for r in res])) <= 0)
+    assert np.allclose(probs.sum(1), 1.0, atol=1e-5)
+    # rows whose reference score is separated from its neighbours by more than the logit tolerance must agree
+    s = g["post_scores"].astype(np.float64)
+    gap = np.full(len(s), np.inf)
+    gap[1:] = np.minimum(gap[1:], s[:-1] - s[1:])
+    gap[:-1] = np.minimum(gap[:-1], s[:-1] - s[1:])
+    clear = gap > 2e-3 * s
+    assert np.array_equal(pp[clear], g["post_pairs"][clear]) and np.array_equal(labels[clear], g["post_labels"][clear])
+    # top-50 as a set of (subject, object, label) triplets, allowing swaps only among unclear rows
+    top_ref = {tuple(r) + (int(l),) for r, l in zip(g["post_pairs"][:50], g["post_labels"][:50])}
+    top_got = {tuple(r) + (int(l),) for r, l in zip(pp[:50], labels[:50])}
+    assert len(top_ref - top_got) <= int((~clear[45:55]).sum())
+    # and against the oracle's post-processing of OUR logits: exact ranking wherever scores are distinct
+    logits = np.concatenate([H.np_(r) for r in out[1]])
+    obj_logits = [H.np_(b.get_field("predict_logits")) for b in bls]
+    ora = O.postprocess(np.split(logits, np.cumsum(g["pair_counts"])[:-1]), obj_logits, [H.np_(p) for p in pairs])
+    so = np.concatenate([r["triple_scores"] for r in ora]).astype(np.float64)
+    gap = np.full(len(so), np.inf)
+    gap[1:] = np.minimum(gap[1:], so[:-1] - so[1:])
+    gap[:-1] = np.minimum(gap[:-1], so[:-1] - so[1:])
+    clear = gap > 1e-5 * so
+    assert np.array_equal(pp[clear], np.concatenate([r["rel_pair_idxs"] for r in ora])[clear])
+
+
+def test_chunking_and_permutation_invariance():
+    """Size-independent properties: the chunk size never changes a bit of the result, and permuting the pair list
+    permutes the logits (rows are independent)."""
+    name = "cfg1_predcls_vg"
+    for precision in ("fp32", "bf16x3"):
+        base = np.concatenate([H.np_(r) for r in _run_predictor(name, precision)[6][1]])
+        for chunk in (1, 37, 380):
+            alt = np.concatenate([H.np_(r) for r in _run_predictor(name, precision, chunk=chunk)[6][1]])
+            assert np.array_equal(base, alt), (precision, chunk)
+        c = CASES[name]
+        g = load_golden(name)
+        perm = np.random.default_rng(3).permutation(len(g["pairs"]))
+        out = _run_predictor(name, precision, pairs=[_t(g["pairs"][perm])])[6]
+        assert np.array_equal(H.np_(out[1][0]), base[perm]), precision
+
+
+def test_frequency_bias_epilogue_off_by_default_and_additive():
+    """The optional freq-bias add (model_motifs.py:29-38 semantics) is OFF for VETO parity; when enabled it adds
+    table[label_s * num_obj + label_o]."""
+    name = "ragged_predcls"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, "fp32")
+    base = torch.cat(list(out[1]))
+    assert pred.use_freq_bias is False
+    table = torch.randn(151 * 151, 51, device=DEV)
+    pred.use_freq_bias, pred.freq_bias_table = True, table
+    feats, depth = H.device_features(batch, DEV)
+    x2d, d2d = ops.roi_gather(feats[:4], depth, torch.cat([b.bbox for b in bls]), batch["n_boxes"], synth.POOLER_SCALES,
+                              synth.DEPTH_SCALE)
+    with torch.no_grad():
+        biased = torch.cat(list(pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]))
+    lab = torch.cat([b.get_field("labels") for b in bls])
+    s, o = ops.globalize_pairs(pairs, batch["n_boxes"])
+    assert torch.equal(biased, base + table[lab[s.long()] * 151 + lab[o.long()]])
+
+
+def test_full_size_sgdet_batch_properties():
+    """BASELINE.json configs[2] shape (80 proposals / image, 6320 pairs / image, cap 8192) on a few images: pair
+    enumeration against the closed form, finite logits, mirror/permutation consistency, bf16x3 vs fp32 agreement."""
+    n_img, n_box = 3, 80
+    batch = synth.make_batch(31, [n_box] * n_img, mode="sgdet")
+    state = synth.predictor_state(13)
+    outs = {}
+    for precision in ("fp32", "bf16x3"):
+        cfg = H.make_cfg(mode="sgdet", max_pairs=8192, precision=precision)
+        outs[precision] = H.run_head(cfg, state, batch, DEV, post=False)
+    pairs = [H.np_(p) for p in outs["fp32"]["pairs"]]
+    assert [len(p) for p in pairs] == [n_box * (n_box - 1)] * n_img
+    r = np.arange(n_box * (n_box - 1))
+    i, j = r // (n_box - 1), r % (n_box - 1)
+    assert all(np.array_equal(p, np.stack([i, j + (j >= i)], 1)) for p in pairs)
+    a = np.concatenate([H.np_(x) for x in outs["fp32"]["rel_dists"]])
+    b = np.concatenate([H.np_(x) for x in outs["bf16x3"]["rel_dists"]])
+    assert np.isfinite(a).all() and a.shape == (n_img * n_box * (n_box - 1), 51)
+    assert rel_err(b, a) < 2e-4
+    assert (a.argmax(1) == b.argmax(1)).mean() > 0.999
+    # oracle spot-check of a random sample of pairs at full batch size
+    sel = np.random.default_rng(0).choice(len(a), 48, replace=False)
+    x_ref, d_ref = O.pooler_forward(batch["feats"], batch["depth"], batch["boxes"])
+    assert np.array_equal(H.np_(outs["fp32"]["x2d"]), x_ref)
+    off = np.repeat(np.arange(n_img) * n_box, n_box * (n_box - 1))
+    gp = np.concatenate(pairs) + off[:, None]
+    one = dict(batch, n_boxes=[n_img * n_box], boxes=[np.concatenate(batch["boxes"])],
+               predict_logits=[np.concatenate(batch["predict_logits"])])
+    ref = O.predictor_forward(state, one, [gp[sel]], x_ref, d_ref, "sgdet")
+    assert rel_err(a[sel], ref) < FP32_TOL
+    assert np.array_equal(a[sel].argmax(1), ref.argmax(1))
+
+
+def test_no_cpu_fallback_and_errors():
+    with pytest.raises(RuntimeError):
+        ops.roi_align_forward(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 1.0, 2, 2, 2)      # CPU tensors
+    pred = H.build_predictor(H.make_cfg(), synth.predictor_state(1), DEV)
+    pred.train()
+    with pytest.raises(NotImplementedError):
+        pred([], [], None, None)
+    with pytest.raises(ValueError):
+        ops.make_config(151, 51, precision="fp8")
+    cfg = ops.make_config(151, 51, "fp32", dim=512)
+    import ctypes
+    assert L.load().veto_packed_bytes(ctypes.byref(cfg)) == 0
+    assert b"unsupported architecture" in L.load().veto_last_error()

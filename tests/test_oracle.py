@@ -183,3 +183,31 @@ def test_roialign_backward_matches_torchvision():
     ref = torch.ops.torchvision._roi_align_backward(torch.from_numpy(g), torch.from_numpy(rois), 0.0625, 8, 8,
                                                     2, 3, 10, 13, 2, False).numpy()
     assert np.allclose(mine, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cfg1_predcls_vg", "ragged_predcls", "sgdet_cap"])
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the CPU baseline bench.py times) against the golden outputs of the unmodified reference:
+    pairs and ROI gather bit-exact, logits within summation-order noise."""
+    import torch
+    from oracle import torch_port as TP
+    c = CASES[name]
+    g = load_golden(name)
+    batch = case_batch(c)
+    sd = TP.to_torch(case_state(c))
+    boxes = [torch.from_numpy(b) for b in batch["boxes"]]
+    scores = [torch.from_numpy(s) for s in batch["pred_scores"]] if "pred_scores" in batch else None
+    with torch.no_grad():
+        pairs = TP.prepare_test_pairs(batch["n_boxes"], c.get("max_pairs", 2048), scores)
+        assert [len(p) for p in pairs] == list(g["pair_counts"])
+        if "max_pairs" not in c:
+            assert np.array_equal(torch.cat(pairs).numpy(), g["pairs"])
+        pairs = [torch.from_numpy(p) for p in np.split(g["pairs"], np.cumsum(g["pair_counts"])[:-1])]
+        x2d, d2d = TP.pooler_forward([torch.from_numpy(f) for f in batch["feats"]], torch.from_numpy(batch["depth"]), boxes)
+        assert np.array_equal(x2d.numpy()[:, ::16], g["x2d_sub"]) and np.array_equal(d2d.numpy()[:, ::16], g["d2d_sub"])
+        logits = TP.predictor_forward(sd, boxes, pairs, x2d, d2d, c["mode"],
+                                      labels=[torch.from_numpy(l) for l in batch["labels"]],
+                                      predict_logits=[torch.from_numpy(l) for l in batch.get("predict_logits", [])] or None)
+    ref = g["logits"]
+    assert np.abs(logits.numpy() - ref).max() <= REL_TOL * np.abs(ref).max()
+    assert np.array_equal(logits.numpy().argmax(1), ref.argmax(1))

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "stages.cuh"
 
 namespace veto {
@@ -21,7 +23,28 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     set_error("%s: %s (%s) at %s:%d", what, cudaGetErrorString(e), cudaGetErrorName(e), file, line);
     return VETO_ERR_CUDA;
 }
-void count_launch(int n) { g_launches += n; }
+
+// per-stage event timing (veto_profile_begin / _end)
+struct ProfEvent { cudaEvent_t ev; int tag; };
+static thread_local bool g_prof = false;
+static thread_local cudaStream_t g_prof_stream = nullptr;
+static thread_local std::vector<ProfEvent> g_prof_events;
+static thread_local int g_tag = 0;
+static const char* kTagNames[VETO_PROFILE_TAGS] = {"other", "pairs", "roi_gather", "box_stage", "tokens", "layernorm",
+                                                   "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
+                                                   "classifier", "postprocess", "pack", "", ""};
+
+void set_tag(int tag) { g_tag = tag; }
+void count_launch(int n) {
+    g_launches += n;
+    if (g_prof) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            cudaEventRecord(e, g_prof_stream);
+            g_prof_events.push_back({e, g_tag});
+        }
+    }
+}
 
 int num_sms() {
     static int n = 0;
@@ -125,7 +148,7 @@ size_t act_bytes(int precision, size_t elems) {
     return elems * sizeof(__nv_bfloat16);
 }
 
-constexpr int32_t kDefaultChunk = 512;
+constexpr int32_t kDefaultChunk = 2048;  // measured on B200: larger chunks win (fewer, fuller waves per launch)
 
 WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
     WorkLayout W{};
@@ -215,6 +238,7 @@ extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, 
                  L.total);
     cudaStream_t s = (cudaStream_t)stream;
     char* P = (char*)packed_dev;
+    set_tag(TAG_PACK);
     if ((rc = pack_halves(w->loc_proj_w, (float*)(P + L.w_loc2), kDim, kPosDim, s))) return rc;
     if ((rc = pack_bias2(w->loc_proj_b, (float*)(P + L.b_loc2), kDim, s))) return rc;
     if ((rc = pack_halves(w->class_proj_w, (float*)(P + L.w_cls2), kDim, kEmbDim, s))) return rc;
@@ -249,7 +273,6 @@ extern "C" size_t veto_workspace_bytes(const veto_config* cfg, int32_t n_boxes, 
 extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights* w, const void* packed_dev,
                                      const veto_inputs* in, const veto_outputs* out, void* workspace_dev,
                                      size_t workspace_bytes, int32_t chunk_pairs, veto_stream_t stream) {
-    g_launches = 0;
     int rc = check_config(cfg);
     if (rc) return rc;
     VETO_REQUIRE(w && packed_dev && in && out && workspace_dev, VETO_ERR_ARG, "veto_relation_forward: NULL argument");
@@ -277,6 +300,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
     float* cso = (float*)(B + W.cso);
     float* so_d = (float*)(B + W.so_d);
     float* so_v = (float*)(B + W.so_v);
+    set_tag(TAG_BOX);
     if ((rc = box_embed(in->boxes, in->labels, in->obj_logits, cfg->num_obj, N, *w, pos, emb, s))) return rc;
     {
         GemmEpilogue ep;
@@ -315,18 +339,22 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
         const int M = (int)(rc_pairs * kTokens);
         ActBuf xn = act_at(B, W.xn, prec, (size_t)M * kDim);
         ActBuf hb = act_at(B, W.h, prec, (size_t)M * kMlp);
+        set_tag(TAG_TOKENS);
         if ((rc = build_tokens(ts, in->subj + r0, in->obj + r0, rc_pairs, x, s))) return rc;
         if (out->tokens)
             VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
                                       cudaMemcpyDeviceToDevice, s));
         for (int l = 0; l < cfg->layers; ++l) {
             // x = to_out(softmax(q k^T * scale) v) + x      (PreNorm + Attention, model_veto.py:18-19,86-96)
+            set_tag(TAG_LN);
             if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
             GemmEpilogue e1;
             e1.out.f32 = qkv;
             e1.ldc = 3 * kDim;
             WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+            set_tag(TAG_QKV);
             if ((rc = linear(prec, xn, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
+            set_tag(TAG_ATT);
             if ((rc = attention_seq(qkv, rc_pairs, xn.out(), s))) return rc;
             GemmEpilogue e2;
             e2.bias = w->out_b[l];
@@ -334,8 +362,10 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             e2.out.f32 = x;
             e2.ldc = kDim;
             WRef wo{w->out_w[l], bf(P, L.out_hi[l]), bf(P, L.out_lo[l])};
+            set_tag(TAG_OUT);
             if ((rc = linear(prec, xn, kDim, wo, M, kDim, kDim, e2, s))) return rc;
             // x = W2 gelu(W1 LN(x) + b1) + b2 + x           (PreNorm + FeedForward, model_veto.py:20,134-146)
+            set_tag(TAG_LN);
             if ((rc = layernorm_rows(x, kDim, w->ln2_w[l], w->ln2_b[l], M, xn.out(), s))) return rc;
             GemmEpilogue e3;
             e3.bias = w->ff1_b[l];
@@ -343,6 +373,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             e3.out = hb.out();
             e3.ldc = kMlp;
             WRef w1{w->ff1_w[l], bf(P, L.ff1_hi[l]), bf(P, L.ff1_lo[l])};
+            set_tag(TAG_FF1);
             if ((rc = linear(prec, xn, kDim, w1, M, kMlp, kDim, e3, s))) return rc;
             GemmEpilogue e4;
             e4.bias = w->ff2_b[l];
@@ -350,6 +381,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             e4.out.f32 = x;
             e4.ldc = kDim;
             WRef w2{w->ff2_w[l], bf(P, L.ff2_hi[l]), bf(P, L.ff2_lo[l])};
+            set_tag(TAG_FF2);
             if ((rc = linear(prec, hb, kMlp, w2, M, kDim, kMlp, e4, s))) return rc;
         }
         // rel_out on the CLS row x[:,0] (model_veto.py:25; roi_relation_predictors.py:4125): always fp32 FMA
@@ -357,18 +389,53 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
         ec.bias = w->rel_out_b;
         ec.out.f32 = out->rel_logits + (size_t)r0 * cfg->num_out;
         ec.ldc = cfg->num_out;
+        set_tag(TAG_CLS);
         if ((rc = gemm_simt(x, kTokens * kDim, w->rel_out_w, (int)rc_pairs, cfg->num_out, kDim, ec, s))) return rc;
         if (out->rel_features)
             VETO_CUDA(cudaMemcpy2DAsync(out->rel_features + (size_t)r0 * kDim, sizeof(float) * kDim, x,
                                         sizeof(float) * kTokens * kDim, sizeof(float) * kDim, (size_t)rc_pairs,
                                         cudaMemcpyDeviceToDevice, s));
     }
+    set_tag(TAG_OTHER);
     if (in->freq_bias)
         if ((rc = add_freq_bias(out->rel_logits, cfg->num_out, in->freq_bias, in->labels, cfg->num_obj, in->subj, in->obj,
                                 in->n_pairs, s)))
             return rc;
     return VETO_OK;
 }
+
+extern "C" int veto_profile_begin(veto_stream_t stream) {
+    VETO_REQUIRE(!g_prof, VETO_ERR_ARG, "veto_profile_begin: already profiling");
+    g_prof_stream = (cudaStream_t)stream;
+    g_prof_events.clear();
+    cudaEvent_t e;
+    VETO_CUDA(cudaEventCreate(&e));
+    VETO_CUDA(cudaEventRecord(e, g_prof_stream));
+    g_prof_events.push_back({e, -1});
+    g_prof = true;
+    return VETO_OK;
+}
+
+extern "C" int veto_profile_end(double* ms_by_tag_host, int64_t* launches_by_tag_host) {
+    VETO_REQUIRE(g_prof && ms_by_tag_host && launches_by_tag_host, VETO_ERR_ARG, "veto_profile_end: not profiling / NULL");
+    g_prof = false;
+    cudaError_t err = cudaEventSynchronize(g_prof_events.back().ev);
+    for (size_t i = 1; i < g_prof_events.size() && err == cudaSuccess; ++i) {
+        float ms = 0.f;
+        err = cudaEventElapsedTime(&ms, g_prof_events[i - 1].ev, g_prof_events[i].ev);
+        const int t = g_prof_events[i].tag;
+        if (t >= 0 && t < VETO_PROFILE_TAGS) {
+            ms_by_tag_host[t] += ms;
+            launches_by_tag_host[t] += 1;
+        }
+    }
+    for (auto& pe : g_prof_events) cudaEventDestroy(pe.ev);
+    g_prof_events.clear();
+    VETO_CUDA(err);
+    return VETO_OK;
+}
+
+extern "C" const char* veto_profile_tag_name(int tag) { return (tag >= 0 && tag < VETO_PROFILE_TAGS) ? kTagNames[tag] : ""; }
 
 // ------------------------------------------------------------------------------------------ test hooks
 extern "C" int veto_test_gemm(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,

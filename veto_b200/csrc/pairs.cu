@@ -200,6 +200,7 @@ extern "C" int veto_pairs_enumerate(const int32_t* n_boxes_host, int n_images, c
                                     const float* scores_dev, int require_overlap, int max_pairs,
                                     int64_t* pairs_out_dev, int32_t* counts_out_dev, int32_t* scratch_dev,
                                     veto_stream_t stream) {
+    set_tag(TAG_PAIRS);
     cudaStream_t s = (cudaStream_t)stream;
     VETO_REQUIRE(n_boxes_host && pairs_out_dev && scratch_dev && n_images >= 0 && max_pairs > 0, VETO_ERR_ARG,
                  "veto_pairs_enumerate: bad argument");
@@ -269,6 +270,7 @@ extern "C" int veto_pairs_globalize(const int64_t* pairs_dev, int64_t n_pairs, c
                                     const int32_t* box_offsets_dev, int n_images, int32_t* subj_out_dev,
                                     int32_t* obj_out_dev, veto_stream_t stream) {
     if (n_pairs <= 0) return VETO_OK;
+    set_tag(TAG_PAIRS);
     VETO_REQUIRE(pairs_dev && rel_offsets_dev && box_offsets_dev && subj_out_dev && obj_out_dev && n_images > 0,
                  VETO_ERR_ARG, "veto_pairs_globalize: bad argument");
     const int64_t blocks = (n_pairs + 255) / 256;

@@ -120,6 +120,7 @@ extern "C" int veto_postprocess(const float* rel_logits_dev, int num_rel, const 
     VETO_REQUIRE(rel_logits_dev && pairs_dev && obj_scores_dev && rel_offsets_dev && box_offsets_dev && pairs_out_dev &&
                      probs_out_dev && labels_out_dev && triple_out_dev && num_rel >= 2 && num_rel < 65536,
                  VETO_ERR_ARG, "veto_postprocess: bad argument");
+    set_tag(TAG_POST);
     static bool attr_set = false;
     const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
     if (!attr_set) {

@@ -225,6 +225,7 @@ extern "C" int veto_roi_align_forward(const float* input_dev, int batch, int cha
                  VETO_ERR_UNSUPPORTED, "veto_roi_align_forward: needs sampling_ratio > 0 and ph*pw*sr^2 <= %d", kMaxTaps);
     int rc = ensure_attrs();
     if (rc) return rc;
+    set_tag(TAG_GATHER);
     const int slices = channel_slices(n_rois, channels);
     const int c_per = (channels + slices - 1) / slices;
     dim3 grid(n_rois, slices);
@@ -268,6 +269,7 @@ extern "C" int veto_roi_gather_forward(const float* const* feats_dev, const int3
                  VETO_ERR_UNSUPPORTED, "veto_roi_gather_forward: needs sampling_ratio > 0 and pool^2*sr^2 <= %d", kMaxTaps);
     int rc = ensure_attrs();
     if (rc) return rc;
+    set_tag(TAG_GATHER);
     GatherLevels lv{};
     for (int l = 0; l < n_levels; ++l) {
         VETO_REQUIRE(feats_dev[l] && feat_h[l] > 0 && feat_w[l] > 0, VETO_ERR_ARG, "veto_roi_gather_forward: bad level %d", l);

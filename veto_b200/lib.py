@@ -69,6 +69,9 @@ _PROTOS = {
     "veto_relation_forward": (c_int, [POINTER(VetoConfig), POINTER(VetoWeights), _fp, POINTER(VetoInputs),
                                       POINTER(VetoOutputs), _fp, c_size_t, c_int32, c_void_p]),
     "veto_last_launch_count": (c_int64, []),
+    "veto_profile_begin": (c_int, [c_void_p]),
+    "veto_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "veto_profile_tag_name": (c_char_p, [c_int]),
     "veto_postprocess": (c_int, [_fp, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp, _fp, _fp, c_void_p]),
     "veto_test_gemm": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_void_p]),
     "veto_test_layernorm": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_void_p]),

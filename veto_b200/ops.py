@@ -311,6 +311,32 @@ def postprocess(rel_logits: torch.Tensor, pairs: torch.Tensor, obj_scores: torch
 
 
 # --------------------------------------------------------------------------------------------
+# launch accounting / per-stage device timing (bench.py)
+# --------------------------------------------------------------------------------------------
+def launch_count() -> int:
+    """Kernel launches this thread has enqueued through the library so far."""
+    return int(L.load().veto_last_launch_count())
+
+
+class StageTimer:
+    """with StageTimer() as t: ...  -> t.ms[stage], t.launches[stage] (CUDA events around every library launch)."""
+    N_TAGS = 16
+
+    def __enter__(self):
+        L.check(L.load().veto_profile_begin(L.stream_ptr()), "veto_profile_begin")
+        return self
+
+    def __exit__(self, *exc):
+        ms = (ctypes.c_double * self.N_TAGS)()
+        n = (ctypes.c_int64 * self.N_TAGS)()
+        L.check(L.load().veto_profile_end(ms, n), "veto_profile_end")
+        names = [L.load().veto_profile_tag_name(i).decode() for i in range(self.N_TAGS)]
+        self.ms = {names[i]: float(ms[i]) for i in range(self.N_TAGS) if n[i]}
+        self.launches = {names[i]: int(n[i]) for i in range(self.N_TAGS) if n[i]}
+        return False
+
+
+# --------------------------------------------------------------------------------------------
 # test hooks
 # --------------------------------------------------------------------------------------------
 def test_gemm(a, w, bias=None, residual=None, act: int = 0, precision: str = "fp32"):
