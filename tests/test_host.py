@@ -1,0 +1,149 @@
+"""CPU tests of the host-side mirror of the reference's plugin interface (no GPU needed): registries, constructor
+contracts, state_dict keys, config handling, BoxList arithmetic, image sharding and the world_size-2 gloo path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import veto_b200
+from tests import harness as H
+from tests.cases import CASES, load_golden
+from veto_b200 import config as vcfg
+from veto_b200 import distributed as vdist
+from veto_b200 import registry, synth
+from veto_b200.structures import BoxList
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_names_and_selection():
+    preds, extractors = veto_b200.load_modules()
+    assert set(preds) == {"VETOPredictor", "VETOPredictor_MEET"}          # roi_relation_predictors.py:3997,3876
+    assert set(extractors) == {"VETOFeatureExtractor"}                    # roi_box_feature_extractors.py:75
+    cfg = vcfg.default_cfg()
+    assert type(registry.make_roi_relation_predictor(cfg, 512)).__name__ == "VETOPredictor"
+    cfg.MODEL.ROI_RELATION_HEAD.PREDICTOR = "VETOPredictor_MEET"
+    assert type(registry.make_roi_relation_predictor(cfg, 512)).__name__ == "VETOPredictor_MEET"
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True)
+    assert fe.out_channels == 256 and (fe.k_min, fe.k_max) == (2, 5) and fe.depth_scale == 0.0625
+    with pytest.raises(AssertionError):                                    # utils/registry.py:4-6 semantics
+        registry.ROI_RELATION_PREDICTOR.register("VETOPredictor", object)
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    """Keys and shapes are those of the reference modules, so reference checkpoints load strictly."""
+    cfg = vcfg.default_cfg()
+    p = registry.make_roi_relation_predictor(cfg, 512)
+    sd = synth.predictor_state(3)
+    assert set(p.state_dict()) == set(sd)
+    p.load_state_dict(synth.to_torch_state(sd), strict=True)
+    assert sum(v.numel() for v in p.parameters()) == 17_608_299            # SURVEY.md §6 probe: 17.608 M
+    for ds, gs, n_obj in (("VG", [4, 6, 9, 19, 12], 151), ("GQA", [5, 10, 20, 65], 201)):
+        cfg = H.make_cfg("VETOPredictor_MEET", dataset=ds)
+        m = registry.make_roi_relation_predictor(cfg, 512)
+        sd = synth.meet_state(4, n_obj, gs)
+        assert set(m.state_dict()) == set(sd)
+        m.load_state_dict(synth.to_torch_state(sd), strict=True)
+        assert [h.out_features for h in m.model.rel_out] == [n + 2 for n in gs]
+        assert m.incre_idx_list == list(load_golden("meet_gqa" if ds == "GQA" else "meet_vg")["incre_idx_list"])
+    cfg = H.make_cfg("VETOPredictor_MEET")
+    cfg.ENSEMBLE_LEARNING.EXPERT_GROUP = True                              # defaults.py:864: 3 experts per group
+    m = registry.make_roi_relation_predictor(cfg, 512)
+    sd = synth.meet_state(5, 151, [4, 6, 9, 19, 12], experts_per_group=3, expert_group=True)
+    assert set(m.state_dict()) == set(sd)
+    assert [k for k, _ in m.model._head_sets()][:6] == ["group_01", "group_11", "group_21", "group_31", "group_41", "group_02"]
+
+
+def test_unsupported_architecture_is_refused():
+    cfg = vcfg.default_cfg()
+    cfg.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER.T_INPUT_DIM = 512
+    with pytest.raises(RuntimeError, match="576"):
+        registry.make_roi_relation_predictor(cfg, 512)
+    cfg = vcfg.default_cfg()
+    cfg.GLOBAL_SETTING.BETA_LOSS = True
+    with pytest.raises(NotImplementedError):
+        registry.make_roi_relation_predictor(cfg, 512)
+
+
+def test_boxlist_conventions():
+    b = BoxList(torch.tensor([[10., 20., 49., 79.]]), (800, 592))
+    assert b.convert("xywh").bbox.tolist() == [[10., 20., 40., 60.]]        # +1 (bounding_box.py:72-75)
+    assert b.area().tolist() == [2400.]                                     # +1 (bounding_box.py:249-253)
+    assert b.convert("xywh").convert("xyxy").bbox.tolist() == b.bbox.tolist()
+    b.add_field("labels", torch.tensor([3]))
+    assert b.has_field("labels") and b.fields() == ["labels"] and len(b) == 1
+    with pytest.raises(ValueError):
+        BoxList(torch.zeros(3), (1, 1))
+
+
+def test_config_defaults_follow_veto_final_yaml():
+    cfg = vcfg.default_cfg()
+    t = cfg.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER
+    assert (t.PATCH_SIZE, t.T_INPUT_DIM, t.ENC_LAYERS, t.NHEADS) == (2, 576, 6, 6)
+    assert cfg.MODEL.ROI_RELATION_HEAD.POOLER_RESOLUTION == 8 and cfg.MODEL.ROI_RELATION_HEAD.MAX_PROPOSAL_PAIR == 2048
+    assert vcfg.num_classes(cfg) == (151, 51)
+    cfg.GLOBAL_SETTING.DATASET_CHOICE = "GQA"
+    assert vcfg.num_classes(cfg) == (201, 101)
+    assert vcfg.get(cfg, "VETO_B200.PRECISION") == "bf16x3" and vcfg.get(cfg, "NOT.THERE", 7) == 7
+    with pytest.raises(KeyError):
+        cfg.merge_from_list(["MODEL.NOPE", 1])
+    assert vcfg.GROUP_SPLITS[("VG", "divide4")] == synth.GROUP_SPLITS[("VG", "divide4")]
+
+
+def test_image_sharding_balances_pairs():
+    n_boxes = [20] * 48 + [80] * 48                                          # BASELINE.json configs[4]
+    for world in (1, 2, 4, 8):
+        shards = vdist.shard_images(n_boxes, world)
+        assert sorted(i for s in shards for i in s) == list(range(96))
+        load = [sum(n_boxes[i] * (n_boxes[i] - 1) for i in s) for s in shards]
+        assert max(load) - min(load) <= 80 * 79
+    assert vdist.shard_images([5, 1, 0], 2) == [[0], [1, 2]]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from veto_b200 import distributed as vdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+n_boxes = [3, 9, 4, 2, 7]
+mine = vdist.shard_images(n_boxes, 2)[rank]
+# stand-in for the per-image results of this rank: one row per pair, tagged with (image, pair index)
+rows = torch.tensor([[i, r] for i in mine for r in range(n_boxes[i] * (n_boxes[i] - 1))], dtype=torch.int64).reshape(-1, 2)
+parts = vdist.gather_rows(rows)
+allrows = torch.cat(parts)
+assert allrows.shape[0] == sum(n * (n - 1) for n in n_boxes), allrows.shape
+assert sorted(set(allrows[:, 0].tolist())) == list(range(5))
+t = vdist.max_over_ranks(1.0 + rank, "cpu")
+assert t == 2.0
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding_and_gather(tmp_path):
+    """The N>1 host path on CPU: world_size 2 over gloo (127.0.0.1), image sharding + fixed-layout result gather."""
+    script = tmp_path / "worker.py"
+    port = 29600 + os.getpid() % 200
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints one JSON line with the contract keys (a tiny sample keeps this fast)."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-pairs", "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]

@@ -153,6 +153,186 @@ attention_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, _
     }
 }
 
+
+// ---------------------------------------------------------------- attention on the tensor cores (mma.sync)
+// One warp per (sequence, head).  S = Q K^T (19x19, padded to 32x24) and O = P V (19x96) run as m16n8k16 bf16
+// warp MMAs with fp32 accumulation; with SPLIT every fp32 operand is split into bf16 hi + lo and each product
+// takes three MMAs (hi*hi + lo*hi + hi*lo), which keeps ~16 mantissa bits — the same scheme as the GEMMs.
+// Fragments are loaded straight from global memory in MMA layout (float2 / 32-byte row segments, every sector
+// fully used); the softmax runs on the accumulator registers (a row lives in the 4 lanes of a quad) and P is
+// re-used from registers as the A operand of the second product, flash-attention style.  No shared memory.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// (x0, x1) -> packed bf16 hi pair and lo pair (lo = x - float(hi))
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, __nv_bfloat16* out_hi,
+                     __nv_bfloat16* out_lo) {
+    constexpr int LD = 3 * kDim;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float scale = 0.10206207261596575f;  // 96 ** -0.5 (model_veto.py:74)
+    const int64_t items = n_seq * kHeads;
+    for (int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); item < items; item += (int64_t)gridDim.x * 8) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
+        auto ld2 = [&](int row, int col, int which) -> float2 {  // which: 0 q, 1 k, 2 v
+            return (row < kTokens) ? __ldg((const float2*)(base + (size_t)row * LD + which * kDim + col)) : make_float2(0.f, 0.f);
+        };
+
+        // ---- S = Q K^T : 2 m-tiles (rows 16mt+g, +8) x 3 n-tiles (keys 8nt+g)
+        float S[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) S[mt][nt][e] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < kHeadDim / 16; ++ks) {
+            const int d0 = ks * 16 + 2 * t;
+            uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float2 x0 = ld2(16 * mt + g, d0, 0), x1 = ld2(16 * mt + g + 8, d0, 0);
+                const float2 x2 = ld2(16 * mt + g, d0 + 8, 0), x3 = ld2(16 * mt + g + 8, d0 + 8, 0);
+                split_pair(x0.x, x0.y, qh[mt][0], ql[mt][0]);
+                split_pair(x1.x, x1.y, qh[mt][1], ql[mt][1]);
+                split_pair(x2.x, x2.y, qh[mt][2], ql[mt][2]);
+                split_pair(x3.x, x3.y, qh[mt][3], ql[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const float2 y0 = ld2(8 * nt + g, d0, 1), y1 = ld2(8 * nt + g, d0 + 8, 1);
+                uint32_t kh[2], kl[2];
+                split_pair(y0.x, y0.y, kh[0], kl[0]);
+                split_pair(y1.x, y1.y, kh[1], kl[1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_bf16_16816(S[mt][nt], qh[mt], kh);
+                    if (SPLIT) {
+                        mma_bf16_16816(S[mt][nt], ql[mt], kh);
+                        mma_bf16_16816(S[mt][nt], qh[mt], kl);
+                    }
+                }
+            }
+        }
+
+        // ---- softmax over the 19 keys of each row (a row = the 4 lanes of a quad; e 0,1 -> row g, e 2,3 -> row g+8)
+        uint32_t ph[2][2][4], pl[2][2][4];  // [mt][ks2][a-fragment]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * nt + 2 * t + e;
+                        float v = S[mt][nt][2 * hrow + e] * scale;
+                        v = (col < kTokens) ? v : -INFINITY;
+                        S[mt][nt][2 * hrow + e] = v;
+                        m = fmaxf(m, v);
+                    }
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                float sum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = expf(S[mt][nt][2 * hrow + e] - m);  // exp(-inf) = 0 for the padding keys
+                        S[mt][nt][2 * hrow + e] = p;
+                        sum += p;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) S[mt][nt][2 * hrow + e] *= inv;
+            }
+            // P as A fragments of the second product: k-step ks2 covers keys 16ks2..16ks2+15 = n-tiles 2ks2, 2ks2+1
+#pragma unroll
+            for (int ks2 = 0; ks2 < 2; ++ks2) {
+                split_pair(S[mt][2 * ks2][0], S[mt][2 * ks2][1], ph[mt][ks2][0], pl[mt][ks2][0]);
+                split_pair(S[mt][2 * ks2][2], S[mt][2 * ks2][3], ph[mt][ks2][1], pl[mt][ks2][1]);
+                split_pair(S[mt][2 * ks2 + 1][0], S[mt][2 * ks2 + 1][1], ph[mt][ks2][2], pl[mt][ks2][2]);  // n-tile 3 is all zero
+                split_pair(S[mt][2 * ks2 + 1][2], S[mt][2 * ks2 + 1][3], ph[mt][ks2][3], pl[mt][ks2][3]);
+            }
+        }
+
+        // ---- O = P V : 12 n-tiles of 8 head dims, 2 k-steps of 16 keys; 4 n-tiles at a time to bound registers
+        auto ldv = [&](int key, int d) -> float {
+            return (key < kTokens) ? __ldg(base + (size_t)key * LD + 2 * kDim + d) : 0.f;
+        };
+#pragma unroll 1
+        for (int nb = 0; nb < 3; ++nb) {
+            float O[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) O[mt][j][e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = 8 * (4 * nb + j) + g;
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ++ks2) {
+                    const int k0 = 16 * ks2 + 2 * t;
+                    uint32_t vh[2], vl[2];
+                    split_pair(ldv(k0, d), ldv(k0 + 1, d), vh[0], vl[0]);
+                    split_pair(ldv(k0 + 8, d), ldv(k0 + 9, d), vh[1], vl[1]);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma_bf16_16816(O[mt][j], ph[mt][ks2], vh);
+                        if (SPLIT) {
+                            mma_bf16_16816(O[mt][j], pl[mt][ks2], vh);
+                            mma_bf16_16816(O[mt][j], ph[mt][ks2], vl);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int row = 16 * mt + g + 8 * hrow;
+                    if (row < kTokens) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v0 = O[mt][j][2 * hrow], v1 = O[mt][j][2 * hrow + 1];
+                            const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 8 * (4 * nb + j) + 2 * t;
+                            if (out_f32) *(float2*)(out_f32 + o) = make_float2(v0, v1);
+                            if (out_hi) {
+                                uint32_t hh, ll;
+                                split_pair(v0, v1, hh, ll);
+                                *(uint32_t*)(out_hi + o) = hh;
+                                if (out_lo) *(uint32_t*)(out_lo + o) = ll;
+                            }
+                        }
+                    }
+                }
+        }
+    }
+}
+
 }  // namespace
 
 int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, int64_t rows, const ActOut& out,
@@ -169,6 +349,15 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
 
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
+    if (out.hi) {  // tensor-core modes: bf16x3 (hi + lo outputs) or single-pass bf16 (hi only)
+        const int64_t blocks = (n_seq * kHeads + 7) / 8;
+        const int64_t capb = (int64_t)num_sms() * 8;
+        const int gridb = (int)(blocks < capb ? blocks : capb);
+        if (out.lo) attention_mma_kernel<true><<<gridb, 256, 0, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+        else attention_mma_kernel<false><<<gridb, 256, 0, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+        VETO_LAUNCH_CHECK();
+        return VETO_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         VETO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));

@@ -24,8 +24,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B: one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;                       // two per TMEM lane quarter, alternating column chunks
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
+constexpr int EPI_COLS = 16;                           // columns per epilogue chunk (one tcgen05.ld x16)
+constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;     // per-warp transpose buffer: 32 rows x 16 fp32
 
 template <int BLOCK_N>
 struct TileCfg {
@@ -34,7 +36,10 @@ struct TileCfg {
     static constexpr int kStageBytes = kBytesA + kBytesB;
     static constexpr int kStages = (BLOCK_N > 128) ? 5 : 6;
     static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert((BLOCK_N / EPI_COLS) % 2 == 0, "column chunks must split evenly over the two warps of a quarter");
 };
 
 // ------------------------------------------------------------------------------------------
@@ -109,15 +114,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
@@ -157,7 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::kStages * C::kBytesA;
-    uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+    uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // per-epilogue-warp transpose buffers
+    uint64_t* bars = (uint64_t*)(smem_epi + C::kEpiBytes);
     uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
     uint64_t* empty_bar = bars + C::kStages;      // [kStages]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * C::kStages;  // [2]        MMA -> epilogue
@@ -257,51 +260,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        // Warp w drains TMEM lanes [32q, 32q+32), q = w % 4 (the lane quarter a warp may touch), and the column
+        // chunks c = half, half+2, ... of the tile (half = (w-4)/4).  A chunk of 16 accumulator columns arrives with
+        // one row per thread; it is transposed through a swizzled 2 KB shared buffer so that the global accesses
+        // (residual read, fp32 / bf16 stores) are row-contiguous: lane L handles rows 8*rr + L/4 (rr = 0..3) and the
+        // float4 column group L % 4, i.e. every instruction covers 8 rows x 64 contiguous bytes.  The residual of the
+        // next chunk is prefetched while the current one is processed.
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        float4* stage4 = reinterpret_cast<float4*>(smem_epi + (warp - 4) * EPI_STAGE_BYTES);
+        const int rsub = lane >> 2, cg = lane & 3;
+        constexpr int kChunks = BLOCK_N / EPI_COLS;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * BLOCK_M;
+            const int m0 = (tile / num_n) * BLOCK_M + q * 32;
             const int n0 = (tile % num_n) * BLOCK_N;
-            const int row = m0 + ew * 32 + lane;
+            float4 res[4], res_next[4];
+            auto load_res = [&](int c, float4 (&dst)[4]) {
+                const int col = n0 + c * EPI_COLS + cg * 4;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int row = m0 + rr * 8 + rsub;
+                    dst[rr] = (ep.residual && row < M && col < N)
+                                  ? *(const float4*)(ep.residual + (size_t)row * ep.ldc + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            load_res(half, res_next);  // does not depend on the accumulator: overlaps the MMA of this tile
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                if (row < M && col0 < N) {
-                    const size_t off = (size_t)row * ep.ldc + col0;
+            for (int c = half; c < kChunks; c += 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col0 + j < N) {  // N % 4 == 0 is enforced by the host
-                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                            if (ep.bias) {
-                                const float4 b = __ldg((const float4*)(ep.bias + col0 + j));
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            v.x = apply_act(v.x, ep.act); v.y = apply_act(v.y, ep.act);
-                            v.z = apply_act(v.z, ep.act); v.w = apply_act(v.w, ep.act);
-                            if (ep.residual) {
-                                const float4 q = *(const float4*)(ep.residual + off + j);
-                                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-                            }
-                            if (ep.out_f32) *(float4*)(ep.out_f32 + off + j) = v;
-                            if (ep.out_hi) {
-                                __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                                split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
-                                split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-                                *(uint2*)(ep.out_hi + off + j) = pack_bf16x4(h0, h1, h2, h3);
-                                if (ep.out_lo) *(uint2*)(ep.out_lo + off + j) = pack_bf16x4(l0, l1, l2, l3);
-                            }
+                for (int rr = 0; rr < 4; ++rr) res[rr] = res_next[rr];
+                if (c + 2 < kChunks) load_res(c + 2, res_next);
+                uint32_t r[16];
+                tmem_ld16(taddr + c * EPI_COLS, r);
+                tmem_ld_wait();
+                // row `lane` -> 4 float4, XOR-swizzled by (row >> 1) & 3: conflict-free both ways
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    stage4[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                __syncwarp();
+                const int col = n0 + c * EPI_COLS + cg * 4;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias && col < N) bias4 = __ldg((const float4*)(ep.bias + col));
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int lr = rr * 8 + rsub;
+                    float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
+                    const int row = m0 + lr;
+                    if (row < M && col < N) {  // N % 4 == 0 is enforced by the host
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        v.x = apply_act(v.x, ep.act); v.y = apply_act(v.y, ep.act);
+                        v.z = apply_act(v.z, ep.act); v.w = apply_act(v.w, ep.act);
+                        v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
+                        const size_t off = (size_t)row * ep.ldc + col;
+                        if (ep.out_f32) *(float4*)(ep.out_f32 + off) = v;
+                        if (ep.out_hi) {
+                            __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                            split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+                            split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+                            *(uint2*)(ep.out_hi + off) = pack_bf16x4(h0, h1, h2, h3);
+                            if (ep.out_lo) *(uint2*)(ep.out_lo + off) = pack_bf16x4(l0, l1, l2, l3);
                         }
                     }
                 }
+                __syncwarp();  // the transpose buffer is reused by the next chunk
             }
             tc_fence_before();
             __syncwarp();
