@@ -193,6 +193,30 @@ def stage_speed(precision):
                tflops_ref=R * 648.7e6 / ms / 1e9, launches=ops.last_launch_count)
 
 
+def stage_stages(precision):
+    """Per-stage device time (CUDA events around every library launch) of the relation head on an SGDet-shaped batch."""
+    n_img, n_box = (int(os.environ.get("DIAG_IMAGES", 8)), int(os.environ.get("DIAG_BOXES", 80)))
+    batch = synth.make_batch(7, [n_box] * n_img, features=False)
+    from tests import harness as H
+    cfg = H.make_cfg(precision=precision, max_pairs=8192, chunk_pairs=int(os.environ.get("DIAG_CHUNK", 0)))
+    pred = H.build_predictor(cfg, synth.predictor_state(11), DEV)
+    bls = H.boxlists(batch, DEV, 151)
+    N = n_img * n_box
+    x2d = torch.randn(N, 256, 8, 8, device=DEV)
+    d2d = torch.relu(torch.randn(N, 256, 8, 8, device=DEV))
+    pairs = ops.enumerate_pairs(batch["n_boxes"], DEV, 8192)
+    R = sum(p.shape[0] for p in pairs)
+    with torch.no_grad():
+        for _ in range(2):
+            pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)
+        torch.cuda.synchronize()
+        with ops.StageTimer() as st:
+            pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)
+    tot = sum(st.ms.values())
+    report("stages", precision=precision, pairs=R, total_ms=tot, us_per_pair=tot / R * 1e3,
+           ms={k: round(v, 3) for k, v in st.ms.items()}, launches=st.launches)
+
+
 if __name__ == "__main__":
     L.require_device()
     for arg in sys.argv[1:]:

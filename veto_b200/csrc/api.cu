@@ -137,7 +137,7 @@ struct ActBuf {
 
 struct WorkLayout {
     size_t pos, emb, lso, cso, pa_d, pa_v, so_d, so_v;  // box level
-    size_t x, xn, qkv, h;                               // chunk level
+    size_t x, xn, qkv, h, q_cls, x_cls;                 // chunk level
     size_t total;
     int32_t chunk;
 };
@@ -171,6 +171,8 @@ WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, i
     W.xn = k.take(act_bytes(c.precision, M * kDim));
     W.qkv = k.take(sizeof(float) * M * 3 * kDim);
     W.h = k.take(act_bytes(c.precision, M * kMlp));
+    W.q_cls = k.take(sizeof(float) * (size_t)chunk * kDim);
+    W.x_cls = k.take(sizeof(float) * (size_t)chunk * kDim);
     W.total = k.off;
     return W;
 }
@@ -195,9 +197,9 @@ struct WRef {  // a Linear weight in the forms the two GEMM paths need
 int linear(int precision, const ActBuf& a, int lda, const WRef& w, int M, int N, int K, const GemmEpilogue& ep,
            cudaStream_t s) {
     if (precision == VETO_PREC_FP32) return gemm_simt(a.f32, lda, w.f32, M, N, K, ep, s);
-    VETO_REQUIRE(lda == K, VETO_ERR_ARG, "tensor-core GEMM needs a dense A (lda == K)");
     GemmOperand A, W;
     A.hi = a.hi; A.lo = a.lo;
+    A.ld = lda;
     W.hi = w.hi; W.lo = w.lo;
     return gemm_tc(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
 }
@@ -344,7 +346,8 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
         if (out->tokens)
             VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
                                       cudaMemcpyDeviceToDevice, s));
-        for (int l = 0; l < cfg->layers; ++l) {
+        const int R = (int)rc_pairs;
+        for (int l = 0; l + 1 < cfg->layers; ++l) {
             // x = to_out(softmax(q k^T * scale) v) + x      (PreNorm + Attention, model_veto.py:18-19,86-96)
             set_tag(TAG_LN);
             if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
@@ -384,17 +387,71 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             set_tag(TAG_FF2);
             if ((rc = linear(prec, hb, kMlp, w2, M, kDim, kMlp, e4, s))) return rc;
         }
-        // rel_out on the CLS row x[:,0] (model_veto.py:25; roi_relation_predictors.py:4125): always fp32 FMA
-        GemmEpilogue ec;
-        ec.bias = w->rel_out_b;
-        ec.out.f32 = out->rel_logits + (size_t)r0 * cfg->num_out;
-        ec.ldc = cfg->num_out;
-        set_tag(TAG_CLS);
-        if ((rc = gemm_simt(x, kTokens * kDim, w->rel_out_w, (int)rc_pairs, cfg->num_out, kDim, ec, s))) return rc;
-        if (out->rel_features)
-            VETO_CUDA(cudaMemcpy2DAsync(out->rel_features + (size_t)r0 * kDim, sizeof(float) * kDim, x,
-                                        sizeof(float) * kTokens * kDim, sizeof(float) * kDim, (size_t)rc_pairs,
-                                        cudaMemcpyDeviceToDevice, s));
+        {
+            // Last layer: only x[:,0] leaves the encoder (model_veto.py:25), so only the CLS row needs a query, an
+            // attention output, the out-projection and the feed-forward; K and V still need every token.  The CLS
+            // rows are addressed in place with a row stride of 19*576 (TMA tensor map / lda), results stay compact.
+            const int l = cfg->layers - 1;
+            const size_t woff = (size_t)kDim * kDim;  // rows [576, 1728) of to_qkv.weight = K and V projections
+            float* q_cls = (float*)(B + W.q_cls);
+            float* x_cls = (float*)(B + W.x_cls);
+            set_tag(TAG_LN);
+            if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
+            GemmEpilogue e1;
+            e1.out.f32 = qkv + kDim;
+            e1.ldc = 3 * kDim;
+            WRef wkv{w->qkv_w[l] + woff, bf(P, L.qkv_hi[l]) ? bf(P, L.qkv_hi[l]) + woff : nullptr,
+                     bf(P, L.qkv_lo[l]) ? bf(P, L.qkv_lo[l]) + woff : nullptr};
+            set_tag(TAG_QKV);
+            if ((rc = linear(prec, xn, kDim, wkv, M, 2 * kDim, kDim, e1, s))) return rc;
+            GemmEpilogue eq;
+            eq.out.f32 = q_cls;
+            eq.ldc = kDim;
+            WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+            if ((rc = linear(prec, xn, kTokens * kDim, wq, R, kDim, kDim, eq, s))) return rc;
+            ActBuf ao = act_at(B, W.xn, prec, (size_t)R * kDim);  // xn is free once K, V and q exist
+            set_tag(TAG_ATT);
+            if ((rc = attention_cls(q_cls, qkv, rc_pairs, ao.out(), s))) return rc;
+            GemmEpilogue e2;
+            e2.bias = w->out_b[l];
+            e2.residual = x;
+            e2.ldr = kTokens * kDim;
+            e2.out.f32 = x_cls;
+            e2.ldc = kDim;
+            WRef wo{w->out_w[l], bf(P, L.out_hi[l]), bf(P, L.out_lo[l])};
+            set_tag(TAG_OUT);
+            if ((rc = linear(prec, ao, kDim, wo, R, kDim, kDim, e2, s))) return rc;
+            ActBuf xn_cls = act_at(B, W.xn, prec, (size_t)R * kDim);
+            set_tag(TAG_LN);
+            if ((rc = layernorm_rows(x_cls, kDim, w->ln2_w[l], w->ln2_b[l], R, xn_cls.out(), s))) return rc;
+            ActBuf h_cls = act_at(B, W.h, prec, (size_t)R * kMlp);
+            GemmEpilogue e3;
+            e3.bias = w->ff1_b[l];
+            e3.act = ACT_GELU;
+            e3.out = h_cls.out();
+            e3.ldc = kMlp;
+            WRef w1{w->ff1_w[l], bf(P, L.ff1_hi[l]), bf(P, L.ff1_lo[l])};
+            set_tag(TAG_FF1);
+            if ((rc = linear(prec, xn_cls, kDim, w1, R, kMlp, kDim, e3, s))) return rc;
+            GemmEpilogue e4;
+            e4.bias = w->ff2_b[l];
+            e4.residual = x_cls;
+            e4.out.f32 = x_cls;
+            e4.ldc = kDim;
+            WRef w2{w->ff2_w[l], bf(P, L.ff2_hi[l]), bf(P, L.ff2_lo[l])};
+            set_tag(TAG_FF2);
+            if ((rc = linear(prec, h_cls, kMlp, w2, R, kDim, kMlp, e4, s))) return rc;
+            // rel_out on x[:,0] (model_veto.py:25; roi_relation_predictors.py:4125): always fp32 FMA
+            GemmEpilogue ec;
+            ec.bias = w->rel_out_b;
+            ec.out.f32 = out->rel_logits + (size_t)r0 * cfg->num_out;
+            ec.ldc = cfg->num_out;
+            set_tag(TAG_CLS);
+            if ((rc = gemm_simt(x_cls, kDim, w->rel_out_w, R, cfg->num_out, kDim, ec, s))) return rc;
+            if (out->rel_features)
+                VETO_CUDA(cudaMemcpyAsync(out->rel_features + (size_t)r0 * kDim, x_cls, sizeof(float) * (size_t)R * kDim,
+                                          cudaMemcpyDeviceToDevice, s));
+        }
     }
     set_tag(TAG_OTHER);
     if (in->freq_bias)

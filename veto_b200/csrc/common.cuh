@@ -87,10 +87,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 struct GemmEpilogue {
     const float* bias = nullptr;      // [N]
-    const float* residual = nullptr;  // [M, ldc] fp32 (may alias out.f32)
+    const float* residual = nullptr;  // [M, ldr] fp32 (may alias out.f32)
     int act = ACT_NONE;
     ActOut out;                       // any subset of f32 / hi / lo; row stride ldc
     int ldc = 0;
+    int ldr = 0;                      // residual row stride (0 = ldc)
 };
 
 // A operand of a GEMM: fp32 (SIMT path) or bf16 hi[/lo] (tensor-core path); W likewise.
@@ -98,11 +99,12 @@ struct GemmOperand {
     const float* f32 = nullptr;
     const __nv_bfloat16* hi = nullptr;
     const __nv_bfloat16* lo = nullptr;
+    int ld = 0;                       // row stride in elements (0 = K, dense)
 };
 
 // C[M,N] = epi(A[M,K] @ W[N,K]^T).  A row stride lda (elements), W row stride K.
 int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s);
-// passes = 1 (bf16) or 3 (bf16x3: hi*hi + lo*hi + hi*lo). Requires K % 64 == 0, N % 16 == 0, lda == K.
+// passes = 1 (bf16) or 3 (bf16x3: hi*hi + lo*hi + hi*lo). Requires K % 64 == 0, N % 4 == 0, A.ld % 8 == 0.
 int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
             const GemmEpilogue& ep, cudaStream_t s);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
@@ -112,6 +114,9 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
                    cudaStream_t s);
 // softmax(q k^T * 96^-0.5) v per (sequence, head); qkv fp32 [n_seq*19, 1728] -> out [n_seq*19, 576]
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
+// the same for the CLS query row only (last encoder layer: only x[:,0] is consumed, model_veto.py:25):
+// q_cls fp32 [n_seq, 576]; k, v from qkv [n_seq*19, 1728] cols 576..1727; out [n_seq, 576]
+int attention_cls(const float* q_cls, const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
 
 int num_sms();
 

@@ -177,20 +177,44 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// shared-memory staging of one (sequence, head): row strides chosen so that the fragment reads are conflict-free
+// (Q/K: 64-bit reads at [g][2t] need stride = 8 mod 32 words; V: 32-bit reads at [2t][g] need 2*stride = 8 mod 32)
+constexpr int ATT_QK_STRIDE = 104, ATT_V_STRIDE = 100;  // floats (416 B / 400 B: 16-byte aligned for cp.async)
+constexpr int ATT_ITEM_FLOATS = 2 * kTokens * ATT_QK_STRIDE + kTokens * ATT_V_STRIDE;
+constexpr int ATT_MMA_WARPS = 8;
+constexpr int ATT_MMA_SMEM = ATT_MMA_WARPS * ATT_ITEM_FLOATS * (int)sizeof(float);
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ATT_MMA_WARPS * 32)
 attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, __nv_bfloat16* out_hi,
                      __nv_bfloat16* out_lo) {
+    extern __shared__ float4 att_smem[];
     constexpr int LD = 3 * kDim;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* sQ = reinterpret_cast<float*>(att_smem) + (threadIdx.x >> 5) * ATT_ITEM_FLOATS;
+    float* sK = sQ + kTokens * ATT_QK_STRIDE;
+    float* sV = sK + kTokens * ATT_QK_STRIDE;
     const float scale = 0.10206207261596575f;  // 96 ** -0.5 (model_veto.py:74)
     const int64_t items = n_seq * kHeads;
-    for (int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); item < items; item += (int64_t)gridDim.x * 8) {
+    for (int64_t item = (int64_t)blockIdx.x * ATT_MMA_WARPS + (threadIdx.x >> 5); item < items;
+         item += (int64_t)gridDim.x * ATT_MMA_WARPS) {
         const int64_t seq = item / kHeads;
         const int h = (int)(item - seq * kHeads);
         const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
-        auto ld2 = [&](int row, int col, int which) -> float2 {  // which: 0 q, 1 k, 2 v
-            return (row < kTokens) ? __ldg((const float2*)(base + (size_t)row * LD + which * kDim + col)) : make_float2(0.f, 0.f);
+        // stage q, k, v of this (sequence, head): 57 rows of 384 B, 16-byte cp.async, fully coalesced
+        __syncwarp();
+        for (int idx = lane; idx < 3 * kTokens * (kHeadDim / 4); idx += 32) {
+            const int m = idx / (kHeadDim / 4), c = idx - m * (kHeadDim / 4);
+            const int which = m / kTokens, row = m - which * kTokens;
+            const float* src = base + (size_t)row * LD + which * kDim + c * 4;
+            float* dst = (which == 0 ? sQ + row * ATT_QK_STRIDE : which == 1 ? sK + row * ATT_QK_STRIDE : sV + row * ATT_V_STRIDE) + c * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        auto ld2 = [&](int row, int col, int which) -> float2 {  // which: 0 q, 1 k
+            return (row < kTokens) ? *(const float2*)((which == 0 ? sQ : sK) + row * ATT_QK_STRIDE + col) : make_float2(0.f, 0.f);
         };
 
         // ---- S = Q K^T : 2 m-tiles (rows 16mt+g, +8) x 3 n-tiles (keys 8nt+g)
@@ -278,9 +302,7 @@ attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f3
         }
 
         // ---- O = P V : 12 n-tiles of 8 head dims, 2 k-steps of 16 keys; 4 n-tiles at a time to bound registers
-        auto ldv = [&](int key, int d) -> float {
-            return (key < kTokens) ? __ldg(base + (size_t)key * LD + 2 * kDim + d) : 0.f;
-        };
+        auto ldv = [&](int key, int d) -> float { return (key < kTokens) ? sV[key * ATT_V_STRIDE + d] : 0.f; };
 #pragma unroll 1
         for (int nb = 0; nb < 3; ++nb) {
             float O[2][4][4];
@@ -333,6 +355,61 @@ attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f3
     }
 }
 
+
+// ---------------------------------------------------------------- CLS-only attention (last layer)
+// One warp per (sequence, head): lane j < 19 scores key j against the single CLS query, the softmax is a pair of
+// warp reductions, and lane L accumulates output dims L, L+32, L+64 with p_j broadcast by shuffle.
+__global__ void __launch_bounds__(256)
+attention_cls_kernel(const float* __restrict__ q_cls, const float* __restrict__ qkv, int64_t n_seq, float* out_f32,
+                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+    constexpr int LD = 3 * kDim;
+    const int lane = threadIdx.x & 31;
+    const float scale = 0.10206207261596575f;
+    const int64_t items = n_seq * kHeads;
+    for (int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); item < items; item += (int64_t)gridDim.x * 8) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const float4* q = (const float4*)(q_cls + (size_t)seq * kDim + h * kHeadDim);
+        const float* kbase = qkv + (size_t)seq * kTokens * LD + kDim + h * kHeadDim;
+        const float* vbase = kbase + kDim;
+        float s = 0.f;
+        if (lane < kTokens) {
+            const float4* kr = (const float4*)(kbase + (size_t)lane * LD);
+#pragma unroll 6
+            for (int c = 0; c < kHeadDim / 4; ++c) {
+                const float4 a = __ldg(q + c), b = __ldg(kr + c);
+                s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+            }
+        }
+        s = (lane < kTokens) ? s * scale : -INFINITY;
+        float m = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float p = expf(s - m);  // 0 for the padding lanes
+        const float inv = 1.f / warp_sum(p);
+        p *= inv;
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < kTokens; ++j) {
+            const float pj = __shfl_sync(0xffffffffu, p, j);
+            const float* vr = vbase + (size_t)j * LD + lane;
+            acc[0] = fmaf(pj, __ldg(vr), acc[0]);
+            acc[1] = fmaf(pj, __ldg(vr + 32), acc[1]);
+            acc[2] = fmaf(pj, __ldg(vr + 64), acc[2]);
+        }
+        const size_t o = (size_t)seq * kDim + h * kHeadDim + lane;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (out_f32) out_f32[o + 32 * k] = acc[k];
+            if (out_hi) {
+                __nv_bfloat16 hh, ll;
+                split_bf16(acc[k], hh, ll);
+                out_hi[o + 32 * k] = hh;
+                if (out_lo) out_lo[o + 32 * k] = ll;
+            }
+        }
+    }
+}
 }  // namespace
 
 int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, int64_t rows, const ActOut& out,
@@ -350,11 +427,17 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
     if (out.hi) {  // tensor-core modes: bf16x3 (hi + lo outputs) or single-pass bf16 (hi only)
-        const int64_t blocks = (n_seq * kHeads + 7) / 8;
-        const int64_t capb = (int64_t)num_sms() * 8;
+        static bool mma_attr_set = false;
+        if (!mma_attr_set) {
+            VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));
+            VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));
+            mma_attr_set = true;
+        }
+        const int64_t blocks = (n_seq * kHeads + ATT_MMA_WARPS - 1) / ATT_MMA_WARPS;
+        const int64_t capb = (int64_t)num_sms();  // one 187 KB CTA per SM
         const int gridb = (int)(blocks < capb ? blocks : capb);
-        if (out.lo) attention_mma_kernel<true><<<gridb, 256, 0, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
-        else attention_mma_kernel<false><<<gridb, 256, 0, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+        if (out.lo) attention_mma_kernel<true><<<gridb, ATT_MMA_WARPS * 32, ATT_MMA_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+        else attention_mma_kernel<false><<<gridb, ATT_MMA_WARPS * 32, ATT_MMA_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
         VETO_LAUNCH_CHECK();
         return VETO_OK;
     }
@@ -366,6 +449,15 @@ int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream
     const int64_t cap = (int64_t)num_sms() * 2;
     const int grid = (int)(n_seq < cap ? n_seq : cap);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int attention_cls(const float* q_cls, const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s) {
+    if (n_seq <= 0) return VETO_OK;
+    const int64_t blocks = (n_seq * kHeads + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    attention_cls_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(q_cls, qkv, n_seq, out.f32, out.hi, out.lo);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -15,7 +15,7 @@ constexpr int PAD = 4;
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int N, int K,
                  const float* __restrict__ bias, const float* residual, int act, float* out_f32,
-                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc) {
+                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc, int ldr) {
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
@@ -120,7 +120,7 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
                 if (c + j < N) {
                     if (bias) v[j] += __ldg(bias + c + j);
                     v[j] = apply_act(v[j], act);
-                    if (residual) v[j] += residual[off + j];
+                    if (residual) v[j] += residual[(size_t)r * ldr + c + j];
                 }
             }
             if (vec_out && c + 3 < N) {
@@ -158,7 +158,7 @@ int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, cons
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "gemm_simt: M=%d too large for one launch", M);
     gemm_simt_kernel<<<grid, 256, 0, s>>>(A, lda, W, M, N, K, ep.bias, ep.residual, ep.act, ep.out.f32, ep.out.hi,
-                                          ep.out.lo, ep.ldc);
+                                          ep.out.lo, ep.ldc, ep.ldr ? ep.ldr : ep.ldc);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

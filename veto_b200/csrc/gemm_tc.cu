@@ -146,6 +146,7 @@ struct EpiParams {
     __nv_bfloat16* out_lo;
     int act;
     int ldc;
+    int ldr;
 };
 
 template <int BLOCK_N>
@@ -284,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 for (int rr = 0; rr < 4; ++rr) {
                     const int row = m0 + rr * 8 + rsub;
                     dst[rr] = (ep.residual && row < M && col < N)
-                                  ? *(const float4*)(ep.residual + (size_t)row * ep.ldc + col)
+                                  ? *(const float4*)(ep.residual + (size_t)row * ep.ldr + col)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
@@ -359,20 +360,22 @@ bool g_inited = false;
 
 struct MapKey {
     const void* p;
-    uint64_t rows, cols;
+    uint64_t rows, cols, ld;
     uint32_t box_rows;
-    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+    bool operator==(const MapKey& o) const {
+        return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
-        return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ k.box_rows;
+        return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7) ^ k.box_rows;
     }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// bf16 row-major [rows, cols] -> tiled map with a {64, box_rows} box and 128-byte swizzle
-int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint32_t box_rows, CUtensorMap* out) {
-    MapKey key{p, rows, cols, box_rows};
+// bf16 row-major [rows, cols] with row stride ld -> tiled map with a {64, box_rows} box and 128-byte swizzle
+int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+    MapKey key{p, rows, cols, ld, box_rows};
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) {
@@ -380,7 +383,7 @@ int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint32_t box_r
         return VETO_OK;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
     cuuint32_t box[2] = {BLOCK_K, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p, dims, strides, box, estr,
@@ -402,17 +405,18 @@ int launch(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int 
     using C = TileCfg<BLOCK_N>;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     int rc;
-    if ((rc = get_map(A.hi, M, K, BLOCK_M, &ta_hi))) return rc;
-    if ((rc = get_map(W.hi, N, K, BLOCK_N, &tw_hi))) return rc;
+    const uint64_t lda = A.ld ? A.ld : K, ldw = W.ld ? W.ld : K;
+    if ((rc = get_map(A.hi, M, K, lda, BLOCK_M, &ta_hi))) return rc;
+    if ((rc = get_map(W.hi, N, K, ldw, BLOCK_N, &tw_hi))) return rc;
     ta_lo = ta_hi;
     tw_lo = tw_hi;
     if (passes == 3) {
-        if ((rc = get_map(A.lo, M, K, BLOCK_M, &ta_lo))) return rc;
-        if ((rc = get_map(W.lo, N, K, BLOCK_N, &tw_lo))) return rc;
+        if ((rc = get_map(A.lo, M, K, lda, BLOCK_M, &ta_lo))) return rc;
+        if ((rc = get_map(W.lo, N, K, ldw, BLOCK_N, &tw_lo))) return rc;
     }
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc};
+    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc};
     gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
@@ -440,7 +444,9 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int
     if (M <= 0 || N <= 0) return VETO_OK;
     VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tc: passes must be 1 or 3");
     VETO_REQUIRE(K % BLOCK_K == 0 && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a positive multiple of %d", K, BLOCK_K);
-    VETO_REQUIRE(N % 4 == 0 && ep.ldc % 4 == 0, VETO_ERR_UNSUPPORTED, "gemm_tc: N=%d and ldc=%d must be multiples of 4", N, ep.ldc);
+    VETO_REQUIRE(N % 4 == 0 && ep.ldc % 4 == 0 && ep.ldr % 4 == 0, VETO_ERR_UNSUPPORTED,
+                 "gemm_tc: N=%d, ldc=%d and ldr=%d must be multiples of 4", N, ep.ldc, ep.ldr);
+    VETO_REQUIRE(A.ld % 8 == 0 && W.ld % 8 == 0, VETO_ERR_UNSUPPORTED, "gemm_tc: operand row strides must be multiples of 8");
     VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)), VETO_ERR_ARG, "gemm_tc: missing bf16 operand");
     int rc = gemm_tc_init();
     if (rc) return rc;
