@@ -274,10 +274,16 @@ def main():
     passes = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
     achieved = algo_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     total_stage_ms = sum(st.ms.values())
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the GEMM kernel from the committed ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+        traffic, traffic_src = tj.get(args.precision), tj.get("source")
+    except Exception:
+        pass
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM)" if args.precision != "fp32" else "gemm_simt_kernel",
-        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-        "peak_source": peak_src,
+        "bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05.mma cta_group::2, TMEM accumulators, TMA)" if args.precision != "fp32" else "gemm_simt_kernel",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+        "peak_source": peak_src, "traffic_source": traffic_src,
         "algorithmic_flops_per_launch": algo_flops / max(g_launch, 1), "launches_per_step": g_launch,
         "avg_launch_ms": g_ms / max(g_launch, 1), "share_of_step": g_ms / total_stage_ms if total_stage_ms else None,
         "executed_mma_tflops": achieved * passes, "frac_executed": achieved * passes / peak_tf,

@@ -193,6 +193,35 @@ def stage_speed(precision):
                tflops_ref=R * 648.7e6 / ms / 1e9, launches=ops.last_launch_count)
 
 
+def stage_gemm(precision):
+    """GEMM micro-benchmark at the encoder's shapes (one default chunk = 37886 token rows): TFLOP/s per epilogue."""
+    M = int(os.environ.get("DIAG_M", 37886))
+    passes = 3 if precision == "bf16x3" else 1
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for (N, K, name) in [(1728, 576, "qkv"), (576, 576, "out"), (1152, 576, "ff1"), (576, 1152, "ff2")]:
+        a = torch.randn(M, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        b = torch.randn(N, generator=g).to(DEV)
+        r = torch.randn(M, N, generator=g).to(DEV)
+        c = torch.empty(M, N, device=DEV)
+        scratch = torch.empty(4 * (M * K + N * K) + 4 * M * N + 256, dtype=torch.uint8, device=DEV)
+        variants = {"plain_f32": (None, None, 0), "bias_f32": (b, None, 0), "bias_res_f32": (b, r, 0),
+                    "bias_gelu_f32": (b, None, 2), "bias_gelu_split": (b, None, 2 | 0x100), "plain_split": (None, None, 0x100)}
+        out = {}
+        for vn, (bias, res, act) in variants.items():
+            ops.test_gemm(a, w, bias=bias, residual=res, act=act, precision=precision, scratch=scratch, c=c)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.test_gemm(a, w, bias=bias, residual=res, act=act | 0x200, precision=precision, scratch=scratch, c=c)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            out[vn] = round(2.0 * M * N * K * passes / ms / 1e9, 1)
+        report("gemm", precision=precision, shape=[M, N, K], gemm=name, executed_tflops=out)
+
+
 def stage_stages(precision):
     """Per-stage device time (CUDA events around every library launch) of the relation head on an SGDet-shaped batch."""
     n_img, n_box = (int(os.environ.get("DIAG_IMAGES", 8)), int(os.environ.get("DIAG_BOXES", 80)))

@@ -14,10 +14,10 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
    python bench.py --images 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.out 2>&1; echo "rc=$?"
 echo "== ncu full: gemm"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 30 -c 4 -f -o gpurun_out/prof_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 -s 30 -c 8 -f -o gpurun_out/prof_gemm \
    python bench.py --images 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_gemm.out 2>&1; echo "rc=$?"
 echo "== ncu full: attention + layernorm + tokens + gather"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_kernel|layernorm_kernel|tokens_kernel|roi_gather_kernel" -s 4 -c 6 -f -o gpurun_out/prof_rows \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_mma_kernel|layernorm_kernel|tokens_kernel|roi_gather_kernel|gemm_simt" -s 4 -c 8 -f -o gpurun_out/prof_rows \
    python bench.py --images 4 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_rows.out 2>&1; echo "rc=$?"
 fi
 ls -la gpurun_out | head -30

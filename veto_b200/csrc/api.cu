@@ -148,7 +148,9 @@ size_t act_bytes(int precision, size_t elems) {
     return elems * sizeof(__nv_bfloat16);
 }
 
-constexpr int32_t kDefaultChunk = 2048;  // measured on B200: larger chunks win (fewer, fuller waves per launch)
+// 1994 pairs = 37886 token rows = 148 CTA-pair tiles of 256 rows: with 74 SM pairs every encoder GEMM of a chunk is a
+// whole number of waves (N/192 = 9, 6 and 3 column tiles -> 18, 12 and 6 waves)
+constexpr int32_t kDefaultChunk = 1994;
 
 WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
     WorkLayout W{};
@@ -201,7 +203,7 @@ int linear(int precision, const ActBuf& a, int lda, const WRef& w, int M, int N,
     A.hi = a.hi; A.lo = a.lo;
     A.ld = lda;
     W.hi = w.hi; W.lo = w.lo;
-    return gemm_tc(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+    return gemm_tc_auto(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
 }
 
 const __nv_bfloat16* bf(const void* base, size_t off) { return off ? (const __nv_bfloat16*)((const char*)base + off) : nullptr; }
@@ -499,26 +501,37 @@ extern "C" int veto_test_gemm(const float* a_dev, const float* w_dev, const floa
                               float* c_dev, int M, int N, int K, int act, int precision, void* scratch_dev,
                               size_t scratch_bytes, veto_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    // act bits: low byte = activation; 0x100 = write bf16 hi/lo outputs (into the scratch) instead of fp32;
+    // 0x200 = operands were already split by a previous call with the same scratch (timing runs)
+    const bool split_out = (act & 0x100) != 0, reuse = (act & 0x200) != 0;
     GemmEpilogue ep;
     ep.bias = bias_dev;
     ep.residual = residual_dev;
-    ep.act = act;
+    ep.act = act & 0xff;
     ep.out.f32 = c_dev;
     ep.ldc = N;
     if (precision == VETO_PREC_FP32) return gemm_simt(a_dev, K, w_dev, M, N, K, ep, s);
-    const size_t ae = (size_t)M * K, we = (size_t)N * K;
-    VETO_REQUIRE(scratch_dev && scratch_bytes >= 4 * (ae + we), VETO_ERR_WORKSPACE, "veto_test_gemm: scratch too small");
+    const size_t ae = (size_t)M * K, we = (size_t)N * K, ce = (size_t)M * N;
+    VETO_REQUIRE(scratch_dev && scratch_bytes >= 4 * (ae + we) + (split_out ? 4 * ce : 0), VETO_ERR_WORKSPACE,
+                 "veto_test_gemm: scratch too small");
     __nv_bfloat16* a_hi = (__nv_bfloat16*)scratch_dev;
     __nv_bfloat16* a_lo = a_hi + ae;
     __nv_bfloat16* w_hi = a_lo + ae;
     __nv_bfloat16* w_lo = w_hi + we;
     int rc;
-    if ((rc = pack_split_bf16(a_dev, a_hi, a_lo, ae, s))) return rc;
-    if ((rc = pack_split_bf16(w_dev, w_hi, w_lo, we, s))) return rc;
+    if (!reuse) {
+        if ((rc = pack_split_bf16(a_dev, a_hi, a_lo, ae, s))) return rc;
+        if ((rc = pack_split_bf16(w_dev, w_hi, w_lo, we, s))) return rc;
+    }
+    if (split_out) {
+        ep.out.f32 = nullptr;
+        ep.out.hi = w_lo + we;
+        ep.out.lo = precision == VETO_PREC_BF16X3 ? ep.out.hi + ce : nullptr;
+    }
     GemmOperand A, W;
     A.hi = a_hi; A.lo = a_lo;
     W.hi = w_hi; W.lo = w_lo;
-    return gemm_tc(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+    return gemm_tc_auto(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
 }
 
 extern "C" int veto_test_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev, int64_t rows,

@@ -85,6 +85,34 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// GELU for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 + fp32 rounding, the same
+// order as erff's own), one exp and one reciprocal, no branches — the exact-erff version made the FF1 epilogue
+// ALU-bound (it costs about as many issue slots per tile as the MMAs take cycles).
+__device__ __forceinline__ float gelu_fast(float v) {
+    const float z = fabsf(v) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.f - p * t * __expf(-z * z);          // erf(|v|/sqrt2)
+    return 0.5f * v * (1.f + copysignf(e, v));
+}
+__device__ __forceinline__ float apply_act_tc(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_GELU) return gelu_fast(v);
+    return v;
+}
+
+// (x0, x1) -> packed bf16 hi pair and lo pair (lo = x - float(hi)): 6 instructions for two elements
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 struct GemmEpilogue {
     const float* bias = nullptr;      // [N]
     const float* residual = nullptr;  // [M, ldr] fp32 (may alias out.f32)
@@ -108,6 +136,13 @@ int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, cons
 int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
             const GemmEpilogue& ep, cudaStream_t s);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
+// CTA-pair (cta_group::2) version, 256 x 192 tiles; needs N % 192 == 0 (gemm_tc2.cu)
+bool gemm_tc2_supported(int N, int K);
+int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+             cudaStream_t s);
+// picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc
+int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+                 cudaStream_t s);
 
 // LayerNorm over rows of kDim (eps 1e-5, model_veto.py:128) -> out format(s)
 int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, int64_t rows, const ActOut& out,

@@ -168,15 +168,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// (x0, x1) -> packed bf16 hi pair and lo pair (lo = x - float(hi))
-__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // shared-memory staging of one (sequence, head): row strides chosen so that the fragment reads are conflict-free
 // (Q/K: 64-bit reads at [g][2t] need stride = 8 mod 32 words; V: 32-bit reads at [2t][g] need 2*stride = 8 mod 32)
 constexpr int ATT_QK_STRIDE = 104, ATT_V_STRIDE = 100;  // floats (416 B / 400 B: 16-byte aligned for cp.async)

@@ -1,0 +1,481 @@
+// Token-wise GEMM of the relation encoder, CTA-pair version (tcgen05 cta_group::2): the kernel the encoder layers
+// run on.  Same contract as gemm_tc.cu (C[M,N] = epilogue(A[M,K] @ W[N,K]^T), bf16 operands, fp32 TMEM accumulate,
+// passes = 1 or 3 for the bf16x3 split), different mapping:
+//
+//   * a cluster of two CTAs (one SM pair) owns a 256 x 192 output tile; each CTA holds its own 128 rows of A and
+//     HALF of the W tile (96 rows) in shared memory, and one tcgen05.mma.cta_group::2 (M=256, N=192, K=16), issued
+//     by the leader CTA, feeds both tensor cores.  The single-CTA kernel is shared-memory-bandwidth bound (every
+//     operand byte is written once by TMA and read once per MMA: 2 x 40 KB per 384 tensor cycles > 128 B/clk,
+//     profiles/r1_v2_gemm_ncu.txt); the pair halves the W traffic per SM;
+//   * in 3-pass mode one pipeline stage holds A_hi, A_lo, W_hi, W_lo of a 64-wide K block and serves all three
+//     products (hi*hi, lo*hi, hi*lo): each operand tile is written once instead of twice.
+//
+// Barrier protocol (all mbarriers live at the same offset in both CTAs):
+//   full[s]   (leader)  : TMA of BOTH CTAs completes its bytes on the leader's barrier (peer bit of the address
+//                         cleared, as SM100_TMA_2SM_LOAD does); the leader's producer arms it with 2 x stage bytes.
+//   empty[s]  (each CTA): tcgen05.commit.cta_group::2 ... multicast 0b11 — both producers see the slot freed.
+//   tfull[a]  (each CTA): the same multicast commit after the last K block: both epilogues may drain.
+//   tempty[a] (leader)  : 2 x 8 epilogue warps arrive (the peer's through mapa + remote mbarrier.arrive).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace veto {
+namespace {
+
+constexpr int BLOCK_M = 128;      // rows per CTA (256 per pair)
+constexpr int BLOCK_N = 192;      // columns per pair tile; each CTA stages BLOCK_N / 2 rows of W
+constexpr int HALF_N = BLOCK_N / 2;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 12;  // three per TMEM lane quarter, interleaved over the 12 column chunks
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int EPI_COLS = 16;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;
+constexpr int BYTES_A = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int BYTES_B = HALF_N * BLOCK_K * 2;    // 12 KB
+constexpr int PIPE_BYTES = 168 * 1024;           // 3 stages of 56 KB (3-pass) or 6 stages of 28 KB (1-pass)
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int MAX_STAGES = 6;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("veto gemm_tc2: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+// TMA load whose completion bytes go to the LEADER CTA's barrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B descriptor (see gemm_tc.cu)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct EpiParams {
+    const float* bias;
+    const float* residual;
+    float* out_f32;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    int act;
+    int ldc;
+    int ldr;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                int M, int N, int K, int passes, EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_epi = smem + PIPE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_epi + EPI_BYTES);
+    uint64_t* full_bar = bars;                   // [MAX_STAGES]
+    uint64_t* empty_bar = bars + MAX_STAGES;     // [MAX_STAGES]
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES; // [2]
+    uint64_t* tmem_empty = tmem_full + 2;        // [2] (used in the leader)
+    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    const bool split = passes == 3;
+    const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
+    const int num_stages = PIPE_BYTES / stage_bytes;  // 3 or 6
+    const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = K / BLOCK_K;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_w_hi);
+        if (split) {
+            tma_prefetch_desc(&tm_a_lo);
+            tma_prefetch_desc(&tm_w_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < MAX_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc2(tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    // stage layout: [A_hi][A_lo][W_hi][W_lo] (3-pass) or [A][W] (1-pass)
+    auto stage_ptr = [&](int s) { return smem + s * stage_bytes; };
+    const int off_a_lo = BYTES_A;
+    const int off_w_hi = split ? 2 * BYTES_A : BYTES_A;
+    const int off_w_lo = off_w_hi + BYTES_B;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / num_n) * (2 * BLOCK_M) + rank * BLOCK_M;
+                const int n0 = (tile % num_n) * BLOCK_N + rank * HALF_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int k0 = kb * BLOCK_K;
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    uint8_t* sp = stage_ptr(stage);
+                    tma_load_2d_pair(sp, &tm_a_hi, &full_bar[stage], k0, m0);
+                    tma_load_2d_pair(sp + off_w_hi, &tm_w_hi, &full_bar[stage], k0, n0);
+                    if (split) {
+                        tma_load_2d_pair(sp + off_a_lo, &tm_a_lo, &full_bar[stage], k0, m0);
+                        tma_load_2d_pair(sp + off_w_lo, &tm_w_lo, &full_bar[stage], k0, n0);
+                    }
+                    if (++stage == num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(stage_ptr(stage));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t ko = k * UMMA_K * 2;
+                        const uint64_t a_hi = make_smem_desc(sp + ko);
+                        const uint64_t w_hi = make_smem_desc(sp + off_w_hi + ko);
+                        umma2_bf16(tmem_d, a_hi, w_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (split) {
+                            umma2_bf16(tmem_d, make_smem_desc(sp + off_a_lo + ko), w_hi, idesc, 1u);
+                            umma2_bf16(tmem_d, a_hi, make_smem_desc(sp + off_w_lo + ko), idesc, 1u);
+                        }
+                    }
+                    umma2_commit_both(&empty_bar[stage]);
+                    if (++stage == num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma2_commit_both(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) — see gemm_tc.cu for the data path ============
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;          // 0..2: which of the three warps of this lane quarter
+        constexpr int kStride = NUM_EPI_WARPS / 4;  // chunks c = half, half + 3, ...
+        float4* stage4 = reinterpret_cast<float4*>(smem_epi + (warp - 4) * EPI_STAGE_BYTES);
+        const int rsub = lane >> 2, cg = lane & 3;
+        constexpr int kChunks = BLOCK_N / EPI_COLS;
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / num_n) * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
+            const int n0 = (tile % num_n) * BLOCK_N;
+            float4 res[4], res_next[4];
+            auto load_res = [&](int c, float4 (&dst)[4]) {
+                const int col = n0 + c * EPI_COLS + cg * 4;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int row = m0 + rr * 8 + rsub;
+                    dst[rr] = (ep.residual && row < M && col < N)
+                                  ? *(const float4*)(ep.residual + (size_t)row * ep.ldr + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            load_res(half, res_next);
+            if (ep.residual && tile + num_pairs < num_tiles) {
+                // pull the NEXT tile's residual lines of this warp into L2 while this tile is processed
+                const int nt = tile + num_pairs;
+                const int pr = (nt / num_n) * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
+                const int pc = (nt % num_n) * BLOCK_N;
+                if (pr < M) {
+#pragma unroll
+                    for (int c = half; c < kChunks; c += kStride)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = half; c < kChunks; c += kStride) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) res[rr] = res_next[rr];
+                if (c + kStride < kChunks) load_res(c + kStride, res_next);
+                uint32_t r[16];
+                tmem_ld16(taddr + c * EPI_COLS, r);
+                tmem_ld_wait();
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    stage4[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                __syncwarp();
+                const int col = n0 + c * EPI_COLS + cg * 4;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias && col < N) bias4 = __ldg((const float4*)(ep.bias + col));
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int lr = rr * 8 + rsub;
+                    float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
+                    const int row = m0 + lr;
+                    if (row < M && col < N) {
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        v.x = apply_act_tc(v.x, ep.act); v.y = apply_act_tc(v.y, ep.act);
+                        v.z = apply_act_tc(v.z, ep.act); v.w = apply_act_tc(v.w, ep.act);
+                        v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
+                        const size_t off = (size_t)row * ep.ldc + col;
+                        if (ep.out_f32) *(float4*)(ep.out_f32 + off) = v;
+                        if (ep.out_hi) {
+                            uint2 hh, ll;
+                            split_pair(v.x, v.y, hh.x, ll.x);
+                            split_pair(v.z, v.w, hh.y, ll.y);
+                            *(uint2*)(ep.out_hi + off) = hh;
+                            if (ep.out_lo) *(uint2*)(ep.out_lo + off) = ll;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA thread waits for both CTAs
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_mu;
+bool g_inited = false;
+
+struct MapKey {
+    const void* p;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const MapKey& o) const {
+        return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7) ^ k.box_rows;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+    MapKey key{p, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+        *out = it->second;
+        return VETO_OK;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%llu,%llu] ld %llu box %u at %p", (int)r, (unsigned long long)rows,
+                  (unsigned long long)cols, (unsigned long long)ld, box_rows, (const void*)p);
+        return VETO_ERR_CUDA;
+    }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return VETO_OK;
+}
+
+int init2() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return VETO_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
+                 "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    g_inited = true;
+    return VETO_OK;
+}
+
+}  // namespace
+
+bool gemm_tc2_supported(int N, int K) { return N % BLOCK_N == 0 && K % BLOCK_K == 0; }
+
+int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+             cudaStream_t s) {
+    if (M <= 0 || N <= 0) return VETO_OK;
+    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tc2: passes must be 1 or 3");
+    VETO_REQUIRE(gemm_tc2_supported(N, K) && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc2: N=%d must be a multiple of %d, K=%d of %d",
+                 N, BLOCK_N, K, BLOCK_K);
+    VETO_REQUIRE(ep.ldc % 4 == 0 && ep.ldr % 4 == 0 && A.ld % 8 == 0 && W.ld % 8 == 0, VETO_ERR_UNSUPPORTED,
+                 "gemm_tc2: unaligned strides");
+    VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)), VETO_ERR_ARG, "gemm_tc2: missing bf16 operand");
+    int rc = init2();
+    if (rc) return rc;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    const uint64_t lda = A.ld ? A.ld : K, ldw = W.ld ? W.ld : K;
+    if ((rc = get_map(A.hi, M, K, lda, BLOCK_M, &ta_hi))) return rc;
+    if ((rc = get_map(W.hi, N, K, ldw, HALF_N, &tw_hi))) return rc;
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (passes == 3) {
+        if ((rc = get_map(A.lo, M, K, lda, BLOCK_M, &ta_lo))) return rc;
+        if ((rc = get_map(W.lo, N, K, ldw, HALF_N, &tw_lo))) return rc;
+    }
+    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / BLOCK_N);
+    const int pairs_avail = num_sms() / 2;
+    const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
+    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc};
+    gemm_tc2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
+                 cudaStream_t s) {
+    static int use2 = -1;
+    if (use2 < 0) {
+        const char* e = getenv("VETO_GEMM_2CTA");
+        use2 = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use2 && gemm_tc2_supported(N, K) && M > BLOCK_M) return gemm_tc2(A, W, M, N, K, passes, ep, s);
+    return gemm_tc(A, W, M, N, K, passes, ep, s);
+}
+
+}  // namespace veto

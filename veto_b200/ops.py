@@ -339,13 +339,17 @@ class StageTimer:
 # --------------------------------------------------------------------------------------------
 # test hooks
 # --------------------------------------------------------------------------------------------
-def test_gemm(a, w, bias=None, residual=None, act: int = 0, precision: str = "fp32"):
+def test_gemm(a, w, bias=None, residual=None, act: int = 0, precision: str = "fp32", scratch=None, c=None):
+    """act: low byte activation (0 none, 1 relu, 2 gelu); 0x100 bf16 hi/lo outputs into the scratch; 0x200 reuse the
+    operand split already in `scratch` (timing loops)."""
     L.require_device()
     a, w = _cuda_f32(a), _cuda_f32(w)
     M, K = a.shape
     N = w.shape[0]
-    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    scratch = torch.empty(4 * (M * K + N * K) + 256, dtype=torch.uint8, device=a.device)
+    if c is None:
+        c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if scratch is None:
+        scratch = torch.empty(4 * (M * K + N * K) + 4 * M * N + 256, dtype=torch.uint8, device=a.device)
     L.check(L.load().veto_test_gemm(a.data_ptr(), w.data_ptr(), L.ptr(bias), L.ptr(residual), c.data_ptr(), M, N, K, act,
                                     L.PRECISIONS[precision], scratch.data_ptr(), scratch.numel(), L.stream_ptr()),
             "veto_test_gemm")
