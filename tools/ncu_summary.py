@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Summaries of ncu output for profiles/ (text, committed):
+   ncu_summary.py launches <launches.csv> <out.txt>          per-kernel launch counts / time shares
+   ncu_summary.py report <file.ncu-rep> <out.txt> [regex]    selected metrics per captured launch
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+METRICS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+           "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+           "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+           "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+           "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+           "smsp__inst_executed.sum"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none : {sum(v[0] for v in agg.values())} launches, "
+                f"{tot / 1e3:.2f} ms of kernel time (cold-cache, serialised: compare SHARES)\n")
+        f.write(f"{'kernel':72s} {'launches':>8s} {'total_ms':>10s} {'avg_us':>9s} {'share':>7s}\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:72]:72s} {v[0]:8d} {v[1] / 1e3:10.3f} {v[1] / v[0]:9.1f} {v[1] / tot * 100:6.1f}%\n")
+
+
+def report(path, out, pattern=None):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on : {path.split('/')[-1]}\n")
+        for n, d in enumerate(data):
+            name = d[idx["Kernel Name"]]
+            if pattern and not re.search(pattern, name):
+                continue
+            f.write(f"\n## launch {n}: {name[:150]}\n")
+            for m in METRICS:
+                if m in idx:
+                    f.write(f"{m:100s} {d[idx[m]]:>16s} {units[idx[m]]}\n")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        report(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)

@@ -474,7 +474,7 @@ int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K
         const char* e = getenv("VETO_GEMM_2CTA");
         use2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use2 && gemm_tc2_supported(N, K) && M > BLOCK_M) return gemm_tc2(A, W, M, N, K, passes, ep, s);
+    if (use2 && gemm_tc2_supported(N, K)) return gemm_tc2(A, W, M, N, K, passes, ep, s);  // any M: one K order
     return gemm_tc(A, W, M, N, K, passes, ep, s);
 }
 
