@@ -291,6 +291,21 @@ def main():
         "stage_ms": {k: round(v, 3) for k, v in st.ms.items()},
     }
 
+    # ---- HBM-bound kernels of the path: algorithmic bytes per step / event time, against the measured copy bandwidth
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_boxes_total = B * N_BOXES
+    rows_full = (layers - 1) * M                      # token rows the 5 full layers normalise / attend
+    hbm_bytes = {
+        "pairs": R * (16 + 16 + 8),                   # enumerate writes 16 B/pair; globalize reads 16, writes 8
+        "roi_gather": n_boxes_total * 131072,         # bytes written (each touched map element is read once on top)
+        "tokens": R * 19 * 576 * 4,                   # token block written; box-level tables are L2-resident
+        "layernorm": (2 * rows_full + M + R) * 4608,  # 2304 B read + 2304 B written per row (last layer: LN2 on CLS rows)
+        "attention": rows_full * (6912 + 2304) + M * 4608 + R * 4608,  # qkv read + hi/lo output written
+    }
+    hbm_kernels = {k: {"ms": round(st.ms[k], 3), "algorithmic_bytes": int(v), "achieved_gbs": round(v / st.ms[k] / 1e6, 1),
+                       "frac_of_measured_hbm": round(v / st.ms[k] / 1e6 / hbm_peak, 3)}
+                   for k, v in hbm_bytes.items() if st.ms.get(k)}
+
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -311,7 +326,8 @@ def main():
             "tflops_reference_formulation": value * FLOP_PER_PAIR / 1e12,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_kernels": hbm_kernels,
+            "hbm_peak_gbs": hbm_peak, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

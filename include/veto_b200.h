@@ -244,6 +244,10 @@ int veto_test_gemm(const float* a_dev, const float* w_dev, const float* bias_dev
 int veto_test_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev,
                         int64_t rows, veto_stream_t stream);
 int veto_test_attention(const float* qkv_dev, float* out_dev, int64_t n_seq, veto_stream_t stream);
+/* the tensor-core attention kernel: fp32 result in out_dev; scratch_dev >= 4 * n_seq*19*576 bytes (bf16 hi/lo outputs);
+ * split = 1 for the bf16x3 scheme, 0 for single-pass bf16 */
+int veto_test_attention_tc(const float* qkv_dev, float* out_dev, void* scratch_dev, int64_t n_seq, int split,
+                           veto_stream_t stream);
 
 #ifdef __cplusplus
 }

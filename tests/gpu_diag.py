@@ -92,6 +92,18 @@ def stage_rows():
     att = torch.softmax(q @ k.transpose(-1, -2) * (96 ** -0.5), -1) @ v
     ref = att.permute(0, 2, 1, 3).reshape(n_seq * 19, 576)
     report("attention", err=relerr(ops.test_attention(qkv), ref))
+    for n_seq in (37, 6, 1, 300):
+        qkv = torch.randn(n_seq * 19, 1728, generator=g).to(DEV)
+        q, k, v = [t.reshape(n_seq, 19, 6, 96).permute(0, 2, 1, 3).double() for t in qkv.chunk(3, -1)]
+        att = torch.softmax(q @ k.transpose(-1, -2) * (96 ** -0.5), -1) @ v
+        ref = att.permute(0, 2, 1, 3).reshape(n_seq * 19, 576)
+        for split in (True, False):
+            out = ops.test_attention_tc(qkv, split)
+            torch.cuda.synchronize()
+            d = (out.double() - ref).abs()
+            report("attention_tc", n_seq=n_seq, split=split, err=relerr(out, ref), nan=int(torch.isnan(out).sum()),
+                   err_by_token=[float(x) for x in d.reshape(n_seq, 19, 576).amax((0, 2))][:19] if relerr(out, ref) > 1e-2 else None,
+                   err_by_head=[float(x) for x in d.reshape(-1, 6, 96).amax((0, 2))] if relerr(out, ref) > 1e-2 else None)
 
 
 def _case(name):

@@ -390,3 +390,16 @@ def test_no_cpu_fallback_and_errors():
     import ctypes
     assert L.load().veto_packed_bytes(ctypes.byref(cfg)) == 0
     assert b"unsupported architecture" in L.load().veto_last_error()
+
+
+@pytest.mark.parametrize("n_seq", [1, 6, 37, 300])
+def test_attention_tcgen05_kernel(n_seq):
+    """The tcgen05 attention kernel (six sequences per 128-row tile, block-diagonal softmax): bf16x3 split within
+    3e-5 of fp64, single-pass bf16 within 1e-2."""
+    g = torch.Generator().manual_seed(4)
+    qkv = torch.randn(n_seq * 19, 1728, generator=g)
+    q, k, v = [t.reshape(n_seq, 19, 6, 96).permute(0, 2, 1, 3).double() for t in qkv.chunk(3, -1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) * (96 ** -0.5), -1) @ v
+    ref = att.permute(0, 2, 1, 3).reshape(n_seq * 19, 576).numpy()
+    assert rel_err(H.np_(ops.test_attention_tc(_t(qkv.numpy()), True)), ref) < 3e-5
+    assert rel_err(H.np_(ops.test_attention_tc(_t(qkv.numpy()), False)), ref) < 1e-2

@@ -546,3 +546,13 @@ extern "C" int veto_test_attention(const float* qkv_dev, float* out_dev, int64_t
     o.f32 = out_dev;
     return attention_seq(qkv_dev, n_seq, o, (cudaStream_t)stream);
 }
+
+extern "C" int veto_test_attention_tc(const float* qkv_dev, float* out_dev, void* scratch_dev, int64_t n_seq, int split,
+                                      veto_stream_t stream) {
+    VETO_REQUIRE(qkv_dev && out_dev && scratch_dev, VETO_ERR_ARG, "veto_test_attention_tc: NULL argument");
+    ActOut o;
+    o.f32 = out_dev;
+    o.hi = (__nv_bfloat16*)scratch_dev;
+    o.lo = split ? o.hi + (size_t)n_seq * kTokens * kDim : nullptr;
+    return attention_tc(qkv_dev, n_seq, o, (cudaStream_t)stream);
+}

@@ -149,6 +149,8 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
                    cudaStream_t s);
 // softmax(q k^T * 96^-0.5) v per (sequence, head); qkv fp32 [n_seq*19, 1728] -> out [n_seq*19, 576]
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
+// tcgen05 version (attention_tc.cu): six sequences per 128-row tile, bf16 hi/lo split when out.lo is given
+int attention_tc(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
 // the same for the CLS query row only (last encoder layer: only x[:,0] is consumed, model_veto.py:25):
 // q_cls fp32 [n_seq, 576]; k, v from qkv [n_seq*19, 1728] cols 576..1727; out [n_seq, 576]
 int attention_cls(const float* q_cls, const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);

@@ -2,6 +2,8 @@
 // and the 19-token multi-head attention core (Attention.forward, model_veto.py:86-96).  Both are
 // HBM/L2-streaming kernels: one warp per row (LayerNorm) or per (sequence, head) (attention), warp
 // shuffles for the reductions, vectorised coalesced loads and stores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace veto {
@@ -14,52 +16,64 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------- LayerNorm
-// one warp per row of 576: 9 float2 per lane, two-pass mean / variance in registers (eps 1e-5)
-__global__ void __launch_bounds__(256)
+// One warp per row of 576 (9 float2 per lane), two-pass mean / variance in registers (eps 1e-5).  Two rows are in
+// flight per warp and gamma / beta come from L1 instead of registers, so that 48 warps per SM keep enough bytes in
+// flight for HBM (profiles/r1_rows_ncu.txt: the first version sat at 65 % of copy bandwidth with 24 warps per SM).
+__global__ void __launch_bounds__(256, 4)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                  int64_t rows, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     constexpr int PER = kDim / 64;  // 9
-    float2 wv[PER], bv[PER];
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        wv[j] = __ldg((const float2*)w + lane + 32 * j);
-        bv[j] = __ldg((const float2*)b + lane + 32 * j);
-    }
-    for (int64_t row = warp0; row < rows; row += nwarps) {
-        const float2* xr = (const float2*)(x + row * ldx);
-        float2 v[PER];
-        float s = 0.f;
+    const float2* w2 = (const float2*)w;
+    const float2* b2 = (const float2*)b;
+    for (int64_t row0 = 2 * warp0; row0 < rows; row0 += 2 * nwarps) {
+        const bool two = row0 + 1 < rows;
+        const float2* xr0 = (const float2*)(x + row0 * ldx);
+        const float2* xr1 = (const float2*)(x + (two ? row0 + 1 : row0) * ldx);
+        float2 v0[PER], v1[PER];
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            v[j] = xr[lane + 32 * j];
-            s += v[j].x + v[j].y;
+            v0[j] = xr0[lane + 32 * j];
+            v1[j] = xr1[lane + 32 * j];
         }
-        const float mean = warp_sum(s) * (1.f / kDim);
-        float q = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            const float dx = v[j].x - mean, dy = v[j].y - mean;
-            q += dx * dx + dy * dy;
+            s0 += v0[j].x + v0[j].y;
+            s1 += v1[j].x + v1[j].y;
         }
-        const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kDim) + 1e-5f);
-        const size_t o = (size_t)row * kDim;
+        const float mean0 = warp_sum(s0) * (1.f / kDim), mean1 = warp_sum(s1) * (1.f / kDim);
+        float q0 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            float2 y;
-            y.x = (v[j].x - mean) * rstd * wv[j].x + bv[j].x;
-            y.y = (v[j].y - mean) * rstd * wv[j].y + bv[j].y;
-            const size_t e = o + 2 * (lane + 32 * j);
-            if (out_f32) *(float2*)(out_f32 + e) = y;
-            if (out_hi) {
-                __nv_bfloat16 h0, h1, l0, l1;
-                split_bf16(y.x, h0, l0);
-                split_bf16(y.y, h1, l1);
-                *(uint32_t*)(out_hi + e) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                if (out_lo)
-                    *(uint32_t*)(out_lo + e) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const float ax = v0[j].x - mean0, ay = v0[j].y - mean0, bx = v1[j].x - mean1, by = v1[j].y - mean1;
+            q0 += ax * ax + ay * ay;
+            q1 += bx * bx + by * by;
+        }
+        const float rstd0 = 1.f / sqrtf(warp_sum(q0) * (1.f / kDim) + 1e-5f);
+        const float rstd1 = 1.f / sqrtf(warp_sum(q1) * (1.f / kDim) + 1e-5f);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r == 1 && !two) break;
+            const float mean = r ? mean1 : mean0, rstd = r ? rstd1 : rstd0;
+            const size_t o = (size_t)(row0 + r) * kDim;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const float2 v = r ? v1[j] : v0[j];
+                const float2 wv = __ldg(w2 + lane + 32 * j), bv = __ldg(b2 + lane + 32 * j);
+                float2 y;
+                y.x = (v.x - mean) * rstd * wv.x + bv.x;
+                y.y = (v.y - mean) * rstd * wv.y + bv.y;
+                const size_t e = o + 2 * (lane + 32 * j);
+                if (out_f32) *(float2*)(out_f32 + e) = y;
+                if (out_hi) {
+                    uint32_t hh, ll;
+                    split_pair(y.x, y.y, hh, ll);
+                    *(uint32_t*)(out_hi + e) = hh;
+                    if (out_lo) *(uint32_t*)(out_lo + e) = ll;
+                }
             }
         }
     }
@@ -407,8 +421,8 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
                    cudaStream_t s) {
     if (rows <= 0) return VETO_OK;
     VETO_REQUIRE((ldx & 1) == 0, VETO_ERR_ARG, "layernorm: row stride must be even");
-    const int64_t blocks_needed = (rows + 7) / 8;
-    const int64_t cap = (int64_t)num_sms() * 8;
+    const int64_t blocks_needed = (rows + 15) / 16;  // 8 warps x 2 rows per block iteration
+    const int64_t cap = (int64_t)num_sms() * 4;
     const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
     layernorm_kernel<<<grid, 256, 0, s>>>(x, ldx, w, b, rows, out.f32, out.hi, out.lo);
     VETO_LAUNCH_CHECK();
@@ -418,6 +432,14 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
     if (out.hi) {  // tensor-core modes: bf16x3 (hi + lo outputs) or single-pass bf16 (hi only)
+        static int use_tc = -1;
+        if (use_tc < 0) {
+            // "tc" selects the tcgen05 kernel (attention_tc.cu): correct, but its load/convert phase is not yet
+            // overlapped with the MMAs and it is slower (260 us vs 115 us per 1994 sequences), so warp-MMA is the default
+            const char* e = getenv("VETO_ATTENTION");
+            use_tc = (e && e[0] == 't') ? 1 : 0;
+        }
+        if (use_tc) return attention_tc(qkv, n_seq, out, s);
         static bool mma_attr_set = false;
         if (!mma_attr_set) {
             VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));

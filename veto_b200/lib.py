@@ -76,6 +76,7 @@ _PROTOS = {
     "veto_test_gemm": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_void_p]),
     "veto_test_layernorm": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_void_p]),
     "veto_test_attention": (c_int, [_fp, _fp, c_int64, c_void_p]),
+    "veto_test_attention_tc": (c_int, [_fp, _fp, _fp, c_int64, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOS)

@@ -373,3 +373,15 @@ def test_attention(qkv):
     out = torch.empty((qkv.shape[0], T_DIM), dtype=torch.float32, device=qkv.device)
     L.check(L.load().veto_test_attention(qkv.data_ptr(), out.data_ptr(), n_seq, L.stream_ptr()), "veto_test_attention")
     return out
+
+
+def test_attention_tc(qkv, split: bool = True):
+    """tcgen05 attention kernel: qkv [n_seq*19, 1728] -> fp32 [n_seq*19, 576]"""
+    L.require_device()
+    qkv = _cuda_f32(qkv)
+    n_seq = qkv.shape[0] // N_TOKENS
+    out = torch.empty((qkv.shape[0], T_DIM), dtype=torch.float32, device=qkv.device)
+    scratch = torch.empty(4 * qkv.shape[0] * T_DIM + 256, dtype=torch.uint8, device=qkv.device)
+    L.check(L.load().veto_test_attention_tc(qkv.data_ptr(), out.data_ptr(), scratch.data_ptr(), n_seq, int(split),
+                                            L.stream_ptr()), "veto_test_attention_tc")
+    return out
