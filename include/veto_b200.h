@@ -210,6 +210,66 @@ int veto_relation_forward(const veto_config* cfg, const veto_weights* w, const v
                           const veto_inputs* in, const veto_outputs* out,
                           void* workspace_dev, size_t workspace_bytes, int32_t chunk_pairs,
                           veto_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * a11. Training step of the relation head: VETOPredictor.forward in train() mode
+ * (roi_relation_predictors.py:4074-4136: same trunk with the Dropout layers active and BatchNorm1d batch
+ * statistics, then add_losses['rel_loss'] = CrossEntropyLoss(weight)(rel_dists, cat(rel_labels))) AND the backward
+ * pass autograd would run from that loss (tools/relation_train_net.py:451-452), in one call: forward with saved
+ * activations, loss, then gradients of every parameter the loss depends on, and of the ROI features.
+ *
+ * Dropout (pos_embed Dropout(0.1), Transformer.pos_drop EMB_DROPOUT, Attention.to_out T_DROPOUT; model_veto.py:43,
+ * 83-85) uses a counter-based mask, keyed by `seed` and the element index, regenerated in the backward pass.
+ * BatchNorm1d(4, momentum) normalises with the statistics of all boxes of the step and updates the running
+ * statistics in place (bn_running_mean / bn_running_var, NULL = leave them).
+ *
+ * veto_grads mirrors veto_weights (fp32, state_dict layout); every non-NULL gradient is OVERWRITTEN (not
+ * accumulated).  bn_mean / bn_var have no gradient and must be NULL.  Parameters the reference never uses
+ * (obj_embed2, bbox_embed: SURVEY.md §8a) have none either.  Every reduction has a fixed order: the step is
+ * bitwise reproducible. */
+typedef struct {
+    const int64_t* rel_labels;      /* [R] predicate class per pair (cat(rel_labels), …:4134) */
+    const float* class_weight;      /* [num_out] CrossEntropyLoss weight (criterion_loss_rel.weight) or NULL = ones */
+    const int32_t* rel_offsets;     /* [n_images+1] device: the pairs of image b are rows rel_offsets[b] .. rel_offsets[b+1] */
+    const int32_t* box_offsets;     /* [n_images+1] device: boxes of image b */
+    int32_t n_images;
+    float p_pos_dropout;            /* 0.1  pos_embed Dropout (…:4046) */
+    float p_emb_dropout;            /* EMB_DROPOUT 0.35 (model_veto.py:43,63) */
+    float p_attn_dropout;           /* T_DROPOUT 0.35  (model_veto.py:83-85) */
+    uint64_t seed;
+    float bn_momentum;              /* 0.001 (…:4043) */
+    float* bn_running_mean;         /* [4] updated in place, or NULL */
+    float* bn_running_var;          /* [4] updated in place, or NULL */
+} veto_train_inputs;
+
+typedef struct {
+    float* obj_embed; float* class_proj_w; float* class_proj_b;
+    float* bn_weight; float* bn_bias; float* bn_mean; float* bn_var;
+    float* pos_w; float* pos_b; float* loc_proj_w; float* loc_proj_b;
+    float* cls_token; float* pos_embedding;
+    float* proj_d_w; float* proj_d_b; float* proj_v_w; float* proj_v_b;
+    float* ln1_w[VETO_MAX_LAYERS]; float* ln1_b[VETO_MAX_LAYERS];
+    float* qkv_w[VETO_MAX_LAYERS];
+    float* out_w[VETO_MAX_LAYERS]; float* out_b[VETO_MAX_LAYERS];
+    float* ln2_w[VETO_MAX_LAYERS]; float* ln2_b[VETO_MAX_LAYERS];
+    float* ff1_w[VETO_MAX_LAYERS]; float* ff1_b[VETO_MAX_LAYERS];
+    float* ff2_w[VETO_MAX_LAYERS]; float* ff2_b[VETO_MAX_LAYERS];
+    float* rel_out_w; float* rel_out_b;
+} veto_grads;   /* same field order as veto_weights */
+
+typedef struct {
+    float* loss;                    /* [1] rel_loss */
+    float* rel_logits;              /* optional [R,num_out]: the training-mode logits */
+    float* grad_roi_depth;          /* optional [N,256,8,8]: d loss / d roi_depth_features (flows on into the depth
+                                       backbone through veto_roi_align_backward) */
+    float* grad_roi_rgb;            /* optional [N,256,8,8] (the RGB backbone is frozen in the reference: normally NULL) */
+} veto_train_outputs;
+
+size_t veto_train_workspace_bytes(const veto_config* cfg, int32_t n_boxes, int64_t n_pairs);
+int veto_relation_train_step(const veto_config* cfg, const veto_weights* w, const void* packed_dev,
+                             const veto_inputs* in, const veto_train_inputs* tin, const veto_grads* grads,
+                             const veto_train_outputs* out, void* workspace_dev, size_t workspace_bytes,
+                             veto_stream_t stream);
+
 /* Total number of kernel launches this thread has enqueued through the library so far (monotonic). */
 int64_t veto_last_launch_count(void);
 

@@ -53,8 +53,13 @@ def pooler_forward(feats: Sequence[torch.Tensor], depth: torch.Tensor, boxes: Se
 
 def predictor_forward(sd: Dict[str, torch.Tensor], boxes: Sequence[torch.Tensor], pairs: Sequence[torch.Tensor],
                       x2d: torch.Tensor, d2d: torch.Tensor, mode: str, labels=None, predict_logits=None,
-                      heads: int = 6, layers: int = 6) -> torch.Tensor:
+                      heads: int = 6, layers: int = 6, train: bool = False, drop=None, bn_out=None) -> torch.Tensor:
+    """train=True: BatchNorm1d uses the batch statistics (and writes the updated running statistics into `bn_out`), and
+    `drop` = {"pos": [N,128], "emb": [R,19,576], "attn": [layers x [R,19,576]]} holds explicit keep-scale factors
+    (mask / (1 - p)) applied where the reference's nn.Dropout layers sit (roi_relation_predictors.py:4046,
+    model_veto.py:63,83-85); None = no dropout."""
     T = "fusion_transformer.transformer."
+    drop = drop or {}
     if mode == "predcls":
         obj_embed = sd["obj_embed.weight"][torch.cat(list(labels))]
     else:
@@ -62,9 +67,17 @@ def predictor_forward(sd: Dict[str, torch.Tensor], boxes: Sequence[torch.Tensor]
     b = torch.cat(list(boxes), 0)
     w, h = b[:, 2] - b[:, 0] + 1, b[:, 3] - b[:, 1] + 1
     cx = torch.stack([b[:, 0] + 0.5 * w, b[:, 1] + 0.5 * h, w, h], 1)
-    bn = F.batch_norm(cx, sd["pos_embed.0.running_mean"], sd["pos_embed.0.running_var"], sd["pos_embed.0.weight"],
-                      sd["pos_embed.0.bias"], False, 0.0, 1e-5)
+    if train:
+        rm, rv = sd["pos_embed.0.running_mean"].clone(), sd["pos_embed.0.running_var"].clone()
+        bn = F.batch_norm(cx, rm, rv, sd["pos_embed.0.weight"], sd["pos_embed.0.bias"], True, 0.001, 1e-5)
+        if bn_out is not None:
+            bn_out["running_mean"], bn_out["running_var"] = rm, rv
+    else:
+        bn = F.batch_norm(cx, sd["pos_embed.0.running_mean"], sd["pos_embed.0.running_var"], sd["pos_embed.0.weight"],
+                          sd["pos_embed.0.bias"], False, 0.0, 1e-5)
     pos = F.relu(F.linear(bn, sd["pos_embed.1.weight"], sd["pos_embed.1.bias"]))
+    if drop.get("pos") is not None:
+        pos = pos * drop["pos"]
     subj, obj, off = [], [], 0
     for p, bx in zip(pairs, boxes):
         subj.append(p[:, 0] + off)
@@ -86,6 +99,8 @@ def predictor_forward(sd: Dict[str, torch.Tensor], boxes: Sequence[torch.Tensor]
     x = torch.cat((pd, pv), 2)
     r = x.shape[0]
     x = torch.cat((sd[T + "cls_token"].expand(r, -1, -1), x, loc.unsqueeze(1), cls.unsqueeze(1)), 1) + sd[T + "pos_embedding"]
+    if drop.get("emb") is not None:
+        x = x * drop["emb"]
     D = x.shape[-1]
     dh = D // heads
     for i in range(layers):
@@ -94,7 +109,10 @@ def predictor_forward(sd: Dict[str, torch.Tensor], boxes: Sequence[torch.Tensor]
         q, k, v = [t.reshape(r, -1, heads, dh).permute(0, 2, 1, 3) for t in F.linear(xn, sd[Lk + "0.fn.to_qkv.weight"]).chunk(3, -1)]
         attn = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * dh ** -0.5, -1)
         out = torch.einsum("bhij,bhjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(r, -1, D)
-        x = F.linear(out, sd[Lk + "0.fn.to_out.0.weight"], sd[Lk + "0.fn.to_out.0.bias"]) + x
+        proj = F.linear(out, sd[Lk + "0.fn.to_out.0.weight"], sd[Lk + "0.fn.to_out.0.bias"])
+        if drop.get("attn") is not None:
+            proj = proj * drop["attn"][i]
+        x = proj + x
         xn = F.layer_norm(x, (D,), sd[Lk + "1.norm.weight"], sd[Lk + "1.norm.bias"], 1e-5)
         hdn = F.gelu(F.linear(xn, sd[Lk + "1.fn.net.0.weight"], sd[Lk + "1.fn.net.0.bias"]))
         x = F.linear(hdn, sd[Lk + "1.fn.net.3.weight"], sd[Lk + "1.fn.net.3.bias"]) + x
@@ -103,3 +121,27 @@ def predictor_forward(sd: Dict[str, torch.Tensor], boxes: Sequence[torch.Tensor]
 
 def to_torch(sd_np: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()}
+
+
+TRAINED_KEYS_EXCLUDED = ("obj_embed2.weight", "bbox_embed.", "running_", "num_batches_tracked", "criterion_loss")
+
+
+def train_step(sd: Dict[str, torch.Tensor], boxes, pairs, rel_labels, x2d, d2d, mode: str, labels=None,
+               predict_logits=None, class_weight=None, drop=None, layers: int = 6):
+    """rel_loss of VETOPredictor.forward in train() mode (roi_relation_predictors.py:4131-4136) and, by autograd over
+    this restatement, its gradients: returns (loss, {state_dict key: grad}, grad wrt d2d, grad wrt x2d, bn_out)."""
+    leaves = {}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and not any(t in k for t in TRAINED_KEYS_EXCLUDED):
+            leaves[k] = v.detach().clone().requires_grad_(True)
+    sd2 = dict(sd)
+    sd2.update(leaves)
+    x2d = x2d.detach().clone().requires_grad_(True)
+    d2d = d2d.detach().clone().requires_grad_(True)
+    bn_out = {}
+    logits = predictor_forward(sd2, boxes, pairs, x2d, d2d, mode, labels=labels, predict_logits=predict_logits,
+                               layers=layers, train=True, drop=drop, bn_out=bn_out)
+    loss = F.cross_entropy(logits, torch.cat(list(rel_labels)).long(), weight=class_weight)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return loss.detach(), grads, d2d.grad, x2d.grad, bn_out, logits.detach()

@@ -35,6 +35,32 @@ CASES = {
 }
 
 
+# Training-step fixtures (tests/golden/make_golden.py run_train_case): the reference's VETOPredictor in train() mode
+# with every nn.Dropout set to p = 0 (module attributes), all ordered pairs per image as gtbox_relsample yields them
+# under the 1024-pair cap, seeded predicate labels; loss.backward() through the reference's own autograd.
+TRAIN_CASES = {
+    # BASELINE.json configs[1] shape, reduced: PredCls, ragged images, ~4 foreground pairs per image
+    "train_predcls": dict(predictor="VETOPredictor", mode="predcls", dataset="VG", n_boxes=[6, 3, 5],
+                          batch_seed=7, weight_seed=16, spread=True, H=320, W=416, label_seed=70, fg_per_image=4),
+    # SGCls-style: soft class embedding (softmax @ obj_embed) + the constant obj_loss, class-weighted CE
+    "train_sgcls": dict(predictor="VETOPredictor", mode="sgcls", dataset="VG", n_boxes=[5, 4],
+                        batch_seed=8, weight_seed=17, spread=True, H=320, W=416, label_seed=71, fg_per_image=6,
+                        class_weight_seed=72),
+}
+
+
+def case_rel_labels(c, pair_counts):
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    return synth.make_rel_labels(c["label_seed"], pair_counts, ds["num_rel"], c["fg_per_image"])
+
+
+def case_class_weight(c):
+    if "class_weight_seed" not in c:
+        return None
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    return np.random.default_rng(c["class_weight_seed"]).uniform(0.5, 2.0, ds["num_rel"]).astype(np.float32)
+
+
 def case_batch(c, features=True):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA
     return synth.make_batch(c["batch_seed"], c["n_boxes"], H=c.get("H", 592), W=c.get("W", 800),

@@ -93,13 +93,86 @@ def run_case(ns, name, c):
           {k: v.shape for k, v in out.items() if hasattr(v, 'shape') and v.ndim})
 
 
+def grad_summary(g: np.ndarray):
+    """What a fixture keeps of one gradient tensor: its norm and sum in float64 plus 64 fixed samples."""
+    flat = g.reshape(-1).astype(np.float64)
+    idx = np.unique(np.concatenate([np.arange(min(32, flat.size)), np.linspace(0, flat.size - 1, 32).astype(np.int64)]))
+    return np.array([np.sqrt((flat ** 2).sum()), flat.sum()]), idx, flat[idx].astype(np.float32)
+
+
+def run_train_case(ns, name, c):
+    """One training step of the UNMODIFIED reference predictor (train() mode, dropout p = 0): rel_loss and its
+    gradients wrt every parameter and wrt the depth feature map (through the reference's _ROIAlign autograd)."""
+    import torch
+    from tests.cases import case_class_weight, case_rel_labels
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    cfg = ref_shim.make_cfg(ns, predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"])
+    sd = case_state(c)
+    cw = case_class_weight(c)
+    if cw is not None:
+        sd = dict(sd)
+        sd["criterion_loss_rel.weight"] = cw
+    pred = ref_shim.build_predictor(ns, cfg, ds["num_obj"], ds["num_rel"], synth.to_torch_state(sd)).train()
+    for m in pred.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    batch = case_batch(c)
+    bls = ref_shim.make_boxlists(ns, batch, ds["num_obj"])
+    fe = ns.make_extractor(cfg, 256, for_relation=True).train()
+    samp = ns.make_sampler(cfg)
+    pairs = samp.prepare_test_pairs(torch.device("cpu"), bls)
+    rel_labels = [torch.from_numpy(l) for l in case_rel_labels(c, [len(p) for p in pairs])]
+    feats = [torch.from_numpy(f) for f in batch["feats"]]
+    feats.append(torch.zeros(batch["B"], 256, 1, 1))
+    depth = torch.from_numpy(batch["depth"]).clone().requires_grad_(True)
+    x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+    d2d.retain_grad()
+    obj_d, rel_d, losses, incre, chosen, custom = pred(bls, pairs, rel_labels, None, roi_features=x2d,
+                                                       roi_depth_features=d2d)
+    assert obj_d is None and rel_d is None
+    losses["rel_loss"].backward()
+    out = {"input_digest": np.array(digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"])),
+           "weight_digest": np.array(digest([sd[k] for k in sorted(sd)])),
+           "rel_labels": np.concatenate([l.numpy() for l in rel_labels]),
+           "pair_counts": np.array([len(p) for p in pairs]),
+           "rel_loss": np.array(losses["rel_loss"].item(), np.float64)}
+    if "obj_loss" in losses:
+        out["obj_loss"] = np.array(losses["obj_loss"].item(), np.float64)
+    no_grad = []
+    for k, p in pred.named_parameters():
+        if p.grad is None:
+            no_grad.append(k)
+            continue
+        stat, idx, val = grad_summary(p.grad.numpy())
+        out["gstat/" + k], out["gidx/" + k], out["gval/" + k] = stat, idx, val
+    out["no_grad"] = np.array(sorted(no_grad))
+    stat, idx, val = grad_summary(depth.grad.numpy())
+    out["gstat/depth_features"], out["gidx/depth_features"], out["gval/depth_features"] = stat, idx, val
+    stat, idx, val = grad_summary(d2d.grad.numpy())
+    out["gstat/roi_depth"], out["gidx/roi_depth"], out["gval/roi_depth"] = stat, idx, val
+    bn = pred.pos_embed[0]
+    out["running_mean"], out["running_var"] = bn.running_mean.numpy().copy(), bn.running_var.numpy().copy()
+    out["num_batches_tracked"] = np.array(int(bn.num_batches_tracked))
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KB) rel_loss={out['rel_loss']:.6f} "
+          f"no_grad={no_grad}")
+
+
 def main():
+    from tests.cases import TRAIN_CASES
     ns = ref_shim.load()
     only = sys.argv[1:]
     for name, c in CASES.items():
         if only and name not in only:
             continue
         run_case(ns, name, c)
+    for name, c in TRAIN_CASES.items():
+        if only and name not in only:
+            continue
+        run_train_case(ns, name, c)
 
 
 if __name__ == "__main__":

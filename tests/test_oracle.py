@@ -211,3 +211,28 @@ def test_torch_port_matches_reference(name):
     ref = g["logits"]
     assert np.abs(logits.numpy() - ref).max() <= REL_TOL * np.abs(ref).max()
     assert np.array_equal(logits.numpy().argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("name", ["train_predcls", "train_sgcls"])
+def test_torch_port_train_step_matches_reference(name):
+    """oracle/torch_port.train_step (the gradient oracle of the GPU training tests) against one training step of the
+    unmodified reference (train() mode, dropout p = 0): rel_loss, every parameter gradient, the gradient wrt the
+    pooled depth features, and the BatchNorm running statistics."""
+    from tests.cases import TRAIN_CASES
+    from tests.train_util import check_against_golden, oracle_train_step, train_case_inputs
+    c = TRAIN_CASES[name]
+    g = load_golden(name)
+    batch, sd, pairs, labels = train_case_inputs(c)
+    assert _digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]) == str(g["input_digest"])
+    assert _digest([sd[k] for k in sorted(sd)]) == str(g["weight_digest"])
+    assert np.array_equal(np.concatenate(labels), g["rel_labels"])
+    out = oracle_train_step(c, batch, sd, pairs, labels)
+    assert abs(out["loss"] - float(g["rel_loss"])) <= 2e-5 * abs(float(g["rel_loss"]))
+    grads = dict(out["grads"])
+    grads["roi_depth"] = out["g_roi_depth"]
+    worst = check_against_golden(grads, g, 2e-4, skip=("depth_features",))
+    assert len(worst) >= 80                      # every trained parameter was compared
+    for k in g["no_grad"]:
+        assert str(k) not in out["grads"]
+    assert np.allclose(out["running_mean"], g["running_mean"], rtol=1e-6)
+    assert np.allclose(out["running_var"], g["running_var"], rtol=1e-6)

@@ -6,7 +6,7 @@
 
 #include <vector>
 
-#include "stages.cuh"
+#include "api_internal.cuh"
 
 namespace veto {
 
@@ -32,7 +32,7 @@ static thread_local std::vector<ProfEvent> g_prof_events;
 static thread_local int g_tag = 0;
 static const char* kTagNames[VETO_PROFILE_TAGS] = {"other", "pairs", "roi_gather", "box_stage", "tokens", "layernorm",
                                                    "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
-                                                   "classifier", "postprocess", "pack", "", ""};
+                                                   "classifier", "postprocess", "pack", "bwd_gemm", "bwd_other"};
 
 void set_tag(int tag) { g_tag = tag; }
 void count_launch(int n) {
@@ -58,95 +58,12 @@ int num_sms() {
 
 namespace {
 
-constexpr size_t kAlign = 256;
-struct Carver {
-    size_t off = 0;
-    size_t take(size_t bytes) {
-        const size_t o = off;
-        off += (bytes + kAlign - 1) / kAlign * kAlign;
-        return o;
-    }
-};
-
-int check_config(const veto_config* c) {
-    VETO_REQUIRE(c != nullptr, VETO_ERR_ARG, "veto_config is NULL");
-    VETO_REQUIRE(c->dim == kDim && c->heads == kHeads && c->mlp_dim == kMlp && c->channels == kChannels &&
-                     c->pool == kPool && c->patch == 2,
-                 VETO_ERR_UNSUPPORTED,
-                 "unsupported architecture (dim %d heads %d mlp %d channels %d pool %d patch %d): this library is built "
-                 "for configs/VETO_final.yaml (576/6/1152/256/8/2)",
-                 c->dim, c->heads, c->mlp_dim, c->channels, c->pool, c->patch);
-    VETO_REQUIRE(c->layers >= 1 && c->layers <= VETO_MAX_LAYERS, VETO_ERR_UNSUPPORTED, "layers=%d outside 1..%d", c->layers,
-                 VETO_MAX_LAYERS);
-    VETO_REQUIRE(c->num_obj >= 2 && c->num_obj <= 512 && c->num_out >= 1, VETO_ERR_ARG, "bad num_obj=%d / num_out=%d",
-                 c->num_obj, c->num_out);
-    VETO_REQUIRE(c->precision >= VETO_PREC_FP32 && c->precision <= VETO_PREC_BF16, VETO_ERR_ARG, "bad precision %d",
-                 c->precision);
-    return VETO_OK;
-}
-
-struct PackedLayout {
-    size_t w_loc2, b_loc2, w_cls2, b_cls2, w_d2, b_d2, w_v2, b_v2, clspos;
-    size_t d2_hi, d2_lo, v2_hi, v2_lo;
-    size_t qkv_hi[VETO_MAX_LAYERS], qkv_lo[VETO_MAX_LAYERS], out_hi[VETO_MAX_LAYERS], out_lo[VETO_MAX_LAYERS];
-    size_t ff1_hi[VETO_MAX_LAYERS], ff1_lo[VETO_MAX_LAYERS], ff2_hi[VETO_MAX_LAYERS], ff2_lo[VETO_MAX_LAYERS];
-    size_t total;
-};
-
-PackedLayout packed_layout(const veto_config& c) {
-    PackedLayout L{};
-    Carver k;
-    L.w_loc2 = k.take(sizeof(float) * 2 * kDim * kPosDim);
-    L.b_loc2 = k.take(sizeof(float) * 2 * kDim);
-    L.w_cls2 = k.take(sizeof(float) * 2 * kDim * kEmbDim);
-    L.b_cls2 = k.take(sizeof(float) * 2 * kDim);
-    L.w_d2 = k.take(sizeof(float) * 2 * kDimDepth * kPatchVec);
-    L.b_d2 = k.take(sizeof(float) * 2 * kDimDepth);
-    L.w_v2 = k.take(sizeof(float) * 2 * kDimRgb * kPatchVec);
-    L.b_v2 = k.take(sizeof(float) * 2 * kDimRgb);
-    L.clspos = k.take(sizeof(float) * kDim);
-    if (c.precision != VETO_PREC_FP32) {
-        const bool lo = c.precision == VETO_PREC_BF16X3;
-        const size_t e = sizeof(__nv_bfloat16);
-        L.d2_hi = k.take(e * 2 * kDimDepth * kPatchVec);
-        L.d2_lo = lo ? k.take(e * 2 * kDimDepth * kPatchVec) : 0;
-        L.v2_hi = k.take(e * 2 * kDimRgb * kPatchVec);
-        L.v2_lo = lo ? k.take(e * 2 * kDimRgb * kPatchVec) : 0;
-        for (int l = 0; l < c.layers; ++l) {
-            L.qkv_hi[l] = k.take(e * 3 * kDim * kDim);
-            L.qkv_lo[l] = lo ? k.take(e * 3 * kDim * kDim) : 0;
-            L.out_hi[l] = k.take(e * kDim * kDim);
-            L.out_lo[l] = lo ? k.take(e * kDim * kDim) : 0;
-            L.ff1_hi[l] = k.take(e * kMlp * kDim);
-            L.ff1_lo[l] = lo ? k.take(e * kMlp * kDim) : 0;
-            L.ff2_hi[l] = k.take(e * kDim * kMlp);
-            L.ff2_lo[l] = lo ? k.take(e * kDim * kMlp) : 0;
-        }
-    }
-    L.total = k.off;
-    return L;
-}
-
-// an activation buffer in the storage format of the precision mode
-struct ActBuf {
-    float* f32 = nullptr;
-    __nv_bfloat16* hi = nullptr;
-    __nv_bfloat16* lo = nullptr;
-    ActOut out() const { return ActOut{f32, hi, lo}; }
-};
-
 struct WorkLayout {
     size_t pos, emb, lso, cso, pa_d, pa_v, so_d, so_v;  // box level
     size_t x, xn, qkv, h, q_cls, x_cls;                 // chunk level
     size_t total;
     int32_t chunk;
 };
-
-size_t act_bytes(int precision, size_t elems) {
-    if (precision == VETO_PREC_FP32) return elems * sizeof(float);
-    if (precision == VETO_PREC_BF16X3) return elems * 2 * sizeof(__nv_bfloat16);
-    return elems * sizeof(__nv_bfloat16);
-}
 
 // 1994 pairs = 37886 token rows = 148 CTA-pair tiles of 256 rows: with 74 SM pairs every encoder GEMM of a chunk is a
 // whole number of waves (N/192 = 9, 6 and 3 column tiles -> 18, 12 and 6 waves)
@@ -178,35 +95,6 @@ WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, i
     W.total = k.off;
     return W;
 }
-
-ActBuf act_at(void* base, size_t off, int precision, size_t elems) {
-    ActBuf b;
-    char* p = (char*)base + off;
-    if (precision == VETO_PREC_FP32) b.f32 = (float*)p;
-    else {
-        b.hi = (__nv_bfloat16*)p;
-        if (precision == VETO_PREC_BF16X3) b.lo = b.hi + elems;
-    }
-    return b;
-}
-
-struct WRef {  // a Linear weight in the forms the two GEMM paths need
-    const float* f32;
-    const __nv_bfloat16* hi;
-    const __nv_bfloat16* lo;
-};
-
-int linear(int precision, const ActBuf& a, int lda, const WRef& w, int M, int N, int K, const GemmEpilogue& ep,
-           cudaStream_t s) {
-    if (precision == VETO_PREC_FP32) return gemm_simt(a.f32, lda, w.f32, M, N, K, ep, s);
-    GemmOperand A, W;
-    A.hi = a.hi; A.lo = a.lo;
-    A.ld = lda;
-    W.hi = w.hi; W.lo = w.lo;
-    return gemm_tc_auto(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
-}
-
-const __nv_bfloat16* bf(const void* base, size_t off) { return off ? (const __nv_bfloat16*)((const char*)base + off) : nullptr; }
 
 }  // namespace
 }  // namespace veto

@@ -76,7 +76,7 @@ box_embed_kernel(const float* __restrict__ boxes, const int64_t* __restrict__ la
                  int num_obj, const float* __restrict__ obj_embed, const float* __restrict__ bn_w,
                  const float* __restrict__ bn_b, const float* __restrict__ bn_mean, const float* __restrict__ bn_var,
                  const float* __restrict__ pos_w, const float* __restrict__ pos_b, float* __restrict__ pos_out,
-                 float* __restrict__ emb_out) {
+                 float* __restrict__ emb_out, DropSpec pos_drop) {
     __shared__ float prob[512];
     __shared__ float red[4];
     const int n = blockIdx.x, t = threadIdx.x;
@@ -91,7 +91,9 @@ box_embed_kernel(const float* __restrict__ boxes, const int64_t* __restrict__ la
         float a = pos_b[t];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a = fmaf(pos_w[t * 4 + k], bn[k], a);
-        pos_out[(size_t)n * kPosDim + t] = fmaxf(a, 0.f);
+        a = fmaxf(a, 0.f);
+        if (pos_drop.thr16) a *= drop_scale1(pos_drop, (uint64_t)n * kPosDim + t);  // nn.Dropout(0.1), training only
+        pos_out[(size_t)n * kPosDim + t] = a;
     }
     if (labels) {
         const int64_t lab = labels[n];
@@ -174,12 +176,16 @@ int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size
 }
 
 int box_embed(const float* boxes, const int64_t* labels, const float* obj_logits, int num_obj, int n_boxes,
-              const veto_weights& w, float* pos_out, float* emb_out, cudaStream_t s) {
+              const veto_weights& w, float* pos_out, float* emb_out, cudaStream_t s, const float* batch_stats,
+              const DropSpec& pos_drop) {
     if (n_boxes <= 0) return VETO_OK;
     VETO_REQUIRE(labels || obj_logits, VETO_ERR_ARG, "box_embed: need labels or obj_logits");
     VETO_REQUIRE(num_obj <= 512, VETO_ERR_UNSUPPORTED, "box_embed: num_obj=%d > 512", num_obj);
-    box_embed_kernel<<<n_boxes, 128, 0, s>>>(boxes, labels, obj_logits, num_obj, w.obj_embed, w.bn_weight, w.bn_bias,
-                                             w.bn_mean, w.bn_var, w.pos_w, w.pos_b, pos_out, emb_out);
+    // training mode normalises with the batch statistics (train.cu bn_batch_stats: mean[4], biased var[4])
+    const float* mean = batch_stats ? batch_stats : w.bn_mean;
+    const float* var = batch_stats ? batch_stats + 4 : w.bn_var;
+    box_embed_kernel<<<n_boxes, 128, 0, s>>>(boxes, labels, obj_logits, num_obj, w.obj_embed, w.bn_weight, w.bn_bias, mean, var,
+                                             w.pos_w, w.pos_b, pos_out, emb_out, pos_drop);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

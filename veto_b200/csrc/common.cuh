@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int n = 1);
 // stage tags of the per-stage event timing (veto_profile_*); names in api.cu
 enum { TAG_OTHER = 0, TAG_PAIRS, TAG_GATHER, TAG_BOX, TAG_TOKENS, TAG_LN, TAG_QKV, TAG_ATT, TAG_OUT, TAG_FF1, TAG_FF2,
-       TAG_CLS, TAG_POST, TAG_PACK };
+       TAG_CLS, TAG_POST, TAG_PACK, TAG_BWD_GEMM, TAG_BWD_OTHER };
 void set_tag(int tag);
 
 #define VETO_CUDA(expr)                                                               \
@@ -113,6 +113,61 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ---- counter-based dropout mask (training branch) ----
+// One splitmix64 hash per group of four consecutive elements; element e is KEPT iff the 16-bit field
+// (hash(seed, e >> 2) >> (16 * (e & 3))) & 0xffff is >= thr16 = round(p * 65536).  Stateless, so the backward pass
+// (and the numpy oracle, tests/) regenerates the mask from (seed, element index) instead of storing it.
+__host__ __device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint64_t group) {
+    uint64_t z = seed + (group + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct DropSpec {
+    uint64_t seed = 0;
+    uint32_t thr16 = 0;   // 0 = no dropout
+    float scale = 1.f;    // 1 / (1 - p)
+};
+inline DropSpec make_drop(float p, uint64_t seed) {
+    DropSpec d;
+    if (p > 0.f) {
+        d.seed = seed;
+        d.thr16 = (uint32_t)(p * 65536.f + 0.5f);
+        d.scale = 1.f / (1.f - p);
+    }
+    return d;
+}
+// keep-scale factors of the four elements 4*group .. 4*group+3
+__device__ __forceinline__ float4 drop_scale4(const DropSpec& d, uint64_t group) {
+    const uint64_t h = drop_hash(d.seed, group);
+    return make_float4(((uint32_t)(h) & 0xffffu) >= d.thr16 ? d.scale : 0.f,
+                       ((uint32_t)(h >> 16) & 0xffffu) >= d.thr16 ? d.scale : 0.f,
+                       ((uint32_t)(h >> 32) & 0xffffu) >= d.thr16 ? d.scale : 0.f,
+                       ((uint32_t)(h >> 48) & 0xffffu) >= d.thr16 ? d.scale : 0.f);
+}
+__device__ __forceinline__ float drop_scale1(const DropSpec& d, uint64_t e) {
+    const uint64_t h = drop_hash(d.seed, e >> 2);
+    return ((uint32_t)(h >> (16 * (e & 3))) & 0xffffu) >= d.thr16 ? d.scale : 0.f;
+}
+
+// d/dv of nn.GELU() (exact erf form): Phi(v) + v * phi(v)
+__device__ __forceinline__ float gelu_grad(float v) {
+    return 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.39894228040143267794f * expf(-0.5f * v * v);
+}
+__device__ __forceinline__ float gelu_grad_fast(float v) {
+    const float z = fabsf(v) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float ex = __expf(-z * z);                       // exp(-v^2 / 2)
+    const float e = 1.f - p * t * ex;                      // erf(|v| / sqrt2)
+    return 0.5f * (1.f + copysignf(e, v)) + v * 0.39894228040143267794f * ex;
+}
+
+enum { RES_ADD = 0, RES_GELU_GRAD = 1 };
+
 struct GemmEpilogue {
     const float* bias = nullptr;      // [N]
     const float* residual = nullptr;  // [M, ldr] fp32 (may alias out.f32)
@@ -120,6 +175,12 @@ struct GemmEpilogue {
     ActOut out;                       // any subset of f32 / hi / lo; row stride ldc
     int ldc = 0;
     int ldr = 0;                      // residual row stride (0 = ldc)
+    // ---- training-branch extras (gemm_tc2 and gemm_simt only) ----
+    float* pre_f32 = nullptr;         // optional [M, ldc]: acc + bias BEFORE the activation (saved for the backward pass)
+    int res_mode = RES_ADD;           // RES_GELU_GRAD: out = (acc + bias) * gelu'(residual[row, col]) (FF1 backward)
+    DropSpec drop;                    // dropout on act(acc + bias) before the residual add; element index row * ldc + col
+    int split_k = 1;                  // > 1: partial products over K slices, slice s written at out.f32 + s * split_stride
+    size_t split_stride = 0;          //      (no bias / act / residual; reduce with splitk_reduce)
 };
 
 // A operand of a GEMM: fp32 (SIMT path) or bf16 hi[/lo] (tensor-core path); W likewise.
@@ -138,6 +199,7 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
 // CTA-pair (cta_group::2) version, 256 x 192 tiles; needs N % 192 == 0 (gemm_tc2.cu)
 bool gemm_tc2_supported(int N, int K);
+int gemm_tc2_slices(int K, int split_k);  // K slices a GemmEpilogue::split_k request really produces
 int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
              cudaStream_t s);
 // picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc

@@ -15,7 +15,8 @@ constexpr int PAD = 4;
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int N, int K,
                  const float* __restrict__ bias, const float* residual, int act, float* out_f32,
-                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc, int ldr) {
+                 __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc, int ldr, float* pre_f32, int res_mode,
+                 DropSpec drop) {
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
@@ -119,8 +120,14 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
             for (int j = 0; j < 4; ++j) {
                 if (c + j < N) {
                     if (bias) v[j] += __ldg(bias + c + j);
-                    v[j] = apply_act(v[j], act);
-                    if (residual) v[j] += residual[(size_t)r * ldr + c + j];
+                    if (pre_f32) pre_f32[off + j] = v[j];
+                    if (res_mode == RES_GELU_GRAD) {
+                        v[j] *= gelu_grad(residual[(size_t)r * ldr + c + j]);
+                    } else {
+                        v[j] = apply_act(v[j], act);
+                        if (drop.thr16) v[j] *= drop_scale1(drop, off + j);
+                        if (residual) v[j] += residual[(size_t)r * ldr + c + j];
+                    }
                 }
             }
             if (vec_out && c + 3 < N) {
@@ -157,8 +164,10 @@ int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, cons
     VETO_REQUIRE(K > 0 && A && W, VETO_ERR_ARG, "gemm_simt: bad operands");
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "gemm_simt: M=%d too large for one launch", M);
+    VETO_REQUIRE(ep.split_k <= 1, VETO_ERR_ARG, "gemm_simt: no split-K");
+    VETO_REQUIRE(ep.res_mode == RES_ADD || ep.residual, VETO_ERR_ARG, "gemm_simt: RES_GELU_GRAD needs the pre-activation");
     gemm_simt_kernel<<<grid, 256, 0, s>>>(A, lda, W, M, N, K, ep.bias, ep.residual, ep.act, ep.out.f32, ep.out.hi,
-                                          ep.out.lo, ep.ldc, ep.ldr ? ep.ldr : ep.ldc);
+                                          ep.out.lo, ep.ldc, ep.ldr ? ep.ldr : ep.ldc, ep.pre_f32, ep.res_mode, ep.drop);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -443,6 +443,8 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int
             cudaStream_t s) {
     if (M <= 0 || N <= 0) return VETO_OK;
     VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tc: passes must be 1 or 3");
+    VETO_REQUIRE(!ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ep.split_k <= 1, VETO_ERR_UNSUPPORTED,
+                 "gemm_tc: the training-branch epilogue options exist in gemm_tc2 / gemm_simt only (N=%d)", N);
     VETO_REQUIRE(K % BLOCK_K == 0 && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a positive multiple of %d", K, BLOCK_K);
     VETO_REQUIRE(N % 4 == 0 && ep.ldc % 4 == 0 && ep.ldr % 4 == 0, VETO_ERR_UNSUPPORTED,
                  "gemm_tc: N=%d, ldc=%d and ldr=%d must be multiples of 4", N, ep.ldc, ep.ldr);

@@ -151,6 +151,13 @@ struct EpiParams {
     int act;
     int ldc;
     int ldr;
+    // training-branch extras (common.cuh GemmEpilogue)
+    float* pre_f32;
+    int res_mode;
+    DropSpec drop;
+    int ksplit;              // K slices (wgrad: tiny output, huge K); tiles enumerate (slice, m, n)
+    int kb_per;              // K blocks per slice
+    long long split_stride;  // elements between the partial outputs of consecutive slices
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -177,8 +184,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int num_stages = PIPE_BYTES / stage_bytes;  // 3 or 6
     const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m * num_n;
+    const int mn_tiles = num_m * num_n;
+    const int num_tiles = mn_tiles * ep.ksplit;
     const int num_kb = K / BLOCK_K;
+    // tile -> (K slice, m tile, n tile) and the K-block range of the slice
+    auto tile_mn = [&](int tile, int& tm, int& tn) {
+        const int t2 = tile % mn_tiles;
+        tm = t2 / num_n;
+        tn = t2 - tm * num_n;
+        return tile / mn_tiles;
+    };
+    auto kb_range = [&](int ks, int& kb0, int& kb1) {
+        kb0 = ks * ep.kb_per;
+        kb1 = kb0 + ep.kb_per < num_kb ? kb0 + ep.kb_per : num_kb;
+    };
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -218,9 +237,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m0 = (tile / num_n) * (2 * BLOCK_M) + rank * BLOCK_M;
-                const int n0 = (tile % num_n) * BLOCK_N + rank * HALF_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int tm, tn, kb0, kb1;
+                kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M;
+                const int n0 = tn * BLOCK_N + rank * HALF_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     const int k0 = kb * BLOCK_K;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
@@ -252,7 +273,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int tm, tn, kb0, kb1;
+                kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
                     const uint32_t sp = smem_u32(stage_ptr(stage));
@@ -261,7 +284,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         const uint32_t ko = k * UMMA_K * 2;
                         const uint64_t a_hi = make_smem_desc(sp + ko);
                         const uint64_t w_hi = make_smem_desc(sp + off_w_hi + ko);
-                        umma2_bf16(tmem_d, a_hi, w_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma2_bf16(tmem_d, a_hi, w_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                         if (split) {
                             umma2_bf16(tmem_d, make_smem_desc(sp + off_a_lo + ko), w_hi, idesc, 1u);
                             umma2_bf16(tmem_d, a_hi, make_smem_desc(sp + off_w_lo + ko), idesc, 1u);
@@ -289,8 +312,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
-            const int n0 = (tile % num_n) * BLOCK_N;
+            int tm, tn;
+            const int ks = tile_mn(tile, tm, tn);
+            const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
+            const int n0 = tn * BLOCK_N;
+            const size_t split_off = (size_t)ks * (size_t)ep.split_stride;
             float4 res[4], res_next[4];
             auto load_res = [&](int c, float4 (&dst)[4]) {
                 const int col = n0 + c * EPI_COLS + cg * 4;
@@ -305,9 +331,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             load_res(half, res_next);
             if (ep.residual && tile + num_pairs < num_tiles) {
                 // pull the NEXT tile's residual lines of this warp into L2 while this tile is processed
-                const int nt = tile + num_pairs;
-                const int pr = (nt / num_n) * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
-                const int pc = (nt % num_n) * BLOCK_N;
+                int ntm, ntn;
+                tile_mn(tile + num_pairs, ntm, ntn);
+                const int pr = ntm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
+                const int pc = ntn * BLOCK_N;
                 if (pr < M) {
 #pragma unroll
                     for (int c = half; c < kChunks; c += kStride)
@@ -341,10 +368,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     const int row = m0 + lr;
                     if (row < M && col < N) {
                         v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-                        v.x = apply_act_tc(v.x, ep.act); v.y = apply_act_tc(v.y, ep.act);
-                        v.z = apply_act_tc(v.z, ep.act); v.w = apply_act_tc(v.w, ep.act);
-                        v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
-                        const size_t off = (size_t)row * ep.ldc + col;
+                        const size_t off = (size_t)row * ep.ldc + col + split_off;
+                        if (ep.pre_f32) *(float4*)(ep.pre_f32 + off) = v;
+                        if (ep.res_mode == RES_GELU_GRAD) {
+                            v.x *= gelu_grad_fast(res[rr].x); v.y *= gelu_grad_fast(res[rr].y);
+                            v.z *= gelu_grad_fast(res[rr].z); v.w *= gelu_grad_fast(res[rr].w);
+                        } else {
+                            v.x = apply_act_tc(v.x, ep.act); v.y = apply_act_tc(v.y, ep.act);
+                            v.z = apply_act_tc(v.z, ep.act); v.w = apply_act_tc(v.w, ep.act);
+                            if (ep.drop.thr16) {
+                                const float4 ds = drop_scale4(ep.drop, off >> 2);
+                                v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
+                            }
+                            v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
+                        }
                         if (ep.out_f32) *(float4*)(ep.out_f32 + off) = v;
                         if (ep.out_hi) {
                             uint2 hh, ll;
@@ -437,6 +474,16 @@ int init2() {
 
 bool gemm_tc2_supported(int N, int K) { return N % BLOCK_N == 0 && K % BLOCK_K == 0; }
 
+// number of K slices a split-K request really produces (every slice non-empty)
+int gemm_tc2_slices(int K, int split_k) {
+    const int num_kb = K / BLOCK_K;
+    int ksplit = split_k > 1 ? split_k : 1;
+    if (ksplit > num_kb) ksplit = num_kb;
+    if (ksplit < 1) ksplit = 1;
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    return (num_kb + kb_per - 1) / kb_per;
+}
+
 int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
              cudaStream_t s) {
     if (M <= 0 || N <= 0) return VETO_OK;
@@ -458,10 +505,19 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
         if ((rc = get_map(A.lo, M, K, lda, BLOCK_M, &ta_lo))) return rc;
         if ((rc = get_map(W.lo, N, K, ldw, HALF_N, &tw_lo))) return rc;
     }
-    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / BLOCK_N);
+    const int num_kb = K / BLOCK_K;
+    const int ksplit = gemm_tc2_slices(K, ep.split_k);
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    VETO_REQUIRE(ksplit == 1 || (!ep.bias && !ep.residual && ep.act == ACT_NONE && !ep.pre_f32 && !ep.drop.thr16 &&
+                                 ep.out.f32 && !ep.out.hi),
+                 VETO_ERR_ARG, "gemm_tc2: split-K writes plain fp32 partial products only");
+    VETO_REQUIRE(ep.res_mode == RES_ADD || ep.residual, VETO_ERR_ARG, "gemm_tc2: RES_GELU_GRAD needs the pre-activation");
+    VETO_REQUIRE(!ep.drop.thr16 || ep.ldc % 4 == 0, VETO_ERR_ARG, "gemm_tc2: dropout needs ldc % 4 == 0");
+    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / BLOCK_N) * ksplit;
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
-    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc};
+    EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
+                ep.pre_f32, ep.res_mode, ep.drop, ksplit, kb_per, (long long)ep.split_stride};
     gemm_tc2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;

@@ -19,7 +19,8 @@ int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size
 // pos_embed (BN1d eval -> Linear(4,128) -> ReLU, roi_relation_predictors.py:4042-4047,4097-4102) and the class
 // embedding (hard lookup :4087 / soft softmax@W :4095) of every box.
 int box_embed(const float* boxes, const int64_t* labels, const float* obj_logits, int num_obj, int n_boxes,
-              const veto_weights& w, float* pos_out, float* emb_out, cudaStream_t s);
+              const veto_weights& w, float* pos_out, float* emb_out, cudaStream_t s, const float* batch_stats = nullptr,
+              const DropSpec& pos_drop = DropSpec());
 // roi [N,256,8,8] -> patch rows [N*16, 1024] in (p1 p2 c) order
 int patchify(const float* roi, int n_boxes, const ActOut& out, cudaStream_t s);
 

@@ -1,0 +1,901 @@
+// Training-branch kernels of the relation head that are not GEMMs: the cross-entropy loss of
+// VETOPredictor.forward (roi_relation_predictors.py:4134-4135, nn.CrossEntropyLoss(weight)), and the backward twins
+// of the row-wise forward kernels — LayerNorm (model_veto.py:125-132), the 19-token attention core (:86-96), the
+// relation-token gather (tokens.cu; model_veto.py:52-64), the per-box embeddings (box_stage.cu;
+// roi_relation_predictors.py:4042-4047, 4086-4102) — plus the data-movement helpers the weight-gradient GEMMs need
+// (transposes into K-major bf16 hi/lo operands, split-K reduction, deterministic column sums).
+//
+// Every reduction here has a fixed order (no floating-point atomics): a training step is bitwise reproducible.
+#include "stages.cuh"
+#include "train.cuh"
+
+namespace veto {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+int grid_cap(size_t blocks, int per_sm) {
+    const size_t cap = (size_t)num_sms() * per_sm;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+__device__ __forceinline__ float load_act(const float* f32, const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t e) {
+    if (f32) return f32[e];
+    float v = __bfloat162float(hi[e]);
+    if (lo) v += __bfloat162float(lo[e]);
+    return v;
+}
+__device__ __forceinline__ void store_act(float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t e, float v) {
+    if (f32) f32[e] = v;
+    if (hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[e] = h;
+        if (lo) lo[e] = l;
+    }
+}
+
+// ---------------------------------------------------------------- cross entropy
+// loss = sum_i w[y_i] * (logsumexp(z_i) - z_i[y_i]) / sum_i w[y_i]   (nn.CrossEntropyLoss(weight), mean reduction)
+// warp per row: row_loss[i] = w * nll, row_w[i] = w
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const float* __restrict__ logits, int C, const int64_t* __restrict__ labels, const float* __restrict__ weight,
+               int64_t rows, float* __restrict__ row_loss, float* __restrict__ row_w) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        const float* z = logits + r * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const int64_t y = labels[r];
+            const float w = weight ? weight[y] : 1.f;
+            row_loss[r] = w * (logf(s) + m - z[y]);
+            row_w[r] = w;
+        }
+    }
+}
+// single block: fixed-order tree sums of row_loss and row_w -> out[0] = loss, out[1] = 1 / sum(w)
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_w, int64_t rows, float* __restrict__ loss_out,
+                   float* __restrict__ inv_w_out) {
+    __shared__ double sl[1024], sw[1024];
+    double a = 0.0, b = 0.0;
+    for (int64_t r = threadIdx.x; r < rows; r += 1024) {
+        a += row_loss[r];
+        b += row_w[r];
+    }
+    sl[threadIdx.x] = a;
+    sw[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sl[threadIdx.x] += sl[threadIdx.x + o];
+            sw[threadIdx.x] += sw[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *loss_out = (float)(sl[0] / sw[0]);
+        *inv_w_out = (float)(1.0 / sw[0]);
+    }
+}
+// dlogits[i, c] = w[y_i] * (softmax(z_i)[c] - [c == y_i]) / sum(w)
+__global__ void __launch_bounds__(256)
+ce_grad_kernel(const float* __restrict__ logits, int C, const int64_t* __restrict__ labels, const float* __restrict__ weight,
+               const float* __restrict__ inv_w, int64_t rows, float* __restrict__ dlogits) {
+    const int lane = threadIdx.x & 31;
+    const float iw = *inv_w;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        const float* z = logits + r * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+        s = warp_sum(s);
+        const int64_t y = labels[r];
+        const float w = (weight ? weight[y] : 1.f) * iw;
+        const float inv = 1.f / s;
+        for (int c = lane; c < C; c += 32) dlogits[r * C + c] = w * (expf(z[c] - m) * inv - (c == y ? 1.f : 0.f));
+    }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// stage 1: block (128 columns) x row chunk -> partial[chunk, cols]; stage 2: fixed-order sum over chunks
+__global__ void __launch_bounds__(128)
+colsum_partial_kernel(const float* f32, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t ld, int64_t rows, int cols,
+                      int rows_per_chunk, float* __restrict__ partial) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    float a = 0.f;
+    for (int64_t r = r0; r < r1; ++r) a += load_act(f32, hi, lo, (size_t)(r * ld + c));
+    partial[(size_t)blockIdx.y * cols + c] = a;
+}
+__global__ void __launch_bounds__(128)
+colsum_final_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out, int accumulate) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= cols) return;
+    float a = 0.f;
+    for (int k = 0; k < chunks; ++k) a += partial[(size_t)k * cols + c];
+    out[c] = accumulate ? out[c] + a : a;
+}
+
+// ---------------------------------------------------------------- transposes
+// dst[c, r] = op(src[r, c]) (* dropout), r < rows; columns rows..rows_pad of dst are zero-filled (K padding of the
+// weight-gradient GEMMs).  Optionally also writes the (dropped) values row-major into `rm` (same shape as src, ld cols).
+constexpr int TR_OP_NONE = 0, TR_OP_GELU = 1;
+__global__ void __launch_bounds__(256)
+transpose_f32_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols, int op, DropSpec drop,
+                     int64_t drop_ld, float* t_f32, __nv_bfloat16* t_hi, __nv_bfloat16* t_lo, int64_t ld_dst, int64_t rows_pad,
+                     float* rm_f32, __nv_bfloat16* rm_hi, __nv_bfloat16* rm_lo, int64_t ld_rm) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = r0 + ty + 8 * k;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (r < rows && c < cols) {
+            v = src[r * ld_src + c];
+            if (op == TR_OP_GELU) v = apply_act(v, ACT_GELU);
+            if (drop.thr16) v *= drop_scale1(drop, (uint64_t)(r * drop_ld + c));
+            store_act(rm_f32, rm_hi, rm_lo, (size_t)(r * ld_rm + c), v);
+        }
+        tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k;
+        const int64_t r = r0 + tx;
+        if (c < cols && r < rows_pad) store_act(t_f32, t_hi, t_lo, (size_t)((int64_t)c * ld_dst + r), tile[tx][ty + 8 * k]);
+    }
+}
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                      __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int64_t rows_pad) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.y * 64;
+    const int c0 = blockIdx.x * 64;
+    // read: thread (ty, tx) moves the bf16 pair (row ty + 8k, cols 2tx, 2tx+1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t r = r0 + ty + 8 * k;
+        const int c = c0 + 2 * tx;
+        __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+        if (r < rows) {
+            if (c + 1 < cols) v = *(const __nv_bfloat162*)(src + r * ld_src + c);
+            else if (c < cols) v.x = src[r * ld_src + c];
+        }
+        tile[ty + 8 * k][2 * tx] = v.x;
+        tile[ty + 8 * k][2 * tx + 1] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + ty + 8 * k;
+        const int64_t r = r0 + 2 * tx;
+        if (c < cols && r < rows_pad) {
+            __nv_bfloat162 v;
+            v.x = tile[2 * tx][ty + 8 * k];
+            v.y = tile[2 * tx + 1][ty + 8 * k];
+            *(__nv_bfloat162*)(dst + (int64_t)c * ld_dst + r) = v;  // ld_dst and rows_pad are even
+        }
+    }
+}
+
+// out[e] = sum_s partial[s, e] (fixed order), optionally into the un-packed layout of a factored weight
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int slices, size_t n, size_t stride, float* __restrict__ out) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < slices; ++s) a += partial[(size_t)s * stride + e];
+        out[e] = a;
+    }
+}
+
+// x[e] *= keep-scale(e)
+__global__ void __launch_bounds__(256)
+dropout_kernel(float* __restrict__ x, size_t n4, DropSpec drop) {
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
+        float4 v = ((float4*)x)[g];
+        const float4 d = drop_scale4(drop, g);
+        v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+        ((float4*)x)[g] = v;
+    }
+}
+
+// fp32 -> activation storage format (no transpose)
+__global__ void __launch_bounds__(256)
+convert_kernel(const float* __restrict__ src, size_t n, float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        store_act(f32, hi, lo, e, src[e]);
+}
+
+// ---------------------------------------------------------------- LayerNorm backward
+// warp per row.  xhat = (x - mean) * rstd, g = dy * gamma:
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres);  dgamma += dy * xhat;  dbeta += dy
+// Per-block partial dgamma / dbeta go to partial[block, 2, 576]; a column sum over blocks finishes them.
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, const float* __restrict__ gamma,
+              const float* dres, float* dx, int64_t rows, float* __restrict__ partial) {
+    constexpr int PER = kDim / 64;  // 9 float2 per lane
+    __shared__ float red[8][2 * kDim];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float2 gam[PER], dg[PER], db[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        gam[j] = __ldg((const float2*)gamma + lane + 32 * j);
+        dg[j] = make_float2(0.f, 0.f);
+        db[j] = make_float2(0.f, 0.f);
+    }
+    for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < rows; row += (int64_t)gridDim.x * 8) {
+        const float2* xr = (const float2*)(x + row * ldx);
+        const float2* dyr = (const float2*)(dy + row * kDim);
+        float2 v[PER], d[PER];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            v[j] = xr[lane + 32 * j];
+            d[j] = dyr[lane + 32 * j];
+            s += v[j].x + v[j].y;
+        }
+        const float mean = warp_sum(s) * (1.f / kDim);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const float ax = v[j].x - mean, ay = v[j].y - mean;
+            q += ax * ax + ay * ay;
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kDim) + 1e-5f);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            v[j].x = (v[j].x - mean) * rstd;  // xhat
+            v[j].y = (v[j].y - mean) * rstd;
+            dg[j].x += d[j].x * v[j].x;
+            dg[j].y += d[j].y * v[j].y;
+            db[j].x += d[j].x;
+            db[j].y += d[j].y;
+            d[j].x *= gam[j].x;  // g
+            d[j].y *= gam[j].y;
+            s1 += d[j].x + d[j].y;
+            s2 += d[j].x * v[j].x + d[j].y * v[j].y;
+        }
+        s1 = warp_sum(s1) * (1.f / kDim);
+        s2 = warp_sum(s2) * (1.f / kDim);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            float2 o;
+            o.x = rstd * (d[j].x - s1 - v[j].x * s2);
+            o.y = rstd * (d[j].y - s1 - v[j].y * s2);
+            const size_t e = (size_t)row * kDim + 2 * (lane + 32 * j);
+            if (dres) {
+                const float2 rr = *(const float2*)(dres + e);
+                o.x += rr.x;
+                o.y += rr.y;
+            }
+            *(float2*)(dx + e) = o;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int c = 2 * (lane + 32 * j);
+        red[wid][c] = dg[j].x;
+        red[wid][c + 1] = dg[j].y;
+        red[wid][kDim + c] = db[j].x;
+        red[wid][kDim + c + 1] = db[j].y;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * kDim; c += 256) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += red[w][c];
+        partial[(size_t)blockIdx.x * 2 * kDim + c] = a;
+    }
+}
+
+// ---------------------------------------------------------------- attention backward
+// One warp per (sequence, head).  Q, K, V of the head (from the saved qkv) and dO are staged in shared memory; lane i
+// owns query row i for S = Q K^T, P = softmax, dP = dO V^T, dS = P * (dP - rowsum(P * dP)) * scale and dQ = dS K;
+// lane j then owns key row j for dK = dS^T Q and dV = P^T dO.  Results overwrite the staging buffers that are no
+// longer needed (dQ -> V, dK -> K, dV -> Q) and leave with coalesced 128-bit stores.
+constexpr int AB_STRIDE = 100;                   // floats per staged row (96 + 4: float4 reads of different rows hit different banks)
+constexpr int AB_PS = 20;                        // row stride of the P / dS tiles
+constexpr int AB_ITEM = 4 * kTokens * AB_STRIDE + 2 * kTokens * AB_PS;  // floats per warp
+constexpr int AB_WARPS = 6;
+constexpr int AB_SMEM = AB_WARPS * AB_ITEM * (int)sizeof(float);  // 200,640 B
+
+__global__ void __launch_bounds__(AB_WARPS * 32)
+attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int64_t n_seq, float* g_f32,
+                     __nv_bfloat16* g_hi, __nv_bfloat16* g_lo) {
+    extern __shared__ float4 ab_smem[];
+    constexpr int LD = 3 * kDim, V4 = kHeadDim / 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* sQ = reinterpret_cast<float*>(ab_smem) + wid * AB_ITEM;
+    float* sK = sQ + kTokens * AB_STRIDE;
+    float* sV = sK + kTokens * AB_STRIDE;
+    float* sDO = sV + kTokens * AB_STRIDE;
+    float* sP = sDO + kTokens * AB_STRIDE;
+    float* sDS = sP + kTokens * AB_PS;
+    const float scale = 0.10206207261596575f;
+    const int64_t items = n_seq * kHeads;
+    for (int64_t item = (int64_t)blockIdx.x * AB_WARPS + wid; item < items; item += (int64_t)gridDim.x * AB_WARPS) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
+        const float* dob = d_out + (size_t)seq * kTokens * kDim + h * kHeadDim;
+        __syncwarp();
+        for (int idx = lane; idx < 4 * kTokens * V4; idx += 32) {
+            const int m = idx / V4, c = idx - m * V4;
+            const int which = m / kTokens, row = m - which * kTokens;
+            const float4 v = which < 3 ? __ldg((const float4*)(base + (size_t)row * LD + which * kDim) + c)
+                                       : __ldg((const float4*)(dob + (size_t)row * kDim) + c);
+            *((float4*)(sQ + (which * kTokens + row) * AB_STRIDE) + c) = v;
+        }
+        __syncwarp();
+        float ds[kTokens];
+        if (lane < kTokens) {
+            float p[kTokens], dp[kTokens];
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) { p[j] = 0.f; dp[j] = 0.f; }
+            const float4* q4 = (const float4*)(sQ + lane * AB_STRIDE);
+            const float4* do4 = (const float4*)(sDO + lane * AB_STRIDE);
+#pragma unroll 2
+            for (int c = 0; c < V4; ++c) {
+                const float4 q = q4[c], g = do4[c];
+#pragma unroll
+                for (int j = 0; j < kTokens; ++j) {
+                    const float4 k4 = *((const float4*)(sK + j * AB_STRIDE) + c);
+                    const float4 v4 = *((const float4*)(sV + j * AB_STRIDE) + c);
+                    p[j] = fmaf(q.x, k4.x, p[j]); p[j] = fmaf(q.y, k4.y, p[j]);
+                    p[j] = fmaf(q.z, k4.z, p[j]); p[j] = fmaf(q.w, k4.w, p[j]);
+                    dp[j] = fmaf(g.x, v4.x, dp[j]); dp[j] = fmaf(g.y, v4.y, dp[j]);
+                    dp[j] = fmaf(g.z, v4.z, dp[j]); dp[j] = fmaf(g.w, v4.w, dp[j]);
+                }
+            }
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) {
+                p[j] *= scale;
+                m = fmaxf(m, p[j]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) {
+                p[j] = expf(p[j] - m);
+                sum += p[j];
+            }
+            const float inv = 1.f / sum;
+            float dsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) {
+                p[j] *= inv;
+                dsum = fmaf(p[j], dp[j], dsum);
+            }
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) {
+                ds[j] = p[j] * (dp[j] - dsum) * scale;
+                sP[lane * AB_PS + j] = p[j];
+                sDS[lane * AB_PS + j] = ds[j];
+            }
+        }
+        __syncwarp();  // every lane is done with V: dQ may overwrite it
+        if (lane < kTokens) {
+            float4* dq4 = (float4*)(sV + lane * AB_STRIDE);
+#pragma unroll 2
+            for (int c = 0; c < V4; ++c) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < kTokens; ++j) {
+                    const float4 k4 = *((const float4*)(sK + j * AB_STRIDE) + c);
+                    a.x = fmaf(ds[j], k4.x, a.x); a.y = fmaf(ds[j], k4.y, a.y);
+                    a.z = fmaf(ds[j], k4.z, a.z); a.w = fmaf(ds[j], k4.w, a.w);
+                }
+                dq4[c] = a;
+            }
+        }
+        __syncwarp();  // K is free now: dK overwrites it; lane j = key row j, column j of dS / P
+        float col[kTokens];
+        if (lane < kTokens) {
+#pragma unroll
+            for (int i = 0; i < kTokens; ++i) col[i] = sDS[i * AB_PS + lane];
+            float4* dk4 = (float4*)(sK + lane * AB_STRIDE);
+#pragma unroll 2
+            for (int c = 0; c < V4; ++c) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < kTokens; ++i) {
+                    const float4 q4 = *((const float4*)(sQ + i * AB_STRIDE) + c);
+                    a.x = fmaf(col[i], q4.x, a.x); a.y = fmaf(col[i], q4.y, a.y);
+                    a.z = fmaf(col[i], q4.z, a.z); a.w = fmaf(col[i], q4.w, a.w);
+                }
+                dk4[c] = a;
+            }
+        }
+        __syncwarp();  // Q is free now: dV overwrites it
+        if (lane < kTokens) {
+#pragma unroll
+            for (int i = 0; i < kTokens; ++i) col[i] = sP[i * AB_PS + lane];
+            float4* dv4 = (float4*)(sQ + lane * AB_STRIDE);
+#pragma unroll 2
+            for (int c = 0; c < V4; ++c) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < kTokens; ++i) {
+                    const float4 g4 = *((const float4*)(sDO + i * AB_STRIDE) + c);
+                    a.x = fmaf(col[i], g4.x, a.x); a.y = fmaf(col[i], g4.y, a.y);
+                    a.z = fmaf(col[i], g4.z, a.z); a.w = fmaf(col[i], g4.w, a.w);
+                }
+                dv4[c] = a;
+            }
+        }
+        __syncwarp();
+        // dq (in sV) -> cols [0,576), dk (sK) -> [576,1152), dv (sQ) -> [1152,1728) of the head's 96-wide slice
+        for (int idx = lane; idx < 3 * kTokens * V4; idx += 32) {
+            const int m = idx / V4, c = idx - m * V4;
+            const int which = m / kTokens, row = m - which * kTokens;
+            const float* srcb = which == 0 ? sV : which == 1 ? sK : sQ;
+            const float4 v = *((const float4*)(srcb + row * AB_STRIDE) + c);
+            const size_t o = ((size_t)seq * kTokens + row) * LD + which * kDim + h * kHeadDim + 4 * c;
+            if (g_f32) *(float4*)(g_f32 + o) = v;
+            if (g_hi) {
+                uint2 hh, ll;
+                split_pair(v.x, v.y, hh.x, ll.x);
+                split_pair(v.z, v.w, hh.y, ll.y);
+                *(uint2*)(g_hi + o) = hh;
+                if (g_lo) *(uint2*)(g_lo + o) = ll;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- relation-token backward
+// grid (N boxes, 18 slots): slot p < 16 = patch token 1+p, 16 = location token, 17 = class token.  The block scans the
+// pairs of the box's image in order and adds the token-gradient rows of the pairs the box is subject / object of
+// (thread t owns float4 column t, like tokens_kernel): a deterministic gather instead of an atomic scatter.
+__device__ __forceinline__ void acc4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+__global__ void __launch_bounds__(kDim / 4)
+tokens_bwd_kernel(const float* __restrict__ dx, const int32_t* __restrict__ subj, const int32_t* __restrict__ obj,
+                  const int32_t* __restrict__ rel_offsets, const int32_t* __restrict__ box_offsets, int n_images,
+                  const float* __restrict__ lso, const float* __restrict__ cso, float* __restrict__ d_so_d,
+                  float* __restrict__ d_so_v, float* __restrict__ d_lso, float* __restrict__ d_cso) {
+    __shared__ int s_img;
+    const int b = blockIdx.x, slot = blockIdx.y, t = threadIdx.x;
+    if (t == 0) {
+        int lo = 0, hi = n_images - 1;  // last image whose first box is <= b
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (box_offsets[mid] <= b) lo = mid; else hi = mid - 1;
+        }
+        // skip empty images that share the offset
+        while (lo + 1 < n_images && box_offsets[lo + 1] <= b) ++lo;
+        s_img = lo;
+    }
+    __syncthreads();
+    const int r0 = rel_offsets[s_img], r1 = rel_offsets[s_img + 1];
+    const int tok = slot < kPatches ? 1 + slot : slot + 1;  // 16 -> 17, 17 -> 18
+    float4 as = make_float4(0.f, 0.f, 0.f, 0.f), ao = as;
+    if (slot < kPatches) {
+        for (int r = r0; r < r1; ++r) {
+            const int s = subj[r], o = obj[r];
+            if (s == b || o == b) {
+                const float4 g = __ldg((const float4*)(dx + ((size_t)r * kTokens + tok) * kDim) + t);
+                if (s == b) acc4(as, g);
+                if (o == b) acc4(ao, g);
+            }
+        }
+        if (t < kDimDepth / 4) {
+            float4* dst = (float4*)(d_so_d + ((size_t)b * kPatches + slot) * 2 * kDimDepth);
+            dst[t] = as;
+            dst[kDimDepth / 4 + t] = ao;
+        } else {
+            const int tv = t - kDimDepth / 4;
+            float4* dst = (float4*)(d_so_v + ((size_t)b * kPatches + slot) * 2 * kDimRgb);
+            dst[tv] = as;
+            dst[kDimRgb / 4 + tv] = ao;
+        }
+    } else {
+        const float* pre = slot == kPatches ? lso : cso;
+        float* dst = slot == kPatches ? d_lso : d_cso;
+        const float4 own_s = __ldg((const float4*)(pre + (size_t)b * 2 * kDim) + t);
+        const float4 own_o = __ldg((const float4*)(pre + (size_t)b * 2 * kDim + kDim) + t);
+        for (int r = r0; r < r1; ++r) {
+            const int s = subj[r], o = obj[r];
+            if (s == b || o == b) {
+                const float4 g = __ldg((const float4*)(dx + ((size_t)r * kTokens + tok) * kDim) + t);
+                if (s == b) {  // ReLU(pre_s[b] + pre_o[o]) (tokens.cu)
+                    const float4 other = __ldg((const float4*)(pre + (size_t)o * 2 * kDim + kDim) + t);
+                    as.x += (own_s.x + other.x > 0.f) ? g.x : 0.f; as.y += (own_s.y + other.y > 0.f) ? g.y : 0.f;
+                    as.z += (own_s.z + other.z > 0.f) ? g.z : 0.f; as.w += (own_s.w + other.w > 0.f) ? g.w : 0.f;
+                }
+                if (o == b) {
+                    const float4 other = __ldg((const float4*)(pre + (size_t)s * 2 * kDim) + t);
+                    ao.x += (other.x + own_o.x > 0.f) ? g.x : 0.f; ao.y += (other.y + own_o.y > 0.f) ? g.y : 0.f;
+                    ao.z += (other.z + own_o.z > 0.f) ? g.z : 0.f; ao.w += (other.w + own_o.w > 0.f) ? g.w : 0.f;
+                }
+            }
+        }
+        ((float4*)(dst + (size_t)b * 2 * kDim))[t] = as;
+        ((float4*)(dst + (size_t)b * 2 * kDim + kDim))[t] = ao;
+    }
+}
+
+// ---------------------------------------------------------------- box stage, training mode
+// BatchNorm1d(4) batch statistics over all boxes of the step (roi_relation_predictors.py:4042-4047 in train()):
+// stats[0..3] = mean, stats[4..7] = biased variance; running stats updated with `momentum` (unbiased variance).
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ boxes, int n, float momentum, float* __restrict__ stats, float* running_mean,
+                float* running_var) {
+    __shared__ double red[256][4];
+    auto feat = [&](int i, float (&f)[4]) {
+        const float4 bx = __ldg((const float4*)boxes + i);
+        const float w = bx.z - bx.x + 1.f, h = bx.w - bx.y + 1.f;
+        f[0] = bx.x + 0.5f * w; f[1] = bx.y + 0.5f * h; f[2] = w; f[3] = h;
+    };
+    auto block_sum4 = [&](double (&a)[4]) {
+        for (int k = 0; k < 4; ++k) red[threadIdx.x][k] = a[k];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o)
+                for (int k = 0; k < 4; ++k) red[threadIdx.x][k] += red[threadIdx.x + o][k];
+            __syncthreads();
+        }
+        for (int k = 0; k < 4; ++k) a[k] = red[0][k];
+        __syncthreads();
+    };
+    double a[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += 256) {
+        float f[4];
+        feat(i, f);
+        for (int k = 0; k < 4; ++k) a[k] += f[k];
+    }
+    block_sum4(a);
+    double mean[4];
+    for (int k = 0; k < 4; ++k) mean[k] = a[k] / n;
+    double q[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += 256) {
+        float f[4];
+        feat(i, f);
+        for (int k = 0; k < 4; ++k) q[k] += (f[k] - mean[k]) * (f[k] - mean[k]);
+    }
+    block_sum4(q);
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        stats[k] = (float)mean[k];
+        stats[4 + k] = (float)(q[k] / n);
+        if (running_mean) running_mean[k] = (1.f - momentum) * running_mean[k] + momentum * (float)mean[k];
+        if (running_var) running_var[k] = (1.f - momentum) * running_var[k] + momentum * (float)(q[k] / (n > 1 ? n - 1 : 1));
+    }
+}
+
+// pos = dropout(ReLU(Linear(4,128)(BN(f)))) backward, single block of 128 threads (thread t = pos feature t):
+// d pos_w [128,4], d pos_b [128], d bn_weight [4], d bn_bias [4].  No gradient flows into the boxes.
+__global__ void __launch_bounds__(128)
+pos_embed_bwd_kernel(const float* __restrict__ boxes, int n, const float* __restrict__ stats, const float* __restrict__ bn_w,
+                     const float* __restrict__ bn_b, const float* __restrict__ pos_w, const float* __restrict__ pos_out,
+                     const float* __restrict__ d_pos, float drop_scale, float* __restrict__ g_pos_w, float* __restrict__ g_pos_b,
+                     float* __restrict__ g_bn_w, float* __restrict__ g_bn_b) {
+    __shared__ float red[4][4];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    float w[4], gw[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = pos_w[t * 4 + k];
+    float mean[4], rstd[4], gam[4], bet[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mean[k] = stats[k];
+        rstd[k] = 1.f / sqrtf(stats[4 + k] + 1e-5f);
+        gam[k] = bn_w[k];
+        bet[k] = bn_b[k];
+    }
+    float g_gamma = 0.f, g_beta = 0.f;  // thread k < 4 accumulates feature k
+    for (int i = 0; i < n; ++i) {
+        const float4 bx = __ldg((const float4*)boxes + i);
+        const float bw = bx.z - bx.x + 1.f, bh = bx.w - bx.y + 1.f;
+        const float f[4] = {bx.x + 0.5f * bw, bx.y + 0.5f * bh, bw, bh};
+        float xh[4], bn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xh[k] = (f[k] - mean[k]) * rstd[k];
+            bn[k] = xh[k] * gam[k] + bet[k];
+        }
+        const float g = pos_out[(size_t)i * kPosDim + t] > 0.f ? d_pos[(size_t)i * kPosDim + t] * drop_scale : 0.f;
+        gb += g;
+        float part[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gw[k] = fmaf(g, bn[k], gw[k]);
+            part[k] = warp_sum(g * w[k]);
+        }
+        __syncthreads();
+        if (lane == 0)
+            for (int k = 0; k < 4; ++k) red[wid][k] = part[k];
+        __syncthreads();
+        if (t < 4) {
+            const float dbn = red[0][t] + red[1][t] + red[2][t] + red[3][t];
+            g_gamma = fmaf(dbn, xh[t], g_gamma);
+            g_beta += dbn;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g_pos_w[t * 4 + k] = gw[k];
+    g_pos_b[t] = gb;
+    if (t < 4) {
+        g_bn_w[t] = g_gamma;
+        g_bn_b[t] = g_beta;
+    }
+}
+
+// d obj_embed[c, :] = sum over boxes with label c of d_emb[n, :]   (block per class, fixed box order)
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const float* __restrict__ d_emb, const int64_t* __restrict__ labels, int n, float* __restrict__ g_embed) {
+    const int c = blockIdx.x, d = threadIdx.x;
+    if (d >= kEmbDim) return;
+    float a = 0.f;
+    for (int i = 0; i < n; ++i)
+        if (labels[i] == c) a += d_emb[(size_t)i * kEmbDim + d];
+    g_embed[(size_t)c * kEmbDim + d] = a;
+}
+
+// soft class embedding emb = softmax(z) @ E (roi_relation_predictors.py:4095): d E[c, :] = sum_n softmax(z_n)[c] d_emb[n, :]
+// (obj_logits are detached in the reference, so no gradient flows into them).  Block per class.
+__global__ void __launch_bounds__(256)
+embed_soft_bwd_kernel(const float* __restrict__ d_emb, const float* __restrict__ obj_logits, int num_obj, int n,
+                      float* __restrict__ g_embed) {
+    __shared__ float s_p;
+    const int c = blockIdx.x, d = threadIdx.x;
+    float a = 0.f;
+    for (int i = 0; i < n; ++i) {
+        if (d < 32) {  // warp 0: softmax probability of class c for box i
+            const float* z = obj_logits + (size_t)i * num_obj;
+            float m = -INFINITY;
+            for (int k = d; k < num_obj; k += 32) m = fmaxf(m, z[k]);
+            m = warp_max(m);
+            float s = 0.f;
+            for (int k = d; k < num_obj; k += 32) s += expf(z[k] - m);
+            s = warp_sum(s);
+            if (d == 0) s_p = expf(z[c] - m) / s;
+        }
+        __syncthreads();
+        if (d < kEmbDim) a = fmaf(s_p, d_emb[(size_t)i * kEmbDim + d], a);
+        __syncthreads();
+    }
+    if (d < kEmbDim) g_embed[(size_t)c * kEmbDim + d] = a;
+}
+
+// inverse of patchify_kernel: d_patch rows [N*16, 1024] in (p1 p2 c) order -> d_roi [N,256,8,8]
+__global__ void __launch_bounds__(256)
+unpatchify_kernel(const float* __restrict__ d_patch, float* __restrict__ d_roi) {
+    __shared__ float tile[32][65];
+    const int n = blockIdx.x, c0 = blockIdx.y * 32, t = threadIdx.x;
+    for (int e = t; e < 64 * 32; e += 256) {
+        const int c = e & 31, q = e >> 5;
+        const int patch = q >> 2, pp = q & 3;
+        const int ph = patch >> 2, pw = patch & 3, p1 = pp >> 1, p2 = pp & 1;
+        tile[c][(2 * ph + p1) * 8 + 2 * pw + p2] = d_patch[((size_t)n * kPatches + patch) * kPatchVec + pp * kChannels + c0 + c];
+    }
+    __syncthreads();
+    float* dst = d_roi + ((size_t)n * kChannels + c0) * 64;
+    for (int e = t; e < 32 * 64; e += 256) dst[e] = tile[e >> 6][e & 63];
+}
+
+// gradient of a factored weight back in the reference's layout (inverse index maps of pack_halves / pack_patch)
+__global__ void unpack_halves_kernel(const float* __restrict__ g_packed, float* __restrict__ g_src, int out, int in) {
+    const int total = 2 * out * in;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int i = e % in, r = e / in;
+        const int h = r / out, o = r - h * out;
+        g_src[(size_t)o * 2 * in + h * in + i] = g_packed[e];
+    }
+}
+__global__ void unpack_patch_kernel(const float* __restrict__ g_packed, float* __restrict__ g_src, int out) {
+    const int total = 2 * out * kPatchVec;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int col = e % kPatchVec, r = e / kPatchVec;
+        const int h = r / out, o = r - h * out;
+        const int p = col / kChannels, c = col - p * kChannels;
+        g_src[(size_t)o * 2 * kPatchVec + p * 2 * kChannels + h * kChannels + c] = g_packed[e];
+    }
+}
+
+// dst[r * ld_dst + c] = src[r * ld_src + c] for a [rows, cols] block (strided row copy, fp32)
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(const float* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst, int64_t rows, int cols) {
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols;
+        const int c = (int)(e - r * cols);
+        dst[r * ld_dst + c] = src[r * ld_src + c];
+    }
+}
+
+}  // namespace
+
+// ================================================================ host wrappers
+int ce_loss_grad(const float* logits, int C, const int64_t* labels, const float* weight, int64_t rows, float* row_scratch,
+                 float* loss_out, float* dlogits, cudaStream_t s) {
+    if (rows <= 0) return VETO_OK;
+    float* row_loss = row_scratch;
+    float* row_w = row_scratch + rows;
+    float* inv_w = row_scratch + 2 * rows;
+    const int grid = grid_cap((size_t)(rows + 7) / 8, 8);
+    ce_rows_kernel<<<grid, 256, 0, s>>>(logits, C, labels, weight, rows, row_loss, row_w);
+    VETO_LAUNCH_CHECK();
+    ce_finalize_kernel<<<1, 1024, 0, s>>>(row_loss, row_w, rows, loss_out, inv_w);
+    VETO_LAUNCH_CHECK();
+    ce_grad_kernel<<<grid, 256, 0, s>>>(logits, C, labels, weight, inv_w, rows, dlogits);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+size_t colsum_scratch_floats(int cols) { return (size_t)kColsumMaxChunks * cols; }
+
+int colsum(const ActIn& src, int64_t ld, int64_t rows, int cols, float* scratch, float* out, bool accumulate, cudaStream_t s) {
+    if (cols <= 0) return VETO_OK;
+    int chunks = (int)((rows + 127) / 128);
+    if (chunks > kColsumMaxChunks) chunks = kColsumMaxChunks;
+    if (chunks < 1) chunks = 1;
+    const int per = (int)((rows + chunks - 1) / chunks);
+    dim3 grid((cols + 127) / 128, chunks);
+    colsum_partial_kernel<<<grid, 128, 0, s>>>(src.f32, src.hi, src.lo, ld, rows, cols, per > 0 ? per : 1, scratch);
+    VETO_LAUNCH_CHECK();
+    colsum_final_kernel<<<(cols + 127) / 128, 128, 0, s>>>(scratch, chunks, cols, out, accumulate ? 1 : 0);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int transpose_f32(const float* src, int64_t ld_src, int64_t rows, int cols, bool gelu, const DropSpec& drop, int64_t drop_ld,
+                  const ActOut& t_out, int64_t ld_dst, int64_t rows_pad, const ActOut& rm_out, int64_t ld_rm, cudaStream_t s) {
+    if (cols <= 0 || rows_pad <= 0) return VETO_OK;
+    dim3 grid((cols + 31) / 32, (unsigned)((rows_pad + 31) / 32));
+    VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "transpose: %lld rows exceed one launch", (long long)rows_pad);
+    transpose_f32_kernel<<<grid, 256, 0, s>>>(src, ld_src, rows, cols, gelu ? TR_OP_GELU : TR_OP_NONE, drop, drop_ld, t_out.f32,
+                                              t_out.hi, t_out.lo, ld_dst, rows_pad, rm_out.f32, rm_out.hi, rm_out.lo, ld_rm);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int transpose_bf16(const __nv_bfloat16* src, int64_t ld_src, int64_t rows, int cols, __nv_bfloat16* dst, int64_t ld_dst,
+                   int64_t rows_pad, cudaStream_t s) {
+    if (cols <= 0 || rows_pad <= 0) return VETO_OK;
+    VETO_REQUIRE((ld_dst & 1) == 0 && (rows_pad & 1) == 0 && (ld_src & 1) == 0, VETO_ERR_ARG, "transpose_bf16: odd strides");
+    dim3 grid((cols + 63) / 64, (unsigned)((rows_pad + 63) / 64));
+    VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "transpose: %lld rows exceed one launch", (long long)rows_pad);
+    transpose_bf16_kernel<<<grid, 256, 0, s>>>(src, ld_src, rows, cols, dst, ld_dst, rows_pad);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int splitk_reduce(const float* partial, int slices, size_t n, size_t stride, float* out, cudaStream_t s) {
+    splitk_reduce_kernel<<<grid_cap((n + 255) / 256, 8), 256, 0, s>>>(partial, slices, n, stride, out);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int dropout_inplace(float* x, size_t n, const DropSpec& drop, cudaStream_t s) {
+    if (!drop.thr16 || n == 0) return VETO_OK;
+    VETO_REQUIRE(n % 4 == 0, VETO_ERR_ARG, "dropout: element count must be a multiple of 4");
+    dropout_kernel<<<grid_cap((n / 4 + 255) / 256, 8), 256, 0, s>>>(x, n / 4, drop);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int convert_act(const float* src, size_t n, const ActOut& out, cudaStream_t s) {
+    if (n == 0) return VETO_OK;
+    convert_kernel<<<grid_cap((n + 255) / 256, 8), 256, 0, s>>>(src, n, out.f32, out.hi, out.lo);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int ln_bwd_blocks(int64_t rows) { return grid_cap((size_t)(rows + 7) / 8, 4); }
+
+int layernorm_bwd(const float* x, int64_t ldx, const float* dy, const float* gamma, const float* dres, float* dx, int64_t rows,
+                  float* partial, float* colsum_scratch, float* g_gamma, float* g_beta, cudaStream_t s) {
+    if (rows <= 0) return VETO_OK;
+    const int grid = ln_bwd_blocks(rows);
+    ln_bwd_kernel<<<grid, 256, 0, s>>>(x, ldx, dy, gamma, dres, dx, rows, partial);
+    VETO_LAUNCH_CHECK();
+    ActIn p;
+    p.f32 = partial;
+    int rc;
+    if ((rc = colsum(p, 2 * kDim, grid, kDim, colsum_scratch, g_gamma, false, s))) return rc;
+    p.f32 = partial + kDim;
+    return colsum(p, 2 * kDim, grid, kDim, colsum_scratch, g_beta, false, s);
+}
+
+int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const ActOut& d_qkv, cudaStream_t s) {
+    if (n_seq <= 0) return VETO_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VETO_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        attr_set = true;
+    }
+    const int64_t blocks = (n_seq * kHeads + AB_WARPS - 1) / AB_WARPS;
+    const int grid = (int)(blocks < num_sms() ? blocks : num_sms());
+    attention_bwd_kernel<<<grid, AB_WARPS * 32, AB_SMEM, s>>>(qkv, d_out, n_seq, d_qkv.f32, d_qkv.hi, d_qkv.lo);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int tokens_bwd(const float* dx, const int32_t* subj, const int32_t* obj, const int32_t* rel_offsets, const int32_t* box_offsets,
+               int n_images, int n_boxes, const float* lso, const float* cso, float* d_so_d, float* d_so_v, float* d_lso,
+               float* d_cso, cudaStream_t s) {
+    if (n_boxes <= 0) return VETO_OK;
+    dim3 grid(n_boxes, kPatches + 2);
+    tokens_bwd_kernel<<<grid, kDim / 4, 0, s>>>(dx, subj, obj, rel_offsets, box_offsets, n_images, lso, cso, d_so_d, d_so_v,
+                                                d_lso, d_cso);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int bn_batch_stats(const float* boxes, int n_boxes, float momentum, float* stats, float* running_mean, float* running_var,
+                   cudaStream_t s) {
+    bn_stats_kernel<<<1, 256, 0, s>>>(boxes, n_boxes, momentum, stats, running_mean, running_var);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int pos_embed_bwd(const float* boxes, int n_boxes, const float* stats, const veto_weights& w, const float* pos_out,
+                  const float* d_pos, float drop_scale, float* g_pos_w, float* g_pos_b, float* g_bn_w, float* g_bn_b,
+                  cudaStream_t s) {
+    pos_embed_bwd_kernel<<<1, 128, 0, s>>>(boxes, n_boxes, stats, w.bn_weight, w.bn_bias, w.pos_w, pos_out, d_pos, drop_scale,
+                                           g_pos_w, g_pos_b, g_bn_w, g_bn_b);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int embed_bwd(const float* d_emb, const int64_t* labels, const float* obj_logits, int num_obj, int n_boxes, float* g_embed,
+              cudaStream_t s) {
+    if (labels) embed_bwd_kernel<<<num_obj, 256, 0, s>>>(d_emb, labels, n_boxes, g_embed);
+    else embed_soft_bwd_kernel<<<num_obj, 256, 0, s>>>(d_emb, obj_logits, num_obj, n_boxes, g_embed);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int unpatchify(const float* d_patch, int n_boxes, float* d_roi, cudaStream_t s) {
+    if (n_boxes <= 0) return VETO_OK;
+    dim3 grid(n_boxes, kChannels / 32);
+    unpatchify_kernel<<<grid, 256, 0, s>>>(d_patch, d_roi);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int unpack_halves(const float* g_packed, float* g_src, int out, int in, cudaStream_t s) {
+    unpack_halves_kernel<<<grid_cap(((size_t)2 * out * in + 255) / 256, 8), 256, 0, s>>>(g_packed, g_src, out, in);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+int unpack_patch(const float* g_packed, float* g_src, int out, cudaStream_t s) {
+    unpack_patch_kernel<<<grid_cap(((size_t)2 * out * kPatchVec + 255) / 256, 8), 256, 0, s>>>(g_packed, g_src, out);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int copy_rows(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int cols, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return VETO_OK;
+    copy_rows_kernel<<<grid_cap((size_t)((rows * cols + 255) / 256), 8), 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+}  // namespace veto

@@ -17,6 +17,33 @@ from .registry import ROI_BOX_FEATURE_EXTRACTORS
 from .structures import xyxy_boxes
 
 
+class _RoiGather(torch.autograd.Function):
+    """veto_roi_gather_forward with the backward the reference gets from _ROIAlign.backward
+    (pysgg/layers/roi_align.py:26-44 -> _C.roi_align_backward): the gradient of the pooled depth features is
+    scattered back into the depth map (the depth backbone is trainable, tools/relation_train_net.py:166-170).
+    The RGB FPN maps come from the frozen backbone (relation_train_net.py:161-165) and get no gradient."""
+
+    @staticmethod
+    def forward(ctx, depth, boxes, n_boxes, scales, depth_scale, pool, sampling_ratio, k_min, k_max, *feats):
+        x_2d, d_2d = ops.roi_gather(list(feats), depth, boxes, n_boxes, scales, depth_scale, pool=pool,
+                                    sampling_ratio=sampling_ratio, k_min=k_min, k_max=k_max)
+        ctx.save_for_backward(boxes)
+        ctx.meta = (tuple(depth.shape), list(n_boxes), depth_scale, pool, sampling_ratio, len(feats))
+        ctx.mark_non_differentiable(x_2d)
+        return x_2d, d_2d
+
+    @staticmethod
+    def backward(ctx, g_x, g_d):
+        (boxes,) = ctx.saved_tensors
+        shape, n_boxes, depth_scale, pool, sampling_ratio, n_feats = ctx.meta
+        g_depth = None
+        if ctx.needs_input_grad[0] and g_d is not None:
+            B, C, H, W = shape
+            g_depth = ops.roi_align_backward(g_d.contiguous(), _rois(boxes, n_boxes), depth_scale, pool, pool, B, C, H, W,
+                                             sampling_ratio)
+        return (g_depth,) + (None,) * (8 + n_feats)
+
+
 @ROI_BOX_FEATURE_EXTRACTORS.register("VETOFeatureExtractor")
 class VETOFeatureExtractor(nn.Module):
     def __init__(self, cfg, in_channels, half_out=False, cat_all_levels=False, for_relation=False):
@@ -45,9 +72,13 @@ class VETOFeatureExtractor(nn.Module):
             d_2d = ops.roi_align_forward(depth_features, _rois(boxes, n_boxes), self.scales[0], self.resolution,
                                          self.resolution, self.sampling_ratio)
         else:
-            x_2d, d_2d = ops.roi_gather(feats, depth_features, boxes, n_boxes, self.scales, self.depth_scale,
-                                        pool=self.resolution, sampling_ratio=self.sampling_ratio, k_min=self.k_min,
-                                        k_max=self.k_max)
+            if torch.is_grad_enabled() and depth_features.requires_grad:
+                x_2d, d_2d = _RoiGather.apply(depth_features, boxes, n_boxes, self.scales, self.depth_scale,
+                                              self.resolution, self.sampling_ratio, self.k_min, self.k_max, *feats)
+            else:
+                x_2d, d_2d = ops.roi_gather(feats, depth_features, boxes, n_boxes, self.scales, self.depth_scale,
+                                            pool=self.resolution, sampling_ratio=self.sampling_ratio, k_min=self.k_min,
+                                            k_max=self.k_max)
         return x_2d, d_2d, None, None
 
 

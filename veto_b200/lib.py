@@ -45,6 +45,21 @@ class VetoOutputs(Structure):
     _fields_ = [("rel_logits", c_void_p), ("rel_features", c_void_p), ("tokens", c_void_p)]
 
 
+class VetoTrainInputs(Structure):
+    _fields_ = [("rel_labels", c_void_p), ("class_weight", c_void_p), ("rel_offsets", c_void_p),
+                ("box_offsets", c_void_p), ("n_images", c_int32), ("p_pos_dropout", c_float),
+                ("p_emb_dropout", c_float), ("p_attn_dropout", c_float), ("seed", ctypes.c_uint64),
+                ("bn_momentum", c_float), ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p)]
+
+
+class VetoGrads(VetoWeights):
+    """veto_grads: the field order of veto_weights, non-const pointers."""
+
+
+class VetoTrainOutputs(Structure):
+    _fields_ = [("loss", c_void_p), ("rel_logits", c_void_p), ("grad_roi_depth", c_void_p), ("grad_roi_rgb", c_void_p)]
+
+
 class VetoError(RuntimeError):
     """A negative return code from libveto_b200 (the reference raises RuntimeError from AT_ERROR)."""
 
@@ -68,6 +83,10 @@ _PROTOS = {
     "veto_workspace_bytes": (c_size_t, [POINTER(VetoConfig), c_int32, c_int64, c_int32]),
     "veto_relation_forward": (c_int, [POINTER(VetoConfig), POINTER(VetoWeights), _fp, POINTER(VetoInputs),
                                       POINTER(VetoOutputs), _fp, c_size_t, c_int32, c_void_p]),
+    "veto_train_workspace_bytes": (c_size_t, [POINTER(VetoConfig), c_int32, c_int64]),
+    "veto_relation_train_step": (c_int, [POINTER(VetoConfig), POINTER(VetoWeights), _fp, POINTER(VetoInputs),
+                                         POINTER(VetoTrainInputs), POINTER(VetoGrads), POINTER(VetoTrainOutputs), _fp,
+                                         c_size_t, c_void_p]),
     "veto_last_launch_count": (c_int64, []),
     "veto_profile_begin": (c_int, [c_void_p]),
     "veto_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),

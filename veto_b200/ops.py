@@ -282,6 +282,111 @@ def relation_forward(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.Tens
 
 
 # --------------------------------------------------------------------------------------------
+# a11: training step (forward in train() mode + loss + backward)
+# --------------------------------------------------------------------------------------------
+def grad_fields(n_layers: int) -> List[Tuple[str, Optional[int], str]]:
+    """(veto_grads field, layer or None, state_dict key relative to the trunk) of every parameter the training
+    step produces a gradient for, in a fixed order (the layout of the flat gradient buffer)."""
+    out = []
+    for field, key in _SCALAR_KEYS.items():
+        if field in ("bn_mean", "bn_var"):
+            continue  # running statistics: buffers, no gradient
+        out.append((field, None, key))
+    for i in range(n_layers):
+        for field, key in _LAYER_KEYS.items():
+            out.append((field, i, f"fusion_transformer.transformer.layers.{i}.{key}"))
+    return out
+
+
+def relation_train_step(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.Tensor, roi_depth: torch.Tensor,
+                        subj: torch.Tensor, obj: torch.Tensor, rel_labels: torch.Tensor, rel_counts: Sequence[int],
+                        n_boxes: Sequence[int], grads: Dict[str, torch.Tensor], rel_out_w_grad: torch.Tensor,
+                        rel_out_b_grad: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                        obj_logits: Optional[torch.Tensor] = None, class_weight: Optional[torch.Tensor] = None,
+                        p_pos: float = 0.1, p_emb: float = 0.35, p_attn: float = 0.35, seed: int = 0,
+                        bn_momentum: float = 0.001, bn_running_mean: Optional[torch.Tensor] = None,
+                        bn_running_var: Optional[torch.Tensor] = None, want_roi_depth_grad: bool = True,
+                        want_roi_rgb_grad: bool = False, return_logits: bool = False):
+    """veto_relation_train_step: rel_loss of VETOPredictor.forward in train() mode and its gradients.
+
+    `grads` maps the trunk's state_dict keys (grad_fields) to fp32 CUDA tensors of the parameter shapes; they are
+    OVERWRITTEN.  Returns (loss [1], grad_roi_depth or None, grad_roi_rgb or None, logits or None)."""
+    global last_launch_count
+    lib = L.load()
+    cfg = pw.cfg
+    dev = pw.device
+    boxes, roi_rgb, roi_depth = _cuda_f32(boxes), _cuda_f32(roi_rgb), _cuda_f32(roi_depth)
+    N, R = boxes.shape[0], subj.shape[0]
+    if N == 0 or R == 0:
+        raise RuntimeError("a training step needs at least one box and one pair")
+    if tuple(roi_rgb.shape) != (N, 256, 8, 8) or tuple(roi_depth.shape) != (N, 256, 8, 8):
+        raise RuntimeError(f"roi features must be [{N},256,8,8], got {tuple(roi_rgb.shape)} / {tuple(roi_depth.shape)}")
+    if sum(rel_counts) != R or sum(n_boxes) != N or rel_labels.shape[0] != R:
+        raise RuntimeError("rel_counts / n_boxes / rel_labels do not match the pair and box tensors")
+    subj = subj.to(torch.int32).contiguous()
+    obj = obj.to(torch.int32).contiguous()
+    rel_labels = rel_labels.to(torch.int64).contiguous()
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    if obj_logits is not None:
+        obj_logits = _cuda_f32(obj_logits)
+    if class_weight is not None:
+        class_weight = _cuda_f32(class_weight)
+    rel_off = offsets_tensor(rel_counts, dev)
+    box_off = offsets_tensor(n_boxes, dev)
+    g = L.VetoGrads()
+    for field, layer, key in grad_fields(cfg.layers):
+        t = grads[key]
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"gradient buffer of {key} must be a contiguous fp32 CUDA tensor")
+        if layer is None:
+            setattr(g, field, t.data_ptr())
+        else:
+            getattr(g, field)[layer] = t.data_ptr()
+    g.rel_out_w, g.rel_out_b = rel_out_w_grad.data_ptr(), rel_out_b_grad.data_ptr()
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    logits = torch.empty((R, cfg.num_out), dtype=torch.float32, device=dev) if return_logits else None
+    g_depth = torch.empty_like(roi_depth) if want_roi_depth_grad else None
+    g_rgb = torch.empty_like(roi_rgb) if want_roi_rgb_grad else None
+    nbytes = lib.veto_train_workspace_bytes(ctypes.byref(cfg), N, R)
+    ws = _workspace(dev, nbytes)
+    vin = L.VetoInputs(N, R, boxes.data_ptr(), L.ptr(labels), L.ptr(obj_logits), roi_rgb.data_ptr(),
+                       roi_depth.data_ptr(), subj.data_ptr(), obj.data_ptr(), None)
+    tin = L.VetoTrainInputs(rel_labels.data_ptr(), L.ptr(class_weight), rel_off.data_ptr(), box_off.data_ptr(),
+                            len(rel_counts), float(p_pos), float(p_emb), float(p_attn), int(seed) & (2 ** 64 - 1),
+                            float(bn_momentum), L.ptr(bn_running_mean), L.ptr(bn_running_var))
+    tout = L.VetoTrainOutputs(loss.data_ptr(), L.ptr(logits), L.ptr(g_depth), L.ptr(g_rgb))
+    with torch.cuda.device(dev):
+        L.check(lib.veto_relation_train_step(ctypes.byref(cfg), ctypes.byref(pw.struct), pw.packed.data_ptr(),
+                                             ctypes.byref(vin), ctypes.byref(tin), ctypes.byref(g), ctypes.byref(tout),
+                                             ws.data_ptr(), ws.numel(), L.stream_ptr()), "veto_relation_train_step")
+    last_launch_count = int(lib.veto_last_launch_count())
+    return loss, g_depth, g_rgb, logits
+
+
+def dropout_keep_mask(seed: int, sub: int, n: int, p: float):
+    """The keep mask (numpy bool [n]) the library uses for stream `sub` of a step seeded `seed` (csrc/common.cuh
+    drop_hash / train_api.cu sub_seed): sub 1 = pos_embed dropout over [N,128], 2 = token dropout over [R,19,576],
+    16 + l = to_out dropout of layer l over [R*19,576].  For tests that reproduce a dropped step on the oracle."""
+    import numpy as np
+    M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def mix(seed64, group):
+        with np.errstate(over="ignore"):
+            z = (seed64 + (group + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)) & M64
+            z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M64
+            z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M64
+            return z ^ (z >> np.uint64(31))
+
+    s = mix(np.uint64(seed & (2 ** 64 - 1)) ^ np.uint64(0xA5A5A5A5A5A5A5A5), np.uint64(sub))
+    e = np.arange(n, dtype=np.uint64)
+    h = mix(s, e >> np.uint64(2))
+    field = (h >> (np.uint64(16) * (e & np.uint64(3)))) & np.uint64(0xFFFF)
+    thr = np.uint64(int(p * 65536.0 + 0.5))
+    return field >= thr if p > 0 else np.ones(n, dtype=bool)
+
+
+# --------------------------------------------------------------------------------------------
 # a12: post-processing
 # --------------------------------------------------------------------------------------------
 def postprocess(rel_logits: torch.Tensor, pairs: torch.Tensor, obj_scores: torch.Tensor, rel_counts: Sequence[int],

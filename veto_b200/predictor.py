@@ -8,8 +8,11 @@ state_dict keys as the reference, so reference checkpoints load and ``ROIRelatio
 computation is ``veto_relation_forward`` of libveto_b200.so (sm_100a kernels).  There is no PyTorch or
 CPU fallback: without the library or an sm_100 device, forward raises.
 
-Scope of this round: inference (``eval()``) forward.  The training branch (losses, dropout, BN batch
-statistics, backward) is the next row of SURVEY.md §8 and raises NotImplementedError.
+``eval()`` forward returns the logits; ``train()`` forward of VETOPredictor returns ``add_losses['rel_loss']``
+(roi_relation_predictors.py:4131-4136) as a scalar wired into autograd: ``veto_relation_train_step`` computes the
+loss AND every gradient in one library call, and ``loss.backward()`` hands those gradients to the parameters and
+to ``roi_depth_features`` (so the depth backbone trains through VETOFeatureExtractor's ROIAlign backward).
+The MEET training branch (group sampling, per-group losses) is not built yet and raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -93,6 +96,7 @@ class _Transformer(nn.Module):
         self.patch_embed = _PatchEmbed(in_channels, t.PATCH_SIZE)
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
         self.pos_embedding = nn.Parameter(torch.randn(1, 1, dim))
+        self.pos_drop = nn.Dropout(t.EMB_DROPOUT)  # model_veto.py:43 (no parameters: state_dict unchanged)
         self.layers = nn.ModuleList([
             nn.ModuleList([_PreNorm(dim, _Attention(dim, t.NHEADS, t.T_DROPOUT)),
                            _PreNorm(dim, _FeedForward(dim, dim * 2))])
@@ -154,6 +158,22 @@ class _Trunk(nn.Module):
                                     obj_logits=obj_logits, freq_bias=freq_bias, chunk_pairs=self.chunk_pairs)
 
 
+class _TrainStep(torch.autograd.Function):
+    """rel_loss with all of its gradients computed eagerly by veto_relation_train_step; backward() only scales them
+    by the incoming gradient and hands them to autograd (parameters are inputs, so DDP / optimizers see .grad)."""
+
+    @staticmethod
+    def forward(ctx, module, run, roi_rgb, roi_depth, *params):
+        loss, g_depth, g_rgb, grads = run(want_depth=ctx.needs_input_grad[3], want_rgb=ctx.needs_input_grad[2])
+        ctx.grads, ctx.g_depth, ctx.g_rgb = grads, g_depth, g_rgb
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        scale = lambda t: None if t is None else t * gout
+        return (None, None, scale(ctx.g_rgb), scale(ctx.g_depth)) + tuple(scale(t) for t in ctx.grads)
+
+
 def _mode(config) -> str:
     if config.MODEL.ROI_RELATION_HEAD.USE_GT_BOX:
         return "predcls" if config.MODEL.ROI_RELATION_HEAD.USE_GT_OBJECT_LABEL else "sgcls"
@@ -181,10 +201,64 @@ class VETOPredictor(_Trunk):
         self.use_freq_bias = bool(C.get(config, "VETO_B200.FREQ_BIAS", False))
         self.freq_bias_table = None  # [num_obj^2, num_rel] fp32, set by the caller when use_freq_bias
 
+    # ---- training branch (roi_relation_predictors.py:4131-4136) ----
+    def _trained_params(self):
+        """(state_dict key, parameter) of everything rel_loss depends on, in the order of ops.grad_fields."""
+        named = dict(self.named_parameters())
+        return [(key, named[key]) for _, _, key in ops.grad_fields(self.n_layers)]
+
+    def _train_forward(self, proposals, rel_pair_idxs, rel_labels, roi_features, roi_depth_features, hard, soft):
+        n_boxes = [len(p) for p in proposals]
+        rel_counts = [int(r.shape[0]) for r in rel_pair_idxs]
+        boxes = torch.cat([xyxy_boxes(p) for p in proposals], 0)
+        subj, obj = ops.globalize_pairs(rel_pair_idxs, n_boxes)
+        labels_cat = torch.cat(list(rel_labels), 0).long()
+        keyed = self._trained_params()
+        params = [p for _, p in keyed] + [self.rel_out.weight, self.rel_out.bias]
+        tr = self.fusion_transformer.transformer
+        p_attn = {float(layer[0].fn.to_out[1].p) for layer in tr.layers}
+        if len(p_attn) != 1:
+            raise RuntimeError("veto_b200: every Attention.to_out Dropout must use the same p")
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: follows torch.manual_seed, no device sync
+        bn = self.pos_embed[0]
+
+        def run(want_depth, want_rgb):
+            pw = self._pack(self.rel_out.weight, self.rel_out.bias)
+            flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=boxes.device)
+            views, off = [], 0
+            for p in params:
+                views.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            grads = {key: v for (key, _), v in zip(keyed, views)}
+            loss, g_depth, g_rgb, _ = ops.relation_train_step(
+                pw, boxes, roi_features.detach(), roi_depth_features.detach(), subj, obj, labels_cat, rel_counts, n_boxes,
+                grads, views[-2], views[-1], labels=hard, obj_logits=soft, class_weight=self.criterion_loss_rel.weight,
+                p_pos=float(self.pos_embed[3].p), p_emb=float(tr.pos_drop.p), p_attn=p_attn.pop(), seed=seed,
+                bn_momentum=float(bn.momentum), bn_running_mean=bn.running_mean if bn.track_running_stats else None,
+                bn_running_var=bn.running_var if bn.track_running_stats else None, want_roi_depth_grad=want_depth,
+                want_roi_rgb_grad=want_rgb)
+            if bn.track_running_stats:
+                bn.num_batches_tracked += 1
+            self.last_flat_grad = flat
+            return loss, g_depth, g_rgb, views
+
+        return _TrainStep.apply(self, run, roi_features, roi_depth_features, *params)
+
     def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
                 rel_binarys=None):
         if self.training:
-            raise NotImplementedError("veto_b200.VETOPredictor: the training branch is not built yet (eval() only)")
+            if self.mode == "predcls":
+                hard, soft = torch.cat([p.get_field("labels") for p in proposals], 0).long(), None
+            else:
+                hard, soft = None, torch.cat([p.get_field("predict_logits") for p in proposals], 0).detach()
+            add_losses = {}
+            if self.mode != "predcls":  # :4131-4133: CE of the (detached) one-hot predictions, a constant
+                pred = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
+                fg = torch.cat([p.get_field("labels") for p in proposals], 0).long()
+                add_losses["obj_loss"] = self.criterion_loss(nn.functional.one_hot(pred, self.num_obj_cls).float(), fg)
+            add_losses["rel_loss"] = self._train_forward(proposals, rel_pair_idxs, rel_labels, roi_features,
+                                                         roi_depth_features, hard, soft)
+            return None, None, add_losses, None, None, None
         if self.mode == "predcls":
             obj_labels = torch.cat([p.get_field("labels") for p in proposals], 0).long()
             hard, soft = obj_labels, None
