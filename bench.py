@@ -3,19 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16x3|bf16|fp32]
 
-Workload: BASELINE.json configs[2] — SGDet-shaped inference, 80 proposals / image (6320 candidate pairs, cap
-MAX_PROPOSAL_PAIR 8192), batch 32, VG 151/51, one batch per GPU.  (configs[1] is a training step; the training
-branch of the head is not built yet, so the largest single-GPU inference configuration is the bench line — DESIGN.md.)
-A "step" = prepare_test_pairs -> VETOFeatureExtractor (ROI gather) -> VETOPredictor forward for one batch.
+Headline workload: BASELINE.json configs[1] — VETO vanilla PredCls TRAINING step, IMS_PER_BATCH 12 per GPU, 20 GT
+boxes / image (all 380 ordered pairs per image are under the 1024-pair cap of gtbox_relsample, so a step trains on
+12 x 380 = 4560 pairs), VG 151/51, 592x800 images.  A "step" = candidate pairs -> VETOFeatureExtractor (ROI gather)
+-> VETOPredictor in train() mode with the reference's dropout rates -> rel_loss.backward() (incl. the ROIAlign
+backward into the depth feature map) -> gradient all-reduce (N > 1, NCCL) -> clip_grad_norm 5.0 -> Adam step
+(tools/relation_train_net.py:418-483).
 
-  value : relation pairs / s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks.
-  e2e   : the same metric through the public API from pinned HOST buffers: H2D of the step's feature maps, boxes
-          and logits and D2H of the relation logits inside the timed region.
-  roofline : tcgen05 GEMM kernel (the dominant one): algorithmic FLOPs per launch / CUDA-event duration per
-          launch (veto_profile_*), against MEASURED_PEAKS.json bf16_tflops_sustained.
-  cpu_baseline : the numpy/C oracle (port of the reference's CPU path) on a bounded sample, host cores.
+  value : relation pairs / s trained, whole job, inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e   : the same through the public API from pinned HOST buffers: H2D of the step's feature maps, boxes and labels
+          and D2H of the loss inside the timed region.
+  roofline : gemm_tc2_kernel (tcgen05, forward + both backward GEMMs of every encoder Linear): algorithmic FLOPs per
+          launch / CUDA-event duration per launch (veto_profile_*), against MEASURED_PEAKS.json bf16_tflops_sustained.
+  cpu_baseline : oracle/torch_port.py (the reference's formulation on torch CPU kernels + autograd) on one image.
+  inference : configs[2] (SGDet-shaped inference, 32 images x 80 proposals = 202 240 pairs per step), same keys.
 
-Multi-GPU: images are independent, so every rank runs its own batch (weak scaling, no data-path collective).
+Multi-GPU: images are independent, so every rank runs its own batch (weak scaling); the only collective is the
+gradient all-reduce of the training step.
 """
 from __future__ import annotations
 
@@ -33,24 +37,31 @@ if ROOT not in sys.path:
 
 METRIC = "relation_pairs_per_sec"
 UNIT = "pairs/s"
-N_IMAGES, N_BOXES, MAX_PAIRS = 32, 80, 8192
 IMG_H, IMG_W = 592, 800
-FLOP_PER_PAIR = 648.7e6          # reference formulation (SURVEY.md §8d / BASELINE.md §3)
-WORKLOAD = ("configs[2]: SGDet-shaped inference, 32 images x 80 proposals (6320 pairs/image, MAX_PROPOSAL_PAIR 8192), "
-            "VG 151/51, 592x800 images, P2-P5 + depth NCHW fp32")
+FLOP_PER_PAIR = 648.7e6          # forward, reference formulation (SURVEY.md §8d / BASELINE.md §3)
+# configs[1]: training step
+TR_IMAGES, TR_BOXES = 12, 20
+TR_WORKLOAD = ("configs[1]: VETO vanilla PredCls training step, IMS_PER_BATCH 12 x 20 GT boxes (380 pairs/image, 4560 pairs/step), "
+               "VG 151/51, 592x800 images, P2-P5 + depth NCHW fp32, dropout 0.1/0.35/0.35, Adam + clip 5.0")
+# configs[2]: SGDet-shaped inference
+N_IMAGES, N_BOXES, MAX_PAIRS = 32, 80, 8192
+INF_WORKLOAD = ("configs[2]: SGDet-shaped inference, 32 images x 80 proposals (6320 pairs/image, MAX_PROPOSAL_PAIR 8192), "
+                "VG 151/51, 592x800 images, P2-P5 + depth NCHW fp32")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("VETO_PRECISION", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("VETO_CHUNK_PAIRS", "0")))
-    ap.add_argument("--images", type=int, default=N_IMAGES)
+    ap.add_argument("--images", type=int, default=TR_IMAGES, help="training images per GPU per step")
+    ap.add_argument("--inference-images", type=int, default=N_IMAGES)
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("VETO_CPU_SAMPLE_PAIRS", "2048")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the configs[2] inference leg")
     return ap.parse_args()
 
 
@@ -66,7 +77,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -98,11 +109,45 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
-    """The reference's CPU path for this workload, restated by the oracle (numpy + C ROIAlign; the Python reference
-    itself cannot travel to the GPU box): one image of the bench shape — pair enumeration for 80 boxes, ROI gather of
-    the 80 boxes, and the predictor on the first `sample_pairs` of its 6320 pairs.  Returns (pairs/s, cores, sample)."""
+# ------------------------------------------------------------------------------------------------ CPU baselines
+def cpu_train_leg(steps: int = 1, warmup: int = 0):
+    """The reference's CPU training step for this workload, restated by oracle/torch_port.py (the reference's own
+    formulation on torch CPU kernels, gradients by torch autograd — what the reference itself runs on CPU; the Python
+    reference cannot travel to the GPU box): ONE image of the bench shape (20 boxes, 380 pairs): pair enumeration,
+    ROI gather, predictor forward in train() mode, CE loss, backward.  Returns (pairs/s, cores, sample, s/step)."""
+    import torch
+    from oracle import torch_port as TP
+    from veto_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = synth.make_batch(1000, [TR_BOXES], H=IMG_H, W=IMG_W, mode="predcls")
+    sd = TP.to_torch(synth.predictor_state(11))
+    feats = [torch.from_numpy(f) for f in batch["feats"]]
+    depth = torch.from_numpy(batch["depth"])
+    boxes = [torch.from_numpy(b) for b in batch["boxes"]]
+    labels = [torch.from_numpy(l) for l in batch["labels"]]
+    R = TR_BOXES * (TR_BOXES - 1)
+    rel_labels = [torch.from_numpy(l) for l in synth.make_rel_labels(5, [R])]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        pairs = TP.prepare_test_pairs(batch["n_boxes"], 2048)
+        x2d, d2d = TP.pooler_forward(feats, depth, boxes)
+        loss, grads, *_ = TP.train_step(sd, boxes, pairs, rel_labels, x2d, d2d, "predcls", labels=labels)
+        dt = time.perf_counter() - t0
+        assert bool(torch.isfinite(loss))
+        if it >= warmup:
+            times.append(dt)
+    per_step = sorted(times)[len(times) // 2]
+    sample = (f"1 image x {TR_BOXES} boxes = {R} pairs: pair enumeration + ROI gather + VETOPredictor train() forward + CE loss "
+              f"+ backward (no optimizer step); oracle/torch_port.py = the reference's formulation on torch CPU fp32 kernels "
+              f"with torch autograd, {cores} threads")
+    return R / per_step, cores, sample, per_step
+
+
+def cpu_infer_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
+    """configs[2] on the host cores: one image of 80 proposals, the predictor on the first `sample_pairs` of its 6320
+    pairs (the reference materialises 262 KB per pair).  Returns (pairs/s, cores, sample, s/pair)."""
     import torch
     from oracle import torch_port as TP
     from veto_b200 import synth
@@ -127,12 +172,10 @@ def cpu_reference_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
             t_pairs = time.perf_counter() - t1
             assert bool(torch.isfinite(logits).all())
             if it >= warmup:
-                # per-image fixed cost amortised over the image's 6320 pairs + per-pair cost of the sampled pairs
                 times.append(t_fixed / len(pairs[0]) + t_pairs / len(sub[0]))
     per_pair = sorted(times)[len(times) // 2]
-    sample = (f"1 image x {N_BOXES} proposals: pair enumeration + ROI gather of {N_BOXES} boxes (amortised over 6320 pairs) "
-              f"+ predictor on the first {len(sub[0])} pairs (the reference materialises 262 KB per pair, 6320 at once "
-              f"need 1.66 GB); oracle/torch_port.py = the reference's formulation on torch CPU fp32 kernels, {cores} threads")
+    sample = (f"1 image x {N_BOXES} proposals: pair enumeration + ROI gather (amortised over 6320 pairs) + predictor on the "
+              f"first {len(sub[0])} pairs; oracle/torch_port.py on torch CPU fp32 kernels, {cores} threads")
     return 1.0 / per_pair, cores, sample, per_pair
 
 
@@ -141,15 +184,18 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    val, cores, sample, per_pair = cpu_reference_leg(args.cpu_sample_pairs, steps=max(1, min(args.steps, 3)),
-                                                     warmup=min(args.warmup, 1))
+    val, cores, sample, per_step = cpu_train_leg(steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_pair * args.cpu_sample_pairs * 1e3, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "host CPU run"},
+            "config": {"workload": TR_WORKLOAD, "l2": "host CPU run"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "gpu_launches": 0}
+    if not args.no_inference:
+        iv, _, isample, _ = cpu_infer_leg(args.cpu_sample_pairs)
+        line["inference"] = {"value": iv, "unit": UNIT, "config": {"workload": INF_WORKLOAD}, "sample": isample}
+    line["wall_s"] = time.perf_counter() - t0
     print(json.dumps(line), flush=True)
 
 
@@ -159,14 +205,14 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from tests import harness as H
     from veto_b200 import lib as L
     from veto_b200 import ops, registry, synth
-    from veto_b200.distributed import max_over_ranks
+    from veto_b200.distributed import allreduce_gradients, max_over_ranks
     from veto_b200.sampling import make_roi_relation_samp_processor
+    from veto_b200.structures import BoxList
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -176,55 +222,17 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.require_device()
-
-    # ---- synthetic batch of this rank (independent images: every rank has its own, weak scaling)
-    B = args.images
-    batch = synth.make_batch(100 + rank, [N_BOXES] * B, H=IMG_H, W=IMG_W, mode="sgdet", features=False)
     rgb_hw, depth_hw = synth.fpn_shapes(IMG_H, IMG_W)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    feats_dev = [torch.randn((B, 256) + hw, generator=g, device=dev) for hw in rgb_hw]
-    depth_dev = torch.relu(torch.randn((B, 256) + depth_hw, generator=g, device=dev))
-    state = synth.predictor_state(11)
-    cfg = H.make_cfg(mode="sgdet", max_pairs=MAX_PAIRS, precision=args.precision, chunk_pairs=args.chunk)
-    pred = H.build_predictor(cfg, state, dev)
-    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(dev).eval()
-    samp = make_roi_relation_samp_processor(cfg)
-    bls_dev = H.boxlists(batch, dev, 151)
-    R = B * N_BOXES * (N_BOXES - 1)
-
-    def step_resident():
-        with torch.no_grad():
-            pairs = samp.prepare_test_pairs(dev, bls_dev)
-            x2d, d2d, _, _ = fe(feats_dev, bls_dev, depth_features=depth_dev)
-            out = pred(bls_dev, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)
-        return out[1]
-
-    # ---- host-side copies for the end-to-end leg (pinned)
-    pin = lambda t: t.cpu().pin_memory()
-    feats_host = [pin(f) for f in feats_dev]
-    depth_host = pin(depth_dev)
-    boxes_host = [pin(b.bbox) for b in bls_dev]
-    fields_host = [{k: pin(b.get_field(k)) for k in ("labels", "predict_logits", "pred_scores", "pred_labels")} for b in bls_dev]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in feats_host + [depth_host] + boxes_host)
-    h2d_bytes += sum(t.numel() * t.element_size() for f in fields_host for t in f.values())
-    logits_host = torch.empty((R, 51), dtype=torch.float32).pin_memory()
-    d2h_bytes = logits_host.numel() * 4
-    from veto_b200.structures import BoxList
-
-    def step_e2e():
-        with torch.no_grad():
-            feats = [f.to(dev, non_blocking=True) for f in feats_host]
-            depth = depth_host.to(dev, non_blocking=True)
-            bls = []
-            for bb, ff in zip(boxes_host, fields_host):
-                bl = BoxList(bb.to(dev, non_blocking=True), (IMG_W, IMG_H), "xyxy")
-                for k, v in ff.items():
-                    bl.add_field(k, v.to(dev, non_blocking=True))
-                bls.append(bl)
-            pairs = samp.prepare_test_pairs(dev, bls)
-            x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
-            rel = pred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
-            logits_host.copy_(torch.cat(list(rel)), non_blocking=True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1.4 PFLOP/s sustained (of fallback)"
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    passes = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    pin = lambda t: t.detach().cpu().pin_memory()
 
     def barrier():
         if world > 1:
@@ -244,73 +252,203 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), dev) / steps, (ops.launch_count() - n0)
 
-    # ---- headline: resident inputs
+    def host_boxlists(bls):
+        return ([pin(b.bbox) for b in bls],
+                [{k: pin(b.get_field(k)) for k in ("labels", "predict_logits", "pred_scores", "pred_labels")} for b in bls])
+
+    def device_boxlists(boxes_host, fields_host):
+        out = []
+        for bb, ff in zip(boxes_host, fields_host):
+            bl = BoxList(bb.to(dev, non_blocking=True), (IMG_W, IMG_H), "xyxy")
+            for k, v in ff.items():
+                bl.add_field(k, v.to(dev, non_blocking=True))
+            out.append(bl)
+        return out
+
+    # =============================================================================== configs[1]: training step
+    B = args.images
+    R = B * TR_BOXES * (TR_BOXES - 1)
+    batch = synth.make_batch(100 + rank, [TR_BOXES] * B, H=IMG_H, W=IMG_W, mode="predcls", features=False)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feats_dev = [torch.randn((B, 256) + hw, generator=g, device=dev) for hw in rgb_hw]
+    feats_dev.append(torch.zeros(B, 256, 1, 1, device=dev))           # P6: present in the reference's list, unused
+    depth_dev = torch.relu(torch.randn((B, 256) + depth_hw, generator=g, device=dev)).requires_grad_(True)
+    state = synth.predictor_state(11, spread=False)                   # torch-default-like init: a sane training start
+    cfg = H.make_cfg(mode="predcls", precision=args.precision)
+    pred = registry.make_roi_relation_predictor(cfg, 512)
+    pred.load_state_dict(synth.to_torch_state(state), strict=True)
+    pred = pred.to(dev).train()
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(dev).train()
+    samp = make_roi_relation_samp_processor(cfg)
+    bls_dev = H.boxlists(batch, dev, 151)
+    rel_labels_np = synth.make_rel_labels(7 + rank, [TR_BOXES * (TR_BOXES - 1)] * B)
+    rel_labels_dev = [torch.from_numpy(l).to(dev) for l in rel_labels_np]
+    params = [p for p in pred.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4 * B, fused=True)           # BASE_LR x IMS_PER_BATCH (relation_train_net.py:330-339)
+    losses = []
+
+    def train_step(feats, depth, bls, rel_labels):
+        opt.zero_grad(set_to_none=True)
+        depth.grad = None
+        # all ordered pairs per image: what gtbox_relsample hands the predictor under its 1024-pair cap (sampling.py:54-107)
+        pairs = samp.prepare_test_pairs(dev, bls)
+        x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+        loss = pred(bls, pairs, rel_labels, None, roi_features=x2d, roi_depth_features=d2d)[2]["rel_loss"]
+        loss.backward()
+        allreduce_gradients(params)                                   # DDP's NCCL all-reduce (relation_train_net.py:372-380)
+        torch.nn.utils.clip_grad_norm_(params, 5.0, foreach=True)     # GRAD_NORM_CLIP 5.0 (:475-481)
+        opt.step()
+        return loss.detach()
+
+    def step_resident():
+        losses.append(train_step(feats_dev, depth_dev, bls_dev, rel_labels_dev))
+
+    feats_host = [pin(f) for f in feats_dev]
+    depth_host = pin(depth_dev)
+    boxes_host, fields_host = host_boxlists(bls_dev)
+    labels_host = [pin(l) for l in rel_labels_dev]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in feats_host + [depth_host] + boxes_host + labels_host)
+    h2d_bytes += sum(t.numel() * t.element_size() for f in fields_host for t in f.values())
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        feats = [f.to(dev, non_blocking=True) for f in feats_host]
+        depth = depth_host.to(dev, non_blocking=True).requires_grad_(True)
+        bls = device_boxlists(boxes_host, fields_host)
+        rl = [l.to(dev, non_blocking=True) for l in labels_host]
+        loss = train_step(feats, depth, bls, rl)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+
     with ClockSampler(local) as clk:
         ms_step, launches = timed(step_resident, args.steps, args.warmup)
     clocks = clk.summary()
     value = world * R / ms_step * 1e3
-    # ---- end to end from host buffers
-    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+    loss_first, loss_last = float(losses[0]), float(losses[-1])
+    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 5)), 1)
     e2e_value = world * R / ms_e2e * 1e3
 
     # ---- per-stage device time of one step (CUDA events around every launch) -> roofline of the GEMM kernel
     torch.cuda.synchronize()
     with ops.StageTimer() as st:
         step_resident()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "1.4 PFLOP/s sustained (of fallback)"
     M = R * 19
-    gemm_flops = {"gemm_qkv": 2.0 * M * 1728 * 576, "gemm_out": 2.0 * M * 576 * 576, "gemm_ff1": 2.0 * M * 1152 * 576,
-                  "gemm_ff2": 2.0 * M * 576 * 1152}
-    layers = 6
-    g_ms = sum(st.ms.get(k, 0.0) for k in gemm_flops)
-    g_launch = sum(st.launches.get(k, 0) for k in gemm_flops)
-    algo_flops = layers * sum(gemm_flops.values())
-    passes = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    enc_flops = 6 * 2.0 * M * (1728 * 576 + 576 * 576 + 2 * 576 * 1152)   # forward encoder Linears, 6 full layers
+    fwd_tags = ["gemm_qkv", "gemm_out", "gemm_ff1", "gemm_ff2"]
+    g_ms = sum(st.ms.get(k, 0.0) for k in fwd_tags + ["bwd_gemm"])
+    g_launch = sum(st.launches.get(k, 0) for k in fwd_tags + ["bwd_gemm"])
+    algo_flops = 3.0 * enc_flops                                           # forward + input-gradient + weight-gradient
     achieved = algo_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     total_stage_ms = sum(st.ms.values())
     traffic, traffic_src = None, None
-    try:  # DRAM bytes per launch of the GEMM kernel from the committed ncu --set full capture (profiles/)
+    try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
-        traffic, traffic_src = tj.get(args.precision), tj.get("source")
+        traffic, traffic_src = tj.get("train_" + args.precision), tj.get("source")
     except Exception:
         pass
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05.mma cta_group::2, TMEM accumulators, TMA)" if args.precision != "fp32" else "gemm_simt_kernel",
+        "bound": "tensor",
+        "kernel": "gemm_tc2_kernel (tcgen05.mma cta_group::2, TMEM accumulators, TMA): forward, dX and dW GEMMs" if args.precision != "fp32" else "gemm_simt_kernel",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
         "peak_source": peak_src, "traffic_source": traffic_src,
         "algorithmic_flops_per_launch": algo_flops / max(g_launch, 1), "launches_per_step": g_launch,
         "avg_launch_ms": g_ms / max(g_launch, 1), "share_of_step": g_ms / total_stage_ms if total_stage_ms else None,
         "executed_mma_tflops": achieved * passes, "frac_executed": achieved * passes / peak_tf,
-        "note": "algorithmic = 2*M*N*K of the reference's fp32 Linear layers; bf16x3 executes 3 bf16 MMAs per product",
+        "note": ("algorithmic = 2*M*N*K of the reference's fp32 encoder Linears x 3 (forward, dX, dW); bf16x3 executes 3 bf16 MMAs "
+                 "per product; the bwd_gemm time also holds the split-K reductions, the patch-projection and the small fp32 GEMMs"),
         "stage_ms": {k: round(v, 3) for k, v in st.ms.items()},
+        "stage_launches": dict(st.launches),
     }
 
-    # ---- HBM-bound kernels of the path: algorithmic bytes per step / event time, against the measured copy bandwidth
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_boxes_total = B * N_BOXES
-    rows_full = (layers - 1) * M                      # token rows the 5 full layers normalise / attend
-    hbm_bytes = {
-        "pairs": R * (16 + 16 + 8),                   # enumerate writes 16 B/pair; globalize reads 16, writes 8
-        "roi_gather": n_boxes_total * 131072,         # bytes written (each touched map element is read once on top)
-        "tokens": R * 19 * 576 * 4,                   # token block written; box-level tables are L2-resident
-        "layernorm": (2 * rows_full + M + R) * 4608,  # 2304 B read + 2304 B written per row (last layer: LN2 on CLS rows)
-        "attention": rows_full * (6912 + 2304) + M * 4608 + R * 4608,  # qkv read + hi/lo output written
-    }
-    hbm_kernels = {k: {"ms": round(st.ms[k], 3), "algorithmic_bytes": int(v), "achieved_gbs": round(v / st.ms[k] / 1e6, 1),
-                       "frac_of_measured_hbm": round(v / st.ms[k] / 1e6 / hbm_peak, 3)}
-                   for k, v in hbm_bytes.items() if st.ms.get(k)}
-
-    # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference_leg(args.cpu_sample_pairs)
+        v, cores, sample, _ = cpu_train_leg()
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    # release the training state before the inference leg
+    train_ws_gb = sum(t.numel() for t in ops._workspaces.values()) / 1e9
+    del opt, params, pred, fe, feats_dev, depth_dev, feats_host, depth_host
+    ops._workspaces.clear()
+    torch.cuda.empty_cache()
+
+    # =============================================================================== configs[2]: inference
+    inference = None
+    if not args.no_inference:
+        Bi = args.inference_images
+        Ri = Bi * N_BOXES * (N_BOXES - 1)
+        ibatch = synth.make_batch(200 + rank, [N_BOXES] * Bi, H=IMG_H, W=IMG_W, mode="sgdet", features=False)
+        ifeats = [torch.randn((Bi, 256) + hw, generator=g, device=dev) for hw in rgb_hw]
+        idepth = torch.relu(torch.randn((Bi, 256) + depth_hw, generator=g, device=dev))
+        icfg = H.make_cfg(mode="sgdet", max_pairs=MAX_PAIRS, precision=args.precision, chunk_pairs=args.chunk)
+        ipred = H.build_predictor(icfg, synth.predictor_state(11), dev)
+        ife = registry.make_roi_box_feature_extractor(icfg, 256, for_relation=True).to(dev).eval()
+        isamp = make_roi_relation_samp_processor(icfg)
+        ibls = H.boxlists(ibatch, dev, 151)
+
+        def infer_resident():
+            with torch.no_grad():
+                pairs = isamp.prepare_test_pairs(dev, ibls)
+                x2d, d2d, _, _ = ife(ifeats, ibls, depth_features=idepth)
+                return ipred(ibls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
+
+        ifeats_host = [pin(f) for f in ifeats]
+        idepth_host = pin(idepth)
+        iboxes_host, ifields_host = host_boxlists(ibls)
+        ih2d = sum(t.numel() * t.element_size() for t in ifeats_host + [idepth_host] + iboxes_host)
+        ih2d += sum(t.numel() * t.element_size() for f in ifields_host for t in f.values())
+        logits_host = torch.empty((Ri, 51), dtype=torch.float32).pin_memory()
+
+        def infer_e2e():
+            with torch.no_grad():
+                feats = [f.to(dev, non_blocking=True) for f in ifeats_host]
+                depth = idepth_host.to(dev, non_blocking=True)
+                bls = device_boxlists(iboxes_host, ifields_host)
+                pairs = isamp.prepare_test_pairs(dev, bls)
+                x2d, d2d, _, _ = ife(feats, bls, depth_features=depth)
+                rel = ipred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
+                logits_host.copy_(torch.cat(list(rel)), non_blocking=True)
+
+        isteps = max(2, min(args.steps, 5))
+        ims, ilaunches = timed(infer_resident, isteps, max(3, min(args.warmup, 3)))
+        ims_e2e, _ = timed(infer_e2e, max(1, min(args.steps, 3)), 1)
+        torch.cuda.synchronize()
+        with ops.StageTimer() as ist:
+            infer_resident()
+        Mi = Ri * 19
+        iflops = (5 * 2.0 * Mi * (1728 * 576 + 576 * 576 + 2 * 576 * 1152)           # five full layers
+                  + 2.0 * Mi * 1152 * 576 + 2.0 * Ri * (576 * 576 * 2 + 2 * 576 * 1152))  # last layer: K, V of all rows; CLS row only elsewhere
+        ig_ms = sum(ist.ms.get(k, 0.0) for k in fwd_tags)
+        ig_launch = sum(ist.launches.get(k, 0) for k in fwd_tags)
+        iach = iflops / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
+        nb_total = Bi * N_BOXES
+        rows_full = 5 * Mi
+        hbm_bytes = {
+            "pairs": Ri * (16 + 16 + 8),
+            "roi_gather": nb_total * 131072,
+            "tokens": Ri * 19 * 576 * 4,
+            "layernorm": (2 * rows_full + Mi + Ri) * 4608,
+            "attention": rows_full * (6912 + 2304) + Mi * 4608 + Ri * 4608,
+        }
+        hbm_kernels = {k: {"ms": round(ist.ms[k], 3), "algorithmic_bytes": int(v), "achieved_gbs": round(v / ist.ms[k] / 1e6, 1),
+                           "frac_of_measured_hbm": round(v / ist.ms[k] / 1e6 / hbm_peak, 3)}
+                       for k, v in hbm_bytes.items() if ist.ms.get(k)}
+        icpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_infer_leg(args.cpu_sample_pairs)
+            icpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        inference = {
+            "metric": METRIC, "value": world * Ri / ims * 1e3, "unit": UNIT, "ms_per_step": ims, "steps": isteps,
+            "images_per_sec": world * Bi / ims * 1e3,
+            "config": {"workload": INF_WORKLOAD, "images_per_gpu": Bi, "pairs_per_step_per_gpu": Ri,
+                       "chunk_pairs": ipred.chunk_pairs or "library default"},
+            "e2e": {"value": world * Ri / ims_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": ih2d,
+                    "d2h_bytes_per_step": logits_host.numel() * 4, "ms_per_step": ims_e2e},
+            "gpu_launches": ilaunches,
+            "tflops_reference_formulation": world * Ri / ims * 1e3 * FLOP_PER_PAIR / 1e12,
+            "roofline": {"bound": "tensor", "achieved": iach, "peak": peak_tf, "unit": "TFLOP/s", "frac": iach / peak_tf,
+                         "executed_mma_tflops": iach * passes, "frac_executed": iach * passes / peak_tf,
+                         "launches_per_step": ig_launch, "stage_ms": {k: round(v, 3) for k, v in ist.ms.items()}},
+            "hbm_kernels": hbm_kernels, "cpu_baseline": icpu,
+        }
 
     if rank == 0:
         line = {
@@ -319,15 +457,17 @@ def main():
             "dtype": {"bf16x3": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32-grade)", "bf16": "bf16",
                       "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu": B, "pairs_per_step_per_gpu": R, "precision": args.precision,
-                       "chunk_pairs": pred.chunk_pairs or "library default", "parallelism": f"image-sharded x{world}",
-                       "l2": "inputs larger than L2 (1.38 GB of feature maps + 0.34 GB of ROI features per step)"},
+            "config": {"workload": TR_WORKLOAD, "images_per_gpu": B, "pairs_per_step_per_gpu": R, "precision": args.precision,
+                       "parallelism": f"image-sharded data parallel x{world}, one flat NCCL gradient all-reduce per step",
+                       "optimizer": "Adam (torch fused), clip_grad_norm 5.0",
+                       "l2": "inputs larger than L2 (0.52 GB of feature maps per step; 14 GB of saved activations)"},
             "images_per_sec": world * B / ms_step * 1e3,
-            "tflops_reference_formulation": value * FLOP_PER_PAIR / 1e12,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+            "tflops_reference_formulation": value * 3 * FLOP_PER_PAIR / 1e12,
+            "loss_first_last": [loss_first, loss_last], "train_workspace_gb": round(train_ws_gb, 2),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_kernels": hbm_kernels,
-            "hbm_peak_gbs": hbm_peak, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_peak_gbs": hbm_peak,
+            "cpu_baseline": cpu, "inference": inference,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -309,6 +309,13 @@ int veto_test_attention(const float* qkv_dev, float* out_dev, int64_t n_seq, vet
 int veto_test_attention_tc(const float* qkv_dev, float* out_dev, void* scratch_dev, int64_t n_seq, int split,
                            veto_stream_t stream);
 
+/* the weight-gradient GEMM out[Nw,Kw] = y[rows,Nw]^T @ x[rows,Kw] (both operands read in place as MN-major tcgen05
+ * operands); scratch_dev >= 4*(rows*Nw + rows*Kw) + 4*Nw*Kw*split_k bytes; geometry_host = {LBO, SBO, K advance} bytes of
+ * the shared-memory descriptors or NULL for the production constants (the parameter exists for the bring-up sweep) */
+int veto_test_gemm_tn(const float* y_dev, const float* x_dev, float* out_dev, int rows, int Nw, int Kw, int precision,
+                      int split_k, const uint32_t* geometry_host, void* scratch_dev, size_t scratch_bytes,
+                      veto_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,11 @@ assert allrows.shape[0] == sum(n * (n - 1) for n in n_boxes), allrows.shape
 assert sorted(set(allrows[:, 0].tolist())) == list(range(5))
 t = vdist.max_over_ranks(1.0 + rank, "cpu")
 assert t == 2.0
+# the training step's gradient exchange: one flat bucket, averaged over ranks (DDP semantics)
+ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+ps[0].grad = torch.full((3, 4), 1.0 + rank); ps[1].grad = torch.arange(5.0) * (rank + 1)   # ps[2] has no gradient
+vdist.allreduce_gradients(ps)
+assert torch.equal(ps[0].grad, torch.full((3, 4), 1.5)) and torch.equal(ps[1].grad, torch.arange(5.0) * 1.5) and ps[2].grad is None
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
@@ -141,9 +146,10 @@ def test_bench_reference_arm_contract():
     """bench.py --impl reference prints one JSON line with the contract keys (a tiny sample keeps this fast)."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-pairs", "64"], capture_output=True, text=True, timeout=300)
+                        "--cpu-sample-pairs", "64"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "configs[1]" in line["config"]["workload"] and line["inference"]["value"] > 0

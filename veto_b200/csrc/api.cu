@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "api_internal.cuh"
+#include "train.cuh"
 
 namespace veto {
 
@@ -443,4 +444,31 @@ extern "C" int veto_test_attention_tc(const float* qkv_dev, float* out_dev, void
     o.hi = (__nv_bfloat16*)scratch_dev;
     o.lo = split ? o.hi + (size_t)n_seq * kTokens * kDim : nullptr;
     return attention_tc(qkv_dev, n_seq, o, (cudaStream_t)stream);
+}
+
+extern "C" int veto_test_gemm_tn(const float* y_dev, const float* x_dev, float* out_dev, int rows, int Nw, int Kw, int precision,
+                                 int split_k, const uint32_t* geometry_host, void* scratch_dev, size_t scratch_bytes,
+                                 veto_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    VETO_REQUIRE(y_dev && x_dev && out_dev && scratch_dev, VETO_ERR_ARG, "veto_test_gemm_tn: NULL argument");
+    VETO_REQUIRE(precision == VETO_PREC_BF16X3 || precision == VETO_PREC_BF16, VETO_ERR_ARG, "veto_test_gemm_tn: tensor-core modes only");
+    const size_t ye = (size_t)rows * Nw, xe = (size_t)rows * Kw, oe = (size_t)Nw * Kw;
+    const int slices = gemm_tn2_slices(rows, split_k);
+    VETO_REQUIRE(scratch_bytes >= 4 * (ye + xe) + (slices > 1 ? 4 * oe * slices : 0), VETO_ERR_WORKSPACE,
+                 "veto_test_gemm_tn: scratch too small");
+    __nv_bfloat16* y_hi = (__nv_bfloat16*)scratch_dev;
+    __nv_bfloat16* y_lo = y_hi + ye;
+    __nv_bfloat16* x_hi = y_lo + ye;
+    __nv_bfloat16* x_lo = x_hi + xe;
+    float* partial = (float*)(x_lo + xe);
+    int rc;
+    if ((rc = pack_split_bf16(y_dev, y_hi, y_lo, ye, s))) return rc;
+    if ((rc = pack_split_bf16(x_dev, x_hi, x_lo, xe, s))) return rc;
+    GemmOperand Y, X;
+    Y.hi = y_hi; Y.lo = y_lo;
+    X.hi = x_hi; X.lo = x_lo;
+    const int passes = precision == VETO_PREC_BF16X3 ? 3 : 1;
+    if ((rc = gemm_tn2(Y, X, Nw, Kw, rows, passes, slices > 1 ? partial : out_dev, Kw, slices, oe, s, geometry_host))) return rc;
+    if (slices > 1) rc = splitk_reduce(partial, slices, oe, oe, out_dev, s);
+    return rc;
 }

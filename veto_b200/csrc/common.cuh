@@ -202,6 +202,13 @@ bool gemm_tc2_supported(int N, int K);
 int gemm_tc2_slices(int K, int split_k);  // K slices a GemmEpilogue::split_k request really produces
 int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
              cudaStream_t s);
+// Weight-gradient GEMM G[Nw,Kw] = dY[rows,Nw]^T @ X[rows,Kw] with both operands read in place as MN-major tcgen05
+// operands (gemm_tn2.cu).  split_k > 1: slice s of the rows is written at out + s * split_stride (gemm_tn2_slices tells
+// how many slices a request really produces).  geometry = {LBO, SBO, K advance} bytes, NULL = the production constants.
+bool gemm_tn2_supported(int Nw, int Kw, int ld_y, int ld_x);
+int gemm_tn2_slices(int rows, int split_k);
+int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
+             size_t split_stride, cudaStream_t s, const uint32_t* geometry = nullptr);
 // picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc
 int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
                  cudaStream_t s);

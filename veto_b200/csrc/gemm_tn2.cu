@@ -1,0 +1,453 @@
+// Weight-gradient GEMM of the training step on the tensor cores, with BOTH operands read in place:
+//
+//   G[Nw, Kw] = dY[rows, Nw]^T @ X[rows, Kw]          (dW = dY^T X of a Linear y = x W^T; reduction over the token rows)
+//
+// dY and X are the row-major bf16 hi/lo activation arrays the backward pass already holds, so the reduction dimension
+// (rows) is the SLOW dimension of both: for tcgen05 these are "MN-major" operands (instruction-descriptor bits 15 / 16),
+// staged by TMA as [64 rows] x [64 contiguous elements = 128 B] boxes with the 128-byte swizzle — the canonical layout
+// Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) elements of cute's make_umma_desc<Major::MN>: a K row is 128 B,
+// eight K rows form a 1024-byte swizzle atom (SBO), the next 64 MN elements live LBO bytes further (the next TMA box).
+// No transposed copies of the activations are ever written (the first version of the backward spent 10 ms of a 51 ms
+// step on them, profiles/r1_train_launches_v1.txt).
+//
+// Everything else follows gemm_tc2.cu: a cluster of two CTAs owns a 256 x 128 output tile (tcgen05 cta_group::2,
+// M = 256, N = 128, K = 16), warp-specialised TMA / MMA / 12 epilogue warps, TMEM double buffering, one pipeline stage
+// serving the three products of the bf16x3 split, and split-K over the rows (tiny output, huge reduction): partial
+// tiles are written as plain fp32 and summed in a fixed order by splitk_reduce (train.cu).  Rows beyond the end of the
+// arrays are zero-filled by TMA, so the row count needs no padding.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace veto {
+namespace {
+
+constexpr int BLOCK_M = 128;      // output rows (Nw) per CTA, 256 per pair
+constexpr int BLOCK_N = 128;      // output columns (Kw) per pair tile; each CTA stages 64 of them
+constexpr int HALF_N = BLOCK_N / 2;
+constexpr int BLOCK_K = 64;       // reduction rows per stage
+constexpr int UMMA_K = 16;
+constexpr int MN_CHUNK = 64;      // contiguous elements per TMA box row (128 B)
+constexpr int NUM_EPI_WARPS = 12;
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int EPI_COLS = 16;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;
+constexpr int CHUNK_BYTES = BLOCK_K * MN_CHUNK * 2;        // 8 KB: one TMA box
+constexpr int BYTES_A = (BLOCK_M / MN_CHUNK) * CHUNK_BYTES;  // 16 KB
+constexpr int BYTES_B = (HALF_N / MN_CHUNK) * CHUNK_BYTES;   // 8 KB
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int MAX_STAGES = 8;
+constexpr int PIPE_BYTES = 192 * 1024;                      // 4 stages of 48 KB (3-pass) or 8 stages of 24 KB
+constexpr int TMEM_COLS = 256;
+constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("veto gemm_tn2: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+// TMA load whose completion bytes go to the LEADER CTA's barrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// MN-major SWIZZLE_128B shared-memory descriptor: leading byte offset = distance between 64-element MN chunks,
+// stride byte offset = distance between groups of eight K rows
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// fp32 accumulate, bf16 A and B, both MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TnParams {
+    float* out;              // [ksplit][Nw, ldc] fp32 partial products
+    int ldc;
+    int ksplit, kb_per;
+    long long split_stride;
+    uint32_t lbo, sbo, kadv;  // descriptor geometry (constants in production; parameters for the bring-up test)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                int Nw, int Kw, int rows, int passes, TnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_epi = smem + PIPE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_epi + EPI_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + MAX_STAGES;
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    const bool split = passes == 3;
+    const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
+    const int num_stages = PIPE_BYTES / stage_bytes;  // 4 or 8
+    const int num_m = (Nw + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int num_n = (Kw + BLOCK_N - 1) / BLOCK_N;
+    const int mn_tiles = num_m * num_n;
+    const int num_tiles = mn_tiles * p.ksplit;
+    const int num_kb = (rows + BLOCK_K - 1) / BLOCK_K;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    auto tile_mn = [&](int tile, int& tm, int& tn) {
+        const int t2 = tile % mn_tiles;
+        tm = t2 / num_n;
+        tn = t2 - tm * num_n;
+        return tile / mn_tiles;
+    };
+    auto kb_range = [&](int ks, int& kb0, int& kb1) {
+        kb0 = ks * p.kb_per;
+        kb1 = kb0 + p.kb_per < num_kb ? kb0 + p.kb_per : num_kb;
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_b_hi);
+        if (split) {
+            tma_prefetch_desc(&tm_a_lo);
+            tma_prefetch_desc(&tm_b_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < MAX_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc2(tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    // stage layout: [A_hi][A_lo][B_hi][B_lo] (3-pass) or [A][B] (1-pass); A = two 8 KB boxes, B = one
+    auto stage_ptr = [&](int s) { return smem + s * stage_bytes; };
+    const int off_a_lo = BYTES_A;
+    const int off_b_hi = split ? 2 * BYTES_A : BYTES_A;
+    const int off_b_lo = off_b_hi + BYTES_B;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                int tm, tn, kb0, kb1;
+                kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M;   // first dY column (output row) of this CTA
+                const int n0 = tn * BLOCK_N + rank * HALF_N;          // first X column (output column) of this CTA
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int r0 = kb * BLOCK_K;
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    uint8_t* sp = stage_ptr(stage);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_M / MN_CHUNK; ++j) {
+                        tma_load_2d_pair(sp + j * CHUNK_BYTES, &tm_a_hi, &full_bar[stage], m0 + j * MN_CHUNK, r0);
+                        if (split) tma_load_2d_pair(sp + off_a_lo + j * CHUNK_BYTES, &tm_a_lo, &full_bar[stage], m0 + j * MN_CHUNK, r0);
+                    }
+                    tma_load_2d_pair(sp + off_b_hi, &tm_b_hi, &full_bar[stage], n0, r0);
+                    if (split) tma_load_2d_pair(sp + off_b_lo, &tm_b_lo, &full_bar[stage], n0, r0);
+                    if (++stage == num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_mn(2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                int tm, tn, kb0, kb1;
+                kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(stage_ptr(stage));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t ko = k * p.kadv;
+                        const uint64_t a_hi = make_desc_mn(sp + ko, p.lbo, p.sbo);
+                        const uint64_t b_hi = make_desc_mn(sp + off_b_hi + ko, p.lbo, p.sbo);
+                        umma2_bf16(tmem_d, a_hi, b_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (split) {
+                            umma2_bf16(tmem_d, make_desc_mn(sp + off_a_lo + ko, p.lbo, p.sbo), b_hi, idesc, 1u);
+                            umma2_bf16(tmem_d, a_hi, make_desc_mn(sp + off_b_lo + ko, p.lbo, p.sbo), idesc, 1u);
+                        }
+                    }
+                    umma2_commit_both(&empty_bar[stage]);
+                    if (++stage == num_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma2_commit_both(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 output rows): plain fp32 partial tiles =====================
+        const int q = warp & 3;
+        const int third = (warp - 4) >> 2;
+        constexpr int kStride = NUM_EPI_WARPS / 4;
+        float4* stage4 = reinterpret_cast<float4*>(smem_epi + (warp - 4) * EPI_STAGE_BYTES);
+        const int rsub = lane >> 2, cg = lane & 3;
+        constexpr int kChunks = BLOCK_N / EPI_COLS;
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            int tm, tn;
+            const int ks = tile_mn(tile, tm, tn);
+            const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
+            const int n0 = tn * BLOCK_N;
+            float* outp = p.out + (size_t)ks * (size_t)p.split_stride;
+            mbar_wait(&tmem_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = third; c < kChunks; c += kStride) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c * EPI_COLS, r);
+                tmem_ld_wait();
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    stage4[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                __syncwarp();
+                const int col = n0 + c * EPI_COLS + cg * 4;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int lr = rr * 8 + rsub;
+                    const float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
+                    const int row = m0 + lr;
+                    if (row < Nw && col < Kw) *(float4*)(outp + (size_t)row * p.ldc + col) = v;
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_mu;
+bool g_inited = false;
+
+struct MapKey {
+    const void* p;
+    uint64_t rows, cols, ld;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7);
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// [rows, cols] row-major bf16 with row stride ld: boxes of 64 rows x 64 contiguous elements, 128-byte swizzle
+int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, CUtensorMap* out) {
+    MapKey key{p, rows, cols, ld};
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+        *out = it->second;
+        return VETO_OK;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {MN_CHUNK, BLOCK_K};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%llu,%llu] ld %llu at %p (gemm_tn2)", (int)r, (unsigned long long)rows,
+                  (unsigned long long)cols, (unsigned long long)ld, (const void*)p);
+        return VETO_ERR_CUDA;
+    }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return VETO_OK;
+}
+
+int init_tn() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return VETO_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
+                 "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    g_inited = true;
+    return VETO_OK;
+}
+
+}  // namespace
+
+bool gemm_tn2_supported(int Nw, int Kw, int ld_y, int ld_x) {
+    return Nw % 8 == 0 && Kw % 8 == 0 && ld_y % 8 == 0 && ld_x % 8 == 0;
+}
+
+int gemm_tn2_slices(int rows, int split_k) { return gemm_tc2_slices((rows + BLOCK_K - 1) / BLOCK_K * BLOCK_K, split_k); }
+
+int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
+             size_t split_stride, cudaStream_t s, const uint32_t* geometry) {
+    if (Nw <= 0 || Kw <= 0 || rows <= 0) return VETO_OK;
+    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tn2: passes must be 1 or 3");
+    VETO_REQUIRE(dY.hi && X.hi && (passes == 1 || (dY.lo && X.lo)), VETO_ERR_ARG, "gemm_tn2: missing bf16 operand");
+    const int ldy = dY.ld ? dY.ld : Nw, ldx = X.ld ? X.ld : Kw;
+    VETO_REQUIRE(gemm_tn2_supported(Nw, Kw, ldy, ldx) && ldc % 4 == 0 && Kw % 4 == 0, VETO_ERR_UNSUPPORTED,
+                 "gemm_tn2: Nw=%d Kw=%d ld %d/%d ldc %d must be multiples of 8 (ldc of 4)", Nw, Kw, ldy, ldx, ldc);
+    int rc = init_tn();
+    if (rc) return rc;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if ((rc = get_map(dY.hi, rows, Nw, ldy, &ta_hi))) return rc;
+    if ((rc = get_map(X.hi, rows, Kw, ldx, &tb_hi))) return rc;
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+    if (passes == 3) {
+        if ((rc = get_map(dY.lo, rows, Nw, ldy, &ta_lo))) return rc;
+        if ((rc = get_map(X.lo, rows, Kw, ldx, &tb_lo))) return rc;
+    }
+    const int num_kb = (rows + BLOCK_K - 1) / BLOCK_K;
+    const int ksplit = gemm_tn2_slices(rows, split_k);
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    const int tiles = ((Nw + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((Kw + BLOCK_N - 1) / BLOCK_N) * ksplit;
+    const int pairs_avail = num_sms() / 2;
+    const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
+    TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride,
+               geometry ? geometry[0] : (uint32_t)CHUNK_BYTES, geometry ? geometry[1] : 1024u, geometry ? geometry[2] : 2048u};
+    gemm_tn2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, Nw, Kw, rows, passes, p);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+}  // namespace veto

@@ -223,11 +223,24 @@ dropout_kernel(float* __restrict__ x, size_t n4, DropSpec drop) {
     }
 }
 
-// fp32 -> activation storage format (no transpose)
+// fp32 -> activation storage format (no transpose), optionally through the dropout mask of element index e; 4 per thread
 __global__ void __launch_bounds__(256)
-convert_kernel(const float* __restrict__ src, size_t n, float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
-        store_act(f32, hi, lo, e, src[e]);
+convert_kernel(const float* __restrict__ src, size_t n4, DropSpec drop, float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg((const float4*)src + g);
+        if (drop.thr16) {
+            const float4 d = drop_scale4(drop, g);
+            v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
+        }
+        if (f32) ((float4*)f32)[g] = v;
+        if (hi) {
+            uint2 hh, ll;
+            split_pair(v.x, v.y, hh.x, ll.x);
+            split_pair(v.z, v.w, hh.y, ll.y);
+            ((uint2*)hi)[g] = hh;
+            if (lo) ((uint2*)lo)[g] = ll;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- LayerNorm backward
@@ -800,9 +813,10 @@ int dropout_inplace(float* x, size_t n, const DropSpec& drop, cudaStream_t s) {
     return VETO_OK;
 }
 
-int convert_act(const float* src, size_t n, const ActOut& out, cudaStream_t s) {
+int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s) {
     if (n == 0) return VETO_OK;
-    convert_kernel<<<grid_cap((n + 255) / 256, 8), 256, 0, s>>>(src, n, out.f32, out.hi, out.lo);
+    VETO_REQUIRE(n % 4 == 0, VETO_ERR_ARG, "convert_act: element count must be a multiple of 4");
+    convert_kernel<<<grid_cap((n / 4 + 255) / 256, 8), 256, 0, s>>>(src, n / 4, drop, out.f32, out.hi, out.lo);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -5,8 +5,9 @@
 // qkv, the attention output, the FeedForward pre-activation and activation).  Backward runs every Linear's two
 // gradients on the same tcgen05 GEMM kernel as the forward:
 //   dX = dY @ W          ->  gemm(A = dY [M,N],    W' = W^T  [K,N])      (W^T packed once per step)
-//   dW = dY^T @ X        ->  gemm(A = dY^T [N,Mp], W' = X^T  [K,Mp])     (activations transposed into K-major bf16
-//                                                                         hi/lo operands; split-K over the M rows)
+//   dW = dY^T @ X        ->  gemm_tn2(dY [M,N], X [M,K])                  (both read in place as MN-major tcgen05
+//                                                                         operands, split-K over the M rows; fp32
+//                                                                         mode: transposes + the SIMT GEMM)
 // so the bf16x3 mode keeps its fp32-grade products in the gradients too.  Declarations: include/veto_b200.h.
 #include <string.h>
 
@@ -87,9 +88,11 @@ TrainLayout train_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs)
     T.tmp = k.take(f * M * kDim);
     T.a576 = k.take(act_bytes(prec, M * kDim));
     T.a1728 = k.take(act_bytes(prec, M * 3 * kDim));
-    T.T1 = k.take(act_bytes(prec, max_sz((size_t)3 * kDim * T.Mp, (size_t)2 * kDimDepth * T.Kb)));
-    T.T2 = k.take(act_bytes(prec, max_sz((size_t)kMlp * T.Mp, (size_t)kPatchVec * T.Kb)));
-    T.splitk = k.take(f * (size_t)kMaxSplit * 3 * kDim * kDim);
+    // transposed operands: only the fp32 (SIMT) mode needs them, the tensor-core modes read dY and X in place
+    const bool simt = prec == VETO_PREC_FP32;
+    T.T1 = k.take(simt ? f * max_sz((size_t)3 * kDim * T.Mp, (size_t)2 * kDimDepth * T.Kb) : 0);
+    T.T2 = k.take(simt ? f * max_sz((size_t)kMlp * T.Mp, (size_t)kPatchVec * T.Kb) : 0);
+    T.splitk = k.take(simt ? 0 : f * (size_t)kMaxSplit * max_sz((size_t)3 * kDim * kDim, (size_t)2 * kDimDepth * kPatchVec));
     T.ln_partial = k.take(f * (size_t)ln_bwd_blocks((int64_t)M) * 2 * kDim);
     T.colsum_scratch = k.take(f * colsum_scratch_floats(3 * kDim));
     for (int l = 0; l < c.layers; ++l) {
@@ -135,35 +138,49 @@ struct Ctx {
     int mm(const ActBuf& A, int lda, const ActBuf& W, int M, int N, int K, const GemmEpilogue& ep) const {
         return linear(prec, A, lda, WRef{W.f32, W.hi, W.lo}, M, N, K, ep, s);
     }
-    // dst[c, r] = src[r, c], r < rows (zero up to rows_pad); dst row stride rows_pad
-    int transpose_act(const ActBuf& src, int64_t ld, int64_t rows, int cols, const ActBuf& dst, int64_t rows_pad) const {
-        if (src.f32) return transpose_f32(src.f32, ld, rows, cols, false, DropSpec(), 0, dst.out(), rows_pad, rows_pad, ActOut(), 0, s);
-        int rc = transpose_bf16(src.hi, ld, rows, cols, dst.hi, rows_pad, rows_pad, s);
-        if (rc) return rc;
-        if (src.lo) rc = transpose_bf16(src.lo, ld, rows, cols, dst.lo, rows_pad, rows_pad, s);
-        return rc;
-    }
-    // gW[Nw,Kw] = dYT[Nw,Kp] @ XT[Kw,Kp]^T  (the weight gradient dY^T X, reduction over the Kp padded rows)
-    int wgrad(const ActBuf& dYT, const ActBuf& XT, int Nw, int Kw, int64_t Kp, float* gW) const {
-        GemmEpilogue ep;
-        ep.ldc = Kw;
-        ep.out.f32 = gW;
-        int slices = 1;
-        if (prec != VETO_PREC_FP32 && gemm_tc2_supported(Kw, (int)Kp)) {
-            const int mn_tiles = ((Nw + 255) / 256) * (Kw / 192);
-            int want = (2 * (num_sms() / 2) + mn_tiles - 1) / mn_tiles;  // about two waves of CTA pairs
-            if (want > kMaxSplit) want = kMaxSplit;
-            slices = gemm_tc2_slices((int)Kp, want);
-            if (slices > 1) {
-                ep.split_k = slices;
-                ep.split_stride = (size_t)Nw * Kw;
-                ep.out.f32 = splitk;
+    // gW[Nw,Kw] = dY[rows,Nw]^T @ X[rows,Kw]: the weight gradient of y = x W^T, operands row-major as the backward holds them
+    int wgrad(const ActBuf& dY, int ldy, const ActBuf& X, int ldx, int64_t rows, int Nw, int Kw, float* gW) const {
+        if (prec == VETO_PREC_FP32) {
+            const int64_t Kp = pad64(rows);
+            float* t1 = f32(T->T1);
+            float* t2 = f32(T->T2);
+            ActOut o1, o2;
+            o1.f32 = t1; o2.f32 = t2;
+            int rc = transpose_f32(dY.f32, ldy, rows, Nw, false, DropSpec(), 0, o1, Kp, Kp, ActOut(), 0, s);
+            if (rc) return rc;
+            if ((rc = transpose_f32(X.f32, ldx, rows, Kw, false, DropSpec(), 0, o2, Kp, Kp, ActOut(), 0, s))) return rc;
+            GemmEpilogue ep;
+            ep.ldc = Kw;
+            ep.out.f32 = gW;
+            return gemm_simt(t1, (int)Kp, t2, Nw, Kw, (int)Kp, ep, s);
+        }
+        // split-K: pick the slice count whose tile total fills whole waves of CTA pairs best (>= 8 K blocks per slice)
+        const int mn_tiles = ((Nw + 255) / 256) * ((Kw + 127) / 128);
+        const int pairs = num_sms() / 2;
+        const int max_s = (int)((rows + 511) / 512) < kMaxSplit ? (int)((rows + 511) / 512) : kMaxSplit;
+        int best = 1;
+        double best_eff = 0.0;
+        for (int want = 1; want <= (max_s > 1 ? max_s : 1); ++want) {
+            const int sl = gemm_tn2_slices((int)rows, want);
+            const int tiles = mn_tiles * sl;
+            const double eff = (double)tiles / (double)(((tiles + pairs - 1) / pairs) * pairs);
+            if (eff > best_eff + 0.02) {
+                best_eff = eff;
+                best = sl;
             }
         }
-        int rc = mm(dYT, (int)Kp, XT, Nw, Kw, (int)Kp, ep);
+        GemmOperand A, B;
+        A.hi = dY.hi; A.lo = dY.lo; A.ld = ldy;
+        B.hi = X.hi; B.lo = X.lo; B.ld = ldx;
+        const size_t n = (size_t)Nw * Kw;
+        int rc = gemm_tn2(A, B, Nw, Kw, (int)rows, prec == VETO_PREC_BF16X3 ? 3 : 1, best > 1 ? splitk : gW, Kw, best, n, s);
         if (rc) return rc;
-        if (slices > 1) rc = splitk_reduce(splitk, slices, (size_t)Nw * Kw, (size_t)Nw * Kw, gW, s);
+        if (best > 1) rc = splitk_reduce(splitk, best, n, n, gW, s);
         return rc;
+    }
+    // fp32 -> the operand format of the precision mode (optionally through a dropout mask)
+    int to_operand(const float* src, size_t n, const DropSpec& drop, const ActBuf& dst) const {
+        return convert_act(src, n, drop, dst.out(), s);
     }
     int bias_grad(const ActIn& src, int64_t ld, int64_t rows, int cols, float* out) const {
         return colsum(src, ld, rows, cols, colsum_scratch, out, false, s);
@@ -386,21 +403,16 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     ActBuf a576 = X.act(T.a576, (size_t)M * kDim);
     ActBuf a1728 = X.act(T.a1728, (size_t)M * 3 * kDim);
     float* ln_partial = X.f32(T.ln_partial);
-    const int64_t Mp = T.Mp;
     for (int l = NL - 1; l >= 0; --l) {
         const LayerSave& S = T.L[l];
         ActBuf xn1 = X.act(S.xn1, (size_t)M * kDim), ao = X.act(S.ao, (size_t)M * kDim), xn2 = X.act(S.xn2, (size_t)M * kDim);
         ActBuf hb = X.act(S.h, (size_t)M * kMlp);
-        ActBuf T1, T2;
         // ---- FeedForward second Linear: x_out = h W2^T + b2 + x_mid
         set_tag(TAG_BWD_OTHER);
-        T1 = X.act(T.T1, (size_t)kDim * Mp);
-        T2 = X.act(T.T2, (size_t)kMlp * Mp);
-        RC(transpose_f32(dx, kDim, M, kDim, false, DropSpec(), 0, T1.out(), Mp, Mp, a576.out(), kDim, s));
+        RC(X.to_operand(dx, (size_t)M * kDim, DropSpec(), a576));
         RC(X.bias_grad(f32_in(dx), kDim, M, kDim, g->ff2_b[l]));
-        RC(X.transpose_act(hb, kMlp, M, kMlp, T2, Mp));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, kDim, kMlp, Mp, g->ff2_w[l]));
+        RC(X.wgrad(a576, kDim, hb, kMlp, M, kDim, kMlp, g->ff2_w[l]));
         ActBuf dh = X.act(T.a1728, (size_t)M * kMlp);
         {
             GemmEpilogue ep;  // d h_pre = (dx W2) * gelu'(h_pre)
@@ -413,12 +425,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         // ---- FeedForward first Linear: h_pre = LN2(x_mid) W1^T + b1
         set_tag(TAG_BWD_OTHER);
         RC(X.bias_grad(as_in(dh), kMlp, M, kMlp, g->ff1_b[l]));
-        T1 = X.act(T.T1, (size_t)kMlp * Mp);
-        T2 = X.act(T.T2, (size_t)kDim * Mp);
-        RC(X.transpose_act(dh, kMlp, M, kMlp, T1, Mp));
-        RC(X.transpose_act(xn2, kDim, M, kDim, T2, Mp));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, kMlp, kDim, Mp, g->ff1_w[l]));
+        RC(X.wgrad(dh, kMlp, xn2, kDim, M, kMlp, kDim, g->ff1_w[l]));
         {
             GemmEpilogue ep;
             ep.out.f32 = tmp;
@@ -429,13 +437,10 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         RC(layernorm_bwd(X.f32(S.x_mid), kDim, tmp, w->ln2_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln2_w[l], g->ln2_b[l], s));
         // ---- attention output projection: x_mid = Dropout(ao Wo^T + bo) + x_in
         const DropSpec drop_l = make_drop(tin->p_attn_dropout, sub_seed(tin->seed, 16 + l));
-        T1 = X.act(T.T1, (size_t)kDim * Mp);
-        T2 = X.act(T.T2, (size_t)kDim * Mp);
-        RC(transpose_f32(dx, kDim, M, kDim, false, drop_l, kDim, T1.out(), Mp, Mp, a576.out(), kDim, s));
+        RC(X.to_operand(dx, (size_t)M * kDim, drop_l, a576));
         RC(X.bias_grad(as_in(a576), kDim, M, kDim, g->out_b[l]));
-        RC(X.transpose_act(ao, kDim, M, kDim, T2, Mp));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, kDim, kDim, Mp, g->out_w[l]));
+        RC(X.wgrad(a576, kDim, ao, kDim, M, kDim, kDim, g->out_w[l]));
         {
             GemmEpilogue ep;
             ep.out.f32 = tmp;
@@ -446,12 +451,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         set_tag(TAG_BWD_OTHER);
         ActBuf dqkv = X.act(T.a1728, (size_t)M * 3 * kDim);
         RC(attention_bwd(X.f32(S.qkv), tmp, R, dqkv.out(), s));
-        T1 = X.act(T.T1, (size_t)3 * kDim * Mp);
-        T2 = X.act(T.T2, (size_t)kDim * Mp);
-        RC(X.transpose_act(dqkv, 3 * kDim, M, 3 * kDim, T1, Mp));
-        RC(X.transpose_act(xn1, kDim, M, kDim, T2, Mp));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, 3 * kDim, kDim, Mp, g->qkv_w[l]));
+        RC(X.wgrad(dqkv, 3 * kDim, xn1, kDim, M, 3 * kDim, kDim, g->qkv_w[l]));
         {
             GemmEpilogue ep;
             ep.out.f32 = tmp;
@@ -476,17 +477,13 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
 
     // ---- patch projections (per box): so = patches W2^T + b2, W2 the subject/object-factored proj_d / proj_v
     const int rowsB = N * kPatches;
-    const int64_t Kb = T.Kb;
     {
-        ActBuf T1 = X.act(T.T1, (size_t)2 * kDimDepth * Kb), T2 = X.act(T.T2, (size_t)kPatchVec * Kb);
         ActBuf a_box = X.act(T.a_box, (size_t)rowsB * 2 * kDimDepth);
         float* g_w_d2 = X.f32(T.g_w_d2);
-        RC(transpose_f32(d_so_d, 2 * kDimDepth, rowsB, 2 * kDimDepth, false, DropSpec(), 0, T1.out(), Kb, Kb, a_box.out(),
-                         2 * kDimDepth, s));
+        RC(X.to_operand(d_so_d, (size_t)rowsB * 2 * kDimDepth, DropSpec(), a_box));
         RC(X.bias_grad(f32_in(d_so_d), 2 * kDimDepth, rowsB, kDimDepth, g->proj_d_b));  // the bias sits in the subject half
-        RC(X.transpose_act(pa_d, kPatchVec, rowsB, kPatchVec, T2, Kb));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, 2 * kDimDepth, kPatchVec, Kb, g_w_d2));
+        RC(X.wgrad(a_box, 2 * kDimDepth, pa_d, kPatchVec, rowsB, 2 * kDimDepth, kPatchVec, g_w_d2));
         set_tag(TAG_BWD_OTHER);
         RC(unpack_patch(g_w_d2, g->proj_d_w, kDimDepth, s));
         if (out->grad_roi_depth) {
@@ -503,14 +500,12 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         }
     }
     {
-        ActBuf T1 = X.act(T.T1, (size_t)2 * kDimRgb * Kb), T2 = X.act(T.T2, (size_t)kPatchVec * Kb);
         ActBuf a_box = X.act(T.a_box, (size_t)rowsB * 2 * kDimRgb);
         float* g_w_v2 = X.f32(T.g_w_v2);
-        RC(transpose_f32(d_so_v, 2 * kDimRgb, rowsB, 2 * kDimRgb, false, DropSpec(), 0, T1.out(), Kb, Kb, a_box.out(), 2 * kDimRgb, s));
+        RC(X.to_operand(d_so_v, (size_t)rowsB * 2 * kDimRgb, DropSpec(), a_box));
         RC(X.bias_grad(f32_in(d_so_v), 2 * kDimRgb, rowsB, kDimRgb, g->proj_v_b));
-        RC(X.transpose_act(pa_v, kPatchVec, rowsB, kPatchVec, T2, Kb));
         set_tag(TAG_BWD_GEMM);
-        RC(X.wgrad(T1, T2, 2 * kDimRgb, kPatchVec, Kb, g_w_v2));
+        RC(X.wgrad(a_box, 2 * kDimRgb, pa_v, kPatchVec, rowsB, 2 * kDimRgb, kPatchVec, g_w_v2));
         set_tag(TAG_BWD_OTHER);
         RC(unpack_patch(g_w_v2, g->proj_v_w, kDimRgb, s));
         if (out->grad_roi_rgb) {

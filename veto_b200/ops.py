@@ -461,6 +461,20 @@ def test_gemm(a, w, bias=None, residual=None, act: int = 0, precision: str = "fp
     return c
 
 
+def test_gemm_tn(y, x, precision: str = "bf16x3", split_k: int = 1, geometry=None):
+    """out[Nw,Kw] = y[rows,Nw]^T @ x[rows,Kw] through the MN-major tcgen05 weight-gradient kernel."""
+    L.require_device()
+    y, x = _cuda_f32(y), _cuda_f32(x)
+    rows, Nw = y.shape
+    Kw = x.shape[1]
+    out = torch.empty((Nw, Kw), dtype=torch.float32, device=y.device)
+    scratch = torch.empty(4 * (rows * Nw + rows * Kw) + 4 * Nw * Kw * max(1, split_k) + 256, dtype=torch.uint8, device=y.device)
+    geo = (ctypes.c_uint32 * 3)(*[int(v) for v in geometry]) if geometry is not None else None
+    L.check(L.load().veto_test_gemm_tn(y.data_ptr(), x.data_ptr(), out.data_ptr(), rows, Nw, Kw, L.PRECISIONS[precision],
+                                       split_k, geo, scratch.data_ptr(), scratch.numel(), L.stream_ptr()), "veto_test_gemm_tn")
+    return out
+
+
 def test_layernorm(x, w, b):
     L.require_device()
     x = _cuda_f32(x)
