@@ -276,7 +276,7 @@ int64_t veto_last_launch_count(void);
 /* Per-stage device timing (used by bench.py for the roofline line; not a profiler): between begin and end every
  * kernel launch of this thread is bracketed by CUDA events on `stream`; end synchronises and adds, per stage tag,
  * the elapsed milliseconds and the launch count into the caller's host arrays of length VETO_PROFILE_TAGS. */
-#define VETO_PROFILE_TAGS 16
+#define VETO_PROFILE_TAGS 24
 int veto_profile_begin(veto_stream_t stream);
 int veto_profile_end(double* ms_by_tag_host, int64_t* launches_by_tag_host);
 const char* veto_profile_tag_name(int tag);

@@ -33,7 +33,8 @@ static thread_local std::vector<ProfEvent> g_prof_events;
 static thread_local int g_tag = 0;
 static const char* kTagNames[VETO_PROFILE_TAGS] = {"other", "pairs", "roi_gather", "box_stage", "tokens", "layernorm",
                                                    "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
-                                                   "classifier", "postprocess", "pack", "bwd_gemm", "bwd_other"};
+                                                   "classifier", "postprocess", "pack", "bwd_dgrad", "bwd_other", "bwd_attention", "bwd_layernorm",
+                                                   "bwd_box_stage", "bwd_wgrad", "loss", "", "", ""};
 
 void set_tag(int tag) { g_tag = tag; }
 void count_launch(int n) {

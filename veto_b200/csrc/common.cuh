@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int n = 1);
 // stage tags of the per-stage event timing (veto_profile_*); names in api.cu
 enum { TAG_OTHER = 0, TAG_PAIRS, TAG_GATHER, TAG_BOX, TAG_TOKENS, TAG_LN, TAG_QKV, TAG_ATT, TAG_OUT, TAG_FF1, TAG_FF2,
-       TAG_CLS, TAG_POST, TAG_PACK, TAG_BWD_GEMM, TAG_BWD_OTHER };
+       TAG_CLS, TAG_POST, TAG_PACK, TAG_BWD_GEMM, TAG_BWD_OTHER, TAG_BWD_ATT, TAG_BWD_LN, TAG_BWD_BOX, TAG_BWD_WGRAD, TAG_LOSS };
 void set_tag(int tag);
 
 #define VETO_CUDA(expr)                                                               \

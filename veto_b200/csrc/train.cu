@@ -246,19 +246,25 @@ convert_kernel(const float* __restrict__ src, size_t n4, DropSpec drop, float* f
 // ---------------------------------------------------------------- LayerNorm backward
 // warp per row.  xhat = (x - mean) * rstd, g = dy * gamma:
 //   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres);  dgamma += dy * xhat;  dbeta += dy
-// Per-block partial dgamma / dbeta go to partial[block, 2, 576]; a column sum over blocks finishes them.
+// Per-block partial dgamma / dbeta go to partial[block, 3, 576]; a column sum over blocks finishes them.
+// The gradient that leaves (dx) is what the next backward GEMMs consume, so the kernel also writes it in their operand
+// format (op_*: fp32 or bf16 hi/lo), through the dropout mask of the Linear below when there is one, and accumulates
+// its column sums (partial[block, 2, :]) = that Linear's bias gradient — no separate convert / column-sum passes.
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, const float* __restrict__ gamma,
-              const float* dres, float* dx, int64_t rows, float* __restrict__ partial) {
+              const float* dres, float* dx, int64_t rows, float* __restrict__ partial, DropSpec drop, float* op_f32,
+              __nv_bfloat16* op_hi, __nv_bfloat16* op_lo) {
     constexpr int PER = kDim / 64;  // 9 float2 per lane
-    __shared__ float red[8][2 * kDim];
+    __shared__ float red[8][kDim];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float2 gam[PER], dg[PER], db[PER];
+    const bool want_op = op_f32 || op_hi;
+    float2 gam[PER], dg[PER], db[PER], ds[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
         gam[j] = __ldg((const float2*)gamma + lane + 32 * j);
         dg[j] = make_float2(0.f, 0.f);
         db[j] = make_float2(0.f, 0.f);
+        ds[j] = make_float2(0.f, 0.f);
     }
     for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < rows; row += (int64_t)gridDim.x * 8) {
         const float2* xr = (const float2*)(x + row * ldx);
@@ -307,167 +313,214 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
                 o.y += rr.y;
             }
             *(float2*)(dx + e) = o;
+            if (want_op) {
+                if (drop.thr16) {  // elements e, e + 1 share a 4-group (e is even)
+                    const uint64_t h = drop_hash(drop.seed, e >> 2);
+                    const int sh = 16 * (int)(e & 3);
+                    o.x = ((uint32_t)(h >> sh) & 0xffffu) >= drop.thr16 ? o.x * drop.scale : 0.f;
+                    o.y = ((uint32_t)(h >> (sh + 16)) & 0xffffu) >= drop.thr16 ? o.y * drop.scale : 0.f;
+                }
+                ds[j].x += o.x;
+                ds[j].y += o.y;
+                if (op_f32) *(float2*)(op_f32 + e) = o;
+                if (op_hi) {
+                    uint32_t hh, ll;
+                    split_pair(o.x, o.y, hh, ll);
+                    *(uint32_t*)(op_hi + e) = hh;
+                    if (op_lo) *(uint32_t*)(op_lo + e) = ll;
+                }
+            }
         }
     }
+    for (int v = 0; v < 3; ++v) {  // dgamma, dbeta, colsum(op): cross-warp sums through one 18 KB buffer
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int c = 2 * (lane + 32 * j);
-        red[wid][c] = dg[j].x;
-        red[wid][c + 1] = dg[j].y;
-        red[wid][kDim + c] = db[j].x;
-        red[wid][kDim + c + 1] = db[j].y;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 2 * kDim; c += 256) {
-        float a = 0.f;
+        for (int j = 0; j < PER; ++j) {
+            const float2 t = v == 0 ? dg[j] : v == 1 ? db[j] : ds[j];
+            *(float2*)&red[wid][2 * (lane + 32 * j)] = t;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < kDim; c += 256) {
+            float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += red[w][c];
-        partial[(size_t)blockIdx.x * 2 * kDim + c] = a;
+            for (int w = 0; w < 8; ++w) a += red[w][c];
+            partial[(size_t)blockIdx.x * 3 * kDim + v * kDim + c] = a;
+        }
     }
 }
 
 // ---------------------------------------------------------------- attention backward
-// One warp per (sequence, head).  Q, K, V of the head (from the saved qkv) and dO are staged in shared memory; lane i
-// owns query row i for S = Q K^T, P = softmax, dP = dO V^T, dS = P * (dP - rowsum(P * dP)) * scale and dQ = dS K;
-// lane j then owns key row j for dK = dS^T Q and dV = P^T dO.  Results overwrite the staging buffers that are no
-// longer needed (dQ -> V, dK -> K, dV -> Q) and leave with coalesced 128-bit stores.
-constexpr int AB_STRIDE = 100;                   // floats per staged row (96 + 4: float4 reads of different rows hit different banks)
+// TWO warps per (sequence, head): each owns 48 of the 96 head dims (float4 columns 12h .. 12h+11) of Q, K, V, dO in
+// shared memory, so everything except the 19 x 19 score tile is private to a warp.  Lane i owns query row i:
+//   partial S = Q K^T and dP = dO V^T over the warp's dims  -> the odd warp hands its partials to the even one through
+//   the P / dS tiles (named barrier), which finishes P = softmax(S * scale), dS = P * (dP - rowsum(P * dP)) * scale and
+//   leaves both tiles in shared memory (second barrier);
+//   dQ = dS K (row i);  then lane j owns key row j: dK = dS^T Q, dV = P^T dO, each for the warp's own dims.
+// Results overwrite the staging buffers that are no longer needed (dQ -> V, dK -> K, dV -> Q) and leave with coalesced
+// 128-bit stores.  The first version (one warp per item, six warps per SM, synchronous staging loop) ran at 1.18 ms
+// per launch, latency-bound; 14 warps per SM with cp.async staging hide the shared-memory latency.
+// Rows are 96 floats with the float4 column index XOR-swizzled by the row (c ^ (row & 7) within groups of 8), so the
+// per-lane row reads are bank-conflict free without padding: 7 items fit in 227 KB.
+constexpr int AB_ROW = kHeadDim;                 // floats per staged row
 constexpr int AB_PS = 20;                        // row stride of the P / dS tiles
-constexpr int AB_ITEM = 4 * kTokens * AB_STRIDE + 2 * kTokens * AB_PS;  // floats per warp
-constexpr int AB_WARPS = 6;
-constexpr int AB_SMEM = AB_WARPS * AB_ITEM * (int)sizeof(float);  // 200,640 B
+constexpr int AB_ITEM = 4 * kTokens * AB_ROW + 2 * kTokens * AB_PS;  // floats per item (32,224 B)
+constexpr int AB_ITEMS = 7;
+constexpr int AB_THREADS = AB_ITEMS * 64;
+constexpr int AB_SMEM = AB_ITEMS * AB_ITEM * (int)sizeof(float);  // 225,568 B
 
-__global__ void __launch_bounds__(AB_WARPS * 32)
+__device__ __forceinline__ int ab_col(int row, int c) { return (c & ~7) | ((c ^ row) & 7); }  // swizzled float4 column
+__device__ __forceinline__ void ab_bar(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int64_t n_seq, float* g_f32,
                      __nv_bfloat16* g_hi, __nv_bfloat16* g_lo) {
     extern __shared__ float4 ab_smem[];
-    constexpr int LD = 3 * kDim, V4 = kHeadDim / 4;
+    constexpr int LD = 3 * kDim, V4 = kHeadDim / 4, HV4 = V4 / 2;  // 24 float4 columns per row, 12 per warp
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* sQ = reinterpret_cast<float*>(ab_smem) + wid * AB_ITEM;
-    float* sK = sQ + kTokens * AB_STRIDE;
-    float* sV = sK + kTokens * AB_STRIDE;
-    float* sDO = sV + kTokens * AB_STRIDE;
-    float* sP = sDO + kTokens * AB_STRIDE;
+    const int slot = wid >> 1, half = wid & 1, c_lo = half * HV4;
+    float* sQ = reinterpret_cast<float*>(ab_smem) + slot * AB_ITEM;
+    float* sK = sQ + kTokens * AB_ROW;
+    float* sV = sK + kTokens * AB_ROW;
+    float* sDO = sV + kTokens * AB_ROW;
+    float* sP = sDO + kTokens * AB_ROW;
     float* sDS = sP + kTokens * AB_PS;
+    auto cell = [&](float* buf, int row, int c) { return (float4*)(buf + row * AB_ROW) + ab_col(row, c); };
     const float scale = 0.10206207261596575f;
     const int64_t items = n_seq * kHeads;
-    for (int64_t item = (int64_t)blockIdx.x * AB_WARPS + wid; item < items; item += (int64_t)gridDim.x * AB_WARPS) {
+    // every warp of a slot runs the same number of iterations (the barriers are per slot)
+    for (int64_t item = (int64_t)blockIdx.x * AB_ITEMS + slot; item < items; item += (int64_t)gridDim.x * AB_ITEMS) {
         const int64_t seq = item / kHeads;
         const int h = (int)(item - seq * kHeads);
         const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
         const float* dob = d_out + (size_t)seq * kTokens * kDim + h * kHeadDim;
         __syncwarp();
-        for (int idx = lane; idx < 4 * kTokens * V4; idx += 32) {
-            const int m = idx / V4, c = idx - m * V4;
+        // stage this warp's 12 columns of the 76 rows (q, k, v, dO): 912 16-byte cp.async, all in flight at once
+        for (int idx = lane; idx < 4 * kTokens * HV4; idx += 32) {
+            const int m = idx / HV4, c = c_lo + (idx - m * HV4);
             const int which = m / kTokens, row = m - which * kTokens;
-            const float4 v = which < 3 ? __ldg((const float4*)(base + (size_t)row * LD + which * kDim) + c)
-                                       : __ldg((const float4*)(dob + (size_t)row * kDim) + c);
-            *((float4*)(sQ + (which * kTokens + row) * AB_STRIDE) + c) = v;
+            const float* src = which < 3 ? base + (size_t)row * LD + which * kDim + 4 * c : dob + (size_t)row * kDim + 4 * c;
+            float4* dst = cell(sQ + which * kTokens * AB_ROW, row, c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         float ds[kTokens];
-        if (lane < kTokens) {
+        {
             float p[kTokens], dp[kTokens];
 #pragma unroll
             for (int j = 0; j < kTokens; ++j) { p[j] = 0.f; dp[j] = 0.f; }
-            const float4* q4 = (const float4*)(sQ + lane * AB_STRIDE);
-            const float4* do4 = (const float4*)(sDO + lane * AB_STRIDE);
+            if (lane < kTokens) {
 #pragma unroll 2
-            for (int c = 0; c < V4; ++c) {
-                const float4 q = q4[c], g = do4[c];
+                for (int cc = 0; cc < HV4; ++cc) {
+                    const int c = c_lo + cc;
+                    const float4 q = *cell(sQ, lane, c), g = *cell(sDO, lane, c);
 #pragma unroll
-                for (int j = 0; j < kTokens; ++j) {
-                    const float4 k4 = *((const float4*)(sK + j * AB_STRIDE) + c);
-                    const float4 v4 = *((const float4*)(sV + j * AB_STRIDE) + c);
-                    p[j] = fmaf(q.x, k4.x, p[j]); p[j] = fmaf(q.y, k4.y, p[j]);
-                    p[j] = fmaf(q.z, k4.z, p[j]); p[j] = fmaf(q.w, k4.w, p[j]);
-                    dp[j] = fmaf(g.x, v4.x, dp[j]); dp[j] = fmaf(g.y, v4.y, dp[j]);
-                    dp[j] = fmaf(g.z, v4.z, dp[j]); dp[j] = fmaf(g.w, v4.w, dp[j]);
+                    for (int j = 0; j < kTokens; ++j) {
+                        const float4 k4 = *cell(sK, j, c);
+                        const float4 v4 = *cell(sV, j, c);
+                        p[j] = fmaf(q.x, k4.x, p[j]); p[j] = fmaf(q.y, k4.y, p[j]);
+                        p[j] = fmaf(q.z, k4.z, p[j]); p[j] = fmaf(q.w, k4.w, p[j]);
+                        dp[j] = fmaf(g.x, v4.x, dp[j]); dp[j] = fmaf(g.y, v4.y, dp[j]);
+                        dp[j] = fmaf(g.z, v4.z, dp[j]); dp[j] = fmaf(g.w, v4.w, dp[j]);
+                    }
                 }
             }
-            float m = -INFINITY;
+            if (half == 1 && lane < kTokens) {
 #pragma unroll
-            for (int j = 0; j < kTokens; ++j) {
-                p[j] *= scale;
-                m = fmaxf(m, p[j]);
+                for (int j = 0; j < kTokens; ++j) {
+                    sP[lane * AB_PS + j] = p[j];
+                    sDS[lane * AB_PS + j] = dp[j];
+                }
             }
-            float sum = 0.f;
+            ab_bar(slot);  // the odd warp's partial scores are in the tiles
+            if (half == 0 && lane < kTokens) {
+                float m = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kTokens; ++j) {
-                p[j] = expf(p[j] - m);
-                sum += p[j];
-            }
-            const float inv = 1.f / sum;
-            float dsum = 0.f;
+                for (int j = 0; j < kTokens; ++j) {
+                    p[j] = (p[j] + sP[lane * AB_PS + j]) * scale;
+                    dp[j] += sDS[lane * AB_PS + j];
+                    m = fmaxf(m, p[j]);
+                }
+                float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < kTokens; ++j) {
-                p[j] *= inv;
-                dsum = fmaf(p[j], dp[j], dsum);
-            }
+                for (int j = 0; j < kTokens; ++j) {
+                    p[j] = expf(p[j] - m);
+                    sum += p[j];
+                }
+                const float inv = 1.f / sum;
+                float dsum = 0.f;
 #pragma unroll
-            for (int j = 0; j < kTokens; ++j) {
-                ds[j] = p[j] * (dp[j] - dsum) * scale;
-                sP[lane * AB_PS + j] = p[j];
-                sDS[lane * AB_PS + j] = ds[j];
+                for (int j = 0; j < kTokens; ++j) {
+                    p[j] *= inv;
+                    dsum = fmaf(p[j], dp[j], dsum);
+                }
+#pragma unroll
+                for (int j = 0; j < kTokens; ++j) {
+                    sP[lane * AB_PS + j] = p[j];
+                    sDS[lane * AB_PS + j] = p[j] * (dp[j] - dsum) * scale;
+                }
             }
+            ab_bar(slot);  // P and dS are final
         }
-        __syncwarp();  // every lane is done with V: dQ may overwrite it
         if (lane < kTokens) {
-            float4* dq4 = (float4*)(sV + lane * AB_STRIDE);
+#pragma unroll
+            for (int j = 0; j < kTokens; ++j) ds[j] = sDS[lane * AB_PS + j];
+            // dQ (row = lane) over the warp's columns -> V buffer (V is dead: every lane of this warp is past dP,
+            // and the other warp never touches these columns)
 #pragma unroll 2
-            for (int c = 0; c < V4; ++c) {
+            for (int cc = 0; cc < HV4; ++cc) {
+                const int c = c_lo + cc;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < kTokens; ++j) {
-                    const float4 k4 = *((const float4*)(sK + j * AB_STRIDE) + c);
+                    const float4 k4 = *cell(sK, j, c);
                     a.x = fmaf(ds[j], k4.x, a.x); a.y = fmaf(ds[j], k4.y, a.y);
                     a.z = fmaf(ds[j], k4.z, a.z); a.w = fmaf(ds[j], k4.w, a.w);
                 }
-                dq4[c] = a;
+                *cell(sV, lane, c) = a;
             }
         }
-        __syncwarp();  // K is free now: dK overwrites it; lane j = key row j, column j of dS / P
-        float col[kTokens];
+        __syncwarp();  // this warp's K columns are free now: dK overwrites them; lane j = key row j, column j of dS / P
         if (lane < kTokens) {
 #pragma unroll
-            for (int i = 0; i < kTokens; ++i) col[i] = sDS[i * AB_PS + lane];
-            float4* dk4 = (float4*)(sK + lane * AB_STRIDE);
+            for (int i = 0; i < kTokens; ++i) ds[i] = sDS[i * AB_PS + lane];
 #pragma unroll 2
-            for (int c = 0; c < V4; ++c) {
+            for (int cc = 0; cc < HV4; ++cc) {
+                const int c = c_lo + cc;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < kTokens; ++i) {
-                    const float4 q4 = *((const float4*)(sQ + i * AB_STRIDE) + c);
-                    a.x = fmaf(col[i], q4.x, a.x); a.y = fmaf(col[i], q4.y, a.y);
-                    a.z = fmaf(col[i], q4.z, a.z); a.w = fmaf(col[i], q4.w, a.w);
+                    const float4 q4 = *cell(sQ, i, c);
+                    a.x = fmaf(ds[i], q4.x, a.x); a.y = fmaf(ds[i], q4.y, a.y);
+                    a.z = fmaf(ds[i], q4.z, a.z); a.w = fmaf(ds[i], q4.w, a.w);
                 }
-                dk4[c] = a;
+                *cell(sK, lane, c) = a;
             }
         }
-        __syncwarp();  // Q is free now: dV overwrites it
+        __syncwarp();  // Q columns are free now: dV overwrites them
         if (lane < kTokens) {
 #pragma unroll
-            for (int i = 0; i < kTokens; ++i) col[i] = sP[i * AB_PS + lane];
-            float4* dv4 = (float4*)(sQ + lane * AB_STRIDE);
+            for (int i = 0; i < kTokens; ++i) ds[i] = sP[i * AB_PS + lane];
 #pragma unroll 2
-            for (int c = 0; c < V4; ++c) {
+            for (int cc = 0; cc < HV4; ++cc) {
+                const int c = c_lo + cc;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < kTokens; ++i) {
-                    const float4 g4 = *((const float4*)(sDO + i * AB_STRIDE) + c);
-                    a.x = fmaf(col[i], g4.x, a.x); a.y = fmaf(col[i], g4.y, a.y);
-                    a.z = fmaf(col[i], g4.z, a.z); a.w = fmaf(col[i], g4.w, a.w);
+                    const float4 g4 = *cell(sDO, i, c);
+                    a.x = fmaf(ds[i], g4.x, a.x); a.y = fmaf(ds[i], g4.y, a.y);
+                    a.z = fmaf(ds[i], g4.z, a.z); a.w = fmaf(ds[i], g4.w, a.w);
                 }
-                dv4[c] = a;
+                *cell(sQ, lane, c) = a;
             }
         }
         __syncwarp();
-        // dq (in sV) -> cols [0,576), dk (sK) -> [576,1152), dv (sQ) -> [1152,1728) of the head's 96-wide slice
-        for (int idx = lane; idx < 3 * kTokens * V4; idx += 32) {
-            const int m = idx / V4, c = idx - m * V4;
+        // dq (in sV) -> cols [0,576), dk (sK) -> [576,1152), dv (sQ) -> [1152,1728): this warp's 48 dims of the head
+        for (int idx = lane; idx < 3 * kTokens * HV4; idx += 32) {
+            const int m = idx / HV4, c = c_lo + (idx - m * HV4);
             const int which = m / kTokens, row = m - which * kTokens;
-            const float* srcb = which == 0 ? sV : which == 1 ? sK : sQ;
-            const float4 v = *((const float4*)(srcb + row * AB_STRIDE) + c);
+            const float4 v = *cell(which == 0 ? sV : which == 1 ? sK : sQ, row, c);
             const size_t o = ((size_t)seq * kTokens + row) * LD + which * kDim + h * kHeadDim + 4 * c;
             if (g_f32) *(float4*)(g_f32 + o) = v;
             if (g_hi) {
@@ -478,6 +531,8 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
                 if (g_lo) *(uint2*)(g_lo + o) = ll;
             }
         }
+        // the P / dS tiles are rewritten by the odd warp in the next iteration: both warps must be past their reads
+        ab_bar(slot);
     }
 }
 
@@ -824,17 +879,24 @@ int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& 
 int ln_bwd_blocks(int64_t rows) { return grid_cap((size_t)(rows + 7) / 8, 4); }
 
 int layernorm_bwd(const float* x, int64_t ldx, const float* dy, const float* gamma, const float* dres, float* dx, int64_t rows,
-                  float* partial, float* colsum_scratch, float* g_gamma, float* g_beta, cudaStream_t s) {
+                  float* partial, float* colsum_scratch, float* g_gamma, float* g_beta, cudaStream_t s, const DropSpec& drop,
+                  const ActOut& op_out, float* g_op_colsum) {
     if (rows <= 0) return VETO_OK;
     const int grid = ln_bwd_blocks(rows);
-    ln_bwd_kernel<<<grid, 256, 0, s>>>(x, ldx, dy, gamma, dres, dx, rows, partial);
+    ln_bwd_kernel<<<grid, 256, 0, s>>>(x, ldx, dy, gamma, dres, dx, rows, partial, drop, op_out.f32, op_out.hi, op_out.lo);
     VETO_LAUNCH_CHECK();
+    // one two-stage column sum over the per-block partials finishes dgamma | dbeta | colsum(op) together
+    const bool want_op = (op_out.f32 || op_out.hi) && g_op_colsum;
+    const int cols = want_op ? 3 * kDim : 2 * kDim;
     ActIn p;
     p.f32 = partial;
-    int rc;
-    if ((rc = colsum(p, 2 * kDim, grid, kDim, colsum_scratch, g_gamma, false, s))) return rc;
-    p.f32 = partial + kDim;
-    return colsum(p, 2 * kDim, grid, kDim, colsum_scratch, g_beta, false, s);
+    float* packed = colsum_scratch + colsum_scratch_floats(3 * kDim);
+    int rc = colsum(p, 3 * kDim, grid, cols, colsum_scratch, packed, false, s);
+    if (rc) return rc;
+    VETO_CUDA(cudaMemcpyAsync(g_gamma, packed, sizeof(float) * kDim, cudaMemcpyDeviceToDevice, s));
+    VETO_CUDA(cudaMemcpyAsync(g_beta, packed + kDim, sizeof(float) * kDim, cudaMemcpyDeviceToDevice, s));
+    if (want_op) VETO_CUDA(cudaMemcpyAsync(g_op_colsum, packed + 2 * kDim, sizeof(float) * kDim, cudaMemcpyDeviceToDevice, s));
+    return VETO_OK;
 }
 
 int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const ActOut& d_qkv, cudaStream_t s) {
@@ -844,9 +906,9 @@ int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const Act
         VETO_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
         attr_set = true;
     }
-    const int64_t blocks = (n_seq * kHeads + AB_WARPS - 1) / AB_WARPS;
+    const int64_t blocks = (n_seq * kHeads + AB_ITEMS - 1) / AB_ITEMS;
     const int grid = (int)(blocks < num_sms() ? blocks : num_sms());
-    attention_bwd_kernel<<<grid, AB_WARPS * 32, AB_SMEM, s>>>(qkv, d_out, n_seq, d_qkv.f32, d_qkv.hi, d_qkv.lo);
+    attention_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(qkv, d_out, n_seq, d_qkv.f32, d_qkv.hi, d_qkv.lo);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -32,10 +32,13 @@ int dropout_inplace(float* x, size_t n, const DropSpec& drop, cudaStream_t s);
 int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s);
 
 // LayerNorm backward over rows of 576: dx = dres + dLN(dy) (dx may alias dres or dy), g_gamma / g_beta overwritten.
-// partial: >= ln_bwd_blocks(rows) * 1152 floats.
+// Optionally also writes op_out = dropout(dx) in the operand format of the next backward GEMMs and its column sums
+// g_op_colsum[576] (the bias gradient of the Linear below).  partial: >= ln_bwd_blocks(rows) * 1728 floats;
+// colsum_scratch: >= colsum_scratch_floats(1728) + 1728 floats.
 int ln_bwd_blocks(int64_t rows);
 int layernorm_bwd(const float* x, int64_t ldx, const float* dy, const float* gamma, const float* dres, float* dx, int64_t rows,
-                  float* partial, float* colsum_scratch, float* g_gamma, float* g_beta, cudaStream_t s);
+                  float* partial, float* colsum_scratch, float* g_gamma, float* g_beta, cudaStream_t s,
+                  const DropSpec& drop = DropSpec(), const ActOut& op_out = ActOut(), float* g_op_colsum = nullptr);
 // attention core backward: qkv fp32 [n_seq*19, 1728] (saved), d_out fp32 [n_seq*19, 576] -> d_qkv [n_seq*19, 1728]
 int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const ActOut& d_qkv, cudaStream_t s);
 // token gather backward: dx [R,19,576] -> d_so_d [N*16,1024], d_so_v [N*16,128], d_lso / d_cso [N,1152]

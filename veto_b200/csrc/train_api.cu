@@ -93,8 +93,8 @@ TrainLayout train_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs)
     T.T1 = k.take(simt ? f * max_sz((size_t)3 * kDim * T.Mp, (size_t)2 * kDimDepth * T.Kb) : 0);
     T.T2 = k.take(simt ? f * max_sz((size_t)kMlp * T.Mp, (size_t)kPatchVec * T.Kb) : 0);
     T.splitk = k.take(simt ? 0 : f * (size_t)kMaxSplit * max_sz((size_t)3 * kDim * kDim, (size_t)2 * kDimDepth * kPatchVec));
-    T.ln_partial = k.take(f * (size_t)ln_bwd_blocks((int64_t)M) * 2 * kDim);
-    T.colsum_scratch = k.take(f * colsum_scratch_floats(3 * kDim));
+    T.ln_partial = k.take(f * (size_t)ln_bwd_blocks((int64_t)M) * 3 * kDim);
+    T.colsum_scratch = k.take(f * (colsum_scratch_floats(3 * kDim) + 3 * kDim));
     for (int l = 0; l < c.layers; ++l) {
         T.WT[l].qkv = k.take(act_bytes(prec, (size_t)3 * kDim * kDim));
         T.WT[l].out = k.take(act_bytes(prec, (size_t)kDim * kDim));
@@ -140,6 +140,12 @@ struct Ctx {
     }
     // gW[Nw,Kw] = dY[rows,Nw]^T @ X[rows,Kw]: the weight gradient of y = x W^T, operands row-major as the backward holds them
     int wgrad(const ActBuf& dY, int ldy, const ActBuf& X, int ldx, int64_t rows, int Nw, int Kw, float* gW) const {
+        set_tag(TAG_BWD_WGRAD);
+        const int rc = wgrad_impl(dY, ldy, X, ldx, rows, Nw, Kw, gW);
+        set_tag(TAG_BWD_GEMM);
+        return rc;
+    }
+    int wgrad_impl(const ActBuf& dY, int ldy, const ActBuf& X, int ldx, int64_t rows, int Nw, int Kw, float* gW) const {
         if (prec == VETO_PREC_FP32) {
             const int64_t Kp = pad64(rows);
             float* t1 = f32(T->T1);
@@ -359,11 +365,12 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     }
 
     // =====================================================================================  loss and backward
-    set_tag(TAG_BWD_OTHER);
+    set_tag(TAG_LOSS);
     float* dlogits = X.f32(T.dlogits);
     RC(ce_loss_grad(logits, C, tin->rel_labels, tin->class_weight, R, X.f32(T.ce_scratch), out->loss, dlogits, s));
     float* dx = X.f32(T.dx);
     float* tmp = X.f32(T.tmp);
+    set_tag(TAG_BWD_OTHER);
     {
         // rel_out: d b = colsum(dlogits); d W = dlogits^T x_cls; d x_cls = dlogits W (scattered into rows r*19 of dx)
         RC(X.bias_grad(f32_in(dlogits), C, R, C, g->rel_out_b));
@@ -407,10 +414,13 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         const LayerSave& S = T.L[l];
         ActBuf xn1 = X.act(S.xn1, (size_t)M * kDim), ao = X.act(S.ao, (size_t)M * kDim), xn2 = X.act(S.xn2, (size_t)M * kDim);
         ActBuf hb = X.act(S.h, (size_t)M * kMlp);
-        // ---- FeedForward second Linear: x_out = h W2^T + b2 + x_mid
+        // ---- FeedForward second Linear: x_out = h W2^T + b2 + x_mid.  dx in operand format (a576) and its column
+        // sums (ff2_b) come from the LayerNorm backward of the layer above; only the top layer converts here
         set_tag(TAG_BWD_OTHER);
-        RC(X.to_operand(dx, (size_t)M * kDim, DropSpec(), a576));
-        RC(X.bias_grad(f32_in(dx), kDim, M, kDim, g->ff2_b[l]));
+        if (l == NL - 1) {
+            RC(X.to_operand(dx, (size_t)M * kDim, DropSpec(), a576));
+            RC(X.bias_grad(f32_in(dx), kDim, M, kDim, g->ff2_b[l]));
+        }
         set_tag(TAG_BWD_GEMM);
         RC(X.wgrad(a576, kDim, hb, kMlp, M, kDim, kMlp, g->ff2_w[l]));
         ActBuf dh = X.act(T.a1728, (size_t)M * kMlp);
@@ -433,12 +443,12 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
             ep.ldc = kDim;
             RC(X.mm(dh, kMlp, wT_ff1[l], M, kDim, kMlp, ep));
         }
-        set_tag(TAG_BWD_OTHER);
-        RC(layernorm_bwd(X.f32(S.x_mid), kDim, tmp, w->ln2_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln2_w[l], g->ln2_b[l], s));
-        // ---- attention output projection: x_mid = Dropout(ao Wo^T + bo) + x_in
+        set_tag(TAG_BWD_LN);
+        // ---- attention output projection: x_mid = Dropout(ao Wo^T + bo) + x_in: the LayerNorm backward also emits
+        // mask * dx in operand format (a576) and its column sums = the to_out bias gradient
         const DropSpec drop_l = make_drop(tin->p_attn_dropout, sub_seed(tin->seed, 16 + l));
-        RC(X.to_operand(dx, (size_t)M * kDim, drop_l, a576));
-        RC(X.bias_grad(as_in(a576), kDim, M, kDim, g->out_b[l]));
+        RC(layernorm_bwd(X.f32(S.x_mid), kDim, tmp, w->ln2_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln2_w[l], g->ln2_b[l], s,
+                         drop_l, a576.out(), g->out_b[l]));
         set_tag(TAG_BWD_GEMM);
         RC(X.wgrad(a576, kDim, ao, kDim, M, kDim, kDim, g->out_w[l]));
         {
@@ -448,7 +458,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
             RC(X.mm(a576, kDim, wT_out[l], M, kDim, kDim, ep));
         }
         // ---- attention core, then to_qkv: qkv = LN1(x_in) Wqkv^T
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_ATT);
         ActBuf dqkv = X.act(T.a1728, (size_t)M * 3 * kDim);
         RC(attention_bwd(X.f32(S.qkv), tmp, R, dqkv.out(), s));
         set_tag(TAG_BWD_GEMM);
@@ -459,12 +469,16 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
             ep.ldc = kDim;
             RC(X.mm(dqkv, 3 * kDim, wT_qkv[l], M, kDim, 3 * kDim, ep));
         }
-        set_tag(TAG_BWD_OTHER);
-        RC(layernorm_bwd(x_in[l], kDim, tmp, w->ln1_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln1_w[l], g->ln1_b[l], s));
+        set_tag(TAG_BWD_LN);
+        if (l > 0)  // dx feeds the FeedForward backward of layer l - 1: operand copy + ff2 bias gradient ride along
+            RC(layernorm_bwd(x_in[l], kDim, tmp, w->ln1_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln1_w[l], g->ln1_b[l], s,
+                             DropSpec(), a576.out(), g->ff2_b[l - 1]));
+        else
+            RC(layernorm_bwd(x_in[l], kDim, tmp, w->ln1_w[l], dx, dx, M, ln_partial, X.colsum_scratch, g->ln1_w[l], g->ln1_b[l], s));
     }
 
     // ---- encoder input: x = Dropout(cat(cls, patches, loc, cls) + pos_embedding)
-    set_tag(TAG_BWD_OTHER);
+    set_tag(TAG_BWD_BOX);
     RC(dropout_inplace(dx, (size_t)M * kDim, drop_emb, s));
     RC(X.bias_grad(f32_in(dx), kDim, M, kDim, g->pos_embedding));
     RC(X.bias_grad(f32_in(dx), (int64_t)kTokens * kDim, R, kDim, g->cls_token));
@@ -484,7 +498,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         RC(X.bias_grad(f32_in(d_so_d), 2 * kDimDepth, rowsB, kDimDepth, g->proj_d_b));  // the bias sits in the subject half
         set_tag(TAG_BWD_GEMM);
         RC(X.wgrad(a_box, 2 * kDimDepth, pa_d, kPatchVec, rowsB, 2 * kDimDepth, kPatchVec, g_w_d2));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(unpack_patch(g_w_d2, g->proj_d_w, kDimDepth, s));
         if (out->grad_roi_depth) {
             ActBuf d2T = X.act(T.d2T, (size_t)2 * kDimDepth * kPatchVec);  // [1024 in, 1024 out]
@@ -495,7 +509,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
             ep.ldc = kPatchVec;
             set_tag(TAG_BWD_GEMM);
             RC(X.mm(a_box, 2 * kDimDepth, d2T, rowsB, kPatchVec, 2 * kDimDepth, ep));
-            set_tag(TAG_BWD_OTHER);
+            set_tag(TAG_BWD_BOX);
             RC(unpatchify(X.f32(T.d_pa), N, out->grad_roi_depth, s));
         }
     }
@@ -506,7 +520,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         RC(X.bias_grad(f32_in(d_so_v), 2 * kDimRgb, rowsB, kDimRgb, g->proj_v_b));
         set_tag(TAG_BWD_GEMM);
         RC(X.wgrad(a_box, 2 * kDimRgb, pa_v, kPatchVec, rowsB, 2 * kDimRgb, kPatchVec, g_w_v2));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(unpack_patch(g_w_v2, g->proj_v_w, kDimRgb, s));
         if (out->grad_roi_rgb) {
             ActBuf v2T = X.act(T.v2T, (size_t)2 * kDimRgb * kPatchVec);  // [1024 in, 128 out]
@@ -517,7 +531,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
             ep.ldc = kPatchVec;
             set_tag(TAG_BWD_GEMM);
             RC(X.mm(a_box, 2 * kDimRgb, v2T, rowsB, kPatchVec, 2 * kDimRgb, ep));
-            set_tag(TAG_BWD_OTHER);
+            set_tag(TAG_BWD_BOX);
             RC(unpatchify(X.f32(T.d_pa), N, out->grad_roi_rgb, s));
         }
     }
@@ -537,7 +551,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         ep.ldc = kPosDim;
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(tb1, (int)Nb, tb2, 2 * kDim, kPosDim, (int)Nb, ep, s));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(unpack_halves(X.f32(T.g_w_loc2), g->loc_proj_w, kDim, kPosDim, s));
         RC(X.bias_grad(f32_in(d_lso), 2 * kDim, N, kDim, g->loc_proj_b));
         ActOut ot;
@@ -549,7 +563,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         e2.ldc = kPosDim;
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(d_lso, 2 * kDim, X.f32(T.loc2T), N, kPosDim, 2 * kDim, e2, s));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(pos_embed_bwd(in->boxes, N, bn_stats, *w, pos, X.f32(T.d_pos), drop_pos.scale, g->pos_w, g->pos_b, g->bn_weight, g->bn_bias, s));
         // class_projection: cso = emb W_cls2^T + b
         RC(transpose_f32(d_cso, 2 * kDim, N, 2 * kDim, false, DropSpec(), 0, o1, Nb, Nb, ActOut(), 0, s));
@@ -559,7 +573,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         e3.ldc = kEmbDim;
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(tb1, (int)Nb, tb2, 2 * kDim, kEmbDim, (int)Nb, e3, s));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(unpack_halves(X.f32(T.g_w_cls2), g->class_proj_w, kDim, kEmbDim, s));
         RC(X.bias_grad(f32_in(d_cso), 2 * kDim, N, kDim, g->class_proj_b));
         ActOut oc;
@@ -571,7 +585,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         e4.ldc = kEmbDim;
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(d_cso, 2 * kDim, X.f32(T.cls2T), N, kEmbDim, 2 * kDim, e4, s));
-        set_tag(TAG_BWD_OTHER);
+        set_tag(TAG_BWD_BOX);
         RC(embed_bwd(X.f32(T.d_emb), in->labels, in->obj_logits, cfg->num_obj, N, g->obj_embed, s));
     }
     set_tag(TAG_OTHER);

@@ -425,7 +425,7 @@ def launch_count() -> int:
 
 class StageTimer:
     """with StageTimer() as t: ...  -> t.ms[stage], t.launches[stage] (CUDA events around every library launch)."""
-    N_TAGS = 16
+    N_TAGS = 24
 
     def __enter__(self):
         L.check(L.load().veto_profile_begin(L.stream_ptr()), "veto_profile_begin")
