@@ -2,6 +2,7 @@
 // VETOPredictor.forward / Ensemble.forward (roi_relation_predictors.py:4074-4139, 3752-3853) over the
 // stage kernels.  Declarations: include/veto_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -369,15 +370,19 @@ extern "C" int veto_profile_end(double* ms_by_tag_host, int64_t* launches_by_tag
     VETO_REQUIRE(g_prof && ms_by_tag_host && launches_by_tag_host, VETO_ERR_ARG, "veto_profile_end: not profiling / NULL");
     g_prof = false;
     cudaError_t err = cudaEventSynchronize(g_prof_events.back().ev);
+    FILE* dump = nullptr;  // VETO_PROFILE_DUMP=<path>: one line per launch (index, stage tag, microseconds), for diagnosis
+    if (const char* path = getenv("VETO_PROFILE_DUMP")) dump = fopen(path, "a");
     for (size_t i = 1; i < g_prof_events.size() && err == cudaSuccess; ++i) {
         float ms = 0.f;
         err = cudaEventElapsedTime(&ms, g_prof_events[i - 1].ev, g_prof_events[i].ev);
         const int t = g_prof_events[i].tag;
+        if (dump) fprintf(dump, "%zu %s %.1f\n", i, (t >= 0 && t < VETO_PROFILE_TAGS) ? kTagNames[t] : "?", ms * 1e3f);
         if (t >= 0 && t < VETO_PROFILE_TAGS) {
             ms_by_tag_host[t] += ms;
             launches_by_tag_host[t] += 1;
         }
     }
+    if (dump) fclose(dump);
     for (auto& pe : g_prof_events) cudaEventDestroy(pe.ev);
     g_prof_events.clear();
     VETO_CUDA(err);

@@ -193,6 +193,7 @@ struct GemmOperand {
 
 // C[M,N] = epi(A[M,K] @ W[N,K]^T).  A row stride lda (elements), W row stride K.
 int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s);
+int gemm_simt_slices(int K, int split_k);  // K slices an ep.split_k request really produces (partials at out.f32 + z * split_stride)
 // passes = 1 (bf16) or 3 (bf16x3: hi*hi + lo*hi + hi*lo). Requires K % 64 == 0, N % 4 == 0, A.ld % 8 == 0.
 int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
             const GemmEpilogue& ep, cudaStream_t s);

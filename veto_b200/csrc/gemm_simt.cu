@@ -16,13 +16,17 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int N, int K,
                  const float* __restrict__ bias, const float* residual, int act, float* out_f32,
                  __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldc, int ldr, float* pre_f32, int res_mode,
-                 DropSpec drop) {
+                 DropSpec drop, int k_per, size_t split_stride) {
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // split-K (tall-skinny weight gradients): slice blockIdx.z covers K columns [k_lo, k_hi), partial tile at z * split_stride
+    const int k_lo = blockIdx.z * k_per;
+    const int k_hi = (k_lo + k_per < K) ? k_lo + k_per : K;
+    if (out_f32) out_f32 += (size_t)blockIdx.z * split_stride;
 
     // global -> register staging: each thread moves two float4 of A and two of W per K step
     const int lrow = tid >> 2;        // 0..63 (+64)
@@ -38,12 +42,12 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < M) {
                 const float* p = A + (size_t)r * lda + k;
-                if (vec_ok && k + 3 < K) v = __ldg((const float4*)p);
+                if (vec_ok && k + 3 < k_hi) v = __ldg((const float4*)p);
                 else {
-                    if (k < K) v.x = __ldg(p);
-                    if (k + 1 < K) v.y = __ldg(p + 1);
-                    if (k + 2 < K) v.z = __ldg(p + 2);
-                    if (k + 3 < K) v.w = __ldg(p + 3);
+                    if (k < k_hi) v.x = __ldg(p);
+                    if (k + 1 < k_hi) v.y = __ldg(p + 1);
+                    if (k + 2 < k_hi) v.z = __ldg(p + 2);
+                    if (k + 3 < k_hi) v.w = __ldg(p + 3);
                 }
             }
             ra[h] = v;
@@ -51,12 +55,12 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < N) {
                 const float* p = W + (size_t)c * K + k;
-                if (vec_ok && k + 3 < K) w = __ldg((const float4*)p);
+                if (vec_ok && k + 3 < k_hi) w = __ldg((const float4*)p);
                 else {
-                    if (k < K) w.x = __ldg(p);
-                    if (k + 1 < K) w.y = __ldg(p + 1);
-                    if (k + 2 < K) w.z = __ldg(p + 2);
-                    if (k + 3 < K) w.w = __ldg(p + 3);
+                    if (k < k_hi) w.x = __ldg(p);
+                    if (k + 1 < k_hi) w.y = __ldg(p + 1);
+                    if (k + 2 < k_hi) w.z = __ldg(p + 2);
+                    if (k + 3 < k_hi) w.w = __ldg(p + 3);
                 }
             }
             rb[h] = w;
@@ -79,13 +83,13 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    const int nk = (K + BK - 1) / BK;
-    load_tile(0);
+    const int nk = (k_hi - k_lo + BK - 1) / BK;
+    load_tile(k_lo);
     store_tile(0);
     __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
-        if (kt + 1 < nk) load_tile((kt + 1) * BK);
+        if (kt + 1 < nk) load_tile(k_lo + (kt + 1) * BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a0 = *(const float4*)&As[buf][k][ty * 4];
@@ -159,15 +163,31 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 
 }  // namespace
 
+int gemm_simt_slices(int K, int split_k) {
+    if (split_k <= 1) return 1;
+    const int k_per = ((K + split_k - 1) / split_k + BK - 1) / BK * BK;
+    return (K + k_per - 1) / k_per;
+}
+
 int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
     if (M <= 0 || N <= 0) return VETO_OK;
     VETO_REQUIRE(K > 0 && A && W, VETO_ERR_ARG, "gemm_simt: bad operands");
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "gemm_simt: M=%d too large for one launch", M);
-    VETO_REQUIRE(ep.split_k <= 1, VETO_ERR_ARG, "gemm_simt: no split-K");
+    int slices = ep.split_k > 1 ? ep.split_k : 1;
+    int k_per = K;
+    if (slices > 1) {
+        VETO_REQUIRE(!ep.bias && !ep.residual && ep.act == ACT_NONE && !ep.pre_f32 && !ep.drop.thr16 && ep.out.f32 && !ep.out.hi,
+                     VETO_ERR_ARG, "gemm_simt: split-K writes plain fp32 partial products only");
+        k_per = ((K + slices - 1) / slices + BK - 1) / BK * BK;  // whole K tiles per slice (keeps float4 alignment)
+        slices = (K + k_per - 1) / k_per;
+        VETO_REQUIRE(slices == gemm_simt_slices(K, ep.split_k), VETO_ERR_ARG, "gemm_simt: slice count mismatch");
+        grid.z = slices;
+    }
     VETO_REQUIRE(ep.res_mode == RES_ADD || ep.residual, VETO_ERR_ARG, "gemm_simt: RES_GELU_GRAD needs the pre-activation");
     gemm_simt_kernel<<<grid, 256, 0, s>>>(A, lda, W, M, N, K, ep.bias, ep.residual, ep.act, ep.out.f32, ep.out.hi,
-                                          ep.out.lo, ep.ldc, ep.ldr ? ep.ldr : ep.ldc, ep.pre_f32, ep.res_mode, ep.drop);
+                                          ep.out.lo, ep.ldc, ep.ldr ? ep.ldr : ep.ldc, ep.pre_f32, ep.res_mode, ep.drop, k_per,
+                                          ep.split_stride);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

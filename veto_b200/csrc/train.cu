@@ -656,13 +656,17 @@ bn_stats_kernel(const float* __restrict__ boxes, int n, float momentum, float* _
     }
 }
 
-// pos = dropout(ReLU(Linear(4,128)(BN(f)))) backward, single block of 128 threads (thread t = pos feature t):
-// d pos_w [128,4], d pos_b [128], d bn_weight [4], d bn_bias [4].  No gradient flows into the boxes.
+// pos = dropout(ReLU(Linear(4,128)(BN(f)))) backward, blocks of 128 threads (thread t = pos feature t), block b takes
+// boxes b, b + gridDim.x, ...: partial[b] = { d pos_w [128,4] | d pos_b [128] | d bn_weight [4] | d bn_bias [4] } (648
+// floats), summed over blocks by a column sum.  No gradient flows into the boxes.
 __global__ void __launch_bounds__(128)
 pos_embed_bwd_kernel(const float* __restrict__ boxes, int n, const float* __restrict__ stats, const float* __restrict__ bn_w,
                      const float* __restrict__ bn_b, const float* __restrict__ pos_w, const float* __restrict__ pos_out,
-                     const float* __restrict__ d_pos, float drop_scale, float* __restrict__ g_pos_w, float* __restrict__ g_pos_b,
-                     float* __restrict__ g_bn_w, float* __restrict__ g_bn_b) {
+                     const float* __restrict__ d_pos, float drop_scale, float* __restrict__ partial) {
+    float* g_pos_w = partial + (size_t)blockIdx.x * kPosBwdCols;
+    float* g_pos_b = g_pos_w + 4 * kPosDim;
+    float* g_bn_w = g_pos_b + kPosDim;
+    float* g_bn_b = g_bn_w + 4;
     __shared__ float red[4][4];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     float w[4], gw[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
@@ -677,7 +681,7 @@ pos_embed_bwd_kernel(const float* __restrict__ boxes, int n, const float* __rest
         bet[k] = bn_b[k];
     }
     float g_gamma = 0.f, g_beta = 0.f;  // thread k < 4 accumulates feature k
-    for (int i = 0; i < n; ++i) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const float4 bx = __ldg((const float4*)boxes + i);
         const float bw = bx.z - bx.x + 1.f, bh = bx.w - bx.y + 1.f;
         const float f[4] = {bx.x + 0.5f * bw, bx.y + 0.5f * bh, bw, bh};
@@ -931,12 +935,24 @@ int bn_batch_stats(const float* boxes, int n_boxes, float momentum, float* stats
     return VETO_OK;
 }
 
+size_t pos_embed_bwd_scratch_floats() { return (size_t)(kPosBwdBlocks + 1) * kPosBwdCols; }
+
 int pos_embed_bwd(const float* boxes, int n_boxes, const float* stats, const veto_weights& w, const float* pos_out,
-                  const float* d_pos, float drop_scale, float* g_pos_w, float* g_pos_b, float* g_bn_w, float* g_bn_b,
-                  cudaStream_t s) {
-    pos_embed_bwd_kernel<<<1, 128, 0, s>>>(boxes, n_boxes, stats, w.bn_weight, w.bn_bias, w.pos_w, pos_out, d_pos, drop_scale,
-                                           g_pos_w, g_pos_b, g_bn_w, g_bn_b);
+                  const float* d_pos, float drop_scale, float* scratch, float* colsum_scratch, float* g_pos_w, float* g_pos_b,
+                  float* g_bn_w, float* g_bn_b, cudaStream_t s) {
+    const int grid = n_boxes < kPosBwdBlocks ? (n_boxes > 0 ? n_boxes : 1) : kPosBwdBlocks;
+    pos_embed_bwd_kernel<<<grid, 128, 0, s>>>(boxes, n_boxes, stats, w.bn_weight, w.bn_bias, w.pos_w, pos_out, d_pos, drop_scale,
+                                              scratch);
     VETO_LAUNCH_CHECK();
+    float* packed = scratch + (size_t)kPosBwdBlocks * kPosBwdCols;
+    ActIn p;
+    p.f32 = scratch;
+    int rc = colsum(p, kPosBwdCols, grid, kPosBwdCols, colsum_scratch, packed, false, s);
+    if (rc) return rc;
+    VETO_CUDA(cudaMemcpyAsync(g_pos_w, packed, sizeof(float) * 4 * kPosDim, cudaMemcpyDeviceToDevice, s));
+    VETO_CUDA(cudaMemcpyAsync(g_pos_b, packed + 4 * kPosDim, sizeof(float) * kPosDim, cudaMemcpyDeviceToDevice, s));
+    VETO_CUDA(cudaMemcpyAsync(g_bn_w, packed + 5 * kPosDim, sizeof(float) * 4, cudaMemcpyDeviceToDevice, s));
+    VETO_CUDA(cudaMemcpyAsync(g_bn_b, packed + 5 * kPosDim + 4, sizeof(float) * 4, cudaMemcpyDeviceToDevice, s));
     return VETO_OK;
 }
 

@@ -48,9 +48,13 @@ int tokens_bwd(const float* dx, const int32_t* subj, const int32_t* obj, const i
 // BatchNorm1d(4) batch statistics of the box geometry: stats[0..3] mean, [4..7] biased variance; running stats updated
 int bn_batch_stats(const float* boxes, int n_boxes, float momentum, float* stats, float* running_mean, float* running_var,
                    cudaStream_t s);
+// scratch: >= pos_embed_bwd_scratch_floats(); colsum_scratch: >= colsum_scratch_floats(648)
+constexpr int kPosBwdBlocks = 64;
+constexpr int kPosBwdCols = 5 * kPosDim + 8;  // 648
+size_t pos_embed_bwd_scratch_floats();
 int pos_embed_bwd(const float* boxes, int n_boxes, const float* stats, const veto_weights& w, const float* pos_out,
-                  const float* d_pos, float drop_scale, float* g_pos_w, float* g_pos_b, float* g_bn_w, float* g_bn_b,
-                  cudaStream_t s);
+                  const float* d_pos, float drop_scale, float* scratch, float* colsum_scratch, float* g_pos_w, float* g_pos_b,
+                  float* g_bn_w, float* g_bn_b, cudaStream_t s);
 int embed_bwd(const float* d_emb, const int64_t* labels, const float* obj_logits, int num_obj, int n_boxes, float* g_embed,
               cudaStream_t s);
 int unpatchify(const float* d_patch, int n_boxes, float* d_roi, cudaStream_t s);

@@ -36,7 +36,7 @@ struct TrainLayout {
     LayerSave L[VETO_MAX_LAYERS];
     size_t logits;
     // backward temporaries
-    size_t dlogits, ce_scratch, tc1, tc2, wcT;
+    size_t dlogits, ce_scratch, tc1, tc2, wcT, wc_partial, pos_partial;
     size_t dx, tmp, a576, a1728, T1, T2, splitk, ln_partial, colsum_scratch;
     LayerWT WT[VETO_MAX_LAYERS];
     size_t d2T, v2T, loc2T, cls2T;
@@ -84,6 +84,8 @@ TrainLayout train_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs)
     T.tc1 = k.take(f * (size_t)c.num_out * T.Rp);
     T.tc2 = k.take(f * (size_t)kDim * T.Rp);
     T.wcT = k.take(f * (size_t)kDim * c.num_out);
+    T.wc_partial = k.take(f * (size_t)kMaxSplit * kDim * c.num_out);
+    T.pos_partial = k.take(f * pos_embed_bwd_scratch_floats());
     T.dx = k.take(f * M * kDim);
     T.tmp = k.take(f * M * kDim);
     T.a576 = k.take(act_bytes(prec, M * kDim));
@@ -382,11 +384,16 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         RC(transpose_f32(dlogits, C, R, C, false, DropSpec(), 0, o1, T.Rp, T.Rp, ActOut(), 0, s));
         RC(transpose_f32(x_in[NL], (int64_t)kTokens * kDim, R, kDim, false, DropSpec(), 0, o2, T.Rp, T.Rp, ActOut(), 0, s));
         RC(transpose_f32(w->rel_out_w, kDim, C, kDim, false, DropSpec(), 0, o3, C, C, ActOut(), 0, s));
+        // d W = dlogits^T x_cls: a [C, 576] output over R rows — split-K over the rows, fixed-order reduction
         GemmEpilogue ep;
-        ep.out.f32 = g->rel_out_w;
         ep.ldc = kDim;
+        const int wc_slices = gemm_simt_slices((int)T.Rp, kMaxSplit);
+        ep.out.f32 = wc_slices > 1 ? X.f32(T.wc_partial) : g->rel_out_w;
+        ep.split_k = wc_slices;
+        ep.split_stride = (size_t)C * kDim;
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(tc1, (int)T.Rp, tc2, C, kDim, (int)T.Rp, ep, s));
+        if (wc_slices > 1) RC(splitk_reduce(X.f32(T.wc_partial), wc_slices, (size_t)C * kDim, (size_t)C * kDim, g->rel_out_w, s));
         VETO_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)M * kDim, s));
         GemmEpilogue ed;
         ed.out.f32 = dx;
@@ -564,7 +571,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         set_tag(TAG_BWD_GEMM);
         RC(gemm_simt(d_lso, 2 * kDim, X.f32(T.loc2T), N, kPosDim, 2 * kDim, e2, s));
         set_tag(TAG_BWD_BOX);
-        RC(pos_embed_bwd(in->boxes, N, bn_stats, *w, pos, X.f32(T.d_pos), drop_pos.scale, g->pos_w, g->pos_b, g->bn_weight, g->bn_bias, s));
+        RC(pos_embed_bwd(in->boxes, N, bn_stats, *w, pos, X.f32(T.d_pos), drop_pos.scale, X.f32(T.pos_partial), X.colsum_scratch,
+                         g->pos_w, g->pos_b, g->bn_weight, g->bn_bias, s));
         // class_projection: cso = emb W_cls2^T + b
         RC(transpose_f32(d_cso, 2 * kDim, N, 2 * kDim, false, DropSpec(), 0, o1, Nb, Nb, ActOut(), 0, s));
         RC(transpose_f32(emb, kEmbDim, N, kEmbDim, false, DropSpec(), 0, o2, Nb, Nb, ActOut(), 0, s));

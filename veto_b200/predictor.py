@@ -164,14 +164,15 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, run, roi_rgb, roi_depth, *params):
-        loss, g_depth, g_rgb, grads = run(want_depth=ctx.needs_input_grad[3], want_rgb=ctx.needs_input_grad[2])
-        ctx.grads, ctx.g_depth, ctx.g_rgb = grads, g_depth, g_rgb
+        loss, g_depth, g_rgb, flat, grads = run(want_depth=ctx.needs_input_grad[3], want_rgb=ctx.needs_input_grad[2])
+        ctx.flat, ctx.grads, ctx.g_depth, ctx.g_rgb = flat, grads, g_depth, g_rgb
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
+        ctx.flat.mul_(gout)  # one kernel over the flat gradient buffer; `grads` are views of it
         scale = lambda t: None if t is None else t * gout
-        return (None, None, scale(ctx.g_rgb), scale(ctx.g_depth)) + tuple(scale(t) for t in ctx.grads)
+        return (None, None, scale(ctx.g_rgb), scale(ctx.g_depth)) + tuple(ctx.grads)
 
 
 def _mode(config) -> str:
@@ -239,8 +240,7 @@ class VETOPredictor(_Trunk):
                 want_roi_rgb_grad=want_rgb)
             if bn.track_running_stats:
                 bn.num_batches_tracked += 1
-            self.last_flat_grad = flat
-            return loss, g_depth, g_rgb, views
+            return loss, g_depth, g_rgb, flat, views
 
         return _TrainStep.apply(self, run, roi_features, roi_depth_features, *params)
 
