@@ -239,6 +239,16 @@ typedef struct {
     float bn_momentum;              /* 0.001 (…:4043) */
     float* bn_running_mean;         /* [4] updated in place, or NULL */
     float* bn_running_var;          /* [4] updated in place, or NULL */
+    /* MEET group heads (VETOPredictor_MEET / Ensemble in train() mode, roi_relation_predictors.py:3812-3846): with
+     * n_heads > 1 the num_out logit columns are n_heads classifiers, head k owning columns head_offsets[k] ..
+     * head_offsets[k+1]; the loss of head k is the plain mean CE over the pairs the group sampling chose for it,
+     * against group-local labels: head_labels[k*R + r] = label of pair r in head k, or -1 = pair r is not in head k's
+     * loss.  outputs.loss then holds n_heads values ('group_k_CE_loss') and the gradients are those of their SUM
+     * (what the trainer back-propagates, tools/relation_train_net.py:451-452).  rel_labels / class_weight are unused.
+     * n_heads <= 1: the single rel_out head above. */
+    int32_t n_heads;
+    const int32_t* head_offsets;    /* HOST [n_heads+1] */
+    const int64_t* head_labels;     /* device [n_heads, R] */
 } veto_train_inputs;
 
 typedef struct {
@@ -257,7 +267,7 @@ typedef struct {
 } veto_grads;   /* same field order as veto_weights */
 
 typedef struct {
-    float* loss;                    /* [1] rel_loss */
+    float* loss;                    /* [1] rel_loss ([n_heads] group losses for MEET) */
     float* rel_logits;              /* optional [R,num_out]: the training-mode logits */
     float* grad_roi_depth;          /* optional [N,256,8,8]: d loss / d roi_depth_features (flows on into the depth
                                        backbone through veto_roi_align_backward) */

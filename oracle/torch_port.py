@@ -145,3 +145,35 @@ def train_step(sd: Dict[str, torch.Tensor], boxes, pairs, rel_labels, x2d, d2d, 
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     return loss.detach(), grads, d2d.grad, x2d.grad, bn_out, logits.detach()
+
+
+def train_step_meet(sd: Dict[str, torch.Tensor], boxes, pairs, head_labels, x2d, d2d, obj_preds, drop=None,
+                    layers: int = 6):
+    """VETOPredictor_MEET / Ensemble in train() mode (roi_relation_predictors.py:3806-3848, EXPERT_GROUP False): the
+    trunk with hard class embeddings of `obj_preds`, one Linear head per group, and per head k the plain mean CE over
+    the rows with head_labels[k] >= 0 (the pairs the group sampling chose, already relabelled group-locally); gradients
+    of the SUM of the head losses by autograd.  `sd` holds the MEET state_dict keys ('model.' prefix).
+    Returns ([loss_k], {state_dict key: grad}, grad wrt d2d, grad wrt x2d, bn_out)."""
+    leaves = {}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and not any(t in k for t in TRAINED_KEYS_EXCLUDED):
+            leaves[k] = v.detach().clone().requires_grad_(True)
+    flat = {k[len("model."):]: leaves.get(k, v) for k, v in sd.items() if k.startswith("model.")}
+    n_heads = len(head_labels)
+    flat["rel_out.weight"] = torch.cat([flat[f"rel_out.{k}.weight"] for k in range(n_heads)], 0)
+    flat["rel_out.bias"] = torch.cat([flat[f"rel_out.{k}.bias"] for k in range(n_heads)], 0)
+    x2d = x2d.detach().clone().requires_grad_(True)
+    d2d = d2d.detach().clone().requires_grad_(True)
+    bn_out = {}
+    logits = predictor_forward(flat, boxes, pairs, x2d, d2d, "predcls", labels=[obj_preds], layers=layers, train=True,
+                               drop=drop, bn_out=bn_out)
+    losses, col = [], 0
+    for k in range(n_heads):
+        n = flat[f"rel_out.{k}.weight"].shape[0]
+        y = torch.as_tensor(head_labels[k]).long()
+        rows = torch.nonzero(y >= 0)[:, 0]
+        losses.append(F.cross_entropy(logits[rows, col:col + n], y[rows]))
+        col += n
+    torch.stack(losses).sum().backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return [l.detach() for l in losses], grads, d2d.grad, x2d.grad, bn_out

@@ -46,13 +46,21 @@ __device__ __forceinline__ void store_act(float* f32, __nv_bfloat16* hi, __nv_bf
 
 // ---------------------------------------------------------------- cross entropy
 // loss = sum_i w[y_i] * (logsumexp(z_i) - z_i[y_i]) / sum_i w[y_i]   (nn.CrossEntropyLoss(weight), mean reduction)
+// over the C columns [col0, col0 + C) of a logits matrix with row stride ld (one head of the MEET group classifier, or
+// the whole row for the single rel_out head); rows with a negative label are not part of this head's loss (the rows
+// MEET's group sampling left out, roi_relation_predictors.py:3842-3846): weight 0, zero gradient.
 // warp per row: row_loss[i] = w * nll, row_w[i] = w
 __global__ void __launch_bounds__(256)
-ce_rows_kernel(const float* __restrict__ logits, int C, const int64_t* __restrict__ labels, const float* __restrict__ weight,
-               int64_t rows, float* __restrict__ row_loss, float* __restrict__ row_w) {
+ce_rows_kernel(const float* __restrict__ logits, int ld, int col0, int C, const int64_t* __restrict__ labels,
+               const float* __restrict__ weight, int64_t rows, float* __restrict__ row_loss, float* __restrict__ row_w) {
     const int lane = threadIdx.x & 31;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
-        const float* z = logits + r * C;
+        const int64_t y = labels[r];
+        if (y < 0) {
+            if (lane == 0) { row_loss[r] = 0.f; row_w[r] = 0.f; }
+            continue;
+        }
+        const float* z = logits + r * ld + col0;
         float m = -INFINITY;
         for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
         m = warp_max(m);
@@ -60,7 +68,6 @@ ce_rows_kernel(const float* __restrict__ logits, int C, const int64_t* __restric
         for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
         s = warp_sum(s);
         if (lane == 0) {
-            const int64_t y = labels[r];
             const float w = weight ? weight[y] : 1.f;
             row_loss[r] = w * (logf(s) + m - z[y]);
             row_w[r] = w;
@@ -68,6 +75,7 @@ ce_rows_kernel(const float* __restrict__ logits, int C, const int64_t* __restric
     }
 }
 // single block: fixed-order tree sums of row_loss and row_w -> out[0] = loss, out[1] = 1 / sum(w)
+// (no row in the head: loss = NaN like torch's mean over an empty selection, and a zero gradient scale)
 __global__ void __launch_bounds__(1024)
 ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_w, int64_t rows, float* __restrict__ loss_out,
                    float* __restrict__ inv_w_out) {
@@ -89,27 +97,32 @@ ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__
     }
     if (threadIdx.x == 0) {
         *loss_out = (float)(sl[0] / sw[0]);
-        *inv_w_out = (float)(1.0 / sw[0]);
+        *inv_w_out = sw[0] != 0.0 ? (float)(1.0 / sw[0]) : 0.f;
     }
 }
-// dlogits[i, c] = w[y_i] * (softmax(z_i)[c] - [c == y_i]) / sum(w)
+// dlogits[i, col0 + c] = w[y_i] * (softmax(z_i)[c] - [c == y_i]) / sum(w)
 __global__ void __launch_bounds__(256)
-ce_grad_kernel(const float* __restrict__ logits, int C, const int64_t* __restrict__ labels, const float* __restrict__ weight,
-               const float* __restrict__ inv_w, int64_t rows, float* __restrict__ dlogits) {
+ce_grad_kernel(const float* __restrict__ logits, int ld, int col0, int C, const int64_t* __restrict__ labels,
+               const float* __restrict__ weight, const float* __restrict__ inv_w, int64_t rows, float* __restrict__ dlogits) {
     const int lane = threadIdx.x & 31;
     const float iw = *inv_w;
     for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
-        const float* z = logits + r * C;
+        const int64_t y = labels[r];
+        float* d = dlogits + r * ld + col0;
+        if (y < 0) {
+            for (int c = lane; c < C; c += 32) d[c] = 0.f;
+            continue;
+        }
+        const float* z = logits + r * ld + col0;
         float m = -INFINITY;
         for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
         m = warp_max(m);
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
         s = warp_sum(s);
-        const int64_t y = labels[r];
         const float w = (weight ? weight[y] : 1.f) * iw;
         const float inv = 1.f / s;
-        for (int c = lane; c < C; c += 32) dlogits[r * C + c] = w * (expf(z[c] - m) * inv - (c == y ? 1.f : 0.f));
+        for (int c = lane; c < C; c += 32) d[c] = w * (expf(z[c] - m) * inv - (c == y ? 1.f : 0.f));
     }
 }
 
@@ -804,18 +817,18 @@ copy_rows_kernel(const float* __restrict__ src, int64_t ld_src, float* __restric
 }  // namespace
 
 // ================================================================ host wrappers
-int ce_loss_grad(const float* logits, int C, const int64_t* labels, const float* weight, int64_t rows, float* row_scratch,
-                 float* loss_out, float* dlogits, cudaStream_t s) {
+int ce_loss_grad(const float* logits, int ld, int col0, int C, const int64_t* labels, const float* weight, int64_t rows,
+                 float* row_scratch, float* loss_out, float* dlogits, cudaStream_t s) {
     if (rows <= 0) return VETO_OK;
     float* row_loss = row_scratch;
     float* row_w = row_scratch + rows;
     float* inv_w = row_scratch + 2 * rows;
     const int grid = grid_cap((size_t)(rows + 7) / 8, 8);
-    ce_rows_kernel<<<grid, 256, 0, s>>>(logits, C, labels, weight, rows, row_loss, row_w);
+    ce_rows_kernel<<<grid, 256, 0, s>>>(logits, ld, col0, C, labels, weight, rows, row_loss, row_w);
     VETO_LAUNCH_CHECK();
     ce_finalize_kernel<<<1, 1024, 0, s>>>(row_loss, row_w, rows, loss_out, inv_w);
     VETO_LAUNCH_CHECK();
-    ce_grad_kernel<<<grid, 256, 0, s>>>(logits, C, labels, weight, inv_w, rows, dlogits);
+    ce_grad_kernel<<<grid, 256, 0, s>>>(logits, ld, col0, C, labels, weight, inv_w, rows, dlogits);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -14,9 +14,10 @@ struct ActIn {
 constexpr int kColsumMaxChunks = 256;
 
 // nn.CrossEntropyLoss(weight) with mean reduction (roi_relation_predictors.py:4070,4134-4135): scalar loss and
-// d loss / d logits.  row_scratch: >= 2*rows + 1 floats.
-int ce_loss_grad(const float* logits, int C, const int64_t* labels, const float* weight, int64_t rows, float* row_scratch,
-                 float* loss_out, float* dlogits, cudaStream_t s);
+// d loss / d logits, over columns [col0, col0 + C) of a matrix with row stride ld; rows whose label is negative are
+// outside the loss (zero gradient).  row_scratch: >= 2*rows + 1 floats.
+int ce_loss_grad(const float* logits, int ld, int col0, int C, const int64_t* labels, const float* weight, int64_t rows,
+                 float* row_scratch, float* loss_out, float* dlogits, cudaStream_t s);
 // out[c] (+)= sum_r src[r, c]; deterministic two-stage sum.  scratch: >= colsum_scratch_floats(cols)
 size_t colsum_scratch_floats(int cols);
 int colsum(const ActIn& src, int64_t ld, int64_t rows, int cols, float* scratch, float* out, bool accumulate, cudaStream_t s);

@@ -233,7 +233,15 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     VETO_REQUIRE(in->boxes && in->roi_rgb && in->roi_depth && in->subj && in->obj && (in->labels || in->obj_logits),
                  VETO_ERR_ARG, "veto_relation_train_step: missing input pointer");
     VETO_REQUIRE(!in->freq_bias, VETO_ERR_UNSUPPORTED, "the frequency-bias epilogue has no training branch (VETO never uses it)");
-    VETO_REQUIRE(tin->rel_labels && tin->rel_offsets && tin->box_offsets && tin->n_images > 0, VETO_ERR_ARG,
+    if (tin->n_heads > 1) {
+        VETO_REQUIRE(tin->head_offsets && tin->head_labels && !tin->class_weight, VETO_ERR_ARG,
+                     "veto_relation_train_step: group heads need head_offsets and head_labels (and take no class weight)");
+        VETO_REQUIRE(tin->head_offsets[0] == 0 && tin->head_offsets[tin->n_heads] == cfg->num_out, VETO_ERR_ARG,
+                     "veto_relation_train_step: head_offsets must cover the num_out logit columns");
+        for (int k = 0; k < tin->n_heads; ++k)
+            VETO_REQUIRE(tin->head_offsets[k + 1] > tin->head_offsets[k], VETO_ERR_ARG, "veto_relation_train_step: empty head %d", k);
+    }
+    VETO_REQUIRE((tin->rel_labels || tin->n_heads > 1) && tin->rel_offsets && tin->box_offsets && tin->n_images > 0, VETO_ERR_ARG,
                  "veto_relation_train_step: rel_labels / rel_offsets / box_offsets missing");
     VETO_REQUIRE(out->loss, VETO_ERR_ARG, "veto_relation_train_step: loss output missing");
     VETO_REQUIRE(tin->p_pos_dropout >= 0.f && tin->p_pos_dropout < 1.f && tin->p_emb_dropout >= 0.f && tin->p_emb_dropout < 1.f &&
@@ -369,7 +377,17 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     // =====================================================================================  loss and backward
     set_tag(TAG_LOSS);
     float* dlogits = X.f32(T.dlogits);
-    RC(ce_loss_grad(logits, C, tin->rel_labels, tin->class_weight, R, X.f32(T.ce_scratch), out->loss, dlogits, s));
+    if (tin->n_heads > 1) {
+        // MEET group heads (roi_relation_predictors.py:3834-3846): one unweighted CE per head over its own columns and the
+        // rows the group sampling chose for it; the step's gradient is that of the SUM of the head losses
+        for (int k = 0; k < tin->n_heads; ++k) {
+            const int c0 = tin->head_offsets[k], ck = tin->head_offsets[k + 1] - c0;
+            RC(ce_loss_grad(logits, C, c0, ck, tin->head_labels + (size_t)k * R, nullptr, R, X.f32(T.ce_scratch), out->loss + k,
+                            dlogits, s));
+        }
+    } else {
+        RC(ce_loss_grad(logits, C, 0, C, tin->rel_labels, tin->class_weight, R, X.f32(T.ce_scratch), out->loss, dlogits, s));
+    }
     float* dx = X.f32(T.dx);
     float* tmp = X.f32(T.tmp);
     set_tag(TAG_BWD_OTHER);

@@ -49,7 +49,8 @@ class VetoTrainInputs(Structure):
     _fields_ = [("rel_labels", c_void_p), ("class_weight", c_void_p), ("rel_offsets", c_void_p),
                 ("box_offsets", c_void_p), ("n_images", c_int32), ("p_pos_dropout", c_float),
                 ("p_emb_dropout", c_float), ("p_attn_dropout", c_float), ("seed", ctypes.c_uint64),
-                ("bn_momentum", c_float), ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p)]
+                ("bn_momentum", c_float), ("bn_running_mean", c_void_p), ("bn_running_var", c_void_p),
+                ("n_heads", c_int32), ("head_offsets", c_void_p), ("head_labels", c_void_p)]
 
 
 class VetoGrads(VetoWeights):

@@ -3,6 +3,7 @@ work is done by libveto_b200.so on the current stream.  No CPU fallback."""
 from __future__ import annotations
 
 import ctypes
+import itertools
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -306,11 +307,16 @@ def relation_train_step(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.T
                         p_pos: float = 0.1, p_emb: float = 0.35, p_attn: float = 0.35, seed: int = 0,
                         bn_momentum: float = 0.001, bn_running_mean: Optional[torch.Tensor] = None,
                         bn_running_var: Optional[torch.Tensor] = None, want_roi_depth_grad: bool = True,
-                        want_roi_rgb_grad: bool = False, return_logits: bool = False):
+                        want_roi_rgb_grad: bool = False, return_logits: bool = False,
+                        head_sizes: Optional[Sequence[int]] = None, head_labels: Optional[torch.Tensor] = None):
     """veto_relation_train_step: rel_loss of VETOPredictor.forward in train() mode and its gradients.
 
     `grads` maps the trunk's state_dict keys (grad_fields) to fp32 CUDA tensors of the parameter shapes; they are
-    OVERWRITTEN.  Returns (loss [1], grad_roi_depth or None, grad_roi_rgb or None, logits or None)."""
+    OVERWRITTEN.  Returns (loss [1], grad_roi_depth or None, grad_roi_rgb or None, logits or None).
+
+    MEET group heads: `head_sizes` = the n_k + 2 columns of each head (their sum = cfg.num_out) and `head_labels`
+    int64 [n_heads, R] (group-local label, -1 = pair not sampled into that head's loss); loss is then [n_heads] and
+    the gradients are those of the sum of the head losses; `rel_labels` / `class_weight` are ignored."""
     global last_launch_count
     lib = L.load()
     cfg = pw.cfg
@@ -321,6 +327,14 @@ def relation_train_step(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.T
         raise RuntimeError("a training step needs at least one box and one pair")
     if tuple(roi_rgb.shape) != (N, 256, 8, 8) or tuple(roi_depth.shape) != (N, 256, 8, 8):
         raise RuntimeError(f"roi features must be [{N},256,8,8], got {tuple(roi_rgb.shape)} / {tuple(roi_depth.shape)}")
+    n_heads = len(head_sizes) if head_sizes is not None else 0
+    if n_heads > 1:
+        if sum(head_sizes) != cfg.num_out or head_labels is None or tuple(head_labels.shape) != (n_heads, R):
+            raise RuntimeError("head_sizes must sum to num_out and head_labels must be [n_heads, R]")
+        head_labels = head_labels.to(device=dev, dtype=torch.int64).contiguous()
+        head_off = (ctypes.c_int32 * (n_heads + 1))(*([0] + list(itertools.accumulate(int(n) for n in head_sizes))))
+        rel_labels = head_labels[0]
+        class_weight = None
     if sum(rel_counts) != R or sum(n_boxes) != N or rel_labels.shape[0] != R:
         raise RuntimeError("rel_counts / n_boxes / rel_labels do not match the pair and box tensors")
     subj = subj.to(torch.int32).contiguous()
@@ -344,7 +358,7 @@ def relation_train_step(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.T
         else:
             getattr(g, field)[layer] = t.data_ptr()
     g.rel_out_w, g.rel_out_b = rel_out_w_grad.data_ptr(), rel_out_b_grad.data_ptr()
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    loss = torch.empty(max(1, n_heads), dtype=torch.float32, device=dev)
     logits = torch.empty((R, cfg.num_out), dtype=torch.float32, device=dev) if return_logits else None
     g_depth = torch.empty_like(roi_depth) if want_roi_depth_grad else None
     g_rgb = torch.empty_like(roi_rgb) if want_roi_rgb_grad else None
@@ -354,7 +368,10 @@ def relation_train_step(pw: PackedWeights, boxes: torch.Tensor, roi_rgb: torch.T
                        roi_depth.data_ptr(), subj.data_ptr(), obj.data_ptr(), None)
     tin = L.VetoTrainInputs(rel_labels.data_ptr(), L.ptr(class_weight), rel_off.data_ptr(), box_off.data_ptr(),
                             len(rel_counts), float(p_pos), float(p_emb), float(p_attn), int(seed) & (2 ** 64 - 1),
-                            float(bn_momentum), L.ptr(bn_running_mean), L.ptr(bn_running_var))
+                            float(bn_momentum), L.ptr(bn_running_mean), L.ptr(bn_running_var),
+                            n_heads if n_heads > 1 else 0,
+                            ctypes.cast(head_off, ctypes.c_void_p) if n_heads > 1 else None,
+                            head_labels.data_ptr() if n_heads > 1 else None)
     tout = L.VetoTrainOutputs(loss.data_ptr(), L.ptr(logits), L.ptr(g_depth), L.ptr(g_rgb))
     with torch.cuda.device(dev):
         L.check(lib.veto_relation_train_step(ctypes.byref(cfg), ctypes.byref(pw.struct), pw.packed.data_ptr(),

@@ -12,7 +12,8 @@ CPU fallback: without the library or an sm_100 device, forward raises.
 (roi_relation_predictors.py:4131-4136) as a scalar wired into autograd: ``veto_relation_train_step`` computes the
 loss AND every gradient in one library call, and ``loss.backward()`` hands those gradients to the parameters and
 to ``roi_depth_features`` (so the depth backbone trains through VETOFeatureExtractor's ROIAlign backward).
-The MEET training branch (group sampling, per-group losses) is not built yet and raises NotImplementedError.
+VETOPredictor_MEET in ``train()`` mode samples the pairs of every group head on the host (meet_sampling.py, the
+reference's ``random`` stream) and returns one 'group_k_CE_loss' per head from the same library call.
 """
 from __future__ import annotations
 
@@ -23,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import config as C
-from . import ops
+from . import meet_sampling, ops
 from .registry import ROI_RELATION_PREDICTOR
 from .structures import xyxy_boxes
 
@@ -158,18 +159,90 @@ class _Trunk(nn.Module):
                                     obj_logits=obj_logits, freq_bias=freq_bias, chunk_pairs=self.chunk_pairs)
 
 
+    # ---- training branch (roi_relation_predictors.py:4131-4136 / 3812-3846) ----
+    def _trained_params(self):
+        """(state_dict key, parameter) of everything the losses depend on, in the order of ops.grad_fields."""
+        named = dict(self.named_parameters())
+        return [(key, named[key]) for _, _, key in ops.grad_fields(self.n_layers)]
+
+    def _train_forward(self, proposals, rel_pair_idxs, roi_features, roi_depth_features, hard, soft, heads,
+                       rel_labels=None, class_weight=None, head_labels=None):
+        """One veto_relation_train_step wired into autograd.  `heads`: the classifier Linear modules whose rows,
+        concatenated, are the library's rel_out ([rel_out] for VETOPredictor, the group heads for MEET); with more
+        than one head `head_labels` [n_heads, R] (-1 = pair not in that head's loss) replaces `rel_labels` and the
+        result is the vector of head losses."""
+        n_boxes = [len(p) for p in proposals]
+        rel_counts = [int(r.shape[0]) for r in rel_pair_idxs]
+        boxes = torch.cat([xyxy_boxes(p) for p in proposals], 0)
+        subj, obj = ops.globalize_pairs(rel_pair_idxs, n_boxes)
+        keyed = self._trained_params()
+        head_sizes = [int(m.weight.shape[0]) for m in heads]
+        n_out = sum(head_sizes)
+        params = [p for _, p in keyed] + [m.weight for m in heads] + [m.bias for m in heads]
+        tr = self.fusion_transformer.transformer
+        p_attn = {float(layer[0].fn.to_out[1].p) for layer in tr.layers}
+        if len(p_attn) != 1:
+            raise RuntimeError("veto_b200: every Attention.to_out Dropout must use the same p")
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: follows torch.manual_seed, no device sync
+        bn = self.pos_embed[0]
+        dim = heads[0].weight.shape[1]
+
+        def run(want_depth, want_rgb):
+            if len(heads) == 1:
+                rel_w, rel_b = heads[0].weight, heads[0].bias
+            else:
+                rel_w = torch.cat([m.weight.detach() for m in heads], 0)
+                rel_b = torch.cat([m.bias.detach() for m in heads], 0)
+            pw = self._pack(rel_w, rel_b)
+            n_trunk = sum(p.numel() for _, p in keyed)
+            flat = torch.empty(n_trunk + n_out * dim + n_out, dtype=torch.float32, device=boxes.device)
+            views, off = [], 0
+            for _, p in keyed:
+                views.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            g_w = flat[off:off + n_out * dim].view(n_out, dim)    # gradient of the concatenated classifier
+            g_b = flat[off + n_out * dim:]
+            row = 0
+            for n in head_sizes:                                   # a head's rows are a contiguous slice of it
+                views.append(g_w[row:row + n])
+                row += n
+            row = 0
+            for n in head_sizes:
+                views.append(g_b[row:row + n])
+                row += n
+            grads = {key: v for (key, _), v in zip(keyed, views)}
+            loss, g_depth, g_rgb, _ = ops.relation_train_step(
+                pw, boxes, roi_features.detach(), roi_depth_features.detach(), subj, obj, rel_labels, rel_counts, n_boxes,
+                grads, g_w, g_b, labels=hard, obj_logits=soft, class_weight=class_weight,
+                p_pos=float(self.pos_embed[3].p), p_emb=float(tr.pos_drop.p), p_attn=next(iter(p_attn)), seed=seed,
+                bn_momentum=float(bn.momentum), bn_running_mean=bn.running_mean if bn.track_running_stats else None,
+                bn_running_var=bn.running_var if bn.track_running_stats else None, want_roi_depth_grad=want_depth,
+                want_roi_rgb_grad=want_rgb, head_sizes=head_sizes if len(heads) > 1 else None, head_labels=head_labels)
+            if bn.track_running_stats:
+                bn.num_batches_tracked += 1
+            return loss, g_depth, g_rgb, flat, views
+
+        return _TrainStep.apply(self, run, roi_features, roi_depth_features, *params)
+
+
 class _TrainStep(torch.autograd.Function):
-    """rel_loss with all of its gradients computed eagerly by veto_relation_train_step; backward() only scales them
-    by the incoming gradient and hands them to autograd (parameters are inputs, so DDP / optimizers see .grad)."""
+    """The training losses with all of their gradients computed eagerly by veto_relation_train_step; backward() only
+    scales them by the incoming gradient and hands them to autograd (parameters are inputs, so DDP / optimizers see
+    .grad).  Vanilla: one scalar rel_loss.  MEET: a vector of group losses whose gradients the library computed for
+    their SUM — what the reference's trainer back-propagates (tools/relation_train_net.py:451: losses = sum(...));
+    unequal incoming weights cannot be honoured and poison the gradients with NaN instead of being silently wrong."""
 
     @staticmethod
     def forward(ctx, module, run, roi_rgb, roi_depth, *params):
         loss, g_depth, g_rgb, flat, grads = run(want_depth=ctx.needs_input_grad[3], want_rgb=ctx.needs_input_grad[2])
         ctx.flat, ctx.grads, ctx.g_depth, ctx.g_rgb = flat, grads, g_depth, g_rgb
-        return loss.reshape(())
+        return loss.reshape(()) if loss.numel() == 1 else loss
 
     @staticmethod
     def backward(ctx, gout):
+        if gout.dim():
+            uniform = (gout == gout[0]).all()
+            gout = torch.where(uniform, gout[0], torch.full_like(gout[0], float("nan")))
         ctx.flat.mul_(gout)  # one kernel over the flat gradient buffer; `grads` are views of it
         scale = lambda t: None if t is None else t * gout
         return (None, None, scale(ctx.g_rgb), scale(ctx.g_depth)) + tuple(ctx.grads)
@@ -202,48 +275,6 @@ class VETOPredictor(_Trunk):
         self.use_freq_bias = bool(C.get(config, "VETO_B200.FREQ_BIAS", False))
         self.freq_bias_table = None  # [num_obj^2, num_rel] fp32, set by the caller when use_freq_bias
 
-    # ---- training branch (roi_relation_predictors.py:4131-4136) ----
-    def _trained_params(self):
-        """(state_dict key, parameter) of everything rel_loss depends on, in the order of ops.grad_fields."""
-        named = dict(self.named_parameters())
-        return [(key, named[key]) for _, _, key in ops.grad_fields(self.n_layers)]
-
-    def _train_forward(self, proposals, rel_pair_idxs, rel_labels, roi_features, roi_depth_features, hard, soft):
-        n_boxes = [len(p) for p in proposals]
-        rel_counts = [int(r.shape[0]) for r in rel_pair_idxs]
-        boxes = torch.cat([xyxy_boxes(p) for p in proposals], 0)
-        subj, obj = ops.globalize_pairs(rel_pair_idxs, n_boxes)
-        labels_cat = torch.cat(list(rel_labels), 0).long()
-        keyed = self._trained_params()
-        params = [p for _, p in keyed] + [self.rel_out.weight, self.rel_out.bias]
-        tr = self.fusion_transformer.transformer
-        p_attn = {float(layer[0].fn.to_out[1].p) for layer in tr.layers}
-        if len(p_attn) != 1:
-            raise RuntimeError("veto_b200: every Attention.to_out Dropout must use the same p")
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # CPU generator: follows torch.manual_seed, no device sync
-        bn = self.pos_embed[0]
-
-        def run(want_depth, want_rgb):
-            pw = self._pack(self.rel_out.weight, self.rel_out.bias)
-            flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=boxes.device)
-            views, off = [], 0
-            for p in params:
-                views.append(flat[off:off + p.numel()].view(p.shape))
-                off += p.numel()
-            grads = {key: v for (key, _), v in zip(keyed, views)}
-            loss, g_depth, g_rgb, _ = ops.relation_train_step(
-                pw, boxes, roi_features.detach(), roi_depth_features.detach(), subj, obj, labels_cat, rel_counts, n_boxes,
-                grads, views[-2], views[-1], labels=hard, obj_logits=soft, class_weight=self.criterion_loss_rel.weight,
-                p_pos=float(self.pos_embed[3].p), p_emb=float(tr.pos_drop.p), p_attn=p_attn.pop(), seed=seed,
-                bn_momentum=float(bn.momentum), bn_running_mean=bn.running_mean if bn.track_running_stats else None,
-                bn_running_var=bn.running_var if bn.track_running_stats else None, want_roi_depth_grad=want_depth,
-                want_roi_rgb_grad=want_rgb)
-            if bn.track_running_stats:
-                bn.num_batches_tracked += 1
-            return loss, g_depth, g_rgb, flat, views
-
-        return _TrainStep.apply(self, run, roi_features, roi_depth_features, *params)
-
     def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
                 rel_binarys=None):
         if self.training:
@@ -256,8 +287,9 @@ class VETOPredictor(_Trunk):
                 pred = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
                 fg = torch.cat([p.get_field("labels") for p in proposals], 0).long()
                 add_losses["obj_loss"] = self.criterion_loss(nn.functional.one_hot(pred, self.num_obj_cls).float(), fg)
-            add_losses["rel_loss"] = self._train_forward(proposals, rel_pair_idxs, rel_labels, roi_features,
-                                                         roi_depth_features, hard, soft)
+            add_losses["rel_loss"] = self._train_forward(
+                proposals, rel_pair_idxs, roi_features, roi_depth_features, hard, soft, [self.rel_out],
+                rel_labels=torch.cat(list(rel_labels), 0).long(), class_weight=self.criterion_loss_rel.weight)
             return None, None, add_losses, None, None, None
         if self.mode == "predcls":
             obj_labels = torch.cat([p.get_field("labels") for p in proposals], 0).long()
@@ -319,24 +351,52 @@ class Ensemble(_Trunk):
         self.criterion_loss = nn.CrossEntropyLoss()
         self.nms_thresh = config.TEST.RELATION.LATER_NMS_PREDICTION_THRES
 
+    def _forward_train(self, proposals, rel_pair_idxs, rel_labels, roi_features, roi_depth_features, obj_preds,
+                       cur_chosen_matrix):
+        """roi_relation_predictors.py:3806-3848 in train() mode: per-group relabelling of the sampled pairs and one
+        CE per head ('group_k_CE_loss'; with EXPERT_GROUP every expert j of group k sees group k's pairs, :3834-3840).
+        `rel_labels` is the concatenated label tensor, `cur_chosen_matrix` = expert_dist of VETOPredictor_MEET."""
+        if cur_chosen_matrix is None:
+            raise RuntimeError("Ensemble in train() mode needs cur_chosen_matrix (VETOPredictor_MEET.forward builds it)")
+        labels_host = rel_labels if isinstance(rel_labels, (list, tuple)) else rel_labels.tolist()
+        table = meet_sampling.group_local_labels(labels_host, cur_chosen_matrix[0], self.incre_idx_list)   # [G, R]
+        heads = self._head_sets()
+        # group index of every head, in _head_sets order (expert-major)
+        per_head = [k for _ in range(self.experts_per_group if self.expert_group else 1) for k in range(self.group_num)]
+        dev = roi_features.device
+        head_labels = torch.from_numpy(table[per_head]).to(dev, non_blocking=True)
+        add_losses = {}
+        if self.mode != "predcls":  # :3826-3830: CE of the detached detector logits, a constant of the step
+            obj_logits = torch.cat([p.get_field("predict_logits") for p in proposals], 0).detach()
+            fg = torch.cat([p.get_field("labels") for p in proposals], 0).long()
+            add_losses["obj_loss"] = self.criterion_loss(obj_logits, fg)
+        losses = self._train_forward(proposals, rel_pair_idxs, roi_features, roi_depth_features, obj_preds, None,
+                                     [m for _, m in heads], head_labels=head_labels)
+        for i, (name, _) in enumerate(heads):
+            add_losses[name + "_CE_loss"] = losses[i]
+        return None, None, add_losses, None
+
     def _head_sets(self):
         if self.expert_group:
             return [(f"group_%d%d" % (k, j + 1), self.rel_out_group[j][k]) for j in range(self.experts_per_group)
                     for k in range(self.group_num)]
         return [("group_%d" % k, self.rel_out[k]) for k in range(self.group_num)]
 
-    def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None):
-        if self.training:
-            raise NotImplementedError("veto_b200 Ensemble: the training branch is not built yet (eval() only)")
+    def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
+                cur_chosen_matrix=None):
+        soft = None
         if self.mode == "predcls":
             obj_preds = torch.cat([p.get_field("labels") for p in proposals], 0).long()
             obj_dists = nn.functional.one_hot(obj_preds, self.num_obj_cls).float()
         else:
             obj_labels = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
             obj_dists = nn.functional.one_hot(obj_labels, self.num_obj_cls).float()
-            if self.mode == "sgdet":
+            if self.mode == "sgdet" and not self.training:
                 raise NotImplementedError("MEET sgdet test uses nms_per_cls (:3855-3874): not built yet")
             obj_preds = obj_dists[:, 1:].max(1)[1] + 1  # :3783
+        if self.training:
+            return self._forward_train(proposals, rel_pair_idxs, rel_labels, roi_features, roi_depth_features,
+                                       obj_preds, cur_chosen_matrix)
         heads = self._head_sets()
         # all expert heads as ONE [sum(n_k+2), 576] classifier GEMM, split afterwards
         w = torch.cat([m.weight for _, m in heads], 0)
@@ -373,13 +433,22 @@ class VETOPredictor_MEET(nn.Module):
         self.num_groups = len(self.max_group_element_number_list)
         self.experts_per_group = 3 if config.ENSEMBLE_LEARNING.EXPERT_GROUP else 1
         self.ensemble_type = config.ENSEMBLE_LEARNING.TYPE
+        self.zero_label_padding_mode = config.GCL_SETTING.ZERO_LABEL_PADDING_MODE
+        self.sample_rate_matrix = meet_sampling.sample_rate_matrix(ds, self.max_group_element_number_list)
         self.model = Ensemble(config, self.mode, self.params, self.num_groups, self.experts_per_group,
                               self.max_group_element_number_list, self.incre_idx_list)
 
     def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
                 rel_binarys=None):
         if self.training:
-            raise NotImplementedError("veto_b200.VETOPredictor_MEET: the training branch is not built yet")
+            # :3926-3969 — the reference walks the pairs with one .item() sync each; here the labels cross once
+            labels_host = torch.cat(list(rel_labels), 0).tolist()
+            chosen = meet_sampling.group_sampling(labels_host, self.incre_idx_list, self.sample_rate_matrix,
+                                                  self.num_groups, self.zero_label_padding_mode)
+            expert_dist = [chosen] * len(labels_host)   # the reference appends the same list once per pair (:3969)
+            _, _, add_losses, _ = self.model(proposals, rel_pair_idxs, labels_host, logger, roi_features=roi_features,
+                                             roi_depth_features=roi_depth_features, cur_chosen_matrix=expert_dist)
+            return None, None, dict(add_losses), self.incre_idx_list, expert_dist, None
         obj_dists, rel_dists, add_losses, _ = self.model(proposals, rel_pair_idxs, rel_labels, logger,
                                                          roi_features=roi_features,
                                                          roi_depth_features=roi_depth_features)
