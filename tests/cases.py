@@ -48,6 +48,14 @@ TRAIN_CASES = {
                         class_weight_seed=72),
 }
 
+# MEET training fixtures (run_meet_train_case): VETOPredictor_MEET in train() mode, dropout p = 0, `random` seeded with
+# sample_seed right before the forward so that the group sampling (roi_relation_predictors.py:3940-3969) is reproducible.
+MEET_TRAIN_CASES = {
+    "train_meet_vg": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", n_boxes=[6, 4, 5],
+                          batch_seed=9, weight_seed=18, spread=True, H=320, W=416, label_seed=73, fg_per_image=10,
+                          sample_seed=123),
+}
+
 
 def case_rel_labels(c, pair_counts):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA

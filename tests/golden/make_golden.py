@@ -161,8 +161,109 @@ def run_train_case(ns, name, c):
           f"no_grad={no_grad}")
 
 
+def run_meet_train_case(ns, name, c):
+    """One training step of the UNMODIFIED reference VETOPredictor_MEET (train() mode, dropout p = 0, EXPERT_GROUP
+    False): the group sampling under random.seed(sample_seed), the per-group CE losses, and the gradients of their sum
+    (what tools/relation_train_net.py:451 back-propagates)."""
+    import random
+    import torch
+    from tests.cases import case_rel_labels
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    ds = synth.VG if c["dataset"] == "VG" else synth.GQA
+    cfg = ref_shim.make_cfg(ns, predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"])
+    sd = case_state(c)
+    pred = ref_shim.build_predictor(ns, cfg, ds["num_obj"], ds["num_rel"], synth.to_torch_state(sd)).train()
+    for m in pred.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    batch = case_batch(c)
+    bls = ref_shim.make_boxlists(ns, batch, ds["num_obj"])
+    fe = ns.make_extractor(cfg, 256, for_relation=True).train()
+    samp = ns.make_sampler(cfg)
+    pairs = samp.prepare_test_pairs(torch.device("cpu"), bls)
+    rel_labels = [torch.from_numpy(l) for l in case_rel_labels(c, [len(p) for p in pairs])]
+    feats = [torch.from_numpy(f) for f in batch["feats"]]
+    feats.append(torch.zeros(batch["B"], 256, 1, 1))
+    depth = torch.from_numpy(batch["depth"]).clone().requires_grad_(True)
+    x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+    d2d.retain_grad()
+    random.seed(c["sample_seed"])
+    obj_d, rel_d, losses, incre, chosen, custom = pred(bls, pairs, rel_labels, None, roi_features=x2d,
+                                                       roi_depth_features=d2d)
+    assert obj_d is None and rel_d is None and custom is None
+    sum(losses.values()).backward()
+    out = {"input_digest": np.array(digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"])),
+           "weight_digest": np.array(digest([sd[k] for k in sorted(sd)])),
+           "rel_labels": np.concatenate([l.numpy() for l in rel_labels]),
+           "pair_counts": np.array([len(p) for p in pairs]),
+           "incre_idx_list": np.array(incre),
+           "loss_names": np.array(sorted(losses)),
+           "losses": np.array([losses[k].item() for k in sorted(losses)], np.float64),
+           "expert_dist_len": np.array(len(chosen))}
+    for k, rows in enumerate(chosen[0]):
+        out[f"chosen/{k}"] = np.array(rows, dtype=np.int64)
+    no_grad = []
+    for k, p in pred.named_parameters():
+        if p.grad is None:
+            no_grad.append(k)
+            continue
+        stat, idx, val = grad_summary(p.grad.numpy())
+        out["gstat/" + k], out["gidx/" + k], out["gval/" + k] = stat, idx, val
+    out["no_grad"] = np.array(sorted(no_grad))
+    stat, idx, val = grad_summary(d2d.grad.numpy())
+    out["gstat/roi_depth"], out["gidx/roi_depth"], out["gval/roi_depth"] = stat, idx, val
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KB) losses={dict(zip(out['loss_names'], out['losses']))} "
+          f"chosen sizes={[len(r) for r in chosen[0]]} no_grad={no_grad}")
+
+
+def run_sample_rates():
+    """generate_sample_rate_vector_sep2 / get_current_predicate_idx of the reference for every (dataset, split) the
+    drop-in knows, and its group sampling on seeded label vectors (the loop of VETOPredictor_MEET.forward :3940-3969
+    needs a predictor instance, so the sampled rows are taken from run_meet_train_case instead)."""
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    from SHA_GCL_extra.extra_function_utils import (generate_num_stage_vector, generate_sample_rate_vector_sep2,
+                                                    get_current_predicate_idx)
+    from SHA_GCL_extra.group_chosen_function import get_group_splits
+    from veto_b200 import config as vcfg
+    out = {}
+    for (ds, split), sizes in vcfg.GROUP_SPLITS.items():
+        try:
+            stage_list, stage_count = get_group_splits(ds, split)
+        except (AssertionError, SystemExit):
+            continue
+        if stage_list is None:
+            continue
+        assert list(stage_count) == list(sizes), (ds, split)
+        out[f"rates/{ds}/{split}"] = np.array(generate_sample_rate_vector_sep2(ds, generate_num_stage_vector(stage_list)))
+        out[f"incre/{ds}/{split}"] = np.array(get_current_predicate_idx(stage_list, 0.1, ds)[0])
+    # GLOBAL_SETTING.BETA_LOSS: the reference reads a hard-coded absolute path (roi_relation_predictors.py:4059) and
+    # calls .cuda(); redirect that one open() to the copy shipped in its repository and neutralise .cuda()
+    import builtins
+    import torch
+    ns = ref_shim.load()
+    real_open, real_cuda = builtins.open, torch.Tensor.cuda
+    def _open(f, *a, **k):
+        if isinstance(f, str) and f.endswith("VETO_rebuttal/pred_counts.pkl"):
+            f = os.path.join(ref_shim.REF_ROOT, "pred_counts.pkl")
+        return real_open(f, *a, **k)
+    builtins.open, torch.Tensor.cuda = _open, (lambda self, *a, **k: self)
+    try:
+        cfg = ref_shim.make_cfg(ns)
+        cfg.merge_from_list(["GLOBAL_SETTING.BETA_LOSS", True])
+        pred = ref_shim.build_predictor(ns, cfg, 151, 51)
+        out["beta_loss_weight"] = pred.criterion_loss_rel.weight.numpy().copy()
+    finally:
+        builtins.open, torch.Tensor.cuda = real_open, real_cuda
+    path = os.path.join(OUT, "meet_sample_rates.npz")
+    np.savez_compressed(path, **out)
+    print(f"meet_sample_rates: wrote {path}", sorted(out))
+
+
 def main():
-    from tests.cases import TRAIN_CASES
+    from tests.cases import MEET_TRAIN_CASES, TRAIN_CASES
     ns = ref_shim.load()
     only = sys.argv[1:]
     for name, c in CASES.items():
@@ -173,6 +274,12 @@ def main():
         if only and name not in only:
             continue
         run_train_case(ns, name, c)
+    for name, c in MEET_TRAIN_CASES.items():
+        if only and name not in only:
+            continue
+        run_meet_train_case(ns, name, c)
+    if not only or "meet_sample_rates" in only:
+        run_sample_rates()
 
 
 if __name__ == "__main__":

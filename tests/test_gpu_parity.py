@@ -380,11 +380,11 @@ def test_full_size_sgdet_batch_properties():
 def test_no_cpu_fallback_and_errors():
     with pytest.raises(RuntimeError):
         ops.roi_align_forward(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 1.0, 2, 2, 2)      # CPU tensors
-    meet = H.build_predictor(H.make_cfg(predictor="VETOPredictor_MEET"),
-                             synth.meet_state(1, 151, synth.GROUP_SPLITS[("VG", "divide4")]), DEV)
-    meet.train()
-    with pytest.raises(NotImplementedError):      # the MEET training branch is not built (the vanilla one is: test_gpu_train.py)
-        meet([], [], None, None)
+    sg = H.make_cfg(predictor="VETOPredictor_MEET", mode="sgdet")
+    meet = H.build_predictor(sg, synth.meet_state(1, 151, synth.GROUP_SPLITS[("VG", "divide4")]), DEV)
+    batch = synth.make_batch(3, [3], H=320, W=416, mode="sgdet")
+    with pytest.raises(NotImplementedError):      # MEET sgdet test needs nms_per_cls (roi_relation_predictors.py:3855-3874)
+        meet(H.boxlists(batch, DEV, 151), [torch.zeros((1, 2), dtype=torch.long, device=DEV)], None, None)
     with pytest.raises(ValueError):
         ops.make_config(151, 51, precision="fp8")
     cfg = ops.make_config(151, 51, "fp32", dim=512)

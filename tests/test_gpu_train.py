@@ -177,9 +177,119 @@ def test_train_step_lowers_the_loss():
     assert hist[-1] < hist[0], hist
 
 
+def _run_meet_train(c, precision, batch, sd, pairs, rel_labels, sample_seed, expert_group=False, dropout=(0.0, 0.0, 0.0)):
+    import random
+    cfg = H.make_cfg(predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"], precision=precision)
+    cfg.ENSEMBLE_LEARNING.EXPERT_GROUP = expert_group
+    num_obj = vcfg.num_classes(cfg)[0]
+    bls = H.boxlists(batch, DEV, num_obj)
+    feats, depth = H.device_features(batch, DEV)
+    depth.requires_grad_(True)
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(DEV).train()
+    pred = registry.make_roi_relation_predictor(cfg, 512)
+    pred.load_state_dict(synth.to_torch_state(sd), strict=True)
+    pred = pred.to(DEV).train()
+    _set_dropout(pred.model, *dropout)
+    x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+    d2d.retain_grad()
+    random.seed(sample_seed)
+    out = pred(bls, [torch.from_numpy(p).to(DEV) for p in pairs], [torch.from_numpy(l).to(DEV) for l in rel_labels], None,
+               roi_features=x2d, roi_depth_features=d2d)
+    assert out[0] is None and out[1] is None and out[5] is None
+    losses = out[2]
+    sum(losses.values()).backward()           # tools/relation_train_net.py:451
+    torch.cuda.synchronize()
+    grads = {k: H.np_(p.grad) for k, p in pred.named_parameters() if p.grad is not None}
+    no_grad = sorted(k for k, p in pred.named_parameters() if p.grad is None)
+    return dict(losses={k: float(v.detach()) for k, v in losses.items()}, grads=grads, no_grad=no_grad,
+                g_roi_depth=H.np_(d2d.grad), g_depth_map=H.np_(depth.grad), incre=out[3], chosen=out[4], pred=pred)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_meet_train_step_matches_oracle_and_reference(precision):
+    """VETOPredictor_MEET in train() mode: the group sampling under the reference's `random`
+    stream picks the reference's pairs, the five 'group_k_CE_loss' values and the gradients of their sum match the
+    gradient oracle (torch_port.train_step_meet) and the fixture of the unmodified reference."""
+    from tests.cases import MEET_TRAIN_CASES
+    from tests.train_util import meet_train_case_inputs, oracle_meet_train_step
+    from veto_b200 import meet_sampling as MS
+    name = "train_meet_vg"
+    c = MEET_TRAIN_CASES[name]
+    g = load_golden(name)
+    batch, sd, pairs, labels = meet_train_case_inputs(c)
+    mine = _run_meet_train(c, precision, batch, sd, pairs, labels, c["sample_seed"])
+    chosen = mine["chosen"][0]
+    assert len(mine["chosen"]) == int(g["expert_dist_len"])
+    for k, rows in enumerate(chosen):
+        assert np.array_equal(np.array(rows, dtype=np.int64), g[f"chosen/{k}"]), f"group {k}: sampled pairs differ"
+    assert list(mine["incre"]) == list(g["incre_idx_list"])
+    names = [str(n) for n in g["loss_names"]]
+    assert sorted(mine["losses"]) == names
+    got = np.array([mine["losses"][n] for n in names])
+    assert np.abs(got - g["losses"]).max() <= 4 * LOSS_TOL[precision] * np.abs(g["losses"]).max(), (got, g["losses"])
+    table = MS.group_local_labels(np.concatenate(labels).tolist(), chosen, list(g["incre_idx_list"]))
+    ref = oracle_meet_train_step(c, batch, sd, pairs, table)
+    tol = GRAD_TOL[precision]
+    rows = [("losses", float(np.abs(got - ref["losses"]).max() / np.abs(ref["losses"]).max()))]
+    for k, gr in ref["grads"].items():
+        assert k in mine["grads"], f"no gradient for {k}"
+        rows.append((k, grad_error(mine["grads"][k], gr)))
+    rows.append(("roi_depth_features", grad_error(mine["g_roi_depth"], ref["g_roi_depth"])))
+    _report(f"{name} {precision}", rows)
+    bad = [(k, e) for k, e in rows[1:] if not e <= tol]
+    assert not bad, f"gradients outside {tol}: {bad[:8]}"
+    # each group loss averages only the 11..41 pairs sampled into it (rel_loss averages all of them): 3x the rel_loss bar
+    assert rows[0][1] <= 3 * LOSS_TOL[precision]
+    assert mine["no_grad"] == sorted(str(k) for k in g["no_grad"])
+    grads = dict(mine["grads"])
+    grads["roi_depth"] = mine["g_roi_depth"]
+    check_against_golden(grads, g, 2 * tol)
+
+
+def test_meet_train_expert_group_and_loss_weights():
+    """EXPERT_GROUP True: 3 experts x 5 groups = 15 heads, expert j of group k sees group k's pairs (:3834-3840), so
+    with identical weights per expert the 15 losses repeat the 5 group losses.  Unequal loss weights cannot be
+    honoured by the fused step and must poison the gradients instead of being silently wrong."""
+    from tests.cases import MEET_TRAIN_CASES
+    from tests.train_util import meet_train_case_inputs
+    c = MEET_TRAIN_CASES["train_meet_vg"]
+    batch, sd, pairs, labels = meet_train_case_inputs(c)
+    base = _run_meet_train(c, "bf16x3", batch, sd, pairs, labels, c["sample_seed"])
+    sizes = synth.GROUP_SPLITS[("VG", "divide4")]
+    sd3 = {k: v for k, v in sd.items() if ".rel_out." not in k}
+    for j in range(3):
+        for k in range(len(sizes)):
+            for t in ("weight", "bias"):
+                sd3[f"model.rel_out_group.{j}.{k}.{t}"] = sd[f"model.rel_out.{k}.{t}"]
+    for k in range(len(sizes)):
+        for t in ("weight", "bias"):
+            sd3[f"model.rel_out.{k}.{t}"] = sd[f"model.rel_out.{k}.{t}"]
+    exp = _run_meet_train(c, "bf16x3", batch, sd3, pairs, labels, c["sample_seed"], expert_group=True)
+    assert len(exp["losses"]) == 15
+    for k in range(len(sizes)):
+        for j in range(3):
+            assert abs(exp["losses"]["group_%d%d_CE_loss" % (k, j + 1)] - base["losses"]["group_%d_CE_loss" % k]) <= 1e-6 * abs(base["losses"]["group_%d_CE_loss" % k])
+    # trunk gradients: three identical expert sets -> three times the single-set gradient
+    key = "model.fusion_transformer.transformer.layers.0.1.fn.net.0.weight"
+    assert grad_error(exp["grads"][key], 3.0 * base["grads"][key]) <= 1e-4
+    # unequal weights
+    cfg = H.make_cfg(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", precision="bf16x3")
+    bls = H.boxlists(batch, DEV, 151)
+    feats, depth = H.device_features(batch, DEV)
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(DEV).train()
+    pred = registry.make_roi_relation_predictor(cfg, 512)
+    pred.load_state_dict(synth.to_torch_state(sd), strict=True)
+    pred = pred.to(DEV).train()
+    x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+    losses = pred(bls, [torch.from_numpy(p).to(DEV) for p in pairs], [torch.from_numpy(l).to(DEV) for l in labels], None,
+                  roi_features=x2d, roi_depth_features=d2d)[2]
+    (losses["group_0_CE_loss"] * 2.0 + losses["group_1_CE_loss"]).backward()
+    assert bool(torch.isnan(pred.model.location_projection[0].weight.grad).all())
+
+
 def test_training_branch_errors():
     c = TRAIN_CASES["train_predcls"]
-    cfg = H.make_cfg(predictor="VETOPredictor_MEET", precision="bf16x3")
+    cfg = H.make_cfg(predictor="VETOPredictor", precision="bf16x3")
     pred = registry.make_roi_relation_predictor(cfg, 512).to(DEV).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(Exception):            # no proposals / pairs: a training step needs at least one of each
         pred([], [], [], None, roi_features=None, roi_depth_features=None)

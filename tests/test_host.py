@@ -64,8 +64,22 @@ def test_unsupported_architecture_is_refused():
         registry.make_roi_relation_predictor(cfg, 512)
     cfg = vcfg.default_cfg()
     cfg.GLOBAL_SETTING.BETA_LOSS = True
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):           # the predicate counts must be supplied (VETO_B200.PRED_COUNTS)
         registry.make_roi_relation_predictor(cfg, 512)
+
+
+def test_beta_loss_weights_match_reference():
+    """GLOBAL_SETTING.BETA_LOSS (roi_relation_predictors.py:4057-4066): the CE class weights the unmodified reference
+    builds from its pred_counts.pkl (golden: make_golden.py run_sample_rates) — bit-exact."""
+    import os
+    from tests.cases import GOLDEN_DIR
+    cfg = vcfg.default_cfg()
+    cfg.GLOBAL_SETTING.BETA_LOSS = True
+    cfg.VETO_B200.PRED_COUNTS = os.path.join(GOLDEN_DIR, "pred_counts_vg.npy")
+    m = registry.make_roi_relation_predictor(cfg, 512)
+    ref = load_golden("meet_sample_rates")["beta_loss_weight"]
+    assert np.array_equal(m.criterion_loss_rel.weight.numpy(), ref)
+    assert "criterion_loss_rel.weight" in m.state_dict()
 
 
 def test_boxlist_conventions():

@@ -236,3 +236,67 @@ def test_torch_port_train_step_matches_reference(name):
         assert str(k) not in out["grads"]
     assert np.allclose(out["running_mean"], g["running_mean"], rtol=1e-6)
     assert np.allclose(out["running_var"], g["running_var"], rtol=1e-6)
+
+
+def test_meet_sample_rates_and_group_index_match_reference():
+    """veto_b200.meet_sampling.sample_rate_matrix / predictor.incre_idx_list against the reference's
+    generate_sample_rate_vector_sep2 / get_current_predicate_idx for every (dataset, split) (golden: make_golden.py)."""
+    from veto_b200 import config as vcfg
+    from veto_b200 import meet_sampling as MS
+    from veto_b200.predictor import incre_idx_list
+    g = load_golden("meet_sample_rates")
+    seen = 0
+    for (ds, split), sizes in vcfg.GROUP_SPLITS.items():
+        key = f"rates/{ds}/{split}"
+        if key not in g.files:
+            continue
+        seen += 1
+        ref = g[key]
+        mine = MS.sample_rate_matrix(ds, sizes)
+        assert mine.shape == ref.shape
+        assert np.array_equal(mine, ref), (ds, split, np.abs(mine - ref).max())
+        assert incre_idx_list(sizes, ref.shape[1]) == list(g[f"incre/{ds}/{split}"])
+    assert seen >= 8
+
+
+def test_meet_group_sampling_matches_reference():
+    """The host-side group sampling + relabelling reproduces the reference's cur_chosen_matrix under the same
+    random.seed, and torch_port.train_step_meet reproduces the reference's group losses and gradients."""
+    import random
+    from tests.cases import MEET_TRAIN_CASES
+    from tests.train_util import check_against_golden, meet_train_case_inputs, oracle_meet_train_step
+    from veto_b200 import meet_sampling as MS
+    name = "train_meet_vg"
+    c = MEET_TRAIN_CASES[name]
+    g = load_golden(name)
+    batch, sd, pairs, labels = meet_train_case_inputs(c)
+    assert _digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]) == str(g["input_digest"])
+    assert _digest([sd[k] for k in sorted(sd)]) == str(g["weight_digest"])
+    flat = np.concatenate(labels)
+    assert np.array_equal(flat, g["rel_labels"])
+    sizes = synth.GROUP_SPLITS[("VG", "divide4")]
+    incre = list(g["incre_idx_list"])
+    random.seed(c["sample_seed"])
+    chosen = MS.group_sampling(flat.tolist(), incre, MS.sample_rate_matrix("VG", sizes), len(sizes), "rand_insert")
+    for k, rows in enumerate(chosen):
+        assert np.array_equal(np.array(rows, dtype=np.int64), g[f"chosen/{k}"]), k
+    assert int(g["expert_dist_len"]) == len(flat)
+    table = MS.group_local_labels(flat.tolist(), chosen, incre)
+    # the relabelling, restated naively (roi_relation_predictors.py:3812-3821)
+    for k, rows in enumerate(chosen):
+        members = [i for i, x in enumerate(incre) if x == k + 1]
+        for r in range(len(flat)):
+            if r not in rows:
+                assert table[k, r] == -1
+            else:
+                p = int(flat[r])
+                assert table[k, r] == (0 if p == 0 else members.index(p) + 1 if p in members else len(members) + 1)
+    out = oracle_meet_train_step(c, batch, sd, pairs, table)
+    assert [str(n) for n in g["loss_names"]] == [f"group_{k}_CE_loss" for k in range(len(sizes))]
+    assert np.abs(out["losses"] - g["losses"]).max() <= 2e-5 * np.abs(g["losses"]).max()
+    grads = dict(out["grads"])
+    grads["roi_depth"] = out["g_roi_depth"]
+    worst = check_against_golden(grads, g, 2e-4)
+    assert len(worst) >= 85
+    for k in g["no_grad"]:
+        assert str(k) not in out["grads"]

@@ -60,3 +60,27 @@ def check_against_golden(grads, g, tol, skip=()):
         worst[k] = max(e_samples, e_norm)
         assert e_samples <= tol and e_norm <= tol, f"{k}: samples {e_samples:.2e} norm {e_norm:.2e} > {tol}"
     return worst
+
+
+def meet_train_case_inputs(c):
+    """(batch, MEET state_dict numpy, per-image pair arrays, concatenated rel_labels list, obj_preds) of a MEET case."""
+    from oracle import veto_oracle as O
+    batch = case_batch(c)
+    sd = dict(case_state(c))
+    pairs = O.prepare_test_pairs(batch["n_boxes"])
+    labels = case_rel_labels(c, [len(p) for p in pairs])
+    return batch, sd, pairs, labels
+
+
+def oracle_meet_train_step(c, batch, sd, pairs, head_labels, drop=None):
+    """oracle/torch_port.train_step_meet on a MEET case: dict(losses [G], grads{key: np}, g_roi_depth)."""
+    import torch
+    from oracle import torch_port as TP
+    tsd = TP.to_torch(sd)
+    boxes = [torch.from_numpy(b) for b in batch["boxes"]]
+    x2d, d2d = TP.pooler_forward([torch.from_numpy(f) for f in batch["feats"]], torch.from_numpy(batch["depth"]), boxes)
+    obj_preds = torch.from_numpy(np.concatenate(batch["labels"])).long()
+    losses, grads, g_d2d, g_x2d, bn_out = TP.train_step_meet(
+        tsd, boxes, [torch.from_numpy(p) for p in pairs], head_labels, x2d, d2d, obj_preds, drop=drop)
+    return dict(losses=np.array([float(l) for l in losses]), grads={k: v.numpy() for k, v in grads.items()},
+                g_roi_depth=g_d2d.numpy(), g_roi_rgb=g_x2d.numpy(), x2d=x2d.numpy(), d2d=d2d.numpy())

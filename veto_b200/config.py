@@ -80,7 +80,7 @@ _DEFAULTS = {
     "GLOVE_DIR": "",
     "OUTPUT_DIR": "",
     # extension (not a reference key): arithmetic of the encoder GEMMs, see include/veto_b200.h
-    "VETO_B200": {"PRECISION": "bf16x3", "CHUNK_PAIRS": 0, "FREQ_BIAS": False},
+    "VETO_B200": {"PRECISION": "bf16x3", "CHUNK_PAIRS": 0, "FREQ_BIAS": False, "PRED_COUNTS": ""},
 }
 
 # predicate_stage_count of SHA_GCL_extra/group_chosen_function.py:6-95 (groups are contiguous id ranges)

@@ -48,14 +48,14 @@ def sample_rate_matrix(dataset: str, group_sizes: Sequence[int]) -> np.ndarray:
         seen = counts[1:hi + 1]
         out[g, 1:hi + 1] = np.where(seen > median, np.maximum(median / seen, 0.01), 1.0)
         if counts[0] > median:
-            out[g, 0] = max(10.0 * median / counts[0], 0.01)
+            out[g, 0] = max(median / counts[0] * 10.0, 0.01)   # the reference's operation order (bit-exact table)
         else:                                   # never true for the real tables; the reference's indexing quirk (:222-224)
             out[g, 0] = 1.0 if lo == 0 else 0.0
         ceiling = max(counts[0], counts[lo + 1:hi + 1].max())
         later = counts[hi + 1:]
         rate = np.maximum(median / later, 0.01)
         if later.size:
-            rate[0] = max(10.0 * median / later[0], 0.01)
+            rate[0] = max(median / later[0] * 10.0, 0.01)
         out[g, hi + 1:] = np.where(later > ceiling, rate, 1.0)
     return out
 

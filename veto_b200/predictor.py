@@ -52,6 +52,37 @@ def obj_edge_vectors(names, wv_dir, wv_dim):
         return torch.randn(len(names), wv_dim)
 
 
+REFERENCE_PRED_COUNTS_PATH = "/visinf/home/gsudhakaran/scene_graphs/VETO_rebuttal/pred_counts.pkl"
+
+
+def load_pred_counts(config):
+    """Per-predicate training counts for GLOBAL_SETTING.BETA_LOSS.  The reference reads a hard-coded absolute path
+    (roi_relation_predictors.py:4059; the same file ships at the root of its repository); here the path comes from
+    the extension key VETO_B200.PRED_COUNTS (a .pkl or .npy), falling back to the reference's path."""
+    import os
+    import pickle
+    import numpy as np
+    path = C.get(config, "VETO_B200.PRED_COUNTS", "") or REFERENCE_PRED_COUNTS_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"GLOBAL_SETTING.BETA_LOSS needs the predicate counts: set VETO_B200.PRED_COUNTS "
+                                f"(tried {path})")
+    if path.endswith(".npy"):
+        return np.load(path)
+    with open(path, "rb") as fin:
+        return np.asarray(pickle.load(fin))
+
+
+def beta_loss_weights(rel_counts, num_rel: int, beta: float = 0.999) -> torch.Tensor:
+    """Class-balanced CE weights (roi_relation_predictors.py:4060-4066): counts sorted descending, effective-number
+    weighting (1 - beta) / (1 - beta^n) normalised to sum num_rel; computed in the counts' own dtype like the reference."""
+    import numpy as np
+    counts = np.array(rel_counts, copy=True)
+    counts[::-1].sort()
+    w = (1.0 - beta) / (1 - (beta ** counts))
+    w *= float(num_rel) / np.sum(w)
+    return torch.FloatTensor(w)
+
+
 def xavier_init(m: nn.Linear) -> nn.Linear:
     """pysgg/modeling/utils.py-style xavier_normal_ + zero bias is NOT what the reference uses for rel_out:
     miscellaneous.py:85-93 applies xavier_normal_ to the weight only."""
@@ -268,9 +299,12 @@ class VETOPredictor(_Trunk):
         self._build_trunk(config, self.obj_classes)
         dim = config.MODEL.ROI_RELATION_HEAD.VETOTRANSFORMER.T_INPUT_DIM
         self.rel_out = xavier_init(nn.Linear(dim, self.num_rel_cls, bias=True))
-        if config.GLOBAL_SETTING.BETA_LOSS:
-            raise NotImplementedError("GLOBAL_SETTING.BETA_LOSS needs the training branch (next round)")
-        self.criterion_loss_rel = nn.CrossEntropyLoss(weight=torch.ones(self.num_rel_cls))
+        self.beta_loss = bool(config.GLOBAL_SETTING.BETA_LOSS)
+        if self.beta_loss:
+            rel_class_weights = beta_loss_weights(load_pred_counts(config), self.num_rel_cls)
+        else:
+            rel_class_weights = torch.ones(self.num_rel_cls)
+        self.criterion_loss_rel = nn.CrossEntropyLoss(weight=rel_class_weights)
         self.criterion_loss = nn.CrossEntropyLoss()
         self.use_freq_bias = bool(C.get(config, "VETO_B200.FREQ_BIAS", False))
         self.freq_bias_table = None  # [num_obj^2, num_rel] fp32, set by the caller when use_freq_bias
