@@ -306,6 +306,20 @@ int veto_postprocess(const float* rel_logits_dev, int num_rel, const int64_t* pa
                      float* triple_out_dev, veto_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a10. Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874) with nms_overlaps
+ * (relation_head/utils_relation.py:56-79): MEET's greedy per-class label assignment at SGDet test time.
+ * Per image, n rounds: take the arg max of the [n, num_obj] score tile (column 0 excluded; first index in
+ * row-major order on ties, like numpy.argmax), give that box that class, zero the class's score of every box
+ * whose class box overlaps it by IoU >= thresh (+1 box convention, fp32, the reference's operation order), and
+ * retire the box.  scores_dev [N,num_obj] fp32 = softmax of the detector distribution (the caller computes it:
+ * the reference feeds softmax(one_hot(pred_labels))); boxes_per_cls_dev [N,num_obj,4] fp32 xyxy;
+ * box_offsets_dev int32 [n_images+1]; n_boxes_host [n_images]; labels_out_dev int64 [N].
+ * One CTA per image with the score tile in shared memory: n * num_obj <= 56 320 (80 boxes x 151 classes = 12 080). */
+int veto_obj_nms_per_cls(const float* scores_dev, const float* boxes_per_cls_dev, const int32_t* box_offsets_dev,
+                         const int32_t* n_boxes_host, int n_images, int num_obj, float thresh,
+                         int64_t* labels_out_dev, veto_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): one GEMM  C[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual)
  * through the SIMT or the tcgen05 kernel, fp32 in / fp32 out. scratch_dev: >= 4*(M*K + N*K) bytes. */
 int veto_test_gemm(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,

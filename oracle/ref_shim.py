@@ -221,7 +221,10 @@ def make_boxlists(ns, batch, num_obj):
             bl.add_field("predict_logits", torch.from_numpy(batch["predict_logits"][i]))
             bl.add_field("pred_scores", torch.from_numpy(batch["pred_scores"][i]))
             bl.add_field("pred_labels", torch.from_numpy(batch["pred_labels"][i]))
-            bpc = torch.from_numpy(batch["boxes"][i])[:, None, :].expand(-1, num_obj, -1).contiguous()
+            if "boxes_per_cls" in batch:
+                bpc = torch.from_numpy(batch["boxes_per_cls"][i])
+            else:
+                bpc = torch.from_numpy(batch["boxes"][i])[:, None, :].expand(-1, num_obj, -1).contiguous()
             bl.add_field("boxes_per_cls", bpc)
         out.append(bl)
     return out

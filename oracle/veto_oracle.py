@@ -319,11 +319,23 @@ def incre_idx_list(group_sizes: Sequence[int], num_rel: int) -> List[int]:
     return out
 
 
-def meet_forward(sd, batch, pairs, x2d, d2d, group_sizes, mode="predcls") -> Dict[str, np.ndarray]:
+def softmax_rows(x: np.ndarray) -> np.ndarray:
+    e = np.exp(x - x.max(1, keepdims=True), dtype=np.float32)
+    return e / e.sum(1, keepdims=True, dtype=np.float32)
+
+
+def meet_forward(sd, batch, pairs, x2d, d2d, group_sizes, mode="predcls", nms_thresh: float = 0.5,
+                 nms_scores: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """VETOPredictor_MEET.forward eval (:3909-3995) -> Ensemble.forward (:3752-3853),
-    EXPERT_GROUP False: {'group_k': [R, n_k+2]} un-split."""
+    EXPERT_GROUP False: {'group_k': [R, n_k+2]} un-split.  sgdet test with boxes_per_cls: obj_preds from nms_per_cls
+    over softmax(one_hot(pred_labels)) (:3776-3781; `nms_scores` overrides that softmax, see tests)."""
     obj_preds = None
-    if mode != "predcls":
+    if mode == "sgdet" and "boxes_per_cls" in batch:
+        labels = np.concatenate(batch["pred_labels"])
+        if nms_scores is None:
+            nms_scores = softmax_rows(np.eye(batch["num_obj"], dtype=np.float32)[labels])
+        obj_preds = nms_per_cls(nms_scores, batch["boxes_per_cls"], batch["n_boxes"], nms_thresh)
+    elif mode != "predcls":
         # non-sgdet-test branch: obj_dists one-hot -> argmax over [1:] (+1) (:3783)
         obj_preds = np.concatenate(batch["pred_labels"])
     feat = relation_features(sd, batch, pairs, x2d, d2d, mode, prefix="model.", meet=True, obj_preds=obj_preds)
@@ -363,3 +375,35 @@ def postprocess(rel_logits: Sequence[np.ndarray], obj_logits: Sequence[np.ndarra
         res.append(dict(rel_pair_idxs=pr[order], pred_rel_scores=rp[order], pred_rel_labels=rel_class[order],
                         triple_scores=triple[order], pred_labels=obj_pred, pred_scores=obj_scores))
     return res
+
+
+def nms_overlaps(boxes: np.ndarray) -> np.ndarray:
+    """relation_head/utils_relation.py:56-79: per-class IoU [n, n, C] of boxes [n, C, 4] (xyxy, +1 convention), fp32 in
+    the reference's operation order."""
+    b = boxes.astype(np.float32)
+    max_xy = np.minimum(b[:, None, :, 2:], b[None, :, :, 2:])
+    min_xy = np.maximum(b[:, None, :, :2], b[None, :, :, :2])
+    inter = np.clip(max_xy - min_xy + np.float32(1.0), 0, None)
+    inters = inter[..., 0] * inter[..., 1]
+    areas = (b[..., 2] - b[..., 0] + np.float32(1.0)) * (b[..., 3] - b[..., 1] + np.float32(1.0))
+    union = -inters + areas[None] + areas[:, None]
+    return inters / union
+
+
+def nms_per_cls(scores: np.ndarray, boxes_per_cls: Sequence[np.ndarray], n_boxes: Sequence[int], thresh: float) -> np.ndarray:
+    """Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874).  `scores` [N, C] = softmax of the object
+    distribution (the reference computes F.softmax(obj_dists[i], -1) per image and takes it to numpy)."""
+    out, off = [], 0
+    for i, n in enumerate(n_boxes):
+        is_overlap = nms_overlaps(boxes_per_cls[i]) >= np.float32(thresh)
+        sampled = scores[off:off + n].astype(np.float32).copy()
+        off += n
+        sampled[:, 0] = -1
+        label = np.zeros(n, np.int64)
+        for _ in range(n):
+            box_ind, cls_ind = np.unravel_index(sampled.argmax(), sampled.shape)
+            label[int(box_ind)] = int(cls_ind)
+            sampled[is_overlap[box_ind, :, cls_ind], cls_ind] = 0.0
+            sampled[box_ind] = -1.0
+        out.append(label)
+    return np.concatenate(out) if out else np.zeros(0, np.int64)

@@ -32,6 +32,10 @@ CASES = {
                      batch_seed=5, weight_seed=14, spread=True),
     "meet_vg": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", n_boxes=[10],
                     batch_seed=6, weight_seed=15, spread=True, H=320, W=416),
+    # MEET at SGDet test time: obj_preds from the per-class greedy NMS (Ensemble.nms_per_cls, :3855-3874); detector
+    # labels from 3 classes + jittered boxes_per_cls so that overlapping boxes compete for a class
+    "meet_sgdet_nms": dict(predictor="VETOPredictor_MEET", mode="sgdet", dataset="VG", n_boxes=[12, 7],
+                           batch_seed=10, weight_seed=19, spread=True, H=320, W=416, nms_seed=3),
 }
 
 
@@ -71,8 +75,11 @@ def case_class_weight(c):
 
 def case_batch(c, features=True):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA
-    return synth.make_batch(c["batch_seed"], c["n_boxes"], H=c.get("H", 592), W=c.get("W", 800),
-                            num_obj=ds["num_obj"], mode=c["mode"], features=features)
+    batch = synth.make_batch(c["batch_seed"], c["n_boxes"], H=c.get("H", 592), W=c.get("W", 800),
+                             num_obj=ds["num_obj"], mode=c["mode"], features=features)
+    if "nms_seed" in c:
+        synth.add_nms_fields(batch, c["nms_seed"])
+    return batch
 
 
 def case_state(c):

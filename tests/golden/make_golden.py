@@ -47,6 +47,15 @@ def run_case(ns, name, c):
     fe = ns.make_extractor(cfg, 256, for_relation=True).eval()
     samp, post = ns.make_sampler(cfg), ns.make_post(cfg)
     out = {}
+    if "nms_seed" in c:
+        # record what Ensemble.nms_per_cls saw and returned (its softmax input is computed per image on CPU torch)
+        real_nms = pred.model.nms_per_cls
+        def _nms(obj_dists, boxes_per_cls, num_objs):
+            out["nms_scores"] = np.concatenate([torch.softmax(d, -1).numpy() for d in obj_dists.split(num_objs, dim=0)])
+            res = real_nms(obj_dists, boxes_per_cls, num_objs)
+            out["nms_labels"] = res.numpy().copy()
+            return res
+        pred.model.nms_per_cls = _nms
     with torch.no_grad():
         pairs = samp.prepare_test_pairs(torch.device("cpu"), bls)
         feats = [torch.from_numpy(f) for f in batch["feats"]]
@@ -54,6 +63,10 @@ def run_case(ns, name, c):
         x2d, d2d, _, _ = fe(feats, bls, depth_features=torch.from_numpy(batch["depth"]))
         obj_d, rel_d, losses, incre, chosen, custom = pred(bls, pairs, None, None, roi_features=x2d,
                                                           roi_depth_features=d2d)
+    if "nms_seed" in c:
+        changed = int((out["nms_labels"] != np.concatenate(batch["pred_labels"])).sum())
+        print(f"{name}: per-class NMS changed {changed} of {len(out['nms_labels'])} labels")
+        assert changed >= 2, "the NMS case must exercise suppression"
     out["input_digest"] = np.array(digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]))
     out["weight_digest"] = np.array(digest([sd[k] for k in sorted(sd)]))
     out["pairs"] = np.concatenate([p.numpy() for p in pairs])

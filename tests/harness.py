@@ -50,6 +50,8 @@ def boxlists(batch, device, num_obj):
             bl.add_field("predict_logits", torch.from_numpy(batch["predict_logits"][i]).to(device))
             bl.add_field("pred_scores", torch.from_numpy(batch["pred_scores"][i]).to(device))
             bl.add_field("pred_labels", torch.from_numpy(batch["pred_labels"][i]).to(device))
+            if "boxes_per_cls" in batch:
+                bl.add_field("boxes_per_cls", torch.from_numpy(batch["boxes_per_cls"][i]).to(device))
         out.append(bl)
     return out
 

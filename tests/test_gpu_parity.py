@@ -255,7 +255,7 @@ def test_tokens_match_reference(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("name", ["meet_gqa", "meet_vg"])
+@pytest.mark.parametrize("name", ["meet_gqa", "meet_vg", "meet_sgdet_nms"])
 def test_meet_group_heads(name, precision):
     c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
     obj_dists, rel_dists, add_losses, incre, chosen, custom = out
@@ -268,6 +268,34 @@ def test_meet_group_heads(name, precision):
         assert got.shape == ref.shape                           # un-split [R_total, n_k+2] (…:3843,3851-3853)
         assert rel_err(got, ref) < TOL[precision]
         _check_argmax(got, ref, precision)
+
+
+def test_meet_per_class_nms_bit_exact():
+    """veto_obj_nms_per_cls against Ensemble.nms_per_cls of the unmodified reference (golden: the score tile the
+    reference fed it and the labels it returned) and against the numpy oracle on larger seeded cases, incl. ragged /
+    empty images and a class count where many boxes compete."""
+    from oracle import veto_oracle as O
+    c, g = CASES["meet_sgdet_nms"], load_golden("meet_sgdet_nms")
+    batch = case_batch(c, features=False)
+    bpc = _t(np.concatenate(batch["boxes_per_cls"]))
+    got = H.np_(ops.obj_nms_per_cls(_t(g["nms_scores"]), bpc, batch["n_boxes"], 0.5))
+    assert np.array_equal(got, g["nms_labels"])
+    assert (got != np.concatenate(batch["pred_labels"])).sum() >= 2
+    # the drop-in's own score tile (torch softmax on the device) gives the same labels here
+    onehot = torch.nn.functional.one_hot(_t(np.concatenate(batch["pred_labels"])), 151).float()
+    assert np.array_equal(H.np_(ops.obj_nms_per_cls(torch.softmax(onehot, -1), bpc, batch["n_boxes"], 0.5)), g["nms_labels"])
+    for seed, n_boxes, n_cls, thr in ((1, [80, 0, 33, 1], 4, 0.5), (2, [64] * 8, 2, 0.3), (3, [100, 7], 10, 0.7)):
+        b = synth.make_batch(seed, n_boxes, H=592, W=800, mode="sgdet", features=False)
+        synth.add_nms_fields(b, seed + 10, n_classes=n_cls, jitter=12.0)
+        rng = np.random.default_rng(seed)
+        # generic soft scores (not only one-hot): softmax of noisy logits peaked at the detector label
+        lg = rng.standard_normal((sum(n_boxes), 151)).astype(np.float32)
+        lg[np.arange(sum(n_boxes)), np.concatenate(b["pred_labels"])] += 4.0
+        scores = O.softmax_rows(lg)
+        ref = O.nms_per_cls(scores, b["boxes_per_cls"], b["n_boxes"], thr)
+        got = H.np_(ops.obj_nms_per_cls(_t(scores), _t(np.concatenate(b["boxes_per_cls"])), b["n_boxes"], thr))
+        assert np.array_equal(got, ref), (seed, int((got != ref).sum()))
+        assert (ref != scores[:, 1:].argmax(1) + 1).any()          # suppression happened
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
@@ -383,7 +411,7 @@ def test_no_cpu_fallback_and_errors():
     sg = H.make_cfg(predictor="VETOPredictor_MEET", mode="sgdet")
     meet = H.build_predictor(sg, synth.meet_state(1, 151, synth.GROUP_SPLITS[("VG", "divide4")]), DEV)
     batch = synth.make_batch(3, [3], H=320, W=416, mode="sgdet")
-    with pytest.raises(NotImplementedError):      # MEET sgdet test needs nms_per_cls (roi_relation_predictors.py:3855-3874)
+    with pytest.raises(KeyError):      # MEET sgdet test reads the detector's boxes_per_cls field like the reference (:3778)
         meet(H.boxlists(batch, DEV, 151), [torch.zeros((1, 2), dtype=torch.long, device=DEV)], None, None)
     with pytest.raises(ValueError):
         ops.make_config(151, 51, precision="fp8")

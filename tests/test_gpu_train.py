@@ -173,7 +173,7 @@ def test_train_step_lowers_the_loss():
         loss = pred(bls, pr, lb, None, roi_features=x2d, roi_depth_features=d2d)[2]["rel_loss"]
         loss.backward()
         opt.step()
-        hist.append(float(loss))
+        hist.append(float(loss.detach()))
     assert hist[-1] < hist[0], hist
 
 

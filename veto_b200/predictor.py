@@ -425,9 +425,12 @@ class Ensemble(_Trunk):
         else:
             obj_labels = torch.cat([p.get_field("pred_labels") for p in proposals], 0).detach().long()
             obj_dists = nn.functional.one_hot(obj_labels, self.num_obj_cls).float()
-            if self.mode == "sgdet" and not self.training:
-                raise NotImplementedError("MEET sgdet test uses nms_per_cls (:3855-3874): not built yet")
-            obj_preds = obj_dists[:, 1:].max(1)[1] + 1  # :3783
+            if self.mode == "sgdet" and not self.training:  # use_decoder_nms (:3776-3781)
+                boxes_per_cls = torch.cat([p.get_field("boxes_per_cls") for p in proposals], 0)
+                obj_preds = ops.obj_nms_per_cls(torch.softmax(obj_dists, -1), boxes_per_cls,
+                                                [len(p) for p in proposals], self.nms_thresh)
+            else:
+                obj_preds = obj_dists[:, 1:].max(1)[1] + 1  # :3783
         if self.training:
             return self._forward_train(proposals, rel_pair_idxs, rel_labels, roi_features, roi_depth_features,
                                        obj_preds, cur_chosen_matrix)
