@@ -7,6 +7,8 @@
 //
 // Every reduction here has a fixed order (no floating-point atomics): a training step is bitwise reproducible.
 #include "stages.cuh"
+#include <stdlib.h>
+
 #include "train.cuh"
 
 namespace veto {
@@ -263,18 +265,22 @@ convert_kernel(const float* __restrict__ src, size_t n4, DropSpec drop, float* f
 // The gradient that leaves (dx) is what the next backward GEMMs consume, so the kernel also writes it in their operand
 // format (op_*: fp32 or bf16 hi/lo), through the dropout mask of the Linear below when there is one, and accumulates
 // its column sums (partial[block, 2, :]) = that Linear's bias gradient — no separate convert / column-sum passes.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, const float* __restrict__ gamma,
-              const float* dres, float* dx, int64_t rows, float* __restrict__ partial, DropSpec drop, float* op_f32,
-              __nv_bfloat16* op_hi, __nv_bfloat16* op_lo) {
+              const float* dres, float* dx, int64_t rows, float* __restrict__ partial, DropSpec drop,
+              float* __restrict__ op_f32, __nv_bfloat16* __restrict__ op_hi, __nv_bfloat16* __restrict__ op_lo) {
     constexpr int PER = kDim / 64;  // 9 float2 per lane
     __shared__ float red[8][kDim];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool want_op = op_f32 || op_hi;
-    float2 gam[PER], dg[PER], db[PER], ds[PER];
+    // gamma is re-read through L1 where it is used (2.3 KB, always resident) instead of living in 18 registers: the
+    // registers hold the row's THREE input streams, so that all of a row's global loads are in flight together (one
+    // DRAM round trip per row instead of two — the residual used to be fetched after the reductions).  dres may alias
+    // dx (in-place accumulation into the residual gradient): a row's residual is fully loaded before its first store.
+    const float2* gam = (const float2*)gamma;
+    float2 dg[PER], db[PER], ds[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-        gam[j] = __ldg((const float2*)gamma + lane + 32 * j);
         dg[j] = make_float2(0.f, 0.f);
         db[j] = make_float2(0.f, 0.f);
         ds[j] = make_float2(0.f, 0.f);
@@ -282,14 +288,17 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
     for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < rows; row += (int64_t)gridDim.x * 8) {
         const float2* xr = (const float2*)(x + row * ldx);
         const float2* dyr = (const float2*)(dy + row * kDim);
-        float2 v[PER], d[PER];
+        const float2* rr = (const float2*)(dres ? dres + row * kDim : nullptr);
+        float2 v[PER], d[PER], r[PER];
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            v[j] = xr[lane + 32 * j];
-            d[j] = dyr[lane + 32 * j];
-            s += v[j].x + v[j].y;
+            v[j] = __ldcs(xr + lane + 32 * j);   // streamed: every input element is read exactly once
+            d[j] = __ldcs(dyr + lane + 32 * j);
+            r[j] = rr ? __ldcs(rr + lane + 32 * j) : make_float2(0.f, 0.f);
         }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) s += v[j].x + v[j].y;
         const float mean = warp_sum(s) * (1.f / kDim);
         float q = 0.f;
 #pragma unroll
@@ -301,14 +310,15 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
+            const float2 gm = __ldg(gam + lane + 32 * j);
             v[j].x = (v[j].x - mean) * rstd;  // xhat
             v[j].y = (v[j].y - mean) * rstd;
             dg[j].x += d[j].x * v[j].x;
             dg[j].y += d[j].y * v[j].y;
             db[j].x += d[j].x;
             db[j].y += d[j].y;
-            d[j].x *= gam[j].x;  // g
-            d[j].y *= gam[j].y;
+            d[j].x *= gm.x;  // g
+            d[j].y *= gm.y;
             s1 += d[j].x + d[j].y;
             s2 += d[j].x * v[j].x + d[j].y * v[j].y;
         }
@@ -317,14 +327,9 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             float2 o;
-            o.x = rstd * (d[j].x - s1 - v[j].x * s2);
-            o.y = rstd * (d[j].y - s1 - v[j].y * s2);
+            o.x = rstd * (d[j].x - s1 - v[j].x * s2) + r[j].x;
+            o.y = rstd * (d[j].y - s1 - v[j].y * s2) + r[j].y;
             const size_t e = (size_t)row * kDim + 2 * (lane + 32 * j);
-            if (dres) {
-                const float2 rr = *(const float2*)(dres + e);
-                o.x += rr.x;
-                o.y += rr.y;
-            }
             *(float2*)(dx + e) = o;
             if (want_op) {
                 if (drop.thr16) {  // elements e, e + 1 share a 4-group (e is even)
@@ -363,8 +368,8 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 }
 
 // ---------------------------------------------------------------- attention backward
-// TWO warps per (sequence, head): each owns 48 of the 96 head dims (float4 columns 12h .. 12h+11) of Q, K, V, dO in
-// shared memory, so everything except the 19 x 19 score tile is private to a warp.  Lane i owns query row i:
+// TWO warps per (sequence, head): each owns 48 of the 96 head dims of Q, K, V, dO in shared memory, so everything
+// except the 19 x 19 score tile is private to a warp.  Lane i owns query row i:
 //   partial S = Q K^T and dP = dO V^T over the warp's dims  -> the odd warp hands its partials to the even one through
 //   the P / dS tiles (named barrier), which finishes P = softmax(S * scale), dS = P * (dP - rowsum(P * dP)) * scale and
 //   leaves both tiles in shared memory (second barrier);
@@ -374,30 +379,42 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 // per launch, latency-bound; 14 warps per SM with cp.async staging hide the shared-memory latency.
 // Rows are 96 floats with the float4 column index XOR-swizzled by the row (c ^ (row & 7) within groups of 8), so the
 // per-lane row reads are bank-conflict free without padding: 7 items fit in 227 KB.
+// Column ownership: warp h owns the float4 columns c = 8g + 4h + i (g < 3, i < 4).  The swizzled position of (row, c)
+// is 8g + 4 (h ^ row bit 2) + (i ^ (row & 3)), so in the inner loops — which walk the 19 rows of a K / V / Q / dO tile
+// with the row index unrolled — every shared-memory address is one of two per-warp base registers (h, 1 - h) plus an
+// immediate.  The second version computed the swizzle per access and was issue-bound on integer work (ncu: issue
+// slots 63 % busy at 20 % warps active, 888 us per launch).
 constexpr int AB_ROW = kHeadDim;                 // floats per staged row
 constexpr int AB_PS = 20;                        // row stride of the P / dS tiles
 constexpr int AB_ITEM = 4 * kTokens * AB_ROW + 2 * kTokens * AB_PS;  // floats per item (32,224 B)
 constexpr int AB_ITEMS = 7;
 constexpr int AB_THREADS = AB_ITEMS * 64;
 constexpr int AB_SMEM = AB_ITEMS * AB_ITEM * (int)sizeof(float);  // 225,568 B
+constexpr int AB_BUF = kTokens * AB_ROW;         // floats per staged tile
 
 __device__ __forceinline__ int ab_col(int row, int c) { return (c & ~7) | ((c ^ row) & 7); }  // swizzled float4 column
 __device__ __forceinline__ void ab_bar(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
+// float offset of (row, column i of the warp's group) relative to the per-group base `pa` (row bit 2 clear) / `pb` (set)
+#define AB_AT(pa, pb, row, i) ((((row) >> 2) & 1 ? (pb) : (pa)) + (row) * AB_ROW + 4 * ((i) ^ ((row) & 3)))
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int64_t n_seq, float* g_f32,
                      __nv_bfloat16* g_hi, __nv_bfloat16* g_lo) {
     extern __shared__ float4 ab_smem[];
-    constexpr int LD = 3 * kDim, V4 = kHeadDim / 4, HV4 = V4 / 2;  // 24 float4 columns per row, 12 per warp
+    constexpr int LD = 3 * kDim, HV4 = kHeadDim / 8;  // 12 float4 columns per row per warp
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int slot = wid >> 1, half = wid & 1, c_lo = half * HV4;
+    const int slot = wid >> 1, half = wid & 1;
     float* sQ = reinterpret_cast<float*>(ab_smem) + slot * AB_ITEM;
-    float* sK = sQ + kTokens * AB_ROW;
-    float* sV = sK + kTokens * AB_ROW;
-    float* sDO = sV + kTokens * AB_ROW;
-    float* sP = sDO + kTokens * AB_ROW;
+    float* sK = sQ + AB_BUF;
+    float* sV = sK + AB_BUF;
+    float* sDO = sV + AB_BUF;
+    float* sP = sDO + AB_BUF;
     float* sDS = sP + kTokens * AB_PS;
     auto cell = [&](float* buf, int row, int c) { return (float4*)(buf + row * AB_ROW) + ab_col(row, c); };
+    auto own_col = [&](int t) { return 8 * (t >> 2) + 4 * half + (t & 3); };  // t-th owned column
+    // this lane's own row (query row i / key row j = lane): float offset of group 0, and the XOR of the in-group index
+    const int lrow = lane * AB_ROW + 16 * (half ^ ((lane >> 2) & 1));
+    const int lx = lane & 3;
     const float scale = 0.10206207261596575f;
     const int64_t items = n_seq * kHeads;
     // every warp of a slot runs the same number of iterations (the barriers are per slot)
@@ -409,10 +426,10 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         __syncwarp();
         // stage this warp's 12 columns of the 76 rows (q, k, v, dO): 912 16-byte cp.async, all in flight at once
         for (int idx = lane; idx < 4 * kTokens * HV4; idx += 32) {
-            const int m = idx / HV4, c = c_lo + (idx - m * HV4);
+            const int m = idx / HV4, c = own_col(idx - m * HV4);
             const int which = m / kTokens, row = m - which * kTokens;
             const float* src = which < 3 ? base + (size_t)row * LD + which * kDim + 4 * c : dob + (size_t)row * kDim + 4 * c;
-            float4* dst = cell(sQ + which * kTokens * AB_ROW, row, c);
+            float4* dst = cell(sQ + which * AB_BUF, row, c);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -424,18 +441,24 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
 #pragma unroll
             for (int j = 0; j < kTokens; ++j) { p[j] = 0.f; dp[j] = 0.f; }
             if (lane < kTokens) {
-#pragma unroll 2
-                for (int cc = 0; cc < HV4; ++cc) {
-                    const int c = c_lo + cc;
-                    const float4 q = *cell(sQ, lane, c), g = *cell(sDO, lane, c);
+#pragma unroll 1
+                for (int g = 0; g < 3; ++g) {
+                    const float* ka = sK + 32 * g + 16 * half;          // K tile; the V tile sits AB_BUF floats behind it
+                    const float* kb = sK + 32 * g + 16 * (half ^ 1);
+                    const float* ql = sQ + lrow + 32 * g;               // own row of Q; dO sits 3 * AB_BUF behind it
 #pragma unroll
-                    for (int j = 0; j < kTokens; ++j) {
-                        const float4 k4 = *cell(sK, j, c);
-                        const float4 v4 = *cell(sV, j, c);
-                        p[j] = fmaf(q.x, k4.x, p[j]); p[j] = fmaf(q.y, k4.y, p[j]);
-                        p[j] = fmaf(q.z, k4.z, p[j]); p[j] = fmaf(q.w, k4.w, p[j]);
-                        dp[j] = fmaf(g.x, v4.x, dp[j]); dp[j] = fmaf(g.y, v4.y, dp[j]);
-                        dp[j] = fmaf(g.z, v4.z, dp[j]); dp[j] = fmaf(g.w, v4.w, dp[j]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 q = *(const float4*)(ql + 4 * (i ^ lx));
+                        const float4 go = *(const float4*)(ql + 3 * AB_BUF + 4 * (i ^ lx));
+#pragma unroll
+                        for (int j = 0; j < kTokens; ++j) {
+                            const float4 k4 = *(const float4*)AB_AT(ka, kb, j, i);
+                            const float4 v4 = *(const float4*)(AB_AT(ka, kb, j, i) + AB_BUF);
+                            p[j] = fmaf(q.x, k4.x, p[j]); p[j] = fmaf(q.y, k4.y, p[j]);
+                            p[j] = fmaf(q.z, k4.z, p[j]); p[j] = fmaf(q.w, k4.w, p[j]);
+                            dp[j] = fmaf(go.x, v4.x, dp[j]); dp[j] = fmaf(go.y, v4.y, dp[j]);
+                            dp[j] = fmaf(go.z, v4.z, dp[j]); dp[j] = fmaf(go.w, v4.w, dp[j]);
+                        }
                     }
                 }
             }
@@ -481,57 +504,72 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
             for (int j = 0; j < kTokens; ++j) ds[j] = sDS[lane * AB_PS + j];
             // dQ (row = lane) over the warp's columns -> V buffer (V is dead: every lane of this warp is past dP,
             // and the other warp never touches these columns)
-#pragma unroll 2
-            for (int cc = 0; cc < HV4; ++cc) {
-                const int c = c_lo + cc;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int g = 0; g < 3; ++g) {
+                const float* ka = sK + 32 * g + 16 * half;
+                const float* kb = sK + 32 * g + 16 * (half ^ 1);
+                float* ol = sV + lrow + 32 * g;
 #pragma unroll
-                for (int j = 0; j < kTokens; ++j) {
-                    const float4 k4 = *cell(sK, j, c);
-                    a.x = fmaf(ds[j], k4.x, a.x); a.y = fmaf(ds[j], k4.y, a.y);
-                    a.z = fmaf(ds[j], k4.z, a.z); a.w = fmaf(ds[j], k4.w, a.w);
+                for (int i = 0; i < 4; ++i) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < kTokens; ++j) {
+                        const float4 k4 = *(const float4*)AB_AT(ka, kb, j, i);
+                        a.x = fmaf(ds[j], k4.x, a.x); a.y = fmaf(ds[j], k4.y, a.y);
+                        a.z = fmaf(ds[j], k4.z, a.z); a.w = fmaf(ds[j], k4.w, a.w);
+                    }
+                    *(float4*)(ol + 4 * (i ^ lx)) = a;
                 }
-                *cell(sV, lane, c) = a;
             }
         }
         __syncwarp();  // this warp's K columns are free now: dK overwrites them; lane j = key row j, column j of dS / P
         if (lane < kTokens) {
 #pragma unroll
             for (int i = 0; i < kTokens; ++i) ds[i] = sDS[i * AB_PS + lane];
-#pragma unroll 2
-            for (int cc = 0; cc < HV4; ++cc) {
-                const int c = c_lo + cc;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int g = 0; g < 3; ++g) {
+                const float* qa = sQ + 32 * g + 16 * half;
+                const float* qb = sQ + 32 * g + 16 * (half ^ 1);
+                float* ol = sK + lrow + 32 * g;
 #pragma unroll
-                for (int i = 0; i < kTokens; ++i) {
-                    const float4 q4 = *cell(sQ, i, c);
-                    a.x = fmaf(ds[i], q4.x, a.x); a.y = fmaf(ds[i], q4.y, a.y);
-                    a.z = fmaf(ds[i], q4.z, a.z); a.w = fmaf(ds[i], q4.w, a.w);
+                for (int c = 0; c < 4; ++c) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < kTokens; ++i) {
+                        const float4 q4 = *(const float4*)AB_AT(qa, qb, i, c);
+                        a.x = fmaf(ds[i], q4.x, a.x); a.y = fmaf(ds[i], q4.y, a.y);
+                        a.z = fmaf(ds[i], q4.z, a.z); a.w = fmaf(ds[i], q4.w, a.w);
+                    }
+                    *(float4*)(ol + 4 * (c ^ lx)) = a;
                 }
-                *cell(sK, lane, c) = a;
             }
         }
         __syncwarp();  // Q columns are free now: dV overwrites them
         if (lane < kTokens) {
 #pragma unroll
             for (int i = 0; i < kTokens; ++i) ds[i] = sP[i * AB_PS + lane];
-#pragma unroll 2
-            for (int cc = 0; cc < HV4; ++cc) {
-                const int c = c_lo + cc;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int g = 0; g < 3; ++g) {
+                const float* ga = sDO + 32 * g + 16 * half;
+                const float* gb = sDO + 32 * g + 16 * (half ^ 1);
+                float* ol = sQ + lrow + 32 * g;
 #pragma unroll
-                for (int i = 0; i < kTokens; ++i) {
-                    const float4 g4 = *cell(sDO, i, c);
-                    a.x = fmaf(ds[i], g4.x, a.x); a.y = fmaf(ds[i], g4.y, a.y);
-                    a.z = fmaf(ds[i], g4.z, a.z); a.w = fmaf(ds[i], g4.w, a.w);
+                for (int c = 0; c < 4; ++c) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < kTokens; ++i) {
+                        const float4 g4 = *(const float4*)AB_AT(ga, gb, i, c);
+                        a.x = fmaf(ds[i], g4.x, a.x); a.y = fmaf(ds[i], g4.y, a.y);
+                        a.z = fmaf(ds[i], g4.z, a.z); a.w = fmaf(ds[i], g4.w, a.w);
+                    }
+                    *(float4*)(ol + 4 * (c ^ lx)) = a;
                 }
-                *cell(sQ, lane, c) = a;
             }
         }
         __syncwarp();
         // dq (in sV) -> cols [0,576), dk (sK) -> [576,1152), dv (sQ) -> [1152,1728): this warp's 48 dims of the head
         for (int idx = lane; idx < 3 * kTokens * HV4; idx += 32) {
-            const int m = idx / HV4, c = c_lo + (idx - m * HV4);
+            const int m = idx / HV4, c = own_col(idx - m * HV4);
             const int which = m / kTokens, row = m - which * kTokens;
             const float4 v = *cell(which == 0 ? sV : which == 1 ? sK : sQ, row, c);
             const size_t o = ((size_t)seq * kTokens + row) * LD + which * kDim + h * kHeadDim + 4 * c;
@@ -546,6 +584,300 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         }
         // the P / dS tiles are rewritten by the odd warp in the next iteration: both warps must be past their reads
         ab_bar(slot);
+    }
+}
+#undef AB_AT
+
+// ---------------------------------------------------------------- attention backward on the tensor cores (mma.sync)
+// The SIMT kernel above is bound by the shared-memory return path: a lane-per-row dot product needs one LDS.128 per
+// four FMAs (2340 LDS.128 per (sequence, head) x 4 clk = the 888 us ncu measures).  Warp MMAs read every operand once
+// per 16x8x16 tile instead.  Same bf16 hi/lo split as the forward kernel (attention_mma_kernel, encoder_ops.cu) and
+// the GEMMs: each product = hi*hi + lo*hi + hi*lo, fp32 accumulate.
+//   S  = Q K^T, dP = dO V^T       A = rows of Q / dO, B = rows of K / V        (64-bit fragment reads, 6 k-steps)
+//   P  = softmax(S * scale), dS = P o (dP - rowsum(P o dP)) * scale            on the accumulator registers (quad shuffles)
+//   dQ = dS K                      A = dS straight from the accumulators (flash-attention style), B = K by key pairs
+//   dK = dS^T Q, dV = P^T dO       A = the transposed tiles, through a 19x20 fp32 tile in shared memory
+// TWO warps per (sequence, head) share one staged copy of Q, K, V, dO: warp w takes k-steps 3w..3w+2 of S / dP (the
+// partial accumulators meet through two small tiles) and half of the 12 output n-tiles of dQ, dK, dV — 12 warps per
+// SM instead of 6 for the same shared memory (the first, one-warp version: 696 us, latency-bound at 1.5 warps per
+// scheduler).  Independent accumulators are interleaved between the three split terms so that dependent MMAs are
+// 6-8 instructions apart.  Row stride 104 floats makes the 64-bit row reads conflict-free; the key-pair (column)
+// reads are 2-way conflicted.
+constexpr int ABM_STRIDE = 104;
+constexpr int ABM_BUF = kTokens * ABM_STRIDE;
+constexpr int ABM_TILE = kTokens * AB_PS;
+constexpr int ABM_ITEM = 4 * ABM_BUF + 4 * ABM_TILE;  // floats per warp pair (37,696 B)
+constexpr int ABM_PAIRS = 6;
+constexpr int ABM_THREADS = ABM_PAIRS * 64;
+constexpr int ABM_SMEM = ABM_PAIRS * ABM_ITEM * (int)sizeof(float);  // 226,176 B
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(ABM_THREADS, 1)
+attention_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out, int64_t n_seq,
+                         __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo) {
+    extern __shared__ float4 ab_smem[];
+    constexpr int LD = 3 * kDim;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pair = threadIdx.x >> 6, w = (threadIdx.x >> 5) & 1, lane64 = threadIdx.x & 63;
+    float* sQ = reinterpret_cast<float*>(ab_smem) + pair * ABM_ITEM;
+    float* sK = sQ + ABM_BUF;
+    float* sV = sK + ABM_BUF;
+    float* sDO = sV + ABM_BUF;
+    float* tiles = sDO + ABM_BUF;                 // [warp][2][19][20]: partial S / dP of each warp
+    float* myS = tiles + w * 2 * ABM_TILE;
+    float* myDP = myS + ABM_TILE;
+    const float* otherS = tiles + (w ^ 1) * 2 * ABM_TILE;
+    const float* otherDP = otherS + ABM_TILE;
+    float* sP = tiles;                            // final P / dS: warp 0's tiles, rewritten after both warps read them
+    float* sDS = tiles + ABM_TILE;
+    const float scale = 0.10206207261596575f;
+    const int64_t items = n_seq * kHeads;
+    auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
+    // A / B fragments of "X rows" (row-major [19][96], k = head dim): 64-bit reads, rows past 18 are zero
+    auto row2 = [&](const float* buf, int row, int col) -> float2 {
+        return row < kTokens ? *(const float2*)(buf + row * ABM_STRIDE + col) : make_float2(0.f, 0.f);
+    };
+    // B fragments with k = token index (pairs of rows of one column), tokens past 18 are zero
+    auto col1 = [&](const float* buf, int row, int col) -> float { return row < kTokens ? buf[row * ABM_STRIDE + col] : 0.f; };
+    // transposed 19x19 tile element [k][m] (k = contraction index = tile row), zero outside
+    auto tile = [&](const float* tl, int k, int m) -> float { return (k < kTokens && m < kTokens) ? tl[k * AB_PS + m] : 0.f; };
+
+    // both warps of a pair run the same number of iterations (the barriers are per pair)
+    for (int64_t item = (int64_t)blockIdx.x * ABM_PAIRS + pair; item < items; item += (int64_t)gridDim.x * ABM_PAIRS) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
+        const float* dob = d_out + (size_t)seq * kTokens * kDim + h * kHeadDim;
+        for (int idx = lane64; idx < 4 * kTokens * (kHeadDim / 4); idx += 64) {
+            const int m = idx / (kHeadDim / 4), c = idx - m * (kHeadDim / 4);
+            const int which = m / kTokens, row = m - which * kTokens;
+            const float* src = which < 3 ? base + (size_t)row * LD + which * kDim + 4 * c : dob + (size_t)row * kDim + 4 * c;
+            float* dst = sQ + which * ABM_BUF + row * ABM_STRIDE + 4 * c;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        pair_bar();  // (1) the staged operands of both warps are visible
+
+        // ---- partial S = Q K^T and dP = dO V^T over this warp's 3 k-steps of 16 head dims:
+        // 2 m-tiles (rows 16mt+g, +8) x 3 n-tiles (keys 8nt+g)
+        float S[2][3][4], DP[2][3][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { S[mt][nt][e] = 0.f; DP[mt][nt][e] = 0.f; }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {          // pass 0: (Q, K) -> S; pass 1: (dO, V) -> dP
+            const float* A = pass == 0 ? sQ : sDO;
+            const float* B = pass == 0 ? sK : sV;
+#pragma unroll 1
+            for (int ks = 3 * w; ks < 3 * w + 3; ++ks) {
+                const int d0 = ks * 16 + 2 * t;
+                uint32_t ah[2][4], al[2][4], bh[3][2], bl[3][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const float2 x0 = row2(A, 16 * mt + g, d0), x1 = row2(A, 16 * mt + g + 8, d0);
+                    const float2 x2 = row2(A, 16 * mt + g, d0 + 8), x3 = row2(A, 16 * mt + g + 8, d0 + 8);
+                    split_pair(x0.x, x0.y, ah[mt][0], al[mt][0]);
+                    split_pair(x1.x, x1.y, ah[mt][1], al[mt][1]);
+                    split_pair(x2.x, x2.y, ah[mt][2], al[mt][2]);
+                    split_pair(x3.x, x3.y, ah[mt][3], al[mt][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    const float2 y0 = row2(B, 8 * nt + g, d0), y1 = row2(B, 8 * nt + g, d0 + 8);
+                    split_pair(y0.x, y0.y, bh[nt][0], bl[nt][0]);
+                    split_pair(y1.x, y1.y, bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            if (pass == 0) mma_16816(S[mt][nt], term == 1 ? al[mt] : ah[mt], term == 2 ? bl[nt] : bh[nt]);
+                            else mma_16816(DP[mt][nt], term == 1 ? al[mt] : ah[mt], term == 2 ? bl[nt] : bh[nt]);
+                        }
+            }
+        }
+        // ---- the two warps exchange their partial accumulators (e 0,1 -> row 16mt+g, e 2,3 -> row +8; cols 8nt+2t+e)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 16 * mt + g + 8 * (e >> 1), col = 8 * nt + 2 * t + (e & 1);
+                    if (row < kTokens && col < kTokens) {
+                        myS[row * AB_PS + col] = S[mt][nt][e];
+                        myDP[row * AB_PS + col] = DP[mt][nt][e];
+                    }
+                }
+        pair_bar();  // (2) partials written
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 16 * mt + g + 8 * (e >> 1), col = 8 * nt + 2 * t + (e & 1);
+                    if (row < kTokens && col < kTokens) {
+                        S[mt][nt][e] += otherS[row * AB_PS + col];
+                        DP[mt][nt][e] += otherDP[row * AB_PS + col];
+                    }
+                }
+        pair_bar();  // (3) partials consumed: warp 0's tiles may be overwritten with the final P / dS
+
+        // ---- P = softmax(S * scale), dS = P o (dP - rowsum(P o dP)) * scale; a row = the 4 lanes of a quad.
+        // S becomes P, DP becomes dS (both warps hold the full tiles; warp 0 publishes them).
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * nt + 2 * t + e;
+                        float v = S[mt][nt][2 * hrow + e] * scale;
+                        v = (col < kTokens) ? v : -INFINITY;
+                        S[mt][nt][2 * hrow + e] = v;
+                        m = fmaxf(m, v);
+                    }
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                float sum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = expf(S[mt][nt][2 * hrow + e] - m);  // exp(-inf) = 0 for the padding keys
+                        S[mt][nt][2 * hrow + e] = p;
+                        sum += p;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float inv = 1.f / sum;
+                float dsum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = S[mt][nt][2 * hrow + e] * inv;
+                        S[mt][nt][2 * hrow + e] = p;
+                        dsum = fmaf(p, DP[mt][nt][2 * hrow + e], dsum);   // p = 0 on the padding keys
+                    }
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                const int row = 16 * mt + g + 8 * hrow;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = S[mt][nt][2 * hrow + e];
+                        const float dsv = p * (DP[mt][nt][2 * hrow + e] - dsum) * scale;
+                        DP[mt][nt][2 * hrow + e] = dsv;
+                        const int col = 8 * nt + 2 * t + e;
+                        if (w == 0 && row < kTokens && col < kTokens) {
+                            sP[row * AB_PS + col] = p;
+                            sDS[row * AB_PS + col] = dsv;
+                        }
+                    }
+            }
+        pair_bar();  // (4) final P / dS tiles visible
+
+        // output rows of this item: (seq * 19 + row) * 1728 + which * 576 + h * 96 + d
+        auto store2 = [&](int which, int row, int d, float v0, float v1) {
+            if (row < kTokens) {
+                const size_t o = ((size_t)seq * kTokens + row) * LD + which * kDim + h * kHeadDim + d;
+                uint32_t hh, ll;
+                split_pair(v0, v1, hh, ll);
+                *(uint32_t*)(g_hi + o) = hh;
+                if (g_lo) *(uint32_t*)(g_lo + o) = ll;
+            }
+        };
+        // C[19 x 96] = A[19 x 19] B[19 x 96] with A fragments in registers ([mt][ks2][4], hi / lo), B = rows of `buf`
+        // taken by token pairs.  12 n-tiles of 8 head dims in 4 blocks of 3; this warp takes blocks 2w, 2w+1.
+        auto product = [&](const uint32_t (&ah)[2][2][4], const uint32_t (&al)[2][2][4], const float* buf, int which) {
+#pragma unroll 1
+            for (int blk = 2 * w; blk < 2 * w + 2; ++blk) {
+                float O[2][3][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) O[mt][j][e] = 0.f;
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ++ks2) {
+                    const int k0 = 16 * ks2 + 2 * t;
+                    uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int d = 8 * (3 * blk + j) + g;
+                        split_pair(col1(buf, k0, d), col1(buf, k0 + 1, d), bh[j][0], bl[j][0]);
+                        split_pair(col1(buf, k0 + 8, d), col1(buf, k0 + 9, d), bh[j][1], bl[j][1]);
+                    }
+#pragma unroll
+                    for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt)
+                                mma_16816(O[mt][j], term == 1 ? al[mt][ks2] : ah[mt][ks2], term == 2 ? bl[j] : bh[j]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int d = 8 * (3 * blk + j) + 2 * t;
+                        store2(which, 16 * mt + g, d, O[mt][j][0], O[mt][j][1]);
+                        store2(which, 16 * mt + g + 8, d, O[mt][j][2], O[mt][j][3]);
+                    }
+            }
+        };
+
+        uint32_t fh[2][2][4], fl[2][2][4];
+        // ---- dQ = dS K : dS as A fragments straight from the accumulators; k-step ks2 covers keys 16ks2 .. 16ks2+15 =
+        // n-tiles 2ks2, 2ks2+1 (n-tile 3 does not exist: keys 24..31 are padding)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            split_pair(DP[mt][0][0], DP[mt][0][1], fh[mt][0][0], fl[mt][0][0]);
+            split_pair(DP[mt][0][2], DP[mt][0][3], fh[mt][0][1], fl[mt][0][1]);
+            split_pair(DP[mt][1][0], DP[mt][1][1], fh[mt][0][2], fl[mt][0][2]);
+            split_pair(DP[mt][1][2], DP[mt][1][3], fh[mt][0][3], fl[mt][0][3]);
+            split_pair(DP[mt][2][0], DP[mt][2][1], fh[mt][1][0], fl[mt][1][0]);
+            split_pair(DP[mt][2][2], DP[mt][2][3], fh[mt][1][1], fl[mt][1][1]);
+            fh[mt][1][2] = fl[mt][1][2] = fh[mt][1][3] = fl[mt][1][3] = 0u;
+        }
+        product(fh, fl, sK, 0);
+        // ---- dK = dS^T Q and dV = P^T dO : A[m = key][k = query] = tile[query][key]
+        auto transposed = [&](const float* tl) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ++ks2) {
+                    const int k0 = 16 * ks2 + 2 * t, m0 = 16 * mt + g;
+                    split_pair(tile(tl, k0, m0), tile(tl, k0 + 1, m0), fh[mt][ks2][0], fl[mt][ks2][0]);
+                    split_pair(tile(tl, k0, m0 + 8), tile(tl, k0 + 1, m0 + 8), fh[mt][ks2][1], fl[mt][ks2][1]);
+                    split_pair(tile(tl, k0 + 8, m0), tile(tl, k0 + 9, m0), fh[mt][ks2][2], fl[mt][ks2][2]);
+                    split_pair(tile(tl, k0 + 8, m0 + 8), tile(tl, k0 + 9, m0 + 8), fh[mt][ks2][3], fl[mt][ks2][3]);
+                }
+        };
+        transposed(sDS);
+        product(fh, fl, sQ, 1);
+        transposed(sP);
+        product(fh, fl, sDO, 2);
+        pair_bar();  // (5) both warps are done with the staged operands and the tiles
     }
 }
 
@@ -921,7 +1253,20 @@ int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const Act
     static bool attr_set = false;
     if (!attr_set) {
         VETO_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        VETO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
+        VETO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
         attr_set = true;
+    }
+    static const bool simt_only = getenv("VETO_ATTN_BWD_SIMT") != nullptr;  // diagnosis: the fp32 SIMT kernel in every mode
+    if (d_qkv.hi && !d_qkv.f32 && !simt_only) {  // tensor-core modes: bf16 hi (+ lo) operands for the qkv weight / input gradients
+        const int64_t blocks = (n_seq * kHeads + ABM_PAIRS - 1) / ABM_PAIRS;
+        const int grid = (int)(blocks < num_sms() ? blocks : num_sms());
+        if (d_qkv.lo)
+            attention_bwd_mma_kernel<true><<<grid, ABM_THREADS, ABM_SMEM, s>>>(qkv, d_out, n_seq, d_qkv.hi, d_qkv.lo);
+        else
+            attention_bwd_mma_kernel<false><<<grid, ABM_THREADS, ABM_SMEM, s>>>(qkv, d_out, n_seq, d_qkv.hi, nullptr);
+        VETO_LAUNCH_CHECK();
+        return VETO_OK;
     }
     const int64_t blocks = (n_seq * kHeads + AB_ITEMS - 1) / AB_ITEMS;
     const int grid = (int)(blocks < num_sms() ? blocks : num_sms());
