@@ -176,7 +176,7 @@ attention_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, _
 // fully used); the softmax runs on the accumulator registers (a row lives in the 4 lanes of a quad) and P is
 // re-used from registers as the A operand of the second product, flash-attention style.  No shared memory.
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
+    asm(  // not volatile: a pure function of its operands, the scheduler may interleave independent accumulator chains
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -243,21 +243,21 @@ attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f3
                 split_pair(x2.x, x2.y, qh[mt][2], ql[mt][2]);
                 split_pair(x3.x, x3.y, qh[mt][3], ql[mt][3]);
             }
+            uint32_t kh[3][2], kl[3][2];
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
                 const float2 y0 = ld2(8 * nt + g, d0, 1), y1 = ld2(8 * nt + g, d0 + 8, 1);
-                uint32_t kh[2], kl[2];
-                split_pair(y0.x, y0.y, kh[0], kl[0]);
-                split_pair(y1.x, y1.y, kh[1], kl[1]);
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    mma_bf16_16816(S[mt][nt], qh[mt], kh);
-                    if (SPLIT) {
-                        mma_bf16_16816(S[mt][nt], ql[mt], kh);
-                        mma_bf16_16816(S[mt][nt], qh[mt], kl);
-                    }
-                }
+                split_pair(y0.x, y0.y, kh[nt][0], kl[nt][0]);
+                split_pair(y1.x, y1.y, kh[nt][1], kl[nt][1]);
             }
+            // split terms outermost: consecutive MMAs hit the 6 independent accumulators, dependent ones are 6 apart
+#pragma unroll
+            for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        mma_bf16_16816(S[mt][nt], term == 1 ? ql[mt] : qh[mt], term == 2 ? kl[nt] : kh[nt]);
         }
 
         // ---- softmax over the 19 keys of each row (a row = the 4 lanes of a quad; e 0,1 -> row g, e 2,3 -> row g+8)
@@ -318,23 +318,22 @@ attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f3
 #pragma unroll
                     for (int e = 0; e < 4; ++e) O[mt][j][e] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int d = 8 * (4 * nb + j) + g;
+            for (int ks2 = 0; ks2 < 2; ++ks2) {
+                const int k0 = 16 * ks2 + 2 * t;
+                uint32_t vh[4][2], vl[4][2];
 #pragma unroll
-                for (int ks2 = 0; ks2 < 2; ++ks2) {
-                    const int k0 = 16 * ks2 + 2 * t;
-                    uint32_t vh[2], vl[2];
-                    split_pair(ldv(k0, d), ldv(k0 + 1, d), vh[0], vl[0]);
-                    split_pair(ldv(k0 + 8, d), ldv(k0 + 9, d), vh[1], vl[1]);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_bf16_16816(O[mt][j], ph[mt][ks2], vh);
-                        if (SPLIT) {
-                            mma_bf16_16816(O[mt][j], pl[mt][ks2], vh);
-                            mma_bf16_16816(O[mt][j], ph[mt][ks2], vl);
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const int d = 8 * (4 * nb + j) + g;
+                    split_pair(ldv(k0, d), ldv(k0 + 1, d), vh[j][0], vl[j][0]);
+                    split_pair(ldv(k0 + 8, d), ldv(k0 + 9, d), vh[j][1], vl[j][1]);
                 }
+#pragma unroll
+                for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            mma_bf16_16816(O[mt][j], term == 1 ? pl[mt][ks2] : ph[mt][ks2], term == 2 ? vl[j] : vh[j]);
             }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
