@@ -314,9 +314,12 @@ int veto_postprocess(const float* rel_logits_dev, int num_rel, const int64_t* pa
  * retire the box.  scores_dev [N,num_obj] fp32 = softmax of the detector distribution (the caller computes it:
  * the reference feeds softmax(one_hot(pred_labels))); boxes_per_cls_dev [N,num_obj,4] fp32 xyxy;
  * box_offsets_dev int32 [n_images+1]; n_boxes_host [n_images]; labels_out_dev int64 [N].
+ * late_nms = 1 selects obj_prediction_nms (relation_head/utils_relation.py:94-128), the late NMS of
+ * PostProcessor.forward at SGDet test time (relation_head/inference.py:414-417): same rounds, but the background
+ * column counts as score 0 (not -1) and a box keeps its first assignment; scores = softmax(predict_logits).
  * One CTA per image with the score tile in shared memory: n * num_obj <= 56 320 (80 boxes x 151 classes = 12 080). */
 int veto_obj_nms_per_cls(const float* scores_dev, const float* boxes_per_cls_dev, const int32_t* box_offsets_dev,
-                         const int32_t* n_boxes_host, int n_images, int num_obj, float thresh,
+                         const int32_t* n_boxes_host, int n_images, int num_obj, float thresh, int late_nms,
                          int64_t* labels_out_dev, veto_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

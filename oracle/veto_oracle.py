@@ -407,3 +407,37 @@ def nms_per_cls(scores: np.ndarray, boxes_per_cls: Sequence[np.ndarray], n_boxes
             sampled[box_ind] = -1.0
         out.append(label)
     return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
+def obj_prediction_nms(scores: np.ndarray, boxes_per_cls: np.ndarray, thresh: float) -> np.ndarray:
+    """relation_head/utils_relation.py:94-128 for ONE image: `scores` = softmax(pred_logits) [n, C]."""
+    n = scores.shape[0]
+    is_overlap = nms_overlaps(boxes_per_cls) >= np.float32(thresh)
+    prob = scores.astype(np.float32).copy()
+    prob[:, 0] = 0
+    label = np.zeros(n, np.int64)
+    for _ in range(n):
+        box_ind, cls_ind = np.unravel_index(prob.argmax(), prob.shape)
+        if not label[int(box_ind)] > 0:
+            label[int(box_ind)] = int(cls_ind)
+        prob[is_overlap[box_ind, :, cls_ind], cls_ind] = 0.0
+        prob[box_ind] = -1.0
+    return label
+
+
+def postprocess_sgdet(rel_logits, obj_logits, pairs, boxes_per_cls, thresh: float, obj_scores_softmax=None):
+    """PostProcessor.forward, vanilla branch with use_gt_box False (relation_head/inference.py:398-453): per image
+    dict(obj_pred, obj_scores, boxes, pairs, probs, labels, triple), sorted by triple score (stable)."""
+    res = []
+    for i, (rl, ol, pr, bpc) in enumerate(zip(rel_logits, obj_logits, pairs, boxes_per_cls)):
+        op = softmax_rows(ol.astype(np.float32)) if obj_scores_softmax is None else obj_scores_softmax[i].copy()
+        op[:, 0] = 0
+        pred = obj_prediction_nms(op, bpc, thresh)
+        sc = op[np.arange(len(pred)), pred]
+        rp = softmax_rows(rl.astype(np.float32))
+        rs, rc = rp[:, 1:].max(1), rp[:, 1:].argmax(1) + 1
+        triple = rs * sc[pr[:, 0]] * sc[pr[:, 1]]
+        order = np.argsort(-triple, kind="stable")
+        res.append(dict(obj_pred=pred, obj_scores=sc, boxes=bpc[np.arange(len(pred)), pred], pairs=pr[order],
+                        probs=rp[order], labels=rc[order], triple=triple[order]))
+    return res

@@ -34,6 +34,10 @@ CASES = {
                     batch_seed=6, weight_seed=15, spread=True, H=320, W=416),
     # MEET at SGDet test time: obj_preds from the per-class greedy NMS (Ensemble.nms_per_cls, :3855-3874); detector
     # labels from 3 classes + jittered boxes_per_cls so that overlapping boxes compete for a class
+    # vanilla predictor + PostProcessor at SGDet test time: late per-class NMS (obj_prediction_nms) on peaked detector
+    # logits, boxes re-regressed per class (relation_head/inference.py:414-431)
+    "sgdet_post_nms": dict(predictor="VETOPredictor", mode="sgdet", dataset="VG", n_boxes=[12, 7],
+                           batch_seed=11, weight_seed=13, spread=True, H=320, W=416, nms_seed=4, nms_peak=3.0),
     "meet_sgdet_nms": dict(predictor="VETOPredictor_MEET", mode="sgdet", dataset="VG", n_boxes=[12, 7],
                            batch_seed=10, weight_seed=19, spread=True, H=320, W=416, nms_seed=3),
 }
@@ -78,7 +82,7 @@ def case_batch(c, features=True):
     batch = synth.make_batch(c["batch_seed"], c["n_boxes"], H=c.get("H", 592), W=c.get("W", 800),
                              num_obj=ds["num_obj"], mode=c["mode"], features=features)
     if "nms_seed" in c:
-        synth.add_nms_fields(batch, c["nms_seed"])
+        synth.add_nms_fields(batch, c["nms_seed"], peak=c.get("nms_peak", 0.0))
     return batch
 
 

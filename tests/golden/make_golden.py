@@ -47,7 +47,7 @@ def run_case(ns, name, c):
     fe = ns.make_extractor(cfg, 256, for_relation=True).eval()
     samp, post = ns.make_sampler(cfg), ns.make_post(cfg)
     out = {}
-    if "nms_seed" in c:
+    if "nms_seed" in c and meet:
         # record what Ensemble.nms_per_cls saw and returned (its softmax input is computed per image on CPU torch)
         real_nms = pred.model.nms_per_cls
         def _nms(obj_dists, boxes_per_cls, num_objs):
@@ -63,7 +63,7 @@ def run_case(ns, name, c):
         x2d, d2d, _, _ = fe(feats, bls, depth_features=torch.from_numpy(batch["depth"]))
         obj_d, rel_d, losses, incre, chosen, custom = pred(bls, pairs, None, None, roi_features=x2d,
                                                           roi_depth_features=d2d)
-    if "nms_seed" in c:
+    if "nms_seed" in c and meet:
         changed = int((out["nms_labels"] != np.concatenate(batch["pred_labels"])).sum())
         print(f"{name}: per-class NMS changed {changed} of {len(out['nms_labels'])} labels")
         assert changed >= 2, "the NMS case must exercise suppression"
@@ -82,6 +82,22 @@ def run_case(ns, name, c):
         out["incre_idx_list"] = np.array(incre)
     else:
         out["logits"] = np.concatenate([r.numpy() for r in rel_d])
+        if c["mode"] == "sgdet" and "nms_seed" in c:
+            # SGDet branch of the vanilla post-processor (inference.py:414-431): late NMS + per-class box regression
+            cfg.merge_from_list(["TEST.RELATION.LATER_NMS_PREDICTION_THRES", 0.5])
+            post = ns.make_post(cfg)
+            obj_logits = [b.get_field("predict_logits") for b in bls]
+            out["post_obj_prob"] = np.concatenate([torch.softmax(l, -1).numpy() for l in obj_logits])
+            res = post((rel_d, obj_logits), pairs, bls)
+            out["post_obj_labels"] = np.concatenate([r.get_field("pred_labels").numpy() for r in res])
+            out["post_obj_scores"] = np.concatenate([r.get_field("pred_scores").numpy() for r in res])
+            out["post_boxes"] = np.concatenate([r.bbox.numpy() for r in res])
+            out["post_pairs"] = np.concatenate([r.get_field("rel_pair_idxs").numpy() for r in res])
+            out["post_labels"] = np.concatenate([r.get_field("pred_rel_labels").numpy() for r in res])
+            out["post_scores"] = np.concatenate([r.get_field("pred_rel_scores").numpy()[:, 1:].max(1) for r in res])
+            changed = int((out["post_obj_labels"] != np.concatenate(batch["pred_labels"])).sum())
+            print(f"{name}: late NMS changed {changed} of {len(out['post_obj_labels'])} labels")
+            assert changed >= 2
         if c["mode"] == "predcls":
             res = post((rel_d, [b.get_field("predict_logits") for b in bls]), pairs, bls)
             out["post_pairs"] = np.concatenate([r.get_field("rel_pair_idxs").numpy() for r in res])

@@ -299,6 +299,55 @@ def test_meet_per_class_nms_bit_exact():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_sgdet_postprocess_late_nms(precision):
+    """PostProcessor at SGDet test time (inference.py:398-453 with use_gt_box False): object labels from the late
+    per-class NMS (obj_prediction_nms), scores, per-class regressed boxes and the triple ranking against the
+    unmodified reference; the NMS kernel bit-exact on the reference's own softmax tile and on larger seeded cases."""
+    name = "sgdet_post_nms"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    bpc = _t(np.concatenate(batch["boxes_per_cls"]))
+    prob = g["post_obj_prob"].copy()
+    got = H.np_(ops.obj_nms_per_cls(_t(prob), bpc, batch["n_boxes"], 0.5, late_nms=True))
+    assert np.array_equal(got, g["post_obj_labels"])
+    from veto_b200.postprocess import make_roi_relation_post_processor
+    cfg = H.make_cfg("VETOPredictor", "sgdet", precision=precision)
+    cfg.TEST.RELATION.LATER_NMS_PREDICTION_THRES = 0.5
+    res = make_roi_relation_post_processor(cfg)((out[1], [b.get_field("predict_logits") for b in bls]), pairs, bls)
+    assert np.array_equal(np.concatenate([H.np_(r.get_field("pred_labels")) for r in res]), g["post_obj_labels"])
+    assert np.allclose(np.concatenate([H.np_(r.get_field("pred_scores")) for r in res]), g["post_obj_scores"], rtol=1e-5)
+    assert np.array_equal(np.concatenate([H.np_(r.bbox) for r in res]), g["post_boxes"])
+    assert all(not r.has_field("boxes_per_cls") for r in res)          # a NEW BoxList (inference.py:431)
+    pp = np.concatenate([H.np_(r.get_field("rel_pair_idxs")) for r in res])
+    labels = np.concatenate([H.np_(r.get_field("pred_rel_labels")) for r in res])
+    trip = np.concatenate([H.np_(r.get_field("triple_scores")) for r in res]).astype(np.float64)
+    # rows whose triple score is separated from its neighbours by more than the logit tolerance must agree
+    gap = np.full(len(trip), np.inf)
+    off = 0
+    for n in g["pair_counts"]:
+        t = trip[off:off + n]
+        assert np.all(np.diff(t) <= 0)
+        gp = np.full(n, np.inf)
+        gp[1:] = np.minimum(gp[1:], t[:-1] - t[1:])
+        gp[:-1] = np.minimum(gp[:-1], t[:-1] - t[1:])
+        gap[off:off + n] = gp
+        off += n
+    clear = gap > 4e-3 * trip
+    assert clear.mean() > 0.5
+    assert np.array_equal(pp[clear], g["post_pairs"][clear]) and np.array_equal(labels[clear], g["post_labels"][clear])
+    # larger seeded cases against the numpy oracle, generic soft scores
+    for seed, n_boxes, thr in ((5, [80, 0, 33, 1], 0.5), (6, [64] * 4, 0.3)):
+        b = synth.make_batch(seed, n_boxes, H=592, W=800, mode="sgdet", features=False)
+        synth.add_nms_fields(b, seed + 10, n_classes=4, jitter=12.0, peak=2.0)
+        ref, got_all, o = [], [], 0
+        scores = np.concatenate([O.softmax_rows(l) for l in b["predict_logits"] if len(l)])
+        for l, bx in zip(b["predict_logits"], b["boxes_per_cls"]):
+            if len(l):
+                ref.append(O.obj_prediction_nms(O.softmax_rows(l), bx, thr))
+        got = H.np_(ops.obj_nms_per_cls(_t(scores), _t(np.concatenate(b["boxes_per_cls"])), b["n_boxes"], thr, late_nms=True))
+        assert np.array_equal(got, np.concatenate(ref)), seed
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_top50_ranking_and_postprocess(precision):
     """PostProcessor parity: triple scores, and the top-50 triplet ranking of the reference (tie-aware)."""
     name = "cfg1_predcls_vg"

@@ -104,7 +104,28 @@ def test_logits(case):
     if "tokens" in g.files:
         tok = O.tokens_only(sd, batch, pairs, x2d, d2d, c["mode"])[g["token_rows"]]
         assert np.abs(tok - g["tokens"]).max() <= REL_TOL * np.abs(g["tokens"]).max()
-    if "post_pairs" in g.files:
+    if "post_obj_labels" in g.files:
+        # SGDet branch of the post-processor (inference.py:414-431): late per-class NMS on the reference's own softmax
+        # tile, per-class box regression, triple ranking
+        split = np.cumsum([len(p) for p in pairs])[:-1]
+        bsplit = np.cumsum(batch["n_boxes"])[:-1]
+        res = O.postprocess_sgdet(np.split(ref, split), batch["predict_logits"], pairs, batch["boxes_per_cls"], 0.5,
+                                  obj_scores_softmax=np.split(g["post_obj_prob"], bsplit))
+        assert np.array_equal(np.concatenate([r["obj_pred"] for r in res]), g["post_obj_labels"])
+        assert (g["post_obj_labels"] != np.concatenate(batch["pred_labels"])).sum() >= 2
+        assert np.array_equal(np.concatenate([r["obj_scores"] for r in res]), g["post_obj_scores"])
+        assert np.array_equal(np.concatenate([r["boxes"] for r in res]), g["post_boxes"])
+        s = np.concatenate([r["triple"] for r in res])
+        distinct = np.ones(len(s), bool)
+        distinct[1:] &= s[1:] != s[:-1]
+        distinct[:-1] &= s[:-1] != s[1:]
+        assert np.array_equal(np.concatenate([r["pairs"] for r in res])[distinct], g["post_pairs"][distinct])
+        assert np.array_equal(np.concatenate([r["labels"] for r in res])[distinct], g["post_labels"][distinct])
+        assert np.allclose(np.concatenate([r["probs"] for r in res])[:, 1:].max(1), g["post_scores"], rtol=1e-5)
+        # the numpy softmax of the oracle gives the same labels as the reference's torch softmax on this case
+        res2 = O.postprocess_sgdet(np.split(ref, split), batch["predict_logits"], pairs, batch["boxes_per_cls"], 0.5)
+        assert np.array_equal(np.concatenate([r["obj_pred"] for r in res2]), g["post_obj_labels"])
+    elif "post_pairs" in g.files:
         obj_logits, off = [], 0
         for lab in batch["labels"]:
             ol = np.full((len(lab), batch["num_obj"]), -1000.0, np.float32)    # to_onehot, model_kern.py:266-281

@@ -7,6 +7,9 @@
 //            (3) scores[j, cls] = 0 for every box j whose class-`cls` box overlaps box `box`'s by IoU >= thresh —
 //                the one [n] column of the overlap tensor that round needs, computed on the fly,
 //            (4) scores[box, :] = -1.
+// The same kernel serves obj_prediction_nms (relation_head/utils_relation.py:94-128), the late NMS of the vanilla
+// post-processor at SGDet test time (inference.py:414-417): background column 0 instead of -1, and a box keeps its
+// first assignment.
 // The IoU uses the reference's +1 convention and operation order with explicit round-to-nearest intrinsics (no FMA
 // contraction), so the >= thresh decision is bit-identical to the fp32 torch expression.
 #include "stages.cuh"
@@ -22,7 +25,7 @@ __device__ __forceinline__ float box_area(const float4 b) {
 
 __global__ void __launch_bounds__(NMS_THREADS)
 obj_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes_per_cls, const int32_t* __restrict__ box_off,
-               int num_obj, float thresh, int64_t* __restrict__ labels_out) {
+               int num_obj, float thresh, int late_nms, int64_t* __restrict__ labels_out) {
     extern __shared__ float s_scores[];  // [n, num_obj]
     __shared__ float red_v[NMS_THREADS / 32];
     __shared__ int red_i[NMS_THREADS / 32];
@@ -33,7 +36,8 @@ obj_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int e = tid; e < total; e += NMS_THREADS) {
         const int c = e % num_obj;
-        s_scores[e] = c == 0 ? -1.f : scores[(size_t)b0 * num_obj + e];  // out_dists_sampled[:, 0] = -1
+        // background column: out_dists_sampled[:, 0] = -1 (nms_per_cls) / prob_sampled[:, 0] = 0 (obj_prediction_nms)
+        s_scores[e] = c == 0 ? (late_nms ? 0.f : -1.f) : scores[(size_t)b0 * num_obj + e];
     }
     for (int j = tid; j < n; j += NMS_THREADS) labels_out[b0 + j] = 0;
     __syncthreads();
@@ -72,7 +76,8 @@ obj_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes
             const float uni = __fadd_rn(__fadd_rn(-inter, box_area(q)), area_a);
             if (__fdiv_rn(inter, uni) >= thresh) s_scores[j * num_obj + cls] = 0.f;
         }
-        if (tid == 0) labels_out[b0 + box] = cls;
+        // obj_prediction_nms keeps the first (highest-probability) assignment of a box (utils_relation.py:119-123)
+        if (tid == 0 && !(late_nms && labels_out[b0 + box] > 0)) labels_out[b0 + box] = cls;
         __syncthreads();
         // (4) the picked box leaves the pool
         for (int c = tid; c < num_obj; c += NMS_THREADS) s_scores[box * num_obj + c] = -1.f;
@@ -86,7 +91,7 @@ obj_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes
 using namespace veto;
 
 extern "C" int veto_obj_nms_per_cls(const float* scores_dev, const float* boxes_per_cls_dev, const int32_t* box_offsets_dev,
-                                    const int32_t* n_boxes_host, int n_images, int num_obj, float thresh,
+                                    const int32_t* n_boxes_host, int n_images, int num_obj, float thresh, int late_nms,
                                     int64_t* labels_out_dev, veto_stream_t stream) {
     VETO_REQUIRE(scores_dev && boxes_per_cls_dev && box_offsets_dev && n_boxes_host && labels_out_dev && n_images >= 0 && num_obj > 1,
                  VETO_ERR_ARG, "veto_obj_nms_per_cls: bad arguments");
@@ -100,7 +105,7 @@ extern "C" int veto_obj_nms_per_cls(const float* scores_dev, const float* boxes_
     cudaStream_t s = (cudaStream_t)stream;
     VETO_CUDA(cudaFuncSetAttribute(obj_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set_tag(TAG_PAIRS);
-    obj_nms_kernel<<<n_images, NMS_THREADS, smem, s>>>(scores_dev, boxes_per_cls_dev, box_offsets_dev, num_obj, thresh, labels_out_dev);
+    obj_nms_kernel<<<n_images, NMS_THREADS, smem, s>>>(scores_dev, boxes_per_cls_dev, box_offsets_dev, num_obj, thresh, late_nms, labels_out_dev);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -406,9 +406,11 @@ def dropout_keep_mask(seed: int, sub: int, n: int, p: float):
 # --------------------------------------------------------------------------------------------
 # a10: MEET's per-class NMS label assignment (SGDet test)
 # --------------------------------------------------------------------------------------------
-def obj_nms_per_cls(scores: torch.Tensor, boxes_per_cls: torch.Tensor, n_boxes: Sequence[int], thresh: float) -> torch.Tensor:
-    """Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874): scores [N,num_obj] fp32 (softmax of the object
-    distribution), boxes_per_cls [N,num_obj,4]; returns int64 labels [N].  One kernel launch for the whole batch."""
+def obj_nms_per_cls(scores: torch.Tensor, boxes_per_cls: torch.Tensor, n_boxes: Sequence[int], thresh: float,
+                    late_nms: bool = False) -> torch.Tensor:
+    """Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874), or with late_nms obj_prediction_nms
+    (relation_head/utils_relation.py:94-128): scores [N,num_obj] fp32 (softmax of the object distribution),
+    boxes_per_cls [N,num_obj,4]; returns int64 labels [N].  One kernel launch for the whole batch."""
     L.require_device()
     scores, boxes_per_cls = _cuda_f32(scores), _cuda_f32(boxes_per_cls)
     N, num_obj = scores.shape
@@ -421,7 +423,8 @@ def obj_nms_per_cls(scores: torch.Tensor, boxes_per_cls: torch.Tensor, n_boxes: 
         nb = (ctypes.c_int32 * len(n_boxes))(*[int(n) for n in n_boxes])
         with torch.cuda.device(dev):
             L.check(L.load().veto_obj_nms_per_cls(scores.data_ptr(), boxes_per_cls.data_ptr(), box_off.data_ptr(), nb,
-                                                  len(n_boxes), num_obj, float(thresh), out.data_ptr(), L.stream_ptr()),
+                                                  len(n_boxes), num_obj, float(thresh), int(bool(late_nms)), out.data_ptr(),
+                                                  L.stream_ptr()),
                     "veto_obj_nms_per_cls")
     return out
 

@@ -2,8 +2,10 @@
 (pysgg/modeling/roi_heads/relation_head/inference.py:398-453): softmax, max over predicate classes 1..,
 triple score, per-image descending sort — one launch for the whole batch (``veto_postprocess``).
 
-The reference's torch.sort is unstable; ties are broken by the original row (ascending).  The sgdet branch
-(late NMS over boxes_per_cls, :414-432) and the MEET ensemble branches (:93-397) are not built yet.
+The reference's torch.sort is unstable; ties are broken by the original row (ascending).  In SGDet mode
+(use_gt_box False) the object labels come from the late per-class NMS ``obj_prediction_nms`` (:414-417,
+``veto_obj_nms_per_cls`` with late_nms) and the boxes are re-regressed to the chosen class (:425-431).
+The MEET ensemble branches (:93-397) are not built yet.
 """
 from __future__ import annotations
 
@@ -11,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .structures import BoxList
 
 
 class PostProcessor(nn.Module):
@@ -23,8 +26,6 @@ class PostProcessor(nn.Module):
 
     def forward(self, x, rel_pair_idxs, boxes):
         relation_logits, refine_logits = x
-        if not self.use_gt_box:
-            raise NotImplementedError("sgdet post-processing (obj_prediction_nms) is not built yet")
         if isinstance(relation_logits, dict):
             raise NotImplementedError("MEET ensemble post-processing is not built yet")
         n_boxes = [len(b) for b in boxes]
@@ -32,14 +33,24 @@ class PostProcessor(nn.Module):
         obj_logit = torch.cat(list(refine_logits), 0)
         obj_prob = torch.softmax(obj_logit.float(), -1)
         obj_prob[:, 0] = 0  # :406
-        obj_scores, obj_pred = obj_prob[:, 1:].max(dim=1)
-        obj_pred = obj_pred + 1
+        boxes_per_cls = None
+        if self.use_gt_box:
+            obj_scores, obj_pred = obj_prob[:, 1:].max(dim=1)
+            obj_pred = obj_pred + 1
+        else:  # :414-417, late NMS for the object prediction
+            boxes_per_cls = torch.cat([b.get_field("boxes_per_cls") for b in boxes], 0)
+            obj_pred = ops.obj_nms_per_cls(obj_prob, boxes_per_cls, n_boxes, self.later_nms_pred_thres, late_nms=True)
+            obj_scores = obj_prob.gather(1, obj_pred[:, None])[:, 0]
         pairs_o, probs_o, labels_o, triple_o = ops.postprocess(torch.cat(list(relation_logits), 0),
                                                                torch.cat(list(rel_pair_idxs), 0), obj_scores,
                                                                rel_counts, n_boxes)
         results, ro, bo = [], 0, 0
         for box, nb, nr in zip(boxes, n_boxes, rel_counts):
-            bl = box  # the reference adds the result fields to the input BoxList too (:431-452)
+            if self.use_gt_box:
+                bl = box  # the reference adds the result fields to the input BoxList too (:431-452)
+            else:         # sgdet: boxes regressed for the finetuned class (:425-431); a NEW BoxList without the input's fields
+                cls = obj_pred[bo:bo + nb]
+                bl = BoxList(boxes_per_cls[bo:bo + nb][torch.arange(nb, device=cls.device), cls], box.size, "xyxy")
             bl.add_field("pred_labels", obj_pred[bo:bo + nb])
             bl.add_field("pred_scores", obj_scores[bo:bo + nb])
             bl.add_field("rel_pair_idxs", pairs_o[ro:ro + nr])
