@@ -305,6 +305,23 @@ int veto_postprocess(const float* rel_logits_dev, int num_rel, const int64_t* pa
                      int64_t* pairs_out_dev, float* probs_out_dev, int64_t* labels_out_dev,
                      float* triple_out_dev, veto_stream_t stream);
 
+/* f1. PostProcessor.forward, MEET 'ensemble' branch (ENSEMBLE_LEARNING.ENABLED, EXPERT_GROUP False;
+ * relation_head/inference.py:284-397).  group_logits_dev [R,num_out]: the group heads' logits side by side (head k =
+ * columns head_offsets[k] .. head_offsets[k+1], n_k + 2 of them: background, the n_k member predicates, out-of-group).
+ * Per image and head: softmax over the head's columns, the out-of-group column dropped, score / head-local label = max
+ * over the member columns, triple = score * obj_s * obj_o; the image's G*R_i candidate rows (group-major) are ranked by
+ * triple score descending (ties: merged index ascending) and each row's probabilities are scattered into the global
+ * predicate columns col_map_dev[num_out] (head column -> global predicate id; the dropped columns are never read).
+ * Outputs are image-segmented with G*R_i rows per image at row offset G*rel_offsets[i]: pairs int64 [G*R,2]
+ * (the reference stores them in a float32 tensor, :380), probabilities [G*R,num_rel], head-local labels int64 [G*R]
+ * (:371,388), triple scores [G*R].  One image is sorted in shared memory: G*R_i <= 16384.
+ * The reference consumes image 0 only (TEST.IMS_PER_BATCH 1); this entry point handles a batch. */
+int veto_postprocess_meet(const float* group_logits_dev, int num_out, const int32_t* head_offsets_dev, int n_heads,
+                          const int32_t* col_map_dev, int num_rel, const int64_t* pairs_dev,
+                          const float* obj_scores_dev, const int32_t* rel_offsets_dev,
+                          const int32_t* box_offsets_dev, int n_images, int64_t n_pairs, int64_t* pairs_out_dev,
+                          float* probs_out_dev, int64_t* labels_out_dev, float* triple_out_dev, veto_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a10. Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874) with nms_overlaps
  * (relation_head/utils_relation.py:56-79): MEET's greedy per-class label assignment at SGDet test time.

@@ -441,3 +441,28 @@ def postprocess_sgdet(rel_logits, obj_logits, pairs, boxes_per_cls, thresh: floa
         res.append(dict(obj_pred=pred, obj_scores=sc, boxes=bpc[np.arange(len(pred)), pred], pairs=pr[order],
                         probs=rp[order], labels=rc[order], triple=triple[order]))
     return res
+
+
+def postprocess_meet(group_logits: Dict[str, np.ndarray], obj_logits: np.ndarray, pairs: np.ndarray, incre_idx: Sequence[int]):
+    """PostProcessor.forward, 'ensemble' branch (relation_head/inference.py:284-397) for ONE image in PredCls / SGCls
+    mode (use_gt_box): returns dict(pairs [G*R,2], probs [G*R,num_rel], labels [G*R] head-local, triple [G*R]) ranked by
+    triple score (stable)."""
+    op = softmax_rows(obj_logits.astype(np.float32))
+    op[:, 0] = 0
+    sc = op[:, 1:].max(1)
+    num_rel = len(incre_idx)
+    triple, prs, labs, probs = [], [], [], []
+    for k in range(len(group_logits)):
+        p = softmax_rows(group_logits["group_%d" % k].astype(np.float32))[:, :-1]
+        rs, rc = p[:, 1:].max(1), p[:, 1:].argmax(1) + 1
+        cols = [0] + [i for i, g in enumerate(incre_idx) if g == k + 1]
+        full = np.zeros((len(p), num_rel), np.float32)
+        full[:, cols] = p
+        triple.append(rs * sc[pairs[:, 0]] * sc[pairs[:, 1]])
+        prs.append(pairs)
+        labs.append(rc)
+        probs.append(full)
+    triple = np.concatenate(triple)
+    order = np.argsort(-triple, kind="stable")
+    return dict(pairs=np.concatenate(prs)[order], probs=np.concatenate(probs)[order], labels=np.concatenate(labs)[order],
+                triple=triple[order])

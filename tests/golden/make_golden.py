@@ -80,6 +80,19 @@ def run_case(ns, name, c):
         for k, v in rel_d.items():
             out["logits_" + k] = v.numpy()
         out["incre_idx_list"] = np.array(incre)
+        if c["mode"] == "predcls" and batch["B"] == 1:
+            # MEET 'ensemble' branch of the post-processor (inference.py:284-397); its hard-coded .cuda() calls are
+            # neutralised for the CPU run, nothing else is touched
+            real_cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            try:
+                res = post((rel_d, [b.get_field("predict_logits") for b in bls]), pairs, bls, incre_idx_list=incre)
+            finally:
+                torch.Tensor.cuda = real_cuda
+            r0 = res[0]
+            out["mpost_pairs"] = r0.get_field("rel_pair_idxs").numpy()
+            out["mpost_probs"] = r0.get_field("pred_rel_scores").numpy()
+            out["mpost_labels"] = r0.get_field("pred_rel_labels").numpy()
     else:
         out["logits"] = np.concatenate([r.numpy() for r in rel_d])
         if c["mode"] == "sgdet" and "nms_seed" in c:

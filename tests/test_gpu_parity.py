@@ -299,6 +299,55 @@ def test_meet_per_class_nms_bit_exact():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_meet_postprocess_ensemble_merge(precision):
+    """PostProcessor MEET 'ensemble' branch (inference.py:284-397): the merged, ranked candidate list of the unmodified
+    reference for a one-image batch (the only thing it supports), and the batch generalisation against the oracle."""
+    from veto_b200.postprocess import make_roi_relation_post_processor
+    name = "meet_vg"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    cfg = H.make_cfg("VETOPredictor_MEET", "predcls", "VG", precision=precision)
+    post = make_roi_relation_post_processor(cfg)
+    res = post((out[1], [b.get_field("predict_logits") for b in bls]), pairs, bls, incre_idx_list=out[3])
+    assert len(res) == 1
+    pp, probs = H.np_(res[0].get_field("rel_pair_idxs")), H.np_(res[0].get_field("pred_rel_scores"))
+    labels, trip = H.np_(res[0].get_field("pred_rel_labels")), H.np_(res[0].get_field("triple_scores")).astype(np.float64)
+    assert pp.dtype == np.float32 and pp.shape == g["mpost_pairs"].shape and probs.shape == g["mpost_probs"].shape
+    assert np.all(np.diff(trip) <= 0)
+    gap = np.full(len(trip), np.inf)
+    gap[1:] = np.minimum(gap[1:], trip[:-1] - trip[1:])
+    gap[:-1] = np.minimum(gap[:-1], trip[:-1] - trip[1:])
+    # rows whose score is separated from both neighbours by more than the mode's logit error must sit at the same rank
+    clear = gap > {"fp32": 2e-5, "bf16x3": 4e-4}[precision] * trip
+    assert clear.mean() > 0.3, clear.mean()
+    assert np.array_equal(pp[clear], g["mpost_pairs"][clear]) and np.array_equal(labels[clear], g["mpost_labels"][clear])
+    assert np.abs(probs[clear] - g["mpost_probs"][clear]).max() <= TOL[precision]
+    assert np.array_equal(probs[clear] != 0, g["mpost_probs"][clear] != 0)          # global-column scatter pattern
+    # evaluation re-derives the global label from the scattered probabilities (sgg_eval.py:150): same as the reference's
+    assert np.array_equal(probs[clear][:, 1:].argmax(1), g["mpost_probs"][clear][:, 1:].argmax(1))
+    # batch of two images: per image identical to the oracle's single-image merge of OUR logits
+    name = "meet_gqa"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    cfg = H.make_cfg("VETOPredictor_MEET", "predcls", "GQA", precision=precision)
+    res = make_roi_relation_post_processor(cfg)((out[1], [b.get_field("predict_logits") for b in bls]), pairs, bls,
+                                                incre_idx_list=out[3])
+    off = 0
+    for i, r in enumerate(res):
+        n = len(pairs[i])
+        gl = {k: H.np_(v)[off:off + n] for k, v in out[1].items()}
+        off += n
+        ora = O.postprocess_meet(gl, H.np_(bls[i].get_field("predict_logits")), H.np_(pairs[i]), list(out[3]))
+        s = ora["triple"].astype(np.float64)
+        gap = np.full(len(s), np.inf)
+        gap[1:] = np.minimum(gap[1:], s[:-1] - s[1:])
+        gap[:-1] = np.minimum(gap[:-1], s[:-1] - s[1:])
+        clear = gap > 1e-5 * s
+        assert len(s) == 4 * n and clear.mean() > 0.5
+        assert np.array_equal(H.np_(r.get_field("rel_pair_idxs"))[clear].astype(np.int64), ora["pairs"][clear])
+        assert np.array_equal(H.np_(r.get_field("pred_rel_labels"))[clear], ora["labels"][clear])
+        assert np.abs(H.np_(r.get_field("pred_rel_scores"))[clear] - ora["probs"][clear]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_sgdet_postprocess_late_nms(precision):
     """PostProcessor at SGDet test time (inference.py:398-453 with use_gt_box False): object labels from the late
     per-class NMS (obj_prediction_nms), scores, per-class regressed boxes and the triple ranking against the

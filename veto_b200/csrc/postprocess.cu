@@ -107,6 +107,106 @@ postprocess_kernel(const float* __restrict__ logits, int num_rel, const int64_t*
     }
 }
 
+// PostProcessor.forward, MEET 'ensemble' branch (EXPERT_GROUP False, relation_head/inference.py:284-397), one CTA per
+// image.  Every group head k scores every pair: softmax over the head's n_k + 2 columns, the last (out-of-group) column
+// is dropped (:345-346), rel_score / rel_class = max over the head's member columns 1..n_k; the reference's "chosen"
+// filter (:356-361) keeps every row (rel_class is by construction one of the members), so the image's merged list has
+// G * R rows, group-major.  It is ranked by triple score (ties: merged index ascending) and each row's probabilities
+// are scattered from head-local into global predicate columns (chosen_labels_incr, :387), zeros elsewhere; the label
+// stays head-local like the reference's (:371,388).
+__global__ void __launch_bounds__(1024)
+meet_postprocess_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ head_off, int n_heads,
+                        const int32_t* __restrict__ col_map, int num_rel, const int64_t* __restrict__ pairs,
+                        const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off,
+                        const int32_t* __restrict__ box_off, int64_t* __restrict__ pairs_out, float* __restrict__ probs_out,
+                        int64_t* __restrict__ labels_out, float* __restrict__ triple_out) {
+    extern __shared__ unsigned long long keys[];  // [npow]
+    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
+    float* trip = (float*)(lab + kMaxRows);
+    const int b = blockIdx.x;
+    const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
+    const int merged = rows * n_heads;
+    if (merged <= 0) return;
+    if (merged > kMaxRows) {
+        if (threadIdx.x == 0) printf("veto_postprocess_meet: image %d has %d merged rows > %d\n", b, merged, kMaxRows);
+        __trap();
+    }
+    const int boff = box_off[b];
+    const size_t out0 = (size_t)r0 * n_heads;  // merged rows of the images before this one
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int npow = 1;
+    while (npow < merged) npow <<= 1;
+
+    for (int q = wid; q < merged; q += nw) {
+        const int k = q / rows, r = q - k * rows;
+        const int c0 = head_off[k], nc = head_off[k + 1] - c0;   // n_k + 2 columns
+        const float* lg = logits + (size_t)(r0 + r) * ld + c0;
+        float m = -INFINITY;
+        for (int c = lane; c < nc; c += 32) m = fmaxf(m, lg[c]);
+        m = wmax(m);
+        float sum = 0.f, best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+            const float e = expf(lg[c] - m);
+            sum += e;
+            if (c >= 1 && c < nc - 1 && e > best) { best = e; besti = c; }
+        }
+        sum = wsum(sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) {
+            const float score = best / sum;
+            const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
+            const float t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
+            unsigned int u = __float_as_uint(t);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
+            lab[q] = (unsigned short)besti;
+            trip[q] = t;
+        }
+    }
+    for (int q = merged + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int q = threadIdx.x; q < npow; q += blockDim.x) {
+                const int p = q ^ j;
+                if (p > q) {
+                    const unsigned long long a = keys[q], c = keys[p];
+                    const bool up = ((q & k) == 0);
+                    if ((a > c) == up) { keys[q] = c; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int rank = wid; rank < merged; rank += nw) {
+        const int q = (int)(keys[rank] & 0xffffffffull);
+        const int k = q / rows, r = q - k * rows;
+        const int c0 = head_off[k], nc = head_off[k + 1] - c0;
+        const float* lg = logits + (size_t)(r0 + r) * ld + c0;
+        float m = -INFINITY;
+        for (int c = lane; c < nc; c += 32) m = fmaxf(m, lg[c]);
+        m = wmax(m);
+        float sum = 0.f;
+        for (int c = lane; c < nc; c += 32) sum += expf(lg[c] - m);
+        sum = wsum(sum);
+        float* po = probs_out + (out0 + rank) * num_rel;
+        for (int c = lane; c < num_rel; c += 32) po[c] = 0.f;
+        __syncwarp();
+        for (int c = lane; c < nc - 1; c += 32) po[col_map[c0 + c]] = expf(lg[c] - m) / sum;  // distinct global columns
+        if (lane == 0) {
+            *(longlong2*)(pairs_out + 2 * (out0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
+            labels_out[out0 + rank] = lab[q];
+            triple_out[out0 + rank] = trip[q];
+        }
+    }
+}
+
 }  // namespace
 }  // namespace veto
 
@@ -130,6 +230,31 @@ extern "C" int veto_postprocess(const float* rel_logits_dev, int num_rel, const 
     postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(rel_logits_dev, num_rel, pairs_dev, obj_scores_dev,
                                                                       rel_offsets_dev, box_offsets_dev, pairs_out_dev,
                                                                       probs_out_dev, labels_out_dev, triple_out_dev);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+extern "C" int veto_postprocess_meet(const float* group_logits_dev, int num_out, const int32_t* head_offsets_dev, int n_heads,
+                                     const int32_t* col_map_dev, int num_rel, const int64_t* pairs_dev,
+                                     const float* obj_scores_dev, const int32_t* rel_offsets_dev,
+                                     const int32_t* box_offsets_dev, int n_images, int64_t n_pairs, int64_t* pairs_out_dev,
+                                     float* probs_out_dev, int64_t* labels_out_dev, float* triple_out_dev,
+                                     veto_stream_t stream) {
+    if (n_images <= 0 || n_pairs <= 0) return VETO_OK;
+    VETO_REQUIRE(group_logits_dev && head_offsets_dev && col_map_dev && pairs_dev && obj_scores_dev && rel_offsets_dev &&
+                     box_offsets_dev && pairs_out_dev && probs_out_dev && labels_out_dev && triple_out_dev && n_heads >= 1 &&
+                     num_out >= 3 * n_heads && num_rel >= 2 && num_rel < 65536,
+                 VETO_ERR_ARG, "veto_postprocess_meet: bad argument");
+    set_tag(TAG_POST);
+    static bool attr_set = false;
+    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
+    if (!attr_set) {
+        VETO_CUDA(cudaFuncSetAttribute(meet_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    meet_postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(
+        group_logits_dev, num_out, head_offsets_dev, n_heads, col_map_dev, num_rel, pairs_dev, obj_scores_dev, rel_offsets_dev,
+        box_offsets_dev, pairs_out_dev, probs_out_dev, labels_out_dev, triple_out_dev);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -458,6 +458,39 @@ def postprocess(rel_logits: torch.Tensor, pairs: torch.Tensor, obj_scores: torch
     return pairs_o, probs_o, labels_o, triple_o
 
 
+def postprocess_meet(group_logits: torch.Tensor, head_sizes: Sequence[int], col_map: Sequence[int], num_rel: int,
+                     pairs: torch.Tensor, obj_scores: torch.Tensor, rel_counts: Sequence[int], n_boxes: Sequence[int]):
+    """PostProcessor MEET 'ensemble' branch (inference.py:284-397) for a batch: group_logits [R, sum(n_k+2)], col_map =
+    global predicate id of every concatenated column.  Returns image-segmented (G*R_i rows per image): sorted pairs
+    int64 [G*R,2], probabilities [G*R,num_rel] in global columns, head-local labels [G*R], triple scores [G*R]."""
+    L.require_device()
+    group_logits, obj_scores = _cuda_f32(group_logits), _cuda_f32(obj_scores)
+    pairs = pairs.to(torch.int64).contiguous()
+    R, Ct = group_logits.shape
+    G = len(head_sizes)
+    dev = group_logits.device
+    if sum(head_sizes) != Ct or len(col_map) != Ct or sum(rel_counts) != R:
+        raise RuntimeError("head_sizes / col_map / rel_counts do not match the group logits")
+    if max(rel_counts, default=0) * G > 16384:
+        raise RuntimeError("veto_postprocess_meet sorts one image in shared memory: at most 16384 merged rows per image")
+    pairs_o = torch.empty((G * R, 2), dtype=torch.int64, device=dev)
+    probs_o = torch.empty((G * R, num_rel), dtype=torch.float32, device=dev)
+    labels_o = torch.empty(G * R, dtype=torch.int64, device=dev)
+    triple_o = torch.empty(G * R, dtype=torch.float32, device=dev)
+    if R:
+        rel_off = offsets_tensor(rel_counts, dev)
+        box_off = offsets_tensor(n_boxes, dev)
+        head_off = torch.tensor([0] + list(itertools.accumulate(int(n) for n in head_sizes)), dtype=torch.int32, device=dev)
+        cmap = torch.tensor([int(c) for c in col_map], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().veto_postprocess_meet(group_logits.data_ptr(), Ct, head_off.data_ptr(), G, cmap.data_ptr(),
+                                                   num_rel, pairs.data_ptr(), obj_scores.data_ptr(), rel_off.data_ptr(),
+                                                   box_off.data_ptr(), len(rel_counts), R, pairs_o.data_ptr(),
+                                                   probs_o.data_ptr(), labels_o.data_ptr(), triple_o.data_ptr(),
+                                                   L.stream_ptr()), "veto_postprocess_meet")
+    return pairs_o, probs_o, labels_o, triple_o
+
+
 # --------------------------------------------------------------------------------------------
 # launch accounting / per-stage device timing (bench.py)
 # --------------------------------------------------------------------------------------------

@@ -5,13 +5,17 @@ triple score, per-image descending sort — one launch for the whole batch (``ve
 The reference's torch.sort is unstable; ties are broken by the original row (ascending).  In SGDet mode
 (use_gt_box False) the object labels come from the late per-class NMS ``obj_prediction_nms`` (:414-417,
 ``veto_obj_nms_per_cls`` with late_nms) and the boxes are re-regressed to the chosen class (:425-431).
-The MEET ensemble branches (:93-397) are not built yet.
+The MEET 'ensemble' branch (ENSEMBLE_LEARNING.ENABLED with EXPERT_GROUP False, :284-397) merges the group heads'
+candidates of an image into one ranked list (``veto_postprocess_meet``); the reference only ever processes image 0
+there (TEST.IMS_PER_BATCH 1), the drop-in handles the whole batch and is identical for a batch of one.  The
+EXPERT_GROUP voting branches (consensus / unanimous, :93-283) are not built.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
+from . import config as C
 from . import ops
 from .structures import BoxList
 
@@ -23,11 +27,26 @@ class PostProcessor(nn.Module):
             raise NotImplementedError("attribute head is outside the VETO path")
         self.use_gt_box = use_gt_box
         self.later_nms_pred_thres = later_nms_pred_thres
+        self.cfg = cfg
 
-    def forward(self, x, rel_pair_idxs, boxes):
+    def forward(self, x, rel_pair_idxs, boxes, custom_rel_labels=None, cur_chosen_matrix=None, incre_idx_list=None,
+                ensemble=False):
         relation_logits, refine_logits = x
-        if isinstance(relation_logits, dict):
-            raise NotImplementedError("MEET ensemble post-processing is not built yet")
+        meet = isinstance(relation_logits, dict)
+        if meet:
+            if self.cfg is not None and C.get(self.cfg, "ENSEMBLE_LEARNING.EXPERT_GROUP", False):
+                raise NotImplementedError("EXPERT_GROUP voting post-processing (inference.py:93-283) is not built")
+            if incre_idx_list is None:
+                raise RuntimeError("MEET post-processing needs incre_idx_list (the predictor's 4th return value)")
+            names = ["group_%d" % k for k in range(len(relation_logits))]          # :294-299
+            head_sizes = [int(relation_logits[n].shape[1]) for n in names]
+            col_map = []
+            for k, n in enumerate(head_sizes):                                      # chosen_labels_incr (:351-353)
+                members = [i for i, g in enumerate(incre_idx_list) if g == k + 1]
+                if len(members) + 2 != n:
+                    raise RuntimeError(f"head group_{k} has {n} outputs but {len(members)} member predicates")
+                col_map += [0] + members + [0]                                      # last column (out of group) is dropped
+            group_logits = torch.cat([relation_logits[n] for n in names], 1)
         n_boxes = [len(b) for b in boxes]
         rel_counts = [int(p.shape[0]) for p in rel_pair_idxs]
         obj_logit = torch.cat(list(refine_logits), 0)
@@ -41,9 +60,17 @@ class PostProcessor(nn.Module):
             boxes_per_cls = torch.cat([b.get_field("boxes_per_cls") for b in boxes], 0)
             obj_pred = ops.obj_nms_per_cls(obj_prob, boxes_per_cls, n_boxes, self.later_nms_pred_thres, late_nms=True)
             obj_scores = obj_prob.gather(1, obj_pred[:, None])[:, 0]
-        pairs_o, probs_o, labels_o, triple_o = ops.postprocess(torch.cat(list(relation_logits), 0),
-                                                               torch.cat(list(rel_pair_idxs), 0), obj_scores,
-                                                               rel_counts, n_boxes)
+        if meet:
+            G = len(head_sizes)
+            pairs_o, probs_o, labels_o, triple_o = ops.postprocess_meet(
+                group_logits, head_sizes, col_map, len(incre_idx_list), torch.cat(list(rel_pair_idxs), 0), obj_scores,
+                rel_counts, n_boxes)
+            pairs_o = pairs_o.float()      # the reference collects the merged pairs in a float32 tensor (:380)
+            rel_counts = [G * r for r in rel_counts]
+        else:
+            pairs_o, probs_o, labels_o, triple_o = ops.postprocess(torch.cat(list(relation_logits), 0),
+                                                                   torch.cat(list(rel_pair_idxs), 0), obj_scores,
+                                                                   rel_counts, n_boxes)
         results, ro, bo = [], 0, 0
         for box, nb, nr in zip(boxes, n_boxes, rel_counts):
             if self.use_gt_box:
