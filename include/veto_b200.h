@@ -82,6 +82,23 @@ int veto_pairs_globalize(const int64_t* pairs_dev, int64_t n_pairs,
                          const int32_t* rel_offsets_dev, const int32_t* box_offsets_dev, int n_images,
                          int32_t* subj_out_dev, int32_t* obj_out_dev, veto_stream_t stream);
 
+/* f2. Training-time relation sampling for ground-truth boxes: RelationSampling.gtbox_relsample
+ * (pysgg/modeling/roi_heads/relation_head/sampling.py:54-107), whole batch, one launch.
+ * rel_matrix_dev: the images' target "relation" matrices [n_b, n_b] int64 back to back, image b at cell offset
+ * mat_offsets_dev[b] (int32 [n_images+1]); box_offsets_dev int32 [n_images+1]; n_boxes_host [n_images] (n_b <= 128).
+ * Per image: foreground = the cells with relation > 0 in row-major order — a random num_pos_per_image-subset in
+ * random order when there are more (:91-94); background = every other ordered pair i != j in random order, cut to
+ * batch_size_per_image - (foreground kept) (:97-99).  The random order is a counter-based hash of (seed, image, cell)
+ * — a different stream than the reference's torch.randperm, same distribution (every subset / order equally likely).
+ * Outputs: image b's rows start at row b * batch_size_per_image: pairs_out_dev int64 [n_images*batch,2] (foreground
+ * rows first), labels_out_dev int64 [n_images*batch] (relation label, 0 for background), counts_out_dev int32
+ * [n_images,2] = (foreground rows, total rows); binary_out_dev int64, laid out like rel_matrix_dev: the symmetric
+ * binary relatedness matrix rel_sym_binarys (:77-82). */
+int veto_relsample_gtbox(const int64_t* rel_matrix_dev, const int32_t* mat_offsets_dev, const int32_t* box_offsets_dev,
+                         const int32_t* n_boxes_host, int n_images, int batch_size_per_image, int num_pos_per_image,
+                         uint64_t seed, int64_t* pairs_out_dev, int64_t* labels_out_dev, int32_t* counts_out_dev,
+                         int64_t* binary_out_dev, veto_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a3. ROIAlign.  veto_roi_align_forward is the one-for-one replacement of
  * _C.roi_align_forward(input, rois, spatial_scale, ph, pw, sampling_ratio)

@@ -466,3 +466,21 @@ def postprocess_meet(group_logits: Dict[str, np.ndarray], obj_logits: np.ndarray
     order = np.argsort(-triple, kind="stable")
     return dict(pairs=np.concatenate(prs)[order], probs=np.concatenate(probs)[order], labels=np.concatenate(labs)[order],
                 triple=triple[order])
+
+
+def gtbox_relsample_candidates(rel: np.ndarray):
+    """The deterministic part of RelationSampling.gtbox_relsample (relation_head/sampling.py:54-107) for one image:
+    (foreground pairs in nonzero() order [F,2], their labels [F], background candidates [G,2] = every other ordered
+    pair i != j, symmetric binary matrix [n,n]).  What the reference then draws at random: a num_pos subset of the
+    foreground rows if there are more (:91-94) and a random permutation of the background rows cut to
+    batch_size - num_fg (:97-99)."""
+    n = rel.shape[0]
+    fg = np.argwhere(rel > 0).astype(np.int64).reshape(-1, 2)
+    labels = rel[fg[:, 0], fg[:, 1]].astype(np.int64)
+    binary = np.zeros((n, n), np.int64)
+    binary[fg[:, 0], fg[:, 1]] = 1
+    binary[fg[:, 1], fg[:, 0]] = 1
+    poss = np.ones((n, n), np.int64) - np.eye(n, dtype=np.int64)
+    poss[fg[:, 0], fg[:, 1]] = 0
+    bg = np.argwhere(poss > 0).astype(np.int64).reshape(-1, 2)
+    return fg, labels, bg, binary

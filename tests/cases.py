@@ -64,6 +64,12 @@ MEET_TRAIN_CASES = {
                           sample_seed=123),
 }
 
+# RelationSampling.gtbox_relsample fixtures: seeded relation matrices; `caps` = (BATCH_SIZE_PER_IMAGE, POSITIVE_FRACTION)
+RELSAMPLE_CASES = {
+    "relsample_under_caps": dict(n_boxes=[20, 6, 1, 12], seed=31, fg_per_image=10, caps=(1024, 0.25)),
+    "relsample_over_caps": dict(n_boxes=[20, 9, 12], seed=32, fg_per_image=14, caps=(32, 0.25)),
+}
+
 
 def case_rel_labels(c, pair_counts):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA

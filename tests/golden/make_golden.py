@@ -304,8 +304,36 @@ def run_sample_rates():
     print(f"meet_sample_rates: wrote {path}", sorted(out))
 
 
+def run_relsample_case(ns, name, c):
+    """RelationSampling.gtbox_relsample of the UNMODIFIED reference on seeded relation matrices (CPU, torch.manual_seed)."""
+    import torch
+    cfg = ref_shim.make_cfg(ns)
+    cfg.merge_from_list(["MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE", c["caps"][0],
+                         "MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION", c["caps"][1]])
+    samp = ns.make_sampler(cfg)
+    mats = synth.make_relation_matrices(c["seed"], c["n_boxes"], 51, c["fg_per_image"])
+    props, tgts = [], []
+    for n, m in zip(c["n_boxes"], mats):
+        box = torch.rand(n, 4) * 100
+        props.append(ns.BoxList(box.clone(), (416, 320), mode="xyxy"))
+        t = ns.BoxList(box.clone(), (416, 320), mode="xyxy")
+        t.add_field("relation", torch.from_numpy(m))
+        tgts.append(t)
+    torch.manual_seed(c["seed"])
+    props, rel_labels, rel_idx_pairs, binarys = samp.gtbox_relsample(props, tgts)
+    out = {"n_images": np.array(len(mats))}
+    for i in range(len(mats)):
+        out[f"pairs/{i}"] = rel_idx_pairs[i].numpy()
+        out[f"labels/{i}"] = rel_labels[i].numpy()
+        out[f"binary/{i}"] = binarys[i].numpy()
+        out[f"locating_match/{i}"] = props[i].get_field("locating_match").numpy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path}", [(len(p), int((l > 0).sum())) for p, l in zip(rel_idx_pairs, rel_labels)])
+
+
 def main():
-    from tests.cases import MEET_TRAIN_CASES, TRAIN_CASES
+    from tests.cases import MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
     ns = ref_shim.load()
     only = sys.argv[1:]
     for name, c in CASES.items():
@@ -320,6 +348,10 @@ def main():
         if only and name not in only:
             continue
         run_meet_train_case(ns, name, c)
+    for name, c in RELSAMPLE_CASES.items():
+        if only and name not in only:
+            continue
+        run_relsample_case(ns, name, c)
     if not only or "meet_sample_rates" in only:
         run_sample_rates()
 

@@ -298,6 +298,74 @@ def test_meet_per_class_nms_bit_exact():
         assert (ref != scores[:, 1:].argmax(1) + 1).any()          # suppression happened
 
 
+@pytest.mark.parametrize("name", ["relsample_under_caps", "relsample_over_caps"])
+def test_gtbox_relsample(name):
+    """RelationSampling.gtbox_relsample on the device against the unmodified reference's output on
+    the same relation matrices and against the oracle's candidate sets.  The random draws come from a different
+    stream than torch.randperm, so parity is: identical foreground rows / labels and an identical background SET
+    when everything fits; identical row counts, subset-of-candidates, no duplicates and consistent labels when the
+    caps bite; plus reproducibility under torch.manual_seed and a uniformity check of the random subset."""
+    from tests.cases import RELSAMPLE_CASES
+    from veto_b200.sampling import make_roi_relation_samp_processor
+    from veto_b200.structures import BoxList
+    c, g = RELSAMPLE_CASES[name], load_golden(name)
+    mats = synth.make_relation_matrices(c["seed"], c["n_boxes"], 51, c["fg_per_image"])
+    cfg = H.make_cfg()
+    cfg.MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE = c["caps"][0]
+    cfg.MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION = c["caps"][1]
+    samp = make_roi_relation_samp_processor(cfg)
+    batch, num_pos = c["caps"][0], int(c["caps"][0] * c["caps"][1])
+
+    def run(seed):
+        props, tgts = [], []
+        for n, m in zip(c["n_boxes"], mats):
+            box = torch.rand(n, 4, device=DEV) * 100
+            props.append(BoxList(box, (416, 320), "xyxy"))
+            t = BoxList(box.clone(), (416, 320), "xyxy")
+            t.add_field("relation", _t(m))
+            tgts.append(t)
+        torch.manual_seed(seed)
+        return samp.gtbox_relsample(props, tgts)
+
+    props, rel_labels, rel_pairs, binarys = run(1)
+    for i, m in enumerate(mats):
+        fg, labels, bg, binary = O.gtbox_relsample_candidates(m)
+        pr, lb = H.np_(rel_pairs[i]).reshape(-1, 2), H.np_(rel_labels[i])
+        ref_pairs, ref_labels = g[f"pairs/{i}"].reshape(-1, 2), g[f"labels/{i}"]
+        assert pr.dtype == np.int64 and lb.dtype == np.int64
+        assert np.array_equal(H.np_(binarys[i]), g[f"binary/{i}"])
+        assert np.array_equal(H.np_(props[i].get_field("locating_match")), g[f"locating_match/{i}"])
+        assert len(pr) == len(ref_pairs) and int((lb > 0).sum()) == int((ref_labels > 0).sum())
+        n_fg = int((ref_labels > 0).sum())
+        cand = {tuple(p): int(l) for p, l in zip(fg, labels)}
+        if len(fg) <= num_pos:
+            assert np.array_equal(pr[:n_fg], ref_pairs[:n_fg]) and np.array_equal(lb[:n_fg], ref_labels[:n_fg])
+            assert {tuple(p) for p in pr[n_fg:]} == {tuple(p) for p in ref_pairs[n_fg:]} or len(bg) > batch - n_fg
+        assert all(cand[tuple(p)] == int(l) for p, l in zip(pr[:n_fg], lb[:n_fg]))
+        assert len({tuple(p) for p in pr}) == len(pr)                                  # no duplicates
+        assert {tuple(p) for p in pr[n_fg:]} <= {tuple(p) for p in bg} and np.all(lb[n_fg:] == 0)
+    # reproducible under the same torch seed, different under another
+    again = run(1)
+    other = run(2)
+    assert all(torch.equal(a, b) for a, b in zip(again[2], rel_pairs))
+    assert any(not torch.equal(a, b) for a, b in zip(other[2], rel_pairs) if len(a) > 2)
+    if name == "relsample_over_caps":
+        # every background candidate of image 0 is kept about equally often: 24 of 366 slots -> p = 0.0656
+        fg, labels, bg, _ = O.gtbox_relsample_candidates(mats[0])
+        hits = {tuple(p): 0 for p in bg}
+        trials = 300
+        for s in range(trials):
+            out = run(100 + s)
+            for p in H.np_(out[2][0])[num_pos:]:
+                hits[tuple(p)] += 1
+        kept = batch - num_pos
+        p_exp = kept / len(bg)
+        freq = np.array(list(hits.values())) / trials
+        assert abs(freq.mean() - p_exp) < 1e-9
+        sigma = np.sqrt(p_exp * (1 - p_exp) / trials)
+        assert freq.max() < p_exp + 6 * sigma and freq.min() > p_exp - 6 * sigma, (freq.min(), freq.max(), p_exp)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_meet_postprocess_ensemble_merge(precision):
     """PostProcessor MEET 'ensemble' branch (inference.py:284-397): the merged, ranked candidate list of the unmodified

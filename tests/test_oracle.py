@@ -321,3 +321,33 @@ def test_meet_group_sampling_matches_reference():
     assert len(worst) >= 85
     for k in g["no_grad"]:
         assert str(k) not in out["grads"]
+
+
+@pytest.mark.parametrize("name", ["relsample_under_caps", "relsample_over_caps"])
+def test_gtbox_relsample_candidates_match_reference(name):
+    """oracle.gtbox_relsample_candidates (the deterministic part of RelationSampling.gtbox_relsample) against the
+    unmodified reference's sampler run on seeded relation matrices: under the caps the foreground rows / labels are
+    identical and the background rows are a permutation of the candidates; over the caps the reference's rows are a
+    subset of the candidates of the sizes :91-99 prescribe."""
+    from tests.cases import RELSAMPLE_CASES
+    c, g = RELSAMPLE_CASES[name], load_golden(name)
+    mats = synth.make_relation_matrices(c["seed"], c["n_boxes"], 51, c["fg_per_image"])
+    batch, num_pos = c["caps"][0], int(c["caps"][0] * c["caps"][1])
+    for i, m in enumerate(mats):
+        fg, labels, bg, binary = O.gtbox_relsample_candidates(m)
+        ref_pairs, ref_labels = g[f"pairs/{i}"].reshape(-1, 2), g[f"labels/{i}"]
+        assert np.array_equal(binary, g[f"binary/{i}"])
+        n_fg = min(len(fg), num_pos)
+        n_bg = min(len(bg), batch - n_fg)
+        assert len(ref_pairs) == n_fg + n_bg and int((ref_labels > 0).sum()) == n_fg
+        cand = {tuple(p): int(l) for p, l in zip(fg, labels)}
+        if len(fg) <= num_pos:
+            assert np.array_equal(ref_pairs[:n_fg], fg) and np.array_equal(ref_labels[:n_fg], labels)
+        else:
+            assert all(cand[tuple(p)] == int(l) for p, l in zip(ref_pairs[:n_fg], ref_labels[:n_fg]))
+            assert len({tuple(p) for p in ref_pairs[:n_fg]}) == n_fg
+        bgset = {tuple(p) for p in bg}
+        got_bg = [tuple(p) for p in ref_pairs[n_fg:]]
+        assert len(set(got_bg)) == n_bg and set(got_bg) <= bgset and np.all(ref_labels[n_fg:] == 0)
+        if len(bg) <= batch - n_fg:
+            assert set(got_bg) == bgset

@@ -15,7 +15,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
    python bench.py --steps 1 --warmup 1 --no-inference --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.out 2>&1; echo "rc=$?"
 python tools/ncu_summary.py launches /tmp/launches.csv gpurun_out/${TAG}_launches.txt; head -n 14 gpurun_out/${TAG}_launches.txt
 echo "== ncu full: training kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn2_kernel|gemm_tc2_kernel|attention_bwd_kernel|ln_bwd_kernel" -s 60 -c 24 -f -o /tmp/prof_train \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tn2_kernel|gemm_tc2_kernel|attention_bwd|ln_bwd_kernel|attention_mma" -s 60 -c 24 -f -o /tmp/prof_train \
    python bench.py --steps 1 --warmup 1 --no-inference --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.out 2>&1; echo "rc=$?"
 python tools/ncu_summary.py report /tmp/prof_train.ncu-rep gpurun_out/${TAG}_train_ncu.txt
 ls -la /tmp/prof_train.ncu-rep; [ $(stat -c %s /tmp/prof_train.ncu-rep) -lt 40000000 ] && cp /tmp/prof_train.ncu-rep gpurun_out/${TAG}_train.ncu-rep

@@ -64,6 +64,8 @@ _DEFAULTS = {
             "USE_GT_OBJECT_LABEL": True,
             "POOLER_RESOLUTION": 8,                             # VETO_final.yaml:57
             "MAX_PROPOSAL_PAIR": 2048,                          # defaults.py:305
+            "BATCH_SIZE_PER_IMAGE": 1024,                       # VETO_final.yaml:64
+            "POSITIVE_FRACTION": 0.25,                          # VETO_final.yaml:65
             "CONTEXT_HIDDEN_DIM": 512,
             "CONTEXT_POOLING_DIM": 4096,
             "VG_NUM_CLASSES": 51,                               # defaults.py:301

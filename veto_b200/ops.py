@@ -404,6 +404,39 @@ def dropout_keep_mask(seed: int, sub: int, n: int, p: float):
 
 
 # --------------------------------------------------------------------------------------------
+# f2: training-time relation sampling (ground-truth boxes)
+# --------------------------------------------------------------------------------------------
+def relsample_gtbox(rel_matrices: Sequence[torch.Tensor], batch_size_per_image: int, num_pos_per_image: int, seed: int):
+    """RelationSampling.gtbox_relsample (sampling.py:54-107) for a batch in one launch.  rel_matrices: per image the
+    target's [n, n] "relation" matrix.  Returns (pairs [B*batch,2] int64, labels [B*batch] int64, counts [B,2] int32
+    (foreground rows, total rows) — image b's rows start at b*batch — and the per-image binary matrices)."""
+    L.require_device()
+    n_boxes = [int(m.shape[0]) for m in rel_matrices]
+    dev = rel_matrices[0].device
+    if any(m.dim() != 2 or m.shape[0] != m.shape[1] for m in rel_matrices):
+        raise RuntimeError("relation matrices must be square")
+    flat = torch.cat([m.reshape(-1) for m in rel_matrices]).to(torch.int64).contiguous()
+    mat_off = offsets_tensor([n * n for n in n_boxes], dev)
+    box_off = offsets_tensor(n_boxes, dev)
+    B = len(n_boxes)
+    pairs = torch.zeros((B * batch_size_per_image, 2), dtype=torch.int64, device=dev)
+    labels = torch.zeros(B * batch_size_per_image, dtype=torch.int64, device=dev)
+    counts = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    binary = torch.empty_like(flat)
+    nb = (ctypes.c_int32 * B)(*n_boxes)
+    with torch.cuda.device(dev):
+        L.check(L.load().veto_relsample_gtbox(flat.data_ptr(), mat_off.data_ptr(), box_off.data_ptr(), nb, B,
+                                              int(batch_size_per_image), int(num_pos_per_image), int(seed) & (2 ** 64 - 1),
+                                              pairs.data_ptr(), labels.data_ptr(), counts.data_ptr(), binary.data_ptr(),
+                                              L.stream_ptr()), "veto_relsample_gtbox")
+    binaries, off = [], 0
+    for n in n_boxes:
+        binaries.append(binary[off:off + n * n].view(n, n))
+        off += n * n
+    return pairs, labels, counts, binaries
+
+
+# --------------------------------------------------------------------------------------------
 # a10: MEET's per-class NMS label assignment (SGDet test)
 # --------------------------------------------------------------------------------------------
 def obj_nms_per_cls(scores: torch.Tensor, boxes_per_cls: torch.Tensor, n_boxes: Sequence[int], thresh: float,

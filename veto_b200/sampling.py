@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 
+from . import config as C
 from . import ops
 from .structures import xyxy_boxes
 
@@ -36,16 +37,34 @@ class RelationSampling:
                                    require_overlap=overlap)
 
     def gtbox_relsample(self, proposals, targets):
-        raise NotImplementedError("training-time samplers are a 'next' row (SURVEY.md §8 f2)")
+        """sampling.py:54-107: (proposals, rel_labels, rel_idx_pairs, rel_sym_binarys) for training on ground-truth
+        boxes — one launch for the batch and ONE host sync (the row counts), instead of a per-image loop with three
+        nonzero syncs and two randperms.  The random subset / order comes from a counter-based hash seeded from torch's
+        CPU generator (torch.manual_seed reproduces a run); foreground rows keep the reference's row-major order when
+        all of them fit."""
+        assert self.use_gt_box
+        num_pos = int(self.batch_size_per_image * self.positive_fraction)
+        for p, t in zip(proposals, targets):
+            assert p.bbox.shape[0] == t.bbox.shape[0]
+            p.add_field("locating_match", torch.ones(len(p), device=p.bbox.device))          # :73-75
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        pairs, labels, counts, binaries = ops.relsample_gtbox([t.get_field("relation") for t in targets],
+                                                              self.batch_size_per_image, num_pos, seed)
+        totals = counts[:, 1].tolist()
+        rel_idx_pairs = [pairs[b * self.batch_size_per_image: b * self.batch_size_per_image + n] for b, n in enumerate(totals)]
+        rel_labels = [labels[b * self.batch_size_per_image: b * self.batch_size_per_image + n] for b, n in enumerate(totals)]
+        return proposals, rel_labels, rel_idx_pairs, binaries
 
     def detect_relsample(self, proposals, targets):
-        raise NotImplementedError("training-time samplers are a 'next' row (SURVEY.md §8 f2)")
+        raise NotImplementedError("detect_relsample (SGDet training sampler, sampling.py:109-309) is a 'next' row (SURVEY.md §8 f2)")
 
 
 def make_roi_relation_samp_processor(cfg):
     """sampling.py:312-324."""
     rh = cfg.MODEL.ROI_RELATION_HEAD
     return RelationSampling(
+        batch_size_per_image=C.get(cfg, "MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE", 1024),
+        positive_fraction=C.get(cfg, "MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION", 0.25),
         max_proposal_pairs=rh.MAX_PROPOSAL_PAIR,
         use_gt_box=rh.USE_GT_BOX,
         test_overlap=cfg.TEST.RELATION.REQUIRE_OVERLAP,
