@@ -360,6 +360,208 @@ attention_mma_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f3
 }
 
 
+// ---------------------------------------------------------------- attention on warp MMAs, two warps per item
+// Same arithmetic as attention_mma_kernel, but TWO warps share the staged Q, K, V of a (sequence, head): warp w takes
+// k-steps 3w..3w+2 of S = Q K^T (the partial accumulators meet through a 19x20 tile each) and 6 of the 12 output
+// n-tiles of O = P V; both run the softmax on the full S.  16 warps per SM instead of 8 for nearly the same shared
+// memory: the one-warp kernel is staging-latency bound (cp.async -> wait -> compute -> store per item, 2 warps per
+// scheduler), which the same change fixed in the backward kernel (train.cu: 696 -> 498 us).
+constexpr int ATT2_PAIRS = 8;
+constexpr int ATT2_TILE = kTokens * 20;
+constexpr int ATT2_ITEM_FLOATS = ATT_ITEM_FLOATS + 2 * ATT2_TILE;
+constexpr int ATT2_THREADS = ATT2_PAIRS * 64;
+constexpr int ATT2_SMEM = ATT2_PAIRS * ATT2_ITEM_FLOATS * (int)sizeof(float);  // 213,952 B
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, __nv_bfloat16* out_hi,
+                      __nv_bfloat16* out_lo) {
+    extern __shared__ float4 att_smem[];
+    constexpr int LD = 3 * kDim;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pair = threadIdx.x >> 6, w = (threadIdx.x >> 5) & 1, lane64 = threadIdx.x & 63;
+    float* sQ = reinterpret_cast<float*>(att_smem) + pair * ATT2_ITEM_FLOATS;
+    float* sK = sQ + kTokens * ATT_QK_STRIDE;
+    float* sV = sK + kTokens * ATT_QK_STRIDE;
+    float* myS = sV + kTokens * ATT_V_STRIDE + w * ATT2_TILE;
+    const float* otherS = sV + kTokens * ATT_V_STRIDE + (w ^ 1) * ATT2_TILE;
+    const float scale = 0.10206207261596575f;  // 96 ** -0.5 (model_veto.py:74)
+    const int64_t items = n_seq * kHeads;
+    auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
+    for (int64_t item = (int64_t)blockIdx.x * ATT2_PAIRS + pair; item < items; item += (int64_t)gridDim.x * ATT2_PAIRS) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const float* base = qkv + (size_t)seq * kTokens * LD + h * kHeadDim;
+        for (int idx = lane64; idx < 3 * kTokens * (kHeadDim / 4); idx += 64) {
+            const int m = idx / (kHeadDim / 4), c = idx - m * (kHeadDim / 4);
+            const int which = m / kTokens, row = m - which * kTokens;
+            const float* src = base + (size_t)row * LD + which * kDim + c * 4;
+            float* dst = (which == 0 ? sQ + row * ATT_QK_STRIDE : which == 1 ? sK + row * ATT_QK_STRIDE : sV + row * ATT_V_STRIDE) + c * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        pair_bar();  // (1) staged operands visible to both warps
+        auto ld2 = [&](int row, int col, int which) -> float2 {  // which: 0 q, 1 k
+            return (row < kTokens) ? *(const float2*)((which == 0 ? sQ : sK) + row * ATT_QK_STRIDE + col) : make_float2(0.f, 0.f);
+        };
+
+        // ---- partial S = Q K^T over this warp's three k-steps: 2 m-tiles x 3 n-tiles
+        float S[2][3][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) S[mt][nt][e] = 0.f;
+#pragma unroll 1
+        for (int ks = 3 * w; ks < 3 * w + 3; ++ks) {
+            const int d0 = ks * 16 + 2 * t;
+            uint32_t qh[2][4], ql[2][4], kh[3][2], kl[3][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float2 x0 = ld2(16 * mt + g, d0, 0), x1 = ld2(16 * mt + g + 8, d0, 0);
+                const float2 x2 = ld2(16 * mt + g, d0 + 8, 0), x3 = ld2(16 * mt + g + 8, d0 + 8, 0);
+                split_pair(x0.x, x0.y, qh[mt][0], ql[mt][0]);
+                split_pair(x1.x, x1.y, qh[mt][1], ql[mt][1]);
+                split_pair(x2.x, x2.y, qh[mt][2], ql[mt][2]);
+                split_pair(x3.x, x3.y, qh[mt][3], ql[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const float2 y0 = ld2(8 * nt + g, d0, 1), y1 = ld2(8 * nt + g, d0 + 8, 1);
+                split_pair(y0.x, y0.y, kh[nt][0], kl[nt][0]);
+                split_pair(y1.x, y1.y, kh[nt][1], kl[nt][1]);
+            }
+#pragma unroll
+            for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        mma_bf16_16816(S[mt][nt], term == 1 ? ql[mt] : qh[mt], term == 2 ? kl[nt] : kh[nt]);
+        }
+        // ---- exchange the partial scores (e 0,1 -> row 16mt+g, e 2,3 -> row +8; cols 8nt+2t+e)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 16 * mt + g + 8 * (e >> 1), col = 8 * nt + 2 * t + (e & 1);
+                    if (row < kTokens && col < kTokens) myS[row * 20 + col] = S[mt][nt][e];
+                }
+        pair_bar();  // (2)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 16 * mt + g + 8 * (e >> 1), col = 8 * nt + 2 * t + (e & 1);
+                    if (row < kTokens && col < kTokens) S[mt][nt][e] += otherS[row * 20 + col];
+                }
+
+        // ---- softmax over the 19 keys of each row (a row = the 4 lanes of a quad)
+        uint32_t ph[2][2][4], pl[2][2][4];  // [mt][ks2][a-fragment]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = 8 * nt + 2 * t + e;
+                        float v = S[mt][nt][2 * hrow + e] * scale;
+                        v = (col < kTokens) ? v : -INFINITY;
+                        S[mt][nt][2 * hrow + e] = v;
+                        m = fmaxf(m, v);
+                    }
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                float sum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = expf(S[mt][nt][2 * hrow + e] - m);
+                        S[mt][nt][2 * hrow + e] = p;
+                        sum += p;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) S[mt][nt][2 * hrow + e] *= inv;
+            }
+            split_pair(S[mt][0][0], S[mt][0][1], ph[mt][0][0], pl[mt][0][0]);
+            split_pair(S[mt][0][2], S[mt][0][3], ph[mt][0][1], pl[mt][0][1]);
+            split_pair(S[mt][1][0], S[mt][1][1], ph[mt][0][2], pl[mt][0][2]);
+            split_pair(S[mt][1][2], S[mt][1][3], ph[mt][0][3], pl[mt][0][3]);
+            split_pair(S[mt][2][0], S[mt][2][1], ph[mt][1][0], pl[mt][1][0]);
+            split_pair(S[mt][2][2], S[mt][2][3], ph[mt][1][1], pl[mt][1][1]);
+            ph[mt][1][2] = pl[mt][1][2] = ph[mt][1][3] = pl[mt][1][3] = 0u;  // keys 24..31 do not exist
+        }
+
+        // ---- O = P V : this warp's 6 n-tiles of 8 head dims (blocks 2w, 2w+1 of three), 2 k-steps of 16 keys
+        auto ldv = [&](int key, int d) -> float { return (key < kTokens) ? sV[key * ATT_V_STRIDE + d] : 0.f; };
+#pragma unroll 1
+        for (int blk = 2 * w; blk < 2 * w + 2; ++blk) {
+            float O[2][3][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) O[mt][j][e] = 0.f;
+#pragma unroll
+            for (int ks2 = 0; ks2 < 2; ++ks2) {
+                const int k0 = 16 * ks2 + 2 * t;
+                uint32_t vh[3][2], vl[3][2];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int d = 8 * (3 * blk + j) + g;
+                    split_pair(ldv(k0, d), ldv(k0 + 1, d), vh[j][0], vl[j][0]);
+                    split_pair(ldv(k0 + 8, d), ldv(k0 + 9, d), vh[j][1], vl[j][1]);
+                }
+#pragma unroll
+                for (int term = 0; term < (SPLIT ? 3 : 1); ++term)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            mma_bf16_16816(O[mt][j], term == 1 ? pl[mt][ks2] : ph[mt][ks2], term == 2 ? vl[j] : vh[j]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int row = 16 * mt + g + 8 * hrow;
+                    if (row < kTokens) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const float v0 = O[mt][j][2 * hrow], v1 = O[mt][j][2 * hrow + 1];
+                            const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 8 * (3 * blk + j) + 2 * t;
+                            if (out_f32) *(float2*)(out_f32 + o) = make_float2(v0, v1);
+                            if (out_hi) {
+                                uint32_t hh, ll;
+                                split_pair(v0, v1, hh, ll);
+                                *(uint32_t*)(out_hi + o) = hh;
+                                if (out_lo) *(uint32_t*)(out_lo + o) = ll;
+                            }
+                        }
+                    }
+                }
+        }
+        pair_bar();  // (3) both warps are done with the staged operands and the tiles
+    }
+}
+
+
 // ---------------------------------------------------------------- CLS-only attention (last layer)
 // One warp per (sequence, head): lane j < 19 scores key j against the single CLS query, the softmax is a pair of
 // warp reductions, and lane L accumulates output dims L, L+32, L+64 with p_j broadcast by shuffle.
@@ -439,6 +641,22 @@ int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream
             use_tc = (e && e[0] == 't') ? 1 : 0;
         }
         if (use_tc) return attention_tc(qkv, n_seq, out, s);
+        static int one_warp = -1;
+        if (one_warp < 0) one_warp = getenv("VETO_ATTENTION_ONE_WARP") ? 1 : 0;  // diagnosis: the one-warp-per-item kernel
+        if (!one_warp) {
+            static bool attr2_set = false;
+            if (!attr2_set) {
+                VETO_CUDA(cudaFuncSetAttribute(attention_mma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+                VETO_CUDA(cudaFuncSetAttribute(attention_mma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+                attr2_set = true;
+            }
+            const int64_t blocks2 = (n_seq * kHeads + ATT2_PAIRS - 1) / ATT2_PAIRS;
+            const int grid2 = (int)(blocks2 < (int64_t)num_sms() ? blocks2 : (int64_t)num_sms());
+            if (out.lo) attention_mma2_kernel<true><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+            else attention_mma2_kernel<false><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+            VETO_LAUNCH_CHECK();
+            return VETO_OK;
+        }
         static bool mma_attr_set = false;
         if (!mma_attr_set) {
             VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));

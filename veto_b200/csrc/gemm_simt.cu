@@ -161,6 +161,94 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- skinny outputs (the predicate classifier)
+// C[M, N <= 128] = A[M,K] W[N,K]^T + bias: with N = 51 (VG) / 60 / 108 (MEET heads) the 128x128-tile kernel launches
+// ceil(M/128) CTAs — 16 of 148 SMs for a 1994-pair inference chunk (124 us per chunk, 12.5 ms of the 435 ms inference
+// step).  Here W^T lives in shared memory ([k][n], row stride = 1 mod 32: conflict-free both for the transposing fill
+// and for the lane-per-column reads), a warp owns a row of A at a time (staged in shared memory, read back as
+// broadcast float4), and lane j accumulates output columns j, j + 32, ...: every SM works, rows are independent and
+// the k order is fixed, so results do not depend on how the rows are chunked.
+constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32;
+constexpr int SK_SMEM_FLOATS = 40960;  // 160 KB for the W^T tile
+
+template <int NCH>
+__global__ void __launch_bounds__(SK_THREADS)
+gemm_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int M, int N, int K, int KT,
+                   const float* __restrict__ bias, float* __restrict__ out, int ldc) {
+    extern __shared__ float sk_smem[];
+    constexpr int NP = NCH * 32 + 1;
+    float* sW = sk_smem;                         // [KT][NP]
+    float* sX = sk_smem + (size_t)KT * NP;       // [SK_WARPS][KT]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* xs = sX + wid * KT;
+    const int rows_per_pass = gridDim.x * SK_WARPS;
+    const int passes = (M + rows_per_pass - 1) / rows_per_pass;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int row = pass * rows_per_pass + blockIdx.x * SK_WARPS + wid;
+        float acc[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += KT) {
+            const int kt = (K - k0 < KT) ? K - k0 : KT;
+            if (pass == 0 || K > KT) {           // the W^T tile stays resident when it holds all of K
+                __syncthreads();
+                for (int e = threadIdx.x; e < N * kt; e += SK_THREADS) {
+                    const int n = e / kt, k = e - n * kt;  // consecutive threads walk k: coalesced in W, banks k + n
+                    sW[k * NP + n] = __ldg(W + (size_t)n * K + k0 + k);
+                }
+                __syncthreads();
+            }
+            if (row < M) {
+                for (int k = lane; k < kt; k += 32) xs[k] = __ldg(A + (size_t)row * lda + k0 + k);
+                __syncwarp();
+                int k = 0;
+                for (; k + 3 < kt; k += 4) {
+                    const float4 x = *(const float4*)(xs + k);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float* wp = sW + k * NP + lane + 32 * c;   // columns past N hold stale values: never stored
+                        acc[c] = fmaf(x.x, wp[0], acc[c]);
+                        acc[c] = fmaf(x.y, wp[NP], acc[c]);
+                        acc[c] = fmaf(x.z, wp[2 * NP], acc[c]);
+                        acc[c] = fmaf(x.w, wp[3 * NP], acc[c]);
+                    }
+                }
+                for (; k < kt; ++k) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) acc[c] = fmaf(xs[k], sW[k * NP + lane + 32 * c], acc[c]);
+                }
+                __syncwarp();
+            }
+        }
+        if (row < M) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int n = lane + 32 * c;
+                if (n < N) out[(size_t)row * ldc + n] = acc[c] + (bias ? bias[n] : 0.f);
+            }
+        }
+    }
+}
+
+template <int NCH>
+int launch_skinny(const float* A, int lda, const float* W, int M, int N, int K, const float* bias, float* out, int ldc,
+                  cudaStream_t s) {
+    constexpr int NP = NCH * 32 + 1;
+    int KT = (SK_SMEM_FLOATS / NP) & ~3;
+    if (KT > K) KT = (K + 3) & ~3;
+    const int smem = (KT * NP + SK_WARPS * KT) * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VETO_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int grid = (M + SK_WARPS - 1) / SK_WARPS;
+    if (grid > num_sms()) grid = num_sms();
+    gemm_skinny_kernel<NCH><<<grid, SK_THREADS, smem, s>>>(A, lda, W, M, N, K, KT, bias, out, ldc);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
 }  // namespace
 
 int gemm_simt_slices(int K, int split_k) {
@@ -172,6 +260,16 @@ int gemm_simt_slices(int K, int split_k) {
 int gemm_simt(const float* A, int lda, const float* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
     if (M <= 0 || N <= 0) return VETO_OK;
     VETO_REQUIRE(K > 0 && A && W, VETO_ERR_ARG, "gemm_simt: bad operands");
+    // skinny outputs with a plain (bias-only) epilogue: the predicate classifier
+    if (N <= 128 && K >= 64 && M >= 256 && ep.split_k <= 1 && !ep.residual && ep.act == ACT_NONE && !ep.pre_f32 && !ep.drop.thr16 &&
+        ep.out.f32 && !ep.out.hi && (lda % 4) == 0 && (((uintptr_t)A) & 15) == 0) {
+        switch ((N + 31) / 32) {
+            case 1: return launch_skinny<1>(A, lda, W, M, N, K, ep.bias, ep.out.f32, ep.ldc, s);
+            case 2: return launch_skinny<2>(A, lda, W, M, N, K, ep.bias, ep.out.f32, ep.ldc, s);
+            case 3: return launch_skinny<3>(A, lda, W, M, N, K, ep.bias, ep.out.f32, ep.ldc, s);
+            default: return launch_skinny<4>(A, lda, W, M, N, K, ep.bias, ep.out.f32, ep.ldc, s);
+        }
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "gemm_simt: M=%d too large for one launch", M);
     int slices = ep.split_k > 1 ? ep.split_k : 1;

@@ -382,8 +382,9 @@ ln_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict_
 // Column ownership: warp h owns the float4 columns c = 8g + 4h + i (g < 3, i < 4).  The swizzled position of (row, c)
 // is 8g + 4 (h ^ row bit 2) + (i ^ (row & 3)), so in the inner loops — which walk the 19 rows of a K / V / Q / dO tile
 // with the row index unrolled — every shared-memory address is one of two per-warp base registers (h, 1 - h) plus an
-// immediate.  The second version computed the swizzle per access and was issue-bound on integer work (ncu: issue
-// slots 63 % busy at 20 % warps active, 888 us per launch).
+// immediate.  That removed the integer work per access but not the time (888 us per launch either way): the kernel is
+// bound by the shared-memory RETURN path — a lane-per-row dot product needs one LDS.128 per four FMAs, 2340 LDS.128 per
+// (sequence, head) at 4 clk each.  It remains the fp32-mode kernel; the tensor-core modes use attention_bwd_mma_kernel.
 constexpr int AB_ROW = kHeadDim;                 // floats per staged row
 constexpr int AB_PS = 20;                        // row stride of the P / dS tiles
 constexpr int AB_ITEM = 4 * kTokens * AB_ROW + 2 * kTokens * AB_PS;  // floats per item (32,224 B)
