@@ -5,7 +5,7 @@
 
 Headline workload: BASELINE.json configs[1] — VETO vanilla PredCls TRAINING step, IMS_PER_BATCH 12 per GPU, 20 GT
 boxes / image (all 380 ordered pairs per image are under the 1024-pair cap of gtbox_relsample, so a step trains on
-12 x 380 = 4560 pairs), VG 151/51, 592x800 images.  A "step" = candidate pairs -> VETOFeatureExtractor (ROI gather)
+12 x 380 = 4560 pairs), VG 151/51, 592x800 images.  A "step" = gtbox_relsample (relation sampling) -> VETOFeatureExtractor (ROI gather)
 -> VETOPredictor in train() mode with the reference's dropout rates -> rel_loss.backward() (incl. the ROIAlign
 backward into the depth feature map) -> gradient all-reduce (N > 1, NCCL) -> clip_grad_norm 5.0 -> Adam step
 (tools/relation_train_net.py:418-483).
@@ -127,11 +127,17 @@ def cpu_train_leg(steps: int = 1, warmup: int = 0):
     boxes = [torch.from_numpy(b) for b in batch["boxes"]]
     labels = [torch.from_numpy(l) for l in batch["labels"]]
     R = TR_BOXES * (TR_BOXES - 1)
-    rel_labels = [torch.from_numpy(l) for l in synth.make_rel_labels(5, [R])]
+    import numpy as np
+    from oracle import veto_oracle as O
+    rel_mat = synth.make_relation_matrices(5, [TR_BOXES], 51, 10)[0]
+    rng = np.random.default_rng(5)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        pairs = TP.prepare_test_pairs(batch["n_boxes"], 2048)
+        fg, fg_labels, bg, _ = O.gtbox_relsample_candidates(rel_mat)            # gtbox_relsample (sampling.py:54-107)
+        bg = bg[rng.permutation(len(bg))][:1024 - len(fg)]
+        pairs = [torch.from_numpy(np.concatenate([fg, bg]))]
+        rel_labels = [torch.from_numpy(np.concatenate([fg_labels, np.zeros(len(bg), np.int64)]))]
         x2d, d2d = TP.pooler_forward(feats, depth, boxes)
         loss, grads, *_ = TP.train_step(sd, boxes, pairs, rel_labels, x2d, d2d, "predcls", labels=labels)
         dt = time.perf_counter() - t0
@@ -139,7 +145,7 @@ def cpu_train_leg(steps: int = 1, warmup: int = 0):
         if it >= warmup:
             times.append(dt)
     per_step = sorted(times)[len(times) // 2]
-    sample = (f"1 image x {TR_BOXES} boxes = {R} pairs: pair enumeration + ROI gather + VETOPredictor train() forward + CE loss "
+    sample = (f"1 image x {TR_BOXES} boxes = {R} pairs: relation sampling + ROI gather + VETOPredictor train() forward + CE loss "
               f"+ backward (no optimizer step); oracle/torch_port.py = the reference's formulation on torch CPU fp32 kernels "
               f"with torch autograd, {cores} threads")
     return R / per_step, cores, sample, per_step
@@ -272,17 +278,28 @@ def main():
     fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(dev).train()
     samp = make_roi_relation_samp_processor(cfg)
     bls_dev = H.boxlists(batch, dev, 151)
-    rel_labels_np = synth.make_rel_labels(7 + rank, [TR_BOXES * (TR_BOXES - 1)] * B)
-    rel_labels_dev = [torch.from_numpy(l).to(dev) for l in rel_labels_np]
+    # ground-truth relation matrices (the targets' "relation" field): ~10 annotated relations per image, VG-like
+    rel_mats_np = synth.make_relation_matrices(7 + rank, [TR_BOXES] * B, 51, 10)
+
+    def make_targets(mats):
+        out = []
+        for bl, m in zip(bls_dev, mats):
+            t = BoxList(bl.bbox, (IMG_W, IMG_H), "xyxy")
+            t.add_field("relation", m)
+            out.append(t)
+        return out
+
+    targets_dev = make_targets([torch.from_numpy(m).to(dev) for m in rel_mats_np])
     params = [p for p in pred.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-4 * B, fused=True)           # BASE_LR x IMS_PER_BATCH (relation_train_net.py:330-339)
     losses = []
 
-    def train_step(feats, depth, bls, rel_labels):
+    def train_step(feats, depth, bls, targets):
         opt.zero_grad(set_to_none=True)
         depth.grad = None
-        # all ordered pairs per image: what gtbox_relsample hands the predictor under its 1024-pair cap (sampling.py:54-107)
-        pairs = samp.prepare_test_pairs(dev, bls)
+        # relation sampling on the ground-truth boxes (relation_head.py:118-121 -> sampling.py:54-107): the annotated
+        # pairs + randomly ordered background pairs; 20 boxes give 380 candidates, all under the 1024-pair cap
+        _, rel_labels, pairs, _ = samp.gtbox_relsample(bls, targets)
         x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
         loss = pred(bls, pairs, rel_labels, None, roi_features=x2d, roi_depth_features=d2d)[2]["rel_loss"]
         loss.backward()
@@ -292,12 +309,12 @@ def main():
         return loss.detach()
 
     def step_resident():
-        losses.append(train_step(feats_dev, depth_dev, bls_dev, rel_labels_dev))
+        losses.append(train_step(feats_dev, depth_dev, bls_dev, targets_dev))
 
     feats_host = [pin(f) for f in feats_dev]
     depth_host = pin(depth_dev)
     boxes_host, fields_host = host_boxlists(bls_dev)
-    labels_host = [pin(l) for l in rel_labels_dev]
+    labels_host = [pin(t.get_field("relation")) for t in targets_dev]   # the targets' relation matrices
     h2d_bytes = sum(t.numel() * t.element_size() for t in feats_host + [depth_host] + boxes_host + labels_host)
     h2d_bytes += sum(t.numel() * t.element_size() for f in fields_host for t in f.values())
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -356,9 +373,14 @@ def main():
         feats = [dev_like(f) for f in feats_host]
         depth = dev_like(depth_host).requires_grad_(True)
         bls, copies = boxlist_slot(boxes_host, fields_host)
-        labels = [dev_like(l) for l in labels_host]
-        copies += list(zip(feats, feats_host)) + [(depth, depth_host)] + list(zip(labels, labels_host))
-        return (feats, depth, bls, labels), copies
+        mats = [dev_like(l) for l in labels_host]
+        targets = []
+        for bl, m in zip(bls, mats):
+            t = BoxList(bl.bbox, (IMG_W, IMG_H), "xyxy")
+            t.add_field("relation", m)
+            targets.append(t)
+        copies += list(zip(feats, feats_host)) + [(depth, depth_host)] + list(zip(mats, labels_host))
+        return (feats, depth, bls, targets), copies
 
     train_pipe = InputPipe(train_slot)
 
