@@ -36,7 +36,7 @@ struct TrainLayout {
     LayerSave L[VETO_MAX_LAYERS];
     size_t logits;
     // backward temporaries
-    size_t dlogits, ce_scratch, tc1, tc2, wcT, wc_partial, pos_partial;
+    size_t dlogits, ce_scratch, tc1, tc2, wcT, wc_partial, pos_partial, box_partial;
     size_t dx, tmp, a576, a1728, T1, T2, splitk, ln_partial, colsum_scratch;
     LayerWT WT[VETO_MAX_LAYERS];
     size_t d2T, v2T, loc2T, cls2T;
@@ -86,6 +86,7 @@ TrainLayout train_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs)
     T.wcT = k.take(f * (size_t)kDim * c.num_out);
     T.wc_partial = k.take(f * (size_t)kMaxSplit * kDim * c.num_out);
     T.pos_partial = k.take(f * pos_embed_bwd_scratch_floats());
+    T.box_partial = k.take(f * (size_t)kMaxSplit * max_sz((size_t)T.Nb * kEmbDim, (size_t)2 * kDim * kEmbDim));
     T.dx = k.take(f * M * kDim);
     T.tmp = k.take(f * M * kDim);
     T.a576 = k.take(act_bytes(prec, M * kDim));
@@ -139,6 +140,26 @@ struct Ctx {
     // C[M,N] = epilogue(A[M,K] @ W[N,K]^T), operands in the storage format of the precision mode
     int mm(const ActBuf& A, int lda, const ActBuf& W, int M, int N, int K, const GemmEpilogue& ep) const {
         return linear(prec, A, lda, WRef{W.f32, W.hi, W.lo}, M, N, K, ep, s);
+    }
+    // plain fp32 C[M,N] = A[M,K] @ W[N,K]^T for the small per-box GEMMs of the backward (few output tiles, long K): split-K
+    // over up to kMaxSplit slices of at least 64 columns, fixed-order reduction
+    int mm_small(const float* A, int lda, const float* W, int M, int N, int K, float* out, int ldc) const {
+        GemmEpilogue ep;
+        ep.ldc = ldc;
+        int want = K / 64 < kMaxSplit ? K / 64 : kMaxSplit;
+        if (N <= 128 && K >= 64 && M >= 256) want = 1;  // gemm_simt's skinny-output kernel already fills the machine
+        const int slices = want > 1 ? gemm_simt_slices(K, want) : 1;
+        if (slices <= 1) {
+            ep.out.f32 = out;
+            return gemm_simt(A, lda, W, M, N, K, ep, s);
+        }
+        float* partial = f32(T->box_partial);
+        ep.out.f32 = partial;
+        ep.split_k = want;
+        ep.split_stride = (size_t)M * ldc;
+        int rc = gemm_simt(A, lda, W, M, N, K, ep, s);
+        if (rc) return rc;
+        return splitk_reduce(partial, slices, (size_t)M * ldc, (size_t)M * ldc, out, s);
     }
     // gW[Nw,Kw] = dY[rows,Nw]^T @ X[rows,Kw]: the weight gradient of y = x W^T, operands row-major as the backward holds them
     int wgrad(const ActBuf& dY, int ldy, const ActBuf& X, int ldx, int64_t rows, int Nw, int Kw, float* gW) const {
@@ -571,11 +592,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         // location_projection: lso = pos W_loc2^T + b
         RC(transpose_f32(d_lso, 2 * kDim, N, 2 * kDim, false, DropSpec(), 0, o1, Nb, Nb, ActOut(), 0, s));
         RC(transpose_f32(pos, kPosDim, N, kPosDim, false, DropSpec(), 0, o2, Nb, Nb, ActOut(), 0, s));
-        GemmEpilogue ep;
-        ep.out.f32 = X.f32(T.g_w_loc2);
-        ep.ldc = kPosDim;
         set_tag(TAG_BWD_GEMM);
-        RC(gemm_simt(tb1, (int)Nb, tb2, 2 * kDim, kPosDim, (int)Nb, ep, s));
+        RC(X.mm_small(tb1, (int)Nb, tb2, 2 * kDim, kPosDim, (int)Nb, X.f32(T.g_w_loc2), kPosDim));
         set_tag(TAG_BWD_BOX);
         RC(unpack_halves(X.f32(T.g_w_loc2), g->loc_proj_w, kDim, kPosDim, s));
         RC(X.bias_grad(f32_in(d_lso), 2 * kDim, N, kDim, g->loc_proj_b));
@@ -583,22 +601,16 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         ot.f32 = X.f32(T.loc2T);  // [128, 1152]
         RC(transpose_f32((const float*)(P + L.w_loc2), kPosDim, 2 * kDim, kPosDim, false, DropSpec(), 0, ot, 2 * kDim, 2 * kDim,
                          ActOut(), 0, s));
-        GemmEpilogue e2;
-        e2.out.f32 = X.f32(T.d_pos);
-        e2.ldc = kPosDim;
         set_tag(TAG_BWD_GEMM);
-        RC(gemm_simt(d_lso, 2 * kDim, X.f32(T.loc2T), N, kPosDim, 2 * kDim, e2, s));
+        RC(X.mm_small(d_lso, 2 * kDim, X.f32(T.loc2T), N, kPosDim, 2 * kDim, X.f32(T.d_pos), kPosDim));
         set_tag(TAG_BWD_BOX);
         RC(pos_embed_bwd(in->boxes, N, bn_stats, *w, pos, X.f32(T.d_pos), drop_pos.scale, X.f32(T.pos_partial), X.colsum_scratch,
                          g->pos_w, g->pos_b, g->bn_weight, g->bn_bias, s));
         // class_projection: cso = emb W_cls2^T + b
         RC(transpose_f32(d_cso, 2 * kDim, N, 2 * kDim, false, DropSpec(), 0, o1, Nb, Nb, ActOut(), 0, s));
         RC(transpose_f32(emb, kEmbDim, N, kEmbDim, false, DropSpec(), 0, o2, Nb, Nb, ActOut(), 0, s));
-        GemmEpilogue e3;
-        e3.out.f32 = X.f32(T.g_w_cls2);
-        e3.ldc = kEmbDim;
         set_tag(TAG_BWD_GEMM);
-        RC(gemm_simt(tb1, (int)Nb, tb2, 2 * kDim, kEmbDim, (int)Nb, e3, s));
+        RC(X.mm_small(tb1, (int)Nb, tb2, 2 * kDim, kEmbDim, (int)Nb, X.f32(T.g_w_cls2), kEmbDim));
         set_tag(TAG_BWD_BOX);
         RC(unpack_halves(X.f32(T.g_w_cls2), g->class_proj_w, kDim, kEmbDim, s));
         RC(X.bias_grad(f32_in(d_cso), 2 * kDim, N, kDim, g->class_proj_b));
@@ -606,11 +618,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
         oc.f32 = X.f32(T.cls2T);  // [200, 1152]
         RC(transpose_f32((const float*)(P + L.w_cls2), kEmbDim, 2 * kDim, kEmbDim, false, DropSpec(), 0, oc, 2 * kDim, 2 * kDim,
                          ActOut(), 0, s));
-        GemmEpilogue e4;
-        e4.out.f32 = X.f32(T.d_emb);
-        e4.ldc = kEmbDim;
         set_tag(TAG_BWD_GEMM);
-        RC(gemm_simt(d_cso, 2 * kDim, X.f32(T.cls2T), N, kEmbDim, 2 * kDim, e4, s));
+        RC(X.mm_small(d_cso, 2 * kDim, X.f32(T.cls2T), N, kEmbDim, 2 * kDim, X.f32(T.d_emb), kEmbDim));
         set_tag(TAG_BWD_BOX);
         RC(embed_bwd(X.f32(T.d_emb), in->labels, in->obj_logits, cfg->num_obj, N, g->obj_embed, s));
     }
