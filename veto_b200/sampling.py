@@ -15,6 +15,23 @@ from . import ops
 from .structures import xyxy_boxes
 
 
+class PendingRelSample:
+    """A gtbox_relsample in flight (RelationSampling.gtbox_relsample_async)."""
+
+    def __init__(self, proposals, pairs, labels, counts_host, binaries, event, batch_size):
+        self.proposals, self.pairs, self.labels, self.counts_host = proposals, pairs, labels, counts_host
+        self.binaries, self.event, self.batch_size = binaries, event, batch_size
+
+    def result(self):
+        """(proposals, rel_labels, rel_idx_pairs, rel_sym_binarys), the return value of gtbox_relsample."""
+        self.event.synchronize()
+        totals = self.counts_host[:, 1].tolist()
+        bs = self.batch_size
+        rel_idx_pairs = [self.pairs[b * bs: b * bs + n] for b, n in enumerate(totals)]
+        rel_labels = [self.labels[b * bs: b * bs + n] for b, n in enumerate(totals)]
+        return self.proposals, rel_labels, rel_idx_pairs, self.binaries
+
+
 class RelationSampling:
     def __init__(self, fg_thres=0.5, require_overlap=False, num_sample_per_gt_rel=4, batch_size_per_image=1024,
                  positive_fraction=0.25, max_proposal_pairs=2048, use_gt_box=True, test_overlap=False):
@@ -36,12 +53,11 @@ class RelationSampling:
         return ops.enumerate_pairs(n_boxes, device, self.max_proposal_pairs, boxes=boxes, scores=scores,
                                    require_overlap=overlap)
 
-    def gtbox_relsample(self, proposals, targets):
-        """sampling.py:54-107: (proposals, rel_labels, rel_idx_pairs, rel_sym_binarys) for training on ground-truth
-        boxes — one launch for the batch and ONE host sync (the row counts), instead of a per-image loop with three
-        nonzero syncs and two randperms.  The random subset / order comes from a counter-based hash seeded from torch's
-        CPU generator (torch.manual_seed reproduces a run); foreground rows keep the reference's row-major order when
-        all of them fit."""
+    def gtbox_relsample_async(self, proposals, targets) -> "PendingRelSample":
+        """Enqueue gtbox_relsample for a batch and return without waiting: the one thing the host needs (the row count
+        per image) travels to pinned memory behind the kernel, guarded by an event.  A training loop issues the
+        sampling of step k+1 right at the start of step k — it depends on the targets only — and calls ``result()``
+        one step later, when the event has long fired: the sampler's host sync then never drains the GPU queue."""
         assert self.use_gt_box
         num_pos = int(self.batch_size_per_image * self.positive_fraction)
         for p, t in zip(proposals, targets):
@@ -50,10 +66,19 @@ class RelationSampling:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         pairs, labels, counts, binaries = ops.relsample_gtbox([t.get_field("relation") for t in targets],
                                                               self.batch_size_per_image, num_pos, seed)
-        totals = counts[:, 1].tolist()
-        rel_idx_pairs = [pairs[b * self.batch_size_per_image: b * self.batch_size_per_image + n] for b, n in enumerate(totals)]
-        rel_labels = [labels[b * self.batch_size_per_image: b * self.batch_size_per_image + n] for b, n in enumerate(totals)]
-        return proposals, rel_labels, rel_idx_pairs, binaries
+        counts_host = torch.empty(counts.shape, dtype=counts.dtype).pin_memory()
+        counts_host.copy_(counts, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        return PendingRelSample(proposals, pairs, labels, counts_host, binaries, event, self.batch_size_per_image)
+
+    def gtbox_relsample(self, proposals, targets):
+        """sampling.py:54-107: (proposals, rel_labels, rel_idx_pairs, rel_sym_binarys) for training on ground-truth
+        boxes — one launch for the batch and ONE host sync (the row counts), instead of a per-image loop with three
+        nonzero syncs and two randperms.  The random subset / order comes from a counter-based hash seeded from torch's
+        CPU generator (torch.manual_seed reproduces a run); foreground rows keep the reference's row-major order when
+        all of them fit."""
+        return self.gtbox_relsample_async(proposals, targets).result()
 
     def detect_relsample(self, proposals, targets):
         raise NotImplementedError("detect_relsample (SGDet training sampler, sampling.py:109-309) is a 'next' row (SURVEY.md §8 f2)")
