@@ -339,6 +339,18 @@ int veto_postprocess_meet(const float* group_logits_dev, int num_out, const int3
                           const int32_t* box_offsets_dev, int n_images, int64_t n_pairs, int64_t* pairs_out_dev,
                           float* probs_out_dev, int64_t* labels_out_dev, float* triple_out_dev, veto_stream_t stream);
 
+/* f4. Triplet matching of the recall metrics: SGRecall.calculate_recall -> _compute_pred_matches
+ * (pysgg/data/datasets/evaluation/vg/sgg_eval.py:44-117,138-186), non-phrdet modes, a batch of images in one launch.
+ * A triplet row = (subject class, predicate, object class), a box row = (subject xyxy, object xyxy) fp32 [.,8];
+ * image b's ground-truth rows are gt_offsets[b] .. gt_offsets[b+1], its predictions (in rank order) pred_offsets[b] ..
+ * A prediction matches a ground-truth triplet when the three labels are equal and both boxes overlap by IoU >=
+ * iou_thres (boxlist_iou, +1 convention, fp32).  first_match_dev int32 [G]: rank (within the image) of the first
+ * matching prediction, INT32_MAX = none — recall@K of an image = #{g : first_match[g] < K} / G_b (:158-160);
+ * pred_hits_dev int32 [P]: number of ground-truth triplets each prediction matches (len(pred_to_gt[p])). */
+int veto_sgg_match(const int64_t* gt_triplets_dev, const float* gt_boxes_dev, const int32_t* gt_offsets_dev,
+                   const int64_t* pred_triplets_dev, const float* pred_boxes_dev, const int32_t* pred_offsets_dev,
+                   int n_images, float iou_thres, int32_t* first_match_dev, int32_t* pred_hits_dev, veto_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a10. Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874) with nms_overlaps
  * (relation_head/utils_relation.py:56-79): MEET's greedy per-class label assignment at SGDet test time.

@@ -130,7 +130,7 @@ def load():
     if not hasattr(_tvr, "model_urls"):
         _tvr.model_urls = {}
     for name in ["ipdb", "matplotlib", "matplotlib.pyplot", "matplotlib.image", "pysgg._C", "apex",
-                 "pycocotools", "pycocotools.mask", "h5py", "cv2", "tensorboardX", "termcolor",
+                 "pycocotools", "pycocotools.mask", "pycocotools.coco", "pycocotools.cocoeval", "h5py", "cv2", "tensorboardX", "termcolor",
                  "overrides", "graphviz", "gpustat"]:
         try:
             __import__(name)

@@ -484,3 +484,28 @@ def gtbox_relsample_candidates(rel: np.ndarray):
     poss[fg[:, 0], fg[:, 1]] = 0
     bg = np.argwhere(poss > 0).astype(np.int64).reshape(-1, 2)
     return fg, labels, bg, binary
+
+
+def compute_pred_matches(gt_triplets, pred_triplets, gt_boxes, pred_boxes, iou_thres: float):
+    """_compute_pred_matches (data/datasets/evaluation/vg/sgg_eval.py:77-117), non-phrdet: pred_to_gt as a list of
+    lists (ground-truth indices matched by each prediction, ascending)."""
+    keeps = (gt_triplets[..., None] == pred_triplets.T[None, ...]).all(1)     # intersect_2d, utils/miscellaneous.py:47-61
+    pred_to_gt = [[] for _ in range(pred_boxes.shape[0])]
+    for g in np.where(keeps.any(1))[0]:
+        idx = np.where(keeps[g])[0]
+        sub = boxlist_iou(gt_boxes[g:g + 1, :4].astype(f32), pred_boxes[idx, :4].astype(f32))[0]
+        obj = boxlist_iou(gt_boxes[g:g + 1, 4:].astype(f32), pred_boxes[idx, 4:].astype(f32))[0]
+        for i in idx[(sub >= iou_thres) & (obj >= iou_thres)]:
+            pred_to_gt[int(i)].append(int(g))
+    return pred_to_gt
+
+
+def recall_at_k(pred_to_gt, n_gt: int, ks=(20, 50, 100)):
+    """SGRecall.calculate_recall (:155-160): recall@k = |union of pred_to_gt[:k]| / n_gt."""
+    out = {}
+    for k in ks:
+        match = set()
+        for m in pred_to_gt[:k]:
+            match |= set(m)
+        out[k] = len(match) / float(n_gt)
+    return out

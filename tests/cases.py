@@ -70,6 +70,11 @@ RELSAMPLE_CASES = {
     "relsample_over_caps": dict(n_boxes=[20, 9, 12], seed=32, fg_per_image=14, caps=(32, 0.25)),
 }
 
+# recall-evaluation fixtures (SGRecall.calculate_recall of the reference on synth.make_eval_case)
+EVAL_CASES = {
+    "eval_recall": dict(seed=41, n_objs=[20, 9, 2, 14], n_gt_rels=12, n_pred_rels=150),
+}
+
 
 def case_rel_labels(c, pair_counts):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA

@@ -332,8 +332,43 @@ def run_relsample_case(ns, name, c):
     print(f"{name}: wrote {path}", [(len(p), int((l > 0).sum())) for p, l in zip(rel_idx_pairs, rel_labels)])
 
 
+def run_eval_case(ns, name, c):
+    """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGRecall
+    imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
+    result_dict = {}
+    ev = SGRecall(result_dict)
+    ev.register_container("sgdet")
+    out = {"n_images": np.array(len(imgs))}
+    for i, im in enumerate(imgs):
+        local = dict(pred_rel_inds=im["rel_pair_idxs"], rel_scores=im["pred_rel_scores"], gt_rels=im["relation_tuple"],
+                     gt_classes=im["labels"], gt_boxes=im["boxes"], pred_classes=im["pred_labels"],
+                     pred_boxes=im["pred_boxes"], obj_scores=np.ones(len(im["labels"]), np.float32))
+        local = ev.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
+        p2g = local["pred_to_gt"]
+        first = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
+        for p, gs in enumerate(p2g):
+            for g in gs:
+                first[g] = min(first[g], p)
+        out[f"first_match/{i}"] = first
+        out[f"pred_hits/{i}"] = np.array([len(g) for g in p2g], np.int64)
+    for k in (20, 50, 100):
+        out[f"recall/{k}"] = np.array(result_dict["sgdet_recall"][k], np.float64)
+        per = {}
+        for d in result_dict["sgdet_recall_per_rel"][k]:
+            for r, (h, n) in d.items():
+                e = per.setdefault(int(r), [0, 0])
+                e[0] += int(h)
+                e[1] += int(n)
+        out[f"per_rel/{k}"] = np.array([[r, h, n] for r, (h, n) in sorted(per.items())], np.int64)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path}", {k: out[f'recall/{k}'].round(3).tolist() for k in (20, 50, 100)})
+
+
 def main():
-    from tests.cases import MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
+    from tests.cases import EVAL_CASES, MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
     ns = ref_shim.load()
     only = sys.argv[1:]
     for name, c in CASES.items():
@@ -352,6 +387,10 @@ def main():
         if only and name not in only:
             continue
         run_relsample_case(ns, name, c)
+    for name, c in EVAL_CASES.items():
+        if only and name not in only:
+            continue
+        run_eval_case(ns, name, c)
     if not only or "meet_sample_rates" in only:
         run_sample_rates()
 

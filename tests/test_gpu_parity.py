@@ -298,6 +298,73 @@ def test_meet_per_class_nms_bit_exact():
         assert (ref != scores[:, 1:].argmax(1) + 1).any()          # suppression happened
 
 
+def test_recall_evaluation_matches_reference():
+    """veto_sgg_match + evaluation.recall_at_k against SGRecall.calculate_recall of the unmodified
+    reference: per ground-truth triplet the rank of the first matching prediction, per prediction the number of
+    matches, recall@20/50/100 per image and the per-predicate hit counts — all exact."""
+    from tests.cases import EVAL_CASES
+    from veto_b200 import evaluation as E
+    from veto_b200.structures import BoxList
+    c, g = EVAL_CASES["eval_recall"], load_golden("eval_recall")
+    imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
+    preds, gts = [], []
+    for im in imgs:
+        gt = BoxList(_t(im["boxes"]), im["size"], "xyxy")
+        gt.add_field("labels", _t(im["labels"]))
+        gt.add_field("relation_tuple", _t(im["relation_tuple"]))
+        pr = BoxList(_t(im["pred_boxes"]), im["size"], "xyxy")
+        pr.add_field("pred_labels", _t(im["pred_labels"]))
+        pr.add_field("rel_pair_idxs", _t(im["rel_pair_idxs"]))
+        pr.add_field("pred_rel_scores", _t(im["pred_rel_scores"]))
+        preds.append(pr)
+        gts.append(gt)
+    # an image without ground-truth relations is skipped (vg_eval.py:473-474)
+    empty = BoxList(_t(imgs[0]["boxes"]), imgs[0]["size"], "xyxy")
+    empty.add_field("labels", _t(imgs[0]["labels"]))
+    empty.add_field("relation_tuple", torch.zeros((0, 3), dtype=torch.int64, device=DEV))
+    out = E.recall_at_k(preds[:2] + [preds[0]] + preds[2:], gts[:2] + [empty] + gts[2:])
+    assert len(out["first_match"]) == len(imgs)
+    for i in range(len(imgs)):
+        assert np.array_equal(out["first_match"][i].numpy().astype(np.int64), g[f"first_match/{i}"])
+    for k in (20, 50, 100):
+        assert np.array_equal(np.array(out["recall"][k]), g[f"recall/{k}"])
+        per = np.array([[r, h, n] for r, (h, n) in sorted(out["hits_per_rel"][k].items())], np.int64)
+        assert np.array_equal(per, g[f"per_rel/{k}"])
+    # raw kernel outputs incl. the per-prediction match counts
+    gt_t, gt_b, pr_t, pr_b = [], [], [], []
+    for pr, gt in zip(preds, gts):
+        rt = gt.get_field("relation_tuple")
+        t, b = E.triplets(rt[:, :2], rt[:, 2], gt.get_field("labels"), gt.bbox)
+        gt_t.append(t); gt_b.append(b)
+        lab = 1 + pr.get_field("pred_rel_scores")[:, 1:].argmax(1)
+        t, b = E.triplets(pr.get_field("rel_pair_idxs"), lab, pr.get_field("pred_labels"), pr.bbox)
+        pr_t.append(t); pr_b.append(b)
+    first, hits = ops.sgg_match(torch.cat(gt_t), torch.cat(gt_b), [len(t) for t in gt_t], torch.cat(pr_t), torch.cat(pr_b),
+                                [len(t) for t in pr_t], 0.5)
+    assert np.array_equal(H.np_(hits), np.concatenate([g[f"pred_hits/{i}"] for i in range(len(imgs))]))
+    assert np.array_equal(H.np_(first).astype(np.int64), np.concatenate([g[f"first_match/{i}"] for i in range(len(imgs))]))
+    # a larger seeded batch against the numpy oracle
+    big = synth.make_eval_case(77, [40, 33, 25, 60, 12, 48], n_gt_rels=40, n_pred_rels=1000)
+    gt_t, gt_b, pr_t, pr_b, ref_first = [], [], [], [], []
+    for im in big:
+        s, o, p = im["relation_tuple"][:, 0], im["relation_tuple"][:, 1], im["relation_tuple"][:, 2]
+        gtt, gtb = np.column_stack((im["labels"][s], p, im["labels"][o])), np.column_stack((im["boxes"][s], im["boxes"][o]))
+        ps, po = im["rel_pair_idxs"][:, 0], im["rel_pair_idxs"][:, 1]
+        prt = np.column_stack((im["pred_labels"][ps], 1 + im["pred_rel_scores"][:, 1:].argmax(1), im["pred_labels"][po]))
+        prb = np.column_stack((im["pred_boxes"][ps], im["pred_boxes"][po]))
+        p2g = O.compute_pred_matches(gtt, prt, gtb, prb, 0.5)
+        f = np.full(len(gtt), 2 ** 31 - 1, np.int64)
+        for k, gs in enumerate(p2g):
+            for gi in gs:
+                f[gi] = min(f[gi], k)
+        ref_first.append(f)
+        gt_t.append(gtt); gt_b.append(gtb); pr_t.append(prt); pr_b.append(prb)
+    first, _ = ops.sgg_match(_t(np.concatenate(gt_t)), _t(np.concatenate(gt_b)), [len(t) for t in gt_t],
+                             _t(np.concatenate(pr_t)), _t(np.concatenate(pr_b)), [len(t) for t in pr_t], 0.5)
+    assert np.array_equal(H.np_(first).astype(np.int64), np.concatenate(ref_first))
+    assert (np.concatenate(ref_first) < 2 ** 31 - 1).mean() > 0.3
+
+
 @pytest.mark.parametrize("name", ["relsample_under_caps", "relsample_over_caps"])
 def test_gtbox_relsample(name):
     """RelationSampling.gtbox_relsample on the device against the unmodified reference's output on

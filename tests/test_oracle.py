@@ -351,3 +351,30 @@ def test_gtbox_relsample_candidates_match_reference(name):
         assert len(set(got_bg)) == n_bg and set(got_bg) <= bgset and np.all(ref_labels[n_fg:] == 0)
         if len(bg) <= batch - n_fg:
             assert set(got_bg) == bgset
+
+
+def test_recall_matching_matches_reference():
+    """oracle.compute_pred_matches / recall_at_k against SGRecall.calculate_recall of the unmodified reference."""
+    from tests.cases import EVAL_CASES
+    c, g = EVAL_CASES["eval_recall"], load_golden("eval_recall")
+    imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
+    assert int(g["n_images"]) == len(imgs)
+    for i, im in enumerate(imgs):
+        s, o, p = im["relation_tuple"][:, 0], im["relation_tuple"][:, 1], im["relation_tuple"][:, 2]
+        gt_t = np.column_stack((im["labels"][s], p, im["labels"][o]))
+        gt_b = np.column_stack((im["boxes"][s], im["boxes"][o]))
+        pl = 1 + im["pred_rel_scores"][:, 1:].argmax(1)
+        ps, po = im["rel_pair_idxs"][:, 0], im["rel_pair_idxs"][:, 1]
+        pr_t = np.column_stack((im["pred_labels"][ps], pl, im["pred_labels"][po]))
+        pr_b = np.column_stack((im["pred_boxes"][ps], im["pred_boxes"][po]))
+        p2g = O.compute_pred_matches(gt_t, pr_t, gt_b, pr_b, 0.5)
+        first = np.full(len(gt_t), 2 ** 31 - 1, np.int64)
+        for k, gs in enumerate(p2g):
+            for gi in gs:
+                first[gi] = min(first[gi], k)
+        assert np.array_equal(first, g[f"first_match/{i}"])
+        assert np.array_equal(np.array([len(x) for x in p2g]), g[f"pred_hits/{i}"])
+        rec = O.recall_at_k(p2g, len(gt_t))
+        for k in (20, 50, 100):
+            assert rec[k] == g[f"recall/{k}"][i]
+    assert g["recall/100"].max() > 0.5 and g["recall/20"].min() < 0.2      # the case discriminates

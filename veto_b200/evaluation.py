@@ -1,0 +1,67 @@
+"""Recall of the scene-graph evaluation on the device.
+
+Mirrors ``SGRecall.calculate_recall`` (pysgg/data/datasets/evaluation/vg/sgg_eval.py:138-186) for a batch of images:
+the reference moves every prediction to the host, builds (subject class, predicate, object class) triplets with numpy
+and matches them image by image on rank 0; here the predictions stay where the post-processor left them and
+``veto_sgg_match`` matches all images in one launch.  Only the final per-image numbers cross to the host.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+
+from . import ops
+
+
+def triplets(rel_pairs: torch.Tensor, rel_labels: torch.Tensor, classes: torch.Tensor, boxes: torch.Tensor):
+    """_triplet (sgg_eval.py:44-74): (triplets int64 [R,3] = (subject class, predicate, object class), boxes [R,8])."""
+    s, o = rel_pairs[:, 0].long(), rel_pairs[:, 1].long()
+    return torch.stack((classes[s].long(), rel_labels.long(), classes[o].long()), 1), torch.cat((boxes[s], boxes[o]), 1)
+
+
+def recall_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), iou_thres: float = 0.5,
+                predcls_like: bool = False) -> Dict[str, object]:
+    """predictions: the post-processor's BoxLists (fields rel_pair_idxs, pred_rel_scores, pred_labels; ranked rows);
+    groundtruths: BoxLists with fields labels and relation_tuple [G,3] = (subject idx, object idx, predicate)
+    (vg_eval.py:469-495).  predcls_like: take boxes / classes from the ground truth (PredCls, vg_eval.py:512-515).
+    Returns {'recall': {k: [per image]}, 'hits_per_rel': {k: {predicate: [hits, count]}}, 'first_match': [per image]}.
+    Images without ground-truth relations are skipped like the reference does (vg_eval.py:473-474)."""
+    gt_t, gt_b, pr_t, pr_b, gt_n, pr_n, gt_pred = [], [], [], [], [], [], []
+    for pred, gt in zip(predictions, groundtruths):
+        rel_tuple = gt.get_field("relation_tuple").long()
+        if rel_tuple.shape[0] == 0:
+            continue
+        gt_cls, gt_box = gt.get_field("labels").long(), gt.convert("xyxy").bbox
+        t, b = triplets(rel_tuple[:, :2], rel_tuple[:, 2], gt_cls, gt_box)
+        gt_t.append(t)
+        gt_b.append(b)
+        gt_n.append(t.shape[0])
+        gt_pred.append(rel_tuple[:, 2])
+        scores = pred.get_field("pred_rel_scores")
+        labels = 1 + scores[:, 1:].argmax(1)                                       # :152
+        cls, box = (gt_cls, gt_box) if predcls_like else (pred.get_field("pred_labels").long(), pred.convert("xyxy").bbox)
+        t, b = triplets(pred.get_field("rel_pair_idxs").long(), labels, cls, box)
+        pr_t.append(t)
+        pr_b.append(b)
+        pr_n.append(t.shape[0])
+    out = {"recall": {k: [] for k in ks}, "hits_per_rel": {k: {} for k in ks}, "first_match": []}
+    if not gt_t:
+        return out
+    first, _ = ops.sgg_match(torch.cat(gt_t), torch.cat(gt_b), gt_n, torch.cat(pr_t), torch.cat(pr_b), pr_n, iou_thres)
+    first_host = first.cpu()
+    preds_host = torch.cat(gt_pred).cpu()
+    off = 0
+    for n in gt_n:
+        fm, pr = first_host[off:off + n], preds_host[off:off + n]
+        off += n
+        out["first_match"].append(fm)
+        for k in ks:
+            hit = fm < k
+            out["recall"][k].append(float(hit.sum()) / float(n))                    # :158-160
+            per = out["hits_per_rel"][k]
+            for r, h in zip(pr.tolist(), hit.tolist()):                             # :161-168
+                e = per.setdefault(r, [0, 0])
+                e[0] += int(h)
+                e[1] += 1
+    return out

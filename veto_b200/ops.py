@@ -525,6 +525,36 @@ def postprocess_meet(group_logits: torch.Tensor, head_sizes: Sequence[int], col_
 
 
 # --------------------------------------------------------------------------------------------
+# f4: evaluation triplet matching
+# --------------------------------------------------------------------------------------------
+def sgg_match(gt_triplets: torch.Tensor, gt_boxes: torch.Tensor, gt_counts: Sequence[int], pred_triplets: torch.Tensor,
+              pred_boxes: torch.Tensor, pred_counts: Sequence[int], iou_thres: float = 0.5):
+    """_compute_pred_matches (sgg_eval.py:77-117) for a batch: triplets int64 [.,3], boxes fp32 [.,8] (subject xyxy,
+    object xyxy), per-image row counts.  Returns (first_match int32 [G] — rank of the first matching prediction within
+    the image, INT32_MAX = none —, pred_hits int32 [P] — ground-truth triplets matched by each prediction)."""
+    L.require_device()
+    gt_boxes, pred_boxes = _cuda_f32(gt_boxes), _cuda_f32(pred_boxes)
+    gt_triplets = gt_triplets.to(torch.int64).contiguous()
+    pred_triplets = pred_triplets.to(torch.int64).contiguous()
+    dev = gt_boxes.device
+    G, P = gt_triplets.shape[0], pred_triplets.shape[0]
+    if sum(gt_counts) != G or sum(pred_counts) != P or len(gt_counts) != len(pred_counts):
+        raise RuntimeError("per-image counts do not match the triplet rows")
+    if tuple(gt_boxes.shape) != (G, 8) or tuple(pred_boxes.shape) != (P, 8):
+        raise RuntimeError("triplet boxes must be [rows, 8]")
+    first = torch.full((G,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+    hits = torch.zeros(P, dtype=torch.int32, device=dev)
+    if G and P:
+        g_off, p_off = offsets_tensor(gt_counts, dev), offsets_tensor(pred_counts, dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().veto_sgg_match(gt_triplets.data_ptr(), gt_boxes.data_ptr(), g_off.data_ptr(),
+                                            pred_triplets.data_ptr(), pred_boxes.data_ptr(), p_off.data_ptr(),
+                                            len(gt_counts), float(iou_thres), first.data_ptr(), hits.data_ptr(),
+                                            L.stream_ptr()), "veto_sgg_match")
+    return first, hits
+
+
+# --------------------------------------------------------------------------------------------
 # launch accounting / per-stage device timing (bench.py)
 # --------------------------------------------------------------------------------------------
 def launch_count() -> int:
