@@ -638,6 +638,38 @@ def test_full_size_sgdet_batch_properties():
     assert np.array_equal(a[sel].argmax(1), ref.argmax(1))
 
 
+@pytest.mark.parametrize("mode", ["predcls", "sgdet"])
+def test_image_sharding_is_exact(mode):
+    """BASELINE.json configs[4] (per-image sharded PredCls + SGDet sweep): images are independent, so running the
+    pair-count-balanced shards of a mixed batch one by one (what ranks 0..3 of a 4-GPU job would each run) reproduces
+    the unsharded batch BITWISE — logits, pairs and ROI features — in the headline bf16x3 mode."""
+    from veto_b200 import distributed as vdist
+    n_boxes = [20, 80, 20, 33, 80, 5, 20, 1, 47]
+    batch = synth.make_batch(51, n_boxes, H=320, W=416, mode=mode)
+    state = synth.predictor_state(13)
+    cfg = H.make_cfg(mode=mode, max_pairs=8192, precision="bf16x3")
+    full = H.run_head(cfg, state, batch, DEV, post=False)
+    shards = vdist.shard_images(n_boxes, 4, 8192)
+    assert sorted(i for s in shards for i in s) == list(range(len(n_boxes)))
+    loads = [sum(vdist.pair_count(n_boxes[i], 8192) for i in s) for s in shards]
+    biggest = max(vdist.pair_count(n, 8192) for n in n_boxes)            # LPT balance by pair count, not image count
+    assert max(loads) <= max(biggest, 4.0 / 3.0 * sum(loads) / 4)
+    for shard in shards:
+        sub = dict(batch, B=len(shard), n_boxes=[n_boxes[i] for i in shard])
+        for k in ("boxes", "labels", "predict_logits", "pred_labels", "pred_scores"):
+            if k in batch:
+                sub[k] = [batch[k][i] for i in shard]
+        sub["feats"] = [f[shard] for f in batch["feats"]]
+        sub["depth"] = batch["depth"][shard]
+        part = H.run_head(cfg, state, sub, DEV, post=False)
+        box_off = np.concatenate([[0], np.cumsum(n_boxes)])
+        for j, i in enumerate(shard):
+            assert torch.equal(part["pairs"][j], full["pairs"][i])
+            assert torch.equal(part["rel_dists"][j], full["rel_dists"][i]), (mode, i)
+        rows = np.concatenate([np.arange(box_off[i], box_off[i + 1]) for i in shard])
+        assert torch.equal(part["x2d"], full["x2d"][rows]) and torch.equal(part["d2d"], full["d2d"][rows])
+
+
 def test_no_cpu_fallback_and_errors():
     with pytest.raises(RuntimeError):
         ops.roi_align_forward(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 1.0, 2, 2, 2)      # CPU tensors
