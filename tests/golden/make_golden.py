@@ -335,17 +335,20 @@ def run_relsample_case(ns, name, c):
 def run_eval_case(ns, name, c):
     """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
     sys.path.insert(0, ref_shim.REF_ROOT)
-    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGRecall
+    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGMeanRecall, SGRecall
     imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
     result_dict = {}
     ev = SGRecall(result_dict)
     ev.register_container("sgdet")
+    mr = SGMeanRecall(result_dict, 51, ["__background__"] + [f"rel{i}" for i in range(1, 51)])
+    mr.register_container("sgdet")
     out = {"n_images": np.array(len(imgs))}
     for i, im in enumerate(imgs):
         local = dict(pred_rel_inds=im["rel_pair_idxs"], rel_scores=im["pred_rel_scores"], gt_rels=im["relation_tuple"],
                      gt_classes=im["labels"], gt_boxes=im["boxes"], pred_classes=im["pred_labels"],
                      pred_boxes=im["pred_boxes"], obj_scores=np.ones(len(im["labels"]), np.float32))
         local = ev.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
+        mr.collect_mean_recall_items({"iou_thres": 0.5}, local, "sgdet")
         p2g = local["pred_to_gt"]
         first = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
         for p, gs in enumerate(p2g):
@@ -353,7 +356,10 @@ def run_eval_case(ns, name, c):
                 first[g] = min(first[g], p)
         out[f"first_match/{i}"] = first
         out[f"pred_hits/{i}"] = np.array([len(g) for g in p2g], np.int64)
+    mr.calculate_mean_recall("sgdet")
     for k in (20, 50, 100):
+        out[f"mean_recall/{k}"] = np.array(result_dict["sgdet_mean_recall"][k], np.float64)
+        out[f"mean_recall_list/{k}"] = np.array(result_dict["sgdet_mean_recall_list"][k], np.float64)
         out[f"recall/{k}"] = np.array(result_dict["sgdet_recall"][k], np.float64)
         per = {}
         for d in result_dict["sgdet_recall_per_rel"][k]:

@@ -330,6 +330,10 @@ def test_recall_evaluation_matches_reference():
         assert np.array_equal(np.array(out["recall"][k]), g[f"recall/{k}"])
         per = np.array([[r, h, n] for r, (h, n) in sorted(out["hits_per_rel"][k].items())], np.int64)
         assert np.array_equal(per, g[f"per_rel/{k}"])
+    mr = E.mean_recall(out["first_match"], out["gt_predicates"], 51)                # SGMeanRecall (:424-466)
+    for k in (20, 50, 100):
+        assert np.allclose(mr["mean_recall_list"][k], g[f"mean_recall_list/{k}"], rtol=1e-12, atol=0)
+        assert abs(mr["mean_recall"][k] - float(g[f"mean_recall/{k}"])) <= 1e-12
     # raw kernel outputs incl. the per-prediction match counts
     gt_t, gt_b, pr_t, pr_b = [], [], [], []
     for pr, gt in zip(preds, gts):

@@ -167,3 +167,18 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "configs[1]" in line["config"]["workload"] and line["inference"]["value"] > 0
+
+
+def test_mean_recall_from_first_match_matches_reference():
+    """evaluation.mean_recall (host arithmetic over the kernel's first-match ranks) against SGMeanRecall of the
+    unmodified reference (sgg_eval.py:424-466), fed with the reference's own matches."""
+    from tests.cases import EVAL_CASES
+    from veto_b200 import evaluation as E
+    c, g = EVAL_CASES["eval_recall"], load_golden("eval_recall")
+    imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
+    fm = [torch.from_numpy(g[f"first_match/{i}"]) for i in range(len(imgs))]
+    pr = [torch.from_numpy(im["relation_tuple"][:, 2]) for im in imgs]
+    mr = E.mean_recall(fm, pr, 51)
+    for k in (20, 50, 100):
+        assert np.allclose(mr["mean_recall_list"][k], g[f"mean_recall_list/{k}"], rtol=1e-12, atol=0)
+        assert abs(mr["mean_recall"][k] - float(g[f"mean_recall/{k}"])) <= 1e-12

@@ -20,12 +20,35 @@ def triplets(rel_pairs: torch.Tensor, rel_labels: torch.Tensor, classes: torch.T
     return torch.stack((classes[s].long(), rel_labels.long(), classes[o].long()), 1), torch.cat((boxes[s], boxes[o]), 1)
 
 
+def mean_recall(first_match: Sequence[torch.Tensor], gt_predicates: Sequence[torch.Tensor], num_rel: int,
+                ks: Sequence[int] = (20, 50, 100)) -> Dict[str, object]:
+    """SGMeanRecall.collect_mean_recall_items + calculate_mean_recall (sgg_eval.py:424-466) from the first-match ranks:
+    per image and predicate class the fraction of its ground-truth triplets matched within the first k predictions;
+    a class's recall = the mean over the images that contain it (0 if none does); mR@k = the mean over the num_rel - 1
+    foreground classes.  Returns {'mean_recall': {k: float}, 'mean_recall_list': {k: [per class]}}."""
+    collect = {k: [[] for _ in range(num_rel)] for k in ks}
+    for fm, pr in zip(first_match, gt_predicates):
+        pr = pr.long().cpu()
+        count = torch.bincount(pr, minlength=num_rel)
+        for k in ks:
+            hit = torch.bincount(pr[fm.cpu() < k], minlength=num_rel)
+            for n in torch.nonzero(count).flatten().tolist():
+                collect[k][n].append(float(hit[n]) / float(count[n]))
+    out = {"mean_recall": {}, "mean_recall_list": {}}
+    for k in ks:
+        per_class = [sum(v) / len(v) if v else 0.0 for v in collect[k][1:]]
+        out["mean_recall_list"][k] = per_class
+        out["mean_recall"][k] = sum(per_class) / float(num_rel - 1)
+    return out
+
+
 def recall_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), iou_thres: float = 0.5,
                 predcls_like: bool = False) -> Dict[str, object]:
     """predictions: the post-processor's BoxLists (fields rel_pair_idxs, pred_rel_scores, pred_labels; ranked rows);
     groundtruths: BoxLists with fields labels and relation_tuple [G,3] = (subject idx, object idx, predicate)
     (vg_eval.py:469-495).  predcls_like: take boxes / classes from the ground truth (PredCls, vg_eval.py:512-515).
-    Returns {'recall': {k: [per image]}, 'hits_per_rel': {k: {predicate: [hits, count]}}, 'first_match': [per image]}.
+    Returns {'recall': {k: [per image]}, 'hits_per_rel': {k: {predicate: [hits, count]}}, 'first_match': [per image],
+    'gt_predicates': [per image]} — feed the last two to mean_recall() for mR@k.
     Images without ground-truth relations are skipped like the reference does (vg_eval.py:473-474)."""
     gt_t, gt_b, pr_t, pr_b, gt_n, pr_n, gt_pred = [], [], [], [], [], [], []
     for pred, gt in zip(predictions, groundtruths):
@@ -45,7 +68,7 @@ def recall_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), io
         pr_t.append(t)
         pr_b.append(b)
         pr_n.append(t.shape[0])
-    out = {"recall": {k: [] for k in ks}, "hits_per_rel": {k: {} for k in ks}, "first_match": []}
+    out = {"recall": {k: [] for k in ks}, "hits_per_rel": {k: {} for k in ks}, "first_match": [], "gt_predicates": []}
     if not gt_t:
         return out
     first, _ = ops.sgg_match(torch.cat(gt_t), torch.cat(gt_b), gt_n, torch.cat(pr_t), torch.cat(pr_b), pr_n, iou_thres)
@@ -56,6 +79,7 @@ def recall_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), io
         fm, pr = first_host[off:off + n], preds_host[off:off + n]
         off += n
         out["first_match"].append(fm)
+        out["gt_predicates"].append(pr)
         for k in ks:
             hit = fm < k
             out["recall"][k].append(float(hit.sum()) / float(n))                    # :158-160
