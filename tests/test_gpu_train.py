@@ -293,3 +293,22 @@ def test_training_branch_errors():
     pred = registry.make_roi_relation_predictor(cfg, 512).to(DEV).train()
     with pytest.raises(Exception):            # no proposals / pairs: a training step needs at least one of each
         pred([], [], [], None, roi_features=None, roi_depth_features=None)
+
+
+@pytest.mark.parametrize("shape", [(1000, 576, 576), (3000, 1728, 576), (2500, 576, 1152), (777, 1152, 576), (300, 200, 72),
+                                   (130, 256, 384), (4000, 576, 2048), (513, 64, 136)])
+@pytest.mark.parametrize("split_k", [1, 4])
+def test_weight_gradient_gemm_mixed_tiles(shape, split_k):
+    """gemm_tn2 (dW = dY^T X, both operands in place) with its mixed 256 / 128-wide column tiles: every width
+    combination the encoder produces (576 = 256 + 256 + 64-of-128, 1152 = 4 x 256 + 128, 2048 = 8 x 256) plus ragged
+    shapes, with and without split-K, against float64."""
+    rows, Nw, Kw = shape
+    g = torch.Generator(device=DEV).manual_seed(rows + Nw + Kw)
+    y = torch.randn(rows, Nw, generator=g, device=DEV)
+    x = torch.randn(rows, Kw, generator=g, device=DEV)
+    ref = y.double().t() @ x.double()
+    for precision, tol in (("bf16x3", 3e-5), ("bf16", 2e-2)):
+        out = ops.test_gemm_tn(y, x, precision, split_k, None)
+        torch.cuda.synchronize()
+        err = float((out.double() - ref).abs().max() / ref.abs().max())
+        assert out.shape == (Nw, Kw) and err < tol, (shape, split_k, precision, err)

@@ -208,6 +208,8 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
 // how many slices a request really produces).  geometry = {LBO, SBO, K advance} bytes, NULL = the production constants.
 bool gemm_tn2_supported(int Nw, int Kw, int ld_y, int ld_x);
 int gemm_tn2_slices(int rows, int split_k);
+int gemm_tn2_mn_tiles(int Nw, int Kw);                                  // output tiles per K slice (mixed 256 / 128-wide)
+double gemm_tn2_efficiency(int Nw, int Kw, int slices, int pairs);         // busy fraction of the CTA pairs for a slice count
 int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
              size_t split_stride, cudaStream_t s, const uint32_t* geometry = nullptr);
 // picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc

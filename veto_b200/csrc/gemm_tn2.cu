@@ -10,16 +10,25 @@
 // No transposed copies of the activations are ever written (the first version of the backward spent 10 ms of a 51 ms
 // step on them, profiles/r1_train_launches_v1.txt).
 //
-// Everything else follows gemm_tc2.cu: a cluster of two CTAs owns a 256 x 128 output tile (tcgen05 cta_group::2,
-// M = 256, N = 128, K = 16), warp-specialised TMA / MMA / 12 epilogue warps, TMEM double buffering, one pipeline stage
-// serving the three products of the bf16x3 split, and split-K over the rows (tiny output, huge reduction): partial
-// tiles are written as plain fp32 and summed in a fixed order by splitk_reduce (train.cu).  Rows beyond the end of the
-// arrays are zero-filled by TMA, so the row count needs no padding.
+// Everything else follows gemm_tc2.cu: a cluster of two CTAs owns an output tile (tcgen05 cta_group::2, M = 256,
+// K = 16), warp-specialised TMA / MMA / 12 epilogue warps, TMEM double buffering, one pipeline stage serving the three
+// products of the bf16x3 split, and split-K over the rows (tiny output, huge reduction): partial tiles are written as
+// plain fp32 and summed in a fixed order by splitk_reduce (train.cu).  Rows beyond the end of the arrays are
+// zero-filled by TMA, so the row count needs no padding.
+//
+// Tile width: the first version used 256 x 128 tiles and ran at 62-68 % tensor-active (profiles/r1_train_ncu_full.txt):
+// per pipeline stage each SM writes 48 KB (TMA) and reads 72 KB (3 products x (A 16 KB + its half of B 8 KB)) for 816
+// tensor cycles = 147 B/clk, above the 128 B/clk shared-memory port.  A 256-wide tile halves the A traffic per MMA
+// cycle (160 KB per 1632 cycles = 98 B/clk), but the 576-wide outputs are 2.25 such tiles.  So the column range of an
+// output is cut into 256-wide tiles plus, for a remainder of at most 128 columns, one 128-wide tile (576 = 256 + 256 +
+// 64 of 128; 1152 = 4 x 256 + 128): the tile width is a per-tile runtime value (instruction descriptor, number of B
+// boxes, bytes expected by the stage barrier, epilogue chunk count), the stage layout is that of the wide tile.
 #include <cuda.h>
 #include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -27,8 +36,8 @@ namespace veto {
 namespace {
 
 constexpr int BLOCK_M = 128;      // output rows (Nw) per CTA, 256 per pair
-constexpr int BLOCK_N = 128;      // output columns (Kw) per pair tile; each CTA stages 64 of them
-constexpr int HALF_N = BLOCK_N / 2;
+constexpr int WIDE_N = 256;       // output columns (Kw) per wide pair tile; each CTA stages half of them
+constexpr int NARROW_N = 128;     // ... per narrow tile (the remainder of a column range)
 constexpr int BLOCK_K = 64;       // reduction rows per stage
 constexpr int UMMA_K = 16;
 constexpr int MN_CHUNK = 64;      // contiguous elements per TMA box row (128 B)
@@ -38,11 +47,11 @@ constexpr int EPI_COLS = 16;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;
 constexpr int CHUNK_BYTES = BLOCK_K * MN_CHUNK * 2;        // 8 KB: one TMA box
 constexpr int BYTES_A = (BLOCK_M / MN_CHUNK) * CHUNK_BYTES;  // 16 KB
-constexpr int BYTES_B = (HALF_N / MN_CHUNK) * CHUNK_BYTES;   // 8 KB
+constexpr int BYTES_B = (WIDE_N / 2 / MN_CHUNK) * CHUNK_BYTES;  // 16 KB reserved (a narrow tile fills the first 8 KB)
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
 constexpr int MAX_STAGES = 8;
-constexpr int PIPE_BYTES = 192 * 1024;                      // 4 stages of 48 KB (3-pass) or 8 stages of 24 KB
-constexpr int TMEM_COLS = 256;
+constexpr int PIPE_BYTES = 192 * 1024;                      // 3 stages of 64 KB (3-pass) or 6 stages of 32 KB
+constexpr int TMEM_COLS = 512;                              // two accumulators of up to 256 columns
 constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -176,9 +185,12 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     const bool split = passes == 3;
     const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
-    const int num_stages = PIPE_BYTES / stage_bytes;  // 4 or 8
+    const int num_stages = PIPE_BYTES / stage_bytes;  // 3 or 6
     const int num_m = (Nw + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-    const int num_n = (Kw + BLOCK_N - 1) / BLOCK_N;
+    // column tiles: n_wide tiles of 256, then at most one narrow tile of 128 for a remainder of <= 128 columns
+    const int rem = Kw % WIDE_N;
+    const int n_wide = Kw / WIDE_N + (rem > NARROW_N ? 1 : 0);
+    const int num_n = n_wide + ((rem > 0 && rem <= NARROW_N) ? 1 : 0);
     const int mn_tiles = num_m * num_n;
     const int num_tiles = mn_tiles * p.ksplit;
     const int num_kb = (rows + BLOCK_K - 1) / BLOCK_K;
@@ -189,6 +201,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         tn = t2 - tm * num_n;
         return tile / mn_tiles;
     };
+    auto tile_width = [&](int tn) { return tn < n_wide ? WIDE_N : NARROW_N; };   // first column of tile tn = tn * WIDE_N
     auto kb_range = [&](int ks, int& kb0, int& kb1) {
         kb0 = ks * p.kb_per;
         kb1 = kb0 + p.kb_per < num_kb ? kb0 + p.kb_per : num_kb;
@@ -219,7 +232,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    // stage layout: [A_hi][A_lo][B_hi][B_lo] (3-pass) or [A][B] (1-pass); A = two 8 KB boxes, B = one
+    // stage layout: [A_hi][A_lo][B_hi][B_lo] (3-pass) or [A][B] (1-pass); A = two 8 KB boxes, B = two (wide) or one
     auto stage_ptr = [&](int s) { return smem + s * stage_bytes; };
     const int off_a_lo = BYTES_A;
     const int off_b_hi = split ? 2 * BYTES_A : BYTES_A;
@@ -233,20 +246,25 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 int tm, tn, kb0, kb1;
                 kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                const int width = tile_width(tn);
+                const int b_boxes = width / 2 / MN_CHUNK;              // 64-column boxes of X this CTA stages: 2 or 1
                 const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M;   // first dY column (output row) of this CTA
-                const int n0 = tn * BLOCK_N + rank * HALF_N;          // first X column (output column) of this CTA
+                const int n0 = tn * WIDE_N + rank * (width / 2);       // first X column (output column) of this CTA
+                const int tx_bytes = 2 * (split ? 2 : 1) * (BYTES_A + b_boxes * CHUNK_BYTES);   // both CTAs of the pair
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int r0 = kb * BLOCK_K;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t* sp = stage_ptr(stage);
 #pragma unroll
                     for (int j = 0; j < BLOCK_M / MN_CHUNK; ++j) {
                         tma_load_2d_pair(sp + j * CHUNK_BYTES, &tm_a_hi, &full_bar[stage], m0 + j * MN_CHUNK, r0);
                         if (split) tma_load_2d_pair(sp + off_a_lo + j * CHUNK_BYTES, &tm_a_lo, &full_bar[stage], m0 + j * MN_CHUNK, r0);
                     }
-                    tma_load_2d_pair(sp + off_b_hi, &tm_b_hi, &full_bar[stage], n0, r0);
-                    if (split) tma_load_2d_pair(sp + off_b_lo, &tm_b_lo, &full_bar[stage], n0, r0);
+                    for (int j = 0; j < b_boxes; ++j) {
+                        tma_load_2d_pair(sp + off_b_hi + j * CHUNK_BYTES, &tm_b_hi, &full_bar[stage], n0 + j * MN_CHUNK, r0);
+                        if (split) tma_load_2d_pair(sp + off_b_lo + j * CHUNK_BYTES, &tm_b_lo, &full_bar[stage], n0 + j * MN_CHUNK, r0);
+                    }
                     if (++stage == num_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -258,7 +276,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_mn(2 * BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc_wide = make_idesc_mn(2 * BLOCK_M, WIDE_N), idesc_narrow = make_idesc_mn(2 * BLOCK_M, NARROW_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -267,9 +285,10 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_base + acc * WIDE_N;
                 int tm, tn, kb0, kb1;
                 kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                const uint32_t idesc = tile_width(tn) == WIDE_N ? idesc_wide : idesc_narrow;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
@@ -302,7 +321,6 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         constexpr int kStride = NUM_EPI_WARPS / 4;
         float4* stage4 = reinterpret_cast<float4*>(smem_epi + (warp - 4) * EPI_STAGE_BYTES);
         const int rsub = lane >> 2, cg = lane & 3;
-        constexpr int kChunks = BLOCK_N / EPI_COLS;
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int acc = it & 1;
@@ -310,11 +328,12 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             int tm, tn;
             const int ks = tile_mn(tile, tm, tn);
             const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
-            const int n0 = tn * BLOCK_N;
+            const int n0 = tn * WIDE_N;
+            const int kChunks = tile_width(tn) / EPI_COLS;
             float* outp = p.out + (size_t)ks * (size_t)p.split_stride;
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * WIDE_N;
 #pragma unroll 1
             for (int c = third; c < kChunks; c += kStride) {
                 uint32_t r[16];
@@ -416,6 +435,32 @@ bool gemm_tn2_supported(int Nw, int Kw, int ld_y, int ld_x) {
     return Nw % 8 == 0 && Kw % 8 == 0 && ld_y % 8 == 0 && ld_x % 8 == 0;
 }
 
+// output tiles of one K slice: 256-row tiles x (256-wide column tiles + at most one 128-wide tile for the remainder)
+int gemm_tn2_mn_tiles(int Nw, int Kw) {
+    const int rem = Kw % WIDE_N;
+    const int n_wide = Kw / WIDE_N + (rem > NARROW_N ? 1 : 0);
+    return ((Nw + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (n_wide + ((rem > 0 && rem <= NARROW_N) ? 1 : 0));
+}
+
+// fraction of the machine a launch with `slices` K slices keeps busy: tiles go round-robin to the CTA pairs, a wide
+// tile costs two narrow ones
+double gemm_tn2_efficiency(int Nw, int Kw, int slices, int pairs) {
+    const int rem = Kw % WIDE_N;
+    const int n_wide = Kw / WIDE_N + (rem > NARROW_N ? 1 : 0);
+    const int num_n = n_wide + ((rem > 0 && rem <= NARROW_N) ? 1 : 0);
+    const int mn = gemm_tn2_mn_tiles(Nw, Kw);
+    std::vector<double> load((size_t)pairs, 0.0);
+    double total = 0.0;
+    for (int t = 0; t < mn * slices; ++t) {
+        const double c = ((t % mn) % num_n) < n_wide ? 2.0 : 1.2;
+        load[(size_t)(t % pairs)] += c;
+        total += c;
+    }
+    double mx = 0.0;
+    for (double l : load) mx = l > mx ? l : mx;
+    return mx > 0.0 ? total / (mx * pairs) : 0.0;
+}
+
 int gemm_tn2_slices(int rows, int split_k) { return gemm_tc2_slices((rows + BLOCK_K - 1) / BLOCK_K * BLOCK_K, split_k); }
 
 int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
@@ -440,7 +485,7 @@ int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int ro
     const int num_kb = (rows + BLOCK_K - 1) / BLOCK_K;
     const int ksplit = gemm_tn2_slices(rows, split_k);
     const int kb_per = (num_kb + ksplit - 1) / ksplit;
-    const int tiles = ((Nw + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((Kw + BLOCK_N - 1) / BLOCK_N) * ksplit;
+    const int tiles = gemm_tn2_mn_tiles(Nw, Kw) * ksplit;
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride,

@@ -184,15 +184,13 @@ struct Ctx {
             return gemm_simt(t1, (int)Kp, t2, Nw, Kw, (int)Kp, ep, s);
         }
         // split-K: pick the slice count whose tile total fills whole waves of CTA pairs best (>= 8 K blocks per slice)
-        const int mn_tiles = ((Nw + 255) / 256) * ((Kw + 127) / 128);
         const int pairs = num_sms() / 2;
         const int max_s = (int)((rows + 511) / 512) < kMaxSplit ? (int)((rows + 511) / 512) : kMaxSplit;
         int best = 1;
         double best_eff = 0.0;
         for (int want = 1; want <= (max_s > 1 ? max_s : 1); ++want) {
             const int sl = gemm_tn2_slices((int)rows, want);
-            const int tiles = mn_tiles * sl;
-            const double eff = (double)tiles / (double)(((tiles + pairs - 1) / pairs) * pairs);
+            const double eff = gemm_tn2_efficiency(Nw, Kw, sl, pairs);
             if (eff > best_eff + 0.02) {
                 best_eff = eff;
                 best = sl;
