@@ -455,6 +455,20 @@ def main():
         "stage_launches": dict(st.launches),
     }
 
+    # HBM-bound kernels of the training step: algorithmic bytes (every operand read / written once) / stage time
+    nb_tr = B * TR_BOXES
+    tr_bytes = {
+        "roi_gather": nb_tr * 131072,
+        "layernorm": 12 * M * 576 * (4 + 4),                               # fp32 in, bf16 hi + lo out
+        "bwd_layernorm": 12 * M * 576 * (3 * 4 + 4 + 4),                   # x, dy, residual in; dx fp32 + operand hi/lo out
+        "attention": 6 * M * (1728 * 4 + 576 * 4),                         # qkv fp32 in, output hi + lo
+        "bwd_attention": 6 * M * (1728 * 4 + 576 * 4 + 1728 * 4),          # qkv, dO in; d_qkv hi + lo out
+        "tokens": R * 19 * 576 * 4,
+    }
+    train_hbm = {k: {"ms": round(st.ms[k], 3), "algorithmic_bytes": int(v), "achieved_gbs": round(v / st.ms[k] / 1e6, 1),
+                     "frac_of_measured_hbm": round(v / st.ms[k] / 1e6 / hbm_peak, 3)}
+                 for k, v in tr_bytes.items() if st.ms.get(k)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_train_leg()
@@ -575,6 +589,7 @@ def main():
                     "ms_per_step": ms_e2e,
                     "pipeline": "double-buffered: the H2D copy of step k+1 (copy stream) overlaps the training of step k"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_peak_gbs": hbm_peak,
+            "hbm_kernels": train_hbm,
             "cpu_baseline": cpu, "inference": inference,
         }
         print(json.dumps(line), flush=True)
