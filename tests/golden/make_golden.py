@@ -335,13 +335,15 @@ def run_relsample_case(ns, name, c):
 def run_eval_case(ns, name, c):
     """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
     sys.path.insert(0, ref_shim.REF_ROOT)
-    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGMeanRecall, SGRecall
+    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGMeanRecall, SGNoGraphConstraintRecall, SGRecall
     imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
     result_dict = {}
     ev = SGRecall(result_dict)
     ev.register_container("sgdet")
     mr = SGMeanRecall(result_dict, 51, ["__background__"] + [f"rel{i}" for i in range(1, 51)])
     mr.register_container("sgdet")
+    ng = SGNoGraphConstraintRecall(result_dict)
+    ng.register_container("sgdet")
     out = {"n_images": np.array(len(imgs))}
     for i, im in enumerate(imgs):
         local = dict(pred_rel_inds=im["rel_pair_idxs"], rel_scores=im["pred_rel_scores"], gt_rels=im["relation_tuple"],
@@ -349,6 +351,13 @@ def run_eval_case(ns, name, c):
                      pred_boxes=im["pred_boxes"], obj_scores=np.ones(len(im["labels"]), np.float32))
         local = ev.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
         mr.collect_mean_recall_items({"iou_thres": 0.5}, local, "sgdet")
+        local["obj_scores"] = im["pred_scores"]
+        ng.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
+        nfirst = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
+        for p, gs in enumerate(local["nogc_pred_to_gt"]):
+            for g in gs:
+                nfirst[g] = min(nfirst[g], p)
+        out[f"nogc_first_match/{i}"] = nfirst
         p2g = local["pred_to_gt"]
         first = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
         for p, gs in enumerate(p2g):
@@ -361,6 +370,7 @@ def run_eval_case(ns, name, c):
         out[f"mean_recall/{k}"] = np.array(result_dict["sgdet_mean_recall"][k], np.float64)
         out[f"mean_recall_list/{k}"] = np.array(result_dict["sgdet_mean_recall_list"][k], np.float64)
         out[f"recall/{k}"] = np.array(result_dict["sgdet_recall"][k], np.float64)
+        out[f"recall_nogc/{k}"] = np.array(result_dict["sgdet_recall_nogc"][k], np.float64)
         per = {}
         for d in result_dict["sgdet_recall_per_rel"][k]:
             for r, (h, n) in d.items():

@@ -316,6 +316,7 @@ def test_recall_evaluation_matches_reference():
         pr.add_field("pred_labels", _t(im["pred_labels"]))
         pr.add_field("rel_pair_idxs", _t(im["rel_pair_idxs"]))
         pr.add_field("pred_rel_scores", _t(im["pred_rel_scores"]))
+        pr.add_field("pred_scores", _t(im["pred_scores"]))
         preds.append(pr)
         gts.append(gt)
     # an image without ground-truth relations is skipped (vg_eval.py:473-474)
@@ -330,6 +331,12 @@ def test_recall_evaluation_matches_reference():
         assert np.array_equal(np.array(out["recall"][k]), g[f"recall/{k}"])
         per = np.array([[r, h, n] for r, (h, n) in sorted(out["hits_per_rel"][k].items())], np.int64)
         assert np.array_equal(per, g[f"per_rel/{k}"])
+    ng = E.recall_nogc_at_k(preds, gts)                                             # SGNoGraphConstraintRecall (:213-252)
+    for i in range(len(imgs)):
+        assert np.array_equal(ng["first_match"][i].numpy().astype(np.int64), g[f"nogc_first_match/{i}"])
+    for k in (20, 50, 100):
+        assert np.array_equal(np.array(ng["recall"][k]), g[f"recall_nogc/{k}"])
+    assert max(ng["recall"][100]) > max(out["recall"][100]) - 1e-9                  # no graph constraint can only help
     mr = E.mean_recall(out["first_match"], out["gt_predicates"], 51)                # SGMeanRecall (:424-466)
     for k in (20, 50, 100):
         assert np.allclose(mr["mean_recall_list"][k], g[f"mean_recall_list/{k}"], rtol=1e-12, atol=0)

@@ -89,3 +89,49 @@ def recall_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), io
                 e[0] += int(h)
                 e[1] += 1
     return out
+
+
+def recall_nogc_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), iou_thres: float = 0.5,
+                     predcls_like: bool = False, top: int = 100) -> Dict[str, object]:
+    """SGNoGraphConstraintRecall.calculate_recall (sgg_eval.py:213-252): every (pair, predicate) combination is a
+    candidate, scored obj_s * obj_o * rel_scores[pair, predicate]; the `top` best per image (descending, ties by flat
+    index — the reference's numpy argsort is not stable) are matched like the graph-constrained ones.
+    Returns {'recall': {k: [per image]}, 'first_match': [per image]}."""
+    gt_t, gt_b, pr_t, pr_b, gt_n, pr_n = [], [], [], [], [], []
+    for pred, gt in zip(predictions, groundtruths):
+        rel_tuple = gt.get_field("relation_tuple").long()
+        if rel_tuple.shape[0] == 0:
+            continue
+        gt_cls, gt_box = gt.get_field("labels").long(), gt.convert("xyxy").bbox
+        t, b = triplets(rel_tuple[:, :2], rel_tuple[:, 2], gt_cls, gt_box)
+        gt_t.append(t)
+        gt_b.append(b)
+        gt_n.append(t.shape[0])
+        scores = pred.get_field("pred_rel_scores")
+        pairs = pred.get_field("rel_pair_idxs").long()
+        if predcls_like:
+            cls, box = gt_cls, gt_box
+            obj_scores = torch.ones(len(gt_cls), dtype=scores.dtype, device=scores.device)     # vg_eval.py:515
+        else:
+            cls, box = pred.get_field("pred_labels").long(), pred.convert("xyxy").bbox
+            obj_scores = pred.get_field("pred_scores")
+        overall = (obj_scores[pairs[:, 0]] * obj_scores[pairs[:, 1]])[:, None] * scores[:, 1:]   # :221-222
+        order = torch.sort(overall.reshape(-1), descending=True, stable=True)[1][:top]            # :223
+        row, col = order // overall.shape[1], order % overall.shape[1]
+        t, b = triplets(pairs[row], col + 1, cls, box)                                            # :224-231
+        pr_t.append(t)
+        pr_b.append(b)
+        pr_n.append(t.shape[0])
+    out = {"recall": {k: [] for k in ks}, "first_match": []}
+    if not gt_t:
+        return out
+    first, _ = ops.sgg_match(torch.cat(gt_t), torch.cat(gt_b), gt_n, torch.cat(pr_t), torch.cat(pr_b), pr_n, iou_thres)
+    first_host = first.cpu()
+    off = 0
+    for n in gt_n:
+        fm = first_host[off:off + n]
+        off += n
+        out["first_match"].append(fm)
+        for k in ks:
+            out["recall"][k].append(float((fm < k).sum()) / float(n))                            # :249-252
+    return out
