@@ -99,6 +99,30 @@ int veto_relsample_gtbox(const int64_t* rel_matrix_dev, const int32_t* mat_offse
                          uint64_t seed, int64_t* pairs_out_dev, int64_t* labels_out_dev, int32_t* counts_out_dev,
                          int64_t* binary_out_dev, veto_stream_t stream);
 
+/* f2 (cont.). RelationSampling.detect_relsample + motif_rel_fg_bg_sampling (sampling.py:109-309): the training
+ * sampler for DETECTED boxes (SGDet, SGCls), whole batch, one launch.  Per image: detections prp_* (boxes [P,4] xyxy,
+ * labels [P], pred_scores [P]; rows prp_offsets[b] ..), ground truth tgt_* (boxes [T,4], labels [T], relation matrix
+ * [T,T] at cell offset rel_offsets[b]); P, T <= 128 (host counts n_prp_host / n_tgt_host are checked).
+ *   foreground: for every ground-truth relation (nonzero() order) the detection pairs (a, b), a != b, whose boxes match
+ *     its head / tail (same label, IoU > fg_thres); more than num_sample_per_gt_rel (<= 4) of them: that many drawn
+ *     without replacement with probability ~ iou_head * iou_tail; more than num_pos_per_image rows overall: a uniform
+ *     subset.  background: the other pairs between foreground-labelled detections (require_overlap: only overlapping
+ *     ones), the 2 * num_neg best by pred_scores[a] * pred_scores[b], of which num_neg = min(batch - #fg, #bg) are drawn
+ *     uniformly.  Nothing at all: two (0,0,0) rows.  Random draws: counter-based hash of (seed, image, item).
+ * Outputs: image b's rows start at b * batch_size_per_image: triplets_out_dev int64 [n_images*batch, 3] (subject,
+ * object, label; foreground first), corrsp_out_dev int64 [n_images*batch] (index of the ground-truth relation of a
+ * foreground row, -1 for background), counts_out_dev int32 [n_images, 2] = (foreground rows, total rows),
+ * binary_out_dev int64 [P,P] per image at cell offset bin_offsets[b] (symmetric relatedness of detections, :216-227),
+ * locating_out_dev fp32 [sum P] (1 where a detection overlaps any ground-truth box by more than fg_thres, :137-141). */
+int veto_relsample_detect(const float* prp_boxes_dev, const int64_t* prp_labels_dev, const float* prp_scores_dev,
+                          const int32_t* prp_offsets_dev, const float* tgt_boxes_dev, const int64_t* tgt_labels_dev,
+                          const int32_t* tgt_offsets_dev, const int64_t* tgt_rel_dev, const int32_t* rel_offsets_dev,
+                          const int32_t* bin_offsets_dev, const int32_t* n_prp_host, const int32_t* n_tgt_host,
+                          int n_images, float fg_thres, int require_overlap, int num_sample_per_gt_rel,
+                          int batch_size_per_image, int num_pos_per_image, uint64_t seed, int64_t* triplets_out_dev,
+                          int64_t* corrsp_out_dev, int32_t* counts_out_dev, int64_t* binary_out_dev,
+                          float* locating_out_dev, veto_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a3. ROIAlign.  veto_roi_align_forward is the one-for-one replacement of
  * _C.roi_align_forward(input, rois, spatial_scale, ph, pw, sampling_ratio)

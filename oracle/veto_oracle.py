@@ -509,3 +509,40 @@ def recall_at_k(pred_to_gt, n_gt: int, ks=(20, 50, 100)):
             match |= set(m)
         out[k] = len(match) / float(n_gt)
     return out
+
+
+def detect_relsample_candidates(prp_boxes, prp_labels, prp_scores, tgt_boxes, tgt_labels, relation, fg_thres: float = 0.5,
+                                require_overlap: bool = False):
+    """The deterministic part of RelationSampling.detect_relsample / motif_rel_fg_bg_sampling
+    (relation_head/sampling.py:109-309) for one image: dict(locating [P], binary [P,P], gt = [(head, tail, label,
+    candidate pairs [(a,b)...] in head-major order)] in nonzero() order, bg = background pairs [(a,b)...] sorted by
+    pred_scores[a]*pred_scores[b] descending (stable), the pool the reference cuts to 2*num_neg and then draws from).
+    What the reference draws at random: <= num_sample_per_gt_rel candidates per ground-truth relation with probability
+    ~ iou_head*iou_tail (:256-261), a num_pos subset of all foreground rows (:271-273), num_neg of the pool (:290-291)."""
+    P = len(prp_boxes)
+    ious = boxlist_iou(tgt_boxes.astype(f32), prp_boxes.astype(f32))                   # [T, P]
+    is_match = (tgt_labels[:, None] == prp_labels[None]) & (ious > f32(fg_thres))
+    locating = (ious > f32(fg_thres)).any(0).astype(f32)
+    if require_overlap:
+        self_iou = boxlist_iou(prp_boxes.astype(f32), prp_boxes.astype(f32))
+        poss = (self_iou > 0) & (self_iou < 1)
+    else:
+        poss = ~np.eye(P, dtype=bool)
+    poss = poss.copy()
+    poss[prp_labels == 0] = False
+    poss[:, prp_labels == 0] = False
+    binary = np.zeros((P, P), np.int64)
+    gt = []
+    for h, t in np.argwhere(relation != 0):
+        heads, tails = np.nonzero(is_match[h])[0], np.nonzero(is_match[t])[0]
+        if len(heads) and len(tails):
+            binary[np.ix_(heads, tails)] = 1
+            binary[np.ix_(tails, heads)] = 1
+        pairs = [(int(a), int(b)) for a in heads for b in tails if a != b]
+        for a, b in pairs:
+            poss[a, b] = False
+        gt.append((int(h), int(t), int(relation[h, t]), pairs))
+    bg = np.argwhere(poss)
+    q = prp_scores.astype(f32)[bg[:, 0]] * prp_scores.astype(f32)[bg[:, 1]] if len(bg) else np.zeros(0, f32)
+    bg = bg[np.argsort(-q, kind="stable")]
+    return dict(locating=locating, binary=binary, gt=gt, bg=[(int(a), int(b)) for a, b in bg], ious=ious)

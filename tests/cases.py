@@ -70,6 +70,12 @@ RELSAMPLE_CASES = {
     "relsample_over_caps": dict(n_boxes=[20, 9, 12], seed=32, fg_per_image=14, caps=(32, 0.25)),
 }
 
+# RelationSampling.detect_relsample fixtures (synth.make_detect_case); caps = (BATCH_SIZE_PER_IMAGE, POSITIVE_FRACTION)
+DETECT_SAMPLE_CASES = {
+    "detsample_default": dict(seed=61, n_tgt=[9, 5, 1, 12], caps=(1024, 0.25), require_overlap=False),
+    "detsample_tight": dict(seed=62, n_tgt=[10, 8], caps=(24, 0.25), require_overlap=True),
+}
+
 # recall-evaluation fixtures (SGRecall.calculate_recall of the reference on synth.make_eval_case)
 EVAL_CASES = {
     "eval_recall": dict(seed=41, n_objs=[20, 9, 2, 14], n_gt_rels=12, n_pred_rels=150),

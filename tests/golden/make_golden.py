@@ -332,6 +332,40 @@ def run_relsample_case(ns, name, c):
     print(f"{name}: wrote {path}", [(len(p), int((l > 0).sum())) for p, l in zip(rel_idx_pairs, rel_labels)])
 
 
+def run_detect_sample_case(ns, name, c):
+    """RelationSampling.detect_relsample of the UNMODIFIED reference on seeded detections / ground truth (CPU; numpy and
+    torch seeded)."""
+    import torch
+    cfg = ref_shim.make_cfg(ns, mode="sgdet")
+    cfg.merge_from_list(["MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE", c["caps"][0],
+                         "MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION", c["caps"][1],
+                         "MODEL.ROI_RELATION_HEAD.REQUIRE_BOX_OVERLAP", c["require_overlap"]])
+    samp = ns.make_sampler(cfg)
+    imgs = synth.make_detect_case(c["seed"], c["n_tgt"])
+    props, tgts = [], []
+    for im in imgs:
+        p = ns.BoxList(torch.from_numpy(im["prp_boxes"]), im["size"], mode="xyxy")
+        p.add_field("labels", torch.from_numpy(im["prp_labels"]))
+        p.add_field("pred_scores", torch.from_numpy(im["prp_scores"]))
+        t = ns.BoxList(torch.from_numpy(im["tgt_boxes"]), im["size"], mode="xyxy")
+        t.add_field("labels", torch.from_numpy(im["tgt_labels"]))
+        t.add_field("relation", torch.from_numpy(im["relation"]))
+        props.append(p)
+        tgts.append(t)
+    np.random.seed(c["seed"])
+    torch.manual_seed(c["seed"])
+    props, rel_labels, rel_labels_all, rel_idx_pairs, binarys = samp.detect_relsample(props, tgts)
+    out = {"n_images": np.array(len(imgs))}
+    for i in range(len(imgs)):
+        out[f"pairs/{i}"] = rel_idx_pairs[i].numpy()
+        out[f"labels/{i}"] = rel_labels[i].numpy()
+        out[f"binary/{i}"] = binarys[i].numpy()
+        out[f"locating_match/{i}"] = props[i].get_field("locating_match").numpy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path}", [(len(p), int((l > 0).sum())) for p, l in zip(rel_idx_pairs, rel_labels)])
+
+
 def run_eval_case(ns, name, c):
     """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
     sys.path.insert(0, ref_shim.REF_ROOT)
@@ -384,7 +418,7 @@ def run_eval_case(ns, name, c):
 
 
 def main():
-    from tests.cases import EVAL_CASES, MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
+    from tests.cases import DETECT_SAMPLE_CASES, EVAL_CASES, MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
     ns = ref_shim.load()
     only = sys.argv[1:]
     for name, c in CASES.items():
@@ -403,6 +437,10 @@ def main():
         if only and name not in only:
             continue
         run_relsample_case(ns, name, c)
+    for name, c in DETECT_SAMPLE_CASES.items():
+        if only and name not in only:
+            continue
+        run_detect_sample_case(ns, name, c)
     for name, c in EVAL_CASES.items():
         if only and name not in only:
             continue

@@ -298,6 +298,78 @@ def test_meet_per_class_nms_bit_exact():
         assert (ref != scores[:, 1:].argmax(1) + 1).any()          # suppression happened
 
 
+@pytest.mark.parametrize("name", ["detsample_default", "detsample_tight"])
+def test_detect_relsample(name):
+    """RelationSampling.detect_relsample on the device (SGDet / SGCls training): binary matrices,
+    locating_match and the row counts are identical to the unmodified reference's; the sampled rows satisfy the same
+    structural properties against the oracle's candidate sets as the reference's own rows do (tests/test_oracle.py);
+    reproducible under torch.manual_seed; the IoU-weighted draw prefers better-overlapping candidates."""
+    from tests.cases import DETECT_SAMPLE_CASES
+    from tests.train_util import check_detect_sample
+    from veto_b200.sampling import make_roi_relation_samp_processor
+    from veto_b200.structures import BoxList
+    c, g = DETECT_SAMPLE_CASES[name], load_golden(name)
+    imgs = synth.make_detect_case(c["seed"], c["n_tgt"])
+    cfg = H.make_cfg(mode="sgdet")
+    cfg.MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE = c["caps"][0]
+    cfg.MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION = c["caps"][1]
+    cfg.MODEL.ROI_RELATION_HEAD.REQUIRE_BOX_OVERLAP = c["require_overlap"]
+    samp = make_roi_relation_samp_processor(cfg)
+    assert samp.require_overlap == c["require_overlap"] and samp.num_sample_per_gt_rel == 4 and samp.fg_thres == 0.5
+    batch, num_pos = c["caps"][0], int(c["caps"][0] * c["caps"][1])
+
+    def run(seed):
+        props, tgts = [], []
+        for im in imgs:
+            p = BoxList(_t(im["prp_boxes"]), im["size"], "xyxy")
+            p.add_field("labels", _t(im["prp_labels"]))
+            p.add_field("pred_scores", _t(im["prp_scores"]))
+            t = BoxList(_t(im["tgt_boxes"]), im["size"], "xyxy")
+            t.add_field("labels", _t(im["tgt_labels"]))
+            t.add_field("relation", _t(im["relation"]))
+            props.append(p)
+            tgts.append(t)
+        torch.manual_seed(seed)
+        return samp.detect_relsample(props, tgts)
+
+    props, rel_labels, rel_labels_all, rel_pairs, binarys = run(1)
+    assert rel_labels_all is rel_labels
+    cands = []
+    for i, im in enumerate(imgs):
+        cand = O.detect_relsample_candidates(im["prp_boxes"], im["prp_labels"], im["prp_scores"], im["tgt_boxes"],
+                                             im["tgt_labels"], im["relation"], 0.5, c["require_overlap"])
+        cands.append(cand)
+        assert np.array_equal(H.np_(binarys[i]), g[f"binary/{i}"])
+        assert np.array_equal(H.np_(props[i].get_field("locating_match")), g[f"locating_match/{i}"])
+        pr, lb = H.np_(rel_pairs[i]), H.np_(rel_labels[i])
+        assert pr.dtype == np.int64 and lb.dtype == np.int64
+        check_detect_sample(cand, pr, lb, batch, num_pos)
+        assert len(pr) == len(g[f"pairs/{i}"]) and int((lb > 0).sum()) == int((g[f"labels/{i}"] > 0).sum())
+    again, other = run(1), run(2)
+    assert all(torch.equal(a, b) for a, b in zip(again[3], rel_pairs))
+    assert any(not torch.equal(a, b) for a, b in zip(other[3], rel_pairs))
+    if name == "detsample_default":
+        # the weighted draw: over many seeds, among the candidates of a ground-truth relation with more than four of
+        # them, the selection frequency follows the weight iou_head * iou_tail (rank correlation), and every draw keeps 4
+        i, rel = next((i, r) for i, cnd in enumerate(cands) for r in cnd["gt"] if len(r[3]) > 6)
+        h, t, l, cc = rel
+        w = np.array([cands[i]["ious"][h, a] * cands[i]["ious"][t, b] for a, b in cc])
+        freq = np.zeros(len(cc))
+        trials = 200
+        for s in range(trials):
+            out = run(100 + s)
+            pr, lb = H.np_(out[3][i]), H.np_(out[1][i])
+            rows = {(int(a), int(b)) for (a, b), x in zip(pr, lb) if x == l}
+            hit = np.array([(a, b) in rows for a, b in cc], float)
+            freq += hit
+        others = sum(1 for r in cands[i]["gt"] if r[2] == l and r is not rel)
+        if others == 0:
+            assert np.all(np.isclose(freq.sum(), 4 * trials))
+        order_w, order_f = np.argsort(np.argsort(w)), np.argsort(np.argsort(freq))
+        rho = np.corrcoef(order_w, order_f)[0, 1]
+        assert rho > 0.5, (rho, w, freq)
+
+
 def test_recall_evaluation_matches_reference():
     """veto_sgg_match + evaluation.recall_at_k against SGRecall.calculate_recall of the unmodified
     reference: per ground-truth triplet the rank of the first matching prediction, per prediction the number of

@@ -378,3 +378,24 @@ def test_recall_matching_matches_reference():
         for k in (20, 50, 100):
             assert rec[k] == g[f"recall/{k}"][i]
     assert g["recall/100"].max() > 0.5 and g["recall/20"].min() < 0.2      # the case discriminates
+
+
+@pytest.mark.parametrize("name", ["detsample_default", "detsample_tight"])
+def test_detect_relsample_candidates_match_reference(name):
+    """oracle.detect_relsample_candidates against RelationSampling.detect_relsample of the unmodified reference: the
+    deterministic outputs (binary matrix, locating_match) are identical and the reference's sampled rows satisfy every
+    structural property the candidate sets imply."""
+    from tests.cases import DETECT_SAMPLE_CASES
+    from tests.train_util import check_detect_sample
+    c, g = DETECT_SAMPLE_CASES[name], load_golden(name)
+    imgs = synth.make_detect_case(c["seed"], c["n_tgt"])
+    batch, num_pos = c["caps"][0], int(c["caps"][0] * c["caps"][1])
+    drew = 0
+    for i, im in enumerate(imgs):
+        cand = O.detect_relsample_candidates(im["prp_boxes"], im["prp_labels"], im["prp_scores"], im["tgt_boxes"],
+                                             im["tgt_labels"], im["relation"], 0.5, c["require_overlap"])
+        assert np.array_equal(cand["binary"], g[f"binary/{i}"])
+        assert np.array_equal(cand["locating"], g[f"locating_match/{i}"])
+        check_detect_sample(cand, g[f"pairs/{i}"], g[f"labels/{i}"], batch, num_pos)
+        drew += sum(len(x[3]) > 4 for x in cand["gt"])
+    assert drew >= 1                                            # the weighted draw is exercised

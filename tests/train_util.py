@@ -84,3 +84,40 @@ def oracle_meet_train_step(c, batch, sd, pairs, head_labels, drop=None):
         tsd, boxes, [torch.from_numpy(p) for p in pairs], head_labels, x2d, d2d, obj_preds, drop=drop)
     return dict(losses=np.array([float(l) for l in losses]), grads={k: v.numpy() for k, v in grads.items()},
                 g_roi_depth=g_d2d.numpy(), g_roi_rgb=g_x2d.numpy(), x2d=x2d.numpy(), d2d=d2d.numpy())
+
+
+def check_detect_sample(cand, pairs, labels, batch_size, num_pos, per_gt=4):
+    """Structural check of one image's detect_relsample output (pairs [R,2], labels [R]) against the oracle's candidate
+    sets (oracle.detect_relsample_candidates): sizes as sampling.py:256-293 prescribes, every foreground row a candidate
+    of a ground-truth relation with that label, all candidates present where nothing had to be drawn, background rows
+    distinct members of the quality-ranked pool.  Returns (n_fg, n_bg_rows)."""
+    pairs = np.asarray(pairs).reshape(-1, 2)
+    labels = np.asarray(labels)
+    kept = [min(len(c[3]), per_gt) for c in cand["gt"]]
+    n_fg_all = sum(kept)
+    n_fg = min(n_fg_all, num_pos)
+    n_bg_pool = len(cand["bg"])
+    num_neg = max(0, min(batch_size - n_fg, n_bg_pool))
+    if n_fg + num_neg == 0:                                   # :298-304 placeholder rows
+        assert pairs.tolist() == [[0, 0], [0, 0]] and labels.tolist() == [0, 0]
+        return 0, 2
+    assert len(pairs) == n_fg + num_neg, (len(pairs), n_fg, num_neg)
+    assert np.all(labels[:n_fg] != 0) and np.all(labels[n_fg:] == 0)
+    by_label = {}
+    for h, t, l, c in cand["gt"]:
+        by_label.setdefault(l, set()).update(c)
+    fg_rows = [(int(a), int(b), int(l)) for (a, b), l in zip(pairs[:n_fg], labels[:n_fg])]
+    for a, b, l in fg_rows:
+        assert (a, b) in by_label.get(l, ()), (a, b, l)
+    if n_fg_all <= num_pos:
+        # nothing cut at the image level: relations with <= per_gt candidates contribute all of them
+        from collections import Counter
+        have = Counter(fg_rows)
+        for h, t, l, c in cand["gt"]:
+            if len(c) <= per_gt:
+                for a, b in c:
+                    assert have[(a, b, l)] >= 1, (h, t, l, a, b)
+    bg_rows = [(int(a), int(b)) for a, b in pairs[n_fg:]]
+    assert len(set(bg_rows)) == len(bg_rows)
+    assert set(bg_rows) <= set(cand["bg"][: int(num_neg * 2.0)])
+    return n_fg, num_neg

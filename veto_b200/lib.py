@@ -94,6 +94,8 @@ _PROTOS = {
     "veto_profile_tag_name": (c_char_p, [c_int]),
     "veto_postprocess": (c_int, [_fp, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp, _fp, _fp, c_void_p]),
     "veto_sgg_match": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, _fp, _fp, c_void_p]),
+    "veto_relsample_detect": (c_int, [_fp] * 10 + [POINTER(c_int32), POINTER(c_int32), c_int, c_float, c_int, c_int, c_int, c_int,
+                                      ctypes.c_uint64, _fp, _fp, _fp, _fp, _fp, c_void_p]),
     "veto_relsample_gtbox": (c_int, [_fp, _fp, _fp, POINTER(c_int32), c_int, c_int, c_int, ctypes.c_uint64, _fp, _fp, _fp, _fp,
                                      c_void_p]),
     "veto_postprocess_meet": (c_int, [_fp, c_int, _fp, c_int, _fp, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp, _fp, _fp,

@@ -436,6 +436,50 @@ def relsample_gtbox(rel_matrices: Sequence[torch.Tensor], batch_size_per_image: 
     return pairs, labels, counts, binaries
 
 
+def relsample_detect(prp_boxes: Sequence[torch.Tensor], prp_labels: Sequence[torch.Tensor], prp_scores: Sequence[torch.Tensor],
+                     tgt_boxes: Sequence[torch.Tensor], tgt_labels: Sequence[torch.Tensor], tgt_rels: Sequence[torch.Tensor],
+                     fg_thres: float, require_overlap: bool, num_sample_per_gt_rel: int, batch_size_per_image: int,
+                     num_pos_per_image: int, seed: int):
+    """RelationSampling.detect_relsample (sampling.py:109-309) for a batch in one launch; per-image lists in.
+    Returns (triplets [B*batch,3], corrsp [B*batch], counts [B,2] int32 (fg rows, total rows), binaries (per image
+    [P,P]), locating (per image [P])); image b's rows start at b*batch."""
+    L.require_device()
+    dev = prp_boxes[0].device
+    n_prp = [int(b.shape[0]) for b in prp_boxes]
+    n_tgt = [int(b.shape[0]) for b in tgt_boxes]
+    B = len(n_prp)
+    pb = _cuda_f32(torch.cat(list(prp_boxes), 0)).reshape(-1, 4)
+    tb = _cuda_f32(torch.cat(list(tgt_boxes), 0)).reshape(-1, 4)
+    pl = torch.cat(list(prp_labels), 0).to(torch.int64).contiguous()
+    tl = torch.cat(list(tgt_labels), 0).to(torch.int64).contiguous()
+    ps = _cuda_f32(torch.cat(list(prp_scores), 0))
+    rel = torch.cat([r.reshape(-1) for r in tgt_rels]).to(torch.int64).contiguous()
+    p_off, t_off = offsets_tensor(n_prp, dev), offsets_tensor(n_tgt, dev)
+    r_off = offsets_tensor([n * n for n in n_tgt], dev)
+    b_off = offsets_tensor([n * n for n in n_prp], dev)
+    trip = torch.zeros((B * batch_size_per_image, 3), dtype=torch.int64, device=dev)
+    corr = torch.full((B * batch_size_per_image,), -1, dtype=torch.int64, device=dev)
+    counts = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    binary = torch.zeros(max(1, sum(n * n for n in n_prp)), dtype=torch.int64, device=dev)
+    locating = torch.zeros(max(1, sum(n_prp)), dtype=torch.float32, device=dev)
+    np_h = (ctypes.c_int32 * B)(*n_prp)
+    nt_h = (ctypes.c_int32 * B)(*n_tgt)
+    with torch.cuda.device(dev):
+        L.check(L.load().veto_relsample_detect(
+            pb.data_ptr(), pl.data_ptr(), ps.data_ptr(), p_off.data_ptr(), tb.data_ptr(), tl.data_ptr(), t_off.data_ptr(),
+            rel.data_ptr(), r_off.data_ptr(), b_off.data_ptr(), np_h, nt_h, B, float(fg_thres), int(bool(require_overlap)),
+            int(num_sample_per_gt_rel), int(batch_size_per_image), int(num_pos_per_image), int(seed) & (2 ** 64 - 1),
+            trip.data_ptr(), corr.data_ptr(), counts.data_ptr(), binary.data_ptr(), locating.data_ptr(), L.stream_ptr()),
+            "veto_relsample_detect")
+    binaries, locs, bo, po = [], [], 0, 0
+    for n in n_prp:
+        binaries.append(binary[bo:bo + n * n].view(n, n))
+        locs.append(locating[po:po + n])
+        bo += n * n
+        po += n
+    return trip, corr, counts, binaries, locs
+
+
 # --------------------------------------------------------------------------------------------
 # a10: MEET's per-class NMS label assignment (SGDet test)
 # --------------------------------------------------------------------------------------------

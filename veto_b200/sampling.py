@@ -81,13 +81,45 @@ class RelationSampling:
         return self.gtbox_relsample_async(proposals, targets).result()
 
     def detect_relsample(self, proposals, targets):
-        raise NotImplementedError("detect_relsample (SGDet training sampler, sampling.py:109-309) is a 'next' row (SURVEY.md §8 f2)")
+        """sampling.py:109-309 (with motif_rel_fg_bg_sampling): (proposals, rel_labels, rel_labels_all, rel_idx_pairs,
+        rel_sym_binarys) for training on DETECTED boxes — IoU matching against the ground truth, per-relation
+        candidate pairs, the IoU-weighted draw, the quality-ranked background pool — one launch and one host sync per
+        batch instead of a Python loop over images and ground-truth relations."""
+        num_pos = int(self.batch_size_per_image * self.positive_fraction)
+        self.num_pos_per_img = num_pos
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        trip, corr, counts, binaries, locs = ops.relsample_detect(
+            [xyxy_boxes(p) for p in proposals], [p.get_field("labels") for p in proposals],
+            [p.get_field("pred_scores") for p in proposals], [xyxy_boxes(t) for t in targets],
+            [t.get_field("labels") for t in targets], [t.get_field("relation") for t in targets], self.fg_thres,
+            self.require_overlap and not self.use_gt_box, self.num_sample_per_gt_rel, self.batch_size_per_image, num_pos, seed)
+        totals = counts[:, 1].tolist()
+        bs = self.batch_size_per_image
+        rel_idx_pairs, rel_labels, rel_labels_all = [], [], []
+        for b, (p, t, n) in enumerate(zip(proposals, targets, totals)):
+            p.add_field("locating_match", locs[b])                                          # :137-141
+            rows = trip[b * bs: b * bs + n]
+            rel_idx_pairs.append(rows[:, :2])
+            rel_labels.append(rows[:, 2])
+            if t.has_field("relation_non_masked"):                                          # :160-169
+                rel_map = t.get_field("relation_non_masked")
+                gt_rel_idx = torch.nonzero(rel_map != 0)
+                c = corr[b * bs: b * bs + n]
+                fg = gt_rel_idx[c[c >= 0]]
+                fg_labels = rel_map[fg[:, 0], fg[:, 1]].long()
+                rel_labels_all.append(torch.cat((fg_labels, torch.zeros(int((c < 0).sum()), dtype=torch.long, device=c.device))))
+        if not rel_labels_all:
+            rel_labels_all = rel_labels
+        return proposals, rel_labels, rel_labels_all, rel_idx_pairs, binaries
 
 
 def make_roi_relation_samp_processor(cfg):
     """sampling.py:312-324."""
     rh = cfg.MODEL.ROI_RELATION_HEAD
     return RelationSampling(
+        fg_thres=C.get(cfg, "MODEL.ROI_HEADS.FG_IOU_THRESHOLD", 0.5),
+        require_overlap=C.get(cfg, "MODEL.ROI_RELATION_HEAD.REQUIRE_BOX_OVERLAP", False),
+        num_sample_per_gt_rel=C.get(cfg, "MODEL.ROI_RELATION_HEAD.NUM_SAMPLE_PER_GT_REL", 4),
         batch_size_per_image=C.get(cfg, "MODEL.ROI_RELATION_HEAD.BATCH_SIZE_PER_IMAGE", 1024),
         positive_fraction=C.get(cfg, "MODEL.ROI_RELATION_HEAD.POSITIVE_FRACTION", 0.25),
         max_proposal_pairs=rh.MAX_PROPOSAL_PAIR,
