@@ -369,7 +369,8 @@ def run_detect_sample_case(ns, name, c):
 def run_eval_case(ns, name, c):
     """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
     sys.path.insert(0, ref_shim.REF_ROOT)
-    from pysgg.data.datasets.evaluation.vg.sgg_eval import SGMeanRecall, SGNoGraphConstraintRecall, SGRecall
+    from pysgg.data.datasets.evaluation.vg.sgg_eval import (SGMeanRecall, SGNoGraphConstraintRecall, SGPairAccuracy, SGRecall,
+                                                             SGZeroShotRecall)
     imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
     result_dict = {}
     ev = SGRecall(result_dict)
@@ -378,13 +379,31 @@ def run_eval_case(ns, name, c):
     mr.register_container("sgdet")
     ng = SGNoGraphConstraintRecall(result_dict)
     ng.register_container("sgdet")
-    out = {"n_images": np.array(len(imgs))}
+    zs = SGZeroShotRecall(result_dict)
+    zs.register_container("sgdet")
+    pa = SGPairAccuracy(result_dict)
+    pa.register_container("sgcls")
+    # "zero-shot" triplets: (subject class, object class, predicate) of every third ground-truth relation of the case
+    zs_list = []
+    for im in imgs:
+        r = im["relation_tuple"][::3]
+        zs_list.append(np.column_stack((im["labels"][r[:, 0]], im["labels"][r[:, 1]], r[:, 2])))
+    zs_trip = np.unique(np.concatenate(zs_list), axis=0)
+    out = {"n_images": np.array(len(imgs)), "zeroshot_triplets": zs_trip}
     for i, im in enumerate(imgs):
         local = dict(pred_rel_inds=im["rel_pair_idxs"], rel_scores=im["pred_rel_scores"], gt_rels=im["relation_tuple"],
                      gt_classes=im["labels"], gt_boxes=im["boxes"], pred_classes=im["pred_labels"],
                      pred_boxes=im["pred_boxes"], obj_scores=np.ones(len(im["labels"]), np.float32))
         local = ev.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
         mr.collect_mean_recall_items({"iou_thres": 0.5}, local, "sgdet")
+        zs.prepare_zeroshot({"zeroshot_triplet": zs_trip}, local)
+        zs.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
+        # pair accuracy (SGCls-style: boxes from the ground truth are not required by the metric itself)
+        loc2 = dict(local)
+        pa.prepare_gtpair(loc2)
+        keep = pa.pred_pair_in_gt
+        loc2["pred_to_gt"] = local["pred_to_gt"]
+        pa.calculate_recall({"iou_thres": 0.5}, loc2, "sgcls")
         local["obj_scores"] = im["pred_scores"]
         ng.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
         nfirst = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
@@ -405,6 +424,9 @@ def run_eval_case(ns, name, c):
         out[f"mean_recall_list/{k}"] = np.array(result_dict["sgdet_mean_recall_list"][k], np.float64)
         out[f"recall/{k}"] = np.array(result_dict["sgdet_recall"][k], np.float64)
         out[f"recall_nogc/{k}"] = np.array(result_dict["sgdet_recall_nogc"][k], np.float64)
+        out[f"zeroshot_recall/{k}"] = np.array(result_dict["sgdet_zeroshot_recall"][k], np.float64)
+        out[f"accuracy_hit/{k}"] = np.array(result_dict["sgcls_accuracy_hit"][k], np.float64)
+        out[f"accuracy_count/{k}"] = np.array(result_dict["sgcls_accuracy_count"][k], np.float64)
         per = {}
         for d in result_dict["sgdet_recall_per_rel"][k]:
             for r, (h, n) in d.items():

@@ -409,6 +409,13 @@ def test_recall_evaluation_matches_reference():
     for k in (20, 50, 100):
         assert np.array_equal(np.array(ng["recall"][k]), g[f"recall_nogc/{k}"])
     assert max(ng["recall"][100]) > max(out["recall"][100]) - 1e-9                  # no graph constraint can only help
+    zs = E.zeroshot_recall(out["first_match"], gts[:2] + [empty] + gts[2:], _t(g["zeroshot_triplets"]))   # SGZeroShotRecall
+    pa = E.pair_accuracy(preds, gts, predcls_like=False)                            # SGPairAccuracy (:338-366)
+    for k in (20, 50, 100):
+        assert np.array_equal(np.array(zs[k]), g[f"zeroshot_recall/{k}"])
+        assert np.array_equal(np.array(pa["hit"][k]), g[f"accuracy_hit/{k}"])
+        assert np.array_equal(np.array(pa["count"][k]), g[f"accuracy_count/{k}"])
+    assert sum(pa["hit"][100]) > 0 and len(zs[100]) == len(imgs)
     mr = E.mean_recall(out["first_match"], out["gt_predicates"], 51)                # SGMeanRecall (:424-466)
     for k in (20, 50, 100):
         assert np.allclose(mr["mean_recall_list"][k], g[f"mean_recall_list/{k}"], rtol=1e-12, atol=0)

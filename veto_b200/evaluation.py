@@ -135,3 +135,63 @@ def recall_nogc_at_k(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100
         for k in ks:
             out["recall"][k].append(float((fm < k).sum()) / float(n))                            # :249-252
     return out
+
+
+def zeroshot_recall(first_match: Sequence[torch.Tensor], groundtruths, zeroshot_triplets: torch.Tensor,
+                    ks: Sequence[int] = (20, 50, 100)) -> Dict[int, List[float]]:
+    """SGZeroShotRecall (sgg_eval.py:277-309): recall restricted to the ground-truth triplets whose (subject class,
+    object class, predicate) is in `zeroshot_triplets` [Z,3]; images without such a triplet contribute nothing.
+    `first_match`: recall_at_k(...)['first_match'] for the same (non-empty) images, in order."""
+    out = {k: [] for k in ks}
+    zs = zeroshot_triplets.long().cpu()
+    it = iter(first_match)
+    for gt in groundtruths:
+        rel = gt.get_field("relation_tuple").long().cpu()
+        if rel.shape[0] == 0:
+            continue
+        fm = next(it).cpu()
+        cls = gt.get_field("labels").long().cpu()
+        trip = torch.stack((cls[rel[:, 0]], cls[rel[:, 1]], rel[:, 2]), 1)                       # :283-285
+        is_zs = (trip[:, None, :] == zs[None, :, :]).all(-1).any(-1)                             # :287
+        n = int(is_zs.sum())
+        if n:
+            for k in ks:
+                out[k].append(float(((fm < k) & is_zs).sum()) / float(n))                        # :299-306
+    return out
+
+
+def pair_accuracy(predictions, groundtruths, ks: Sequence[int] = (20, 50, 100), iou_thres: float = 0.5,
+                  predcls_like: bool = True) -> Dict[str, Dict[int, List[float]]]:
+    """SGPairAccuracy (sgg_eval.py:338-366, PredCls / SGCls): matching restricted to the predictions whose (subject,
+    object) pair is a ground-truth pair, ranks counted within that filtered list.  Returns {'hit': {k: [...]},
+    'count': {k: [...]}} per image (ground-truth triplets matched within the first k filtered predictions; #gt)."""
+    gt_t, gt_b, pr_t, pr_b, gt_n, pr_n = [], [], [], [], [], []
+    for pred, gt in zip(predictions, groundtruths):
+        rel_tuple = gt.get_field("relation_tuple").long()
+        if rel_tuple.shape[0] == 0:
+            continue
+        gt_cls, gt_box = gt.get_field("labels").long(), gt.convert("xyxy").bbox
+        t, b = triplets(rel_tuple[:, :2], rel_tuple[:, 2], gt_cls, gt_box)
+        gt_t.append(t)
+        gt_b.append(b)
+        gt_n.append(t.shape[0])
+        pairs = pred.get_field("rel_pair_idxs").long()
+        keep = ((pairs[:, 0] * 1024 + pairs[:, 1])[:, None] == (rel_tuple[:, 0] * 1024 + rel_tuple[:, 1])[None, :]).any(1)  # :339-346
+        scores = pred.get_field("pred_rel_scores")[keep]
+        cls, box = (gt_cls, gt_box) if predcls_like else (pred.get_field("pred_labels").long(), pred.convert("xyxy").bbox)
+        t, b = triplets(pairs[keep], 1 + scores[:, 1:].argmax(1), cls, box)
+        pr_t.append(t)
+        pr_b.append(b)
+        pr_n.append(t.shape[0])
+    out = {"hit": {k: [] for k in ks}, "count": {k: [] for k in ks}}
+    if not gt_t:
+        return out
+    first, _ = ops.sgg_match(torch.cat(gt_t), torch.cat(gt_b), gt_n, torch.cat(pr_t), torch.cat(pr_b), pr_n, iou_thres)
+    first_host, off = first.cpu(), 0
+    for n in gt_n:
+        fm = first_host[off:off + n]
+        off += n
+        for k in ks:
+            out["hit"][k].append(float((fm < k).sum()))
+            out["count"][k].append(float(n))
+    return out
