@@ -375,6 +375,21 @@ int veto_sgg_match(const int64_t* gt_triplets_dev, const float* gt_boxes_dev, co
                    const int64_t* pred_triplets_dev, const float* pred_boxes_dev, const int32_t* pred_offsets_dev,
                    int n_images, float iou_thres, int32_t* first_match_dev, int32_t* pred_hits_dev, veto_stream_t stream);
 
+/* f1 (cont.). PostProcessor.forward, MEET EXPERT_GROUP branch (relation_head/inference.py:93-283): three experts per
+ * group; group_logits_dev [R,num_out] holds the 3*G heads expert-major (head e*G + j = expert e of group j, columns
+ * head_offsets[e*G+j] ..; the three experts of a group have the same width n_j + 2), col_map_dev as above.  A candidate
+ * (group, pair) survives when the experts' predicted classes agree: consensus = 0: all three ('U'; score and
+ * probabilities = the mean over the experts), consensus = 1: at least two ('C'; mean over the agreeing expert pairs of
+ * the pair means, with the reference's mean(p1, p1) for the pair (1,2), :191-193).  Survivors of an image are ranked by
+ * score; outputs as veto_postprocess_meet (capacity G*R_i rows per image at row offset G*rel_offsets[i]) plus
+ * counts_out_dev int32 [n_images] = survivors per image (rows beyond it are unspecified). */
+int veto_postprocess_meet_vote(const float* group_logits_dev, int num_out, const int32_t* head_offsets_dev, int n_groups,
+                               const int32_t* col_map_dev, int num_rel, int consensus, const int64_t* pairs_dev,
+                               const float* obj_scores_dev, const int32_t* rel_offsets_dev,
+                               const int32_t* box_offsets_dev, int n_images, int64_t n_pairs, int64_t* pairs_out_dev,
+                               float* probs_out_dev, int64_t* labels_out_dev, float* triple_out_dev,
+                               int32_t* counts_out_dev, veto_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a10. Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874) with nms_overlaps
  * (relation_head/utils_relation.py:56-79): MEET's greedy per-class label assignment at SGDet test time.

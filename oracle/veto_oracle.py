@@ -339,6 +339,11 @@ def meet_forward(sd, batch, pairs, x2d, d2d, group_sizes, mode="predcls", nms_th
         # non-sgdet-test branch: obj_dists one-hot -> argmax over [1:] (+1) (:3783)
         obj_preds = np.concatenate(batch["pred_labels"])
     feat = relation_features(sd, batch, pairs, x2d, d2d, mode, prefix="model.", meet=True, obj_preds=obj_preds)
+    if "model.rel_out_group.0.0.weight" in sd:      # EXPERT_GROUP: 'group_%d%d' % (k, expert + 1) (:3834-3840)
+        experts = 1 + max(int(key.split(".")[2]) for key in sd if key.startswith("model.rel_out_group."))
+        return {"group_%d%d" % (k, j + 1): _linear(feat, sd[f"model.rel_out_group.{j}.{k}.weight"],
+                                                   sd[f"model.rel_out_group.{j}.{k}.bias"])
+                for j in range(experts) for k in range(len(group_sizes))}
     return {f"group_{k}": _linear(feat, sd[f"model.rel_out.{k}.weight"], sd[f"model.rel_out.{k}.bias"])
             for k in range(len(group_sizes))}
 
@@ -546,3 +551,52 @@ def detect_relsample_candidates(prp_boxes, prp_labels, prp_scores, tgt_boxes, tg
     q = prp_scores.astype(f32)[bg[:, 0]] * prp_scores.astype(f32)[bg[:, 1]] if len(bg) else np.zeros(0, f32)
     bg = bg[np.argsort(-q, kind="stable")]
     return dict(locating=locating, binary=binary, gt=gt, bg=[(int(a), int(b)) for a, b in bg], ious=ious)
+
+
+def postprocess_meet_vote(group_logits: Dict[str, np.ndarray], obj_logits: np.ndarray, pairs: np.ndarray, incre_idx: Sequence[int],
+                          voting: str = "C"):
+    """PostProcessor.forward, EXPERT_GROUP branch (relation_head/inference.py:93-283) for ONE image in PredCls / SGCls
+    mode: three experts per group ('group_%d%d' % (group, expert 1..3)); voting 'C' = at least two experts agree on the
+    class, 'U' = all three.  Returns dict(pairs, probs [.,num_rel], labels (head-local), triple) of the survivors, ranked
+    by score (stable).  Follows the reference's arithmetic, including mean(p1, p1) for the expert pair (1,2) (:191-193)."""
+    op = softmax_rows(obj_logits.astype(np.float32))
+    op[:, 0] = 0
+    sc = op[:, 1:].max(1)
+    so = sc[pairs[:, 0]] * sc[pairs[:, 1]]
+    num_rel = len(incre_idx)
+    n_groups = len(group_logits) // 3
+    T, PR, LB, PB = [], [], [], []
+    for j in range(n_groups):
+        p = [softmax_rows(group_logits["group_%d%d" % (j, e)].astype(np.float32))[:, :-1] for e in (1, 2, 3)]
+        c = [x[:, 1:].argmax(1) + 1 for x in p]
+        t = [x[:, 1:].max(1) * so for x in p]
+        agree = [c[0] == c[1], c[1] == c[2], c[0] == c[2]]
+        if voting == "U":
+            keep = agree[0] & agree[1] & agree[2]
+            triple = np.mean(np.stack(t, 1), 1)
+            prob = np.mean(np.stack(p, 1), 1)
+            cls = c[2]
+        else:
+            ab = np.stack(agree, 1)
+            count = ab.sum(1)
+            tavg = np.stack([(t[0] + t[1]) / 2, (t[1] + t[2]) / 2, (t[0] + t[2]) / 2], 1)
+            pavg = np.stack([(p[0] + p[1]) / 2, (p[1] + p[1]) / 2, (p[0] + p[2]) / 2], 1)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                triple = np.where(ab, tavg, 0).sum(1) / count
+                prob = np.where(ab[:, :, None], pavg, 0).sum(1) / count[:, None]
+            triple = np.nan_to_num(triple, nan=0.0)
+            cls = np.zeros_like(c[0])
+            for cc, a in zip(c, agree):
+                cls[a] = cc[a]
+            keep = ab.any(1)
+        cols = [0] + [i for i, g in enumerate(incre_idx) if g == j + 1]
+        full = np.zeros((len(pairs), num_rel), np.float32)
+        full[:, cols] = prob
+        T.append(triple[keep].astype(np.float32))
+        PR.append(pairs[keep])
+        LB.append(cls[keep])
+        PB.append(full[keep])
+    triple = np.concatenate(T)
+    order = np.argsort(-triple, kind="stable")
+    return dict(pairs=np.concatenate(PR)[order], probs=np.concatenate(PB)[order], labels=np.concatenate(LB)[order],
+                triple=triple[order])

@@ -34,6 +34,9 @@ CASES = {
                     batch_seed=6, weight_seed=15, spread=True, H=320, W=416),
     # MEET at SGDet test time: obj_preds from the per-class greedy NMS (Ensemble.nms_per_cls, :3855-3874); detector
     # labels from 3 classes + jittered boxes_per_cls so that overlapping boxes compete for a class
+    # MEET with EXPERT_GROUP (3 experts per group, defaults.py:864) and the voting post-processor (inference.py:93-283)
+    "meet_vg_experts": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", n_boxes=[10],
+                            batch_seed=12, weight_seed=20, spread=True, H=320, W=416, expert_group=True, expert_noise=0.35),
     # vanilla predictor + PostProcessor at SGDet test time: late per-class NMS (obj_prediction_nms) on peaked detector
     # logits, boxes re-regressed per class (relation_head/inference.py:414-431)
     "sgdet_post_nms": dict(predictor="VETOPredictor", mode="sgdet", dataset="VG", n_boxes=[12, 7],
@@ -107,7 +110,8 @@ def case_state(c):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA
     if c["predictor"].endswith("MEET"):
         return synth.meet_state(c["weight_seed"], ds["num_obj"], synth.GROUP_SPLITS[(c["dataset"], "divide4")],
-                                spread=c["spread"])
+                                spread=c["spread"], experts_per_group=3 if c.get("expert_group") else 1,
+                                expert_group=bool(c.get("expert_group")), expert_noise=c.get("expert_noise", 0.0))
     return synth.predictor_state(c["weight_seed"], ds["num_obj"], ds["num_rel"], spread=c["spread"])
 
 

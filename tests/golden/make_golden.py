@@ -39,7 +39,8 @@ def run_case(ns, name, c):
     ds = synth.VG if c["dataset"] == "VG" else synth.GQA
     meet = c["predictor"].endswith("MEET")
     cfg = ref_shim.make_cfg(ns, predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"],
-                            max_pairs=c.get("max_pairs", 2048), require_overlap=c.get("require_overlap", False))
+                            max_pairs=c.get("max_pairs", 2048), require_overlap=c.get("require_overlap", False),
+                            expert_group=bool(c.get("expert_group")))
     sd = case_state(c)
     pred = ref_shim.build_predictor(ns, cfg, ds["num_obj"], ds["num_rel"], synth.to_torch_state(sd))
     batch = case_batch(c)
@@ -80,7 +81,25 @@ def run_case(ns, name, c):
         for k, v in rel_d.items():
             out["logits_" + k] = v.numpy()
         out["incre_idx_list"] = np.array(incre)
-        if c["mode"] == "predcls" and batch["B"] == 1:
+        if c["mode"] == "predcls" and batch["B"] == 1 and c.get("expert_group"):
+            # EXPERT_GROUP voting branch (inference.py:93-283), both voting rules on the same logits
+            real_cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            try:
+                for voting in ("C", "U"):
+                    cfg.merge_from_list(["ENSEMBLE_LEARNING.VOTING", voting])
+                    vpost = ns.make_post(cfg)
+                    import copy
+                    vb = [copy.deepcopy(b) for b in bls]
+                    res = vpost((rel_d, [b.get_field("predict_logits") for b in vb]), pairs, vb, incre_idx_list=incre)
+                    r0 = res[0]
+                    out[f"vote{voting}_pairs"] = r0.get_field("rel_pair_idxs").numpy()
+                    out[f"vote{voting}_probs"] = r0.get_field("pred_rel_scores").numpy()
+                    out[f"vote{voting}_labels"] = r0.get_field("pred_rel_labels").numpy()
+                    print(f"{name}: voting {voting}: {len(out[f'vote{voting}_labels'])} of {5 * len(pairs[0])} candidates survive")
+            finally:
+                torch.Tensor.cuda = real_cuda
+        elif c["mode"] == "predcls" and batch["B"] == 1:
             # MEET 'ensemble' branch of the post-processor (inference.py:284-397); its hard-coded .cuda() calls are
             # neutralised for the CPU run, nothing else is touched
             real_cuda = torch.Tensor.cuda

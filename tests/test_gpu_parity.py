@@ -187,6 +187,7 @@ def _run_predictor(name, precision, chunk=0, pairs=None):
     batch, state, g = case_batch(c), case_state(c), load_golden(name)
     cfg = H.make_cfg(c["predictor"], c["mode"], c["dataset"], c.get("max_pairs", 2048), c.get("require_overlap", False),
                      precision, chunk)
+    cfg.ENSEMBLE_LEARNING.EXPERT_GROUP = bool(c.get("expert_group"))
     ds_obj = 151 if c["dataset"] == "VG" else 201
     bls = H.boxlists(batch, DEV, ds_obj)
     feats, depth = H.device_features(batch, DEV)
@@ -255,7 +256,7 @@ def test_tokens_match_reference(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("name", ["meet_gqa", "meet_vg", "meet_sgdet_nms"])
+@pytest.mark.parametrize("name", ["meet_gqa", "meet_vg", "meet_sgdet_nms", "meet_vg_experts"])
 def test_meet_group_heads(name, precision):
     c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
     obj_dists, rel_dists, add_losses, incre, chosen, custom = out
@@ -570,6 +571,50 @@ def test_meet_postprocess_ensemble_merge(precision):
         assert np.array_equal(H.np_(r.get_field("rel_pair_idxs"))[clear].astype(np.int64), ora["pairs"][clear])
         assert np.array_equal(H.np_(r.get_field("pred_rel_labels"))[clear], ora["labels"][clear])
         assert np.abs(H.np_(r.get_field("pred_rel_scores"))[clear] - ora["probs"][clear]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("voting", ["C", "U"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_meet_postprocess_expert_voting(precision, voting):
+    """PostProcessor EXPERT_GROUP branch (inference.py:93-283): three experts per group vote on every candidate —
+    survivors, their head-local labels, scattered probabilities and ranking against the unmodified reference; and, on
+    OUR logits, exactly the oracle's survivors."""
+    from veto_b200.postprocess import make_roi_relation_post_processor
+    name = "meet_vg_experts"
+    c, batch, g, bls, pairs, pred, out = _run_predictor(name, precision)
+    assert sorted(out[1]) == sorted("group_%d%d" % (k, e) for k in range(5) for e in (1, 2, 3))
+    cfg = H.make_cfg("VETOPredictor_MEET", "predcls", "VG", precision=precision)
+    cfg.ENSEMBLE_LEARNING.EXPERT_GROUP = True
+    cfg.ENSEMBLE_LEARNING.VOTING = voting
+    res = make_roi_relation_post_processor(cfg)((out[1], [b.get_field("predict_logits") for b in bls]), pairs, bls,
+                                                incre_idx_list=out[3])
+    pp, probs = H.np_(res[0].get_field("rel_pair_idxs")), H.np_(res[0].get_field("pred_rel_scores"))
+    labels, trip = H.np_(res[0].get_field("pred_rel_labels")), H.np_(res[0].get_field("triple_scores")).astype(np.float64)
+    assert pp.dtype == np.float32 and np.all(np.diff(trip) <= 0)
+    # against the oracle's vote on OUR logits: the same survivors in the same order wherever scores are distinct
+    ora = O.postprocess_meet_vote({k: H.np_(v) for k, v in out[1].items()}, H.np_(bls[0].get_field("predict_logits")),
+                                  H.np_(pairs[0]), list(out[3]), voting)
+    assert len(trip) == len(ora["triple"])
+    so = ora["triple"].astype(np.float64)
+    gap = np.full(len(so), np.inf)
+    gap[1:] = np.minimum(gap[1:], so[:-1] - so[1:])
+    gap[:-1] = np.minimum(gap[:-1], so[:-1] - so[1:])
+    clear = gap > 1e-5 * so
+    assert clear.mean() > 0.5
+    assert np.array_equal(pp[clear].astype(np.int64), ora["pairs"][clear]) and np.array_equal(labels[clear], ora["labels"][clear])
+    assert np.abs(probs[clear] - ora["probs"][clear]).max() <= 1e-5
+    # against the reference's output: the survivor count may differ only by candidates whose experts' top-2 margin is
+    # inside the mode's logit tolerance; rows with clearly separated scores sit at the same rank with the same content
+    ref_pairs, ref_probs, ref_labels = g[f"vote{voting}_pairs"], g[f"vote{voting}_probs"], g[f"vote{voting}_labels"]
+    assert abs(len(trip) - len(ref_labels)) <= (0 if precision == "fp32" else 3)
+    if len(trip) == len(ref_labels):
+        gap = np.full(len(trip), np.inf)
+        gap[1:] = np.minimum(gap[1:], trip[:-1] - trip[1:])
+        gap[:-1] = np.minimum(gap[:-1], trip[:-1] - trip[1:])
+        clear = gap > {"fp32": 2e-5, "bf16x3": 4e-4}[precision] * trip
+        assert clear.mean() > 0.3
+        assert np.array_equal(pp[clear], ref_pairs[clear]) and np.array_equal(labels[clear], ref_labels[clear])
+        assert np.abs(probs[clear] - ref_probs[clear]).max() <= TOL[precision]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])

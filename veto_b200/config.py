@@ -78,7 +78,7 @@ _DEFAULTS = {
     "DATASETS": {"USE_DEPTH": True},
     "GLOBAL_SETTING": {"DATASET_CHOICE": "VG", "USE_BIAS": False, "BETA_LOSS": False},
     "GCL_SETTING": {"GROUP_SPLIT_MODE": "divide4", "ZERO_LABEL_PADDING_MODE": "rand_insert"},
-    "ENSEMBLE_LEARNING": {"ENABLED": False, "TYPE": "group", "VOTING": "unanimous", "EXPERT_GROUP": False},
+    "ENSEMBLE_LEARNING": {"ENABLED": False, "TYPE": "group", "VOTING": "C", "EXPERT_GROUP": False},
     "GLOVE_DIR": "",
     "OUTPUT_DIR": "",
     # extension (not a reference key): arithmetic of the encoder GEMMs, see include/veto_b200.h

@@ -207,6 +207,176 @@ meet_postprocess_kernel(const float* __restrict__ logits, int ld, const int32_t*
     }
 }
 
+// PostProcessor.forward, MEET EXPERT_GROUP branch (relation_head/inference.py:93-283): three experts per group, a
+// candidate (group j, pair r) survives the vote when the experts' predicted classes agree — all three ('U', unanimous)
+// or at least two ('C', consensus).  One warp handles one candidate: three softmaxes over the experts' heads (out-of-
+// group column dropped), the per-expert class / triple score, then
+//   unanimous: score = mean of the three triple scores, probabilities = mean of the three rows;
+//   consensus: over the agreeing expert PAIRS (0,1), (1,2), (0,2): score = mean of the pair means, probabilities = mean
+//              of the pair means — where the reference's (1,2) probability "mean" is mean(p1, p1) = p1 (:191-193);
+//              reproduced as is.
+// Survivors are ranked by score (ties: merged index) and scattered into global predicate columns like the 'ensemble'
+// branch; the number of survivors per image goes to counts_out.  Heads are laid out expert-major: head e * G + j.
+struct ExpertRow {
+    float t[3];   // triple scores of the three experts
+    int c[3];     // predicted head-local classes
+};
+
+__device__ __forceinline__ void expert_softmax(const float* lg, int nc, int lane, float& m, float& sum, float& best, int& besti) {
+    m = -INFINITY;
+    for (int c = lane; c < nc; c += 32) m = fmaxf(m, lg[c]);
+    m = wmax(m);
+    sum = 0.f;
+    best = -INFINITY;
+    besti = 0x7fffffff;
+    for (int c = lane; c < nc; c += 32) {
+        const float e = expf(lg[c] - m);
+        sum += e;
+        if (c >= 1 && c < nc - 1 && e > best) { best = e; besti = c; }
+    }
+    sum = wsum(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+}
+
+// vote of one candidate: returns whether it survives; score / class of the survivor; w[e] = weight of expert e's
+// probability row in the survivor's probability row (sums to 1)
+__device__ __forceinline__ bool expert_vote(const ExpertRow& x, int consensus, float& score, int& cls, float (&w)[3]) {
+    const bool a01 = x.c[0] == x.c[1], a12 = x.c[1] == x.c[2], a02 = x.c[0] == x.c[2];
+    if (!consensus) {
+        score = ((x.t[0] + x.t[1]) + x.t[2]) / 3.f;
+        cls = x.c[2];
+        w[0] = w[1] = w[2] = 1.f / 3.f;
+        return a01 && a12 && a02;
+    }
+    const int count = (int)a01 + (int)a12 + (int)a02;
+    if (count == 0) return false;
+    float ssum = 0.f;
+    w[0] = w[1] = w[2] = 0.f;
+    if (a01) { ssum += (x.t[0] + x.t[1]) * 0.5f; w[0] += 0.5f; w[1] += 0.5f; cls = x.c[0]; }
+    if (a12) { ssum += (x.t[1] + x.t[2]) * 0.5f; w[1] += 1.0f; cls = x.c[1]; }              // mean(p1, p1): :191-193
+    if (a02) { ssum += (x.t[0] + x.t[2]) * 0.5f; w[0] += 0.5f; w[2] += 0.5f; cls = x.c[2]; }
+    score = ssum / (float)count;
+    const float inv = 1.f / (float)count;
+    w[0] *= inv; w[1] *= inv; w[2] *= inv;
+    return true;
+}
+
+__global__ void __launch_bounds__(1024)
+meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __restrict__ head_off, int n_groups,
+                 const int32_t* __restrict__ col_map, int num_rel, int consensus, const int64_t* __restrict__ pairs,
+                 const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off, const int32_t* __restrict__ box_off,
+                 int64_t* __restrict__ pairs_out, float* __restrict__ probs_out, int64_t* __restrict__ labels_out,
+                 float* __restrict__ triple_out, int32_t* __restrict__ counts_out) {
+    extern __shared__ unsigned long long keys[];  // [npow]
+    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
+    float* trip = (float*)(lab + kMaxRows);
+    __shared__ int s_kept;
+    const int b = blockIdx.x;
+    const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
+    const int merged = rows * n_groups;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    if (merged <= 0) {
+        if (threadIdx.x == 0) counts_out[b] = 0;
+        return;
+    }
+    if (merged > kMaxRows) {
+        if (threadIdx.x == 0) printf("veto_postprocess_meet_vote: image %d has %d candidate rows > %d\n", b, merged, kMaxRows);
+        __trap();
+    }
+    const int boff = box_off[b];
+    const size_t out0 = (size_t)r0 * n_groups;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int npow = 1;
+    while (npow < merged) npow <<= 1;
+
+    auto experts = [&](int q, ExpertRow& x, float (&mm)[3], float (&ss)[3]) {
+        const int j = q / rows, r = q - j * rows;
+        const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
+        const float so = obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int c0 = head_off[e * n_groups + j], nc = head_off[e * n_groups + j + 1] - c0;
+            float best;
+            int besti;
+            expert_softmax(logits + (size_t)(r0 + r) * ld + c0, nc, lane, mm[e], ss[e], best, besti);
+            x.c[e] = besti;
+            x.t[e] = (best / ss[e]) * so;
+        }
+    };
+
+    int my_kept = 0;
+    for (int q = wid; q < merged; q += nw) {
+        ExpertRow x;
+        float mm[3], ss[3], w[3], score = 0.f;
+        int cls = 0;
+        experts(q, x, mm, ss);
+        const bool keep = expert_vote(x, consensus, score, cls, w);
+        if (lane == 0) {
+            if (keep) {
+                unsigned int u = __float_as_uint(score);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
+                lab[q] = (unsigned short)cls;
+                trip[q] = score;
+                ++my_kept;
+            } else {
+                keys[q] = ~0ull;
+            }
+        }
+    }
+    if (lane == 0 && my_kept) atomicAdd(&s_kept, my_kept);
+    for (int q = merged + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int q = threadIdx.x; q < npow; q += blockDim.x) {
+                const int p = q ^ j;
+                if (p > q) {
+                    const unsigned long long a = keys[q], c = keys[p];
+                    const bool up = ((q & k) == 0);
+                    if ((a > c) == up) { keys[q] = c; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int kept = s_kept;
+    if (threadIdx.x == 0) counts_out[b] = kept;
+    for (int rank = wid; rank < kept; rank += nw) {
+        const int q = (int)(keys[rank] & 0xffffffffull);
+        const int j = q / rows, r = q - j * rows;
+        ExpertRow x;
+        float mm[3], ss[3], w[3], score = 0.f;
+        int cls = 0;
+        experts(q, x, mm, ss);
+        expert_vote(x, consensus, score, cls, w);
+        float* po = probs_out + (out0 + rank) * num_rel;
+        for (int c = lane; c < num_rel; c += 32) po[c] = 0.f;
+        __syncwarp();
+        const int c0 = head_off[j], nc = head_off[j + 1] - c0;   // every expert of group j has the same width / column map
+        for (int c = lane; c < nc - 1; c += 32) {
+            float v = 0.f;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const float* lg = logits + (size_t)(r0 + r) * ld + head_off[e * n_groups + j];
+                v += w[e] * (expf(lg[c] - mm[e]) / ss[e]);
+            }
+            po[col_map[c0 + c]] = v;
+        }
+        if (lane == 0) {
+            *(longlong2*)(pairs_out + 2 * (out0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
+            labels_out[out0 + rank] = lab[q];
+            triple_out[out0 + rank] = trip[q];
+        }
+    }
+}
+
 }  // namespace
 }  // namespace veto
 
@@ -255,6 +425,31 @@ extern "C" int veto_postprocess_meet(const float* group_logits_dev, int num_out,
     meet_postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(
         group_logits_dev, num_out, head_offsets_dev, n_heads, col_map_dev, num_rel, pairs_dev, obj_scores_dev, rel_offsets_dev,
         box_offsets_dev, pairs_out_dev, probs_out_dev, labels_out_dev, triple_out_dev);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+extern "C" int veto_postprocess_meet_vote(const float* group_logits_dev, int num_out, const int32_t* head_offsets_dev, int n_groups,
+                                          const int32_t* col_map_dev, int num_rel, int consensus, const int64_t* pairs_dev,
+                                          const float* obj_scores_dev, const int32_t* rel_offsets_dev,
+                                          const int32_t* box_offsets_dev, int n_images, int64_t n_pairs, int64_t* pairs_out_dev,
+                                          float* probs_out_dev, int64_t* labels_out_dev, float* triple_out_dev,
+                                          int32_t* counts_out_dev, veto_stream_t stream) {
+    if (n_images <= 0) return VETO_OK;
+    VETO_REQUIRE(group_logits_dev && head_offsets_dev && col_map_dev && pairs_dev && obj_scores_dev && rel_offsets_dev &&
+                     box_offsets_dev && pairs_out_dev && probs_out_dev && labels_out_dev && triple_out_dev && counts_out_dev &&
+                     n_groups >= 1 && num_out >= 9 * n_groups && num_rel >= 2 && num_rel < 65536 && n_pairs >= 0,
+                 VETO_ERR_ARG, "veto_postprocess_meet_vote: bad argument");
+    set_tag(TAG_POST);
+    static bool attr_set = false;
+    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
+    if (!attr_set) {
+        VETO_CUDA(cudaFuncSetAttribute(meet_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    meet_vote_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(
+        group_logits_dev, num_out, head_offsets_dev, n_groups, col_map_dev, num_rel, consensus, pairs_dev, obj_scores_dev,
+        rel_offsets_dev, box_offsets_dev, pairs_out_dev, probs_out_dev, labels_out_dev, triple_out_dev, counts_out_dev);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -100,6 +100,8 @@ _PROTOS = {
                                      c_void_p]),
     "veto_postprocess_meet": (c_int, [_fp, c_int, _fp, c_int, _fp, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp, _fp, _fp,
                                       c_void_p]),
+    "veto_postprocess_meet_vote": (c_int, [_fp, c_int, _fp, c_int, _fp, c_int, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp,
+                                           _fp, _fp, _fp, c_void_p]),
     "veto_obj_nms_per_cls": (c_int, [_fp, _fp, _fp, POINTER(c_int32), c_int, c_int, c_float, c_int, _fp, c_void_p]),
     "veto_test_gemm": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_void_p]),
     "veto_test_gemm_tn": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_uint32), _fp, c_size_t,

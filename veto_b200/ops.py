@@ -568,6 +568,43 @@ def postprocess_meet(group_logits: torch.Tensor, head_sizes: Sequence[int], col_
     return pairs_o, probs_o, labels_o, triple_o
 
 
+def postprocess_meet_vote(group_logits: torch.Tensor, head_sizes: Sequence[int], col_map: Sequence[int], num_rel: int,
+                          consensus: bool, pairs: torch.Tensor, obj_scores: torch.Tensor, rel_counts: Sequence[int],
+                          n_boxes: Sequence[int]):
+    """PostProcessor MEET EXPERT_GROUP branch (inference.py:93-283): group_logits [R, 3 * sum(n_k+2)] expert-major,
+    head_sizes / col_map for all 3*G heads.  Returns (pairs [G*R,2], probs [G*R,num_rel], labels [G*R], triple [G*R],
+    counts [B] int32 — survivors per image; image b's rows start at G * (pairs before it))."""
+    L.require_device()
+    group_logits, obj_scores = _cuda_f32(group_logits), _cuda_f32(obj_scores)
+    pairs = pairs.to(torch.int64).contiguous()
+    R, Ct = group_logits.shape
+    if len(head_sizes) % 3 or sum(head_sizes) != Ct or len(col_map) != Ct or sum(rel_counts) != R:
+        raise RuntimeError("head_sizes (3 experts x G groups) / col_map / rel_counts do not match the group logits")
+    G = len(head_sizes) // 3
+    if any(head_sizes[e * G + j] != head_sizes[j] for e in range(3) for j in range(G)):
+        raise RuntimeError("the three experts of a group must have the same number of outputs")
+    dev = group_logits.device
+    if max(rel_counts, default=0) * G > 16384:
+        raise RuntimeError("veto_postprocess_meet_vote sorts one image in shared memory: at most 16384 candidate rows per image")
+    pairs_o = torch.zeros((G * R, 2), dtype=torch.int64, device=dev)
+    probs_o = torch.zeros((G * R, num_rel), dtype=torch.float32, device=dev)
+    labels_o = torch.zeros(G * R, dtype=torch.int64, device=dev)
+    triple_o = torch.zeros(G * R, dtype=torch.float32, device=dev)
+    counts = torch.zeros(len(rel_counts), dtype=torch.int32, device=dev)
+    if R:
+        rel_off = offsets_tensor(rel_counts, dev)
+        box_off = offsets_tensor(n_boxes, dev)
+        head_off = torch.tensor([0] + list(itertools.accumulate(int(n) for n in head_sizes)), dtype=torch.int32, device=dev)
+        cmap = torch.tensor([int(c) for c in col_map], dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().veto_postprocess_meet_vote(
+                group_logits.data_ptr(), Ct, head_off.data_ptr(), G, cmap.data_ptr(), num_rel, int(bool(consensus)),
+                pairs.data_ptr(), obj_scores.data_ptr(), rel_off.data_ptr(), box_off.data_ptr(), len(rel_counts), R,
+                pairs_o.data_ptr(), probs_o.data_ptr(), labels_o.data_ptr(), triple_o.data_ptr(), counts.data_ptr(),
+                L.stream_ptr()), "veto_postprocess_meet_vote")
+    return pairs_o, probs_o, labels_o, triple_o, counts
+
+
 # --------------------------------------------------------------------------------------------
 # f4: evaluation triplet matching
 # --------------------------------------------------------------------------------------------

@@ -7,10 +7,13 @@ The reference's torch.sort is unstable; ties are broken by the original row (asc
 ``veto_obj_nms_per_cls`` with late_nms) and the boxes are re-regressed to the chosen class (:425-431).
 The MEET 'ensemble' branch (ENSEMBLE_LEARNING.ENABLED with EXPERT_GROUP False, :284-397) merges the group heads'
 candidates of an image into one ranked list (``veto_postprocess_meet``); the reference only ever processes image 0
-there (TEST.IMS_PER_BATCH 1), the drop-in handles the whole batch and is identical for a batch of one.  The
-EXPERT_GROUP voting branches (consensus / unanimous, :93-283) are not built.
+there (TEST.IMS_PER_BATCH 1), the drop-in handles the whole batch and is identical for a batch of one.  With
+ENSEMBLE_LEARNING.EXPERT_GROUP the three experts of a group vote on every candidate (VOTING 'C' consensus / 'U'
+unanimous, :93-283, ``veto_postprocess_meet_vote``).
 """
 from __future__ import annotations
+
+import itertools
 
 import torch
 import torch.nn as nn
@@ -33,18 +36,28 @@ class PostProcessor(nn.Module):
                 ensemble=False):
         relation_logits, refine_logits = x
         meet = isinstance(relation_logits, dict)
+        vote = None
         if meet:
-            if self.cfg is not None and C.get(self.cfg, "ENSEMBLE_LEARNING.EXPERT_GROUP", False):
-                raise NotImplementedError("EXPERT_GROUP voting post-processing (inference.py:93-283) is not built")
             if incre_idx_list is None:
                 raise RuntimeError("MEET post-processing needs incre_idx_list (the predictor's 4th return value)")
-            names = ["group_%d" % k for k in range(len(relation_logits))]          # :294-299
+            expert_group = self.cfg is not None and bool(C.get(self.cfg, "ENSEMBLE_LEARNING.EXPERT_GROUP", False))
+            if expert_group:                                                        # :93-113: three experts per group
+                voting = str(C.get(self.cfg, "ENSEMBLE_LEARNING.VOTING", "C"))
+                if voting not in ("C", "U"):
+                    raise RuntimeError("ENSEMBLE_LEARNING.VOTING must be 'C' (consensus) or 'U' (unanimous)")
+                vote = voting == "C"
+                n_groups = len(relation_logits) // 3
+                names = ["group_%d%d" % (k, e) for e in (1, 2, 3) for k in range(n_groups)]
+            else:
+                n_groups = len(relation_logits)
+                names = ["group_%d" % k for k in range(n_groups)]                  # :294-299
             head_sizes = [int(relation_logits[n].shape[1]) for n in names]
             col_map = []
-            for k, n in enumerate(head_sizes):                                      # chosen_labels_incr (:351-353)
-                members = [i for i, g in enumerate(incre_idx_list) if g == k + 1]
+            for i, n in enumerate(head_sizes):                                      # chosen_labels_incr (:351-353)
+                k = i % n_groups
+                members = [c for c, g in enumerate(incre_idx_list) if g == k + 1]
                 if len(members) + 2 != n:
-                    raise RuntimeError(f"head group_{k} has {n} outputs but {len(members)} member predicates")
+                    raise RuntimeError(f"head {names[i]} has {n} outputs but group {k} has {len(members)} member predicates")
                 col_map += [0] + members + [0]                                      # last column (out of group) is dropped
             group_logits = torch.cat([relation_logits[n] for n in names], 1)
         n_boxes = [len(b) for b in boxes]
@@ -60,7 +73,15 @@ class PostProcessor(nn.Module):
             boxes_per_cls = torch.cat([b.get_field("boxes_per_cls") for b in boxes], 0)
             obj_pred = ops.obj_nms_per_cls(obj_prob, boxes_per_cls, n_boxes, self.later_nms_pred_thres, late_nms=True)
             obj_scores = obj_prob.gather(1, obj_pred[:, None])[:, 0]
-        if meet:
+        row_starts = None
+        if meet and vote is not None:
+            pairs_o, probs_o, labels_o, triple_o, kept = ops.postprocess_meet_vote(
+                group_logits, head_sizes, col_map, len(incre_idx_list), vote, torch.cat(list(rel_pair_idxs), 0), obj_scores,
+                rel_counts, n_boxes)
+            pairs_o = pairs_o.float()      # :272
+            row_starts = [n_groups * o for o in itertools.accumulate([0] + rel_counts[:-1])]
+            rel_counts = kept.tolist()     # survivors of the vote per image (one host sync)
+        elif meet:
             G = len(head_sizes)
             pairs_o, probs_o, labels_o, triple_o = ops.postprocess_meet(
                 group_logits, head_sizes, col_map, len(incre_idx_list), torch.cat(list(rel_pair_idxs), 0), obj_scores,
@@ -72,7 +93,9 @@ class PostProcessor(nn.Module):
                                                                    torch.cat(list(rel_pair_idxs), 0), obj_scores,
                                                                    rel_counts, n_boxes)
         results, ro, bo = [], 0, 0
-        for box, nb, nr in zip(boxes, n_boxes, rel_counts):
+        for img, (box, nb, nr) in enumerate(zip(boxes, n_boxes, rel_counts)):
+            if row_starts is not None:
+                ro = row_starts[img]
             if self.use_gt_box:
                 bl = box  # the reference adds the result fields to the input BoxList too (:431-452)
             else:         # sgdet: boxes regressed for the finetuned class (:425-431); a NEW BoxList without the input's fields
