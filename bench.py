@@ -46,7 +46,7 @@ TR_WORKLOAD = ("configs[1]: VETO vanilla PredCls training step, IMS_PER_BATCH 12
 # configs[2]: SGDet-shaped inference
 N_IMAGES, N_BOXES, MAX_PAIRS = 32, 80, 8192
 INF_WORKLOAD = ("configs[2]: SGDet-shaped inference, 32 images x 80 proposals (6320 pairs/image, MAX_PROPOSAL_PAIR 8192), "
-                "VG 151/51, 592x800 images, P2-P5 + depth NCHW fp32")
+                "VG 151/51, 592x800 images, P2-P5 + depth NCHW fp32; pairs -> ROI gather -> predictor -> post-processor")
 
 
 def parse():
@@ -159,7 +159,9 @@ def cpu_infer_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
     from veto_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    from oracle import veto_oracle as O
     batch = synth.make_batch(1000, [N_BOXES], H=IMG_H, W=IMG_W, mode="sgdet")
+    synth.add_nms_fields(batch, 1300, relabel=False)
     sd = TP.to_torch(synth.predictor_state(11))
     feats = [torch.from_numpy(f) for f in batch["feats"]]
     depth = torch.from_numpy(batch["depth"])
@@ -175,13 +177,14 @@ def cpu_infer_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
             sub = [pairs[0][:sample_pairs]]
             t1 = time.perf_counter()
             logits = TP.predictor_forward(sd, boxes, sub, x2d, d2d, "sgdet", predict_logits=plog)
+            O.postprocess_sgdet([logits.numpy()], batch["predict_logits"], [sub[0].numpy()], batch["boxes_per_cls"], 0.5)
             t_pairs = time.perf_counter() - t1
             assert bool(torch.isfinite(logits).all())
             if it >= warmup:
                 times.append(t_fixed / len(pairs[0]) + t_pairs / len(sub[0]))
     per_pair = sorted(times)[len(times) // 2]
-    sample = (f"1 image x {N_BOXES} proposals: pair enumeration + ROI gather (amortised over 6320 pairs) + predictor on the "
-              f"first {len(sub[0])} pairs; oracle/torch_port.py on torch CPU fp32 kernels, {cores} threads")
+    sample = (f"1 image x {N_BOXES} proposals: pair enumeration + ROI gather (amortised over 6320 pairs) + predictor and "
+              f"post-processor on the first {len(sub[0])} pairs; oracle/torch_port.py on torch CPU fp32 kernels, {cores} threads")
     return 1.0 / per_pair, cores, sample, per_pair
 
 
@@ -217,6 +220,7 @@ def main():
     from veto_b200 import lib as L
     from veto_b200 import ops, registry, synth
     from veto_b200.distributed import allreduce_gradients, max_over_ranks
+    from veto_b200.postprocess import make_roi_relation_post_processor
     from veto_b200.sampling import make_roi_relation_samp_processor
     from veto_b200.structures import BoxList
 
@@ -259,8 +263,8 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1), dev) / steps, (ops.launch_count() - n0)
 
     def host_boxlists(bls):
-        return ([pin(b.bbox) for b in bls],
-                [{k: pin(b.get_field(k)) for k in ("labels", "predict_logits", "pred_scores", "pred_labels")} for b in bls])
+        keys = ("labels", "predict_logits", "pred_scores", "pred_labels", "boxes_per_cls")
+        return ([pin(b.bbox) for b in bls], [{k: pin(b.get_field(k)) for k in keys if b.has_field(k)} for b in bls])
 
     # =============================================================================== configs[1]: training step
     B = args.images
@@ -487,26 +491,35 @@ def main():
         Bi = args.inference_images
         Ri = Bi * N_BOXES * (N_BOXES - 1)
         ibatch = synth.make_batch(200 + rank, [N_BOXES] * Bi, H=IMG_H, W=IMG_W, mode="sgdet", features=False)
+        synth.add_nms_fields(ibatch, 300 + rank, relabel=False)          # the detector's per-class boxes (late NMS input)
         ifeats = [torch.randn((Bi, 256) + hw, generator=g, device=dev) for hw in rgb_hw]
         idepth = torch.relu(torch.randn((Bi, 256) + depth_hw, generator=g, device=dev))
         icfg = H.make_cfg(mode="sgdet", max_pairs=MAX_PAIRS, precision=args.precision, chunk_pairs=args.chunk)
         ipred = H.build_predictor(icfg, synth.predictor_state(11), dev)
         ife = registry.make_roi_box_feature_extractor(icfg, 256, for_relation=True).to(dev).eval()
         isamp = make_roi_relation_samp_processor(icfg)
+        ipost = make_roi_relation_post_processor(icfg)
         ibls = H.boxlists(ibatch, dev, 151)
+
+        def infer_head(feats, depth, bls):
+            """ROIRelationHead.forward at test time (relation_head.py:134-243): candidate pairs -> ROI gather ->
+            predictor -> post-processor (late per-class NMS of the objects, triple scores, per-image ranking)."""
+            pairs = isamp.prepare_test_pairs(dev, bls)
+            x2d, d2d, _, _ = ife(feats, bls, depth_features=depth)
+            rel = ipred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
+            return ipost((rel, [b.get_field("predict_logits") for b in bls]), pairs, bls)
 
         def infer_resident():
             with torch.no_grad():
-                pairs = isamp.prepare_test_pairs(dev, ibls)
-                x2d, d2d, _, _ = ife(ifeats, ibls, depth_features=idepth)
-                return ipred(ibls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
+                return infer_head(ifeats, idepth, ibls)
 
         ifeats_host = [pin(f) for f in ifeats]
         idepth_host = pin(idepth)
         iboxes_host, ifields_host = host_boxlists(ibls)
         ih2d = sum(t.numel() * t.element_size() for t in ifeats_host + [idepth_host] + iboxes_host)
         ih2d += sum(t.numel() * t.element_size() for f in ifields_host for t in f.values())
-        logits_host = torch.empty((Ri, 51), dtype=torch.float32).pin_memory()
+        logits_host = torch.empty((Ri, 51), dtype=torch.float32).pin_memory()      # ranked class probabilities
+        pairs_host = torch.empty((Ri, 2), dtype=torch.int64).pin_memory()           # ranked pairs
 
         def infer_slot():
             feats = [dev_like(f) for f in ifeats_host]
@@ -521,11 +534,10 @@ def main():
             with torch.no_grad():
                 sl = infer_pipe.acquire()
                 feats, depth, bls = sl["struct"]
-                pairs = isamp.prepare_test_pairs(dev, bls)
-                x2d, d2d, _, _ = ife(feats, bls, depth_features=depth)
-                rel = ipred(bls, pairs, None, None, roi_features=x2d, roi_depth_features=d2d)[1]
+                res = infer_head(feats, depth, bls)
                 infer_pipe.release(sl)
-                logits_host.copy_(torch.cat(list(rel)), non_blocking=True)
+                logits_host.copy_(torch.cat([r.get_field("pred_rel_scores") for r in res]), non_blocking=True)
+                pairs_host.copy_(torch.cat([r.get_field("rel_pair_idxs") for r in res]), non_blocking=True)
 
         isteps = max(2, min(args.steps, 5))
         ims, ilaunches = timed(infer_resident, isteps, max(3, min(args.warmup, 3)))
@@ -561,7 +573,7 @@ def main():
             "config": {"workload": INF_WORKLOAD, "images_per_gpu": Bi, "pairs_per_step_per_gpu": Ri,
                        "chunk_pairs": ipred.chunk_pairs or "library default"},
             "e2e": {"value": world * Ri / ims_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": ih2d,
-                    "d2h_bytes_per_step": logits_host.numel() * 4, "ms_per_step": ims_e2e,
+                    "d2h_bytes_per_step": logits_host.numel() * 4 + pairs_host.numel() * 8, "ms_per_step": ims_e2e,
                     "pipeline": "double-buffered H2D on a copy stream, overlapped with the previous step"},
             "gpu_launches": ilaunches,
             "tflops_reference_formulation": world * Ri / ims * 1e3 * FLOP_PER_PAIR / 1e12,
