@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VETO_ABI_VERSION 1
+#define VETO_ABI_VERSION 2   /* 2: veto_train_inputs grew the MEET group-head fields; new entry points */
 
 enum {
     VETO_OK = 0,

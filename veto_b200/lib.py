@@ -139,7 +139,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.veto_abi_version() != 1:
+    if lib.veto_abi_version() != 2:
         raise RuntimeError("libveto_b200.so ABI version mismatch")
     _lib = lib
     return lib
