@@ -388,8 +388,8 @@ def run_detect_sample_case(ns, name, c):
 def run_eval_case(ns, name, c):
     """SGRecall.calculate_recall of the UNMODIFIED reference (sgg_eval.py:138-186) on seeded predictions / ground truth."""
     sys.path.insert(0, ref_shim.REF_ROOT)
-    from pysgg.data.datasets.evaluation.vg.sgg_eval import (SGMeanRecall, SGNoGraphConstraintRecall, SGPairAccuracy, SGRecall,
-                                                             SGZeroShotRecall)
+    from pysgg.data.datasets.evaluation.vg.sgg_eval import (SGMeanRecall, SGNGMeanRecall, SGNoGraphConstraintRecall,
+                                                             SGPairAccuracy, SGRecall, SGZeroShotRecall)
     imgs = synth.make_eval_case(c["seed"], c["n_objs"], c["n_gt_rels"], c["n_pred_rels"])
     result_dict = {}
     ev = SGRecall(result_dict)
@@ -400,6 +400,8 @@ def run_eval_case(ns, name, c):
     ng.register_container("sgdet")
     zs = SGZeroShotRecall(result_dict)
     zs.register_container("sgdet")
+    ngm = SGNGMeanRecall(result_dict, 51, ["__background__"] + [f"rel{i}" for i in range(1, 51)])
+    ngm.register_container("sgdet")
     pa = SGPairAccuracy(result_dict)
     pa.register_container("sgcls")
     # "zero-shot" triplets: (subject class, object class, predicate) of every third ground-truth relation of the case
@@ -425,6 +427,7 @@ def run_eval_case(ns, name, c):
         pa.calculate_recall({"iou_thres": 0.5}, loc2, "sgcls")
         local["obj_scores"] = im["pred_scores"]
         ng.calculate_recall({"iou_thres": 0.5}, local, "sgdet")
+        ngm.collect_mean_recall_items({"iou_thres": 0.5}, local, "sgdet")
         nfirst = np.full(len(im["relation_tuple"]), 2 ** 31 - 1, np.int64)
         for p, gs in enumerate(local["nogc_pred_to_gt"]):
             for g in gs:
@@ -438,8 +441,10 @@ def run_eval_case(ns, name, c):
         out[f"first_match/{i}"] = first
         out[f"pred_hits/{i}"] = np.array([len(g) for g in p2g], np.int64)
     mr.calculate_mean_recall("sgdet")
+    ngm.calculate_mean_recall("sgdet")
     for k in (20, 50, 100):
         out[f"mean_recall/{k}"] = np.array(result_dict["sgdet_mean_recall"][k], np.float64)
+        out[f"ng_mean_recall/{k}"] = np.array(result_dict["sgdet_ng_mean_recall"][k], np.float64)
         out[f"mean_recall_list/{k}"] = np.array(result_dict["sgdet_mean_recall_list"][k], np.float64)
         out[f"recall/{k}"] = np.array(result_dict["sgdet_recall"][k], np.float64)
         out[f"recall_nogc/{k}"] = np.array(result_dict["sgdet_recall_nogc"][k], np.float64)

@@ -410,6 +410,9 @@ def test_recall_evaluation_matches_reference():
     for k in (20, 50, 100):
         assert np.array_equal(np.array(ng["recall"][k]), g[f"recall_nogc/{k}"])
     assert max(ng["recall"][100]) > max(out["recall"][100]) - 1e-9                  # no graph constraint can only help
+    ngm = E.mean_recall(ng["first_match"], out["gt_predicates"], 51)                # SGNGMeanRecall (:470-548)
+    for k in (20, 50, 100):
+        assert abs(ngm["mean_recall"][k] - float(g[f"ng_mean_recall/{k}"])) <= 1e-12
     zs = E.zeroshot_recall(out["first_match"], gts[:2] + [empty] + gts[2:], _t(g["zeroshot_triplets"]))   # SGZeroShotRecall
     pa = E.pair_accuracy(preds, gts, predcls_like=False)                            # SGPairAccuracy (:338-366)
     for k in (20, 50, 100):
