@@ -182,3 +182,65 @@ def test_mean_recall_from_first_match_matches_reference():
     for k in (20, 50, 100):
         assert np.allclose(mr["mean_recall_list"][k], g[f"mean_recall_list/{k}"], rtol=1e-12, atol=0)
         assert abs(mr["mean_recall"][k] - float(g[f"mean_recall/{k}"])) <= 1e-12
+
+
+def test_meet_group_sampling_invariants():
+    """Properties of the host-side MEET group sampling (meet_sampling.py) for random label vectors and every padding
+    mode: a pair joins a PREFIX of the group heads (heads 0..a-1), at least the heads up to one before its own group;
+    rows are listed once per head in ascending order; the label table is -1 exactly off the chosen rows, 0 for
+    background, 1..n_k for members and n_k + 1 for foreign predicates."""
+    import random
+    from hypothesis import given, settings, strategies as st
+    from veto_b200 import meet_sampling as MS
+    from veto_b200.predictor import incre_idx_list
+
+    sizes = vcfg.GROUP_SPLITS[("VG", "divide4")]
+    incre = incre_idx_list(sizes, 51)
+    rates = MS.sample_rate_matrix("VG", sizes)
+    assert rates.shape == (5, 51) and np.all(rates > 0) and np.all(rates <= 1)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(0, 50), min_size=1, max_size=200), st.sampled_from(["rand_insert", "rand_choose", "all_include"]),
+           st.integers(0, 2 ** 31))
+    def check(labels, mode, seed):
+        rng = random.Random(seed)
+        chosen = MS.group_sampling(labels, incre, rates, len(sizes), mode, rng)
+        member = np.zeros((len(sizes), len(labels)), bool)
+        for k, rows in enumerate(chosen):
+            assert rows == sorted(set(rows))
+            member[k, rows] = True
+        for i, p in enumerate(labels):
+            col = member[:, i]
+            if p == 0:
+                assert col.sum() == (1 if mode == "rand_insert" else (0 if (mode == "rand_choose" and not col.any()) else len(sizes)))
+            else:
+                a = int(col.sum())
+                assert col[:a].all() and not col[a:].any()            # a prefix of the heads
+                assert a >= incre[p] - 1                              # at least every head before its own group's
+        table = MS.group_local_labels(labels, chosen, incre)
+        assert table.shape == (len(sizes), len(labels)) and np.array_equal(table >= 0, member)
+        for k in range(len(sizes)):
+            for i, p in enumerate(labels):
+                if member[k, i]:
+                    want = 0 if p == 0 else (p - sum(sizes[:k]) if incre[p] == k + 1 else sizes[k] + 1)
+                    assert table[k, i] == want
+
+    check()
+
+
+def test_image_sharding_is_a_partition():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.integers(0, 120), min_size=0, max_size=64), st.integers(1, 8), st.sampled_from([64, 2048, 1 << 62]))
+    def check(n_boxes, world, cap):
+        shards = vdist.shard_images(n_boxes, world, cap)
+        assert len(shards) == world
+        assert sorted(i for s in shards for i in s) == list(range(len(n_boxes)))
+        assert all(s == sorted(s) for s in shards)
+        loads = [sum(vdist.pair_count(n_boxes[i], cap) for i in s) for s in shards]
+        if n_boxes:
+            biggest = max(vdist.pair_count(n, cap) for n in n_boxes)
+            assert max(loads) <= sum(loads) / world + biggest           # the LPT bound
+
+    check()
