@@ -776,6 +776,63 @@ def test_full_size_sgdet_batch_properties():
     assert np.array_equal(a[sel].argmax(1), ref.argmax(1))
 
 
+def test_relation_head_dropin():
+    """veto_b200.relation_head.ROIRelationHead (relation_head.py:27-248), the caller of the path: at test time it
+    reproduces the golden post-processed output of the reference's own head pipeline from raw proposals (labels only:
+    the head overloads the PredCls fields itself); in training it samples, runs the fused step and back-propagates."""
+    from veto_b200.relation_head import build_roi_relation_head
+    from veto_b200.structures import BoxList
+    name = "cfg1_predcls_vg"
+    c, batch, state, g = CASES[name], case_batch(CASES[name]), case_state(CASES[name]), load_golden(name)
+    cfg = H.make_cfg(precision="bf16x3")
+    head = build_roi_relation_head(cfg, 256)
+    head.predictor.load_state_dict(synth.to_torch_state(state), strict=True)
+    head = head.to(DEV).eval()
+    feats, depth = H.device_features(batch, DEV)
+
+    def raw_proposals():
+        out = []
+        for i in range(batch["B"]):
+            bl = BoxList(_t(batch["boxes"][i]), (batch["W"], batch["H"]), "xyxy")
+            bl.add_field("labels", _t(batch["labels"][i]))
+            out.append(bl)
+        return out
+
+    with torch.no_grad():
+        roi, result, losses = head(feats, raw_proposals(), depth_features=depth)
+    assert losses == {} and tuple(roi.shape) == (sum(batch["n_boxes"]), 256, 8, 8)
+    pp = np.concatenate([H.np_(r.get_field("rel_pair_idxs")) for r in result])
+    labels = np.concatenate([H.np_(r.get_field("pred_rel_labels")) for r in result])
+    scores = np.concatenate([H.np_(r.get_field("pred_rel_scores")) for r in result])[:, 1:].max(1)
+    assert np.allclose(scores, g["post_scores"], rtol=5e-4)
+    s = g["post_scores"].astype(np.float64)
+    gap = np.full(len(s), np.inf)
+    gap[1:] = np.minimum(gap[1:], s[:-1] - s[1:])
+    gap[:-1] = np.minimum(gap[:-1], s[:-1] - s[1:])
+    clear = gap > 2e-3 * s
+    assert np.array_equal(pp[clear], g["post_pairs"][clear]) and np.array_equal(labels[clear], g["post_labels"][clear])
+    # training through the head: sampler -> extractor -> predictor -> losses
+    head.train()
+    props = raw_proposals()
+    mats = synth.make_relation_matrices(3, batch["n_boxes"], 51, 10)
+    targets = []
+    for pbl, m in zip(props, mats):
+        t = BoxList(pbl.bbox, pbl.size, "xyxy")
+        t.add_field("relation", _t(m))
+        targets.append(t)
+    depth_t = depth.clone().requires_grad_(True)
+    roi, props_out, losses = head(feats, props, depth_features=depth_t, targets=targets)
+    assert set(losses) == {"rel_loss"} and props_out[0].has_field("locating_match")
+    losses["rel_loss"].backward()
+    grads = [p.grad for p in head.predictor.parameters() if p.grad is not None]
+    assert len(grads) >= 80 and all(bool(torch.isfinite(gr).all()) for gr in grads) and depth_t.grad is not None
+    assert float(losses["rel_loss"].detach()) > 0
+    with pytest.raises(NotImplementedError):
+        bad = H.make_cfg()
+        bad.MODEL.ROI_RELATION_HEAD.PREDICTOR = "MotifPredictor"
+        build_roi_relation_head(bad, 256)
+
+
 @pytest.mark.parametrize("mode", ["predcls", "sgdet"])
 def test_image_sharding_is_exact(mode):
     """BASELINE.json configs[4] (per-image sharded PredCls + SGDet sweep): images are independent, so running the
