@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("VETO_CPU_SAMPLE_PAIRS", "2048")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the configs[2] inference leg")
+    ap.add_argument("--no-depth-backbone", action="store_true", help="skip the depth-backbone (SURVEY.md §8 f3) leg")
     return ap.parse_args()
 
 
@@ -188,6 +189,29 @@ def cpu_infer_leg(sample_pairs: int, steps: int = 1, warmup: int = 0):
     return 1.0 / per_pair, cores, sample, per_pair
 
 
+def cpu_depth_leg(steps: int = 1, warmup: int = 0):
+    """The depth backbone's training forward + backward on the host cores: oracle/depth_port.py (the reference module IS
+    torchvision's ResNet-18 trunk; restated on torch.nn.functional, gradients by autograd) on ONE 592x800 depth image.
+    Returns (images/s, cores, sample)."""
+    import numpy as np
+    import torch
+    from oracle import depth_port as DP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = DP.synth_state(0)
+    depth = DP.synth_depth(1, IMG_H, IMG_W)
+    g = np.ones((1, 256) + DP.out_size(IMG_H, IMG_W), np.float32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        DP.train_step(sd, depth, g)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = sorted(times)[len(times) // 2]
+    return 1.0 / per, cores, (f"1 depth image 1x{IMG_H}x{IMG_W}: ResNetDepth train() forward + backward, oracle/depth_port.py on "
+                              f"torch CPU fp32 kernels, {cores} threads")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -204,6 +228,9 @@ def run_reference(args):
     if not args.no_inference:
         iv, _, isample, _ = cpu_infer_leg(args.cpu_sample_pairs)
         line["inference"] = {"value": iv, "unit": UNIT, "config": {"workload": INF_WORKLOAD}, "sample": isample}
+    if not args.no_depth_backbone:
+        dv, _, dsample = cpu_depth_leg(steps=2, warmup=1)
+        line["depth_backbone"] = {"value": dv, "unit": "images/s", "sample": dsample}
     line["wall_s"] = time.perf_counter() - t0
     print(json.dumps(line), flush=True)
 
@@ -485,6 +512,38 @@ def main():
     ops._workspaces.clear()
     torch.cuda.empty_cache()
 
+    # =============================================================================== f3: the depth backbone
+    depth_leg = None
+    if not args.no_depth_backbone:
+        from oracle import depth_port as DP          # synthetic state / image generators only (numpy)
+        from veto_b200 import depth_backbone as DB
+        dmodel = DB.build_resnet18_depth(cfg).to(dev).train()
+        dmodel.load_state_dict({k: torch.from_numpy(v) for k, v in DP.synth_state(0).items()})
+        dimg = torch.from_numpy(DP.synth_depth(B, IMG_H, IMG_W, seed=rank)).to(dev)
+        dgrad = torch.randn((B, 256) + ops.depth_backbone_out_size(IMG_H, IMG_W), generator=g, device=dev)
+
+        def depth_fwd():
+            with torch.no_grad():
+                dmodel(dimg)
+
+        def depth_step():
+            dmodel(dimg).backward(dgrad)
+
+        d_fwd_ms, _ = timed(depth_fwd, max(3, args.steps // 2), 2)
+        d_ms, _ = timed(depth_step, max(3, args.steps // 2), 2)
+        ws_gb = L.load().veto_depth_backbone_workspace_bytes(L.PRECISIONS[args.precision], B, IMG_H, IMG_W, 1) / 1e9
+        dcpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_depth_leg(steps=2, warmup=1)
+            dcpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        depth_leg = {"metric": "depth_images_per_sec", "value": world * B / d_ms * 1e3, "unit": "images/s",
+                     "ms_fwd_bwd": d_ms, "ms_fwd": d_fwd_ms,
+                     "config": {"workload": f"SURVEY.md §8 f3: ResNetDepth (R-18-C4) train() forward + backward, {B} depth images "
+                                            f"1x{IMG_H}x{IMG_W} per GPU -> [B,256,H/16,W/16]", "precision": args.precision},
+                     "workspace_gb": round(ws_gb, 2), "cpu_baseline": dcpu}
+        del dmodel, dimg, dgrad
+        torch.cuda.empty_cache()
+
     # =============================================================================== configs[2]: inference
     inference = None
     if not args.no_inference:
@@ -602,7 +661,7 @@ def main():
                     "pipeline": "double-buffered: the H2D copy of step k+1 (copy stream) overlaps the training of step k"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "hbm_peak_gbs": hbm_peak,
             "hbm_kernels": train_hbm,
-            "cpu_baseline": cpu, "inference": inference,
+            "cpu_baseline": cpu, "inference": inference, "depth_backbone": depth_leg,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VETO_ABI_VERSION 2   /* 2: veto_train_inputs grew the MEET group-head fields; new entry points */
+#define VETO_ABI_VERSION 3   /* 2: veto_train_inputs grew the MEET group-head fields; 3: depth backbone entry points */
 
 enum {
     VETO_OK = 0,
@@ -406,6 +406,44 @@ int veto_postprocess_meet_vote(const float* group_logits_dev, int num_out, const
 int veto_obj_nms_per_cls(const float* scores_dev, const float* boxes_per_cls_dev, const int32_t* box_offsets_dev,
                          const int32_t* n_boxes_host, int n_images, int num_obj, float thresh, int late_nms,
                          int64_t* labels_out_dev, veto_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f3. The depth backbone (registry "R-18-C4": pysgg/modeling/backbone/backbone.py:83-93 building
+ * ResNetDepth, pysgg/modeling/backbone/resnet_depth.py:11-47 — torchvision's ResNet-18 with a one-channel first
+ * convolution, truncated after layer3), the producer of `depth_features` (detector/generalized_rcnn.py:53-54) and the
+ * one other module relation_train_net.py:166-170 trains: forward in eval() or train() mode (BatchNorm2d on batch
+ * statistics, running statistics updated in place) and the backward pass from the gradient of its output.
+ *
+ * The 15 convolutions in module order, each followed by its BatchNorm2d:
+ *   0 conv1 (1->64, 7x7 s2 p3) | layer1: 1,2 = block 0 conv1,conv2; 3,4 = block 1 | layer2: 5,6 = block 0 conv1 (s2),
+ *   conv2; 7 = block 0 downsample (1x1 s2); 8,9 = block 1 | layer3: 10,11,12 and 13,14 likewise.
+ * Convolutions run as an NHWC im2col into the operand format of the precision mode followed by the library's GEMMs
+ * (forward: tcgen05 bf16 / bf16x3 or fp32 SIMT; weight gradients on the MN-major tcgen05 GEMM). */
+#define VETO_DEPTH_CONVS 15
+typedef struct {
+    const float* conv_w[VETO_DEPTH_CONVS];   /* [Cout,Cin,k,k] as nn.Conv2d holds them */
+    const float* bn_w[VETO_DEPTH_CONVS];     /* [Cout] */
+    const float* bn_b[VETO_DEPTH_CONVS];
+    float* bn_mean[VETO_DEPTH_CONVS];        /* running_mean / running_var: read in eval mode, updated in training */
+    float* bn_var[VETO_DEPTH_CONVS];
+} veto_depth_weights;
+typedef struct {
+    float* conv_w[VETO_DEPTH_CONVS];         /* overwritten (not accumulated) */
+    float* bn_w[VETO_DEPTH_CONVS];
+    float* bn_b[VETO_DEPTH_CONVS];
+} veto_depth_grads;
+/* output spatial size for an input of height x width (the stride-16 map) */
+void veto_depth_backbone_out_size(int height, int width, int* out_h, int* out_w);
+size_t veto_depth_backbone_workspace_bytes(int precision, int batch, int height, int width, int training);
+/* depth_dev [B,1,H,W] fp32 -> out_dev [B,256,H/16,W/16] fp32 NCHW (what the Pooler reads).  training != 0: batch
+ * statistics with `momentum` (nn.BatchNorm2d default 0.1), eps 1e-5, and the workspace keeps what the backward needs. */
+int veto_depth_backbone_forward(int precision, const veto_depth_weights* w, const float* depth_dev, int batch, int height,
+                                int width, int training, float momentum, float* out_dev, void* workspace_dev,
+                                size_t workspace_bytes, veto_stream_t stream);
+/* backward of the last training-mode forward that used this workspace: grad_out_dev [B,256,H/16,W/16] NCHW -> g */
+int veto_depth_backbone_backward(int precision, const veto_depth_weights* w, const float* grad_out_dev, int batch,
+                                 int height, int width, const veto_depth_grads* g, void* workspace_dev,
+                                 size_t workspace_bytes, veto_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): one GEMM  C[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual)

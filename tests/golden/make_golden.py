@@ -463,6 +463,45 @@ def run_eval_case(ns, name, c):
     print(f"{name}: wrote {path}", {k: out[f'recall/{k}'].round(3).tolist() for k in (20, 50, 100)})
 
 
+def run_depth_backbone(name="depth_backbone", batch=2, height=70, width=101):
+    """The UNMODIFIED reference depth backbone (backbone.py:83-93 build_resnet18_depth -> ResNetDepth) on a synthetic
+    depth batch: eval-mode output, then one training-mode forward + backward from a fixed output gradient (parameter
+    gradients summarised, updated running statistics).  Weights come from oracle.depth_port.synth_state (numpy RNG), so
+    the fixture needs to hold no weights."""
+    import importlib
+    import torch
+    import torchvision.models.resnet as tvr
+    from oracle import depth_port
+    if not hasattr(tvr, "model_urls"):          # removed from torchvision 0.13+; resnet_depth.py:5 imports the name
+        tvr.model_urls = {}
+    bb = importlib.import_module("pysgg.modeling.backbone.backbone")
+    torch.manual_seed(0)
+    model = bb.build_resnet18_depth(None, True)
+    keys = list(model.state_dict().keys())
+    sd = depth_port.synth_state(0)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    depth = depth_port.synth_depth(batch, height, width)
+    out = {"keys": np.array(keys), "out_channels": np.array(model.out_channels), "shape": np.array(depth.shape),
+           "input_digest": np.array(digest([depth])), "weight_digest": np.array(digest([sd[k] for k in sorted(sd)]))}
+    model.eval()
+    with torch.no_grad():
+        out["eval_out"] = model(torch.from_numpy(depth)).numpy()
+    model.train()
+    y = model(torch.from_numpy(depth))
+    g = np.random.RandomState(5).standard_normal(tuple(y.shape)).astype(np.float32)
+    y.backward(torch.from_numpy(g))
+    out["train_out"] = y.detach().numpy()
+    out["grad_out_digest"] = np.array(digest([g]))
+    for k, p_ in model.named_parameters():
+        stat, idx, val = grad_summary(p_.grad.numpy())
+        out["gstat/" + k], out["gidx/" + k], out["gval/" + k] = stat, idx, val
+    for k, b in model.named_buffers():
+        out["buf/" + k] = b.numpy().copy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KB) out {tuple(y.shape)}")
+
+
 def main():
     from tests.cases import DETECT_SAMPLE_CASES, EVAL_CASES, MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
     ns = ref_shim.load()
@@ -493,6 +532,8 @@ def main():
         run_eval_case(ns, name, c)
     if not only or "meet_sample_rates" in only:
         run_sample_rates()
+    if not only or "depth_backbone" in only:
+        run_depth_backbone()
 
 
 if __name__ == "__main__":

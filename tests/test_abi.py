@@ -43,7 +43,7 @@ def test_library_is_native_sm100a_code():
 
 
 def test_host_only_entry_points(lib):
-    assert lib.veto_abi_version() == 2
+    assert lib.veto_abi_version() == 3
     n = (ctypes.c_int32 * 4)(0, 1, 20, 80)
     total = ctypes.c_int64(0)
     assert lib.veto_pairs_capacity(n, 4, 2048, ctypes.byref(total)) == 0
@@ -59,6 +59,12 @@ def test_host_only_entry_points(lib):
     assert 0 < small < big < 2e9          # the workspace scales with N and the chunk, not with R
     bad = ops.make_config(151, 51, "fp32", heads=8)
     assert lib.veto_workspace_bytes(ctypes.byref(bad), 20, 380, 0) == 0
+    # depth backbone: stride-16 output size with torch's floor rule, workspace grows with training (saved im2col)
+    assert ops.depth_backbone_out_size(608, 1008) == (38, 63) and ops.depth_backbone_out_size(70, 101) == (5, 7)
+    ev = lib.veto_depth_backbone_workspace_bytes(1, 12, 608, 1008, 0)
+    tr = lib.veto_depth_backbone_workspace_bytes(1, 12, 608, 1008, 1)
+    assert 0 < ev < tr < 40e9
+    assert lib.veto_depth_backbone_workspace_bytes(1, 1, 8, 8, 0) == 0 and b"16 x 16" in lib.veto_last_error()
 
 
 def test_no_gpu_means_loud_failure():

@@ -45,7 +45,7 @@ def test_gemm_simt(shape):
 
 @pytest.mark.parametrize("precision,tol", [("bf16", 5e-6), ("bf16x3", 3e-5)])
 @pytest.mark.parametrize("shape", [(128, 192, 64), (100, 128, 64), (333, 576, 1152), (1000, 1728, 576), (320, 1024, 1024),
-                                   (320, 128, 1024), (19456, 576, 576)])
+                                   (320, 128, 1024), (19456, 576, 576), (700, 64, 576), (1000, 64, 64), (900, 576, 64)])
 def test_gemm_tcgen05(shape, precision, tol):
     """tcgen05/TMEM GEMM.  bf16: exact up to fp32 accumulation against the product of the bf16-rounded operands;
     bf16x3: fp32-grade against the fp64 product of the fp32 operands."""

@@ -16,5 +16,5 @@ __version__ = "0.1.0"
 
 def load_modules():
     """Import the drop-in modules (registers them) and return the registries."""
-    from . import feature_extractor, postprocess, predictor, relation_head, sampling  # noqa: F401
+    from . import depth_backbone, feature_extractor, postprocess, predictor, relation_head, sampling  # noqa: F401
     return registry.ROI_RELATION_PREDICTOR, registry.ROI_BOX_FEATURE_EXTRACTORS

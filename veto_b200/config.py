@@ -50,6 +50,7 @@ class CfgNode(dict):
 _DEFAULTS = {
     "MODEL": {
         "DEVICE": "cuda",
+        "DEPTH_BACKBONE": {"CONV_BODY": "R-18-C4"},             # defaults.py:117-123
         "ROI_BOX_HEAD": {
             "POOLER_RESOLUTION": 7,
             "POOLER_SCALES": (0.25, 0.125, 0.0625, 0.03125),   # VETO_final.yaml:39

@@ -61,6 +61,17 @@ class VetoTrainOutputs(Structure):
     _fields_ = [("loss", c_void_p), ("rel_logits", c_void_p), ("grad_roi_depth", c_void_p), ("grad_roi_rgb", c_void_p)]
 
 
+DEPTH_CONVS = 15
+
+
+class VetoDepthWeights(Structure):
+    _fields_ = [(n, c_void_p * DEPTH_CONVS) for n in ("conv_w", "bn_w", "bn_b", "bn_mean", "bn_var")]
+
+
+class VetoDepthGrads(Structure):
+    _fields_ = [(n, c_void_p * DEPTH_CONVS) for n in ("conv_w", "bn_w", "bn_b")]
+
+
 class VetoError(RuntimeError):
     """A negative return code from libveto_b200 (the reference raises RuntimeError from AT_ERROR)."""
 
@@ -103,6 +114,12 @@ _PROTOS = {
     "veto_postprocess_meet_vote": (c_int, [_fp, c_int, _fp, c_int, _fp, c_int, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp,
                                            _fp, _fp, _fp, c_void_p]),
     "veto_obj_nms_per_cls": (c_int, [_fp, _fp, _fp, POINTER(c_int32), c_int, c_int, c_float, c_int, _fp, c_void_p]),
+    "veto_depth_backbone_out_size": (None, [c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "veto_depth_backbone_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "veto_depth_backbone_forward": (c_int, [c_int, POINTER(VetoDepthWeights), _fp, c_int, c_int, c_int, c_int, c_float, _fp,
+                                            _fp, c_size_t, c_void_p]),
+    "veto_depth_backbone_backward": (c_int, [c_int, POINTER(VetoDepthWeights), _fp, c_int, c_int, c_int,
+                                             POINTER(VetoDepthGrads), _fp, c_size_t, c_void_p]),
     "veto_test_gemm": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, c_size_t, c_void_p]),
     "veto_test_gemm_tn": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, POINTER(ctypes.c_uint32), _fp, c_size_t,
                                   c_void_p]),
@@ -139,7 +156,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.veto_abi_version() != 2:
+    if lib.veto_abi_version() != 3:
         raise RuntimeError("libveto_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -636,6 +636,83 @@ def sgg_match(gt_triplets: torch.Tensor, gt_boxes: torch.Tensor, gt_counts: Sequ
 
 
 # --------------------------------------------------------------------------------------------
+# f3: the depth backbone (ResNetDepth, backbone/resnet_depth.py:11-47)
+# --------------------------------------------------------------------------------------------
+def depth_backbone_out_size(height: int, width: int):
+    h, w = ctypes.c_int(0), ctypes.c_int(0)
+    L.load().veto_depth_backbone_out_size(int(height), int(width), ctypes.byref(h), ctypes.byref(w))
+    return h.value, w.value
+
+
+def _depth_weight_struct(convs, bn_w, bn_b, bn_mean, bn_var):
+    W = L.VetoDepthWeights()
+    for i in range(L.DEPTH_CONVS):
+        W.conv_w[i], W.bn_w[i], W.bn_b[i] = convs[i].data_ptr(), bn_w[i].data_ptr(), bn_b[i].data_ptr()
+        W.bn_mean[i], W.bn_var[i] = bn_mean[i].data_ptr(), bn_var[i].data_ptr()
+    return W
+
+
+def depth_backbone_forward(depth: torch.Tensor, convs, bn_w, bn_b, bn_mean, bn_var, training: bool, momentum: float = 0.1,
+                           precision: str = "bf16x3"):
+    """ResNetDepth.forward: depth [B,1,H,W] -> [B,256,H/16,W/16] (NCHW).  The parameter lists are in the module order
+    of include/veto_b200.h (15 convolutions, each with its BatchNorm2d); in training mode the running statistics are
+    updated in place and the returned workspace holds what ``depth_backbone_backward`` needs."""
+    L.require_device()
+    depth = _cuda_f32(depth)
+    if depth.dim() != 4 or depth.shape[1] != 1:
+        raise RuntimeError("depth images must be [B,1,H,W]")
+    if len(convs) != L.DEPTH_CONVS:
+        raise RuntimeError("the depth backbone has %d convolutions" % L.DEPTH_CONVS)
+    B, _, H, W_ = depth.shape
+    prec = L.PRECISIONS[precision]
+    lib = L.load()
+    nbytes = lib.veto_depth_backbone_workspace_bytes(prec, B, H, W_, int(training))
+    if nbytes == 0:
+        L.check(-1, "veto_depth_backbone_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=depth.device)
+    oh, ow = depth_backbone_out_size(H, W_)
+    out = torch.empty(B, 256, oh, ow, dtype=torch.float32, device=depth.device)
+    tensors = [[_cuda_f32(t) for t in group] for group in (convs, bn_w, bn_b)]
+    for group in (bn_mean, bn_var):      # updated in place: must already be contiguous fp32 on the device
+        for t in group:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("BatchNorm running statistics must be contiguous fp32 CUDA tensors")
+    Wst = _depth_weight_struct(tensors[0], tensors[1], tensors[2], bn_mean, bn_var)
+    with torch.cuda.device(depth.device):
+        L.check(lib.veto_depth_backbone_forward(prec, ctypes.byref(Wst), depth.data_ptr(), B, H, W_, int(training),
+                                                float(momentum), out.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr()),
+                "veto_depth_backbone_forward")
+    return out, ws
+
+
+def depth_backbone_backward(grad_out: torch.Tensor, depth_shape, convs, bn_w, bn_b, bn_mean, bn_var, ws: torch.Tensor,
+                            precision: str = "bf16x3"):
+    """Backward of the training-mode forward that filled ``ws``: returns (flat gradient buffer, [conv_w grads],
+    [bn weight grads], [bn bias grads]) — views into the one flat buffer, in module order."""
+    L.require_device()
+    grad_out = _cuda_f32(grad_out)
+    B, _, H, W_ = depth_shape
+    sizes = [t.numel() for t in convs] + [t.numel() for t in bn_w] + [t.numel() for t in bn_b]
+    padded = [(n + 63) // 64 * 64 for n in sizes]
+    flat = torch.empty(sum(padded), dtype=torch.float32, device=grad_out.device)
+    views, o = [], 0
+    for n, pn, t in zip(sizes, padded, list(convs) + list(bn_w) + list(bn_b)):
+        views.append(flat[o:o + n].view(t.shape))
+        o += pn
+    n = L.DEPTH_CONVS
+    G = L.VetoDepthGrads()
+    for i in range(n):
+        G.conv_w[i], G.bn_w[i], G.bn_b[i] = views[i].data_ptr(), views[n + i].data_ptr(), views[2 * n + i].data_ptr()
+    tensors = [[_cuda_f32(t) for t in group] for group in (convs, bn_w, bn_b)]
+    Wst = _depth_weight_struct(tensors[0], tensors[1], tensors[2], bn_mean, bn_var)
+    with torch.cuda.device(grad_out.device):
+        L.check(L.load().veto_depth_backbone_backward(L.PRECISIONS[precision], ctypes.byref(Wst), grad_out.data_ptr(), B, H, W_,
+                                                      ctypes.byref(G), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                "veto_depth_backbone_backward")
+    return flat, views[:n], views[n:2 * n], views[2 * n:]
+
+
+# --------------------------------------------------------------------------------------------
 # launch accounting / per-stage device timing (bench.py)
 # --------------------------------------------------------------------------------------------
 def launch_count() -> int:

@@ -1,7 +1,8 @@
 """Plugin registries with the reference's names (pysgg/modeling/registry.py, pysgg/utils/registry.py:4-45).
 
 ``ROI_RELATION_PREDICTOR["VETOPredictor" | "VETOPredictor_MEET"]`` and
-``ROI_BOX_FEATURE_EXTRACTORS["VETOFeatureExtractor"]`` resolve to the B200 drop-ins.  With the reference
+``ROI_BOX_FEATURE_EXTRACTORS["VETOFeatureExtractor"]`` and ``BACKBONES["R-18-C4"]`` (the depth backbone) resolve to the
+B200 drop-ins.  With the reference
 importable, ``install_into_reference()`` replaces the entries of pysgg's own registries, so that
 ``cfg.MODEL.ROI_RELATION_HEAD.PREDICTOR`` selects them unchanged
 (roi_relation_predictors.py:4152-4154; roi_box_feature_extractors.py:315-323).
@@ -28,6 +29,7 @@ class Registry(dict):
 
 ROI_RELATION_PREDICTOR = Registry()
 ROI_BOX_FEATURE_EXTRACTORS = Registry()
+BACKBONES = Registry()          # "R-18-C4": the depth backbone (backbone/backbone.py:83-93)
 
 
 def install_into_reference() -> bool:
@@ -39,11 +41,13 @@ def install_into_reference() -> bool:
         from pysgg.modeling import registry as ref_registry
     except Exception:
         return False
-    from . import feature_extractor, predictor  # noqa: F401  (registers into the local registries)
+    from . import depth_backbone, feature_extractor, predictor  # noqa: F401  (registers into the local registries)
     for name, cls in ROI_RELATION_PREDICTOR.items():
         ref_registry.ROI_RELATION_PREDICTOR[name] = cls
     for name, cls in ROI_BOX_FEATURE_EXTRACTORS.items():
         ref_registry.ROI_BOX_FEATURE_EXTRACTORS[name] = cls
+    for name, fn in BACKBONES.items():
+        ref_registry.BACKBONES[name] = fn
     return True
 
 
