@@ -198,6 +198,10 @@ int gemm_simt_slices(int K, int split_k);  // K slices an ep.split_k request rea
 int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
             const GemmEpilogue& ep, cudaStream_t s);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
+// Implicit-GEMM stride-1 ks x ks convolution on the same kernel: A = NHWC bf16 hi[/lo] activation [B,H,W,Cin] (Cin % 64 == 0),
+// W = [N, ks*ks*Cin] with column (kh*ks + kw)*Cin + c; out[(b*H + h)*W + w, 0..N) fp32 with row stride ldc (gemm_tc.cu).
+int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
+            float* out, int ldc, cudaStream_t s);
 // CTA-pair (cta_group::2) version, 256 x 192 tiles; needs N % 192 == 0 (gemm_tc2.cu)
 bool gemm_tc2_supported(int N, int K);
 int gemm_tc2_slices(int K, int split_k);  // K slices a GemmEpilogue::split_k request really produces

@@ -1,11 +1,16 @@
 // f3: the depth backbone — ResNetDepth (pysgg/modeling/backbone/resnet_depth.py:11-47: torchvision ResNet-18 with a
 // one-channel conv1, truncated after layer3; built by backbone.py:83-93) forward in eval()/train() mode and backward.
 //
-// Activations live in HBM as NHWC fp32 ([B*H*W, C] row-major = the GEMM's row-major M x N), so a convolution is
-//   im2col (NHWC -> [M, k*k*Cin] in the operand format of the precision mode; kept for the weight gradient)
-//   -> the library's GEMM against the weights repacked as [Cout, k*k*Cin]                     (forward)
-//   -> dcol = dY @ Wp, gathered back to NHWC by col2im (no atomics: every input pixel sums its taps)   (input gradient)
-//   -> dWp = dY^T @ col on the MN-major tcgen05 GEMM, both operands read in place                     (weight gradient)
+// Activations live in HBM as NHWC fp32 ([B*H*W, C] row-major = the GEMM's row-major M x N) plus, in the tensor-core
+// modes, a bf16 hi/lo copy that is the A operand of the next convolution.
+//   * the 11 stride-1 3x3 convolutions: implicit GEMM (conv_tc, gemm_tc.cu) — an output tile is an 8 x 16 pixel patch,
+//     the A tile of a (tap, 64-channel block) one 4-D TMA box of the activation at the tap's offset, zero fill = padding;
+//     their input gradient is the same kernel over d(output) with the flipped, transposed weights
+//   * conv1, the strided 3x3 and the 1x1 stride-2 convolutions (and everything in fp32 mode): im2col into the operand
+//     format -> the library GEMM against the weights repacked as [Cout, k*k*Cin]; input gradient dcol = dY @ Wp gathered
+//     back to NHWC by col2im (no atomics: every input pixel sums its taps)
+//   * weight gradients: dWp = dY^T @ col on the MN-major tcgen05 GEMM, both operands read in place, the im2col re-derived
+//     from the saved input right before it (one shared buffer)
 // BatchNorm2d on batch statistics is a two-stage column reduction over the [M, C] rows (fp32 partials per block, fp64
 // finalise in a fixed order: deterministic) and a fused normalise + residual + ReLU pass; its backward is the same
 // shape (two column sums, one elementwise pass that emits d(conv output) directly in the GEMM operand format).
@@ -17,7 +22,7 @@ namespace veto {
 namespace {
 
 constexpr int kConvs = VETO_DEPTH_CONVS;
-constexpr int kMaxSplit = 16;
+constexpr int kMaxSplit = 64;    // weight-gradient K slices: Cout = 64 gives few output tiles, the rows are many
 constexpr float kBnEps = 1e-5f;
 constexpr int kBnMaxBlocks = 592;   // 4 per SM
 
@@ -48,9 +53,10 @@ struct ConvDims {
 struct DepthLayout {
     ConvDims d[kConvs];
     int hp, wp;  // after the max-pool
-    size_t col[kConvs], raw[kConvs], y[kConvs], stat[kConvs];  // stat: mean[C], rstd[C]
-    size_t wp_[kConvs], wpT[kConvs];
-    size_t pool, pool_arg, bn_partial, bn_sums;
+    size_t col[kConvs], raw[kConvs], y[kConvs], yop[kConvs], stat[kConvs];  // stat: mean[C], rstd[C]; yop: y as GEMM operand
+    size_t wp_[kConvs], wpT[kConvs];  // wpT: [Kp,Cout] transpose, or for the implicit convolutions the flipped [Cin, 9*Cout]
+    int src[kConvs];                  // which tensor feeds conv i: -2 the depth image, -1 the max-pool output, else y[src]
+    size_t pool, pool_op, pool_arg, bn_partial, bn_sums;
     size_t dcol, gA, gB, gC, dyop, dwp, splitk, T1, T2;
     size_t total;
 };
@@ -71,13 +77,21 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
         d.M = (int64_t)B * d.hout * d.wout;
     };
     set(0, h, w);
+    L.src[0] = -2;
     L.hp = out_dim(L.d[0].hout, 3, 2, 1);
     L.wp = out_dim(L.d[0].wout, 3, 2, 1);
     h = L.hp; w = L.wp;
+    int prev = -1;
     for (const BlockSpec& b : kBlocks) {
         set(b.c1, h, w);
-        if (b.ds >= 0) set(b.ds, h, w);
+        L.src[b.c1] = prev;
+        if (b.ds >= 0) {
+            set(b.ds, h, w);
+            L.src[b.ds] = prev;
+        }
         set(b.c2, L.d[b.c1].hout, L.d[b.c1].wout);
+        L.src[b.c2] = b.c1;
+        prev = b.c2;
         h = L.d[b.c2].hout; w = L.d[b.c2].wout;
     }
     size_t col_max = 0, act_max = 0, yop_max = 0, w_max = 0;
@@ -89,20 +103,25 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
         yop_max = max_sz(yop_max, M * kSpec[i].cout);
         w_max = max_sz(w_max, (size_t)kSpec[i].cout * d.Kp);
     }
-    size_t shared_col = 0;
-    if (!training) shared_col = k.take(act_bytes(prec, col_max));
+    // One im2col buffer serves every convolution that needs one (forward: the strided / first / fp32-mode ones; backward:
+    // re-derived from the saved input right before each weight gradient).  Only conv1 keeps its own: its input, the
+    // depth image, is not available to the backward call.
+    const size_t shared_col = k.take(act_bytes(prec, col_max));
+    const bool ops = prec != VETO_PREC_FP32;
     for (int i = 0; i < kConvs; ++i) {
         const ConvDims& d = L.d[i];
         const size_t M = (size_t)(d.M > 0 ? d.M : 1);
         const int C = kSpec[i].cout;
-        L.col[i] = training ? k.take(act_bytes(prec, M * d.Kp)) : shared_col;
+        L.col[i] = (training && i == 0) ? k.take(act_bytes(prec, M * d.Kp)) : shared_col;
         L.raw[i] = k.take(f * M * C);
         L.y[i] = k.take(f * M * C);
+        L.yop[i] = ops ? k.take(act_bytes(prec, M * C)) : 0;
         L.stat[i] = k.take(f * 2 * C);
         L.wp_[i] = k.take(act_bytes(prec, (size_t)C * d.Kp));
         L.wpT[i] = training ? k.take(act_bytes(prec, (size_t)C * d.Kp)) : 0;
     }
     L.pool = k.take(f * (size_t)B * L.hp * L.wp * 64);
+    L.pool_op = ops ? k.take(act_bytes(prec, (size_t)B * L.hp * L.wp * 64)) : 0;
     L.pool_arg = k.take(training ? (size_t)B * L.hp * L.wp * 64 : 0);
     L.bn_partial = k.take(f * (size_t)kBnMaxBlocks * 2 * 256);
     L.bn_sums = k.take(f * 2 * 256);
@@ -297,23 +316,26 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
     }
 }
 
-// Sum of the per-block partials of one column in fp64, in a fixed order: 256 threads = 32 columns x 8 lanes, lane l
-// takes blocks l, l + 8, ...; the 8 lane sums are combined in lane order.  Returns the totals to the lane-0 threads.
+// Sum of the per-block partials of one column in fp64, in a fixed order: 1024 threads = 32 columns x 32 lanes, lane l
+// takes blocks l, l + 32, ...; the 32 lane sums are combined in lane order.  Returns the totals to the lane-0 threads.
+constexpr int kFinLanes = 32;
 __device__ __forceinline__ bool reduce_partials(const float* __restrict__ partial, int blocks, int C, int c, int lane,
                                                 double& s, double& q) {
-    __shared__ double sh[2][8][32];
+    __shared__ double sh[2][kFinLanes][32];
     s = 0.0;
     q = 0.0;
-    if (c < C)
-        for (int b = lane; b < blocks; b += 8) {
-            s += (double)partial[(size_t)b * 2 * C + c];
-            q += (double)partial[(size_t)b * 2 * C + C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int b = lane; b < blocks; b += kFinLanes) {
+            s += (double)__ldg(partial + (size_t)b * 2 * C + c);
+            q += (double)__ldg(partial + (size_t)b * 2 * C + C + c);
         }
+    }
     sh[0][lane][threadIdx.x & 31] = s;
     sh[1][lane][threadIdx.x & 31] = q;
     __syncthreads();
     if (lane != 0 || c >= C) return false;
-    for (int l = 1; l < 8; ++l) {
+    for (int l = 1; l < kFinLanes; ++l) {
         s += sh[0][l][threadIdx.x & 31];
         q += sh[1][l][threadIdx.x & 31];
     }
@@ -321,7 +343,7 @@ __device__ __forceinline__ bool reduce_partials(const float* __restrict__ partia
 }
 
 // forward: mean / rstd from the partial sums (fp64, fixed order), running statistics as nn.BatchNorm2d updates them
-__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int blocks, int C, int64_t M,
+__global__ void __launch_bounds__(1024) bn_stats_finalize_kernel(const float* __restrict__ partial, int blocks, int C, int64_t M,
                                                                 float momentum, float* stat, float* running_mean,
                                                                 float* running_var) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -345,7 +367,7 @@ __global__ void bn_stats_eval_kernel(const float* __restrict__ running_mean, con
     stat[C + c] = 1.f / sqrtf(running_var[c] + kBnEps);
 }
 // backward: sums[0..C) = sum dz = g_beta, sums[C..2C) = sum dz * xhat = g_gamma
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, float* sums,
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, float* sums,
                                                               float* g_gamma, float* g_beta) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
@@ -356,10 +378,11 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     g_gamma[c] = (float)q;
 }
 
-// y = [relu]((x - mean) * rstd * gamma + beta [+ residual]); optionally also out_nchw[b, c, h*w]
+// y = [relu]((x - mean) * rstd * gamma + beta [+ residual]); optionally also out_nchw[b, c, h*w] and yop = y as bf16 hi[/lo]
+// (the A operand of the implicit-GEMM convolution that consumes it)
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ residual, int relu, int C, int64_t M,
-                                int64_t hw, float* __restrict__ y, float* __restrict__ out_nchw) {
+                                int64_t hw, float* __restrict__ y, float* __restrict__ out_nchw, ActOut yop) {
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * groups) return;
@@ -383,6 +406,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
     reinterpret_cast<float4*>(y)[idx] = o;
+    if (yop.hi) store4(yop, (size_t)idx * 4, o);
     if (out_nchw) {
         const int64_t b = m / hw, pix = m - b * hw;
         float* dst = out_nchw + ((size_t)b * C + 4 * g) * hw + pix;
@@ -422,7 +446,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
 // nn.MaxPool2d(3, 2, 1) on NHWC, 4 channels per thread.  arg (training) records which tap (kh * 3 + kw) holds the FIRST
 // maximum in scan order — torch's `val > maxval` update rule; after a ReLU whole windows tie at zero.
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int hin, int win, int C, int hout, int wout, int64_t out_pixels,
-                                   float* __restrict__ y, uchar4* __restrict__ arg) {
+                                   float* __restrict__ y, uchar4* __restrict__ arg, ActOut yop) {
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= out_pixels * groups) return;
@@ -449,6 +473,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int hin, int win
         }
     }
     reinterpret_cast<float4*>(y)[idx] = m;
+    if (yop.hi) store4(yop, (size_t)idx * 4, m);
     if (arg) arg[idx] = a;
 }
 
@@ -503,6 +528,33 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
     put(wp, (size_t)idx);
     put(wpT, (size_t)kk * cout + o);
 }
+// conv weight [Cout,Cin,k,k] -> Wf [Cin, k*k*Cout] with column (kh'*k + kw')*Cout + o holding w[o, c, k-1-kh', k-1-kw']:
+// the weights of the stride-1 convolution over d(output) that gives d(input)
+__global__ void pack_conv_flipped_kernel(const float* __restrict__ w, int cout, int cin, int ks, ActOut wf) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kk2 = ks * ks, Kf = kk2 * cout;
+    if (idx >= cin * Kf) return;
+    const int c = idx / Kf, r = idx - c * Kf;
+    const int tap = r / cout, o = r - tap * cout;
+    const float v = w[((size_t)o * cin + c) * kk2 + (kk2 - 1 - tap)];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    wf.hi[idx] = hi;
+    if (wf.lo) wf.lo[idx] = lo;
+}
+// dx += add where mask > 0 (the identity branch of a BasicBlock through the block's ReLU)
+__global__ void add_masked_kernel(float* __restrict__ dx, const float* __restrict__ add, const float* __restrict__ mask, int64_t n4) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n4) return;
+    float4 v = reinterpret_cast<float4*>(dx)[idx];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(add) + idx);
+    const float4 mk = __ldg(reinterpret_cast<const float4*>(mask) + idx);
+    v.x += mk.x > 0.f ? a.x : 0.f;
+    v.y += mk.y > 0.f ? a.y : 0.f;
+    v.z += mk.z > 0.f ? a.z : 0.f;
+    v.w += mk.w > 0.f ? a.w : 0.f;
+    reinterpret_cast<float4*>(dx)[idx] = v;
+}
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ gp, int cout, int cin, int ks, int Kp, float* __restrict__ g) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int kk2 = ks * ks;
@@ -542,34 +594,72 @@ struct Run {
     ActBuf wp(int i) const { return act(L->wp_[i], (size_t)kSpec[i].cout * L->d[i].Kp); }
     ActBuf wpT(int i) const { return act(L->wpT[i], (size_t)kSpec[i].cout * L->d[i].Kp); }
 
+    // stride-1 3x3 convolutions on >= 64 channels run as implicit GEMMs (conv_tc: 4-D TMA boxes of the NHWC activation,
+    // nothing materialised) in the tensor-core modes; conv1, the three strided 3x3 and the two 1x1 stride-2 convolutions
+    // go through im2col.  VETO_DEPTH_IM2COL=1 forces im2col everywhere (debugging).
+    bool implicit(int i) const {
+        static const bool off = [] { const char* e = getenv("VETO_DEPTH_IM2COL"); return e && e[0] == '1'; }();
+        const ConvSpec& c = kSpec[i];
+        return !off && prec != VETO_PREC_FP32 && c.stride == 1 && c.k == 3 && c.cin % 64 == 0;
+    }
+    int passes() const { return prec == VETO_PREC_BF16X3 ? 3 : 1; }
+    const float* src_f32(int i, const float* depth) const {
+        const int src = L->src[i];
+        return src == -2 ? depth : src == -1 ? f32(L->pool) : f32(L->y[src]);
+    }
+    ActBuf src_op(int i) const {
+        const int src = L->src[i];
+        if (src == -1) return act(L->pool_op, (size_t)batch * L->hp * L->wp * 64);
+        return act(L->yop[src], (size_t)L->d[src].M * kSpec[src].cout);
+    }
+    ActOut yop_out(int i) const { return prec != VETO_PREC_FP32 ? act(L->yop[i], (size_t)L->d[i].M * kSpec[i].cout).out() : ActOut(); }
+
     int pack(int i) const {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
-        ActOut t = training ? wpT(i).out() : ActOut();
+        const bool flipped = training && implicit(i);
+        ActOut t = (training && !flipped) ? wpT(i).out() : ActOut();
         pack_conv_kernel<<<blocks_for((int64_t)c.cout * d.Kp, 256), 256, 0, s>>>(w->conv_w[i], c.cout, c.cin, c.k, d.K, d.Kp,
                                                                                 wp(i).out(), t);
         VETO_LAUNCH_CHECK();
+        if (flipped) {
+            pack_conv_flipped_kernel<<<blocks_for((int64_t)c.cout * d.Kp, 256), 256, 0, s>>>(w->conv_w[i], c.cout, c.cin, c.k,
+                                                                                            wpT(i).out());
+            VETO_LAUNCH_CHECK();
+        }
         return VETO_OK;
     }
-    int conv(int i, const float* x) const {
+    int im2col(int i, const float* x) const {
+        const ConvSpec& c = kSpec[i];
+        const ConvDims& d = L->d[i];
+        const int64_t n = d.M * (d.Kp / 8);
+        if (c.cin % 8 == 0)
+            im2col_kernel<true><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
+                                                                   d.K, d.Kp, d.M, col(i).out());
+        else
+            im2col_kernel<false><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
+                                                                    d.K, d.Kp, d.M, col(i).out());
+        VETO_LAUNCH_CHECK();
+        return VETO_OK;
+    }
+    int conv(int i, const float* depth) const {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
         int rc = pack(i);
         if (rc) return rc;
-        const ActBuf cb = col(i);
-        const int64_t n = d.M * (d.Kp / 8);
-        if (c.cin % 8 == 0)
-            im2col_kernel<true><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
-                                                                   d.K, d.Kp, d.M, cb.out());
-        else
-            im2col_kernel<false><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
-                                                                    d.K, d.Kp, d.M, cb.out());
-        VETO_LAUNCH_CHECK();
+        const ActBuf W = wp(i);
+        if (implicit(i)) {
+            const ActBuf a = src_op(i);
+            GemmOperand A, Wo;
+            A.hi = a.hi; A.lo = a.lo;
+            Wo.hi = W.hi; Wo.lo = W.lo;
+            return conv_tc(A, Wo, batch, d.hin, d.win, c.cin, c.cout, c.k, c.pad, passes(), f32(L->raw[i]), c.cout, s);
+        }
+        if ((rc = im2col(i, src_f32(i, depth)))) return rc;
         GemmEpilogue ep;
         ep.out.f32 = f32(L->raw[i]);
         ep.ldc = c.cout;
-        const ActBuf W = wp(i);
-        return linear(prec, cb, d.Kp, WRef{W.f32, W.hi, W.lo}, (int)d.M, c.cout, d.Kp, ep, s);
+        return linear(prec, col(i), d.Kp, WRef{W.f32, W.hi, W.lo}, (int)d.M, c.cout, d.Kp, ep, s);
     }
     int reduce_blocks(int64_t M, int64_t* rows_per_block) const {
         int64_t rpb = (M + kBnMaxBlocks - 1) / kBnMaxBlocks;
@@ -586,7 +676,7 @@ struct Run {
             const int blocks = reduce_blocks(M, &rpb);
             bn_reduce_kernel<0><<<blocks, 256, 0, s>>>(f32(L->raw[i]), nullptr, nullptr, nullptr, C, M, rpb, f32(L->bn_partial));
             VETO_LAUNCH_CHECK();
-            bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(f32(L->bn_partial), blocks, C, M, momentum, stat,
+            bn_stats_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(f32(L->bn_partial), blocks, C, M, momentum, stat,
                                                                     w->bn_mean[i], w->bn_var[i]);
             VETO_LAUNCH_CHECK();
         } else {
@@ -595,7 +685,7 @@ struct Run {
         }
         bn_apply_kernel<<<blocks_for(M * (C / 4), 256), 256, 0, s>>>(f32(L->raw[i]), stat, w->bn_w[i], w->bn_b[i], residual,
                                                                     relu ? 1 : 0, C, M, (int64_t)L->d[i].hout * L->d[i].wout,
-                                                                    f32(L->y[i]), out_nchw);
+                                                                    f32(L->y[i]), out_nchw, yop_out(i));
         VETO_LAUNCH_CHECK();
         return VETO_OK;
     }
@@ -609,7 +699,7 @@ struct Run {
         const int blocks = reduce_blocks(M, &rpb);
         bn_reduce_kernel<1><<<blocks, 256, 0, s>>>(f32(L->raw[i]), dy, mask, f32(L->stat[i]), C, M, rpb, f32(L->bn_partial));
         VETO_LAUNCH_CHECK();
-        bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(f32(L->bn_partial), blocks, C, f32(L->bn_sums), g->bn_w[i],
+        bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(f32(L->bn_partial), blocks, C, f32(L->bn_sums), g->bn_w[i],
                                                               g->bn_b[i]);
         VETO_LAUNCH_CHECK();
         bn_bwd_apply_kernel<<<blocks_for(M * (C / 4), 256), 256, 0, s>>>(f32(L->raw[i]), dy, mask, f32(L->stat[i]), w->bn_w[i],
@@ -626,6 +716,7 @@ struct Run {
         const ActBuf X = col(i);
         float* gp = f32(L->dwp);
         int rc;
+        if (i != 0 && (rc = im2col(i, src_f32(i, nullptr)))) return rc;  // conv1 kept its own (its input is not passed here)
         if (prec == VETO_PREC_FP32) {
             const int64_t Mp = pad64(d.M);
             ActOut o1, o2;
@@ -668,10 +759,26 @@ struct Run {
     int dgrad(int i, float* dx, bool accumulate, const float* add, const float* mask) const {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
+        const ActBuf WT = wpT(i);
+        if (implicit(i)) {
+            // d(input) = the stride-1 convolution of d(output) with the flipped, transposed weights
+            VETO_REQUIRE(!accumulate, VETO_ERR_ARG, "depth backbone: implicit input gradient cannot accumulate");
+            const ActBuf dy = act(L->dyop, (size_t)d.M * c.cout);
+            GemmOperand A, Wo;
+            A.hi = dy.hi; A.lo = dy.lo;
+            Wo.hi = WT.hi; Wo.lo = WT.lo;
+            int rc = conv_tc(A, Wo, batch, d.hout, d.wout, c.cout, c.cin, c.k, c.k - 1 - c.pad, passes(), dx, c.cin, s);
+            if (rc) return rc;
+            if (add) {
+                const int64_t n4 = (int64_t)batch * d.hin * d.win * (c.cin / 4);
+                add_masked_kernel<<<blocks_for(n4, 256), 256, 0, s>>>(dx, add, mask, n4);
+                VETO_LAUNCH_CHECK();
+            }
+            return VETO_OK;
+        }
         GemmEpilogue ep;
         ep.out.f32 = f32(L->dcol);
         ep.ldc = d.Kp;
-        const ActBuf WT = wpT(i);
         int rc = linear(prec, act(L->dyop, (size_t)d.M * c.cout), c.cout, WRef{WT.f32, WT.hi, WT.lo}, (int)d.M, d.Kp, c.cout, ep, s);
         if (rc) return rc;
         const int64_t pixels = (int64_t)batch * d.hin * d.win;
@@ -729,27 +836,30 @@ extern "C" int veto_depth_backbone_forward(int precision, const veto_depth_weigh
     if (precision != VETO_PREC_FP32) RC(gemm_tc_init());
     Run R{precision, (cudaStream_t)stream, (char*)workspace_dev, &L, w, batch, training != 0, momentum};
     set_tag(TAG_OTHER);
-    RC(R.conv(0, depth_dev));
+    RC(R.conv(0, depth_dev));  // conv1 reads the depth image; every other convolution knows its source (DepthLayout::src)
     RC(R.bn(0, nullptr, true, nullptr));
     {
         const int64_t n = (int64_t)batch * L.hp * L.wp * (64 / 4);
         maxpool_fwd_kernel<<<blocks_for(n, 256), 256, 0, R.s>>>(R.f32(L.y[0]), L.d[0].hout, L.d[0].wout, 64, L.hp, L.wp,
                                                                (int64_t)batch * L.hp * L.wp, R.f32(L.pool),
-                                                               training ? (uchar4*)(R.B + L.pool_arg) : nullptr);
+                                                               training ? (uchar4*)(R.B + L.pool_arg) : nullptr,
+                                                               precision != VETO_PREC_FP32
+                                                                   ? R.act(L.pool_op, (size_t)batch * L.hp * L.wp * 64).out()
+                                                                   : ActOut());
         VETO_LAUNCH_CHECK();
     }
     const float* x = R.f32(L.pool);
     for (int b = 0; b < 6; ++b) {
         const BlockSpec& bs = kBlocks[b];
-        RC(R.conv(bs.c1, x));
+        RC(R.conv(bs.c1, nullptr));
         RC(R.bn(bs.c1, nullptr, true, nullptr));
         const float* identity = x;
         if (bs.ds >= 0) {
-            RC(R.conv(bs.ds, x));
+            RC(R.conv(bs.ds, nullptr));
             RC(R.bn(bs.ds, nullptr, false, nullptr));
             identity = R.f32(L.y[bs.ds]);
         }
-        RC(R.conv(bs.c2, R.f32(L.y[bs.c1])));
+        RC(R.conv(bs.c2, nullptr));
         RC(R.bn(bs.c2, identity, true, b == 5 ? out_dev : nullptr));
         x = R.f32(L.y[bs.c2]);
     }

@@ -11,6 +11,12 @@
 // the other stage with tcgen05.ld and apply bias / GELU / residual before storing.  With passes == 3
 // the K loop runs three times over (A_hi,W_hi), (A_lo,W_hi), (A_hi,W_lo): the bf16x3 split that gives
 // fp32-grade products on the bf16 pipe (every fp32 operand = hi + lo with 16 mantissa bits kept).
+//
+// CONV = true is the implicit-GEMM form of a stride-1 k x k convolution on NHWC activations (the depth backbone,
+// depth_backbone.cu): an output tile is an 8 x 16 patch of pixels, and the A tile of (tap, 64-channel block) is ONE 4-D
+// TMA box {64 channels, 16, 8, 1} of the activation tensor at the tap's offset — the padding is TMA's out-of-bounds
+// zero fill, the shared-memory image is the same 128 rows x 128 B swizzled tile a 2-D box gives, so the MMA side does
+// not change.  Nothing is materialised: the 9 taps of a pixel are re-read from L2.
 #include <cuda.h>
 
 #include <mutex>
@@ -63,6 +69,11 @@ struct TileCfg {
 // kind::f16 instruction descriptor: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10), both K-major,
 // N>>3 in [17,23), M>>4 in [24,29).
 
+constexpr int CONV_TH = 8, CONV_TW = 16;  // output patch of one tile (CONV_TH * CONV_TW == BLOCK_M)
+struct ConvGeom {
+    int H, W, Cin, ks, pad, n_th, n_tw;
+};
+
 struct EpiParams {
     const float* bias;
     const float* residual;
@@ -74,11 +85,11 @@ struct EpiParams {
     int ldr;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-               int M, int N, int K, int passes, EpiParams ep) {
+               int M, int N, int K, int passes, EpiParams ep, ConvGeom cg_) {
     using C = TileCfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -96,7 +107,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    // CONV: M = batch * n_th * n_tw patches of 128 pixels
+    const int num_m = CONV ? M : (M + BLOCK_M - 1) / BLOCK_M;
     const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
     const int kb_per_pass = K / BLOCK_K;
@@ -140,6 +152,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     const int k0 = (kb - pass * kb_per_pass) * BLOCK_K;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    if (CONV) {
+                        const int patch = tile / num_n;
+                        const int tw = patch % cg_.n_tw, th = (patch / cg_.n_tw) % cg_.n_th, b = patch / (cg_.n_tw * cg_.n_th);
+                        const int tap = k0 / cg_.Cin, c0 = k0 - tap * cg_.Cin;
+                        const int kh = tap / cg_.ks, kw = tap - kh * cg_.ks;
+                        tma_load_4d(smem_a + stage * C::kBytesA, (pass == 1) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], c0,
+                                    tw * CONV_TW + kw - cg_.pad, th * CONV_TH + kh - cg_.pad, b);
+                    } else
                     tma_load_2d(smem_a + stage * C::kBytesA, (pass == 1) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], k0, m0);
                     tma_load_2d(smem_b + stage * C::kBytesB, (pass == 2) ? &tm_w_lo : &tm_w_hi, &full_bar[stage], k0, n0);
                     if (++stage == C::kStages) {
@@ -203,6 +223,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * BLOCK_M + q * 32;
             const int n0 = (tile % num_n) * BLOCK_N;
+            // CONV: tile row r = pixel (th*8 + r/16, tw*16 + r%16) of image b; rows outside the image are not stored
+            int conv_b = 0, conv_h0 = 0, conv_w0 = 0;
+            if (CONV) {
+                const int patch = tile / num_n;
+                conv_w0 = (patch % cg_.n_tw) * CONV_TW;
+                conv_h0 = ((patch / cg_.n_tw) % cg_.n_th) * CONV_TH;
+                conv_b = patch / (cg_.n_tw * cg_.n_th);
+            }
             float4 res[4], res_next[4];
             auto load_res = [&](int c, float4 (&dst)[4]) {
                 const int col = n0 + c * EPI_COLS + cg * 4;
@@ -240,8 +268,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 for (int rr = 0; rr < 4; ++rr) {
                     const int lr = rr * 8 + rsub;
                     float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
-                    const int row = m0 + lr;
-                    if (row < M && col < N) {  // N % 4 == 0 is enforced by the host
+                    long long row = m0 + lr;
+                    bool row_ok = row < M;
+                    if (CONV) {
+                        const int r = q * 32 + lr;
+                        const int h = conv_h0 + r / CONV_TW, w = conv_w0 + r % CONV_TW;
+                        row_ok = h < cg_.H && w < cg_.W;
+                        row = ((long long)conv_b * cg_.H + h) * cg_.W + w;
+                    }
+                    if (row_ok && col < N) {  // N % 4 == 0 is enforced by the host
                         v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
                         v.x = apply_act(v.x, ep.act); v.y = apply_act(v.y, ep.act);
                         v.z = apply_act(v.z, ep.act); v.w = apply_act(v.w, ep.act);
@@ -342,7 +377,49 @@ int launch(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int 
     const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc};
-    gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+    gemm_tc_kernel<BLOCK_N, false><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p,
+                                                                           ConvGeom{});
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+// NHWC bf16 activation [B,H,W,C] -> 4-D tiled map, box {64 channels, CONV_TW, CONV_TH, 1}, 128-byte swizzle, zero fill
+int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap* out) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {BLOCK_K, CONV_TW, CONV_TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for NHWC [%d,%d,%d,%d] at %p", (int)r, B, H, W, C, (const void*)p);
+        return VETO_ERR_CUDA;
+    }
+    return VETO_OK;
+}
+
+template <int BLOCK_N>
+int launch_conv(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
+                float* out, int ldc, cudaStream_t s) {
+    using C = TileCfg<BLOCK_N>;
+    const int K = ks * ks * Cin;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    int rc;
+    if ((rc = get_map_nhwc(A.hi, B, H, Wd, Cin, &ta_hi))) return rc;
+    if ((rc = get_map(W.hi, N, K, K, BLOCK_N, &tw_hi))) return rc;
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (passes == 3) {
+        if ((rc = get_map_nhwc(A.lo, B, H, Wd, Cin, &ta_lo))) return rc;
+        if ((rc = get_map(W.lo, N, K, K, BLOCK_N, &tw_lo))) return rc;
+    }
+    ConvGeom g{H, Wd, Cin, ks, pad, (H + CONV_TH - 1) / CONV_TH, (Wd + CONV_TW - 1) / CONV_TW};
+    const int patches = B * g.n_th * g.n_tw;
+    const int tiles = patches * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    EpiParams p{nullptr, nullptr, out, nullptr, nullptr, ACT_NONE, ldc, ldc};
+    gemm_tc_kernel<BLOCK_N, true><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, patches, N, K, passes, p, g);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
@@ -358,8 +435,10 @@ int gemm_tc_init() {
     VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<192>::kSmemBytes));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<192>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<64>::kSmemBytes));
     g_inited = true;
     return VETO_OK;
 }
@@ -379,6 +458,18 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int
     if (rc) return rc;
     if (N % 192 == 0) return launch<192>(A, W, M, N, K, passes, ep, s);
     return launch<128>(A, W, M, N, K, passes, ep, s);
+}
+
+int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
+            float* out, int ldc, cudaStream_t s) {
+    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "conv_tc: passes must be 1 or 3");
+    VETO_REQUIRE(Cin % BLOCK_K == 0 && N % 4 == 0 && ldc % 4 == 0 && ks >= 1 && pad >= 0 && pad < ks, VETO_ERR_UNSUPPORTED,
+                 "conv_tc: Cin=%d must be a multiple of %d, N=%d and ldc=%d of 4", Cin, BLOCK_K, N, ldc);
+    VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)) && out, VETO_ERR_ARG, "conv_tc: missing operand");
+    int rc = gemm_tc_init();
+    if (rc) return rc;
+    if (N <= 64) return launch_conv<64>(A, W, B, H, Wd, Cin, N, ks, pad, passes, out, ldc, s);
+    return launch_conv<128>(A, W, B, H, Wd, Cin, N, ks, pad, passes, out, ldc, s);
 }
 
 }  // namespace veto
