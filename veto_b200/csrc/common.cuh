@@ -216,6 +216,11 @@ int gemm_tn2_mn_tiles(int Nw, int Kw);                                  // outpu
 double gemm_tn2_efficiency(int Nw, int Kw, int slices, int pairs);         // busy fraction of the CTA pairs for a slice count
 int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
              size_t split_stride, cudaStream_t s, const uint32_t* geometry = nullptr);
+// Convolution form: G[Cout, ks*ks*Cin] = sum over pixels of dY[b,h,w,:]^T x X[b,h+kh-pad,w+kw-pad,:], both NHWC bf16 hi[/lo]
+// of the same spatial size (stride-1 convolution), no im2col; gemm_tn2_conv_rows = the row count to size split-K with.
+int gemm_tn2_conv_rows(int B, int H, int W);
+int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Cout, int Cin, int ks, int pad, int passes,
+                  float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s);
 // picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc
 int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
                  cudaStream_t s);

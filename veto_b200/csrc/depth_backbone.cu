@@ -716,7 +716,8 @@ struct Run {
         const ActBuf X = col(i);
         float* gp = f32(L->dwp);
         int rc;
-        if (i != 0 && (rc = im2col(i, src_f32(i, nullptr)))) return rc;  // conv1 kept its own (its input is not passed here)
+        const bool conv_form = implicit(i);  // reduction over pixel patches of the NHWC operands, no im2col
+        if (i != 0 && !conv_form && (rc = im2col(i, src_f32(i, nullptr)))) return rc;  // conv1 kept its own (its input is not passed here)
         if (prec == VETO_PREC_FP32) {
             const int64_t Mp = pad64(d.M);
             ActOut o1, o2;
@@ -729,12 +730,13 @@ struct Run {
             ep.out.f32 = gp;
             if ((rc = gemm_simt(o1.f32, (int)Mp, o2.f32, c.cout, d.Kp, (int)Mp, ep, s))) return rc;
         } else {
+            const int rows = conv_form ? gemm_tn2_conv_rows(batch, d.hout, d.wout) : (int)d.M;
             const int pairs = num_sms() / 2;
-            const int max_s = (int)((d.M + 511) / 512) < kMaxSplit ? (int)((d.M + 511) / 512) : kMaxSplit;
+            const int max_s = (rows + 511) / 512 < kMaxSplit ? (rows + 511) / 512 : kMaxSplit;
             int best = 1;
             double best_eff = 0.0;
             for (int want = 1; want <= (max_s > 1 ? max_s : 1); ++want) {
-                const int sl = gemm_tn2_slices((int)d.M, want);
+                const int sl = gemm_tn2_slices(rows, want);
                 const double eff = gemm_tn2_efficiency(c.cout, d.Kp, sl, pairs);
                 if (eff > best_eff + 0.02) {
                     best_eff = eff;
@@ -743,11 +745,17 @@ struct Run {
             }
             GemmOperand A, Bo;
             A.hi = dY.hi; A.lo = dY.lo; A.ld = c.cout;
-            Bo.hi = X.hi; Bo.lo = X.lo; Bo.ld = d.Kp;
             const size_t n = (size_t)c.cout * d.Kp;
             float* sk = f32(L->splitk);
-            if ((rc = gemm_tn2(A, Bo, c.cout, d.Kp, (int)d.M, prec == VETO_PREC_BF16X3 ? 3 : 1, best > 1 ? sk : gp, d.Kp, best, n, s)))
-                return rc;
+            if (conv_form) {
+                const ActBuf xin = src_op(i);
+                Bo.hi = xin.hi; Bo.lo = xin.lo;
+                rc = gemm_tn2_conv(A, Bo, batch, d.hout, d.wout, c.cout, c.cin, c.k, c.pad, passes(), best > 1 ? sk : gp, d.Kp, best, n, s);
+            } else {
+                Bo.hi = X.hi; Bo.lo = X.lo; Bo.ld = d.Kp;
+                rc = gemm_tn2(A, Bo, c.cout, d.Kp, (int)d.M, passes(), best > 1 ? sk : gp, d.Kp, best, n, s);
+            }
+            if (rc) return rc;
             if (best > 1 && (rc = splitk_reduce(sk, best, n, n, gp, s))) return rc;
         }
         unpack_conv_grad_kernel<<<blocks_for((int64_t)c.cout * c.cin * c.k * c.k, 256), 256, 0, s>>>(gp, c.cout, c.cin, c.k, d.Kp,

@@ -16,6 +16,12 @@
 // plain fp32 and summed in a fixed order by splitk_reduce (train.cu).  Rows beyond the end of the arrays are
 // zero-filled by TMA, so the row count needs no padding.
 //
+// Convolution form (gemm_tn2_conv, the depth backbone's weight gradients): dY and X are NHWC activations and the
+// reduction runs over pixels.  A K block is a 4 x 16 pixel patch; the dY box is the patch itself, the X box of an output
+// column block (tap, 64 channels) the same patch shifted by the tap — 4-D TMA boxes whose shared-memory image equals the
+// 64-row 2-D box, with out-of-bounds zero fill standing in for the padding (and for patches hanging over the image
+// edge).  Only the producer differs; no im2col matrix exists.
+//
 // Tile width: the first version used 256 x 128 tiles and ran at 62-68 % tensor-active (profiles/r1_train_ncu_full.txt):
 // per pipeline stage each SM writes 48 KB (TMA) and reads 72 KB (3 products x (A 16 KB + its half of B 8 KB)) for 816
 // tensor cycles = 147 B/clk, above the 128 B/clk shared-memory port.  A 256-wide tile halves the A traffic per MMA
@@ -73,7 +79,10 @@ struct TnParams {
     int ksplit, kb_per;
     long long split_stride;
     uint32_t lbo, sbo, kadv;  // descriptor geometry (constants in production; parameters for the bring-up test)
+    // convolution form: K block kb = pixel patch (b, th, tw) of CONV_PH x CONV_PW pixels; X column = (kh*ks + kw)*Cin + c
+    int conv, Cin, ks, pad, n_th, n_tw;
 };
+constexpr int CONV_PH = 4, CONV_PW = 16;  // CONV_PH * CONV_PW == BLOCK_K
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -167,6 +176,31 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t* sp = stage_ptr(stage);
+                    if (p.conv) {
+                        const int w0 = (kb % p.n_tw) * CONV_PW, h0 = ((kb / p.n_tw) % p.n_th) * CONV_PH, b = kb / (p.n_tw * p.n_th);
+                        for (int j = 0; j < BLOCK_M / MN_CHUNK; ++j) {
+                            tma_load_4d_pair(sp + j * CHUNK_BYTES, &tm_a_hi, &full_bar[stage], m0 + j * MN_CHUNK, w0, h0, b);
+                            if (split)
+                                tma_load_4d_pair(sp + off_a_lo + j * CHUNK_BYTES, &tm_a_lo, &full_bar[stage], m0 + j * MN_CHUNK, w0, h0, b);
+                        }
+                        for (int j = 0; j < b_boxes; ++j) {
+                            const int col = n0 + j * MN_CHUNK;
+                            const int tap = col / p.Cin;
+                            // columns beyond the last tap: a box outside the channel range (zero fill)
+                            const int c0 = tap < p.ks * p.ks ? col - tap * p.Cin : p.Cin;
+                            const int kh = tap / p.ks, kw = tap - kh * p.ks;
+                            tma_load_4d_pair(sp + off_b_hi + j * CHUNK_BYTES, &tm_b_hi, &full_bar[stage], c0, w0 + kw - p.pad,
+                                             h0 + kh - p.pad, b);
+                            if (split)
+                                tma_load_4d_pair(sp + off_b_lo + j * CHUNK_BYTES, &tm_b_lo, &full_bar[stage], c0, w0 + kw - p.pad,
+                                                 h0 + kh - p.pad, b);
+                        }
+                        if (++stage == num_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < BLOCK_M / MN_CHUNK; ++j) {
                         tma_load_2d_pair(sp + j * CHUNK_BYTES, &tm_a_hi, &full_bar[stage], m0 + j * MN_CHUNK, r0);
@@ -400,8 +434,61 @@ int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int ro
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride,
-               geometry ? geometry[0] : (uint32_t)CHUNK_BYTES, geometry ? geometry[1] : 1024u, geometry ? geometry[2] : 2048u};
+               geometry ? geometry[0] : (uint32_t)CHUNK_BYTES, geometry ? geometry[1] : 1024u, geometry ? geometry[2] : 2048u,
+               0, 0, 0, 0, 0, 0};
     gemm_tn2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, Nw, Kw, rows, passes, p);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+namespace {
+// NHWC bf16 [B,H,W,C]: boxes of a CONV_PH x CONV_PW pixel patch x 64 channels, 128-byte swizzle, zero fill
+int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap* out) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {MN_CHUNK, CONV_PW, CONV_PH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for NHWC [%d,%d,%d,%d] at %p (gemm_tn2_conv)", (int)r, B, H, W, C, (const void*)p);
+        return VETO_ERR_CUDA;
+    }
+    return VETO_OK;
+}
+}  // namespace
+
+int gemm_tn2_conv_rows(int B, int H, int W) { return B * ((H + CONV_PH - 1) / CONV_PH) * ((W + CONV_PW - 1) / CONV_PW) * BLOCK_K; }
+
+int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Cout, int Cin, int ks, int pad, int passes,
+                  float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s) {
+    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tn2_conv: passes must be 1 or 3");
+    VETO_REQUIRE(dY.hi && X.hi && (passes == 1 || (dY.lo && X.lo)) && out, VETO_ERR_ARG, "gemm_tn2_conv: missing operand");
+    VETO_REQUIRE(Cout % 8 == 0 && Cin % MN_CHUNK == 0 && ldc % 4 == 0, VETO_ERR_UNSUPPORTED,
+                 "gemm_tn2_conv: Cout=%d must be a multiple of 8, Cin=%d of %d, ldc=%d of 4", Cout, Cin, MN_CHUNK, ldc);
+    int rc = init_tn();
+    if (rc) return rc;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if ((rc = get_map_nhwc(dY.hi, B, H, W, Cout, &ta_hi))) return rc;
+    if ((rc = get_map_nhwc(X.hi, B, H, W, Cin, &tb_hi))) return rc;
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+    if (passes == 3) {
+        if ((rc = get_map_nhwc(dY.lo, B, H, W, Cout, &ta_lo))) return rc;
+        if ((rc = get_map_nhwc(X.lo, B, H, W, Cin, &tb_lo))) return rc;
+    }
+    const int Kw = ks * ks * Cin;
+    const int n_th = (H + CONV_PH - 1) / CONV_PH, n_tw = (W + CONV_PW - 1) / CONV_PW;
+    const int num_kb = B * n_th * n_tw;
+    const int rows = num_kb * BLOCK_K;
+    const int ksplit = gemm_tn2_slices(rows, split_k);
+    const int kb_per = (num_kb + ksplit - 1) / ksplit;
+    const int tiles = gemm_tn2_mn_tiles(Cout, Kw) * ksplit;
+    const int pairs_avail = num_sms() / 2;
+    const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
+    TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride, (uint32_t)CHUNK_BYTES, 1024u, 2048u, 1, Cin, ks, pad, n_th, n_tw};
+    gemm_tn2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, Cout, Kw, rows, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
