@@ -2,6 +2,10 @@
 """Summaries of ncu output for profiles/ (text, committed):
    ncu_summary.py launches <launches.csv> <out.txt>          per-kernel launch counts / time shares
    ncu_summary.py report <file.ncu-rep> <out.txt> [regex]    selected metrics per captured launch
+   ncu_summary.py traffic <launches.csv> <out.txt> <first_launch> <title>
+                                                              per-kernel time + DRAM bytes of the library's launches from
+                                                              launch index <first_launch> on (csv with gpu__time_duration.sum,
+                                                              dram__bytes_read.sum, dram__bytes_write.sum)
 """
 import collections
 import csv
@@ -42,6 +46,33 @@ def launches(path, out):
             f.write(f"{k[:72]:72s} {v[0]:8d} {v[1] / 1e3:10.3f} {v[1] / v[0]:9.1f} {v[1] / tot * 100:6.1f}%\n")
 
 
+def traffic(path, out, first, title):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        per.setdefault((row["ID"], row["Kernel Name"]), {})[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+    step = [it for it in list(per.items())[first:] if "veto::" in it[0][1]]
+
+    def short(name):
+        m = re.search(r"(\w+_kernel)\s*(<[^(]{0,12})?", name)
+        return (m.group(1) + (m.group(2) or "")) if m else re.sub(r"\(.*", "", name)[:48]
+
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for (_, name), m in step:
+        a = agg[short(name)]
+        a[0] += 1
+        a[1] += m["gpu__time_duration.sum"] / 1e3
+        a[2] += (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / 1e6
+    tot, tb = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values())
+    with open(out, "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n")
+        f.write(f"# {title}: {len(step)} launches, {tot / 1e3:.2f} ms of kernel time, {tb / 1e3:.1f} GB of DRAM traffic "
+                f"(cold-cache, serialised: compare SHARES)\n")
+        f.write(f"{'kernel':44s} {'launches':>8s} {'total_us':>10s} {'share':>7s} {'dram_MB':>10s} {'TB/s':>6s}\n")
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"{k:44s} {a[0]:8d} {a[1]:10.1f} {100 * a[1] / tot:6.1f}% {a[2]:10.0f} {a[2] / a[1]:6.2f}\n")
+
+
 def report(path, out, pattern=None):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -58,6 +89,10 @@ def report(path, out, pattern=None):
                 if m in idx:
                     f.write(f"{m:100s} {d[idx[m]]:>16s} {units[idx[m]]}\n")
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
+    traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]), sys.argv[5])
+    sys.exit(0)
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
