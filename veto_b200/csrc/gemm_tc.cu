@@ -47,7 +47,13 @@ struct TileCfg {
     static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
     static constexpr int kEpiBytes = NUM_EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    // CONV: one stage holds A_hi, A_lo, W_hi, W_lo of a (tap, channel block) and serves the three bf16x3 products, so
+    // every operand tile crosses L2 -> shared memory once instead of once per product
+    static constexpr int kConvStageBytes = 2 * kStageBytes;
+    static constexpr int kConvStages = (192 * 1024) / kConvStageBytes;
+    static constexpr int kConvSmemBytes = kConvStages * kConvStageBytes + kEpiBytes + 1024 + 256;
+    static_assert(kSmemBytes <= 227 * 1024 && kConvSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert((BLOCK_N > 128 || kConvStages >= 3) && kConvStages <= kStages, "conv pipeline depth (barrier arrays are sized by kStages)");
     static_assert((BLOCK_N / EPI_COLS) % 2 == 0, "column chunks must split evenly over the two warps of a quarter");
 };
 
@@ -96,7 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::kStages * C::kBytesA;
-    uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;  // per-epilogue-warp transpose buffers
+    // per-epilogue-warp transpose buffers behind the pipeline (CONV: kConvStages stages of [A_hi][A_lo][W_hi][W_lo])
+    uint8_t* smem_epi = smem + (CONV ? C::kConvStages * C::kConvStageBytes : C::kStages * C::kStageBytes);
     uint64_t* bars = (uint64_t*)(smem_epi + C::kEpiBytes);
     uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
     uint64_t* empty_bar = bars + C::kStages;      // [kStages]  MMA -> TMA
@@ -112,7 +119,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
     const int kb_per_pass = K / BLOCK_K;
-    const int num_kb = kb_per_pass * passes;
+    const int num_kb = CONV ? kb_per_pass : kb_per_pass * passes;
+    constexpr int kPipe = CONV ? C::kConvStages : C::kStages;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi);
@@ -151,18 +159,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     const int pass = kb / kb_per_pass;
                     const int k0 = (kb - pass * kb_per_pass) * BLOCK_K;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    mbar_arrive_expect_tx(&full_bar[stage], (CONV && passes == 3) ? C::kConvStageBytes : C::kStageBytes);
                     if (CONV) {
                         const int patch = tile / num_n;
                         const int tw = patch % cg_.n_tw, th = (patch / cg_.n_tw) % cg_.n_th, b = patch / (cg_.n_tw * cg_.n_th);
                         const int tap = k0 / cg_.Cin, c0 = k0 - tap * cg_.Cin;
                         const int kh = tap / cg_.ks, kw = tap - kh * cg_.ks;
-                        tma_load_4d(smem_a + stage * C::kBytesA, (pass == 1) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], c0,
-                                    tw * CONV_TW + kw - cg_.pad, th * CONV_TH + kh - cg_.pad, b);
-                    } else
+                        const int x0 = tw * CONV_TW + kw - cg_.pad, y0 = th * CONV_TH + kh - cg_.pad;
+                        uint8_t* sp = smem + stage * C::kConvStageBytes;
+                        tma_load_4d(sp, &tm_a_hi, &full_bar[stage], c0, x0, y0, b);
+                        tma_load_2d(sp + 2 * C::kBytesA, &tm_w_hi, &full_bar[stage], k0, n0);
+                        if (passes == 3) {
+                            tma_load_4d(sp + C::kBytesA, &tm_a_lo, &full_bar[stage], c0, x0, y0, b);
+                            tma_load_2d(sp + 2 * C::kBytesA + C::kBytesB, &tm_w_lo, &full_bar[stage], k0, n0);
+                        }
+                        if (++stage == kPipe) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     tma_load_2d(smem_a + stage * C::kBytesA, (pass == 1) ? &tm_a_lo : &tm_a_hi, &full_bar[stage], k0, m0);
                     tma_load_2d(smem_b + stage * C::kBytesB, (pass == 2) ? &tm_w_lo : &tm_w_hi, &full_bar[stage], k0, n0);
-                    if (++stage == C::kStages) {
+                    if (++stage == kPipe) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -186,16 +205,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * C::kBytesA);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * C::kBytesB);
+                    const uint32_t a_addr = smem_u32(CONV ? smem + stage * C::kConvStageBytes : smem_a + stage * C::kBytesA);
+                    const uint32_t b_addr = CONV ? a_addr + 2 * C::kBytesA : smem_u32(smem_b + stage * C::kBytesB);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
                         const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
                         umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CONV && passes == 3) {  // hi*hi + lo*hi + hi*lo from the one stage
+                            umma_bf16(tmem_d, make_smem_desc(a_addr + C::kBytesA + k * UMMA_K * 2), bdesc, idesc, 1u);
+                            umma_bf16(tmem_d, adesc, make_smem_desc(b_addr + C::kBytesB + k * UMMA_K * 2), idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-                    if (++stage == C::kStages) {
+                    if (++stage == kPipe) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -419,7 +442,7 @@ int launch_conv(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd
     const int tiles = patches * ((N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     EpiParams p{nullptr, nullptr, out, nullptr, nullptr, ACT_NONE, ldc, ldc};
-    gemm_tc_kernel<BLOCK_N, true><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, patches, N, K, passes, p, g);
+    gemm_tc_kernel<BLOCK_N, true><<<grid, NUM_THREADS, C::kConvSmemBytes, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, patches, N, K, passes, p, g);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
@@ -437,8 +460,8 @@ int gemm_tc_init() {
     g_encode = (EncodeTiledFn)fn;
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<192>::kSmemBytes));
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<64>::kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kConvSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<64>::kConvSmemBytes));
     g_inited = true;
     return VETO_OK;
 }
