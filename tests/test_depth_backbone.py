@@ -187,3 +187,60 @@ def test_gpu_full_size_training_step_properties():
     model.eval()
     a, b = model(depth), model(depth)
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_gpu_chain_depth_backbone_into_relation_head():
+    """End to end as relation_train_net.py trains it: depth image -> depth backbone (train()) -> VETOFeatureExtractor ->
+    VETOPredictor train() -> rel_loss.backward() -> gradients of the BACKBONE's parameters, i.e. through both C calls and
+    the ROIAlign backward, against the same chain on the CPU oracle (depth_port -> torchvision roi_align -> torch_port)."""
+    from oracle import torch_port as TP
+    from tests import harness as H
+    from tests.cases import TRAIN_CASES
+    from tests.test_gpu_train import DEV, _set_dropout
+    from tests.train_util import train_case_inputs
+    from veto_b200 import config as vcfg
+    from veto_b200 import registry, synth
+    c = TRAIN_CASES["train_predcls"]
+    batch, sd, pairs, labels = train_case_inputs(c)
+    B, _, hd, wd = batch["depth"].shape
+    dsd, dimg = P.synth_state(2), P.synth_depth(B, 16 * hd, 16 * wd, seed=4)
+    assert P.out_size(16 * hd, 16 * wd) == (hd, wd)
+    # ---- CPU oracle chain
+    st = {k: torch.from_numpy(np.asarray(v)).clone().requires_grad_(v.dtype.kind == "f" and "running_" not in k)
+          for k, v in dsd.items()}
+    dmap = P.forward(st, torch.from_numpy(dimg), True)
+    boxes = [torch.from_numpy(b) for b in batch["boxes"]]
+    x2d, d2d = TP.pooler_forward([torch.from_numpy(f) for f in batch["feats"]], dmap, boxes)
+    tsd = TP.to_torch(sd)
+    loss_ref, _, g_d2d, *_ = TP.train_step(
+        tsd, boxes, [torch.from_numpy(p) for p in pairs], [torch.from_numpy(l) for l in labels], x2d.detach(), d2d.detach(),
+        c["mode"], labels=[torch.from_numpy(l) for l in batch["labels"]], class_weight=tsd["criterion_loss_rel.weight"])
+    d2d.backward(g_d2d)
+    # ---- the product path.  A wiring error is O(1).  fp32 mode: accumulation-order noise only; bf16x3: its 16-bit operands
+    # flip single near-tie ReLU / arg-max decisions, each moving the entries behind it by a few 1e-2 of the tensor's scale
+    # (see the sensitivity measurement in test_gpu_matches_oracle_full_gradients).
+    for precision, med_tol, max_tol in (("fp32", 5e-3, 1e-1), ("bf16x3", 3e-2, 3e-1)):
+        cfg = H.make_cfg(predictor=c["predictor"], mode=c["mode"], dataset=c["dataset"], precision=precision)
+        bls = H.boxlists(batch, DEV, vcfg.num_classes(cfg)[0])
+        feats, _ = H.device_features(batch, DEV)
+        backbone = _model(dsd, precision, DEV).train()
+        fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(DEV).train()
+        pred = registry.make_roi_relation_predictor(cfg, 512)
+        pred.load_state_dict(synth.to_torch_state(sd), strict=True)
+        pred = pred.to(DEV).train()
+        _set_dropout(pred, 0.0, 0.0, 0.0)
+        depth_features = backbone(torch.from_numpy(dimg).to(DEV))
+        assert depth_features.requires_grad and tuple(depth_features.shape) == (B, 256, hd, wd)
+        x2d_g, d2d_g, _, _ = fe(feats, bls, depth_features=depth_features)
+        loss = pred(bls, [torch.from_numpy(p).to(DEV) for p in pairs], [torch.from_numpy(l).to(DEV) for l in labels], None,
+                    roi_features=x2d_g, roi_depth_features=d2d_g)[2]["rel_loss"]
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(float(loss.detach()) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+        errs = {}
+        for k, p in backbone.named_parameters():
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+            errs[k] = grad_error(p.grad.cpu().numpy(), st[k].grad.numpy())
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+        assert np.median(list(errs.values())) < med_tol and max(errs.values()) < max_tol, (precision, worst)
