@@ -55,6 +55,7 @@ struct DepthLayout {
     int hp, wp;  // after the max-pool
     size_t col[kConvs], raw[kConvs], y[kConvs], yop[kConvs], stat[kConvs];  // stat: mean[C], rstd[C]; yop: y as GEMM operand
     size_t wp_[kConvs], wpT[kConvs];  // wpT: [Kp,Cout] transpose, or for the implicit convolutions the flipped [Cin, 9*Cout]
+    bool has_yop[kConvs];
     int src[kConvs];                  // which tensor feeds conv i: -2 the depth image, -1 the max-pool output, else y[src]
     size_t pool, pool_op, pool_arg, bn_partial, bn_sums;
     size_t dcol, gA, gB, gC, dyop, dwp, splitk, T1, T2;
@@ -108,6 +109,10 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
     // depth image, is not available to the backward call.
     const size_t shared_col = k.take(act_bytes(prec, col_max));
     const bool ops = prec != VETO_PREC_FP32;
+    // the bf16 operand copy of y[i] is written only where an implicit (stride-1 3x3) convolution reads it
+    bool feeds_implicit[kConvs] = {};
+    for (int j = 0; j < kConvs; ++j)
+        if (L.src[j] >= 0 && kSpec[j].stride == 1 && kSpec[j].k == 3 && kSpec[j].cin % 64 == 0) feeds_implicit[L.src[j]] = true;
     for (int i = 0; i < kConvs; ++i) {
         const ConvDims& d = L.d[i];
         const size_t M = (size_t)(d.M > 0 ? d.M : 1);
@@ -115,7 +120,8 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
         L.col[i] = (training && i == 0) ? k.take(act_bytes(prec, M * d.Kp)) : shared_col;
         L.raw[i] = k.take(f * M * C);
         L.y[i] = k.take(f * M * C);
-        L.yop[i] = ops ? k.take(act_bytes(prec, M * C)) : 0;
+        L.has_yop[i] = ops && feeds_implicit[i];
+        L.yop[i] = L.has_yop[i] ? k.take(act_bytes(prec, M * C)) : 0;
         L.stat[i] = k.take(f * 2 * C);
         L.wp_[i] = k.take(act_bytes(prec, (size_t)C * d.Kp));
         L.wpT[i] = training ? k.take(act_bytes(prec, (size_t)C * d.Kp)) : 0;
@@ -178,18 +184,19 @@ __device__ __forceinline__ void store4(const ActOut& o, size_t at, float4 v) {
 
 // col[m, (kh*k + kw)*Cin + c] = x[b, ho*s - p + kh, wo*s - p + kw, c] (zero outside the image and for k >= K).
 // One thread per 8 consecutive columns; VEC: Cin % 8 == 0, the 8 columns are one tap's consecutive channels.
-template <bool VEC>
+// (index type: 32-bit when M * Kp / 8 fits — the 64-bit divisions of the decode cost more than the copy itself)
+template <bool VEC, typename idx_t>
 __global__ void im2col_kernel(const float* __restrict__ x, int hin, int win, int cin, int ks, int stride, int pad, int hout,
                               int wout, int K, int Kp, int64_t M, ActOut col) {
     const int groups = Kp >> 3;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * groups) return;
-    const int64_t m = idx / groups;
-    const int k0 = (int)(idx - m * groups) << 3;
-    const int wo = (int)(m % wout);
-    const int64_t t = m / wout;
-    const int ho = (int)(t % hout);
-    const int64_t b = t / hout;
+    const idx_t idx = (idx_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int64_t)idx >= M * groups) return;
+    const idx_t m = idx / (idx_t)groups;
+    const int k0 = (int)(idx - m * (idx_t)groups) << 3;
+    const int wo = (int)(m % (idx_t)wout);
+    const idx_t t = m / (idx_t)wout;
+    const int ho = (int)(t % (idx_t)hout);
+    const int64_t b = (int64_t)(t / (idx_t)hout);
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -612,7 +619,7 @@ struct Run {
         if (src == -1) return act(L->pool_op, (size_t)batch * L->hp * L->wp * 64);
         return act(L->yop[src], (size_t)L->d[src].M * kSpec[src].cout);
     }
-    ActOut yop_out(int i) const { return prec != VETO_PREC_FP32 ? act(L->yop[i], (size_t)L->d[i].M * kSpec[i].cout).out() : ActOut(); }
+    ActOut yop_out(int i) const { return L->has_yop[i] ? act(L->yop[i], (size_t)L->d[i].M * kSpec[i].cout).out() : ActOut(); }
 
     int pack(int i) const {
         const ConvSpec& c = kSpec[i];
@@ -633,12 +640,18 @@ struct Run {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
         const int64_t n = d.M * (d.Kp / 8);
-        if (c.cin % 8 == 0)
-            im2col_kernel<true><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
-                                                                   d.K, d.Kp, d.M, col(i).out());
-        else
-            im2col_kernel<false><<<blocks_for(n, 256), 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout,
-                                                                    d.K, d.Kp, d.M, col(i).out());
+        const bool small = n + 256 < ((int64_t)1 << 32);
+        const unsigned grid = blocks_for(n, 256);
+#define VETO_IM2COL(VEC, T) \
+    im2col_kernel<VEC, T><<<grid, 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout, d.K, d.Kp, d.M, col(i).out())
+        if (c.cin % 8 == 0) {
+            if (small) VETO_IM2COL(true, uint32_t);
+            else VETO_IM2COL(true, int64_t);
+        } else {
+            if (small) VETO_IM2COL(false, uint32_t);
+            else VETO_IM2COL(false, int64_t);
+        }
+#undef VETO_IM2COL
         VETO_LAUNCH_CHECK();
         return VETO_OK;
     }
