@@ -290,7 +290,22 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
         mean = __ldg(reinterpret_cast<const float4*>(stat) + g);
         rstd = __ldg(reinterpret_cast<const float4*>(stat + C) + g);
     }
-    for (int64_t r = r0 + lane; r < r1; r += lanes) {
+    int64_t r = r0 + lane;
+    if (MODE == 0) {
+        // four rows in flight per thread: one 16-byte load per iteration leaves the statistics pass latency-bound
+        for (; r + 3 * lanes < r1; r += 4 * lanes) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(x + (size_t)(r + j * lanes) * C + 4 * g));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s0.x += v[j].x; s0.y += v[j].y; s0.z += v[j].z; s0.w += v[j].w;
+                s1.x = fmaf(v[j].x, v[j].x, s1.x); s1.y = fmaf(v[j].y, v[j].y, s1.y);
+                s1.z = fmaf(v[j].z, v[j].z, s1.z); s1.w = fmaf(v[j].w, v[j].w, s1.w);
+            }
+        }
+    }
+    for (; r < r1; r += lanes) {
         const size_t at = (size_t)r * C + 4 * g;
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + at));
         if (MODE == 0) {
