@@ -536,8 +536,25 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_depth_leg(steps=2, warmup=1)
             dcpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        # convolution FLOPs of one image (forward; the backward's input + weight gradients are twice that, conv1 has no
+        # input gradient)
+        ho, wo = (IMG_H + 6 - 7) // 2 + 1, (IMG_W + 6 - 7) // 2 + 1       # conv1 7x7 / 2, pad 3, one input channel
+        conv1_flop = 2.0 * ho * wo * 64 * 49
+        conv_flop = conv1_flop
+        ph, pw = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1                       # max-pool 3x3 / 2
+        # layer1 keeps the pooled size, layer2 / layer3 halve it; two blocks of two 3x3 each + one 1x1 where the layer strides
+        for cin, cout, div in ((64, 64, 1), (64, 128, 2), (128, 256, 4)):
+            oh, ow = (ph - 1) // div + 1, (pw - 1) // div + 1
+            first = 2.0 * oh * ow * cout * cin * 9 + (2.0 * oh * ow * cout * cin if cin != cout else 0.0)
+            conv_flop += first + 3 * 2.0 * oh * ow * cout * cout * 9
+        step_flop = B * (3 * conv_flop - conv1_flop)
+        d_tf = step_flop / d_ms / 1e9
         depth_leg = {"metric": "depth_images_per_sec", "value": world * B / d_ms * 1e3, "unit": "images/s",
                      "ms_fwd_bwd": d_ms, "ms_fwd": d_fwd_ms,
+                     "roofline": {"bound": "tensor", "achieved": d_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": d_tf / peak_tf,
+                                  "executed_mma_tflops": d_tf * passes, "frac_executed": d_tf * passes / peak_tf,
+                                  "note": "convolution FLOPs (forward + input + weight gradients) / step time; the step is "
+                                          "bound by operand delivery and the BatchNorm HBM passes, DESIGN.md 7a"},
                      "config": {"workload": f"SURVEY.md §8 f3: ResNetDepth (R-18-C4) train() forward + backward, {B} depth images "
                                             f"1x{IMG_H}x{IMG_W} per GPU -> [B,256,H/16,W/16]", "precision": args.precision},
                      "workspace_gb": round(ws_gb, 2), "cpu_baseline": dcpu}
