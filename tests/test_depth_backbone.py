@@ -77,6 +77,22 @@ def test_host_mirror_state_dict_contract():
         D.build_backbone(None, depth_backbone=False)
 
 
+def test_output_size_and_workspace_host_side():
+    """Host-only entry points (no GPU needed): the stride-16 output size follows torch's floor rule for every image size,
+    and the workspace grows with the batch and with training mode."""
+    from veto_b200 import lib as L
+    from veto_b200 import ops
+    lib = L.load()
+    rng = np.random.RandomState(0)
+    for h, w in [(16, 16), (17, 31), (592, 800), (600, 1000), (608, 1008), (1333, 800)] + [tuple(rng.randint(16, 1400, 2)) for _ in range(40)]:
+        assert ops.depth_backbone_out_size(int(h), int(w)) == P.out_size(int(h), int(w)), (h, w)
+    x = torch.zeros(1, 1, 45, 77)
+    assert tuple(P.eval_forward(P.synth_state(0), x.numpy()).shape[2:]) == ops.depth_backbone_out_size(45, 77)
+    sizes = [lib.veto_depth_backbone_workspace_bytes(1, b, 592, 800, t) for b, t in ((1, 0), (1, 1), (12, 0), (12, 1))]
+    assert 0 < sizes[0] < sizes[1] < sizes[3] and sizes[0] < sizes[2] < sizes[3]
+    assert lib.veto_depth_backbone_workspace_bytes(7, 1, 64, 64, 0) == 0          # bad precision code
+
+
 def test_product_path_needs_the_device():
     from veto_b200 import depth_backbone as D
     if torch.cuda.is_available():
