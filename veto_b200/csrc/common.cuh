@@ -198,9 +198,10 @@ int gemm_simt_slices(int K, int split_k);  // K slices an ep.split_k request rea
 int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes,
             const GemmEpilogue& ep, cudaStream_t s);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes (idempotent)
-// Implicit-GEMM stride-1 ks x ks convolution on the same kernel: A = NHWC bf16 hi[/lo] activation [B,H,W,Cin] (Cin % 64 == 0),
-// W = [N, ks*ks*Cin] with column (kh*ks + kw)*Cin + c; out[(b*H + h)*W + w, 0..N) fp32 with row stride ldc (gemm_tc.cu).
-int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
+// Implicit-GEMM ks x ks convolution on the same kernel: A = NHWC bf16 hi[/lo] activation [B,H,W,Cin] (the INPUT size; Cin % 64
+// == 0), W = [N, ks*ks*Cin] with column (kh*ks + kw)*Cin + c; out[(b*Ho + h)*Wo + w, 0..N) fp32 with row stride ldc, Ho / Wo
+// by the floor rule (gemm_tc.cu).  stride > 1 uses TMA element strides.
+int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int stride, int passes,
             float* out, int ldc, cudaStream_t s);
 // CTA-pair (cta_group::2) version, 256 x 192 tiles; needs N % 192 == 0 (gemm_tc2.cu)
 bool gemm_tc2_supported(int N, int K);
@@ -216,11 +217,11 @@ int gemm_tn2_mn_tiles(int Nw, int Kw);                                  // outpu
 double gemm_tn2_efficiency(int Nw, int Kw, int slices, int pairs);         // busy fraction of the CTA pairs for a slice count
 int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int rows, int passes, float* out, int ldc, int split_k,
              size_t split_stride, cudaStream_t s, const uint32_t* geometry = nullptr);
-// Convolution form: G[Cout, ks*ks*Cin] = sum over pixels of dY[b,h,w,:]^T x X[b,h+kh-pad,w+kw-pad,:], both NHWC bf16 hi[/lo]
-// of the same spatial size (stride-1 convolution), no im2col; gemm_tn2_conv_rows = the row count to size split-K with.
+// Convolution form: G[Cout, ks*ks*Cin] = sum over output pixels of dY[b,h,w,:]^T x X[b,h*stride+kh-pad,w*stride+kw-pad,:], both
+// NHWC bf16 hi[/lo] (dY [B,H,W,Cout], X [B,Hin,Win,Cin]), no im2col; gemm_tn2_conv_rows = the row count to size split-K with.
 int gemm_tn2_conv_rows(int B, int H, int W);
-int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Cout, int Cin, int ks, int pad, int passes,
-                  float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s);
+int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Hin, int Win, int Cout, int Cin, int ks, int pad,
+                  int stride, int passes, float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s);
 // picks gemm_tc2 where it applies (env VETO_GEMM_2CTA=0 forces the single-CTA kernel), else gemm_tc
 int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
                  cudaStream_t s);

@@ -3,14 +3,13 @@
 //
 // Activations live in HBM as NHWC fp32 ([B*H*W, C] row-major = the GEMM's row-major M x N) plus, in the tensor-core
 // modes, a bf16 hi/lo copy that is the A operand of the next convolution.
-//   * the 11 stride-1 3x3 convolutions: implicit GEMM (conv_tc, gemm_tc.cu) — an output tile is an 8 x 16 pixel patch,
-//     the A tile of a (tap, 64-channel block) one 4-D TMA box of the activation at the tap's offset, zero fill = padding;
-//     their input gradient is the same kernel over d(output) with the flipped, transposed weights
-//   * conv1, the strided 3x3 and the 1x1 stride-2 convolutions (and everything in fp32 mode): im2col into the operand
-//     format -> the library GEMM against the weights repacked as [Cout, k*k*Cin]; input gradient dcol = dY @ Wp gathered
-//     back to NHWC by col2im (no atomics: every input pixel sums its taps)
-//   * weight gradients: dWp = dY^T @ col on the MN-major tcgen05 GEMM, both operands read in place, the im2col re-derived
-//     from the saved input right before it (one shared buffer)
+//   * every convolution but conv1: implicit GEMM (conv_tc, gemm_tc.cu) — an output tile is an 8 x 16 pixel patch, the A
+//     tile of a (tap, 64-channel block) one 4-D TMA box of the activation at the tap's offset (element strides for the
+//     stride-2 ones), zero fill = padding.  Input gradient of the stride-1 3x3 ones: the same kernel over d(output) with
+//     the flipped, transposed weights; of the strided ones: dcol = dY @ Wp gathered back to NHWC by col2im (no atomics:
+//     every input pixel sums its taps).  Weight gradient: gemm_tn2_conv, pixel-patch K blocks, tap-shifted boxes.
+//   * conv1 (one input channel) and everything in fp32 mode: im2col into the operand format -> the library GEMM against
+//     the weights repacked as [Cout, k*k*Cin]; weight gradient dWp = dY^T @ col on the MN-major tcgen05 GEMM
 // BatchNorm2d on batch statistics is a two-stage column reduction over the [M, C] rows (fp32 partials per block, fp64
 // finalise in a fixed order: deterministic) and a fused normalise + residual + ReLU pass; its backward is the same
 // shape (two column sums, one elementwise pass that emits d(conv output) directly in the GEMM operand format).
@@ -112,7 +111,7 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
     // the bf16 operand copy of y[i] is written only where an implicit (stride-1 3x3) convolution reads it
     bool feeds_implicit[kConvs] = {};
     for (int j = 0; j < kConvs; ++j)
-        if (L.src[j] >= 0 && kSpec[j].stride == 1 && kSpec[j].k == 3 && kSpec[j].cin % 64 == 0) feeds_implicit[L.src[j]] = true;
+        if (L.src[j] >= 0 && kSpec[j].cin % 64 == 0) feeds_implicit[L.src[j]] = true;
     for (int i = 0; i < kConvs; ++i) {
         const ConvDims& d = L.d[i];
         const size_t M = (size_t)(d.M > 0 ? d.M : 1);
@@ -616,14 +615,16 @@ struct Run {
     ActBuf wp(int i) const { return act(L->wp_[i], (size_t)kSpec[i].cout * L->d[i].Kp); }
     ActBuf wpT(int i) const { return act(L->wpT[i], (size_t)kSpec[i].cout * L->d[i].Kp); }
 
-    // stride-1 3x3 convolutions on >= 64 channels run as implicit GEMMs (conv_tc: 4-D TMA boxes of the NHWC activation,
-    // nothing materialised) in the tensor-core modes; conv1, the three strided 3x3 and the two 1x1 stride-2 convolutions
-    // go through im2col.  VETO_DEPTH_IM2COL=1 forces im2col everywhere (debugging).
+    // convolutions on >= 64 input channels run as implicit GEMMs (conv_tc: 4-D TMA boxes of the NHWC activation, nothing
+    // materialised) in the tensor-core modes; conv1 goes through im2col.  VETO_DEPTH_IM2COL=1 forces im2col everywhere
+    // (debugging).
     bool implicit(int i) const {
         static const bool off = [] { const char* e = getenv("VETO_DEPTH_IM2COL"); return e && e[0] == '1'; }();
         const ConvSpec& c = kSpec[i];
-        return !off && prec != VETO_PREC_FP32 && c.stride == 1 && c.k == 3 && c.cin % 64 == 0;
+        return !off && prec != VETO_PREC_FP32 && c.cin % 64 == 0;
     }
+    // the input gradient as a convolution of d(output) with the flipped weights exists for the stride-1 3x3 ones only
+    bool implicit_dgrad(int i) const { return implicit(i) && kSpec[i].stride == 1 && kSpec[i].k == 3; }
     int passes() const { return prec == VETO_PREC_BF16X3 ? 3 : 1; }
     const float* src_f32(int i, const float* depth) const {
         const int src = L->src[i];
@@ -639,7 +640,7 @@ struct Run {
     int pack(int i) const {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
-        const bool flipped = training && implicit(i);
+        const bool flipped = training && implicit_dgrad(i);
         ActOut t = (training && !flipped) ? wpT(i).out() : ActOut();
         pack_conv_kernel<<<blocks_for((int64_t)c.cout * d.Kp, 256), 256, 0, s>>>(w->conv_w[i], c.cout, c.cin, c.k, d.K, d.Kp,
                                                                                 wp(i).out(), t);
@@ -681,7 +682,7 @@ struct Run {
             GemmOperand A, Wo;
             A.hi = a.hi; A.lo = a.lo;
             Wo.hi = W.hi; Wo.lo = W.lo;
-            return conv_tc(A, Wo, batch, d.hin, d.win, c.cin, c.cout, c.k, c.pad, passes(), f32(L->raw[i]), c.cout, s);
+            return conv_tc(A, Wo, batch, d.hin, d.win, c.cin, c.cout, c.k, c.pad, c.stride, passes(), f32(L->raw[i]), c.cout, s);
         }
         if ((rc = im2col(i, src_f32(i, depth)))) return rc;
         GemmEpilogue ep;
@@ -778,7 +779,8 @@ struct Run {
             if (conv_form) {
                 const ActBuf xin = src_op(i);
                 Bo.hi = xin.hi; Bo.lo = xin.lo;
-                rc = gemm_tn2_conv(A, Bo, batch, d.hout, d.wout, c.cout, c.cin, c.k, c.pad, passes(), best > 1 ? sk : gp, d.Kp, best, n, s);
+                rc = gemm_tn2_conv(A, Bo, batch, d.hout, d.wout, d.hin, d.win, c.cout, c.cin, c.k, c.pad, c.stride, passes(),
+                                   best > 1 ? sk : gp, d.Kp, best, n, s);
             } else {
                 Bo.hi = X.hi; Bo.lo = X.lo; Bo.ld = d.Kp;
                 rc = gemm_tn2(A, Bo, c.cout, d.Kp, (int)d.M, passes(), best > 1 ? sk : gp, d.Kp, best, n, s);
@@ -796,14 +798,14 @@ struct Run {
         const ConvSpec& c = kSpec[i];
         const ConvDims& d = L->d[i];
         const ActBuf WT = wpT(i);
-        if (implicit(i)) {
+        if (implicit_dgrad(i)) {
             // d(input) = the stride-1 convolution of d(output) with the flipped, transposed weights
             VETO_REQUIRE(!accumulate, VETO_ERR_ARG, "depth backbone: implicit input gradient cannot accumulate");
             const ActBuf dy = act(L->dyop, (size_t)d.M * c.cout);
             GemmOperand A, Wo;
             A.hi = dy.hi; A.lo = dy.lo;
             Wo.hi = WT.hi; Wo.lo = WT.lo;
-            int rc = conv_tc(A, Wo, batch, d.hout, d.wout, c.cout, c.cin, c.k, c.k - 1 - c.pad, passes(), dx, c.cin, s);
+            int rc = conv_tc(A, Wo, batch, d.hout, d.wout, c.cout, c.cin, c.k, c.k - 1 - c.pad, 1, passes(), dx, c.cin, s);
             if (rc) return rc;
             if (add) {
                 const int64_t n4 = (int64_t)batch * d.hin * d.win * (c.cin / 4);

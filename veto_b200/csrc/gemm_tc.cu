@@ -77,7 +77,7 @@ struct TileCfg {
 
 constexpr int CONV_TH = 8, CONV_TW = 16;  // output patch of one tile (CONV_TH * CONV_TW == BLOCK_M)
 struct ConvGeom {
-    int H, W, Cin, ks, pad, n_th, n_tw;
+    int H, W, Cin, ks, pad, n_th, n_tw, stride;  // H, W: OUTPUT size; input pixel = output pixel * stride + tap - pad
 };
 
 struct EpiParams {
@@ -165,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         const int tw = patch % cg_.n_tw, th = (patch / cg_.n_tw) % cg_.n_th, b = patch / (cg_.n_tw * cg_.n_th);
                         const int tap = k0 / cg_.Cin, c0 = k0 - tap * cg_.Cin;
                         const int kh = tap / cg_.ks, kw = tap - kh * cg_.ks;
-                        const int x0 = tw * CONV_TW + kw - cg_.pad, y0 = th * CONV_TH + kh - cg_.pad;
+                        const int x0 = tw * CONV_TW * cg_.stride + kw - cg_.pad, y0 = th * CONV_TH * cg_.stride + kh - cg_.pad;
                         uint8_t* sp = smem + stage * C::kConvStageBytes;
                         tma_load_4d(sp, &tm_a_hi, &full_bar[stage], c0, x0, y0, b);
                         tma_load_2d(sp + 2 * C::kBytesA, &tm_w_hi, &full_bar[stage], k0, n0);
@@ -406,12 +406,13 @@ int launch(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int 
     return VETO_OK;
 }
 
-// NHWC bf16 activation [B,H,W,C] -> 4-D tiled map, box {64 channels, CONV_TW, CONV_TH, 1}, 128-byte swizzle, zero fill
-int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap* out) {
+// NHWC bf16 activation [B,H,W,C] -> 4-D tiled map, box {64 channels, CONV_TW, CONV_TH, 1} pixels taken every `stride`-th
+// (TMA element strides: the box spans CONV_T* x stride elements and loads every stride-th), 128-byte swizzle, zero fill
+int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, int stride, CUtensorMap* out) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {BLOCK_K, CONV_TW, CONV_TH, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(CONV_TW * stride), (cuuint32_t)(CONV_TH * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -423,21 +424,22 @@ int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap
 }
 
 template <int BLOCK_N>
-int launch_conv(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
-                float* out, int ldc, cudaStream_t s) {
+int launch_conv(const GemmOperand& A, const GemmOperand& W, int B, int Hin, int Win, int Cin, int N, int ks, int pad, int stride,
+                int passes, float* out, int ldc, cudaStream_t s) {
+    const int H = (Hin + 2 * pad - ks) / stride + 1, Wd = (Win + 2 * pad - ks) / stride + 1;  // output size
     using C = TileCfg<BLOCK_N>;
     const int K = ks * ks * Cin;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     int rc;
-    if ((rc = get_map_nhwc(A.hi, B, H, Wd, Cin, &ta_hi))) return rc;
+    if ((rc = get_map_nhwc(A.hi, B, Hin, Win, Cin, stride, &ta_hi))) return rc;
     if ((rc = get_map(W.hi, N, K, K, BLOCK_N, &tw_hi))) return rc;
     ta_lo = ta_hi;
     tw_lo = tw_hi;
     if (passes == 3) {
-        if ((rc = get_map_nhwc(A.lo, B, H, Wd, Cin, &ta_lo))) return rc;
+        if ((rc = get_map_nhwc(A.lo, B, Hin, Win, Cin, stride, &ta_lo))) return rc;
         if ((rc = get_map(W.lo, N, K, K, BLOCK_N, &tw_lo))) return rc;
     }
-    ConvGeom g{H, Wd, Cin, ks, pad, (H + CONV_TH - 1) / CONV_TH, (Wd + CONV_TW - 1) / CONV_TW};
+    ConvGeom g{H, Wd, Cin, ks, pad, (H + CONV_TH - 1) / CONV_TH, (Wd + CONV_TW - 1) / CONV_TW, stride};
     const int patches = B * g.n_th * g.n_tw;
     const int tiles = patches * ((N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -483,16 +485,17 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int
     return launch<128>(A, W, M, N, K, passes, ep, s);
 }
 
-int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int passes,
+int conv_tc(const GemmOperand& A, const GemmOperand& W, int B, int H, int Wd, int Cin, int N, int ks, int pad, int stride, int passes,
             float* out, int ldc, cudaStream_t s) {
     VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "conv_tc: passes must be 1 or 3");
-    VETO_REQUIRE(Cin % BLOCK_K == 0 && N % 4 == 0 && ldc % 4 == 0 && ks >= 1 && pad >= 0 && pad < ks, VETO_ERR_UNSUPPORTED,
+    VETO_REQUIRE(Cin % BLOCK_K == 0 && N % 4 == 0 && ldc % 4 == 0 && ks >= 1 && pad >= 0 && pad < ks && stride >= 1 && stride <= 4,
+                 VETO_ERR_UNSUPPORTED,
                  "conv_tc: Cin=%d must be a multiple of %d, N=%d and ldc=%d of 4", Cin, BLOCK_K, N, ldc);
     VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)) && out, VETO_ERR_ARG, "conv_tc: missing operand");
     int rc = gemm_tc_init();
     if (rc) return rc;
-    if (N <= 64) return launch_conv<64>(A, W, B, H, Wd, Cin, N, ks, pad, passes, out, ldc, s);
-    return launch_conv<128>(A, W, B, H, Wd, Cin, N, ks, pad, passes, out, ldc, s);
+    if (N <= 64) return launch_conv<64>(A, W, B, H, Wd, Cin, N, ks, pad, stride, passes, out, ldc, s);
+    return launch_conv<128>(A, W, B, H, Wd, Cin, N, ks, pad, stride, passes, out, ldc, s);
 }
 
 }  // namespace veto

@@ -80,7 +80,7 @@ struct TnParams {
     long long split_stride;
     uint32_t lbo, sbo, kadv;  // descriptor geometry (constants in production; parameters for the bring-up test)
     // convolution form: K block kb = pixel patch (b, th, tw) of CONV_PH x CONV_PW pixels; X column = (kh*ks + kw)*Cin + c
-    int conv, Cin, ks, pad, n_th, n_tw;
+    int conv, Cin, ks, pad, n_th, n_tw, stride;
 };
 constexpr int CONV_PH = 4, CONV_PW = 16;  // CONV_PH * CONV_PW == BLOCK_K
 
@@ -189,11 +189,9 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             // columns beyond the last tap: a box outside the channel range (zero fill)
                             const int c0 = tap < p.ks * p.ks ? col - tap * p.Cin : p.Cin;
                             const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                            tma_load_4d_pair(sp + off_b_hi + j * CHUNK_BYTES, &tm_b_hi, &full_bar[stage], c0, w0 + kw - p.pad,
-                                             h0 + kh - p.pad, b);
-                            if (split)
-                                tma_load_4d_pair(sp + off_b_lo + j * CHUNK_BYTES, &tm_b_lo, &full_bar[stage], c0, w0 + kw - p.pad,
-                                                 h0 + kh - p.pad, b);
+                            const int xw = w0 * p.stride + kw - p.pad, xh = h0 * p.stride + kh - p.pad;
+                            tma_load_4d_pair(sp + off_b_hi + j * CHUNK_BYTES, &tm_b_hi, &full_bar[stage], c0, xw, xh, b);
+                            if (split) tma_load_4d_pair(sp + off_b_lo + j * CHUNK_BYTES, &tm_b_lo, &full_bar[stage], c0, xw, xh, b);
                         }
                         if (++stage == num_stages) {
                             stage = 0;
@@ -435,7 +433,7 @@ int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int ro
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride,
                geometry ? geometry[0] : (uint32_t)CHUNK_BYTES, geometry ? geometry[1] : 1024u, geometry ? geometry[2] : 2048u,
-               0, 0, 0, 0, 0, 0};
+               0, 0, 0, 0, 0, 0, 1};
     gemm_tn2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, Nw, Kw, rows, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
@@ -443,11 +441,11 @@ int gemm_tn2(const GemmOperand& dY, const GemmOperand& X, int Nw, int Kw, int ro
 
 namespace {
 // NHWC bf16 [B,H,W,C]: boxes of a CONV_PH x CONV_PW pixel patch x 64 channels, 128-byte swizzle, zero fill
-int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap* out) {
+int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, int stride, CUtensorMap* out) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {MN_CHUNK, CONV_PW, CONV_PH, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {MN_CHUNK, (cuuint32_t)(CONV_PW * stride), (cuuint32_t)(CONV_PH * stride), 1};  // every stride-th pixel
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -461,8 +459,8 @@ int get_map_nhwc(const __nv_bfloat16* p, int B, int H, int W, int C, CUtensorMap
 
 int gemm_tn2_conv_rows(int B, int H, int W) { return B * ((H + CONV_PH - 1) / CONV_PH) * ((W + CONV_PW - 1) / CONV_PW) * BLOCK_K; }
 
-int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Cout, int Cin, int ks, int pad, int passes,
-                  float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s) {
+int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int W, int Hin, int Win, int Cout, int Cin, int ks, int pad,
+                  int stride, int passes, float* out, int ldc, int split_k, size_t split_stride, cudaStream_t s) {
     VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tn2_conv: passes must be 1 or 3");
     VETO_REQUIRE(dY.hi && X.hi && (passes == 1 || (dY.lo && X.lo)) && out, VETO_ERR_ARG, "gemm_tn2_conv: missing operand");
     VETO_REQUIRE(Cout % 8 == 0 && Cin % MN_CHUNK == 0 && ldc % 4 == 0, VETO_ERR_UNSUPPORTED,
@@ -470,13 +468,13 @@ int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int
     int rc = init_tn();
     if (rc) return rc;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if ((rc = get_map_nhwc(dY.hi, B, H, W, Cout, &ta_hi))) return rc;
-    if ((rc = get_map_nhwc(X.hi, B, H, W, Cin, &tb_hi))) return rc;
+    if ((rc = get_map_nhwc(dY.hi, B, H, W, Cout, 1, &ta_hi))) return rc;
+    if ((rc = get_map_nhwc(X.hi, B, Hin, Win, Cin, stride, &tb_hi))) return rc;
     ta_lo = ta_hi;
     tb_lo = tb_hi;
     if (passes == 3) {
-        if ((rc = get_map_nhwc(dY.lo, B, H, W, Cout, &ta_lo))) return rc;
-        if ((rc = get_map_nhwc(X.lo, B, H, W, Cin, &tb_lo))) return rc;
+        if ((rc = get_map_nhwc(dY.lo, B, H, W, Cout, 1, &ta_lo))) return rc;
+        if ((rc = get_map_nhwc(X.lo, B, Hin, Win, Cin, stride, &tb_lo))) return rc;
     }
     const int Kw = ks * ks * Cin;
     const int n_th = (H + CONV_PH - 1) / CONV_PH, n_tw = (W + CONV_PW - 1) / CONV_PW;
@@ -487,7 +485,7 @@ int gemm_tn2_conv(const GemmOperand& dY, const GemmOperand& X, int B, int H, int
     const int tiles = gemm_tn2_mn_tiles(Cout, Kw) * ksplit;
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
-    TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride, (uint32_t)CHUNK_BYTES, 1024u, 2048u, 1, Cin, ks, pad, n_th, n_tw};
+    TnParams p{out, ldc, ksplit, kb_per, (long long)split_stride, (uint32_t)CHUNK_BYTES, 1024u, 2048u, 1, Cin, ks, pad, n_th, n_tw, stride};
     gemm_tn2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, Cout, Kw, rows, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
