@@ -184,7 +184,8 @@ __device__ __forceinline__ void store4(const ActOut& o, size_t at, float4 v) {
 // col[m, (kh*k + kw)*Cin + c] = x[b, ho*s - p + kh, wo*s - p + kw, c] (zero outside the image and for k >= K).
 // One thread per 8 consecutive columns; VEC: Cin % 8 == 0, the 8 columns are one tap's consecutive channels.
 // (index type: 32-bit when M * Kp / 8 fits — the 64-bit divisions of the decode cost more than the copy itself)
-template <bool VEC, typename idx_t>
+// KS1 > 0: one input channel and a KS1 x KS1 window known at compile time (conv1: the tap decode is divisions by constants)
+template <bool VEC, typename idx_t, int KS1 = 0>
 __global__ void im2col_kernel(const float* __restrict__ x, int hin, int win, int cin, int ks, int stride, int pad, int hout,
                               int wout, int K, int Kp, int64_t M, ActOut col) {
     const int groups = Kp >> 3;
@@ -216,8 +217,8 @@ __global__ void im2col_kernel(const float* __restrict__ x, int hin, int win, int
         for (int j = 0; j < 8; ++j) {
             const int kk = k0 + j;
             if (kk < K) {
-                const int tap = kk / cin, c = kk - tap * cin;
-                const int kh = tap / ks, kw = tap - kh * ks;
+                const int tap = KS1 ? kk : kk / cin, c = KS1 ? 0 : kk - tap * cin;
+                const int kh = KS1 ? tap / KS1 : tap / ks, kw = tap - kh * (KS1 ? KS1 : ks);
                 const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
                 if (hi >= 0 && hi < hin && wi >= 0 && wi < win) v[j] = __ldg(x + ((b * hin + hi) * win + wi) * cin + c);
             }
@@ -663,6 +664,9 @@ struct Run {
         if (c.cin % 8 == 0) {
             if (small) VETO_IM2COL(true, uint32_t);
             else VETO_IM2COL(true, int64_t);
+        } else if (c.cin == 1 && c.k == 7 && small) {
+            im2col_kernel<false, uint32_t, 7><<<grid, 256, 0, s>>>(x, d.hin, d.win, c.cin, c.k, c.stride, c.pad, d.hout, d.wout, d.K,
+                                                                   d.Kp, d.M, col(i).out());
         } else {
             if (small) VETO_IM2COL(false, uint32_t);
             else VETO_IM2COL(false, int64_t);
