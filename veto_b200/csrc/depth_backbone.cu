@@ -155,6 +155,22 @@ DepthLayout depth_layout(int prec, int B, int H, int W, bool training) {
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
+// idx -> (pixel, channel group) for a power-of-two number of channel groups (C / 4 with C = 64, 128 or 256), and pixel ->
+// (image, row, column) in 32-bit arithmetic (pixel counts are < 2^31, check_args): the 64-bit divisions of the plain
+// form cost more issue slots than the 16-byte accesses these kernels exist for
+__device__ __forceinline__ void split_groups(int64_t idx, int groups, int64_t& pixel, int& g) {
+    const int shift = __ffs(groups) - 1;
+    pixel = idx >> shift;
+    g = (int)(idx & (groups - 1));
+}
+__device__ __forceinline__ void split_pixel(int64_t pixel, int height, int width, int& b, int& h, int& w) {
+    const unsigned p = (unsigned)pixel;
+    const unsigned t = p / (unsigned)width;
+    w = (int)(p - t * (unsigned)width);
+    b = (int)(t / (unsigned)height);
+    h = (int)(t - (unsigned)b * (unsigned)height);
+}
+
 __device__ __forceinline__ void store8(const ActOut& o, size_t at, const float (&v)[8]) {
     if (o.f32) {
         *reinterpret_cast<float4*>(o.f32 + at) = make_float4(v[0], v[1], v[2], v[3]);
@@ -234,12 +250,12 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int hin, int win, 
     const int groups = cin >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= pixels * groups) return;
-    const int64_t p = idx / groups;
-    const int c0 = (int)(idx - p * groups) << 2;
-    const int w = (int)(p % win);
-    const int64_t t = p / win;
-    const int h = (int)(t % hin);
-    const int64_t b = t / hin;
+    int64_t p;
+    int cgi, bi, h, w;
+    split_groups(idx, groups, p, cgi);
+    split_pixel(p, hin, win, bi, h, w);
+    const int c0 = cgi << 2;
+    const int64_t b = bi;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int kh = 0; kh < ks; ++kh) {
         const int hs = h + pad - kh;
@@ -408,8 +424,9 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * groups) return;
-    const int64_t m = idx / groups;
-    const int g = (int)(idx - m * groups);
+    int64_t m;
+    int g;
+    split_groups(idx, groups, m, g);
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
     const float4 mean = __ldg(reinterpret_cast<const float4*>(stat) + g);
     const float4 rstd = __ldg(reinterpret_cast<const float4*>(stat + C) + g);
@@ -443,7 +460,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * groups) return;
-    const int g = (int)(idx % groups);
+    const int g = (int)(idx & (groups - 1));   // C / 4 is a power of two
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
     float4 d = __ldg(reinterpret_cast<const float4*>(dy) + idx);
     if (mask) {
@@ -472,12 +489,11 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int hin, int win
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= out_pixels * groups) return;
-    const int64_t p = idx / groups;
-    const int g = (int)(idx - p * groups);
-    const int wo = (int)(p % wout);
-    const int64_t t = p / wout;
-    const int ho = (int)(t % hout);
-    const int64_t b = t / hout;
+    int64_t p;
+    int g, bi, ho, wo;
+    split_groups(idx, groups, p, g);
+    split_pixel(p, hout, wout, bi, ho, wo);
+    const int64_t b = bi;
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     uchar4 a = make_uchar4(255, 255, 255, 255);
     for (int kh = 0; kh < 3; ++kh) {
@@ -505,12 +521,11 @@ __global__ void maxpool_bwd_kernel(const uchar4* __restrict__ arg, const float* 
     const int groups = C >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= in_pixels * groups) return;
-    const int64_t p = idx / groups;
-    const int g = (int)(idx - p * groups);
-    const int w = (int)(p % win);
-    const int64_t t = p / win;
-    const int h = (int)(t % hin);
-    const int64_t b = t / hin;
+    int64_t p;
+    int g, bi, h, w;
+    split_groups(idx, groups, p, g);
+    split_pixel(p, hin, win, bi, h, w);
+    const int64_t b = bi;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ho = h / 2; ho <= (h + 1) / 2 && ho < hout; ++ho) {
         const int kh = h - (ho * 2 - 1);
