@@ -144,18 +144,22 @@ extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, 
     if ((rc = pack_bias2(w->proj_v_b, (float*)(P + L.b_v2), kDimRgb, s))) return rc;
     if ((rc = pack_add(w->cls_token, w->pos_embedding, (float*)(P + L.clspos), kDim, s))) return rc;
     if (cfg->precision != VETO_PREC_FP32) {
+        // one launch re-splits every GEMM weight into its bf16 hi (+ lo) operand arrays
+        SplitJob jobs[kMaxSplitJobs];
+        int nj = 0;
         auto split = [&](const float* src, size_t hi, size_t lo, size_t n) {
-            return pack_split_bf16(src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n, s);
+            jobs[nj++] = SplitJob{src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n};
         };
-        if ((rc = split((const float*)(P + L.w_d2), L.d2_hi, L.d2_lo, (size_t)2 * kDimDepth * kPatchVec))) return rc;
-        if ((rc = split((const float*)(P + L.w_v2), L.v2_hi, L.v2_lo, (size_t)2 * kDimRgb * kPatchVec))) return rc;
+        split((const float*)(P + L.w_d2), L.d2_hi, L.d2_lo, (size_t)2 * kDimDepth * kPatchVec);
+        split((const float*)(P + L.w_v2), L.v2_hi, L.v2_lo, (size_t)2 * kDimRgb * kPatchVec);
         for (int l = 0; l < cfg->layers; ++l) {
             VETO_REQUIRE(w->qkv_w[l] && w->out_w[l] && w->ff1_w[l] && w->ff2_w[l], VETO_ERR_ARG, "layer %d weights missing", l);
-            if ((rc = split(w->qkv_w[l], L.qkv_hi[l], L.qkv_lo[l], (size_t)3 * kDim * kDim))) return rc;
-            if ((rc = split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim))) return rc;
-            if ((rc = split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim))) return rc;
-            if ((rc = split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp))) return rc;
+            split(w->qkv_w[l], L.qkv_hi[l], L.qkv_lo[l], (size_t)3 * kDim * kDim);
+            split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim);
+            split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim);
+            split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp);
         }
+        if ((rc = pack_split_bf16_multi(jobs, nj, s))) return rc;
     }
     return VETO_OK;
 }

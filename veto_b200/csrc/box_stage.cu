@@ -48,6 +48,23 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
     }
 }
 
+struct SplitJobs {
+    SplitJob j[kMaxSplitJobs];
+};
+// blockIdx.y = array, blockIdx.x strides over its elements four at a time (every n is a multiple of 4)
+__global__ void split_bf16_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+    const SplitJob& jb = jobs.j[blockIdx.y];
+    const size_t n4 = jb.n >> 2;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(jb.src) + e);
+        uint2 hi, lo;
+        split_pair(v.x, v.y, hi.x, lo.x);
+        split_pair(v.z, v.w, hi.y, lo.y);
+        reinterpret_cast<uint2*>(jb.hi)[e] = hi;
+        if (jb.lo) reinterpret_cast<uint2*>(jb.lo)[e] = lo;
+    }
+}
+
 int grid_for(size_t n) {
     const size_t b = (n + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -171,6 +188,23 @@ int pack_add(const float* a, const float* b, float* dst, int n, cudaStream_t s) 
 }
 int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s) {
     split_bf16_kernel<<<grid_for(n), 256, 0, s>>>(src, hi, lo, n);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int pack_split_bf16_multi(const SplitJob* jobs, int count, cudaStream_t s) {
+    if (count <= 0) return VETO_OK;
+    VETO_REQUIRE(count <= kMaxSplitJobs, VETO_ERR_ARG, "pack_split_bf16_multi: %d arrays > %d", count, kMaxSplitJobs);
+    SplitJobs J{};
+    size_t n_max = 0;
+    for (int i = 0; i < count; ++i) {
+        VETO_REQUIRE(jobs[i].src && jobs[i].hi && jobs[i].n % 4 == 0, VETO_ERR_ARG, "pack_split_bf16_multi: bad array %d", i);
+        J.j[i] = jobs[i];
+        n_max = jobs[i].n > n_max ? jobs[i].n : n_max;
+    }
+    const size_t bx = (n_max / 4 + 255) / 256;
+    dim3 grid((unsigned)(bx < 64 ? (bx ? bx : 1) : 64), (unsigned)count);
+    split_bf16_multi_kernel<<<grid, 256, 0, s>>>(J);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

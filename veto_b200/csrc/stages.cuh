@@ -14,6 +14,15 @@ int pack_patch(const float* src, float* dst, int out, cudaStream_t s);
 int pack_bias2(const float* b, float* dst, int out, cudaStream_t s);          // [b, 0]
 int pack_add(const float* a, const float* b, float* dst, int n, cudaStream_t s);
 int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
+// the same for up to kMaxSplitJobs arrays in ONE launch (the per-step re-split of the weights was 26 tiny launches)
+constexpr int kMaxSplitJobs = 2 + 4 * VETO_MAX_LAYERS;
+struct SplitJob {
+    const float* src;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    size_t n;
+};
+int pack_split_bf16_multi(const SplitJob* jobs, int count, cudaStream_t s);
 
 // ---- box stage (box_stage.cu) ----
 // pos_embed (BN1d eval -> Linear(4,128) -> ReLU, roi_relation_predictors.py:4042-4047,4097-4102) and the class

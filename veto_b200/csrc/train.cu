@@ -183,6 +183,27 @@ transpose_f32_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows
         if (c < cols && r < rows_pad) store_act(t_f32, t_hi, t_lo, (size_t)((int64_t)c * ld_dst + r), tile[tx][ty + 8 * k]);
     }
 }
+struct TransposeJobs {
+    TransposeJob j[kMaxTransposeJobs];
+};
+__global__ void __launch_bounds__(256) transpose_f32_multi_kernel(const __grid_constant__ TransposeJobs jobs) {
+    __shared__ float tile[32][33];
+    const TransposeJob& jb = jobs.j[blockIdx.z];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= jb.rows || c0 >= jb.cols) return;  // the grid covers the largest matrix
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < jb.rows && c < jb.cols) ? __ldg(jb.src + (size_t)r * jb.cols + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (c < jb.cols && r < jb.rows) store_act(jb.dst.f32, jb.dst.hi, jb.dst.lo, (size_t)c * jb.rows + r, tile[tx][ty + 8 * k]);
+    }
+}
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
                       __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int64_t rows_pad) {
@@ -1189,6 +1210,22 @@ int transpose_f32(const float* src, int64_t ld_src, int64_t rows, int cols, bool
     VETO_REQUIRE(grid.y <= 65535, VETO_ERR_UNSUPPORTED, "transpose: %lld rows exceed one launch", (long long)rows_pad);
     transpose_f32_kernel<<<grid, 256, 0, s>>>(src, ld_src, rows, cols, gelu ? TR_OP_GELU : TR_OP_NONE, drop, drop_ld, t_out.f32,
                                               t_out.hi, t_out.lo, ld_dst, rows_pad, rm_out.f32, rm_out.hi, rm_out.lo, ld_rm);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int transpose_f32_multi(const TransposeJob* jobs, int count, cudaStream_t s) {
+    if (count <= 0) return VETO_OK;
+    VETO_REQUIRE(count <= kMaxTransposeJobs, VETO_ERR_ARG, "transpose_f32_multi: %d matrices > %d", count, kMaxTransposeJobs);
+    TransposeJobs J{};
+    int rows = 0, cols = 0;
+    for (int i = 0; i < count; ++i) {
+        J.j[i] = jobs[i];
+        rows = jobs[i].rows > rows ? jobs[i].rows : rows;
+        cols = jobs[i].cols > cols ? jobs[i].cols : cols;
+    }
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, count);
+    transpose_f32_multi_kernel<<<grid, 256, 0, s>>>(J);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -25,6 +25,15 @@ int colsum(const ActIn& src, int64_t ld, int64_t rows, int cols, float* scratch,
 // rows..rows_pad-1 of t_out are zero.  rm_out (optional formats) receives f(src) row-major with row stride ld_rm.
 int transpose_f32(const float* src, int64_t ld_src, int64_t rows, int cols, bool gelu, const DropSpec& drop, int64_t drop_ld,
                   const ActOut& t_out, int64_t ld_dst, int64_t rows_pad, const ActOut& rm_out, int64_t ld_rm, cudaStream_t s);
+// dst[c, r] = src[r, c] for up to kMaxTransposeJobs dense fp32 matrices in ONE launch (the transposed encoder weights of the
+// input-gradient GEMMs: 4 per layer, re-derived every step)
+constexpr int kMaxTransposeJobs = 4 * VETO_MAX_LAYERS;
+struct TransposeJob {
+    const float* src;  // [rows, cols] dense
+    ActOut dst;        // [cols, rows] dense, any subset of f32 / hi / lo
+    int rows, cols;
+};
+int transpose_f32_multi(const TransposeJob* jobs, int count, cudaStream_t s);
 int transpose_bf16(const __nv_bfloat16* src, int64_t ld_src, int64_t rows, int cols, __nv_bfloat16* dst, int64_t ld_dst,
                    int64_t rows_pad, cudaStream_t s);
 int splitk_reduce(const float* partial, int slices, size_t n, size_t stride, float* out, cudaStream_t s);

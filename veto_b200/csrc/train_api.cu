@@ -440,16 +440,18 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     // transposed encoder weights for the input-gradient GEMMs
     set_tag(TAG_PACK);
     ActBuf wT_qkv[VETO_MAX_LAYERS], wT_out[VETO_MAX_LAYERS], wT_ff1[VETO_MAX_LAYERS], wT_ff2[VETO_MAX_LAYERS];
+    TransposeJob tjobs[kMaxTransposeJobs];
     for (int l = 0; l < NL; ++l) {
         wT_qkv[l] = X.act(T.WT[l].qkv, (size_t)3 * kDim * kDim);  // [576, 1728]
         wT_out[l] = X.act(T.WT[l].out, (size_t)kDim * kDim);      // [576, 576]
         wT_ff1[l] = X.act(T.WT[l].ff1, (size_t)kMlp * kDim);      // [576, 1152]
         wT_ff2[l] = X.act(T.WT[l].ff2, (size_t)kMlp * kDim);      // [1152, 576]
-        RC(transpose_f32(w->qkv_w[l], kDim, 3 * kDim, kDim, false, DropSpec(), 0, wT_qkv[l].out(), 3 * kDim, 3 * kDim, ActOut(), 0, s));
-        RC(transpose_f32(w->out_w[l], kDim, kDim, kDim, false, DropSpec(), 0, wT_out[l].out(), kDim, kDim, ActOut(), 0, s));
-        RC(transpose_f32(w->ff1_w[l], kDim, kMlp, kDim, false, DropSpec(), 0, wT_ff1[l].out(), kMlp, kMlp, ActOut(), 0, s));
-        RC(transpose_f32(w->ff2_w[l], kMlp, kDim, kMlp, false, DropSpec(), 0, wT_ff2[l].out(), kDim, kDim, ActOut(), 0, s));
+        tjobs[4 * l + 0] = TransposeJob{w->qkv_w[l], wT_qkv[l].out(), 3 * kDim, kDim};
+        tjobs[4 * l + 1] = TransposeJob{w->out_w[l], wT_out[l].out(), kDim, kDim};
+        tjobs[4 * l + 2] = TransposeJob{w->ff1_w[l], wT_ff1[l].out(), kMlp, kDim};
+        tjobs[4 * l + 3] = TransposeJob{w->ff2_w[l], wT_ff2[l].out(), kDim, kMlp};
     }
+    RC(transpose_f32_multi(tjobs, 4 * NL, s));  // one launch instead of 4 per layer
 
     ActBuf a576 = X.act(T.a576, (size_t)M * kDim);
     ActBuf a1728 = X.act(T.a1728, (size_t)M * 3 * kDim);
