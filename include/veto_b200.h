@@ -38,8 +38,13 @@ enum {
  *   FP32   : fp32 SIMT FMA everywhere (the reference's own precision, DTYPE "float32").
  *   BF16X3 : tcgen05 tensor cores, every operand split into bf16 hi+lo, 3 MMAs per product,
  *            fp32 accumulate in TMEM — fp32-grade results (rel. error ~1e-5).
- *   BF16   : tcgen05 tensor cores, single bf16 pass, fp32 accumulate (stated tolerance 2e-2). */
-enum { VETO_PREC_FP32 = 0, VETO_PREC_BF16X3 = 1, VETO_PREC_BF16 = 2 };
+ *   BF16   : tcgen05 tensor cores, single bf16 pass, fp32 accumulate (stated tolerance 3e-2).
+ *   F16C8  : tcgen05 tensor cores, ONE fp16 product (kind::f16) plus the two first-order rounding corrections as one
+ *            e4m3 product over 2K (kind::f8f6f4, twice the rate): 2 bf16-MMA equivalents instead of BF16X3's 3,
+ *            rel. error ~1e-4 (bar 1e-3).  Inference forward of the encoder; the per-box patch projections and the
+ *            whole training step run as BF16X3.  Operand ranges |activation| < 3584, |weight| < 32 (saturating).
+ *   F16    : single fp16 product (stated tolerance 5e-3); training runs as BF16. */
+enum { VETO_PREC_FP32 = 0, VETO_PREC_BF16X3 = 1, VETO_PREC_BF16 = 2, VETO_PREC_F16C8 = 3, VETO_PREC_F16 = 4 };
 
 typedef void* veto_stream_t; /* cudaStream_t */
 

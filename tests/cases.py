@@ -46,6 +46,21 @@ CASES = {
 }
 
 
+# Full-size fixtures at the BASELINE.json sizes: compared with the reference's outputs only (the CPU
+# oracle is not re-run on them at test time: the reference itself needed minutes).  `row_stride` / `feat_stride`: the
+# fixture keeps every row_stride-th logit row (argmax labels of ALL rows) and every feat_stride-th ROI channel.
+FULL_CASES = {
+    # BASELINE.json configs[3]: VETOPredictor_MEET PredCls, GQA 201 / 101, divide4 group heads, batch 16 x 20 boxes = 6080 pairs
+    "meet_gqa_full": dict(predictor="VETOPredictor_MEET", mode="predcls", dataset="GQA", n_boxes=[20] * 16,
+                          batch_seed=21, weight_seed=14, spread=True, row_stride=4, feat_stride=64),
+}
+
+# BASELINE.json configs[1]: the training step at IMS_PER_BATCH 12 x 20 GT boxes = 4560 pairs (dropout p = 0 for parity)
+FULL_TRAIN_CASES = {
+    "train_predcls_full": dict(predictor="VETOPredictor", mode="predcls", dataset="VG", n_boxes=[20] * 12,
+                               batch_seed=22, weight_seed=16, spread=True, label_seed=74, fg_per_image=10),
+}
+
 # Training-step fixtures (tests/golden/make_golden.py run_train_case): the reference's VETOPredictor in train() mode
 # with every nn.Dropout set to p = 0 (module attributes), all ordered pairs per image as gtbox_relsample yields them
 # under the 1024-pair cap, seeded predicate labels; loss.backward() through the reference's own autograd.

@@ -72,14 +72,20 @@ def run_case(ns, name, c):
     out["weight_digest"] = np.array(digest([sd[k] for k in sorted(sd)]))
     out["pairs"] = np.concatenate([p.numpy() for p in pairs])
     out["pair_counts"] = np.array([len(p) for p in pairs])
-    out["x2d_sub"] = x2d.numpy()[:, ::16].copy()
-    out["d2d_sub"] = d2d.numpy()[:, ::16].copy()
+    fs = c.get("feat_stride", 16)
+    out["x2d_sub"] = x2d.numpy()[:, ::fs].copy()
+    out["d2d_sub"] = d2d.numpy()[:, ::fs].copy()
     out["x2d_sum"] = x2d.numpy().sum(axis=(1, 2, 3), dtype=np.float64)
     out["d2d_sum"] = d2d.numpy().sum(axis=(1, 2, 3), dtype=np.float64)
     out["obj_dists_argmax"] = np.concatenate([o.numpy().argmax(1) for o in obj_d])
     if meet:
+        rs = c.get("row_stride", 1)
         for k, v in rel_d.items():
-            out["logits_" + k] = v.numpy()
+            out["logits_" + k] = v.numpy()[::rs].copy()
+            if rs > 1:      # full-size case: every rs-th logit row, the argmax label (classes 1..) of every row
+                out["argmax_" + k] = v.numpy()[:, 1:].argmax(1).astype(np.int16)
+                top2 = np.sort(v.numpy()[:, 1:], 1)[:, -2:]
+                out["margin_" + k] = (top2[:, 1] - top2[:, 0]).astype(np.float32)
         out["incre_idx_list"] = np.array(incre)
         if c["mode"] == "predcls" and batch["B"] == 1 and c.get("expert_group"):
             # EXPERT_GROUP voting branch (inference.py:93-283), both voting rules on the same logits
@@ -503,14 +509,15 @@ def run_depth_backbone(name="depth_backbone", batch=2, height=70, width=101):
 
 
 def main():
-    from tests.cases import DETECT_SAMPLE_CASES, EVAL_CASES, MEET_TRAIN_CASES, RELSAMPLE_CASES, TRAIN_CASES
+    from tests.cases import (DETECT_SAMPLE_CASES, EVAL_CASES, FULL_CASES, FULL_TRAIN_CASES, MEET_TRAIN_CASES,
+                             RELSAMPLE_CASES, TRAIN_CASES)
     ns = ref_shim.load()
     only = sys.argv[1:]
-    for name, c in CASES.items():
+    for name, c in list(CASES.items()) + list(FULL_CASES.items()):
         if only and name not in only:
             continue
         run_case(ns, name, c)
-    for name, c in TRAIN_CASES.items():
+    for name, c in list(TRAIN_CASES.items()) + list(FULL_TRAIN_CASES.items()):
         if only and name not in only:
             continue
         run_train_case(ns, name, c)

@@ -18,7 +18,7 @@ import pytest
 import torch
 
 from tests import harness as H
-from tests.cases import TRAIN_CASES, load_golden
+from tests.cases import FULL_TRAIN_CASES, TRAIN_CASES, load_golden
 from tests.train_util import check_against_golden, grad_error, oracle_train_step, train_case_inputs
 from veto_b200 import config as vcfg
 from veto_b200 import ops, registry, synth
@@ -107,6 +107,32 @@ def test_train_step_matches_oracle_and_reference(name, precision):
     assert np.allclose(H.np_(bn.running_mean), g["running_mean"], rtol=1e-5)
     assert np.allclose(H.np_(bn.running_var), g["running_var"], rtol=1e-5)
     assert int(bn.num_batches_tracked) == int(g["num_batches_tracked"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_train_step_full_size_matches_reference(precision):
+    """BASELINE.json configs[1] at its full size — IMS_PER_BATCH 12 x 20 GT boxes = 4560 pairs, the size the training
+    throughput is quoted on (M = 86 640 token rows: the mixed-width weight-gradient tiles, the split-K decisions and the
+    full tile schedule) — against the loss and the gradient summaries (norm + 64 samples of every parameter gradient, of
+    the ROI depth features and of the depth feature map behind the ROIAlign backward) the unmodified reference produced
+    (tests/golden/train_predcls_full.npz)."""
+    name = "train_predcls_full"
+    c = FULL_TRAIN_CASES[name]
+    g = load_golden(name)
+    batch, sd, pairs, labels = train_case_inputs(c)
+    assert sum(len(p) for p in pairs) == 4560 and np.array_equal(np.concatenate(labels), g["rel_labels"])
+    mine = _run_train(c, precision, batch, sd, pairs, labels)
+    tol = GRAD_TOL[precision]
+    assert abs(mine["loss"] - float(g["rel_loss"])) <= 2 * LOSS_TOL[precision] * abs(float(g["rel_loss"]))
+    assert mine["no_grad"] == sorted(str(k) for k in g["no_grad"])
+    grads = dict(mine["grads"])
+    grads["roi_depth"] = mine["g_roi_depth"]
+    grads["depth_features"] = mine["g_depth_map"]
+    worst = check_against_golden(grads, g, 2 * tol)
+    _report(f"{name} {precision}", sorted(worst.items(), key=lambda kv: -kv[1])[:12])
+    bn = mine["pred"].pos_embed[0]
+    assert np.allclose(H.np_(bn.running_mean), g["running_mean"], rtol=1e-5)
+    assert np.allclose(H.np_(bn.running_var), g["running_var"], rtol=1e-5)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])

@@ -41,6 +41,28 @@ def test_inputs_reproduce(case):
     assert _digest([sd[k] for k in sorted(sd)]) == str(g["weight_digest"])
 
 
+@pytest.mark.parametrize("name", ["meet_gqa_full", "train_predcls_full"])
+def test_full_size_fixtures_reproduce_and_pin_the_gather(name):
+    """The BASELINE-size fixtures (configs[3] B = 16 GQA, configs[1] 12 x 20 training step): the seeded inputs / weights
+    regenerate to the digests the reference run recorded, pairs are the reference's, and (configs[3]) the C ROIAlign
+    oracle reproduces the stored ROI feature channels bit-exactly.  The logits / gradients of these fixtures are compared
+    on the GPU only (the reference itself needed minutes for them)."""
+    from tests.cases import FULL_CASES, FULL_TRAIN_CASES
+    c = FULL_CASES.get(name) or FULL_TRAIN_CASES[name]
+    g = load_golden(name)
+    batch = case_batch(c)
+    assert _digest(batch["feats"] + [batch["depth"]] + batch["boxes"] + batch["labels"]) == str(g["input_digest"])
+    sd = case_state(c)
+    assert _digest([sd[k] for k in sorted(sd)]) == str(g["weight_digest"])
+    pairs = O.prepare_test_pairs(batch["n_boxes"])
+    assert [len(p) for p in pairs] == list(g["pair_counts"])
+    if "pairs" in g.files:
+        assert np.array_equal(np.concatenate(pairs), g["pairs"])
+        x2d, d2d = O.pooler_forward(batch["feats"], batch["depth"], batch["boxes"])
+        fs = c["feat_stride"]
+        assert np.array_equal(x2d[:, ::fs], g["x2d_sub"]) and np.array_equal(d2d[:, ::fs], g["d2d_sub"])
+
+
 def test_pairs_bit_exact(case):
     name, c, g, batch = case
     pairs = _pairs(c, batch)

@@ -147,17 +147,18 @@ extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, 
         // one launch re-splits every GEMM weight into its bf16 hi (+ lo) operand arrays
         SplitJob jobs[kMaxSplitJobs];
         int nj = 0;
-        auto split = [&](const float* src, size_t hi, size_t lo, size_t n) {
-            jobs[nj++] = SplitJob{src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n};
+        auto split = [&](const float* src, size_t hi, size_t lo, size_t n, int fmt = FMT_BF16) {
+            jobs[nj++] = SplitJob{src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n, fmt};
         };
+        const int efmt = prec_encoder_fmt(cfg->precision);   // encoder weights in the mode's operand format
         split((const float*)(P + L.w_d2), L.d2_hi, L.d2_lo, (size_t)2 * kDimDepth * kPatchVec);
         split((const float*)(P + L.w_v2), L.v2_hi, L.v2_lo, (size_t)2 * kDimRgb * kPatchVec);
         for (int l = 0; l < cfg->layers; ++l) {
             VETO_REQUIRE(w->qkv_w[l] && w->out_w[l] && w->ff1_w[l] && w->ff2_w[l], VETO_ERR_ARG, "layer %d weights missing", l);
-            split(w->qkv_w[l], L.qkv_hi[l], L.qkv_lo[l], (size_t)3 * kDim * kDim);
-            split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim);
-            split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim);
-            split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp);
+            split(w->qkv_w[l], L.qkv_hi[l], L.qkv_lo[l], (size_t)3 * kDim * kDim, efmt);
+            split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim, efmt);
+            split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim, efmt);
+            split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp, efmt);
         }
         if ((rc = pack_split_bf16_multi(jobs, nj, s))) return rc;
     }
@@ -236,8 +237,8 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
     for (int64_t r0 = 0; r0 < in->n_pairs; r0 += W.chunk) {
         const int64_t rc_pairs = (in->n_pairs - r0 < W.chunk) ? (in->n_pairs - r0) : W.chunk;
         const int M = (int)(rc_pairs * kTokens);
-        ActBuf xn = act_at(B, W.xn, prec, (size_t)M * kDim);
-        ActBuf hb = act_at(B, W.h, prec, (size_t)M * kMlp);
+        ActBuf xn = enc_act_at(B, W.xn, prec, (size_t)M * kDim);
+        ActBuf hb = enc_act_at(B, W.h, prec, (size_t)M * kMlp);
         set_tag(TAG_TOKENS);
         if ((rc = build_tokens(ts, in->subj + r0, in->obj + r0, rc_pairs, x, s))) return rc;
         if (out->tokens)
@@ -306,7 +307,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             eq.ldc = kDim;
             WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
             if ((rc = linear(prec, xn, kTokens * kDim, wq, R, kDim, kDim, eq, s))) return rc;
-            ActBuf ao = act_at(B, W.xn, prec, (size_t)R * kDim);  // xn is free once K, V and q exist
+            ActBuf ao = enc_act_at(B, W.xn, prec, (size_t)R * kDim);  // xn is free once K, V and q exist
             set_tag(TAG_ATT);
             if ((rc = attention_cls(q_cls, qkv, rc_pairs, ao.out(), s))) return rc;
             GemmEpilogue e2;
@@ -318,10 +319,10 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             WRef wo{w->out_w[l], bf(P, L.out_hi[l]), bf(P, L.out_lo[l])};
             set_tag(TAG_OUT);
             if ((rc = linear(prec, ao, kDim, wo, R, kDim, kDim, e2, s))) return rc;
-            ActBuf xn_cls = act_at(B, W.xn, prec, (size_t)R * kDim);
+            ActBuf xn_cls = enc_act_at(B, W.xn, prec, (size_t)R * kDim);
             set_tag(TAG_LN);
             if ((rc = layernorm_rows(x_cls, kDim, w->ln2_w[l], w->ln2_b[l], R, xn_cls.out(), s))) return rc;
-            ActBuf h_cls = act_at(B, W.h, prec, (size_t)R * kMlp);
+            ActBuf h_cls = enc_act_at(B, W.h, prec, (size_t)R * kMlp);
             GemmEpilogue e3;
             e3.bias = w->ff1_b[l];
             e3.act = ACT_GELU;
@@ -418,19 +419,26 @@ extern "C" int veto_test_gemm(const float* a_dev, const float* w_dev, const floa
     __nv_bfloat16* w_hi = a_lo + ae;
     __nv_bfloat16* w_lo = w_hi + we;
     int rc;
+    const bool c8 = prec_encoder_fmt(precision) == FMT_F16C8;
     if (!reuse) {
-        if ((rc = pack_split_bf16(a_dev, a_hi, a_lo, ae, s))) return rc;
-        if ((rc = pack_split_bf16(w_dev, w_hi, w_lo, we, s))) return rc;
+        if (c8) {
+            SplitJob jobs[2] = {SplitJob{a_dev, a_hi, a_lo, ae, FMT_F16C8_ACT}, SplitJob{w_dev, w_hi, w_lo, we, FMT_F16C8}};
+            if ((rc = pack_split_bf16_multi(jobs, 2, s))) return rc;
+        } else {
+            if ((rc = pack_split_bf16(a_dev, a_hi, a_lo, ae, s))) return rc;
+            if ((rc = pack_split_bf16(w_dev, w_hi, w_lo, we, s))) return rc;
+        }
     }
     if (split_out) {
         ep.out.f32 = nullptr;
         ep.out.hi = w_lo + we;
-        ep.out.lo = precision == VETO_PREC_BF16X3 ? ep.out.hi + ce : nullptr;
+        ep.out.lo = prec_two_arrays(precision) ? ep.out.hi + ce : nullptr;
+        ep.out.fmt = prec_encoder_fmt(precision);
     }
     GemmOperand A, W;
     A.hi = a_hi; A.lo = a_lo;
     W.hi = w_hi; W.lo = w_lo;
-    return gemm_tc_auto(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+    return gemm_tc_auto(A, W, M, N, K, prec_encoder_passes(precision), ep, s);
 }
 
 extern "C" int veto_test_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, float* y_dev, int64_t rows,

@@ -27,9 +27,20 @@ static inline int check_config(const veto_config* c) {
                  VETO_MAX_LAYERS);
     VETO_REQUIRE(c->num_obj >= 2 && c->num_obj <= 512 && c->num_out >= 1, VETO_ERR_ARG, "bad num_obj=%d / num_out=%d",
                  c->num_obj, c->num_out);
-    VETO_REQUIRE(c->precision >= VETO_PREC_FP32 && c->precision <= VETO_PREC_BF16, VETO_ERR_ARG, "bad precision %d",
+    VETO_REQUIRE(c->precision >= VETO_PREC_FP32 && c->precision <= VETO_PREC_F16, VETO_ERR_ARG, "bad precision %d",
                  c->precision);
     return VETO_OK;
+}
+
+// Storage class of a precision mode: which arrays exist next to the fp32 ones.  f16c8 stores two 2-byte-per-element
+// arrays like bf16x3, f16 one like bf16 — buffer sizes and offsets depend on this only, not on the element encoding.
+static inline bool prec_two_arrays(int precision) { return precision == VETO_PREC_BF16X3 || precision == VETO_PREC_F16C8; }
+// operand format of the ENCODER GEMMs in a precision mode (the per-box patch projections stay bf16 / bf16x3)
+static inline int prec_encoder_fmt(int precision) {
+    return (precision == VETO_PREC_F16C8 || precision == VETO_PREC_F16) ? FMT_F16C8 : FMT_BF16;
+}
+static inline int prec_encoder_passes(int precision) {
+    return precision == VETO_PREC_BF16X3 ? TC_BF16X3 : precision == VETO_PREC_F16C8 ? TC_F16C8 : precision == VETO_PREC_F16 ? TC_F16 : TC_BF16;
 }
 
 struct PackedLayout {
@@ -53,7 +64,7 @@ static inline PackedLayout packed_layout(const veto_config& c) {
     L.b_v2 = k.take(sizeof(float) * 2 * kDimRgb);
     L.clspos = k.take(sizeof(float) * kDim);
     if (c.precision != VETO_PREC_FP32) {
-        const bool lo = c.precision == VETO_PREC_BF16X3;
+        const bool lo = prec_two_arrays(c.precision);
         const size_t e = sizeof(__nv_bfloat16);
         L.d2_hi = k.take(e * 2 * kDimDepth * kPatchVec);
         L.d2_lo = lo ? k.take(e * 2 * kDimDepth * kPatchVec) : 0;
@@ -79,12 +90,13 @@ struct ActBuf {
     float* f32 = nullptr;
     __nv_bfloat16* hi = nullptr;
     __nv_bfloat16* lo = nullptr;
-    ActOut out() const { return ActOut{f32, hi, lo}; }
+    int fmt = FMT_BF16;
+    ActOut out() const { return ActOut{f32, hi, lo, fmt}; }
 };
 
 static inline size_t act_bytes(int precision, size_t elems) {
     if (precision == VETO_PREC_FP32) return elems * sizeof(float);
-    if (precision == VETO_PREC_BF16X3) return elems * 2 * sizeof(__nv_bfloat16);
+    if (prec_two_arrays(precision)) return elems * 2 * sizeof(__nv_bfloat16);
     return elems * sizeof(__nv_bfloat16);
 }
 
@@ -94,8 +106,14 @@ static inline ActBuf act_at(void* base, size_t off, int precision, size_t elems)
     if (precision == VETO_PREC_FP32) b.f32 = (float*)p;
     else {
         b.hi = (__nv_bfloat16*)p;
-        if (precision == VETO_PREC_BF16X3) b.lo = b.hi + elems;
+        if (prec_two_arrays(precision)) b.lo = b.hi + elems;
     }
+    return b;
+}
+// the same buffer as an operand of the encoder GEMMs (f16c8 / f16 modes store it in the f16c8 format)
+static inline ActBuf enc_act_at(void* base, size_t off, int precision, size_t elems) {
+    ActBuf b = act_at(base, off, precision, elems);
+    b.fmt = prec_encoder_fmt(precision);
     return b;
 }
 
@@ -112,7 +130,9 @@ static inline int linear(int precision, const ActBuf& a, int lda, const WRef& w,
     A.hi = a.hi; A.lo = a.lo;
     A.ld = lda;
     W.hi = w.hi; W.lo = w.lo;
-    return gemm_tc_auto(A, W, M, N, K, precision == VETO_PREC_BF16X3 ? 3 : 1, ep, s);
+    // a.fmt tells the box stage (bf16 operands in every tensor-core mode) from the encoder (format of the mode)
+    const int passes = a.fmt == FMT_F16C8 ? prec_encoder_passes(precision) : (prec_two_arrays(precision) ? TC_BF16X3 : TC_BF16);
+    return gemm_tc_auto(A, W, M, N, K, passes, ep, s);
 }
 
 static inline const __nv_bfloat16* bf(const void* base, size_t off) { return off ? (const __nv_bfloat16*)((const char*)base + off) : nullptr; }

@@ -276,17 +276,17 @@ attention_tc_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32
     }
 }
 
-bool g_attr_set = false;
+DeviceOnce g_attr_set;
 
 }  // namespace
 
 int attention_tc(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
     VETO_REQUIRE(out.hi || out.f32, VETO_ERR_ARG, "attention_tc: no output");
-    if (!g_attr_set) {
+    if (g_attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         VETO_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        g_attr_set = true;
+        g_attr_set.done();
     }
     const int64_t units = (n_seq + SEQ_PER_UNIT - 1) / SEQ_PER_UNIT * kHeads;
     const int grid = (int)(units < num_sms() ? units : num_sms());

@@ -58,6 +58,25 @@ __global__ void split_bf16_multi_kernel(const __grid_constant__ SplitJobs jobs) 
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(jb.src) + e);
         uint2 hi, lo;
+        if (jb.fmt == FMT_F16C8) {
+            // weight side of the f16c8 format: fp16(2048 w); bytes (e4m3(8 w), e4m3(8 r_w)) with r_w = 2048 w - fp16(2048 w)
+            const float4 ws = make_float4(v.x * kC8WScale, v.y * kC8WScale, v.z * kC8WScale, v.w * kC8WScale);
+            hi.x = f16x2_sat(ws.x, ws.y);
+            hi.y = f16x2_sat(ws.z, ws.w);
+            reinterpret_cast<uint2*>(jb.hi)[e] = hi;
+            if (jb.lo) {
+                const float2 a = f16x2_to_float(hi.x), b = f16x2_to_float(hi.y);
+                uint8_t* p8 = (uint8_t*)jb.lo + c8_byte(4 * e);
+                *(uint32_t*)p8 = e4m3x2(v.x * kC8WVal, v.y * kC8WVal) | (e4m3x2(v.z * kC8WVal, v.w * kC8WVal) << 16);
+                *(uint32_t*)(p8 + 64) = e4m3x2((ws.x - a.x) * kC8WRes, (ws.y - a.y) * kC8WRes) |
+                                        (e4m3x2((ws.z - b.x) * kC8WRes, (ws.w - b.y) * kC8WRes) << 16);
+            }
+            continue;
+        }
+        if (jb.fmt == FMT_F16C8_ACT) {   // activation side (test hook: production activations come out of the kernels' epilogues)
+            store_act4_f16c8(jb.hi, jb.lo, 4 * e, v);
+            continue;
+        }
         split_pair(v.x, v.y, hi.x, lo.x);
         split_pair(v.z, v.w, hi.y, lo.y);
         reinterpret_cast<uint2*>(jb.hi)[e] = hi;

@@ -2,11 +2,34 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "../../include/veto_b200.h"
+
+namespace veto {
+// One-time per-DEVICE setup guard: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only,
+// and one process may drive several GPUs.  Usage: static DeviceOnce once; if (once.pending()) { ...set...; once.done(); }
+struct DeviceOnce {
+    unsigned long long mask[2] = {0ull, 0ull};   // devices 0..127; racing threads at worst repeat the (idempotent) setup
+    static int device() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return d & 127;
+    }
+    bool pending() const {
+        const int d = device();
+        return ((mask[d >> 6] >> (d & 63)) & 1ull) == 0ull;
+    }
+    void done() {
+        const int d = device();
+        __atomic_fetch_or(&mask[d >> 6], 1ull << (d & 63), __ATOMIC_RELAXED);
+    }
+};
+}  // namespace veto
 
 namespace veto {
 
@@ -59,10 +82,14 @@ void set_tag(int tag);
 // F32     : one fp32 array
 // BF16    : one bf16 array
 // BF16X2  : bf16 hi array followed (at `lo`) by a bf16 lo array, value ~= hi + lo (16 mantissa bits)
+// F16C8   : (fmt = FMT_F16C8) `hi` holds fp16 values, `lo` holds two e4m3 bytes per element (see the f16c8 block below);
+//           same byte counts as BF16X2, so buffers and offsets do not depend on the format
+enum { FMT_BF16 = 0, FMT_F16C8 = 1, FMT_F16C8_ACT = 2 };   // _ACT: pack jobs only (stages.cuh SplitJob)
 struct ActOut {
     float* f32 = nullptr;
     __nv_bfloat16* hi = nullptr;
     __nv_bfloat16* lo = nullptr;
+    int fmt = FMT_BF16;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -111,6 +138,70 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- f16c8 operand format (precision mode VETO_PREC_F16C8: one fp16 product + fp8 first-order corrections) ----
+// A Linear y = a . w is evaluated on the tensor cores as
+//     2^-11 * [ fp16(a) . fp16(2048 w)                        kind::f16,    K = 16 per instruction
+//             + e4m3(256 r_a) . e4m3(8 w) + e4m3(a / 8) . e4m3(8 r_w) ]    kind::f8f6f4, K = 32 per instruction (2x rate)
+// with r_a = a - fp16(a) and r_w = 2048 w - fp16(2048 w): the fp16 product carries 11 significant bits per operand and
+// the two e4m3 products restore the first-order rounding residuals to ~4 more bits — 2 bf16-MMA equivalents instead of
+// the 3 of the bf16x3 split, measured error 1e-4 of the logit range (tools/precision_study.py; bar 1e-3).  All scale
+// factors are powers of two (exact).  Ranges: |a| < 3584 (e4m3(a/8) saturates at 448), |w| < 32 (fp16(2048 w)); both
+// saturate instead of overflowing.
+// Storage of an [rows, K] operand (K % 64 == 0): `hi` = fp16 [rows, K]; `lo` = bytes [rows, 2K]: for every 64-element
+// K block, 64 bytes of the first e4m3 stream followed by 64 bytes of the second — activations (residual, value),
+// weights (value, residual) — so that one 128-byte row of the K-major SWIZZLE_128B tile of A meets the matching row of W
+// and the correction is ONE fp8 GEMM over 2K.  Byte-compatible with the bf16 hi / lo arrays ([rows, K] 2-byte elements).
+constexpr float kC8ActRes = 256.f, kC8ActVal = 0.125f, kC8WScale = 2048.f, kC8WVal = 8.f, kC8WRes = 8.f;
+constexpr float kC8AccScale = 1.f / 2048.f;
+
+__device__ __forceinline__ uint32_t f16x2_sat(float x0, float x1) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(x0, -65504.f), 65504.f), fminf(fmaxf(x1, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 f16x2_to_float(uint32_t h) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ uint32_t e4m3x2(float x0, float x1) {   // x0 in the low byte; saturating
+    return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(x0, x1), __NV_SATFINITE, __NV_E4M3);
+}
+// byte offset inside the `lo` array of the first-stream byte of element `off` (flat index row * K + k, K % 64 == 0);
+// the second-stream byte sits 64 bytes further
+__device__ __forceinline__ size_t c8_byte(size_t off) { return ((off >> 6) << 7) + (off & 63); }
+
+// two consecutive activations (off even) -> fp16 pair in hi, (residual, value) e4m3 pairs in lo (may be NULL: f16 mode)
+__device__ __forceinline__ void store_act2_f16c8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float x0, float x1) {
+    const uint32_t h = f16x2_sat(x0, x1);
+    *(uint32_t*)(hi + off) = h;
+    if (lo) {
+        const float2 hf = f16x2_to_float(h);
+        uint8_t* p = (uint8_t*)lo + c8_byte(off);
+        *(uint16_t*)p = (uint16_t)e4m3x2((x0 - hf.x) * kC8ActRes, (x1 - hf.y) * kC8ActRes);
+        *(uint16_t*)(p + 64) = (uint16_t)e4m3x2(x0 * kC8ActVal, x1 * kC8ActVal);
+    }
+}
+__device__ __forceinline__ void store_act4_f16c8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float4 v) {
+    uint2 h;
+    h.x = f16x2_sat(v.x, v.y);
+    h.y = f16x2_sat(v.z, v.w);
+    *(uint2*)(hi + off) = h;
+    if (lo) {
+        const float2 a = f16x2_to_float(h.x), b = f16x2_to_float(h.y);
+        uint8_t* p = (uint8_t*)lo + c8_byte(off);
+        *(uint32_t*)p = e4m3x2((v.x - a.x) * kC8ActRes, (v.y - a.y) * kC8ActRes) |
+                        (e4m3x2((v.z - b.x) * kC8ActRes, (v.w - b.y) * kC8ActRes) << 16);
+        *(uint32_t*)(p + 64) = e4m3x2(v.x * kC8ActVal, v.y * kC8ActVal) | (e4m3x2(v.z * kC8ActVal, v.w * kC8ActVal) << 16);
+    }
+}
+__device__ __forceinline__ void store_act1_f16c8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float x) {
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    *((__half*)hi + off) = h;
+    if (lo) {
+        uint8_t* p = (uint8_t*)lo + c8_byte(off);
+        p[0] = (uint8_t)(e4m3x2((x - __half2float(h)) * kC8ActRes, 0.f) & 0xffu);
+        p[64] = (uint8_t)(e4m3x2(x * kC8ActVal, 0.f) & 0xffu);
+    }
 }
 
 // ---- counter-based dropout mask (training branch) ----
@@ -182,6 +273,11 @@ struct GemmEpilogue {
     int split_k = 1;                  // > 1: partial products over K slices, slice s written at out.f32 + s * split_stride
     size_t split_stride = 0;          //      (no bias / act / residual; reduce with splitk_reduce)
 };
+
+// `passes` of the tensor-core GEMMs: the operand format / product scheme
+//   1 = bf16 single product, 3 = bf16x3 (hi*hi + lo*hi + hi*lo), 2 = f16c8 (fp16 product + one fp8 correction GEMM over
+//   2K, see the f16c8 block above; gemm_tc2 only), 4 = fp16 single product (hi arrays of the f16c8 format; gemm_tc2 only)
+enum { TC_BF16 = 1, TC_F16C8 = 2, TC_BF16X3 = 3, TC_F16 = 4 };
 
 // A operand of a GEMM: fp32 (SIMT path) or bf16 hi[/lo] (tensor-core path); W likewise.
 struct GemmOperand {

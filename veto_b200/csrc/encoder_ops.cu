@@ -21,7 +21,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // flight for HBM (profiles/r1_rows_ncu.txt: the first version sat at 65 % of copy bandwidth with 24 warps per SM).
 __global__ void __launch_bounds__(256, 4)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
-                 int64_t rows, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                 int64_t rows, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int fmt) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -69,10 +69,14 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
                 const size_t e = o + 2 * (lane + 32 * j);
                 if (out_f32) *(float2*)(out_f32 + e) = y;
                 if (out_hi) {
-                    uint32_t hh, ll;
-                    split_pair(y.x, y.y, hh, ll);
-                    *(uint32_t*)(out_hi + e) = hh;
-                    if (out_lo) *(uint32_t*)(out_lo + e) = ll;
+                    if (fmt == FMT_F16C8) {
+                        store_act2_f16c8(out_hi, out_lo, e, y.x, y.y);
+                    } else {
+                        uint32_t hh, ll;
+                        split_pair(y.x, y.y, hh, ll);
+                        *(uint32_t*)(out_hi + e) = hh;
+                        if (out_lo) *(uint32_t*)(out_lo + e) = ll;
+                    }
                 }
             }
         }
@@ -375,7 +379,7 @@ constexpr int ATT2_SMEM = ATT2_PAIRS * ATT2_ITEM_FLOATS * (int)sizeof(float);  /
 template <bool SPLIT>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, __nv_bfloat16* out_hi,
-                      __nv_bfloat16* out_lo) {
+                      __nv_bfloat16* out_lo, int fmt) {
     extern __shared__ float4 att_smem[];
     constexpr int LD = 3 * kDim;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -548,10 +552,14 @@ attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f
                             const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 8 * (3 * blk + j) + 2 * t;
                             if (out_f32) *(float2*)(out_f32 + o) = make_float2(v0, v1);
                             if (out_hi) {
-                                uint32_t hh, ll;
-                                split_pair(v0, v1, hh, ll);
-                                *(uint32_t*)(out_hi + o) = hh;
-                                if (out_lo) *(uint32_t*)(out_lo + o) = ll;
+                                if (fmt == FMT_F16C8) {
+                                    store_act2_f16c8(out_hi, out_lo, o, v0, v1);
+                                } else {
+                                    uint32_t hh, ll;
+                                    split_pair(v0, v1, hh, ll);
+                                    *(uint32_t*)(out_hi + o) = hh;
+                                    if (out_lo) *(uint32_t*)(out_lo + o) = ll;
+                                }
                             }
                         }
                     }
@@ -567,7 +575,7 @@ attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f
 // warp reductions, and lane L accumulates output dims L, L+32, L+64 with p_j broadcast by shuffle.
 __global__ void __launch_bounds__(256)
 attention_cls_kernel(const float* __restrict__ q_cls, const float* __restrict__ qkv, int64_t n_seq, float* out_f32,
-                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int fmt) {
     constexpr int LD = 3 * kDim;
     const int lane = threadIdx.x & 31;
     const float scale = 0.10206207261596575f;
@@ -608,10 +616,14 @@ attention_cls_kernel(const float* __restrict__ q_cls, const float* __restrict__ 
         for (int k = 0; k < 3; ++k) {
             if (out_f32) out_f32[o + 32 * k] = acc[k];
             if (out_hi) {
-                __nv_bfloat16 hh, ll;
-                split_bf16(acc[k], hh, ll);
-                out_hi[o + 32 * k] = hh;
-                if (out_lo) out_lo[o + 32 * k] = ll;
+                if (fmt == FMT_F16C8) {
+                    store_act1_f16c8(out_hi, out_lo, o + 32 * k, acc[k]);
+                } else {
+                    __nv_bfloat16 hh, ll;
+                    split_bf16(acc[k], hh, ll);
+                    out_hi[o + 32 * k] = hh;
+                    if (out_lo) out_lo[o + 32 * k] = ll;
+                }
             }
         }
     }
@@ -625,7 +637,7 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
     const int64_t blocks_needed = (rows + 15) / 16;  // 8 warps x 2 rows per block iteration
     const int64_t cap = (int64_t)num_sms() * 4;
     const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
-    layernorm_kernel<<<grid, 256, 0, s>>>(x, ldx, w, b, rows, out.f32, out.hi, out.lo);
+    layernorm_kernel<<<grid, 256, 0, s>>>(x, ldx, w, b, rows, out.f32, out.hi, out.lo, out.fmt);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
@@ -644,24 +656,25 @@ int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream
         static int one_warp = -1;
         if (one_warp < 0) one_warp = getenv("VETO_ATTENTION_ONE_WARP") ? 1 : 0;  // diagnosis: the one-warp-per-item kernel
         if (!one_warp) {
-            static bool attr2_set = false;
-            if (!attr2_set) {
+            static DeviceOnce attr2_set;
+            if (attr2_set.pending()) {
                 VETO_CUDA(cudaFuncSetAttribute(attention_mma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
                 VETO_CUDA(cudaFuncSetAttribute(attention_mma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
-                attr2_set = true;
+                attr2_set.done();
             }
             const int64_t blocks2 = (n_seq * kHeads + ATT2_PAIRS - 1) / ATT2_PAIRS;
             const int grid2 = (int)(blocks2 < (int64_t)num_sms() ? blocks2 : (int64_t)num_sms());
-            if (out.lo) attention_mma2_kernel<true><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
-            else attention_mma2_kernel<false><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo);
+            // the f16 mode (fp16 output, no residual bytes) keeps the split products INSIDE the attention core
+            if (out.lo || out.fmt == FMT_F16C8) attention_mma2_kernel<true><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo, out.fmt);
+            else attention_mma2_kernel<false><<<grid2, ATT2_THREADS, ATT2_SMEM, s>>>(qkv, n_seq, out.f32, out.hi, out.lo, out.fmt);
             VETO_LAUNCH_CHECK();
             return VETO_OK;
         }
-        static bool mma_attr_set = false;
-        if (!mma_attr_set) {
+        static DeviceOnce mma_attr_set;
+        if (mma_attr_set.pending()) {
             VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));
             VETO_CUDA(cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MMA_SMEM));
-            mma_attr_set = true;
+            mma_attr_set.done();
         }
         const int64_t blocks = (n_seq * kHeads + ATT_MMA_WARPS - 1) / ATT_MMA_WARPS;
         const int64_t capb = (int64_t)num_sms();  // one 187 KB CTA per SM
@@ -671,10 +684,10 @@ int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream
         VETO_LAUNCH_CHECK();
         return VETO_OK;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        attr_set = true;
+        attr_set.done();
     }
     const int64_t cap = (int64_t)num_sms() * 2;
     const int grid = (int)(n_seq < cap ? n_seq : cap);
@@ -687,7 +700,7 @@ int attention_cls(const float* q_cls, const float* qkv, int64_t n_seq, const Act
     if (n_seq <= 0) return VETO_OK;
     const int64_t blocks = (n_seq * kHeads + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
-    attention_cls_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(q_cls, qkv, n_seq, out.f32, out.hi, out.lo);
+    attention_cls_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(q_cls, qkv, n_seq, out.f32, out.hi, out.lo, out.fmt);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

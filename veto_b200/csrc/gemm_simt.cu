@@ -237,10 +237,10 @@ int launch_skinny(const float* A, int lda, const float* W, int M, int N, int K, 
     int KT = (SK_SMEM_FLOATS / NP) & ~3;
     if (KT > K) KT = (K + 3) & ~3;
     const int smem = (KT * NP + SK_WARPS * KT) * (int)sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set.done();
     }
     int grid = (M + SK_WARPS - 1) / SK_WARPS;
     if (grid > num_sms()) grid = num_sms();

@@ -339,7 +339,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::mutex g_mu;
-bool g_inited = false;
+DeviceOnce g_inited;
 
 struct MapKey {
     const void* p;
@@ -354,12 +354,12 @@ struct MapKeyHash {
         return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7) ^ k.box_rows;
     }
 };
-std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+// per host thread: no lock on the launch path (descriptors are pure functions of their key)
+thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // bf16 row-major [rows, cols] with row stride ld -> tiled map with a {64, box_rows} box and 128-byte swizzle
 int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
     MapKey key{p, rows, cols, ld, box_rows};
-    std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) {
         *out = it->second;
@@ -452,8 +452,8 @@ int launch_conv(const GemmOperand& A, const GemmOperand& W, int B, int Hin, int 
 }  // namespace
 
 int gemm_tc_init() {
+    if (!g_inited.pending()) return VETO_OK;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_inited) return VETO_OK;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -464,7 +464,7 @@ int gemm_tc_init() {
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kSmemBytes));
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::kConvSmemBytes));
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<64>::kConvSmemBytes));
-    g_inited = true;
+    g_inited.done();
     return VETO_OK;
 }
 

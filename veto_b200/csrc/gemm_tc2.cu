@@ -67,6 +67,8 @@ struct EpiParams {
     float* pre_f32;
     int res_mode;
     DropSpec drop;
+    int out_fmt;             // FMT_BF16 / FMT_F16C8: storage format of out_hi / out_lo
+    float acc_scale;         // accumulator scale (f16c8 / f16: 2^-11, the weights are stored times 2048)
     int ksplit;              // K slices (wgrad: tiny output, huge K); tiles enumerate (slice, m, n)
     int kb_per;              // K blocks per slice
     long long split_stride;  // elements between the partial outputs of consecutive slices
@@ -91,7 +93,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
-    const bool split = passes == 3;
+    const bool split = passes == TC_BF16X3 || passes == TC_F16C8;   // a stage holds hi and lo tiles of both operands
     const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
     const int num_stages = PIPE_BYTES / stage_bytes;  // 3 or 6
     const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
@@ -175,7 +177,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc_bf16 = make_idesc(2 * BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc_fmt0 = make_idesc_fmt0(2 * BLOCK_M, BLOCK_N);   // fp16 (kind::f16) / e4m3 (kind::f8f6f4)
+            const bool fp16_ops = passes == TC_F16C8 || passes == TC_F16;
+            const uint32_t idesc = fp16_ops ? idesc_fmt0 : idesc_bf16;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -196,10 +201,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         const uint32_t ko = k * UMMA_K * 2;
                         const uint64_t a_hi = make_smem_desc(sp + ko);
                         const uint64_t w_hi = make_smem_desc(sp + off_w_hi + ko);
-                        umma2_bf16(tmem_d, a_hi, w_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                        if (split) {
+                        umma2_bf16(tmem_d, a_hi, w_hi, idesc, (kb != kb0 || k != 0) ? 1u : 0u);   // kind::f16: bf16 or fp16 by idesc
+                        if (passes == TC_BF16X3) {
                             umma2_bf16(tmem_d, make_smem_desc(sp + off_a_lo + ko), w_hi, idesc, 1u);
                             umma2_bf16(tmem_d, a_hi, make_smem_desc(sp + off_w_lo + ko), idesc, 1u);
+                        } else if (passes == TC_F16C8) {
+                            // 32 bytes of the 128-byte e4m3 rows = 32 of the 2 x 64 correction terms of this K block
+                            umma2_f8(tmem_d, make_smem_desc(sp + off_a_lo + ko), make_smem_desc(sp + off_w_lo + ko), idesc_fmt0, 1u);
                         }
                     }
                     umma2_commit_both(&empty_bar[stage]);
@@ -279,7 +287,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
                     const int row = m0 + lr;
                     if (row < M && col < N) {
-                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        v.x = fmaf(v.x, ep.acc_scale, bias4.x); v.y = fmaf(v.y, ep.acc_scale, bias4.y);
+                        v.z = fmaf(v.z, ep.acc_scale, bias4.z); v.w = fmaf(v.w, ep.acc_scale, bias4.w);
                         const size_t off = (size_t)row * ep.ldc + col + split_off;
                         if (ep.pre_f32) *(float4*)(ep.pre_f32 + off) = v;
                         if (ep.res_mode == RES_GELU_GRAD) {
@@ -296,11 +305,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         }
                         if (ep.out_f32) *(float4*)(ep.out_f32 + off) = v;
                         if (ep.out_hi) {
-                            uint2 hh, ll;
-                            split_pair(v.x, v.y, hh.x, ll.x);
-                            split_pair(v.z, v.w, hh.y, ll.y);
-                            *(uint2*)(ep.out_hi + off) = hh;
-                            if (ep.out_lo) *(uint2*)(ep.out_lo + off) = ll;
+                            if (ep.out_fmt == FMT_F16C8) {
+                                store_act4_f16c8(ep.out_hi, ep.out_lo, off, v);
+                            } else {
+                                uint2 hh, ll;
+                                split_pair(v.x, v.y, hh.x, ll.x);
+                                split_pair(v.z, v.w, hh.y, ll.y);
+                                *(uint2*)(ep.out_hi + off) = hh;
+                                if (ep.out_lo) *(uint2*)(ep.out_lo + off) = ll;
+                            }
                         }
                     }
                 }
@@ -326,7 +339,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::mutex g_mu;
-bool g_inited = false;
+DeviceOnce g_inited;
 
 struct MapKey {
     const void* p;
@@ -341,11 +354,11 @@ struct MapKeyHash {
         return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7) ^ k.box_rows;
     }
 };
-std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+// per host thread: no lock on the launch path (descriptors are pure functions of their key)
+thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
     MapKey key{p, rows, cols, ld, box_rows};
-    std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) {
         *out = it->second;
@@ -369,8 +382,8 @@ int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, u
 }
 
 int init2() {
+    if (!g_inited.pending()) return VETO_OK;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_inited) return VETO_OK;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -378,7 +391,7 @@ int init2() {
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_inited = true;
+    g_inited.done();
     return VETO_OK;
 }
 
@@ -399,12 +412,15 @@ int gemm_tc2_slices(int K, int split_k) {
 int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, int passes, const GemmEpilogue& ep,
              cudaStream_t s) {
     if (M <= 0 || N <= 0) return VETO_OK;
-    VETO_REQUIRE(passes == 1 || passes == 3, VETO_ERR_ARG, "gemm_tc2: passes must be 1 or 3");
+    VETO_REQUIRE(passes >= TC_BF16 && passes <= TC_F16, VETO_ERR_ARG, "gemm_tc2: passes must be 1 .. 4 (common.cuh TC_*)");
     VETO_REQUIRE(gemm_tc2_supported(N, K) && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc2: N=%d must be a multiple of %d, K=%d of %d",
                  N, BLOCK_N, K, BLOCK_K);
     VETO_REQUIRE(ep.ldc % 4 == 0 && ep.ldr % 4 == 0 && A.ld % 8 == 0 && W.ld % 8 == 0, VETO_ERR_UNSUPPORTED,
                  "gemm_tc2: unaligned strides");
-    VETO_REQUIRE(A.hi && W.hi && (passes == 1 || (A.lo && W.lo)), VETO_ERR_ARG, "gemm_tc2: missing bf16 operand");
+    const bool two_arrays = passes == TC_BF16X3 || passes == TC_F16C8;
+    VETO_REQUIRE(A.hi && W.hi && (!two_arrays || (A.lo && W.lo)), VETO_ERR_ARG, "gemm_tc2: missing operand array");
+    VETO_REQUIRE(ep.out.fmt == FMT_BF16 || (ep.ldc % 64 == 0 && ep.split_k <= 1), VETO_ERR_ARG,
+                 "gemm_tc2: f16c8 outputs need ldc %% 64 == 0");
     int rc = init2();
     if (rc) return rc;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -413,7 +429,7 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     if ((rc = get_map(W.hi, N, K, ldw, HALF_N, &tw_hi))) return rc;
     ta_lo = ta_hi;
     tw_lo = tw_hi;
-    if (passes == 3) {
+    if (two_arrays) {   // the e4m3 byte pairs of f16c8 are addressed as 2-byte elements: the same tensor maps
         if ((rc = get_map(A.lo, M, K, lda, BLOCK_M, &ta_lo))) return rc;
         if ((rc = get_map(W.lo, N, K, ldw, HALF_N, &tw_lo))) return rc;
     }
@@ -428,8 +444,9 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / BLOCK_N) * ksplit;
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
+    const float acc_scale = (passes == TC_F16C8 || passes == TC_F16) ? kC8AccScale : 1.f;
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
-                ep.pre_f32, ep.res_mode, ep.drop, ksplit, kb_per, (long long)ep.split_stride};
+                ep.pre_f32, ep.res_mode, ep.drop, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride};
     gemm_tc2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
     VETO_LAUNCH_CHECK();
     return VETO_OK;

@@ -318,7 +318,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::mutex g_mu;
-bool g_inited = false;
+DeviceOnce g_inited;
 
 struct MapKey {
     const void* p;
@@ -330,12 +330,12 @@ struct MapKeyHash {
         return std::hash<const void*>()(k.p) ^ (k.rows * 0x9E3779B97F4A7C15ull) ^ (k.cols << 20) ^ (k.ld << 7);
     }
 };
-std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+// per host thread: no lock on the launch path (descriptors are pure functions of their key)
+thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // [rows, cols] row-major bf16 with row stride ld: boxes of 64 rows x 64 contiguous elements, 128-byte swizzle
 int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, CUtensorMap* out) {
     MapKey key{p, rows, cols, ld};
-    std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) {
         *out = it->second;
@@ -359,8 +359,8 @@ int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, C
 }
 
 int init_tn() {
+    if (!g_inited.pending()) return VETO_OK;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_inited) return VETO_OK;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     VETO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -368,7 +368,7 @@ int init_tn() {
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
     VETO_CUDA(cudaFuncSetAttribute(gemm_tn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_inited = true;
+    g_inited.done();
     return VETO_OK;
 }
 

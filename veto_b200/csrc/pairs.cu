@@ -254,11 +254,11 @@ extern "C" int veto_pairs_enumerate(const int32_t* n_boxes_host, int n_images, c
         }
         return VETO_OK;
     }
-    static bool attr_set = false;
+    static DeviceOnce attr_set;
     const int smem = kMaxCand * (int)(sizeof(unsigned long long) + sizeof(unsigned int));
-    if (!attr_set) {
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(pairs_filtered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.done();
     }
     pairs_filtered_kernel<<<n_images, 1024, smem, s>>>(d_n, d_boff, d_ooff, boxes_dev, scores_dev, require_overlap,
                                                       max_pairs, pairs_out_dev, counts_out_dev);

@@ -22,59 +22,11 @@ __device__ __forceinline__ float wsum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024)
-postprocess_kernel(const float* __restrict__ logits, int num_rel, const int64_t* __restrict__ pairs,
-                   const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off,
-                   const int32_t* __restrict__ box_off, int64_t* __restrict__ pairs_out, float* __restrict__ probs_out,
-                   int64_t* __restrict__ labels_out, float* __restrict__ triple_out) {
-    extern __shared__ unsigned long long keys[];  // [npow]
-    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
-    float* trip = (float*)(lab + kMaxRows);
-    const int b = blockIdx.x;
-    const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
-    if (rows <= 0) return;
-    if (rows > kMaxRows) {  // documented limit of the in-shared-memory sort (include/veto_b200.h)
-        if (threadIdx.x == 0) printf("veto_postprocess: image %d has %d rows > %d\n", b, rows, kMaxRows);
-        __trap();
-    }
-    const int boff = box_off[b];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int npow = 1;
-    while (npow < rows) npow <<= 1;
-
-    for (int q = wid; q < rows; q += nw) {
-        const float* lg = logits + (size_t)(r0 + q) * num_rel;
-        float m = -INFINITY;
-        for (int c = lane; c < num_rel; c += 32) m = fmaxf(m, lg[c]);
-        m = wmax(m);
-        float sum = 0.f, best = -INFINITY;
-        int besti = 0x7fffffff;
-        for (int c = lane; c < num_rel; c += 32) {
-            const float e = expf(lg[c] - m);
-            sum += e;
-            if (c >= 1 && e > best) { best = e; besti = c; }
-        }
-        sum = wsum(sum);
-        // arg max over classes 1.. of e/sum (monotone in e); first index on ties
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-        }
-        if (lane == 0) {
-            const float score = best / sum;
-            const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + q));
-            const float t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
-            unsigned int u = __float_as_uint(t);
-            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
-            lab[q] = (unsigned short)besti;
-            trip[q] = t;
-        }
-    }
-    for (int q = rows + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
-    __syncthreads();
+// Sort storage: images of up to kMaxRows rows sort their 64-bit keys in shared memory.  Larger images (MAX_PROPOSAL_PAIR
+// 4096+ with the MEET heads merged) sort in place in global memory: the image's own pairs_out region (16 B per row)
+// holds the npow <= 2 * rows keys, the ranked order is then parked in labels_out (one int64 per row) before the
+// output pass overwrites both.  Labels and triple scores are recomputed in the output pass instead of being stored.
+__device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int npow) {
     for (int k = 2; k <= npow; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int q = threadIdx.x; q < npow; q += blockDim.x) {
@@ -88,21 +40,83 @@ postprocess_kernel(const float* __restrict__ logits, int num_rel, const int64_t*
             __syncthreads();
         }
     }
-    for (int rank = wid; rank < rows; rank += nw) {
-        const int q = (int)(keys[rank] & 0xffffffffull);
+}
+__device__ __forceinline__ unsigned long long rank_key(float t, int q) {
+    unsigned int u = __float_as_uint(t);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)(~u) << 32) | (unsigned long long)(unsigned int)q;
+}
+// park the ranked order of an oversized image in labels_out (see above); returns after a CTA barrier
+__device__ __forceinline__ void park_order(const unsigned long long* keys, int n, int64_t* labels_out_img, bool big) {
+    if (!big) return;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) labels_out_img[r] = (int64_t)(keys[r] & 0xffffffffull);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+postprocess_kernel(const float* __restrict__ logits, int num_rel, const int64_t* __restrict__ pairs,
+                   const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off,
+                   const int32_t* __restrict__ box_off, int64_t* __restrict__ pairs_out, float* __restrict__ probs_out,
+                   int64_t* __restrict__ labels_out, float* __restrict__ triple_out) {
+    extern __shared__ unsigned long long smem_keys[];  // [kMaxRows]
+    const int b = blockIdx.x;
+    const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
+    if (rows <= 0) return;
+    const bool big = rows > kMaxRows;
+    unsigned long long* keys = big ? (unsigned long long*)(pairs_out + 2 * (size_t)r0) : smem_keys;
+    const int boff = box_off[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int npow = 1;
+    while (npow < rows) npow <<= 1;
+
+    // softmax statistics, arg max over classes 1.. (first index on ties) and triple score of row q (whole warp)
+    auto score_row = [&](int q, float& m, float& sum, int& besti, float& t) {
         const float* lg = logits + (size_t)(r0 + q) * num_rel;
-        float m = -INFINITY;
+        m = -INFINITY;
         for (int c = lane; c < num_rel; c += 32) m = fmaxf(m, lg[c]);
         m = wmax(m);
-        float sum = 0.f;
-        for (int c = lane; c < num_rel; c += 32) sum += expf(lg[c] - m);
+        sum = 0.f;
+        float best = -INFINITY;
+        besti = 0x7fffffff;
+        for (int c = lane; c < num_rel; c += 32) {
+            const float e = expf(lg[c] - m);
+            sum += e;
+            if (c >= 1 && e > best) { best = e; besti = c; }
+        }
         sum = wsum(sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        const float score = best / sum;
+        const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + q));
+        t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
+    };
+
+    for (int q = wid; q < rows; q += nw) {
+        float m, sum, t;
+        int besti;
+        score_row(q, m, sum, besti, t);
+        if (lane == 0) keys[q] = rank_key(t, q);
+    }
+    for (int q = rows + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
+    __syncthreads();
+    bitonic_sort_keys(keys, npow);
+    park_order(keys, rows, labels_out + r0, big);
+    for (int rank = wid; rank < rows; rank += nw) {
+        const int q = big ? (int)labels_out[r0 + rank] : (int)(keys[rank] & 0xffffffffull);
+        float m, sum, t;
+        int besti;
+        score_row(q, m, sum, besti, t);
+        const float* lg = logits + (size_t)(r0 + q) * num_rel;
         float* po = probs_out + (size_t)(r0 + rank) * num_rel;
         for (int c = lane; c < num_rel; c += 32) po[c] = expf(lg[c] - m) / sum;
         if (lane == 0) {
             *(longlong2*)(pairs_out + 2 * (size_t)(r0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + q));
-            labels_out[r0 + rank] = lab[q];
-            triple_out[r0 + rank] = trip[q];
+            labels_out[r0 + rank] = besti;
+            triple_out[r0 + rank] = t;
         }
     }
 }
@@ -120,32 +134,31 @@ meet_postprocess_kernel(const float* __restrict__ logits, int ld, const int32_t*
                         const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off,
                         const int32_t* __restrict__ box_off, int64_t* __restrict__ pairs_out, float* __restrict__ probs_out,
                         int64_t* __restrict__ labels_out, float* __restrict__ triple_out) {
-    extern __shared__ unsigned long long keys[];  // [npow]
-    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
-    float* trip = (float*)(lab + kMaxRows);
+    extern __shared__ unsigned long long smem_keys[];  // [kMaxRows]
     const int b = blockIdx.x;
     const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
     const int merged = rows * n_heads;
     if (merged <= 0) return;
-    if (merged > kMaxRows) {
-        if (threadIdx.x == 0) printf("veto_postprocess_meet: image %d has %d merged rows > %d\n", b, merged, kMaxRows);
-        __trap();
-    }
+    const bool big = merged > kMaxRows;
     const int boff = box_off[b];
     const size_t out0 = (size_t)r0 * n_heads;  // merged rows of the images before this one
+    unsigned long long* keys = big ? (unsigned long long*)(pairs_out + 2 * out0) : smem_keys;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int npow = 1;
     while (npow < merged) npow <<= 1;
 
-    for (int q = wid; q < merged; q += nw) {
+    // head k's softmax statistics over its n_k + 2 columns, arg max over the member columns 1..n_k and triple score of
+    // merged row q = k * rows + r (whole warp)
+    auto score_row = [&](int q, float& m, float& sum, int& besti, float& t) {
         const int k = q / rows, r = q - k * rows;
-        const int c0 = head_off[k], nc = head_off[k + 1] - c0;   // n_k + 2 columns
+        const int c0 = head_off[k], nc = head_off[k + 1] - c0;
         const float* lg = logits + (size_t)(r0 + r) * ld + c0;
-        float m = -INFINITY;
+        m = -INFINITY;
         for (int c = lane; c < nc; c += 32) m = fmaxf(m, lg[c]);
         m = wmax(m);
-        float sum = 0.f, best = -INFINITY;
-        int besti = 0x7fffffff;
+        sum = 0.f;
+        float best = -INFINITY;
+        besti = 0x7fffffff;
         for (int c = lane; c < nc; c += 32) {
             const float e = expf(lg[c] - m);
             sum += e;
@@ -158,51 +171,37 @@ meet_postprocess_kernel(const float* __restrict__ logits, int ld, const int32_t*
             const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
             if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
-        if (lane == 0) {
-            const float score = best / sum;
-            const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
-            const float t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
-            unsigned int u = __float_as_uint(t);
-            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
-            lab[q] = (unsigned short)besti;
-            trip[q] = t;
-        }
+        const float score = best / sum;
+        const longlong2 pr = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
+        t = score * obj_scores[boff + pr.x] * obj_scores[boff + pr.y];
+    };
+
+    for (int q = wid; q < merged; q += nw) {
+        float m, sum, t;
+        int besti;
+        score_row(q, m, sum, besti, t);
+        if (lane == 0) keys[q] = rank_key(t, q);
     }
     for (int q = merged + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
     __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int q = threadIdx.x; q < npow; q += blockDim.x) {
-                const int p = q ^ j;
-                if (p > q) {
-                    const unsigned long long a = keys[q], c = keys[p];
-                    const bool up = ((q & k) == 0);
-                    if ((a > c) == up) { keys[q] = c; keys[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bitonic_sort_keys(keys, npow);
+    park_order(keys, merged, labels_out + out0, big);
     for (int rank = wid; rank < merged; rank += nw) {
-        const int q = (int)(keys[rank] & 0xffffffffull);
+        const int q = big ? (int)labels_out[out0 + rank] : (int)(keys[rank] & 0xffffffffull);
         const int k = q / rows, r = q - k * rows;
         const int c0 = head_off[k], nc = head_off[k + 1] - c0;
         const float* lg = logits + (size_t)(r0 + r) * ld + c0;
-        float m = -INFINITY;
-        for (int c = lane; c < nc; c += 32) m = fmaxf(m, lg[c]);
-        m = wmax(m);
-        float sum = 0.f;
-        for (int c = lane; c < nc; c += 32) sum += expf(lg[c] - m);
-        sum = wsum(sum);
+        float m, sum, t;
+        int besti;
+        score_row(q, m, sum, besti, t);
         float* po = probs_out + (out0 + rank) * num_rel;
         for (int c = lane; c < num_rel; c += 32) po[c] = 0.f;
         __syncwarp();
         for (int c = lane; c < nc - 1; c += 32) po[col_map[c0 + c]] = expf(lg[c] - m) / sum;  // distinct global columns
         if (lane == 0) {
             *(longlong2*)(pairs_out + 2 * (out0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
-            labels_out[out0 + rank] = lab[q];
-            triple_out[out0 + rank] = trip[q];
+            labels_out[out0 + rank] = besti;
+            triple_out[out0 + rank] = t;
         }
     }
 }
@@ -272,9 +271,7 @@ meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __rest
                  const float* __restrict__ obj_scores, const int32_t* __restrict__ rel_off, const int32_t* __restrict__ box_off,
                  int64_t* __restrict__ pairs_out, float* __restrict__ probs_out, int64_t* __restrict__ labels_out,
                  float* __restrict__ triple_out, int32_t* __restrict__ counts_out) {
-    extern __shared__ unsigned long long keys[];  // [npow]
-    unsigned short* lab = (unsigned short*)(keys + kMaxRows);
-    float* trip = (float*)(lab + kMaxRows);
+    extern __shared__ unsigned long long smem_keys[];  // [kMaxRows]
     __shared__ int s_kept;
     const int b = blockIdx.x;
     const int r0 = rel_off[b], rows = rel_off[b + 1] - r0;
@@ -285,12 +282,10 @@ meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __rest
         if (threadIdx.x == 0) counts_out[b] = 0;
         return;
     }
-    if (merged > kMaxRows) {
-        if (threadIdx.x == 0) printf("veto_postprocess_meet_vote: image %d has %d candidate rows > %d\n", b, merged, kMaxRows);
-        __trap();
-    }
+    const bool big = merged > kMaxRows;
     const int boff = box_off[b];
     const size_t out0 = (size_t)r0 * n_groups;
+    unsigned long long* keys = big ? (unsigned long long*)(pairs_out + 2 * out0) : smem_keys;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int npow = 1;
     while (npow < merged) npow <<= 1;
@@ -319,11 +314,7 @@ meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __rest
         const bool keep = expert_vote(x, consensus, score, cls, w);
         if (lane == 0) {
             if (keep) {
-                unsigned int u = __float_as_uint(score);
-                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-                keys[q] = ((unsigned long long)(~u) << 32) | (unsigned long long)q;
-                lab[q] = (unsigned short)cls;
-                trip[q] = score;
+                keys[q] = rank_key(score, q);
                 ++my_kept;
             } else {
                 keys[q] = ~0ull;
@@ -333,23 +324,17 @@ meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __rest
     if (lane == 0 && my_kept) atomicAdd(&s_kept, my_kept);
     for (int q = merged + threadIdx.x; q < npow; q += blockDim.x) keys[q] = ~0ull;
     __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int q = threadIdx.x; q < npow; q += blockDim.x) {
-                const int p = q ^ j;
-                if (p > q) {
-                    const unsigned long long a = keys[q], c = keys[p];
-                    const bool up = ((q & k) == 0);
-                    if ((a > c) == up) { keys[q] = c; keys[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bitonic_sort_keys(keys, npow);
     const int kept = s_kept;
     if (threadIdx.x == 0) counts_out[b] = kept;
+    park_order(keys, kept, labels_out + out0, big);
+    if (big) {
+        // the key storage was this image's pairs_out region: rows past the survivors go back to the zeros the caller put there
+        for (size_t i = 2 * (size_t)kept + threadIdx.x; i < (size_t)npow && i < 2 * (size_t)merged; i += blockDim.x)
+            pairs_out[2 * out0 + i] = 0;
+    }
     for (int rank = wid; rank < kept; rank += nw) {
-        const int q = (int)(keys[rank] & 0xffffffffull);
+        const int q = big ? (int)labels_out[out0 + rank] : (int)(keys[rank] & 0xffffffffull);
         const int j = q / rows, r = q - j * rows;
         ExpertRow x;
         float mm[3], ss[3], w[3], score = 0.f;
@@ -371,8 +356,8 @@ meet_vote_kernel(const float* __restrict__ logits, int ld, const int32_t* __rest
         }
         if (lane == 0) {
             *(longlong2*)(pairs_out + 2 * (out0 + rank)) = *(const longlong2*)(pairs + 2 * (size_t)(r0 + r));
-            labels_out[out0 + rank] = lab[q];
-            triple_out[out0 + rank] = trip[q];
+            labels_out[out0 + rank] = cls;
+            triple_out[out0 + rank] = score;
         }
     }
 }
@@ -391,11 +376,11 @@ extern "C" int veto_postprocess(const float* rel_logits_dev, int num_rel, const 
                      probs_out_dev && labels_out_dev && triple_out_dev && num_rel >= 2 && num_rel < 65536,
                  VETO_ERR_ARG, "veto_postprocess: bad argument");
     set_tag(TAG_POST);
-    static bool attr_set = false;
-    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    const int smem = kMaxRows * (int)sizeof(unsigned long long);
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.done();
     }
     postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(rel_logits_dev, num_rel, pairs_dev, obj_scores_dev,
                                                                       rel_offsets_dev, box_offsets_dev, pairs_out_dev,
@@ -416,11 +401,11 @@ extern "C" int veto_postprocess_meet(const float* group_logits_dev, int num_out,
                      num_out >= 3 * n_heads && num_rel >= 2 && num_rel < 65536,
                  VETO_ERR_ARG, "veto_postprocess_meet: bad argument");
     set_tag(TAG_POST);
-    static bool attr_set = false;
-    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    const int smem = kMaxRows * (int)sizeof(unsigned long long);
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(meet_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.done();
     }
     meet_postprocess_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(
         group_logits_dev, num_out, head_offsets_dev, n_heads, col_map_dev, num_rel, pairs_dev, obj_scores_dev, rel_offsets_dev,
@@ -441,11 +426,11 @@ extern "C" int veto_postprocess_meet_vote(const float* group_logits_dev, int num
                      n_groups >= 1 && num_out >= 9 * n_groups && num_rel >= 2 && num_rel < 65536 && n_pairs >= 0,
                  VETO_ERR_ARG, "veto_postprocess_meet_vote: bad argument");
     set_tag(TAG_POST);
-    static bool attr_set = false;
-    const int smem = kMaxRows * (int)(sizeof(unsigned long long) + sizeof(unsigned short) + sizeof(float));
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    const int smem = kMaxRows * (int)sizeof(unsigned long long);
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(meet_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.done();
     }
     meet_vote_kernel<<<n_images, 1024, smem, (cudaStream_t)stream>>>(
         group_logits_dev, num_out, head_offsets_dev, n_groups, col_map_dev, num_rel, consensus, pairs_dev, obj_scores_dev,

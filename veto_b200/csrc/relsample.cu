@@ -117,11 +117,11 @@ extern "C" int veto_relsample_gtbox(const int64_t* rel_matrix_dev, const int32_t
     int npow = 1;
     while (npow < n_max * n_max) npow <<= 1;
     const int smem = npow * (int)sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(relsample_gtbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        RS_MAX_CELLS * (int)sizeof(unsigned long long)));
-        attr_set = true;
+        attr_set.done();
     }
     set_tag(TAG_PAIRS);
     relsample_gtbox_kernel<<<n_images, RS_THREADS, smem, (cudaStream_t)stream>>>(
@@ -452,10 +452,10 @@ extern "C" int veto_relsample_detect(const float* prp_boxes_dev, const int64_t* 
                      n_tgt_host[b]);
     const int smem = RS_MAX_CELLS * 8 + RS_MAX_CELLS + RS_MAX_CELLS / 8 + RD_MAX_GT_REL * 4 + (RD_MAX_GT_REL + 2) * 4 +
                      4 * RD_MAX_GT_REL * 8 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(relsample_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set.done();
     }
     DetectParams prm{fg_thres, require_overlap, num_sample_per_gt_rel, batch_size_per_image, num_pos_per_image, seed};
     set_tag(TAG_PAIRS);

@@ -200,12 +200,12 @@ int channel_slices(int n_items, int channels) {
     return slices;
 }
 
-bool g_attr_set = false;
+DeviceOnce g_attr_set;
 int ensure_attrs() {
-    if (g_attr_set) return VETO_OK;
+    if (!g_attr_set.pending()) return VETO_OK;
     VETO_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Taps)));
     VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Taps)));
-    g_attr_set = true;
+    g_attr_set.done();
     return VETO_OK;
 }
 

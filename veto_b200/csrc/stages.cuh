@@ -21,6 +21,7 @@ struct SplitJob {
     __nv_bfloat16* hi;
     __nv_bfloat16* lo;
     size_t n;
+    int fmt = FMT_BF16;   // FMT_F16C8: the WEIGHT side of the f16c8 format (common.cuh): hi = fp16(2048 w), lo = (value, residual) e4m3 bytes
 };
 int pack_split_bf16_multi(const SplitJob* jobs, int count, cudaStream_t s);
 

@@ -1288,12 +1288,12 @@ int layernorm_bwd(const float* x, int64_t ldx, const float* dy, const float* gam
 
 int attention_bwd(const float* qkv, const float* d_out, int64_t n_seq, const ActOut& d_qkv, cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
         VETO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
         VETO_CUDA(cudaFuncSetAttribute(attention_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABM_SMEM));
-        attr_set = true;
+        attr_set.done();
     }
     static const bool simt_only = getenv("VETO_ATTN_BWD_SIMT") != nullptr;  // diagnosis: the fp32 SIMT kernel in every mode
     if (d_qkv.hi && !d_qkv.f32 && !simt_only) {  // tensor-core modes: bf16 hi (+ lo) operands for the qkv weight / input gradients

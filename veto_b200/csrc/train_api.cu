@@ -276,6 +276,8 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
                          g->ff1_w[l] && g->ff1_b[l] && g->ff2_w[l] && g->ff2_b[l],
                      VETO_ERR_ARG, "veto_relation_train_step: a gradient pointer of layer %d is NULL", l);
     const int prec = cfg->precision;
+    VETO_REQUIRE(prec <= VETO_PREC_BF16, VETO_ERR_UNSUPPORTED,
+                 "veto_relation_train_step: f16c8 / f16 are inference modes; train with bf16x3 / bf16 / fp32 (the host layer maps them)");
     const PackedLayout L = packed_layout(*cfg);
     const TrainLayout T = train_layout(*cfg, in->n_boxes, in->n_pairs);
     VETO_REQUIRE(workspace_bytes >= T.total, VETO_ERR_WORKSPACE, "veto_relation_train_step: workspace %zu < %zu bytes",

@@ -13,8 +13,11 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 from . import build as _build
 
 VETO_MAX_LAYERS = 16
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16C8, PREC_F16 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16c8": PREC_F16C8, "f16": PREC_F16}
+# f16c8 / f16 are inference modes of the encoder (include/veto_b200.h): the training step and the depth backbone of a
+# module configured with them run in the bf16 mode of the same storage class
+TRAIN_PRECISION = {"fp32": "fp32", "bf16x3": "bf16x3", "bf16": "bf16", "f16c8": "bf16x3", "f16": "bf16"}
 
 _fp = c_void_p  # device pointers travel as integers
 

@@ -518,8 +518,6 @@ def postprocess(rel_logits: torch.Tensor, pairs: torch.Tensor, obj_scores: torch
     pairs = pairs.to(torch.int64).contiguous()
     R, C = rel_logits.shape
     dev = rel_logits.device
-    if max(rel_counts, default=0) > 16384:
-        raise RuntimeError("veto_postprocess sorts one image in shared memory: at most 16384 pairs per image")
     pairs_o = torch.empty_like(pairs)
     probs_o = torch.empty_like(rel_logits)
     labels_o = torch.empty(R, dtype=torch.int64, device=dev)
@@ -548,8 +546,6 @@ def postprocess_meet(group_logits: torch.Tensor, head_sizes: Sequence[int], col_
     dev = group_logits.device
     if sum(head_sizes) != Ct or len(col_map) != Ct or sum(rel_counts) != R:
         raise RuntimeError("head_sizes / col_map / rel_counts do not match the group logits")
-    if max(rel_counts, default=0) * G > 16384:
-        raise RuntimeError("veto_postprocess_meet sorts one image in shared memory: at most 16384 merged rows per image")
     pairs_o = torch.empty((G * R, 2), dtype=torch.int64, device=dev)
     probs_o = torch.empty((G * R, num_rel), dtype=torch.float32, device=dev)
     labels_o = torch.empty(G * R, dtype=torch.int64, device=dev)
@@ -584,8 +580,6 @@ def postprocess_meet_vote(group_logits: torch.Tensor, head_sizes: Sequence[int],
     if any(head_sizes[e * G + j] != head_sizes[j] for e in range(3) for j in range(G)):
         raise RuntimeError("the three experts of a group must have the same number of outputs")
     dev = group_logits.device
-    if max(rel_counts, default=0) * G > 16384:
-        raise RuntimeError("veto_postprocess_meet_vote sorts one image in shared memory: at most 16384 candidate rows per image")
     pairs_o = torch.zeros((G * R, 2), dtype=torch.int64, device=dev)
     probs_o = torch.zeros((G * R, num_rel), dtype=torch.float32, device=dev)
     labels_o = torch.zeros(G * R, dtype=torch.int64, device=dev)
@@ -664,7 +658,7 @@ def depth_backbone_forward(depth: torch.Tensor, convs, bn_w, bn_b, bn_mean, bn_v
     if len(convs) != L.DEPTH_CONVS:
         raise RuntimeError("the depth backbone has %d convolutions" % L.DEPTH_CONVS)
     B, _, H, W_ = depth.shape
-    prec = L.PRECISIONS[precision]
+    prec = L.PRECISIONS[L.TRAIN_PRECISION[precision]]
     lib = L.load()
     nbytes = lib.veto_depth_backbone_workspace_bytes(prec, B, H, W_, int(training))
     if nbytes == 0:
@@ -706,7 +700,7 @@ def depth_backbone_backward(grad_out: torch.Tensor, depth_shape, convs, bn_w, bn
     tensors = [[_cuda_f32(t) for t in group] for group in (convs, bn_w, bn_b)]
     Wst = _depth_weight_struct(tensors[0], tensors[1], tensors[2], bn_mean, bn_var)
     with torch.cuda.device(grad_out.device):
-        L.check(L.load().veto_depth_backbone_backward(L.PRECISIONS[precision], ctypes.byref(Wst), grad_out.data_ptr(), B, H, W_,
+        L.check(L.load().veto_depth_backbone_backward(L.PRECISIONS[L.TRAIN_PRECISION[precision]], ctypes.byref(Wst), grad_out.data_ptr(), B, H, W_,
                                                       ctypes.byref(G), ws.data_ptr(), ws.numel(), L.stream_ptr()),
                 "veto_depth_backbone_backward")
     return flat, views[:n], views[n:2 * n], views[2 * n:]

@@ -100,7 +100,9 @@ class PostProcessor(nn.Module):
                 bl = box  # the reference adds the result fields to the input BoxList too (:431-452)
             else:         # sgdet: boxes regressed for the finetuned class (:425-431); a NEW BoxList without the input's fields
                 cls = obj_pred[bo:bo + nb]
-                bl = BoxList(boxes_per_cls[bo:bo + nb][torch.arange(nb, device=cls.device), cls], box.size, "xyxy")
+                # built with the INPUT's class: inside the reference that is pysgg's BoxList, whose resize() /
+                # copy_with_fields() the reference evaluation calls on the result (vg_eval.py:55)
+                bl = type(box)(boxes_per_cls[bo:bo + nb][torch.arange(nb, device=cls.device), cls], box.size, "xyxy")
             bl.add_field("pred_labels", obj_pred[bo:bo + nb])
             bl.add_field("pred_scores", obj_scores[bo:bo + nb])
             bl.add_field("rel_pair_idxs", pairs_o[ro:ro + nr])

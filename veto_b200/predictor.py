@@ -35,11 +35,11 @@ def get_dataset_statistics(config):
     otherwise synthesises names from the configured class counts."""
     try:
         from pysgg.data import get_dataset_statistics as ref_stats
-        return ref_stats(config)
-    except Exception:
+    except ImportError:      # the reference is absent (GPU box, tests): errors of an importable reference propagate
         n_obj, n_rel = C.num_classes(config)
         return {"obj_classes": ["__background__"] + [f"obj{i}" for i in range(1, n_obj)],
                 "rel_classes": ["__background__"] + [f"rel{i}" for i in range(1, n_rel)]}
+    return ref_stats(config)
 
 
 def obj_edge_vectors(names, wv_dir, wv_dim):
@@ -47,9 +47,9 @@ def obj_edge_vectors(names, wv_dir, wv_dim):
     reference / the GloVe files are not available (a checkpoint overwrites them anyway)."""
     try:
         from pysgg.modeling.roi_heads.relation_head.utils_motifs import obj_edge_vectors as ref_vecs
-        return ref_vecs(names, wv_dir=wv_dir, wv_dim=wv_dim)
-    except Exception:
+    except ImportError:      # no reference: random rows; a missing GloVe file inside a real install still raises
         return torch.randn(len(names), wv_dim)
+    return ref_vecs(names, wv_dir=wv_dir, wv_dim=wv_dim)
 
 
 REFERENCE_PRED_COUNTS_PATH = "/visinf/home/gsudhakaran/scene_graphs/VETO_rebuttal/pred_counts.pkl"
@@ -170,12 +170,14 @@ class _Trunk(nn.Module):
     def _trunk_tensors(self):
         return {k: v for k, v in self.state_dict(keep_vars=True).items()}
 
-    def _pack(self, rel_w: torch.Tensor, rel_b: torch.Tensor) -> ops.PackedWeights:
+    def _pack(self, rel_w: torch.Tensor, rel_b: torch.Tensor, training: bool = False) -> ops.PackedWeights:
+        from .lib import TRAIN_PRECISION
+        precision = TRAIN_PRECISION[self.precision] if training else self.precision
         tensors = self._trunk_tensors()
-        key = (self.precision, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()),
+        key = (precision, tuple((k, t.data_ptr(), t._version) for k, t in tensors.items()),
                rel_w.data_ptr(), rel_w._version, rel_b._version)
         if self._packed is None or self._packed_key != key:
-            cfg = ops.make_config(self.num_obj_cls, rel_w.shape[0], self.precision, layers=self.n_layers)
+            cfg = ops.make_config(self.num_obj_cls, rel_w.shape[0], precision, layers=self.n_layers)
             self._packed = ops.PackedWeights(cfg, tensors, rel_w, rel_b)
             self._packed_key = key
         return self._packed
@@ -224,7 +226,7 @@ class _Trunk(nn.Module):
             else:
                 rel_w = torch.cat([m.weight.detach() for m in heads], 0)
                 rel_b = torch.cat([m.bias.detach() for m in heads], 0)
-            pw = self._pack(rel_w, rel_b)
+            pw = self._pack(rel_w, rel_b, training=True)
             n_trunk = sum(p.numel() for _, p in keyed)
             flat = torch.empty(n_trunk + n_out * dim + n_out, dtype=torch.float32, device=boxes.device)
             views, off = [], 0
