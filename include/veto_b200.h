@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define VETO_ABI_VERSION 3   /* 2: veto_train_inputs grew the MEET group-head fields; 3: depth backbone entry points */
+#define VETO_ABI_VERSION 4   /* 2: veto_train_inputs grew the MEET group-head fields; 3: depth backbone entry points;
+                              4: veto_meet_group_labels, precision modes F16C8 / F16 */
 
 enum {
     VETO_OK = 0,
@@ -127,6 +128,22 @@ int veto_relsample_detect(const float* prp_boxes_dev, const int64_t* prp_labels_
                           int batch_size_per_image, int num_pos_per_image, uint64_t seed, int64_t* triplets_out_dev,
                           int64_t* corrsp_out_dev, int32_t* counts_out_dev, int64_t* binary_out_dev,
                           float* locating_out_dev, veto_stream_t stream);
+
+/* f2 / a10. Training-time group sampling + relabelling of VETOPredictor_MEET — replaces the per-pair Python loops of
+ * VETOPredictor_MEET.forward (roi_relation_predictors.py:3940-3969: cur_chosen_matrix, one .item() sync per pair) and
+ * Ensemble.forward (:3812-3821: per-head relabelling).  rel_labels_dev int64 [n_pairs] (global predicate ids, 0 =
+ * background); incre_idx_dev int32 [num_rel] = 1-based group of every predicate (incre_idx_list, extra_function_utils.py:
+ * 39-52); rates_dev double [n_groups, num_rel] = generate_sample_rate_vector_sep2 (:185-257); local_label_dev int32
+ * [n_groups, num_rel] = head k's local label of predicate p (0 for p = 0, 1-based position among the head's members,
+ * n_k + 1 for any other foreground predicate).  zero_mode: 0 'rand_insert', 1 'rand_choose', 2 'all_include'
+ * (GCL_SETTING.ZERO_LABEL_PADDING_MODE).  Output head_labels_out_dev int64 [n_groups, n_pairs]: the head-local label of
+ * every pair the head trains on, -1 elsewhere (veto_train_inputs.head_labels).  Draws are counter-based in (seed, pair);
+ * draws_dev (double [n_pairs], the u of every foreground / rand_choose pair) and bg_heads_dev (int32 [n_pairs], the head of
+ * every rand_insert background pair) optionally inject the reference's own `random` stream (parity tests); NULL otherwise. */
+int veto_meet_group_labels(const int64_t* rel_labels_dev, int64_t n_pairs, const int32_t* incre_idx_dev,
+                           const double* rates_dev, const int32_t* local_label_dev, int n_groups, int num_rel,
+                           int zero_mode, uint64_t seed, const double* draws_dev, const int32_t* bg_heads_dev,
+                           int64_t* head_labels_out_dev, veto_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a3. ROIAlign.  veto_roi_align_forward is the one-for-one replacement of

@@ -12,66 +12,11 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-# (key prefix of the conv, key prefix of its BatchNorm, stride, padding) in the module order of include/veto_b200.h
-CONVS = [("conv1", "bn1", 2, 3)]
-BLOCKS = []          # (index of conv1, index of conv2, index of the downsample conv or -1)
-for _l, _stride in (("layer1", 1), ("layer2", 2), ("layer3", 2)):
-    for _b in (0, 1):
-        p = f"{_l}.{_b}."
-        s = _stride if _b == 0 else 1
-        c1 = len(CONVS)
-        CONVS.append((p + "conv1", p + "bn1", s, 1))
-        CONVS.append((p + "conv2", p + "bn2", 1, 1))
-        ds = -1
-        if _b == 0 and _l != "layer1":
-            ds = len(CONVS)
-            CONVS.append((p + "downsample.0", p + "downsample.1", s, 0))
-        BLOCKS.append((c1, c1 + 1, ds))
-CHANNELS = [(1, 64, 7)] + [(64, 64, 3)] * 4 + [(64, 128, 3), (128, 128, 3), (64, 128, 1), (128, 128, 3), (128, 128, 3),
-                                              (128, 256, 3), (256, 256, 3), (128, 256, 1), (256, 256, 3), (256, 256, 3)]
-
-
-def out_size(height, width):
-    """Spatial size of the layer3 output (four stride-2 stages, each floor((n - 1) / 2) + 1)."""
-    for _ in range(4):
-        height, width = (height - 1) // 2 + 1, (width - 1) // 2 + 1
-    return height, width
-
-
-def state_keys(prefix="body."):
-    """state-dict keys in the reference's order."""
-    keys = []
-    order = [0] + [i for c1, c2, ds in BLOCKS for i in ((c1, c2) if ds < 0 else (c1, c2, ds))]
-    for i in order:
-        c, b, _, _ = CONVS[i]
-        keys.append(prefix + c + ".weight")
-        keys += [prefix + b + s for s in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked")]
-    return keys
-
-
-def synth_state(seed=0, prefix="body."):
-    """A deterministic (numpy) state: He-scaled convolutions, BatchNorm affine near (1, 0), non-trivial running stats."""
-    rng = np.random.RandomState(seed)
-    sd = {}
-    for (c, b, _, _), (cin, cout, k) in zip(CONVS, CHANNELS):
-        sd[prefix + c + ".weight"] = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (k * k * cout))).astype(np.float32)
-        sd[prefix + b + ".weight"] = (1.0 + 0.2 * rng.standard_normal(cout)).astype(np.float32)
-        sd[prefix + b + ".bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
-        sd[prefix + b + ".running_mean"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
-        sd[prefix + b + ".running_var"] = (1.0 + 0.3 * rng.random_sample(cout)).astype(np.float32)
-        sd[prefix + b + ".num_batches_tracked"] = np.array(0, np.int64)
-    return sd
-
-
-def synth_depth(batch, height, width, seed=0):
-    """A smooth-ish synthetic depth image batch [B,1,H,W] (low-frequency ramps + noise)."""
-    rng = np.random.RandomState(1000 + seed)
-    yy, xx = np.meshgrid(np.linspace(0, 1, height), np.linspace(0, 1, width), indexing="ij")
-    out = np.empty((batch, 1, height, width), np.float32)
-    for b in range(batch):
-        a = rng.standard_normal(4)
-        out[b, 0] = a[0] * yy + a[1] * xx + 0.5 * np.sin(6.0 * a[2] * xx * yy) + 0.3 * rng.standard_normal((height, width))
-    return out
+# the module table and the seeded numpy generators live with the other synthetic inputs (veto_b200/synth.py) so that the
+# product bench needs nothing from oracle/; re-exported here for the tests
+from veto_b200.synth import (DEPTH_BLOCKS as BLOCKS, DEPTH_CHANNELS as CHANNELS, DEPTH_CONVS as CONVS,  # noqa: E402,F401
+                             depth_out_size as out_size, depth_state as synth_state, depth_state_keys as state_keys,
+                             depth_images as synth_depth)
 
 
 def forward(state, depth, training, prefix="body.", momentum=0.1, eps=1e-5):

@@ -43,7 +43,7 @@ def test_library_is_native_sm100a_code():
 
 
 def test_host_only_entry_points(lib):
-    assert lib.veto_abi_version() == 3
+    assert lib.veto_abi_version() == L.ABI_VERSION == 4
     n = (ctypes.c_int32 * 4)(0, 1, 20, 80)
     total = ctypes.c_int64(0)
     assert lib.veto_pairs_capacity(n, 4, 2048, ctypes.byref(total)) == 0

@@ -776,6 +776,65 @@ def test_top50_ranking_and_postprocess(precision):
     assert np.array_equal(pp[clear], np.concatenate([r["rel_pair_idxs"] for r in ora])[clear])
 
 
+def _clear_ranks(sorted_scores, rel_gap=1e-5):
+    """Rows of a descending score list whose score is separated from both neighbours by more than rel_gap (expf of the
+    device vs numpy's exp differ in the last bits): only these must sit at the same rank on both sides."""
+    s = np.asarray(sorted_scores, dtype=np.float64)
+    gap = np.full(len(s), np.inf)
+    gap[1:] = np.minimum(gap[1:], s[:-1] - s[1:])
+    gap[:-1] = np.minimum(gap[:-1], s[:-1] - s[1:])
+    return gap > rel_gap * s
+
+
+def test_postprocess_oversized_images():
+    """Images whose ranked list does not fit the shared-memory sort (more than 16 384 rows: MAX_PROPOSAL_PAIR 4096+ with
+    the MEET heads merged, or a vanilla image with more than 16 384 pairs) sort in global memory: the same
+    results as the oracle, next to a small image in the same batch."""
+    rng = np.random.default_rng(3)
+    n_boxes = [150, 12]                                         # 150 * 149 = 22 350 pairs > 16 384
+    pairs = O.prepare_test_pairs(n_boxes, max_pairs=1 << 30)
+    counts = [len(p) for p in pairs]
+    R = sum(counts)
+    logits = rng.standard_normal((R, 51)).astype(np.float32) * 3
+    obj_logits = [rng.standard_normal((n, 151)).astype(np.float32) * 3 for n in n_boxes]
+    ora = O.postprocess(np.split(logits, np.cumsum(counts)[:-1]), obj_logits, pairs)
+    obj_scores = np.concatenate([o["pred_scores"] for o in ora])
+    po, pr, lab, tri = ops.postprocess(_t(logits), _t(np.concatenate(pairs)), _t(obj_scores), counts, n_boxes)
+    off = 0
+    for o, n in zip(ora, counts):
+        t = H.np_(tri)[off:off + n]
+        assert np.all(np.diff(t) <= 0) and np.allclose(t, o["triple_scores"], rtol=2e-6)
+        keep = _clear_ranks(o["triple_scores"])
+        assert keep.mean() > 0.5
+        assert np.array_equal(H.np_(po)[off:off + n][keep], o["rel_pair_idxs"][keep])
+        assert np.array_equal(H.np_(lab)[off:off + n][keep], o["pred_rel_labels"][keep])
+        assert np.abs(H.np_(pr)[off:off + n][keep] - o["pred_rel_scores"][keep]).max() < 1e-6
+        off += n
+    # MEET merge: 5 heads x 3540 pairs = 17 700 merged rows
+    sizes = synth.GROUP_SPLITS[("VG", "divide4")]
+    from veto_b200.predictor import incre_idx_list
+    incre = incre_idx_list(sizes, 51)
+    n_boxes = [60]
+    pairs = O.prepare_test_pairs(n_boxes, max_pairs=1 << 30)[0]
+    heads = [n + 2 for n in sizes]
+    gl = {"group_%d" % k: rng.standard_normal((len(pairs), n)).astype(np.float32) * 2 for k, n in enumerate(heads)}
+    obj_logit = rng.standard_normal((60, 151)).astype(np.float32) * 3
+    ora = O.postprocess_meet(gl, obj_logit, pairs, incre)
+    op = O.softmax_rows(obj_logit)
+    op[:, 0] = 0
+    col_map = []
+    for k, n in enumerate(heads):
+        col_map += [0] + [c for c, g in enumerate(incre) if g == k + 1] + [0]
+    po, pr, lab, tri = ops.postprocess_meet(_t(np.concatenate([gl["group_%d" % k] for k in range(5)], 1)), heads, col_map, 51,
+                                            _t(pairs), _t(op[:, 1:].max(1)), [len(pairs)], n_boxes)
+    t, s = H.np_(tri), ora["triple"]
+    assert len(t) == 5 * len(pairs) == 17700 and np.all(np.diff(t) <= 0) and np.allclose(t, s, rtol=2e-6)
+    keep = _clear_ranks(s)
+    assert keep.mean() > 0.5
+    assert np.array_equal(H.np_(po)[keep], ora["pairs"][keep]) and np.array_equal(H.np_(lab)[keep], ora["labels"][keep])
+    assert np.abs(H.np_(pr)[keep] - ora["probs"][keep]).max() < 1e-6
+
+
 def test_chunking_and_permutation_invariance():
     """Size-independent properties: the chunk size never changes a bit of the result, and permuting the pair list
     permutes the logits (rows are independent)."""

@@ -215,6 +215,7 @@ def _run_meet_train(c, precision, batch, sd, pairs, rel_labels, sample_seed, exp
     pred = registry.make_roi_relation_predictor(cfg, 512)
     pred.load_state_dict(synth.to_torch_state(sd), strict=True)
     pred = pred.to(DEV).train()
+    pred.reference_draws = True     # replay the reference's `random` stream: the fixture's sampled pairs
     _set_dropout(pred.model, *dropout)
     x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
     d2d.retain_grad()
@@ -270,6 +271,96 @@ def test_meet_train_step_matches_oracle_and_reference(precision):
     grads = dict(mine["grads"])
     grads["roi_depth"] = mine["g_roi_depth"]
     check_against_golden(grads, g, 2 * tol)
+
+
+@pytest.mark.parametrize("zero_mode", ["rand_insert", "rand_choose", "all_include"])
+def test_meet_group_sampling_kernel(zero_mode):
+    """veto_meet_group_labels (roi_relation_predictors.py:3940-3969 + 3812-3821 on the device):
+    (i) with the draws of Python's `random` injected in the reference's order the [G, R] table is bit-identical to the
+    host restatement of the two loops (itself pinned on the reference's sampled rows, tests/test_oracle.py);
+    (ii) with its own counter-based draws every (head, predicate) keep rate matches the sample-rate table within
+    binomial bounds, backgrounds spread uniformly over the heads; the same seed reproduces the table, another one
+    does not."""
+    import random
+    from veto_b200 import meet_sampling as MS
+    from veto_b200.predictor import incre_idx_list
+    for ds, num_rel in (("VG", 51), ("GQA", 101)):
+        sizes = synth.GROUP_SPLITS[(ds, "divide4")]
+        G = len(sizes)
+        incre = incre_idx_list(sizes, num_rel)
+        rates = MS.sample_rate_matrix(ds, sizes)
+        tables = (torch.tensor(incre, dtype=torch.int32, device=DEV), torch.from_numpy(rates).to(DEV),
+                  torch.from_numpy(MS.local_label_table(incre, G)).to(DEV))
+        rng = np.random.default_rng(5)
+        labels = rng.integers(0, num_rel, size=20000)
+        labels[rng.random(20000) < 0.3] = 0
+        # (i) injected reference stream
+        random.seed(99)
+        u, heads = MS.reference_draws(labels.tolist(), G, zero_mode)
+        got = H.np_(ops.meet_group_labels(torch.from_numpy(labels).to(DEV), *tables, zero_mode, seed=1,
+                                          draws=torch.from_numpy(u), bg_heads=torch.from_numpy(heads)))
+        random.seed(99)
+        chosen = MS.group_sampling(labels.tolist(), incre, rates, G, zero_mode)
+        assert np.array_equal(got, MS.group_local_labels(labels.tolist(), chosen, incre))
+        # (ii) own draws
+        R = 400000
+        labels = rng.integers(0, num_rel, size=R)
+        t1 = H.np_(ops.meet_group_labels(torch.from_numpy(labels).to(DEV), *tables, zero_mode, seed=1234))
+        t2 = H.np_(ops.meet_group_labels(torch.from_numpy(labels).to(DEV), *tables, zero_mode, seed=1234))
+        t3 = H.np_(ops.meet_group_labels(torch.from_numpy(labels).to(DEV), *tables, zero_mode, seed=1235))
+        assert np.array_equal(t1, t2) and not np.array_equal(t1, t3)
+        local = MS.local_label_table(incre, G)
+        kept = t1 >= 0
+        assert np.array_equal(t1[kept], local[np.nonzero(kept)[0], labels[np.nonzero(kept)[1]]])   # relabelling
+        for p in range(num_rel):
+            rows = labels == p
+            n = int(rows.sum())
+            for k in range(G):
+                if p == 0:
+                    prob = {"rand_insert": 1.0 / G, "rand_choose": 0.6, "all_include": 1.0}[zero_mode]
+                else:   # the pair joins head k iff k + 1 < g_p or u <= max over a >= k + 1 of rates[a - 1][p]
+                    prob = 1.0 if k + 1 < incre[p] else float(min(1.0, rates[k:, p].max()))
+                freq = kept[k, rows].mean()
+                sigma = np.sqrt(max(prob * (1 - prob), 1e-12) / n)
+                assert abs(freq - prob) <= 6 * sigma + 1e-12, (ds, p, k, freq, prob)
+        if zero_mode == "rand_choose":     # a background pair joins all heads or none
+            bg = kept[:, labels == 0]
+            assert np.all(bg.all(0) | ~bg.any(0))
+        if zero_mode == "rand_insert":     # exactly one head
+            assert np.all(kept[:, labels == 0].sum(0) == 1)
+        # nested heads for foreground pairs: head k implies every head below it
+        fg = kept[:, labels > 0]
+        assert np.all(fg[:-1] >= fg[1:])
+
+
+def test_meet_train_device_sampling_is_seeded_by_random():
+    """VETOPredictor_MEET.forward(train) with the default device-side draws: no host copy of the labels, the step is
+    reproducible under random.seed, the 5th return value materialises the reference-shaped chosen lists on demand."""
+    import random
+    from tests.cases import MEET_TRAIN_CASES
+    from tests.train_util import meet_train_case_inputs
+    c = MEET_TRAIN_CASES["train_meet_vg"]
+    batch, sd, pairs, labels = meet_train_case_inputs(c)
+    cfg = H.make_cfg(predictor="VETOPredictor_MEET", mode="predcls", dataset="VG", precision="bf16x3")
+    bls = H.boxlists(batch, DEV, 151)
+    feats, depth = H.device_features(batch, DEV)
+    fe = registry.make_roi_box_feature_extractor(cfg, 256, for_relation=True).to(DEV).train()
+    pred = registry.make_roi_relation_predictor(cfg, 512)
+    pred.load_state_dict(synth.to_torch_state(sd), strict=True)
+    pred = pred.to(DEV).train()
+    assert pred.reference_draws is False
+    x2d, d2d, _, _ = fe(feats, bls, depth_features=depth)
+    runs = []
+    for seed in (7, 7, 8):
+        random.seed(seed)
+        torch.manual_seed(3)            # the dropout masks of the step
+        out = pred(bls, [torch.from_numpy(p).to(DEV) for p in pairs], [torch.from_numpy(l).to(DEV) for l in labels], None,
+                   roi_features=x2d, roi_depth_features=d2d)
+        runs.append((H.np_(out[4].table), [float(v.detach()) for v in out[2].values()]))
+        assert len(out[4]) == sum(len(l) for l in labels) and len(out[4][0]) == 5
+        assert out[4][0][0] == np.nonzero(runs[-1][0][0] >= 0)[0].tolist()
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+    assert not np.array_equal(runs[0][0], runs[2][0])
 
 
 def test_meet_train_expert_group_and_loss_weights():

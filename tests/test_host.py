@@ -138,6 +138,18 @@ ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)),
 ps[0].grad = torch.full((3, 4), 1.0 + rank); ps[1].grad = torch.arange(5.0) * (rank + 1)   # ps[2] has no gradient
 vdist.allreduce_gradients(ps)
 assert torch.equal(ps[0].grad, torch.full((3, 4), 1.5)) and torch.equal(ps[1].grad, torch.arange(5.0) * 1.5) and ps[2].grad is None
+# gradients that are views of ONE flat buffer (what the relation head and the depth backbone hand to autograd): the
+# buffer is reduced in place, as one bucket, padding included; the views see the averaged values
+flat = torch.arange(20.0) * (rank + 1)
+qs = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4))]
+qs[0].grad = flat[2:8].view(2, 3); qs[1].grad = flat[12:16]
+assert len(vdist._flat_buckets([q.grad for q in qs])) == 1
+works = vdist.allreduce_gradients(qs, async_op=True)
+vdist.finish_gradient_sync(works)
+assert torch.equal(flat[2:16], torch.arange(20.0)[2:16] * 1.5) and torch.equal(flat[:2], torch.arange(2.0) * (rank + 1))
+assert qs[0].grad.data_ptr() == flat[2:].data_ptr() and torch.equal(qs[1].grad, torch.arange(12.0, 16.0) * 1.5)
+works = vdist.allreduce_flat(flat)
+vdist.finish_gradient_sync(works)
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
@@ -166,7 +178,8 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
-    assert "configs[1]" in line["config"]["workload"] and line["inference"]["value"] > 0
+    assert "configs[2]" in line["config"]["workload"] and line["steps"] == 1 and line["warmup"] == 0
+    assert line["train"]["value"] > 0 and line["meet_gqa"]["value"] > 0 and line["sweep96"]["value"] > 0
 
 
 def test_mean_recall_from_first_match_matches_reference():

@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libveto_b200.so")
 
 SOURCES = ["api.cu", "pairs.cu", "roi_gather.cu", "box_stage.cu", "tokens.cu", "encoder_ops.cu",
-           "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_tc.cu", "postprocess.cu", "train.cu", "train_api.cu", "gemm_tn2.cu", "obj_nms.cu", "relsample.cu", "sgg_eval.cu", "depth_backbone.cu"]
+           "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_tc.cu", "postprocess.cu", "train.cu", "train_api.cu", "gemm_tn2.cu", "obj_nms.cu", "relsample.cu", "meet_sample.cu", "sgg_eval.cu", "depth_backbone.cu"]
 # bit-exact ROIAlign needs un-fused multiply-adds (see roi_gather.cu)
 EXTRA = {"roi_gather.cu": ["--fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -63,12 +63,26 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
     r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", tmp] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
+
+
+def build_library_locked(force: bool = False, verbose: bool = False) -> str:
+    """build_library under an exclusive file lock: concurrent processes (the ranks of a torchrun job on a fresh
+    checkout) would otherwise share the object files and the temporary library of one another's half-finished build.
+    The first process builds, the others wait and find the library up to date."""
+    import fcntl
+    os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build_library(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

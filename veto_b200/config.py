@@ -83,7 +83,8 @@ _DEFAULTS = {
     "GLOVE_DIR": "",
     "OUTPUT_DIR": "",
     # extension (not a reference key): arithmetic of the encoder GEMMs, see include/veto_b200.h
-    "VETO_B200": {"PRECISION": "bf16x3", "CHUNK_PAIRS": 0, "FREQ_BIAS": False, "PRED_COUNTS": ""},
+    "VETO_B200": {"PRECISION": "bf16x3", "CHUNK_PAIRS": 0, "FREQ_BIAS": False, "PRED_COUNTS": "",
+                  "MEET_REFERENCE_DRAWS": False},
 }
 
 # predicate_stage_count of SHA_GCL_extra/group_chosen_function.py:6-95 (groups are contiguous id ranges)

@@ -68,9 +68,11 @@ struct WorkLayout {
     int32_t chunk;
 };
 
-// 1994 pairs = 37886 token rows = 148 CTA-pair tiles of 256 rows: with 74 SM pairs every encoder GEMM of a chunk is a
-// whole number of waves (N/192 = 9, 6 and 3 column tiles -> 18, 12 and 6 waves)
-constexpr int32_t kDefaultChunk = 1994;
+// 7976 pairs = 151 544 token rows = 592 CTA-pair tiles of 256 rows: with 74 SM pairs every encoder GEMM of a chunk is a
+// whole number of waves (8 x 74 row tiles times N/192 = 9, 6 or 3 column tiles).  Measured on configs[2] (202 240 pairs,
+// profiles/r2_chunk_sweep.jsonl): 499 -> 514 ms, 997 -> 450, 1994 -> 423, 3988 -> 412, 7976 -> 404 ms per step: the
+// intermediates never fit L2 usefully, so larger chunks only amortise launch tails (2.4 GB of workspace at this size).
+constexpr int32_t kDefaultChunk = 7976;
 
 WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
     WorkLayout W{};
@@ -84,8 +86,8 @@ WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, i
     W.emb = k.take(sizeof(float) * N * kEmbDim);
     W.lso = k.take(sizeof(float) * N * 2 * kDim);
     W.cso = k.take(sizeof(float) * N * 2 * kDim);
-    W.pa_d = k.take(act_bytes(c.precision, N * kPatches * kPatchVec));
-    W.pa_v = k.take(act_bytes(c.precision, N * kPatches * kPatchVec));
+    W.pa_d = k.take(act_bytes(prec_box(c.precision), N * kPatches * kPatchVec));
+    W.pa_v = k.take(act_bytes(prec_box(c.precision), N * kPatches * kPatchVec));
     W.so_d = k.take(sizeof(float) * N * kPatches * 2 * kDimDepth);
     W.so_v = k.take(sizeof(float) * N * kPatches * 2 * kDimRgb);
     const size_t M = (size_t)chunk * kTokens;
@@ -214,7 +216,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
     }
     {
         const size_t pe = (size_t)N * kPatches * kPatchVec;
-        ActBuf pa_d = act_at(B, W.pa_d, prec, pe), pa_v = act_at(B, W.pa_v, prec, pe);
+        ActBuf pa_d = act_at(B, W.pa_d, prec_box(prec), pe), pa_v = act_at(B, W.pa_v, prec_box(prec), pe);
         if ((rc = patchify(in->roi_depth, N, pa_d.out(), s))) return rc;
         if ((rc = patchify(in->roi_rgb, N, pa_v.out(), s))) return rc;
         GemmEpilogue ep;

@@ -35,6 +35,10 @@ static inline int check_config(const veto_config* c) {
 // Storage class of a precision mode: which arrays exist next to the fp32 ones.  f16c8 stores two 2-byte-per-element
 // arrays like bf16x3, f16 one like bf16 — buffer sizes and offsets depend on this only, not on the element encoding.
 static inline bool prec_two_arrays(int precision) { return precision == VETO_PREC_BF16X3 || precision == VETO_PREC_F16C8; }
+// the per-box stage (patch projections: 0.1 % of the work) runs as bf16x3 in every tensor-core mode but the plain bf16 one
+static inline int prec_box(int precision) {
+    return (precision == VETO_PREC_F16C8 || precision == VETO_PREC_F16) ? VETO_PREC_BF16X3 : precision;
+}
 // operand format of the ENCODER GEMMs in a precision mode (the per-box patch projections stay bf16 / bf16x3)
 static inline int prec_encoder_fmt(int precision) {
     return (precision == VETO_PREC_F16C8 || precision == VETO_PREC_F16) ? FMT_F16C8 : FMT_BF16;
@@ -65,11 +69,12 @@ static inline PackedLayout packed_layout(const veto_config& c) {
     L.clspos = k.take(sizeof(float) * kDim);
     if (c.precision != VETO_PREC_FP32) {
         const bool lo = prec_two_arrays(c.precision);
+        const bool box_lo = prec_two_arrays(prec_box(c.precision));
         const size_t e = sizeof(__nv_bfloat16);
         L.d2_hi = k.take(e * 2 * kDimDepth * kPatchVec);
-        L.d2_lo = lo ? k.take(e * 2 * kDimDepth * kPatchVec) : 0;
+        L.d2_lo = box_lo ? k.take(e * 2 * kDimDepth * kPatchVec) : 0;
         L.v2_hi = k.take(e * 2 * kDimRgb * kPatchVec);
-        L.v2_lo = lo ? k.take(e * 2 * kDimRgb * kPatchVec) : 0;
+        L.v2_lo = box_lo ? k.take(e * 2 * kDimRgb * kPatchVec) : 0;
         for (int l = 0; l < c.layers; ++l) {
             L.qkv_hi[l] = k.take(e * 3 * kDim * kDim);
             L.qkv_lo[l] = lo ? k.take(e * 3 * kDim * kDim) : 0;
@@ -131,7 +136,7 @@ static inline int linear(int precision, const ActBuf& a, int lda, const WRef& w,
     A.ld = lda;
     W.hi = w.hi; W.lo = w.lo;
     // a.fmt tells the box stage (bf16 operands in every tensor-core mode) from the encoder (format of the mode)
-    const int passes = a.fmt == FMT_F16C8 ? prec_encoder_passes(precision) : (prec_two_arrays(precision) ? TC_BF16X3 : TC_BF16);
+    const int passes = a.fmt == FMT_F16C8 ? prec_encoder_passes(precision) : (prec_two_arrays(prec_box(precision)) ? TC_BF16X3 : TC_BF16);
     return gemm_tc_auto(A, W, M, N, K, passes, ep, s);
 }
 

@@ -6,10 +6,20 @@
 // (csrc/cpu/ROIAlign_cpu.cpp:17-219), which accumulates w1*v1 + w2*v2 + w3*v3 + w4*v4 sample by sample
 // without fused multiply-adds and divides once by the sample count.
 //
-// One CTA handles one (roi, map, channel slice).  The ph*pw*sr*sr bilinear taps of the roi (the same for
-// every channel) are computed once into shared memory; the channel loop then streams the feature planes:
-// consecutive threads own consecutive output bins of one channel, so stores are fully coalesced and the
-// 16 taps of neighbouring bins hit the same L1 lines of the NCHW plane.
+// Two kernels, both built on the same idea — stage feature-map elements in shared memory TRANSPOSED to
+// [position][channel] so that lanes own CHANNELS while pooling: the tap positions / weights of a sample are then
+// uniform across the lanes of a bin (broadcast 16-byte reads) and the four tap values are conflict-free rows, instead of
+// 16 scattered 4-byte global loads per output element (the round-1 kernel: 1.9 % of HBM bandwidth, profiles/
+// r2_hbm_kernels_before.txt):
+//   * small maps (the depth map, P4, P5 of a 592x800 image: <= 2400 elements per channel): one CTA per (image, map,
+//     8 channels) stages the WHOLE map once and pools every box of the image that reads this map from it — the map is
+//     read from HBM/L2 exactly once per image instead of once per box (80 boxes per image share the depth map);
+//   * large maps (P2, P3): one CTA per (roi, 32 channels) stages the bounding window of the roi's taps (<= ~900
+//     elements for boxes below 224 px) with 4-byte cp.async copies, lanes along x (coalesced rows of the NCHW plane).
+// Output tiles go back through shared memory so that global stores are contiguous rows of the [N,256,8,8] result.
+// The arithmetic of a bin is unchanged (sample by sample, w1*v1 + w2*v2 + w3*v3 + w4*v4, one division): bit-identical.
+#include <cuda_pipeline_primitives.h>
+
 #include "common.cuh"
 
 namespace veto {
@@ -17,81 +27,200 @@ namespace {
 
 constexpr int kMaxTaps = 1024;
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChanBlock = 32;                 // channels per CTA of the window kernel
+constexpr int kMapChan = 8;                    // channels per CTA of the map-resident kernel
+constexpr int kSmemBytes = 100 * 1024;         // two CTAs per SM
 
-struct Taps {
-    int p[4][kMaxTaps];
-    float w[4][kMaxTaps];
+struct RoiGeom {
+    const float* src;   // [C, H, W] planes of the roi's image
+    int H, W;
+    float scale;
 };
 
-// taps of all bins of one roi; reference operation order (ROIAlign_cpu.cpp:17-112)
-__device__ __forceinline__ void compute_taps(Taps& t, float x1, float y1, float x2, float y2, float scale, int height,
-                                             int width, int ph, int pw, int sr) {
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// one sample of a roi in the reference's operation order (ROIAlign_cpu.cpp:17-112): corner coordinates (y_low, x_low,
+// y_high, x_high) and the four weights; a sample outside the map gets y_low = -1 and zero weights
+__device__ __forceinline__ void sample_taps(int k, float x1, float y1, float x2, float y2, float scale, int height, int width,
+                                            int ph, int pw, int sr, int4& p, float4& w) {
     const float roi_start_w = x1 * scale, roi_start_h = y1 * scale;
     const float roi_end_w = x2 * scale, roi_end_h = y2 * scale;
     const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f);
     const float roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
     const float bin_h = roi_height / (float)ph, bin_w = roi_width / (float)pw;
-    const int spp = sr * sr, ntap = ph * pw * spp;
-    for (int k = threadIdx.x; k < ntap; k += blockDim.x) {
-        const int bin = k / spp, s = k - bin * spp;
-        const int bh = bin / pw, bw = bin - bh * pw;
-        const int iy = s / sr, ix = s - iy * sr;
-        float y = roi_start_h + bh * bin_h + (float)(iy + .5f) * bin_h / (float)sr;
-        float x = roi_start_w + bw * bin_w + (float)(ix + .5f) * bin_w / (float)sr;
-        int p1 = 0, p2 = 0, p3 = 0, p4 = 0;
-        float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
-        if (!(y < -1.0f || y > (float)height || x < -1.0f || x > (float)width)) {
-            if (y <= 0.f) y = 0.f;
-            if (x <= 0.f) x = 0.f;
-            int y_low = (int)y, x_low = (int)x, y_high, x_high;
-            if (y_low >= height - 1) { y_high = y_low = height - 1; y = (float)y_low; } else y_high = y_low + 1;
-            if (x_low >= width - 1) { x_high = x_low = width - 1; x = (float)x_low; } else x_high = x_low + 1;
-            const float ly = y - (float)y_low, lx = x - (float)x_low;
-            const float hy = 1.f - ly, hx = 1.f - lx;
-            p1 = y_low * width + x_low;  p2 = y_low * width + x_high;
-            p3 = y_high * width + x_low; p4 = y_high * width + x_high;
-            w1 = hy * hx; w2 = hy * lx; w3 = ly * hx; w4 = ly * lx;
-        }
-        t.p[0][k] = p1; t.p[1][k] = p2; t.p[2][k] = p3; t.p[3][k] = p4;
-        t.w[0][k] = w1; t.w[1][k] = w2; t.w[2][k] = w3; t.w[3][k] = w4;
+    const int spp = sr * sr;
+    const int bin = k / spp, s = k - bin * spp;
+    const int bh = bin / pw, bw = bin - bh * pw;
+    const int iy = s / sr, ix = s - iy * sr;
+    float y = roi_start_h + bh * bin_h + (float)(iy + .5f) * bin_h / (float)sr;
+    float x = roi_start_w + bw * bin_w + (float)(ix + .5f) * bin_w / (float)sr;
+    p = make_int4(-1, 0, 0, 0);
+    w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(y < -1.0f || y > (float)height || x < -1.0f || x > (float)width)) {
+        if (y <= 0.f) y = 0.f;
+        if (x <= 0.f) x = 0.f;
+        int y_low = (int)y, x_low = (int)x, y_high, x_high;
+        if (y_low >= height - 1) { y_high = y_low = height - 1; y = (float)y_low; } else y_high = y_low + 1;
+        if (x_low >= width - 1) { x_high = x_low = width - 1; x = (float)x_low; } else x_high = x_low + 1;
+        const float ly = y - (float)y_low, lx = x - (float)x_low;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        p = make_int4(y_low, x_low, y_high, x_high);
+        w = make_float4(hy * hx, hy * lx, ly * hx, ly * lx);
     }
 }
 
-__device__ __forceinline__ void pool_channels(const Taps& t, const float* __restrict__ plane0, int plane_elems,
-                                              float* __restrict__ out0, int c_begin, int c_end, int bins, int spp) {
+// taps of all bins of one roi into shared memory + the bounding window of the valid ones (bounds: ymin, ymax, xmin, xmax;
+// initialised by the caller to (INT_MAX, -1, INT_MAX, -1); one shared-memory atomic per warp and bound)
+__device__ __forceinline__ void compute_taps(int4* tp, float4* tw, int* bounds, float x1, float y1, float x2, float y2,
+                                             float scale, int height, int width, int ph, int pw, int sr) {
+    const int ntap = ph * pw * sr * sr;
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < ntap; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int4 p = make_int4(-1, 0, 0, 0);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < ntap) {
+            sample_taps(k, x1, y1, x2, y2, scale, height, width, ph, pw, sr, p, w);
+            tp[k] = p;
+            tw[k] = w;
+        }
+        if (bounds) {
+            const bool ok = p.x >= 0;
+            const int ymin = warp_min(ok ? p.x : 0x7fffffff), ymax = warp_max(ok ? p.z : -1);
+            const int xmin = warp_min(ok ? p.y : 0x7fffffff), xmax = warp_max(ok ? p.w : -1);
+            if (lane == 0 && ymax >= 0) {
+                atomicMin(&bounds[0], ymin);
+                atomicMax(&bounds[1], ymax);
+                atomicMin(&bounds[2], xmin);
+                atomicMax(&bounds[3], xmax);
+            }
+        }
+    }
+}
+
+// pooling of `nc` channels x all bins from a [position][stride] staging buffer: lane = (bin slot, channel), the taps of a
+// sample (positions pre-multiplied by the stride) are uniform across the lanes of a bin slot.  tile[c][bins + 1].
+__device__ __forceinline__ void pool_from_smem(const int4* tp, const float4* tw, const float* win, int cb, int nc, int bins,
+                                               int spp, float* tile, int tile_c0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bins_per_iter = 32 / cb;
+    const int cl = lane % cb, bsub = lane / cb;
     const float count = (float)spp;
-    const int total = (c_end - c_begin) * bins;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int cl = e / bins, bin = e - cl * bins;
-        const int c = c_begin + cl;
-        const float* src = plane0 + (size_t)c * plane_elems;
-        float acc = 0.f;
-        const int k0 = bin * spp;
-        for (int s = 0; s < spp; ++s) {
-            const int k = k0 + s;
-            const float v1 = __ldg(src + t.p[0][k]), v2 = __ldg(src + t.p[1][k]);
-            const float v3 = __ldg(src + t.p[2][k]), v4 = __ldg(src + t.p[3][k]);
-            acc += t.w[0][k] * v1 + t.w[1][k] * v2 + t.w[2][k] * v3 + t.w[3][k] * v4;
+    for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
+        const int bin = b0 + bsub;
+        if (bin < bins && cl < nc) {
+            float acc = 0.f;
+            for (int s = 0; s < spp; ++s) {
+                const int4 p = tp[bin * spp + s];
+                const float4 w = tw[bin * spp + s];
+                const float v1 = win[p.x + cl], v2 = win[p.y + cl], v3 = win[p.z + cl], v4 = win[p.w + cl];
+                acc += w.x * v1 + w.y * v2 + w.z * v3 + w.w * v4;
+            }
+            tile[(tile_c0 + cl) * (bins + 1) + bin] = acc / count;
         }
-        out0[(size_t)c * bins + bin] = acc / count;
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+// One (roi, channel block) tile of the window kernel: channels [c0, c0 + nch) of the roi pooled into dst[(c0 + c) * bins + bin].
+__device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph, int pw, int sr, int c0, int nch,
+                                            float* __restrict__ dst, uint8_t* smem) {
+    const int bins = ph * pw, spp = sr * sr, ntap = bins * spp;
+    int4* tp = reinterpret_cast<int4*>(smem);
+    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
+    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));   // [kChanBlock][bins + 1]
+    float* win = tile + kChanBlock * (bins + 1);
+    const int win_floats = (kSmemBytes - (int)((uint8_t*)win - smem)) / (int)sizeof(float);
+    __shared__ int bounds[4];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        bounds[0] = 0x7fffffff; bounds[1] = -1; bounds[2] = 0x7fffffff; bounds[3] = -1;
+    }
+    __syncthreads();
+    compute_taps(tp, tw, bounds, box.x, box.y, box.z, box.w, g.scale, g.H, g.W, ph, pw, sr);
+    __syncthreads();
+    const int y0 = bounds[0], x0 = bounds[2];
+    const int wh = bounds[1] - y0 + 1, ww = bounds[3] - x0 + 1;
+    const float count = (float)spp;
+    const size_t plane = (size_t)g.H * g.W;
+    if (bounds[1] < 0) {                       // every sample outside the map: zeros (0 / count)
+        for (int e = tid; e < nch * bins; e += kThreads) dst[(size_t)c0 * bins + e] = 0.f;
+        return;
+    }
+    const int nw = wh * ww;
+    int cb = kChanBlock;
+    while (cb > 1 && nw * (cb + 1) > win_floats) cb >>= 1;
+    if (nw * (cb + 1) > win_floats) {
+        // window larger than shared memory even for one channel (maps far beyond the 592x800 geometry): taps from global
+        for (int e = tid; e < nch * bins; e += kThreads) {
+            const int cl = e / bins, bin = e - cl * bins;
+            const float* src = g.src + (size_t)(c0 + cl) * plane;
+            float acc = 0.f;
+            for (int s = 0; s < spp; ++s) {
+                const int4 p = tp[bin * spp + s];
+                const float4 w = tw[bin * spp + s];
+                if (p.x < 0) continue;             // adds +0 in the reference
+                const float v1 = __ldg(src + p.x * g.W + p.y), v2 = __ldg(src + p.x * g.W + p.w);
+                const float v3 = __ldg(src + p.z * g.W + p.y), v4 = __ldg(src + p.z * g.W + p.w);
+                acc += w.x * v1 + w.y * v2 + w.z * v3 + w.w * v4;
+            }
+            dst[(size_t)(c0 + cl) * bins + bin] = acc / count;
+        }
+        return;
+    }
+    const int stride = cb + 1;
+    // window-relative tap positions, pre-multiplied by the channel stride; invalid samples point at element 0 (weight 0)
+    for (int k = tid; k < ntap; k += kThreads) {
+        const int4 p = tp[k];
+        tp[k] = p.x < 0 ? make_int4(0, 0, 0, 0)
+                        : make_int4(((p.x - y0) * ww + (p.y - x0)) * stride, ((p.x - y0) * ww + (p.w - x0)) * stride,
+                                    ((p.z - y0) * ww + (p.y - x0)) * stride, ((p.z - y0) * ww + (p.w - x0)) * stride);
+    }
+    for (int sub = 0; sub * cb < nch; ++sub) {
+        const int nc = min(cb, nch - sub * cb);
+        const float* src0 = g.src + (size_t)(c0 + sub * cb) * plane + (size_t)y0 * g.W + x0;
+        // ---- stage the window: a thread owns window positions (consecutive lanes = consecutive x of a row: coalesced)
+        //      and copies them for every channel of the block — two adds per 4-byte cp.async
+        for (int pos = tid; pos < nw; pos += kThreads) {
+            const int yy = pos / ww, xx = pos - yy * ww;
+            const float* sp = src0 + (size_t)yy * g.W + xx;
+            float* dp = win + (size_t)pos * stride;
+            for (int c = 0; c < nc; ++c) __pipeline_memcpy_async(dp + c, sp + (size_t)c * plane, sizeof(float));
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        pool_from_smem(tp, tw, win, cb, nc, bins, spp, tile, sub * cb);
+        __syncthreads();
+    }
+    // ---- contiguous stores of the [nch][bins] tile
+    for (int e = tid; e < nch * bins; e += kThreads) {
+        const int c = e / bins, b = e - c * bins;
+        dst[(size_t)c0 * bins + e] = tile[c * (bins + 1) + b];
+    }
+}
+
+// grid (n_rois, channel blocks)
+__global__ void __launch_bounds__(kThreads, 2)
 roi_align_fwd_kernel(const float* __restrict__ input, int channels, int height, int width,
-                     const float* __restrict__ rois, float scale, int ph, int pw, int sr, int c_per_cta,
-                     float* __restrict__ out) {
-    extern __shared__ float4 smem_raw4[];
-    Taps& t = *reinterpret_cast<Taps*>(smem_raw4);
+                     const float* __restrict__ rois, float scale, int ph, int pw, int sr, float* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int n = blockIdx.x;
     const float* r = rois + (size_t)n * 5;
     const int b = (int)r[0];
-    compute_taps(t, r[1], r[2], r[3], r[4], scale, height, width, ph, pw, sr);
-    __syncthreads();
-    const int c_begin = blockIdx.y * c_per_cta;
-    const int c_end = min(channels, c_begin + c_per_cta);
-    pool_channels(t, input + (size_t)b * channels * height * width, height * width,
-                  out + (size_t)n * channels * ph * pw, c_begin, c_end, ph * pw, sr * sr);
+    RoiGeom g{input + (size_t)b * channels * height * width, height, width, scale};
+    const int c0 = blockIdx.y * kChanBlock;
+    gather_tile(g, make_float4(r[1], r[2], r[3], r[4]), ph, pw, sr, c0, min(kChanBlock, channels - c0),
+                out + (size_t)n * channels * ph * pw, smem_raw);
 }
 
 struct GatherLevels {
@@ -99,6 +228,7 @@ struct GatherLevels {
     int h[4], w[4];
     float scale[4];
     int n_levels, k_min, k_max;
+    int resident[4];   // 1: the level's map is pooled by the map-resident kernel, 0: by the window kernel
 };
 
 // LevelMapper (poolers.py:32-43) in fp32: floor(4 + log2(sqrt(area)/224 + 1e-6)) clamped to [k_min,k_max].
@@ -113,16 +243,24 @@ __device__ __forceinline__ int map_level(float x1, float y1, float x2, float y2,
     return (int)lvl - k_min;
 }
 
-// grid (N, 2, channel slices): y = 0 RGB from the mapped FPN level, y = 1 depth
-__global__ void __launch_bounds__(kThreads)
+// Window kernel, grid (N, channel blocks): the RGB features of the boxes whose FPN level is not map-resident
+// (and, when the depth map is too large for the resident kernel, grid.z = 2: z = 1 pools the depth features).
+__global__ void __launch_bounds__(kThreads, 2)
 roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                   int channels, const float* __restrict__ boxes, const int32_t* __restrict__ box_off, int n_images,
-                  int pool, int sr, int c_per_cta, float* __restrict__ out_rgb, float* __restrict__ out_depth,
+                  int pool, int sr, float* __restrict__ out_rgb, float* __restrict__ out_depth,
                   int32_t* __restrict__ levels_out) {
-    extern __shared__ float4 smem_raw4[];
-    Taps& t = *reinterpret_cast<Taps*>(smem_raw4);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const int n = blockIdx.x;
     const float4 bx = __ldg((const float4*)boxes + n);
+    RoiGeom g;
+    float* dst;
+    int l = -1;
+    if (blockIdx.z == 0) {
+        l = map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max);
+        if (levels_out && blockIdx.y == 0 && threadIdx.x == 0) levels_out[n] = l;
+        if (lv.resident[l]) return;
+    }
     // image of box n (poolers.py:96-107: roi batch index)
     int lo = 0, hi = n_images - 1;
     while (lo < hi) {
@@ -130,81 +268,263 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
         if (box_off[mid] <= n) lo = mid; else hi = mid - 1;
     }
     const int b = lo;
-    const float* src;
-    float* dst;
-    int H, W;
-    float scale;
-    if (blockIdx.y == 0) {
-        const int l = map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max);
-        if (levels_out && blockIdx.z == 0 && threadIdx.x == 0) levels_out[n] = l;
-        H = lv.h[l]; W = lv.w[l]; scale = lv.scale[l];
-        src = lv.feat[l] + (size_t)b * channels * H * W;
+    if (blockIdx.z == 0) {
+        g = RoiGeom{lv.feat[l] + (size_t)b * channels * lv.h[l] * lv.w[l], lv.h[l], lv.w[l], lv.scale[l]};
         dst = out_rgb + (size_t)n * channels * pool * pool;
     } else {
-        H = depth_h; W = depth_w; scale = depth_scale;
-        src = depth + (size_t)b * channels * H * W;
+        g = RoiGeom{depth + (size_t)b * channels * depth_h * depth_w, depth_h, depth_w, depth_scale};
         dst = out_depth + (size_t)n * channels * pool * pool;
     }
-    compute_taps(t, bx.x, bx.y, bx.z, bx.w, scale, H, W, pool, pool, sr);
-    __syncthreads();
-    const int c_begin = blockIdx.z * c_per_cta;
-    const int c_end = min(channels, c_begin + c_per_cta);
-    pool_channels(t, src, H * W, dst, c_begin, c_end, pool * pool, sr * sr);
+    const int c0 = blockIdx.y * kChanBlock;
+    gather_tile(g, bx, pool, pool, sr, c0, min(kChanBlock, channels - c0), dst, smem_raw);
 }
 
-// backward: scatter with fp32 atomics (ROIAlign_cuda.cu:178-254); one thread per (roi, c, bin)
-__global__ void roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ rois, int64_t total,
-                                     float scale, int channels, int height, int width, int ph, int pw, int sr,
-                                     float* __restrict__ grad_in) {
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int bw = (int)(idx % pw);
-        const int bh = (int)((idx / pw) % ph);
-        const int c = (int)((idx / ((int64_t)pw * ph)) % channels);
-        const int n = (int)(idx / ((int64_t)pw * ph * channels));
-        const float* r = rois + (size_t)n * 5;
-        const int b = (int)r[0];
-        const float roi_start_w = r[1] * scale, roi_start_h = r[2] * scale;
-        const float roi_end_w = r[3] * scale, roi_end_h = r[4] * scale;
-        const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f);
-        const float roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
-        const float bin_h = roi_height / (float)ph, bin_w = roi_width / (float)pw;
-        float* dst = grad_in + ((size_t)b * channels + c) * height * width;
-        const float go = grad[idx];
-        const float count = (float)(sr * sr);
-        for (int iy = 0; iy < sr; ++iy) {
-            float y = roi_start_h + bh * bin_h + (float)(iy + .5f) * bin_h / (float)sr;
-            for (int ix = 0; ix < sr; ++ix) {
-                float x = roi_start_w + bw * bin_w + (float)(ix + .5f) * bin_w / (float)sr;
-                float yy = y;
-                if (yy < -1.0f || yy > (float)height || x < -1.0f || x > (float)width) continue;
-                if (yy <= 0.f) yy = 0.f;
-                if (x <= 0.f) x = 0.f;
-                int y_low = (int)yy, x_low = (int)x, y_high, x_high;
-                if (y_low >= height - 1) { y_high = y_low = height - 1; yy = (float)y_low; } else y_high = y_low + 1;
-                if (x_low >= width - 1) { x_high = x_low = width - 1; x = (float)x_low; } else x_high = x_low + 1;
-                const float ly = yy - (float)y_low, lx = x - (float)x_low;
-                const float hy = 1.f - ly, hx = 1.f - lx;
-                atomicAdd(dst + y_low * width + x_low, go * (hy * hx) / count);
-                atomicAdd(dst + y_low * width + x_high, go * (hy * lx) / count);
-                atomicAdd(dst + y_high * width + x_low, go * (ly * hx) / count);
-                atomicAdd(dst + y_high * width + x_high, go * (ly * lx) / count);
-            }
+// Map-resident kernel, grid (n_images, maps, channels / 8): map 0 = the depth map, map 1 + l = FPN level l (resident ones).
+// The CTA stages its 8 channels of the whole map as [position][9] and pools every box of the image that reads this map.
+__global__ void __launch_bounds__(kThreads, 2)
+roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
+                           int depth_resident, int channels, const float* __restrict__ boxes,
+                           const int32_t* __restrict__ box_off, int pool, int sr, float* __restrict__ out_rgb,
+                           float* __restrict__ out_depth) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int img = blockIdx.x, m = blockIdx.y;
+    const int l = m - 1;
+    if (m == 0 ? !depth_resident : !lv.resident[l]) return;
+    const int bins = pool * pool, spp = sr * sr, ntap = bins * spp;
+    int4* tp = reinterpret_cast<int4*>(smem);
+    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
+    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));   // [kMapChan][bins + 1]
+    float* map = tile + kMapChan * (bins + 1);
+    const int H = m == 0 ? depth_h : lv.h[l], W = m == 0 ? depth_w : lv.w[l];
+    const float scale = m == 0 ? depth_scale : lv.scale[l];
+    const int c0 = blockIdx.z * kMapChan, nc = min(kMapChan, channels - c0);
+    const int n0 = box_off[img], n1 = box_off[img + 1];
+    const int tid = threadIdx.x;
+    // does any box of the image read this map?  (depth: all of them)
+    if (m > 0) {
+        int any = 0;
+        for (int n = n0 + tid; n < n1; n += kThreads) {
+            const float4 bx = __ldg((const float4*)boxes + n);
+            any |= map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) == l;
+        }
+        if (!__syncthreads_or(any)) return;
+    } else if (n1 <= n0) {
+        return;
+    }
+    const float* src = (m == 0 ? depth : lv.feat[l]) + ((size_t)img * channels + c0) * H * W;
+    constexpr int stride = kMapChan + 1;
+    const int hw = H * W;
+    // the nc planes are one contiguous range of nc * hw floats: consecutive threads copy consecutive elements
+    for (int e = tid; e < nc * hw; e += kThreads) {
+        const int c = e / hw, pos = e - c * hw;
+        __pipeline_memcpy_async(map + (size_t)pos * stride + c, src + e, sizeof(float));
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    float* out = m == 0 ? out_depth : out_rgb;
+    for (int n = n0; n < n1; ++n) {
+        const float4 bx = __ldg((const float4*)boxes + n);
+        if (m > 0 && map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) != l) continue;   // uniform across the CTA
+        __syncthreads();                                   // previous box: tile stored, taps consumed; first box: map staged
+        for (int k = tid; k < ntap; k += kThreads) {
+            int4 p;
+            float4 w;
+            sample_taps(k, bx.x, bx.y, bx.z, bx.w, scale, H, W, pool, pool, sr, p, w);
+            tp[k] = p.x < 0 ? make_int4(0, 0, 0, 0)
+                            : make_int4((p.x * W + p.y) * stride, (p.x * W + p.w) * stride, (p.z * W + p.y) * stride,
+                                        (p.z * W + p.w) * stride);
+            tw[k] = w;
+        }
+        __syncthreads();
+        pool_from_smem(tp, tw, map, kMapChan, nc, bins, spp, tile, 0);
+        __syncthreads();
+        float* dst = out + ((size_t)n * channels + c0) * bins;
+        for (int e = tid; e < nc * bins; e += kThreads) {
+            const int c = e / bins, b = e - c * bins;
+            dst[e] = tile[c * (bins + 1) + b];
         }
     }
 }
 
-int channel_slices(int n_items, int channels) {
-    // enough CTAs for >= 2 waves of 148 SMs x 2 resident CTAs, without slicing below 16 channels
-    int slices = 1;
-    while ((int64_t)n_items * slices < (int64_t)num_sms() * 4 && channels / (slices * 2) >= 16) slices *= 2;
-    return slices;
+// backward (replaces RoIAlignBackwardFeature, ROIAlign_cuda.cu:178-254: one thread per output element, 16 global fp32
+// atomics each): the same (roi, 32-channel block) tiling as the forward.  The roi's gradient tile is read with contiguous
+// loads, scattered into a shared-memory copy of the window (lanes own channels, so the lanes of a warp never collide;
+// warps working on neighbouring bins meet through shared-memory atomics), and the window is then added to the map once
+// per element with row-contiguous global atomics — rois overlap, so the map itself still needs them.
+__global__ void __launch_bounds__(kThreads, 2)
+roi_align_bwd_kernel(const float* __restrict__ grad, const float* __restrict__ rois, float scale, int channels, int height,
+                     int width, int ph, int pw, int sr, float* __restrict__ grad_in) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x;
+    const float* r = rois + (size_t)n * 5;
+    const int b = (int)r[0];
+    const int c0 = blockIdx.y * kChanBlock;
+    const int nch = min(kChanBlock, channels - c0);
+    const int bins = ph * pw, spp = sr * sr, ntap = bins * spp;
+    int4* tp = reinterpret_cast<int4*>(smem);
+    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
+    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));
+    float* win = tile + kChanBlock * (bins + 1);
+    const int win_floats = (kSmemBytes - (int)((uint8_t*)win - smem)) / (int)sizeof(float);
+    __shared__ int bounds[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        bounds[0] = 0x7fffffff; bounds[1] = -1; bounds[2] = 0x7fffffff; bounds[3] = -1;
+    }
+    __syncthreads();
+    compute_taps(tp, tw, bounds, r[1], r[2], r[3], r[4], scale, height, width, ph, pw, sr);
+    for (int e = tid; e < nch * bins; e += kThreads) {
+        const int c = e / bins, bb = e - c * bins;
+        tile[c * (bins + 1) + bb] = grad[((size_t)n * channels + c0) * bins + e];
+    }
+    __syncthreads();
+    if (bounds[1] < 0) return;                  // no sample inside the map: no gradient
+    const int y0 = bounds[0], x0 = bounds[2];
+    const int wh = bounds[1] - y0 + 1, ww = bounds[3] - x0 + 1;
+    const int nw = wh * ww;
+    const float count = (float)spp;
+    const size_t plane = (size_t)height * width;
+    float* dst_img = grad_in + ((size_t)b * channels + c0) * plane;
+    int cb = kChanBlock;
+    while (cb > 1 && nw * (cb + 1) > win_floats) cb >>= 1;
+    if (nw * (cb + 1) > win_floats) {           // window beyond shared memory: the element-wise scatter
+        for (int e = tid; e < nch * bins; e += kThreads) {
+            const int c = e / bins, bin = e - c * bins;
+            float* dst = dst_img + (size_t)c * plane;
+            const float go = tile[c * (bins + 1) + bin];
+            for (int s = 0; s < spp; ++s) {
+                const int4 p = tp[bin * spp + s];
+                const float4 w = tw[bin * spp + s];
+                if (p.x < 0) continue;
+                atomicAdd(dst + p.x * width + p.y, go * w.x / count);
+                atomicAdd(dst + p.x * width + p.w, go * w.y / count);
+                atomicAdd(dst + p.z * width + p.y, go * w.z / count);
+                atomicAdd(dst + p.z * width + p.w, go * w.w / count);
+            }
+        }
+        return;
+    }
+    const int stride = cb + 1;
+    for (int k = tid; k < ntap; k += kThreads) {
+        const int4 p = tp[k];
+        tp[k] = p.x < 0 ? make_int4(-1, 0, 0, 0)
+                        : make_int4(((p.x - y0) * ww + (p.y - x0)) * stride, ((p.x - y0) * ww + (p.w - x0)) * stride,
+                                    ((p.z - y0) * ww + (p.y - x0)) * stride, ((p.z - y0) * ww + (p.w - x0)) * stride);
+    }
+    const int bins_per_iter = 32 / cb;
+    const int cl = lane % cb, bsub = lane / cb;
+    for (int sub = 0; sub * cb < nch; ++sub) {
+        const int nc = min(cb, nch - sub * cb);
+        for (int e = tid; e < nw * stride; e += kThreads) win[e] = 0.f;
+        __syncthreads();
+        for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
+            const int bin = b0 + bsub;
+            if (bin < bins && cl < nc) {
+                const float go = tile[(sub * cb + cl) * (bins + 1) + bin];
+                for (int s = 0; s < spp; ++s) {
+                    const int4 p = tp[bin * spp + s];
+                    if (p.x < 0) continue;
+                    const float4 w = tw[bin * spp + s];
+                    atomicAdd(&win[p.x + cl], go * w.x / count);
+                    atomicAdd(&win[p.y + cl], go * w.y / count);
+                    atomicAdd(&win[p.z + cl], go * w.z / count);
+                    atomicAdd(&win[p.w + cl], go * w.w / count);
+                }
+            }
+        }
+        __syncthreads();
+        for (int rr = warp; rr < nc * wh; rr += kWarps) {
+            const int c = rr / wh, yy = rr - c * wh;
+            float* drow = dst_img + (size_t)(sub * cb + c) * plane + (size_t)(y0 + yy) * width + x0;
+            const float* srow = win + (size_t)yy * ww * stride + c;
+            for (int x = lane; x < ww; x += 32) {
+                const float v = srow[x * stride];
+                if (v != 0.f) atomicAdd(drow + x, v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Map-resident backward, grid (batch, channels / 8): the CTA owns 8 channels of one image's gradient map in shared memory
+// ([position][9], zero-initialised), scatters the gradient tiles of the image's rois into it (roi index ascending; lanes
+// own channels, warps working on neighbouring bins meet through shared-memory atomics) and writes the map out ONCE with
+// plain coalesced stores: no global atomics and no separate memset — every element of grad_in is written exactly once.
+__global__ void __launch_bounds__(kThreads, 2)
+roi_align_bwd_resident_kernel(const float* __restrict__ grad, const float* __restrict__ rois, int n_rois, float scale,
+                              int channels, int height, int width, int ph, int pw, int sr, float* __restrict__ grad_in) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int img = blockIdx.x;
+    const int c0 = blockIdx.y * kMapChan, nc = min(kMapChan, channels - c0);
+    const int bins = ph * pw, spp = sr * sr, ntap = bins * spp;
+    int4* tp = reinterpret_cast<int4*>(smem);
+    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
+    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));   // [kMapChan][bins + 1]
+    float* map = tile + kMapChan * (bins + 1);
+    constexpr int stride = kMapChan + 1;
+    const int hw = height * width;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < hw * stride; e += kThreads) map[e] = 0.f;
+    const float count = (float)spp;
+    const int bins_per_iter = 32 / kMapChan;
+    const int cl = lane % kMapChan, bsub = lane / kMapChan;
+    for (int n = 0; n < n_rois; ++n) {
+        const float* r = rois + (size_t)n * 5;
+        if ((int)r[0] != img) continue;                    // uniform across the CTA
+        __syncthreads();                                   // the previous roi's taps / tile are consumed (first: map zeroed)
+        for (int k = tid; k < ntap; k += kThreads) {
+            int4 p;
+            float4 w;
+            sample_taps(k, r[1], r[2], r[3], r[4], scale, height, width, ph, pw, sr, p, w);
+            tp[k] = p.x < 0 ? make_int4(-1, 0, 0, 0)
+                            : make_int4((p.x * width + p.y) * stride, (p.x * width + p.w) * stride,
+                                        (p.z * width + p.y) * stride, (p.z * width + p.w) * stride);
+            tw[k] = w;
+        }
+        const float* gsrc = grad + ((size_t)n * channels + c0) * bins;
+        for (int e = tid; e < nc * bins; e += kThreads) {
+            const int c = e / bins, b = e - c * bins;
+            tile[c * (bins + 1) + b] = gsrc[e];
+        }
+        __syncthreads();
+        for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
+            const int bin = b0 + bsub;
+            if (bin < bins && cl < nc) {
+                const float go = tile[cl * (bins + 1) + bin];
+                for (int s = 0; s < spp; ++s) {
+                    const int4 p = tp[bin * spp + s];
+                    if (p.x < 0) continue;
+                    const float4 w = tw[bin * spp + s];
+                    atomicAdd(&map[p.x + cl], go * w.x / count);
+                    atomicAdd(&map[p.y + cl], go * w.y / count);
+                    atomicAdd(&map[p.z + cl], go * w.z / count);
+                    atomicAdd(&map[p.w + cl], go * w.w / count);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* dst = grad_in + ((size_t)img * channels + c0) * hw;
+    for (int e = tid; e < nc * hw; e += kThreads) {
+        const int c = e / hw, pos = e - c * hw;
+        dst[e] = map[(size_t)pos * stride + c];
+    }
+}
+
+// floats the resident kernels need next to the map: taps + one [8][bins + 1] tile
+__host__ inline bool map_fits_resident(int h, int w, int pool, int sr) {
+    const size_t fixed = (size_t)pool * pool * sr * sr * (sizeof(int4) + sizeof(float4)) + (size_t)kMapChan * (pool * pool + 1) * sizeof(float);
+    return fixed + (size_t)h * w * (kMapChan + 1) * sizeof(float) <= (size_t)kSmemBytes;
 }
 
 DeviceOnce g_attr_set;
 int ensure_attrs() {
     if (!g_attr_set.pending()) return VETO_OK;
-    VETO_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Taps)));
-    VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Taps)));
+    VETO_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_align_bwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     g_attr_set.done();
     return VETO_OK;
 }
@@ -226,11 +546,9 @@ extern "C" int veto_roi_align_forward(const float* input_dev, int batch, int cha
     int rc = ensure_attrs();
     if (rc) return rc;
     set_tag(TAG_GATHER);
-    const int slices = channel_slices(n_rois, channels);
-    const int c_per = (channels + slices - 1) / slices;
-    dim3 grid(n_rois, slices);
-    roi_align_fwd_kernel<<<grid, kThreads, sizeof(Taps), (cudaStream_t)stream>>>(
-        input_dev, channels, height, width, rois_dev, spatial_scale, pooled_h, pooled_w, sampling_ratio, c_per, out_dev);
+    dim3 grid(n_rois, (channels + kChanBlock - 1) / kChanBlock);
+    roi_align_fwd_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        input_dev, channels, height, width, rois_dev, spatial_scale, pooled_h, pooled_w, sampling_ratio, out_dev);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
@@ -241,14 +559,26 @@ extern "C" int veto_roi_align_backward(const float* grad_dev, const float* rois_
     VETO_REQUIRE(grad_input_dev && batch > 0 && channels > 0 && height > 0 && width > 0 && sampling_ratio > 0, VETO_ERR_ARG,
                  "veto_roi_align_backward: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
+    VETO_REQUIRE(n_rois == 0 || (grad_dev && rois_dev), VETO_ERR_ARG, "veto_roi_align_backward: bad argument");
+    VETO_REQUIRE(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w * sampling_ratio * sampling_ratio <= kMaxTaps,
+                 VETO_ERR_UNSUPPORTED, "veto_roi_align_backward: needs ph*pw*sr^2 <= %d", kMaxTaps);
+    int rc = ensure_attrs();
+    if (rc) return rc;
+    set_tag(TAG_GATHER);
+    if (pooled_h == pooled_w && map_fits_resident(height, width, pooled_h, sampling_ratio)) {
+        // the map of one image (8 channels) fits shared memory: no global atomics, no memset
+        dim3 rgrid(batch, (channels + kMapChan - 1) / kMapChan);
+        roi_align_bwd_resident_kernel<<<rgrid, kThreads, kSmemBytes, s>>>(grad_dev, rois_dev, n_rois, spatial_scale, channels,
+                                                                         height, width, pooled_h, pooled_w, sampling_ratio,
+                                                                         grad_input_dev);
+        VETO_LAUNCH_CHECK();
+        return VETO_OK;
+    }
     VETO_CUDA(cudaMemsetAsync(grad_input_dev, 0, (size_t)batch * channels * height * width * sizeof(float), s));
     if (n_rois == 0) return VETO_OK;
-    VETO_REQUIRE(grad_dev && rois_dev, VETO_ERR_ARG, "veto_roi_align_backward: bad argument");
-    const int64_t total = (int64_t)n_rois * channels * pooled_h * pooled_w;
-    const int64_t blocks = (total + 255) / 256;
-    const int grid = (int)(blocks < (int64_t)num_sms() * 32 ? blocks : (int64_t)num_sms() * 32);
-    roi_align_bwd_kernel<<<grid, 256, 0, s>>>(grad_dev, rois_dev, total, spatial_scale, channels, height, width, pooled_h,
-                                              pooled_w, sampling_ratio, grad_input_dev);
+    dim3 grid(n_rois, (channels + kChanBlock - 1) / kChanBlock);
+    roi_align_bwd_kernel<<<grid, kThreads, kSmemBytes, s>>>(grad_dev, rois_dev, spatial_scale, channels, height, width, pooled_h,
+                                                           pooled_w, sampling_ratio, grad_input_dev);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }
@@ -281,12 +611,29 @@ extern "C" int veto_roi_gather_forward(const float* const* feats_dev, const int3
     lv.n_levels = n_levels;
     lv.k_min = k_min;
     lv.k_max = k_max;
-    const int slices = channel_slices(2 * n_boxes, channels);
-    const int c_per = (channels + slices - 1) / slices;
-    dim3 grid(n_boxes, 2, slices);
-    roi_gather_kernel<<<grid, kThreads, sizeof(Taps), (cudaStream_t)stream>>>(
-        lv, depth_dev, depth_h, depth_w, depth_scale, channels, boxes_dev, box_offsets_dev, n_images, pool, sampling_ratio,
-        c_per, out_rgb_dev, out_depth_dev, levels_out_dev);
-    VETO_LAUNCH_CHECK();
+    // small maps are pooled by the map-resident kernel (one staging per image), the others per roi by the window kernel
+    bool any_resident = false, all_resident = true;
+    for (int l = 0; l < n_levels; ++l) {
+        lv.resident[l] = map_fits_resident(feat_h[l], feat_w[l], pool, sampling_ratio) ? 1 : 0;
+        any_resident |= lv.resident[l] != 0;
+        all_resident &= lv.resident[l] != 0;
+    }
+    const int depth_resident = map_fits_resident(depth_h, depth_w, pool, sampling_ratio) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (any_resident || depth_resident) {
+        dim3 rgrid(n_images, 1 + n_levels, (channels + kMapChan - 1) / kMapChan);
+        roi_gather_resident_kernel<<<rgrid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale,
+                                                                      depth_resident, channels, boxes_dev, box_offsets_dev, pool,
+                                                                      sampling_ratio, out_rgb_dev, out_depth_dev);
+        VETO_LAUNCH_CHECK();
+    }
+    if (!all_resident || !depth_resident || levels_out_dev) {
+        // grid.y = 1 with every level resident only writes levels_out (the CTAs return at once)
+        dim3 grid(n_boxes, all_resident && depth_resident ? 1 : (channels + kChanBlock - 1) / kChanBlock, depth_resident ? 1 : 2);
+        roi_gather_kernel<<<grid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, channels, boxes_dev,
+                                                            box_offsets_dev, n_images, pool, sampling_ratio, out_rgb_dev,
+                                                            out_depth_dev, levels_out_dev);
+        VETO_LAUNCH_CHECK();
+    }
     return VETO_OK;
 }

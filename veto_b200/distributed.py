@@ -53,24 +53,70 @@ def max_over_ranks(value: float, device) -> float:
     return float(t.item())
 
 
-def allreduce_gradients(params: Sequence[torch.Tensor], group=None) -> None:
+def _flat_buckets(grads: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """The gradients grouped by the storage they live in: the relation head hands autograd VIEWS of one flat buffer
+    (predictor._TrainStep), the depth backbone views of another (ops.depth_backbone_backward), so the exchange can sweep
+    each buffer in place.  Returns one 1-D alias per storage covering the span its gradients occupy (padding between views
+    is reduced along with them: harmless); a gradient that is not contiguous comes back as is."""
+    spans = {}
+    loose = []
+    for g in grads:
+        if not g.is_contiguous():
+            loose.append(g)
+            continue
+        key = (g.untyped_storage().data_ptr(), g.dtype, g.device)
+        lo, hi = g.storage_offset(), g.storage_offset() + g.numel()
+        if key in spans:
+            spans[key][1] = min(spans[key][1], lo)
+            spans[key][2] = max(spans[key][2], hi)
+        else:
+            spans[key] = [g, lo, hi]
+    out = loose
+    for g, lo, hi in spans.values():
+        out.append(torch.empty(0, dtype=g.dtype, device=g.device).set_(g.untyped_storage(), lo, (hi - lo,)))
+    return out
+
+
+def allreduce_gradients(params: Sequence[torch.Tensor], group=None, async_op: bool = False):
     """The data-parallel gradient exchange of the training step (reference: DistributedDataParallel's bucketed NCCL
-    all-reduce, tools/relation_train_net.py:372-380): the gradients of all trained parameters (about 17.6 M fp32
-    values for the relation head) travel as ONE flat bucket — over NVSwitch the cost is latency, not links — and come
-    back averaged over ranks, like DDP."""
+    all-reduce of the relation head + depth backbone gradients, tools/relation_train_net.py:372-380), averaged over ranks
+    like DDP.  The gradients of this library already live in one flat buffer per module, so each buffer is all-reduced IN
+    PLACE — no concatenation, no copy back (over NVSwitch the cost is latency, not links).  async_op=True returns the NCCL
+    work handles (finish with ``finish_gradient_sync``) so that the exchange of a module whose gradients are ready can run
+    under the backward pass of the next one."""
     if not (dist.is_available() and dist.is_initialized()):
-        return
+        return []
     world = dist.get_world_size(group)
     if world == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+        return []
+    grads = [p.grad if isinstance(p, torch.nn.Parameter) or getattr(p, "grad", None) is not None else None for p in params]
+    grads = [g for g in grads if g is not None]
+    works = []
+    for flat in _flat_buckets(grads):
+        if hasattr(dist.ReduceOp, "AVG") and flat.is_cuda:
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=True), None, world))
+        else:   # gloo (CPU tests): sum, then divide when the work is finished
+            works.append((dist.all_reduce(flat, group=group, async_op=True), flat, world))
+    if async_op:
+        return works
+    finish_gradient_sync(works)
+    return []
+
+
+def allreduce_flat(flat: torch.Tensor, group=None):
+    """Start the in-place averaging all-reduce of one flat gradient buffer; returns work handles for finish_gradient_sync
+    (an empty list without a process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return []
+    world = dist.get_world_size(group)
+    if hasattr(dist.ReduceOp, "AVG") and flat.is_cuda:
+        return [(dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=True), None, world)]
+    return [(dist.all_reduce(flat, group=group, async_op=True), flat, world)]
+
+
+def finish_gradient_sync(works) -> None:
+    """Wait for the all-reduces started with async_op=True (the wait only orders the current stream behind NCCL's)."""
+    for work, flat, world in works:
+        work.wait()
+        if flat is not None:
+            flat.div_(world)

@@ -13,6 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 from . import build as _build
 
 VETO_MAX_LAYERS = 16
+ABI_VERSION = 4     # include/veto_b200.h VETO_ABI_VERSION
 PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16C8, PREC_F16 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16c8": PREC_F16C8, "f16": PREC_F16}
 # f16c8 / f16 are inference modes of the encoder (include/veto_b200.h): the training step and the depth backbone of a
@@ -110,6 +111,7 @@ _PROTOS = {
     "veto_sgg_match": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_float, _fp, _fp, c_void_p]),
     "veto_relsample_detect": (c_int, [_fp] * 10 + [POINTER(c_int32), POINTER(c_int32), c_int, c_float, c_int, c_int, c_int, c_int,
                                       ctypes.c_uint64, _fp, _fp, _fp, _fp, _fp, c_void_p]),
+    "veto_meet_group_labels": (c_int, [_fp, c_int64, _fp, _fp, _fp, c_int, c_int, c_int, ctypes.c_uint64, _fp, _fp, _fp, c_void_p]),
     "veto_relsample_gtbox": (c_int, [_fp, _fp, _fp, POINTER(c_int32), c_int, c_int, c_int, ctypes.c_uint64, _fp, _fp, _fp, _fp,
                                      c_void_p]),
     "veto_postprocess_meet": (c_int, [_fp, c_int, _fp, c_int, _fp, c_int, _fp, _fp, _fp, _fp, c_int, c_int64, _fp, _fp, _fp, _fp,
@@ -148,7 +150,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if build_if_missing:
         try:
             if _build.needs_build():
-                _build.build_library()
+                _build.build_library_locked()   # every rank of a torchrun job gets here at once on a fresh checkout
         except Exception as e:  # no nvcc on the box: fall through to whatever was shipped
             if not os.path.exists(path):
                 raise RuntimeError(f"libveto_b200.so is missing and cannot be built: {e}") from e
@@ -159,7 +161,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.veto_abi_version() != 3:
+    if lib.veto_abi_version() != ABI_VERSION:
         raise RuntimeError("libveto_b200.so ABI version mismatch")
     _lib = lib
     return lib

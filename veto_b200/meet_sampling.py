@@ -2,10 +2,12 @@
 
 The reference decides, pair by pair in a Python loop with one ``.item()`` device sync per pair
 (roi_relation_predictors.py:3940-3969), which group heads a training pair contributes to, then relabels the chosen
-pairs per group with another per-element loop (:3812-3821).  Here the predicate labels cross to the host ONCE, the
-draws use the same ``random`` stream in the same order (so a seeded run picks the same pairs as the reference), and
-the result is a dense ``[n_groups, R]`` table of group-local labels (-1 = pair not in that group's loss) that
-``veto_relation_train_step`` consumes on the device.
+pairs per group with another per-element loop (:3812-3821).  The product path does both on the device
+(``veto_meet_group_labels``, csrc/meet_sample.cu, via ``ops.meet_group_labels``): a dense ``[n_groups, R]`` table of
+group-local labels (-1 = pair not in that group's loss) that ``veto_relation_train_step`` consumes, nothing crossing to
+the host.  This module builds the small tables that kernel reads (``sample_rate_matrix``, ``local_label_table``) and
+keeps the host restatement of the two loops (``group_sampling``, ``group_local_labels``) — the checker the tests compare
+the kernel with, and the way to replay the reference's seeded ``random`` stream (``reference_draws``).
 
 Tables: ``PREDICATE_COUNTS`` are the per-predicate training-set frequencies the reference hard-codes
 (SHA_GCL_extra/extra_function_utils.py:186-205, predicates in the frequency-sorted order the MEET datasets use).
@@ -106,3 +108,61 @@ def group_local_labels(rel_labels: Sequence[int], chosen: Sequence[Sequence[int]
         rows = np.asarray(rows, dtype=np.int64)
         out[k, rows] = position[labels[rows]]
     return out
+
+
+def local_label_table(incre_idx: Sequence[int], n_groups: int) -> np.ndarray:
+    """int32 [n_groups, num_rel]: head k's local label of global predicate p (roi_relation_predictors.py:3806-3821):
+    0 for the background, the 1-based position of p among the head's member predicates, len(members) + 1 otherwise."""
+    incre = np.asarray(incre_idx, dtype=np.int64)
+    out = np.zeros((n_groups, incre.size), dtype=np.int32)
+    for k in range(n_groups):
+        members = np.nonzero(incre == k + 1)[0]
+        out[k, :] = len(members) + 1
+        out[k, members] = np.arange(1, len(members) + 1)
+        out[k, 0] = 0
+    return out
+
+
+def reference_draws(rel_labels: Sequence[int], n_groups: int, zero_mode: str = "rand_insert", rng=_random):
+    """The draws the reference's loop (:3940-3969) takes from ``random`` for these labels, in its order: (u float64 [R],
+    bg_head int32 [R]) to inject into ``ops.meet_group_labels`` so that a run seeded like the reference picks the same
+    pairs.  One draw per pair: randint for a 'rand_insert' background pair, random() for a foreground pair and for a
+    'rand_choose' background pair, none for 'all_include' backgrounds."""
+    u = np.zeros(len(rel_labels), dtype=np.float64)
+    head = np.zeros(len(rel_labels), dtype=np.int32)
+    for i, p in enumerate(rel_labels):
+        if p == 0:
+            if zero_mode == "rand_insert":
+                head[i] = rng.randint(0, n_groups - 1)
+            elif zero_mode == "rand_choose":
+                u[i] = rng.random()
+        else:
+            u[i] = rng.random()
+    return u, head
+
+
+class LazyExpertDist:
+    """What VETOPredictor_MEET.forward returns as its 5th value in train() mode: the reference hands back
+    ``expert_dist`` = the chosen-rows lists, appended once per pair (:3969).  Nothing on the training path reads it
+    (relation_head.py:196-203), so the device table is converted to those lists only if somebody indexes it."""
+
+    def __init__(self, table):
+        self.table = table            # int64 [n_groups, R] on the device
+        self._lists = None
+
+    def chosen(self):
+        if self._lists is None:
+            t = self.table.cpu().numpy()
+            self._lists = [np.nonzero(row >= 0)[0].tolist() for row in t]
+        return self._lists
+
+    def __len__(self):
+        return int(self.table.shape[1])
+
+    def __getitem__(self, i):
+        if not -len(self) <= i < len(self):
+            raise IndexError(i)
+        return self.chosen()
+
+    def __iter__(self):
+        return (self.chosen() for _ in range(len(self)))

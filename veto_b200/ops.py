@@ -483,6 +483,38 @@ def relsample_detect(prp_boxes: Sequence[torch.Tensor], prp_labels: Sequence[tor
 # --------------------------------------------------------------------------------------------
 # a10: MEET's per-class NMS label assignment (SGDet test)
 # --------------------------------------------------------------------------------------------
+ZERO_MODES = {"rand_insert": 0, "rand_choose": 1, "all_include": 2}
+
+
+def meet_group_labels(rel_labels: torch.Tensor, incre_idx: torch.Tensor, rates: torch.Tensor, local_label: torch.Tensor,
+                      zero_mode: str, seed: int, draws: Optional[torch.Tensor] = None,
+                      bg_heads: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cur_chosen_matrix + per-head relabelling of VETOPredictor_MEET's training branch on the device
+    (roi_relation_predictors.py:3940-3969, 3812-3821): int64 [n_groups, R] head-local labels, -1 = pair not in the head's
+    loss.  Tables (device): incre_idx int32 [num_rel], rates float64 [G, num_rel], local_label int32 [G, num_rel]."""
+    L.require_device()
+    if zero_mode not in ZERO_MODES:
+        raise ValueError(f"ZERO_LABEL_PADDING_MODE must be one of {sorted(ZERO_MODES)}, got {zero_mode!r}")
+    rel_labels = rel_labels.to(torch.int64).contiguous()
+    G, num_rel = rates.shape
+    if (rates.dtype != torch.float64 or incre_idx.dtype != torch.int32 or local_label.dtype != torch.int32
+            or tuple(local_label.shape) != (G, num_rel) or incre_idx.numel() != num_rel):
+        raise RuntimeError("meet_group_labels: tables must be float64 [G,num_rel] / int32 [num_rel] / int32 [G,num_rel]")
+    R = rel_labels.numel()
+    out = torch.empty((G, R), dtype=torch.int64, device=rel_labels.device)
+    if R:
+        if draws is not None:
+            draws = draws.to(device=rel_labels.device, dtype=torch.float64).contiguous()
+        if bg_heads is not None:
+            bg_heads = bg_heads.to(device=rel_labels.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(rel_labels.device):
+            L.check(L.load().veto_meet_group_labels(rel_labels.data_ptr(), R, incre_idx.data_ptr(), rates.data_ptr(),
+                                                    local_label.data_ptr(), G, num_rel, ZERO_MODES[zero_mode],
+                                                    int(seed) & (2 ** 64 - 1), L.ptr(draws), L.ptr(bg_heads), out.data_ptr(),
+                                                    L.stream_ptr()), "veto_meet_group_labels")
+    return out
+
+
 def obj_nms_per_cls(scores: torch.Tensor, boxes_per_cls: torch.Tensor, n_boxes: Sequence[int], thresh: float,
                     late_nms: bool = False) -> torch.Tensor:
     """Ensemble.nms_per_cls (roi_relation_predictors.py:3855-3874), or with late_nms obj_prediction_nms

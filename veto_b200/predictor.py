@@ -12,12 +12,13 @@ CPU fallback: without the library or an sm_100 device, forward raises.
 (roi_relation_predictors.py:4131-4136) as a scalar wired into autograd: ``veto_relation_train_step`` computes the
 loss AND every gradient in one library call, and ``loss.backward()`` hands those gradients to the parameters and
 to ``roi_depth_features`` (so the depth backbone trains through VETOFeatureExtractor's ROIAlign backward).
-VETOPredictor_MEET in ``train()`` mode samples the pairs of every group head on the host (meet_sampling.py, the
-reference's ``random`` stream) and returns one 'group_k_CE_loss' per head from the same library call.
+VETOPredictor_MEET in ``train()`` mode samples and relabels the pairs of every group head on the device
+(``veto_meet_group_labels``) and returns one 'group_k_CE_loss' per head from the same library call.
 """
 from __future__ import annotations
 
 import math
+import random as _random
 from typing import List, Optional
 
 import torch
@@ -268,7 +269,7 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, run, roi_rgb, roi_depth, *params):
         loss, g_depth, g_rgb, flat, grads = run(want_depth=ctx.needs_input_grad[3], want_rgb=ctx.needs_input_grad[2])
-        ctx.flat, ctx.grads, ctx.g_depth, ctx.g_rgb = flat, grads, g_depth, g_rgb
+        ctx.flat, ctx.grads, ctx.g_depth, ctx.g_rgb, ctx.module = flat, grads, g_depth, g_rgb, module
         return loss.reshape(()) if loss.numel() == 1 else loss
 
     @staticmethod
@@ -277,6 +278,11 @@ class _TrainStep(torch.autograd.Function):
             uniform = (gout == gout[0]).all()
             gout = torch.where(uniform, gout[0], torch.full_like(gout[0], float("nan")))
         ctx.flat.mul_(gout)  # one kernel over the flat gradient buffer; `grads` are views of it
+        # data-parallel hook (veto_b200.distributed.allreduce_flat): every gradient of the head is final here, before
+        # autograd walks on into the ROIAlign and depth-backbone backward — the exchange can run underneath them
+        hook = getattr(ctx.module, "grad_sync", None)
+        if hook is not None:
+            hook(ctx.flat)
         scale = lambda t: None if t is None else t * gout
         # hand the views over without keeping a reference: autograd's AccumulateGrad then adopts them as .grad instead
         # of cloning each one (about 90 small copy kernels per step), and every .grad stays a view of the one flat
@@ -398,13 +404,17 @@ class Ensemble(_Trunk):
         `rel_labels` is the concatenated label tensor, `cur_chosen_matrix` = expert_dist of VETOPredictor_MEET."""
         if cur_chosen_matrix is None:
             raise RuntimeError("Ensemble in train() mode needs cur_chosen_matrix (VETOPredictor_MEET.forward builds it)")
-        labels_host = rel_labels if isinstance(rel_labels, (list, tuple)) else rel_labels.tolist()
-        table = meet_sampling.group_local_labels(labels_host, cur_chosen_matrix[0], self.incre_idx_list)   # [G, R]
+        dev = roi_features.device
+        if isinstance(cur_chosen_matrix, meet_sampling.LazyExpertDist):
+            table = cur_chosen_matrix.table                       # [G, R] head-local labels, built on the device
+        else:   # chosen-rows lists as the reference passes them (a caller that sampled on the host): relabel on the host
+            labels_host = rel_labels if isinstance(rel_labels, (list, tuple)) else rel_labels.tolist()
+            table = torch.from_numpy(meet_sampling.group_local_labels(labels_host, cur_chosen_matrix[0],
+                                                                      self.incre_idx_list)).to(dev, non_blocking=True)
         heads = self._head_sets()
         # group index of every head, in _head_sets order (expert-major)
         per_head = [k for _ in range(self.experts_per_group if self.expert_group else 1) for k in range(self.group_num)]
-        dev = roi_features.device
-        head_labels = torch.from_numpy(table[per_head]).to(dev, non_blocking=True)
+        head_labels = table if per_head == list(range(self.group_num)) else table[per_head]
         add_losses = {}
         if self.mode != "predcls":  # :3826-3830: CE of the detached detector logits, a constant of the step
             obj_logits = torch.cat([p.get_field("predict_logits") for p in proposals], 0).detach()
@@ -478,18 +488,38 @@ class VETOPredictor_MEET(nn.Module):
         self.ensemble_type = config.ENSEMBLE_LEARNING.TYPE
         self.zero_label_padding_mode = config.GCL_SETTING.ZERO_LABEL_PADDING_MODE
         self.sample_rate_matrix = meet_sampling.sample_rate_matrix(ds, self.max_group_element_number_list)
+        self._tables = None
+        self.reference_draws = bool(C.get(config, "VETO_B200.MEET_REFERENCE_DRAWS", False))
         self.model = Ensemble(config, self.mode, self.params, self.num_groups, self.experts_per_group,
                               self.max_group_element_number_list, self.incre_idx_list)
+
+    def _sampling_tables(self, device):
+        """(incre_idx int32 [num_rel], rates float64 [G, num_rel], local_label int32 [G, num_rel]) on `device`."""
+        if self._tables is None or self._tables[0].device != device:
+            import numpy as np
+            self._tables = (torch.tensor(self.incre_idx_list, dtype=torch.int32, device=device),
+                            torch.from_numpy(np.ascontiguousarray(self.sample_rate_matrix, dtype=np.float64)).to(device),
+                            torch.from_numpy(meet_sampling.local_label_table(self.incre_idx_list, self.num_groups)).to(device))
+        return self._tables
 
     def forward(self, proposals, rel_pair_idxs, rel_labels, logger, roi_features=None, roi_depth_features=None,
                 rel_binarys=None):
         if self.training:
-            # :3926-3969 — the reference walks the pairs with one .item() sync each; here the labels cross once
-            labels_host = torch.cat(list(rel_labels), 0).tolist()
-            chosen = meet_sampling.group_sampling(labels_host, self.incre_idx_list, self.sample_rate_matrix,
-                                                  self.num_groups, self.zero_label_padding_mode)
-            expert_dist = [chosen] * len(labels_host)   # the reference appends the same list once per pair (:3969)
-            _, _, add_losses, _ = self.model(proposals, rel_pair_idxs, labels_host, logger, roi_features=roi_features,
+            # :3926-3969 — the reference walks the pairs in Python with one .item() sync each; here one kernel draws and
+            # relabels every pair on the device.  The seed comes from Python's `random` (the reference's source of
+            # randomness for this step), so random.seed(...) makes a run reproducible; no device sync.
+            labels = torch.cat(list(rel_labels), 0).long()
+            tables = self._sampling_tables(labels.device)
+            draws = heads = None
+            if self.reference_draws:
+                # parity mode (VETO_B200.MEET_REFERENCE_DRAWS): replay the reference's own draws from `random`, in its
+                # order, so that a run seeded like the reference samples the same pairs (one D2H of the labels)
+                draws, heads = meet_sampling.reference_draws(labels.tolist(), self.num_groups, self.zero_label_padding_mode)
+                draws, heads = torch.from_numpy(draws), torch.from_numpy(heads)
+            table = ops.meet_group_labels(labels, *tables, self.zero_label_padding_mode, seed=_random.getrandbits(63),
+                                          draws=draws, bg_heads=heads)
+            expert_dist = meet_sampling.LazyExpertDist(table)
+            _, _, add_losses, _ = self.model(proposals, rel_pair_idxs, labels, logger, roi_features=roi_features,
                                              roi_depth_features=roi_depth_features, cur_chosen_matrix=expert_dist)
             return None, None, dict(add_losses), self.incre_idx_list, expert_dist, None
         obj_dists, rel_dists, add_losses, _ = self.model(proposals, rel_pair_idxs, rel_labels, logger,
