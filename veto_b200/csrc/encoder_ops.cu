@@ -540,6 +540,8 @@ attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f
                         for (int mt = 0; mt < 2; ++mt)
                             mma_bf16_16816(O[mt][j], term == 1 ? pl[mt][ks2] : ph[mt][ks2], term == 2 ? vl[j] : vh[j]);
             }
+            // the accumulator fragments own 2 columns of 8 rows each: through the Q tile (free since barrier 2) so that
+            // the global stores below are whole 16-byte / 8-byte pieces of contiguous rows
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -547,25 +549,31 @@ attention_mma2_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f
                     const int row = 16 * mt + g + 8 * hrow;
                     if (row < kTokens) {
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            const float v0 = O[mt][j][2 * hrow], v1 = O[mt][j][2 * hrow + 1];
-                            const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 8 * (3 * blk + j) + 2 * t;
-                            if (out_f32) *(float2*)(out_f32 + o) = make_float2(v0, v1);
-                            if (out_hi) {
-                                if (fmt == FMT_F16C8) {
-                                    store_act2_f16c8(out_hi, out_lo, o, v0, v1);
-                                } else {
-                                    uint32_t hh, ll;
-                                    split_pair(v0, v1, hh, ll);
-                                    *(uint32_t*)(out_hi + o) = hh;
-                                    if (out_lo) *(uint32_t*)(out_lo + o) = ll;
-                                }
-                            }
-                        }
+                        for (int j = 0; j < 3; ++j)
+                            *(float2*)(sQ + row * ATT_QK_STRIDE + 8 * (3 * blk + j) + 2 * t) =
+                                make_float2(O[mt][j][2 * hrow], O[mt][j][2 * hrow + 1]);
                     }
                 }
         }
-        pair_bar();  // (3) both warps are done with the staged operands and the tiles
+        pair_bar();  // (3) the 19 x 96 output tile is complete; V is no longer read
+        for (int idx = lane64; idx < kTokens * (kHeadDim / 4); idx += 64) {
+            const int row = idx / (kHeadDim / 4), c4 = idx - row * (kHeadDim / 4);
+            const float4 v = *(const float4*)(sQ + row * ATT_QK_STRIDE + 4 * c4);
+            const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 4 * c4;
+            if (out_f32) *(float4*)(out_f32 + o) = v;
+            if (out_hi) {
+                if (fmt == FMT_F16C8) {
+                    store_act4_f16c8(out_hi, out_lo, o, v);
+                } else {
+                    uint2 hh, ll;
+                    split_pair(v.x, v.y, hh.x, ll.x);
+                    split_pair(v.z, v.w, hh.y, ll.y);
+                    *(uint2*)(out_hi + o) = hh;
+                    if (out_lo) *(uint2*)(out_lo + o) = ll;
+                }
+            }
+        }
+        pair_bar();  // (4) the tile is stored before the next item's cp.async overwrites it
     }
 }
 
