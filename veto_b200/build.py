@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libveto_b200.so")
 
 SOURCES = ["api.cu", "pairs.cu", "roi_gather.cu", "box_stage.cu", "tokens.cu", "encoder_ops.cu",
-           "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_tc.cu", "postprocess.cu", "train.cu", "train_api.cu", "gemm_tn2.cu", "obj_nms.cu", "relsample.cu", "meet_sample.cu", "sgg_eval.cu", "depth_backbone.cu"]
+           "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention_tc.cu", "attention_split.cu", "postprocess.cu", "train.cu", "train_api.cu", "gemm_tn2.cu", "obj_nms.cu", "relsample.cu", "meet_sample.cu", "sgg_eval.cu", "depth_backbone.cu"]
 # bit-exact ROIAlign needs un-fused multiply-adds (see roi_gather.cu)
 EXTRA = {"roi_gather.cu": ["--fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

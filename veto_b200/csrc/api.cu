@@ -64,6 +64,7 @@ namespace {
 struct WorkLayout {
     size_t pos, emb, lso, cso, pa_d, pa_v, so_d, so_v;  // box level
     size_t x, xn, qkv, h, q_cls, x_cls;                 // chunk level
+    size_t xo, ln_parts, ln_stats;                      // LayerNorm fusion: x in operand format, its row statistics
     size_t total;
     int32_t chunk;
 };
@@ -73,6 +74,26 @@ struct WorkLayout {
 // profiles/r2_chunk_sweep.jsonl): 499 -> 514 ms, 997 -> 450, 1994 -> 423, 3988 -> 412, 7976 -> 404 ms per step: the
 // intermediates never fit L2 usefully, so larger chunks only amortise launch tails (2.4 GB of workspace at this size).
 constexpr int32_t kDefaultChunk = 7976;
+
+// VETO_ATTENTION_SPLIT=0: the fp32-qkv attention kernel in every mode (A/B measurements, diagnosis)
+bool split_attention_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VETO_ATTENTION_SPLIT");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
+// VETO_LN_FUSION=0 keeps the LayerNorm kernels everywhere (A/B measurements, diagnosis)
+bool ln_fusion_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VETO_LN_FUSION");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
 
 WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, int32_t chunk_pairs) {
     WorkLayout W{};
@@ -97,6 +118,11 @@ WorkLayout work_layout(const veto_config& c, int32_t n_boxes, int64_t n_pairs, i
     W.h = k.take(act_bytes(c.precision, M * kMlp));
     W.q_cls = k.take(sizeof(float) * (size_t)chunk * kDim);
     W.x_cls = k.take(sizeof(float) * (size_t)chunk * kDim);
+    if (prec_two_arrays(c.precision)) {
+        W.xo = k.take(act_bytes(c.precision, M * kDim));
+        W.ln_parts = k.take(sizeof(float2) * (kDim / 64) * M);
+        W.ln_stats = k.take(sizeof(float2) * M);
+    }
     W.total = k.off;
     return W;
 }
@@ -149,8 +175,9 @@ extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, 
         // one launch re-splits every GEMM weight into its bf16 hi (+ lo) operand arrays
         SplitJob jobs[kMaxSplitJobs];
         int nj = 0;
-        auto split = [&](const float* src, size_t hi, size_t lo, size_t n, int fmt = FMT_BF16) {
-            jobs[nj++] = SplitJob{src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n, fmt};
+        auto split = [&](const float* src, size_t hi, size_t lo, size_t n, int fmt = FMT_BF16, const float* col_scale = nullptr,
+                         int row_len = 0) {
+            jobs[nj++] = SplitJob{src, (__nv_bfloat16*)(P + hi), lo ? (__nv_bfloat16*)(P + lo) : nullptr, n, fmt, col_scale, row_len};
         };
         const int efmt = prec_encoder_fmt(cfg->precision);   // encoder weights in the mode's operand format
         split((const float*)(P + L.w_d2), L.d2_hi, L.d2_lo, (size_t)2 * kDimDepth * kPatchVec);
@@ -161,6 +188,15 @@ extern "C" int veto_pack_weights(const veto_config* cfg, const veto_weights* w, 
             split(w->out_w[l], L.out_hi[l], L.out_lo[l], (size_t)kDim * kDim, efmt);
             split(w->ff1_w[l], L.ff1_hi[l], L.ff1_lo[l], (size_t)kMlp * kDim, efmt);
             split(w->ff2_w[l], L.ff2_hi[l], L.ff2_lo[l], (size_t)kDim * kMlp, efmt);
+            // LayerNorm-fused copies: gamma folded into the columns, and the constants of the epilogue
+            VETO_REQUIRE(w->ln1_w[l] && w->ln1_b[l] && w->ln2_w[l] && w->ln2_b[l] && w->ff1_b[l], VETO_ERR_ARG,
+                         "layer %d LayerNorm parameters missing", l);
+            split(w->qkv_w[l], L.qkvf_hi[l], L.qkvf_lo[l], (size_t)3 * kDim * kDim, efmt, w->ln1_w[l], kDim);
+            split(w->ff1_w[l], L.ff1f_hi[l], L.ff1f_lo[l], (size_t)kMlp * kDim, efmt, w->ln2_w[l], kDim);
+            float* cq = (float*)(P + L.c_qkv[l]);
+            float* cf = (float*)(P + L.c_ff1[l]);
+            if ((rc = ln_fold_consts(w->qkv_w[l], w->ln1_w[l], w->ln1_b[l], nullptr, 3 * kDim, kDim, cq, cq + 3 * kDim, s))) return rc;
+            if ((rc = ln_fold_consts(w->ff1_w[l], w->ln2_w[l], w->ln2_b[l], w->ff1_b[l], kMlp, kDim, cf, cf + kMlp, s))) return rc;
         }
         if ((rc = pack_split_bf16_multi(jobs, nj, s))) return rc;
     }
@@ -247,45 +283,106 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
                                       cudaMemcpyDeviceToDevice, s));
         const int R = (int)rc_pairs;
+        // LayerNorm fusion (tensor-core modes): the epilogues that produce x (to_out, FF2) also write it in operand format
+        // with its row statistics, and the next Linear (FF1, the next layer's to_qkv) runs on those raw rows with the
+        // LayerNorm weight folded into its weight (gemm_tc2.cu EPI_*_LN) — the LayerNorm pass over x and its normalised
+        // copy never exist.  Layer 0's first LayerNorm (x comes from the token kernel) keeps the kernel.
+        // Only in the modes that carry ~16 bits per operand (bf16x3, f16c8): on raw rows the products are rounded relative
+        // to |x|, not |x - mean|, and the single-product modes (bf16, f16) have no headroom for that next to their tolerance.
+        const bool fuse_ln = ln_fusion_enabled() && prec_two_arrays(prec);
+        ActBuf xo = fuse_ln ? enc_act_at(B, W.xo, prec, (size_t)M * kDim) : ActBuf();
+        float2* ln_parts = fuse_ln ? (float2*)(B + W.ln_parts) : nullptr;
+        float2* ln_stats = fuse_ln ? (float2*)(B + W.ln_stats) : nullptr;
+        bool x_ops_ready = false;     // xo / ln_stats hold the current x
+        auto emit_x = [&](GemmEpilogue& e) {   // an epilogue that writes x: also its operand copy + statistics partials
+            if (!fuse_ln) return;
+            e.out.hi = xo.hi;
+            e.out.lo = xo.lo;
+            e.out.fmt = xo.fmt;
+            e.stats_partials = ln_parts;
+        };
+        auto finish_x = [&]() -> int {
+            if (!fuse_ln) return VETO_OK;
+            set_tag(TAG_LN);
+            x_ops_ready = true;
+            return ln_stats_finalize(ln_parts, kDim / 64, M, ln_stats, s);
+        };
         for (int l = 0; l + 1 < cfg->layers; ++l) {
             // x = to_out(softmax(q k^T * scale) v) + x      (PreNorm + Attention, model_veto.py:18-19,86-96)
-            set_tag(TAG_LN);
-            if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
             GemmEpilogue e1;
-            e1.out.f32 = qkv;
             e1.ldc = 3 * kDim;
-            WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+            // q, k, v leave the GEMM as bf16 hi + lo arrays (the bytes of the fp32 buffer) for attention_split.cu in every
+            // mode whose attention core runs the split products; the single bf16 product and fp32 keep the fp32 buffer
+            const bool split_qkv = split_attention_enabled() && prec != VETO_PREC_FP32 && prec != VETO_PREC_BF16;
+            __nv_bfloat16* qkv_hi = (__nv_bfloat16*)qkv;
+            __nv_bfloat16* qkv_lo = qkv_hi + (size_t)M * 3 * kDim;
+            if (split_qkv) {
+                e1.out.hi = qkv_hi;
+                e1.out.lo = qkv_lo;
+                e1.out.fmt = FMT_BF16;
+            } else {
+                e1.out.f32 = qkv;
+            }
             set_tag(TAG_QKV);
-            if ((rc = linear(prec, xn, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
+            if (x_ops_ready) {
+                const float* cq = (const float*)(P + L.c_qkv[l]);
+                e1.ln_stats = ln_stats;
+                e1.ln_c1 = cq;
+                e1.bias = cq + 3 * kDim;
+                WRef wq{nullptr, bf(P, L.qkvf_hi[l]), bf(P, L.qkvf_lo[l])};
+                if ((rc = linear(prec, xo, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
+            } else {
+                set_tag(TAG_LN);
+                if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
+                WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+                set_tag(TAG_QKV);
+                if ((rc = linear(prec, xn, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
+            }
             set_tag(TAG_ATT);
-            if ((rc = attention_seq(qkv, rc_pairs, xn.out(), s))) return rc;
+            if (split_qkv) rc = attention_seq_split(qkv_hi, qkv_lo, rc_pairs, xn.out(), s);
+            else rc = attention_seq(qkv, rc_pairs, xn.out(), s);
+            if (rc) return rc;
             GemmEpilogue e2;
             e2.bias = w->out_b[l];
             e2.residual = x;
             e2.out.f32 = x;
             e2.ldc = kDim;
+            emit_x(e2);
             WRef wo{w->out_w[l], bf(P, L.out_hi[l]), bf(P, L.out_lo[l])};
             set_tag(TAG_OUT);
             if ((rc = linear(prec, xn, kDim, wo, M, kDim, kDim, e2, s))) return rc;
+            if ((rc = finish_x())) return rc;
             // x = W2 gelu(W1 LN(x) + b1) + b2 + x           (PreNorm + FeedForward, model_veto.py:20,134-146)
-            set_tag(TAG_LN);
-            if ((rc = layernorm_rows(x, kDim, w->ln2_w[l], w->ln2_b[l], M, xn.out(), s))) return rc;
             GemmEpilogue e3;
-            e3.bias = w->ff1_b[l];
             e3.act = ACT_GELU;
             e3.out = hb.out();
             e3.ldc = kMlp;
-            WRef w1{w->ff1_w[l], bf(P, L.ff1_hi[l]), bf(P, L.ff1_lo[l])};
-            set_tag(TAG_FF1);
-            if ((rc = linear(prec, xn, kDim, w1, M, kMlp, kDim, e3, s))) return rc;
+            if (fuse_ln) {
+                const float* cf = (const float*)(P + L.c_ff1[l]);
+                e3.ln_stats = ln_stats;
+                e3.ln_c1 = cf;
+                e3.bias = cf + kMlp;
+                WRef w1{nullptr, bf(P, L.ff1f_hi[l]), bf(P, L.ff1f_lo[l])};
+                set_tag(TAG_FF1);
+                if ((rc = linear(prec, xo, kDim, w1, M, kMlp, kDim, e3, s))) return rc;
+            } else {
+                set_tag(TAG_LN);
+                if ((rc = layernorm_rows(x, kDim, w->ln2_w[l], w->ln2_b[l], M, xn.out(), s))) return rc;
+                e3.bias = w->ff1_b[l];
+                WRef w1{w->ff1_w[l], bf(P, L.ff1_hi[l]), bf(P, L.ff1_lo[l])};
+                set_tag(TAG_FF1);
+                if ((rc = linear(prec, xn, kDim, w1, M, kMlp, kDim, e3, s))) return rc;
+            }
             GemmEpilogue e4;
             e4.bias = w->ff2_b[l];
             e4.residual = x;
             e4.out.f32 = x;
             e4.ldc = kDim;
+            emit_x(e4);
             WRef w2{w->ff2_w[l], bf(P, L.ff2_hi[l]), bf(P, L.ff2_lo[l])};
             set_tag(TAG_FF2);
             if ((rc = linear(prec, hb, kMlp, w2, M, kDim, kMlp, e4, s))) return rc;
+            if ((rc = finish_x())) return rc;
         }
         {
             // Last layer: only x[:,0] leaves the encoder (model_veto.py:25), so only the CLS row needs a query, an
@@ -295,20 +392,35 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             const size_t woff = (size_t)kDim * kDim;  // rows [576, 1728) of to_qkv.weight = K and V projections
             float* q_cls = (float*)(B + W.q_cls);
             float* x_cls = (float*)(B + W.x_cls);
-            set_tag(TAG_LN);
-            if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
             GemmEpilogue e1;
             e1.out.f32 = qkv + kDim;
             e1.ldc = 3 * kDim;
-            WRef wkv{w->qkv_w[l] + woff, bf(P, L.qkv_hi[l]) ? bf(P, L.qkv_hi[l]) + woff : nullptr,
-                     bf(P, L.qkv_lo[l]) ? bf(P, L.qkv_lo[l]) + woff : nullptr};
-            set_tag(TAG_QKV);
-            if ((rc = linear(prec, xn, kDim, wkv, M, 2 * kDim, kDim, e1, s))) return rc;
             GemmEpilogue eq;
             eq.out.f32 = q_cls;
             eq.ldc = kDim;
-            WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
-            if ((rc = linear(prec, xn, kTokens * kDim, wq, R, kDim, kDim, eq, s))) return rc;
+            if (x_ops_ready) {   // LayerNorm fused (see above): K, V of every row, the query of the CLS rows (row stride 19)
+                const float* cq = (const float*)(P + L.c_qkv[l]);
+                e1.ln_stats = eq.ln_stats = ln_stats;
+                e1.ln_c1 = cq + kDim;
+                e1.bias = cq + 3 * kDim + kDim;
+                eq.ln_c1 = cq;
+                eq.bias = cq + 3 * kDim;
+                eq.ln_row_stride = kTokens;
+                WRef wkv{nullptr, bf(P, L.qkvf_hi[l]) + woff, bf(P, L.qkvf_lo[l]) ? bf(P, L.qkvf_lo[l]) + woff : nullptr};
+                WRef wq{nullptr, bf(P, L.qkvf_hi[l]), bf(P, L.qkvf_lo[l])};
+                set_tag(TAG_QKV);
+                if ((rc = linear(prec, xo, kDim, wkv, M, 2 * kDim, kDim, e1, s))) return rc;
+                if ((rc = linear(prec, xo, kTokens * kDim, wq, R, kDim, kDim, eq, s))) return rc;
+            } else {
+                set_tag(TAG_LN);
+                if ((rc = layernorm_rows(x, kDim, w->ln1_w[l], w->ln1_b[l], M, xn.out(), s))) return rc;
+                WRef wkv{w->qkv_w[l] + woff, bf(P, L.qkv_hi[l]) ? bf(P, L.qkv_hi[l]) + woff : nullptr,
+                         bf(P, L.qkv_lo[l]) ? bf(P, L.qkv_lo[l]) + woff : nullptr};
+                set_tag(TAG_QKV);
+                if ((rc = linear(prec, xn, kDim, wkv, M, 2 * kDim, kDim, e1, s))) return rc;
+                WRef wq{w->qkv_w[l], bf(P, L.qkv_hi[l]), bf(P, L.qkv_lo[l])};
+                if ((rc = linear(prec, xn, kTokens * kDim, wq, R, kDim, kDim, eq, s))) return rc;
+            }
             ActBuf ao = enc_act_at(B, W.xn, prec, (size_t)R * kDim);  // xn is free once K, V and q exist
             set_tag(TAG_ATT);
             if ((rc = attention_cls(q_cls, qkv, rc_pairs, ao.out(), s))) return rc;

@@ -52,6 +52,10 @@ struct PackedLayout {
     size_t d2_hi, d2_lo, v2_hi, v2_lo;
     size_t qkv_hi[VETO_MAX_LAYERS], qkv_lo[VETO_MAX_LAYERS], out_hi[VETO_MAX_LAYERS], out_lo[VETO_MAX_LAYERS];
     size_t ff1_hi[VETO_MAX_LAYERS], ff1_lo[VETO_MAX_LAYERS], ff2_hi[VETO_MAX_LAYERS], ff2_lo[VETO_MAX_LAYERS];
+    // LayerNorm-fused inference (gemm_tc2.cu EPI_*_LN): to_qkv / FF1 weights with the LayerNorm weight folded in, and
+    // their constants c1 | c2 (2 x N floats)
+    size_t qkvf_hi[VETO_MAX_LAYERS], qkvf_lo[VETO_MAX_LAYERS], ff1f_hi[VETO_MAX_LAYERS], ff1f_lo[VETO_MAX_LAYERS];
+    size_t c_qkv[VETO_MAX_LAYERS], c_ff1[VETO_MAX_LAYERS];
     size_t total;
 };
 
@@ -84,6 +88,12 @@ static inline PackedLayout packed_layout(const veto_config& c) {
             L.ff1_lo[l] = lo ? k.take(e * kMlp * kDim) : 0;
             L.ff2_hi[l] = k.take(e * kDim * kMlp);
             L.ff2_lo[l] = lo ? k.take(e * kDim * kMlp) : 0;
+            L.qkvf_hi[l] = k.take(e * 3 * kDim * kDim);
+            L.qkvf_lo[l] = lo ? k.take(e * 3 * kDim * kDim) : 0;
+            L.ff1f_hi[l] = k.take(e * kMlp * kDim);
+            L.ff1f_lo[l] = lo ? k.take(e * kMlp * kDim) : 0;
+            L.c_qkv[l] = k.take(sizeof(float) * 2 * 3 * kDim);
+            L.c_ff1[l] = k.take(sizeof(float) * 2 * kMlp);
         }
     }
     L.total = k.off;

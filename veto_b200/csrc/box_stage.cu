@@ -56,7 +56,11 @@ __global__ void split_bf16_multi_kernel(const __grid_constant__ SplitJobs jobs) 
     const SplitJob& jb = jobs.j[blockIdx.y];
     const size_t n4 = jb.n >> 2;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(jb.src) + e);
+        float4 v = __ldg(reinterpret_cast<const float4*>(jb.src) + e);
+        if (jb.col_scale) {   // LayerNorm weight folded into the Linear weight (row_len % 4 == 0)
+            const float4 g = __ldg(reinterpret_cast<const float4*>(jb.col_scale + (4 * e) % (size_t)jb.row_len));
+            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+        }
         uint2 hi, lo;
         if (jb.fmt == FMT_F16C8) {
             // weight side of the f16c8 format: fp16(2048 w); bytes (e4m3(8 w), e4m3(8 r_w)) with r_w = 2048 w - fp16(2048 w)
@@ -81,6 +85,28 @@ __global__ void split_bf16_multi_kernel(const __grid_constant__ SplitJobs jobs) 
         split_pair(v.z, v.w, hi.y, lo.y);
         reinterpret_cast<uint2*>(jb.hi)[e] = hi;
         if (jb.lo) reinterpret_cast<uint2*>(jb.lo)[e] = lo;
+    }
+}
+
+// one warp per output n: c1 = sum_k gamma_k W[n,k], c2 = sum_k beta_k W[n,k] + bias[n]
+__global__ void ln_fold_consts_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ bias, int N, int K, float* __restrict__ c1, float* __restrict__ c2) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float a = 0.f, b = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[(size_t)n * K + k];
+        a = fmaf(gamma[k], w, a);
+        b = fmaf(beta[k], w, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        c1[n] = a;
+        c2[n] = b + (bias ? bias[n] : 0.f);
     }
 }
 
@@ -211,13 +237,21 @@ int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size
     return VETO_OK;
 }
 
+int ln_fold_consts(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, float* c1, float* c2,
+                   cudaStream_t s) {
+    ln_fold_consts_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, gamma, beta, bias, N, K, c1, c2);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
 int pack_split_bf16_multi(const SplitJob* jobs, int count, cudaStream_t s) {
     if (count <= 0) return VETO_OK;
     VETO_REQUIRE(count <= kMaxSplitJobs, VETO_ERR_ARG, "pack_split_bf16_multi: %d arrays > %d", count, kMaxSplitJobs);
     SplitJobs J{};
     size_t n_max = 0;
     for (int i = 0; i < count; ++i) {
-        VETO_REQUIRE(jobs[i].src && jobs[i].hi && jobs[i].n % 4 == 0, VETO_ERR_ARG, "pack_split_bf16_multi: bad array %d", i);
+        VETO_REQUIRE(jobs[i].src && jobs[i].hi && jobs[i].n % 4 == 0 && (!jobs[i].col_scale || (jobs[i].row_len > 0 && jobs[i].row_len % 4 == 0)),
+                     VETO_ERR_ARG, "pack_split_bf16_multi: bad array %d", i);
         J.j[i] = jobs[i];
         n_max = jobs[i].n > n_max ? jobs[i].n : n_max;
     }

@@ -272,7 +272,14 @@ struct GemmEpilogue {
     DropSpec drop;                    // dropout on act(acc + bias) before the residual add; element index row * ldc + col
     int split_k = 1;                  // > 1: partial products over K slices, slice s written at out.f32 + s * split_stride
     size_t split_stride = 0;          //      (no bias / act / residual; reduce with splitk_reduce)
+    // ---- LayerNorm fusion (gemm_tc2, inference epilogues; gemm_tc2.cu EPI_*) ----
+    const float2* ln_stats = nullptr; // (mean, rstd) per A row: the GEMM runs on the RAW rows with gamma folded into W and
+    int ln_row_stride = 1;            //   the epilogue applies rstd * (acc - mean * ln_c1[n]) + bias[n] (bias = c2);
+    const float* ln_c1 = nullptr;     //   row r's statistics sit at ln_stats[r * ln_row_stride]
+    float2* stats_partials = nullptr; // [N / 64][M] partial (sum, sum of squares) of the OUTPUT rows (ln_stats_finalize)
 };
+// (mean, rstd) of LayerNorm (eps 1e-5) over rows of kDim from the partial sums a gemm_tc2 epilogue wrote
+int ln_stats_finalize(const float2* partials, int n_parts, int64_t rows, float2* stats, cudaStream_t s);
 
 // `passes` of the tensor-core GEMMs: the operand format / product scheme
 //   1 = bf16 single product, 3 = bf16x3 (hi*hi + lo*hi + hi*lo), 2 = f16c8 (fp16 product + one fp8 correction GEMM over
@@ -327,6 +334,9 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
                    cudaStream_t s);
 // softmax(q k^T * 96^-0.5) v per (sequence, head); qkv fp32 [n_seq*19, 1728] -> out [n_seq*19, 576]
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
+// the same on q, k, v already split into bf16 hi + lo arrays [n_seq*19, 1728] (attention_split.cu; the to_qkv epilogue
+// of gemm_tc2 writes them): the inference path of the tensor-core modes with 16-bit-mantissa operands
+int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int64_t n_seq, const ActOut& out, cudaStream_t s);
 // tcgen05 version (attention_tc.cu): six sequences per 128-row tile, bf16 hi/lo split when out.lo is given
 int attention_tc(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
 // the same for the CLS query row only (last encoder layer: only x[:,0] is consumed, model_veto.py:25):

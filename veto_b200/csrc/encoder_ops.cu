@@ -83,6 +83,22 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
     }
 }
 
+// Row statistics for the LayerNorm-fused GEMMs: the epilogue that produced x wrote n_parts partial (sum, sum of squares)
+// per row (one per 64 columns); mean and 1 / sqrt(var + eps) in a fixed summation order.
+__global__ void ln_stats_finalize_kernel(const float2* __restrict__ partials, int n_parts, int64_t rows, float2* __restrict__ stats) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int p = 0; p < n_parts; ++p) {
+            const float2 v = __ldg(partials + (size_t)p * rows + r);
+            s += v.x;
+            q += v.y;
+        }
+        const float mean = s * (1.f / kDim);
+        const float var = fmaxf(q * (1.f / kDim) - mean * mean, 0.f);
+        stats[r] = make_float2(mean, 1.f / sqrtf(var + 1e-5f));
+    }
+}
+
 // ---------------------------------------------------------------- attention
 // One CTA (6 warps) per sequence, warp h = head h.  K and V of the head are staged in shared memory
 // (broadcast reads), lane i < 19 owns query row i: its q row, its 19 scores and its 96-wide output
@@ -646,6 +662,15 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
     const int64_t cap = (int64_t)num_sms() * 4;
     const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
     layernorm_kernel<<<grid, 256, 0, s>>>(x, ldx, w, b, rows, out.f32, out.hi, out.lo, out.fmt);
+    VETO_LAUNCH_CHECK();
+    return VETO_OK;
+}
+
+int ln_stats_finalize(const float2* partials, int n_parts, int64_t rows, float2* stats, cudaStream_t s) {
+    if (rows <= 0) return VETO_OK;
+    const int64_t blocks = (rows + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+    ln_stats_finalize_kernel<<<grid, 256, 0, s>>>(partials, n_parts, rows, stats);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

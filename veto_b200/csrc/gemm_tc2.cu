@@ -67,6 +67,10 @@ struct EpiParams {
     float* pre_f32;
     int res_mode;
     DropSpec drop;
+    const float2* ln_stats;  // fused LayerNorm on the A operand: (mean, rstd) of row r at ln_stats[r * ln_row_stride]
+    const float* ln_c1;      //   and c1[n] = sum_k gamma_k W[n,k]; `bias` then holds c2[n] = sum_k beta_k W[n,k] (+ bias)
+    int ln_row_stride;
+    float2* stats_partials;  // row statistics of the OUTPUT: partial (sum, sum of squares) [N / 64][M] for ln_stats_finalize
     int out_fmt;             // FMT_BF16 / FMT_F16C8: storage format of out_hi / out_lo
     float acc_scale;         // accumulator scale (f16c8 / f16: 2^-11, the weights are stored times 2048)
     int ksplit;              // K slices (wgrad: tiny output, huge K); tiles enumerate (slice, m, n)
@@ -74,6 +78,22 @@ struct EpiParams {
     long long split_stride;  // elements between the partial outputs of consecutive slices
 };
 
+// Epilogue variants.  EPI_GENERIC evaluates every option of EpiParams at run time (training branch, tests); the others
+// are the inference epilogues of the encoder with their options fixed at compile time (the FF1 epilogue — GELU plus the
+// operand-format store — was issue-bound: 58 instructions per element in the generic form, profiles/r2_gemm_f16c8_ncu.txt):
+//   EPI_F32        C = acc                                               (to_qkv; no bias)
+//   EPI_F32_LN     C = rstd * (acc - mean * c1) + c2                     (to_qkv on the raw residual stream: LayerNorm fused)
+//   EPI_RES        C = acc + bias + residual                             (to_out, FF2)
+//   EPI_RES_OPS    the same, and the result also in operand format + its row statistics (feeds a LayerNorm-fused GEMM)
+//   EPI_GELU_OP    operand(gelu(acc + bias))                             (FF1)
+//   EPI_GELU_OP_LN operand(gelu(rstd * (acc - mean * c1) + c2))          (FF1 on the raw residual stream)
+// LayerNorm fusion: LN(x) W^T = rstd * (x (gamma . W)^T - mean * c1) + c2 — the GEMM runs on the raw rows of x with the
+// LayerNorm weight folded into W (veto_pack_weights), the row statistics come from the epilogue that produced x.
+//   EPI_OP / EPI_OP_LN   operand(acc) / operand(rstd * (acc - mean * c1) + c2)  (to_qkv for attention_split.cu: q, k, v as
+//                        bf16 hi + lo arrays instead of fp32)
+enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_COUNT };
+
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -229,6 +249,135 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int rsub = lane >> 2, cg = lane & 3;
         constexpr int kChunks = BLOCK_N / EPI_COLS;
         int it = 0;
+        if constexpr (EPI != EPI_GENERIC) {
+            constexpr bool kLnIn = EPI == EPI_F32_LN || EPI == EPI_GELU_OP_LN || EPI == EPI_OP_LN;
+            constexpr bool kResid = EPI == EPI_RES || EPI == EPI_RES_OPS;
+            constexpr bool kGelu = EPI == EPI_GELU_OP || EPI == EPI_GELU_OP_LN;
+            constexpr bool kOutF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || kResid;
+            constexpr bool kOutOp = kGelu || EPI == EPI_RES_OPS || EPI == EPI_OP || EPI == EPI_OP_LN;
+            constexpr bool kStats = EPI == EPI_RES_OPS;
+            constexpr bool kBias = kResid || kGelu || kLnIn;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                int tm, tn;
+                tile_mn(tile, tm, tn);
+                const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
+                const int n0 = tn * BLOCK_N;
+                float4 res[4], res_next[4];
+                auto load_res = [&](int c, float4 (&dst)[4]) {
+                    const int col = n0 + c * EPI_COLS + cg * 4;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = m0 + rr * 8 + rsub;
+                        dst[rr] = row < M ? *(const float4*)(ep.residual + (size_t)row * ep.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                };
+                float2 st[4];
+                float s_acc[4] = {0.f, 0.f, 0.f, 0.f}, q_acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if constexpr (kLnIn) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = m0 + rr * 8 + rsub;
+                        st[rr] = row < M ? __ldg(ep.ln_stats + (size_t)row * ep.ln_row_stride) : make_float2(0.f, 0.f);
+                    }
+                }
+                if constexpr (kResid) {
+                    load_res(half, res_next);
+                    if (tile + num_pairs < num_tiles) {   // the NEXT tile's residual lines of this warp into L2
+                        int ntm, ntn;
+                        tile_mn(tile + num_pairs, ntm, ntn);
+                        const int pr = ntm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
+                        const int pc = ntn * BLOCK_N;
+                        if (pr < M) {
+#pragma unroll
+                            for (int c = half; c < kChunks; c += kStride)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
+                        }
+                    }
+                }
+                mbar_wait(&tmem_full[acc], acc_phase, 4);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+                for (int c = half; c < kChunks; c += kStride) {
+                    if constexpr (kResid) {
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) res[rr] = res_next[rr];
+                        if (c + kStride < kChunks) load_res(c + kStride, res_next);
+                    }
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c * EPI_COLS, r);
+                    tmem_ld_wait();
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        stage4[lane * 4 + (j ^ sw)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    __syncwarp();
+                    const int col = n0 + c * EPI_COLS + cg * 4;
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (kBias) bias4 = __ldg((const float4*)(ep.bias + col));
+                    if constexpr (kLnIn) c1 = __ldg((const float4*)(ep.ln_c1 + col));
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int lr = rr * 8 + rsub;
+                        float4 v = stage4[lr * 4 + (cg ^ ((lr >> 1) & 3))];
+                        const int row = m0 + lr;
+                        if (row < M) {
+                            if constexpr (kLnIn) {
+                                const float mu = st[rr].x, rs = st[rr].y;
+                                v.x = fmaf(rs, fmaf(v.x, ep.acc_scale, -mu * c1.x), bias4.x);
+                                v.y = fmaf(rs, fmaf(v.y, ep.acc_scale, -mu * c1.y), bias4.y);
+                                v.z = fmaf(rs, fmaf(v.z, ep.acc_scale, -mu * c1.z), bias4.z);
+                                v.w = fmaf(rs, fmaf(v.w, ep.acc_scale, -mu * c1.w), bias4.w);
+                            } else {
+                                v.x = fmaf(v.x, ep.acc_scale, bias4.x); v.y = fmaf(v.y, ep.acc_scale, bias4.y);
+                                v.z = fmaf(v.z, ep.acc_scale, bias4.z); v.w = fmaf(v.w, ep.acc_scale, bias4.w);
+                            }
+                            if constexpr (kGelu) {
+                                v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+                            }
+                            if constexpr (kResid) {
+                                v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
+                            }
+                            const size_t off = (size_t)row * ep.ldc + col;
+                            if constexpr (kOutF32) *(float4*)(ep.out_f32 + off) = v;
+                            if constexpr (kOutOp) {
+                                if (ep.out_fmt == FMT_F16C8) {
+                                    store_act4_f16c8(ep.out_hi, ep.out_lo, off, v);
+                                } else {
+                                    uint2 hh, ll;
+                                    split_pair(v.x, v.y, hh.x, ll.x);
+                                    split_pair(v.z, v.w, hh.y, ll.y);
+                                    *(uint2*)(ep.out_hi + off) = hh;
+                                    if (ep.out_lo) *(uint2*)(ep.out_lo + off) = ll;
+                                }
+                            }
+                            if constexpr (kStats) {
+                                s_acc[rr] += (v.x + v.y) + (v.z + v.w);
+                                q_acc[rr] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                if constexpr (kStats) {
+                    // this warp covered 64 of the row's columns (4 chunks x 16): one partial per (column tile, warp third)
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        float sv = s_acc[rr], qv = q_acc[rr];
+                        sv += __shfl_xor_sync(0xffffffffu, sv, 1); qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+                        sv += __shfl_xor_sync(0xffffffffu, sv, 2); qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+                        const int row = m0 + rr * 8 + rsub;
+                        if (cg == 0 && row < M) ep.stats_partials[(size_t)(tn * kStride + half) * M + row] = make_float2(sv, qv);
+                    }
+                }
+            }
+        } else
         for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -390,7 +539,15 @@ int init2() {
     VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_F32_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES_OPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_OP_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_inited.done();
     return VETO_OK;
 }
@@ -446,8 +603,43 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     const float acc_scale = (passes == TC_F16C8 || passes == TC_F16) ? kC8AccScale : 1.f;
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
-                ep.pre_f32, ep.res_mode, ep.drop, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride};
-    gemm_tc2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+                ep.pre_f32, ep.res_mode, ep.drop, ep.ln_stats, ep.ln_c1, ep.ln_row_stride > 0 ? ep.ln_row_stride : 1,
+                ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride};
+    // the compile-time epilogues of the inference encoder; anything else (training options, tests) is EPI_GENERIC
+    const bool plain = !ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ksplit == 1;
+    const bool ln_in = ep.ln_stats != nullptr;
+    VETO_REQUIRE(!ln_in || (ep.ln_c1 && ep.bias), VETO_ERR_ARG, "gemm_tc2: fused LayerNorm needs ln_c1 and the c2 vector as bias");
+    int epi = EPI_GENERIC;
+    if (plain && ep.act == ACT_NONE && !ep.residual && ep.out.f32 && !ep.out.hi && !ep.stats_partials) {
+        if (ln_in) epi = EPI_F32_LN;
+        else if (!ep.bias) epi = EPI_F32;
+    } else if (plain && ep.act == ACT_NONE && ep.residual && ep.bias && ep.out.f32 && !ln_in) {
+        if (ep.out.hi && ep.stats_partials) epi = EPI_RES_OPS;
+        else if (!ep.out.hi && !ep.stats_partials) epi = EPI_RES;
+    } else if (plain && ep.act == ACT_GELU && !ep.residual && ep.bias && ep.out.hi && !ep.out.f32 && !ep.stats_partials) {
+        epi = ln_in ? EPI_GELU_OP_LN : EPI_GELU_OP;
+    } else if (plain && ep.act == ACT_NONE && !ep.residual && ep.out.hi && !ep.out.f32 && !ep.stats_partials) {
+        if (ln_in) epi = EPI_OP_LN;
+        else if (!ep.bias) epi = EPI_OP;
+    }
+    VETO_REQUIRE(epi != EPI_GENERIC || (!ln_in && !ep.stats_partials), VETO_ERR_UNSUPPORTED,
+                 "gemm_tc2: LayerNorm fusion / row statistics exist for the inference epilogues only");
+    static int force_generic = -1;   // VETO_GEMM_GENERIC_EPI=1: diagnosis, every launch through the run-time epilogue
+    if (force_generic < 0) force_generic = getenv("VETO_GEMM_GENERIC_EPI") ? 1 : 0;
+    if (force_generic && !ln_in && !ep.stats_partials) epi = EPI_GENERIC;
+#define VETO_TC2_LAUNCH(E) gemm_tc2_kernel<E><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    switch (epi) {
+        case EPI_F32: VETO_TC2_LAUNCH(EPI_F32); break;
+        case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN); break;
+        case EPI_RES: VETO_TC2_LAUNCH(EPI_RES); break;
+        case EPI_RES_OPS: VETO_TC2_LAUNCH(EPI_RES_OPS); break;
+        case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP); break;
+        case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN); break;
+        case EPI_OP: VETO_TC2_LAUNCH(EPI_OP); break;
+        case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN); break;
+        default: VETO_TC2_LAUNCH(EPI_GENERIC); break;
+    }
+#undef VETO_TC2_LAUNCH
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

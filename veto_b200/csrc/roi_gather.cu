@@ -49,6 +49,85 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
+// Separable taps.  The sample grid of a roi is a tensor product: sample (bin row bh, iy) fixes y, (bin column bw, ix)
+// fixes x (ROIAlign_cpu.cpp:37-52), validity and clamping act per axis (:54-90), and the four weights of a sample are
+// products of one y factor and one x factor (w1 = hy*hx, w2 = hy*lx, w3 = ly*hx, w4 = ly*lx, :92-98) — the SAME fp32
+// products whether they are formed once per sample or by every lane that uses them.  So a roi needs ph*sr axis entries
+// for y and pw*sr for x (16 + 16 for the 8x8, sampling-ratio-2 pooling) instead of ph*pw*sr*sr = 256 four-tap records.
+// An entry: (low, high) coordinate and the (l, h) interpolation factors; a coordinate outside the map gets l = h = 0
+// (every weight it takes part in is an exact 0, as for the reference's empty samples) and low = high = -1.
+struct AxisTap {
+    int lo, hi;
+    float l, h;
+};
+__device__ __forceinline__ AxisTap axis_tap(int i, float start, float bin, int sr, int extent) {
+    const int b = i / sr, s = i - b * sr;
+    float v = start + b * bin + (float)(s + .5f) * bin / (float)sr;
+    AxisTap t{-1, -1, 0.f, 0.f};
+    if (!(v < -1.0f || v > (float)extent)) {
+        if (v <= 0.f) v = 0.f;
+        int lo = (int)v, hi;
+        if (lo >= extent - 1) { hi = lo = extent - 1; v = (float)lo; } else hi = lo + 1;
+        t.lo = lo;
+        t.hi = hi;
+        t.l = v - (float)lo;
+        t.h = 1.f - t.l;
+    }
+    return t;
+}
+// the axis entries of one roi, computed by ONE warp (lane i < ny + nx): ty[ny], tx[nx] as int4 (lo, hi, l bits, h bits).
+// Returns through `range` (lane-uniform) the bounding coordinates (ymin, ymax, xmin, xmax) of the valid entries, -1 maxima
+// when an axis has none.
+__device__ __forceinline__ void roi_axis_taps(int4* ty, int4* tx, float4 box, float scale, int height, int width, int ph,
+                                              int pw, int sr, int4& range) {
+    const int lane = threadIdx.x & 31;
+    const float roi_start_w = box.x * scale, roi_start_h = box.y * scale;
+    const float roi_end_w = box.z * scale, roi_end_h = box.w * scale;
+    const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f);
+    const float roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
+    const float bin_h = roi_height / (float)ph, bin_w = roi_width / (float)pw;
+    const int ny = ph * sr, nx = pw * sr;
+    int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+    for (int i = lane; i < ny + nx; i += 32) {
+        const bool is_y = i < ny;
+        const AxisTap t = is_y ? axis_tap(i, roi_start_h, bin_h, sr, height) : axis_tap(i - ny, roi_start_w, bin_w, sr, width);
+        (is_y ? ty[i] : tx[i - ny]) = make_int4(t.lo, t.hi, __float_as_int(t.l), __float_as_int(t.h));
+        if (t.lo >= 0) {
+            if (is_y) { ymin = min(ymin, t.lo); ymax = max(ymax, t.hi); }
+            else { xmin = min(xmin, t.lo); xmax = max(xmax, t.hi); }
+        }
+    }
+    range = make_int4(warp_min(ymin), warp_max(ymax), warp_min(xmin), warp_max(xmax));
+}
+// turn the coordinates of the entries into staging-buffer offsets: y -> (y - y0) * row_pitch, x -> (x - x0) * stride;
+// entries outside the map point at offset 0 (their factors are 0)
+__device__ __forceinline__ void axis_taps_to_offsets(int4* ty, int4* tx, int ny, int nx, int y0, int x0, int row_pitch, int stride) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < ny + nx; i += 32) {
+        int4& t = i < ny ? ty[i] : tx[i - ny];
+        if (t.x < 0) { t.x = 0; t.y = 0; }
+        else if (i < ny) { t.x = (t.x - y0) * row_pitch; t.y = (t.y - y0) * row_pitch; }
+        else { t.x = (t.x - x0) * stride; t.y = (t.y - x0) * stride; }
+    }
+}
+// One bin of one channel from a [position][stride] staging buffer (`win` already offset by the lane's channel): samples in
+// the reference's order (iy outer, ix inner), acc += w1*v1 + w2*v2 + w3*v3 + w4*v4, one division by the sample count.
+__device__ __forceinline__ float pool_bin(const int4* ty, const int4* tx, const float* win, int bh, int bw, int sr, float count) {
+    float acc = 0.f;
+    for (int iy = 0; iy < sr; ++iy) {
+        const int4 ye = ty[bh * sr + iy];
+        const float ly = __int_as_float(ye.z), hy = __int_as_float(ye.w);
+        for (int ix = 0; ix < sr; ++ix) {
+            const int4 xe = tx[bw * sr + ix];
+            const float lx = __int_as_float(xe.z), hx = __int_as_float(xe.w);
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const float v1 = win[ye.x + xe.x], v2 = win[ye.x + xe.y], v3 = win[ye.y + xe.x], v4 = win[ye.y + xe.y];
+            acc += w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+        }
+    }
+    return acc / count;
+}
+
 // one sample of a roi in the reference's operation order (ROIAlign_cpu.cpp:17-112): corner coordinates (y_low, x_low,
 // y_high, x_high) and the four weights; a sample outside the map gets y_low = -1 and zero weights
 __device__ __forceinline__ void sample_taps(int k, float x1, float y1, float x2, float y2, float scale, int height, int width,
@@ -108,83 +187,49 @@ __device__ __forceinline__ void compute_taps(int4* tp, float4* tw, int* bounds, 
     }
 }
 
-// pooling of `nc` channels x all bins from a [position][stride] staging buffer: lane = (bin slot, channel), the taps of a
-// sample (positions pre-multiplied by the stride) are uniform across the lanes of a bin slot.  tile[c][bins + 1].
-__device__ __forceinline__ void pool_from_smem(const int4* tp, const float4* tw, const float* win, int cb, int nc, int bins,
-                                               int spp, float* tile, int tile_c0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bins_per_iter = 32 / cb;
-    const int cl = lane % cb, bsub = lane / cb;
-    const float count = (float)spp;
-    for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
-        const int bin = b0 + bsub;
-        if (bin < bins && cl < nc) {
-            float acc = 0.f;
-            for (int s = 0; s < spp; ++s) {
-                const int4 p = tp[bin * spp + s];
-                const float4 w = tw[bin * spp + s];
-                const float v1 = win[p.x + cl], v2 = win[p.y + cl], v3 = win[p.z + cl], v4 = win[p.w + cl];
-                acc += w.x * v1 + w.y * v2 + w.z * v3 + w.w * v4;
-            }
-            tile[(tile_c0 + cl) * (bins + 1) + bin] = acc / count;
-        }
-    }
-}
-
 // One (roi, channel block) tile of the window kernel: channels [c0, c0 + nch) of the roi pooled into dst[(c0 + c) * bins + bin].
 __device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph, int pw, int sr, int c0, int nch,
                                             float* __restrict__ dst, uint8_t* smem) {
-    const int bins = ph * pw, spp = sr * sr, ntap = bins * spp;
-    int4* tp = reinterpret_cast<int4*>(smem);
-    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
-    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));   // [kChanBlock][bins + 1]
+    const int bins = ph * pw, ny = ph * sr, nx = pw * sr;
+    int4* ty = reinterpret_cast<int4*>(smem);
+    int4* tx = ty + ny;
+    float* tile = reinterpret_cast<float*>(tx + nx);                         // [kChanBlock][bins + 1]
     float* win = tile + kChanBlock * (bins + 1);
     const int win_floats = (kSmemBytes - (int)((uint8_t*)win - smem)) / (int)sizeof(float);
-    __shared__ int bounds[4];
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        bounds[0] = 0x7fffffff; bounds[1] = -1; bounds[2] = 0x7fffffff; bounds[3] = -1;
+    __shared__ int4 s_range;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        int4 range;
+        roi_axis_taps(ty, tx, box, g.scale, g.H, g.W, ph, pw, sr, range);
+        if (lane == 0) s_range = range;
     }
     __syncthreads();
-    compute_taps(tp, tw, bounds, box.x, box.y, box.z, box.w, g.scale, g.H, g.W, ph, pw, sr);
-    __syncthreads();
-    const int y0 = bounds[0], x0 = bounds[2];
-    const int wh = bounds[1] - y0 + 1, ww = bounds[3] - x0 + 1;
-    const float count = (float)spp;
+    const int4 range = s_range;
+    const float count = (float)(sr * sr);
     const size_t plane = (size_t)g.H * g.W;
-    if (bounds[1] < 0) {                       // every sample outside the map: zeros (0 / count)
+    if (range.y < 0 || range.w < 0) {          // every sample outside the map: zeros (0 / count)
         for (int e = tid; e < nch * bins; e += kThreads) dst[(size_t)c0 * bins + e] = 0.f;
         return;
     }
+    const int y0 = range.x, x0 = range.z;
+    const int wh = range.y - y0 + 1, ww = range.w - x0 + 1;
     const int nw = wh * ww;
     int cb = kChanBlock;
     while (cb > 1 && nw * (cb + 1) > win_floats) cb >>= 1;
     if (nw * (cb + 1) > win_floats) {
         // window larger than shared memory even for one channel (maps far beyond the 592x800 geometry): taps from global
+        if (warp == 0) axis_taps_to_offsets(ty, tx, ny, nx, 0, 0, g.W, 1);
+        __syncthreads();
         for (int e = tid; e < nch * bins; e += kThreads) {
             const int cl = e / bins, bin = e - cl * bins;
-            const float* src = g.src + (size_t)(c0 + cl) * plane;
-            float acc = 0.f;
-            for (int s = 0; s < spp; ++s) {
-                const int4 p = tp[bin * spp + s];
-                const float4 w = tw[bin * spp + s];
-                if (p.x < 0) continue;             // adds +0 in the reference
-                const float v1 = __ldg(src + p.x * g.W + p.y), v2 = __ldg(src + p.x * g.W + p.w);
-                const float v3 = __ldg(src + p.z * g.W + p.y), v4 = __ldg(src + p.z * g.W + p.w);
-                acc += w.x * v1 + w.y * v2 + w.z * v3 + w.w * v4;
-            }
-            dst[(size_t)(c0 + cl) * bins + bin] = acc / count;
+            dst[(size_t)(c0 + cl) * bins + bin] = pool_bin(ty, tx, g.src + (size_t)(c0 + cl) * plane, bin / pw, bin % pw, sr, count);
         }
         return;
     }
     const int stride = cb + 1;
-    // window-relative tap positions, pre-multiplied by the channel stride; invalid samples point at element 0 (weight 0)
-    for (int k = tid; k < ntap; k += kThreads) {
-        const int4 p = tp[k];
-        tp[k] = p.x < 0 ? make_int4(0, 0, 0, 0)
-                        : make_int4(((p.x - y0) * ww + (p.y - x0)) * stride, ((p.x - y0) * ww + (p.w - x0)) * stride,
-                                    ((p.z - y0) * ww + (p.y - x0)) * stride, ((p.z - y0) * ww + (p.w - x0)) * stride);
-    }
+    if (warp == 0) axis_taps_to_offsets(ty, tx, ny, nx, y0, x0, ww * stride, stride);
+    const int bins_per_iter = 32 / cb;           // a warp covers cb channels x (32 / cb) bins per step
+    const int cl = lane % cb, bsub = lane / cb;
     for (int sub = 0; sub * cb < nch; ++sub) {
         const int nc = min(cb, nch - sub * cb);
         const float* src0 = g.src + (size_t)(c0 + sub * cb) * plane + (size_t)y0 * g.W + x0;
@@ -199,7 +244,12 @@ __device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph
         __pipeline_commit();
         __pipeline_wait_prior(0);
         __syncthreads();
-        pool_from_smem(tp, tw, win, cb, nc, bins, spp, tile, sub * cb);
+        // ---- pool: lane = (bin slot, channel); the axis entries of a bin are uniform across the lanes of a bin slot
+        for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
+            const int bin = b0 + bsub;
+            if (bin < bins && cl < nc)
+                tile[(sub * cb + cl) * (bins + 1) + bin] = pool_bin(ty, tx, win + cl, bin / pw, bin % pw, sr, count);
+        }
         __syncthreads();
     }
     // ---- contiguous stores of the [nch][bins] tile
@@ -280,7 +330,10 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
 }
 
 // Map-resident kernel, grid (n_images, maps, channels / 8): map 0 = the depth map, map 1 + l = FPN level l (resident ones).
-// The CTA stages its 8 channels of the whole map as [position][9] and pools every box of the image that reads this map.
+// The CTA stages its 8 channels of the whole map as [position][9]; after that every WARP works on its own: it takes the
+// image's boxes round-robin, computes the 16 + 16 axis entries of a box (one per lane), pools its 8 channels x 64 bins
+// (lane = (bin slot, channel)) into a private tile and stores the tile as contiguous rows — no block barrier per box.
+constexpr int kResWarpBytes = 2 * 64 * (int)sizeof(int4);     // axis entries of one box: ph*sr + pw*sr <= 128 (checked on the host)
 __global__ void __launch_bounds__(kThreads, 2)
 roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                            int depth_resident, int channels, const float* __restrict__ boxes,
@@ -290,16 +343,16 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     const int img = blockIdx.x, m = blockIdx.y;
     const int l = m - 1;
     if (m == 0 ? !depth_resident : !lv.resident[l]) return;
-    const int bins = pool * pool, spp = sr * sr, ntap = bins * spp;
-    int4* tp = reinterpret_cast<int4*>(smem);
-    float4* tw = reinterpret_cast<float4*>(smem + (size_t)ntap * sizeof(int4));
-    float* tile = reinterpret_cast<float*>(smem + (size_t)ntap * (sizeof(int4) + sizeof(float4)));   // [kMapChan][bins + 1]
-    float* map = tile + kMapChan * (bins + 1);
+    const int bins = pool * pool, ny = pool * sr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int4* ty = reinterpret_cast<int4*>(smem + (size_t)warp * kResWarpBytes);
+    int4* tx = ty + ny;
+    float* tile = reinterpret_cast<float*>(smem + (size_t)kWarps * kResWarpBytes) + (size_t)warp * kMapChan * (bins + 1);
+    float* map = reinterpret_cast<float*>(smem + (size_t)kWarps * kResWarpBytes) + (size_t)kWarps * kMapChan * (bins + 1);
     const int H = m == 0 ? depth_h : lv.h[l], W = m == 0 ? depth_w : lv.w[l];
     const float scale = m == 0 ? depth_scale : lv.scale[l];
     const int c0 = blockIdx.z * kMapChan, nc = min(kMapChan, channels - c0);
     const int n0 = box_off[img], n1 = box_off[img + 1];
-    const int tid = threadIdx.x;
     // does any box of the image read this map?  (depth: all of them)
     if (m > 0) {
         int any = 0;
@@ -321,28 +374,32 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
+    __syncthreads();
     float* out = m == 0 ? out_depth : out_rgb;
+    const float count = (float)(sr * sr);
+    constexpr int kBinsPerIter = 32 / kMapChan;
+    const int cl = lane % kMapChan, bsub = lane / kMapChan;
+    int slot = 0;                                          // boxes of this map are dealt to the warps round-robin
     for (int n = n0; n < n1; ++n) {
         const float4 bx = __ldg((const float4*)boxes + n);
-        if (m > 0 && map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) != l) continue;   // uniform across the CTA
-        __syncthreads();                                   // previous box: tile stored, taps consumed; first box: map staged
-        for (int k = tid; k < ntap; k += kThreads) {
-            int4 p;
-            float4 w;
-            sample_taps(k, bx.x, bx.y, bx.z, bx.w, scale, H, W, pool, pool, sr, p, w);
-            tp[k] = p.x < 0 ? make_int4(0, 0, 0, 0)
-                            : make_int4((p.x * W + p.y) * stride, (p.x * W + p.w) * stride, (p.z * W + p.y) * stride,
-                                        (p.z * W + p.w) * stride);
-            tw[k] = w;
+        if (m > 0 && map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) != l) continue;
+        if ((slot++ % kWarps) != warp) continue;
+        int4 range;
+        roi_axis_taps(ty, tx, bx, scale, H, W, pool, pool, sr, range);
+        __syncwarp();
+        axis_taps_to_offsets(ty, tx, ny, ny, 0, 0, W * stride, stride);
+        __syncwarp();
+        for (int b0 = 0; b0 < bins; b0 += kBinsPerIter) {
+            const int bin = b0 + bsub;
+            if (cl < nc) tile[cl * (bins + 1) + bin] = pool_bin(ty, tx, map + cl, bin / pool, bin % pool, sr, count);
         }
-        __syncthreads();
-        pool_from_smem(tp, tw, map, kMapChan, nc, bins, spp, tile, 0);
-        __syncthreads();
+        __syncwarp();
         float* dst = out + ((size_t)n * channels + c0) * bins;
-        for (int e = tid; e < nc * bins; e += kThreads) {
+        for (int e = lane; e < nc * bins; e += 32) {
             const int c = e / bins, b = e - c * bins;
             dst[e] = tile[c * (bins + 1) + b];
         }
+        __syncwarp();                                      // the tile and the entries are reused for the warp's next box
     }
 }
 
@@ -513,8 +570,11 @@ roi_align_bwd_resident_kernel(const float* __restrict__ grad, const float* __res
 
 // floats the resident kernels need next to the map: taps + one [8][bins + 1] tile
 __host__ inline bool map_fits_resident(int h, int w, int pool, int sr) {
-    const size_t fixed = (size_t)pool * pool * sr * sr * (sizeof(int4) + sizeof(float4)) + (size_t)kMapChan * (pool * pool + 1) * sizeof(float);
-    return fixed + (size_t)h * w * (kMapChan + 1) * sizeof(float) <= (size_t)kSmemBytes;
+    // forward: per-warp axis entries + per-warp [8][bins + 1] tiles; backward: the 2-D taps + one tile — the larger of the two
+    const size_t fwd = (size_t)kWarps * kResWarpBytes + (size_t)kWarps * kMapChan * (pool * pool + 1) * sizeof(float);
+    const size_t bwd = (size_t)pool * pool * sr * sr * (sizeof(int4) + sizeof(float4)) + (size_t)kMapChan * (pool * pool + 1) * sizeof(float);
+    const size_t fixed = fwd > bwd ? fwd : bwd;
+    return pool * sr <= 64 && fixed + (size_t)h * w * (kMapChan + 1) * sizeof(float) <= (size_t)kSmemBytes;
 }
 
 DeviceOnce g_attr_set;

@@ -15,14 +15,19 @@ int pack_bias2(const float* b, float* dst, int out, cudaStream_t s);          //
 int pack_add(const float* a, const float* b, float* dst, int n, cudaStream_t s);
 int pack_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t s);
 // the same for up to kMaxSplitJobs arrays in ONE launch (the per-step re-split of the weights was 26 tiny launches)
-constexpr int kMaxSplitJobs = 2 + 4 * VETO_MAX_LAYERS;
+constexpr int kMaxSplitJobs = 2 + 6 * VETO_MAX_LAYERS;   // + the LayerNorm-folded to_qkv / FF1 weights
 struct SplitJob {
     const float* src;
     __nv_bfloat16* hi;
     __nv_bfloat16* lo;
     size_t n;
     int fmt = FMT_BF16;   // FMT_F16C8: the WEIGHT side of the f16c8 format (common.cuh): hi = fp16(2048 w), lo = (value, residual) e4m3 bytes
+    const float* col_scale = nullptr;   // optional [row_len]: element (r, k) is multiplied by col_scale[k] first (LayerNorm weight
+    int row_len = 0;                    //   folded into a Linear weight, gemm_tc2.cu EPI_*_LN)
 };
+// c1[n] = sum_k gamma[k] W[n,k],  c2[n] = sum_k beta[k] W[n,k] (+ bias[n]): the constants of a LayerNorm-fused Linear
+int ln_fold_consts(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, float* c1, float* c2,
+                   cudaStream_t s);
 int pack_split_bf16_multi(const SplitJob* jobs, int count, cudaStream_t s);
 
 // ---- box stage (box_stage.cu) ----
