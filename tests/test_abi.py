@@ -51,12 +51,13 @@ def test_host_only_entry_points(lib):
     assert lib.veto_pairs_capacity(n, 4, 0, ctypes.byref(total)) < 0 and b"bad argument" in lib.veto_last_error()
     cfg = ops.make_config(151, 51, "bf16x3")
     packed = lib.veto_packed_bytes(ctypes.byref(cfg))
-    # fp32 factored projections (~5.9 MB) + bf16 hi/lo of 6 layers and the patch projections (~68 MB)
-    assert 70e6 < packed < 80e6
+    # fp32 factored projections (~5.9 MB) + bf16 hi/lo of 6 layers and the patch projections (~68 MB) + the LayerNorm-folded
+    # copies of to_qkv / FF1 (~40 MB)
+    assert 105e6 < packed < 125e6
     assert lib.veto_packed_bytes(ctypes.byref(ops.make_config(151, 51, "fp32"))) < 7e6
     small = lib.veto_workspace_bytes(ctypes.byref(cfg), 20, 380, 0)
     big = lib.veto_workspace_bytes(ctypes.byref(cfg), 2560, 202240, 0)
-    assert 0 < small < big < 2e9          # the workspace scales with N and the chunk, not with R
+    assert 0 < small < big < 5e9          # the workspace scales with N and the chunk (7976 pairs), not with R
     bad = ops.make_config(151, 51, "fp32", heads=8)
     assert lib.veto_workspace_bytes(ctypes.byref(bad), 20, 380, 0) == 0
     # depth backbone: stride-16 output size with torch's floor rule, workspace grows with training (saved im2col)

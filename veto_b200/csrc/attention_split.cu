@@ -69,18 +69,30 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
     const int64_t items = n_seq * kHeads;
     auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
     // ldmatrix row / column of this lane inside a 16 x 16 A tile and inside a pair of 8-row B tiles
+    const int ld_slot = lane64 / 12, ld_chunk = lane64 - ld_slot * 12;      // staging: row slot 0..4 (5 = idle), 16-byte chunk 0..11
+    const int st_slot = lane64 / 24, st_c4 = lane64 - st_slot * 24;         // output: row slot 0..1 (2 = idle), 4-column group 0..23
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
     const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
     for (int64_t item = (int64_t)blockIdx.x * AS_PAIRS + pair; item < items; item += (int64_t)gridDim.x * AS_PAIRS) {
         const int64_t seq = item / kHeads;
         const int h = (int)(item - seq * kHeads);
         const size_t gbase = (size_t)seq * kTokens * LD + h * kHeadDim;
-        for (int idx = lane64; idx < 6 * kTokens * (kHeadDim / 8); idx += 64) {
-            const int a = idx / (kTokens * (kHeadDim / 8)), rem = idx - a * (kTokens * (kHeadDim / 8));
-            const int row = rem / (kHeadDim / 8), c = rem - row * (kHeadDim / 8);
-            const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gbase + (size_t)row * LD + (a >> 1) * kDim + c * 8;
-            __nv_bfloat16* dst = arr + a * AS_ARR + row * AS_PITCH + c * 8;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        // 6 arrays x 19 rows of 12 16-byte chunks: 60 of the pair's 64 lanes own (row slot, chunk) once and for all, so
+        // that every copy is two additions away from its addresses (the flat index -> (array, row, chunk) decode of the
+        // first version cost a quarter of the kernel's instructions)
+        if (ld_slot < 5) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gbase + (a >> 1) * kDim + ld_chunk * 8;
+                __nv_bfloat16* dst = arr + a * AS_ARR + ld_chunk * 8;
+#pragma unroll
+                for (int r0 = 0; r0 < 20; r0 += 5) {
+                    const int row = r0 + ld_slot;
+                    if (row < kTokens)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + row * AS_PITCH)),
+                                     "l"(src + (size_t)row * LD) : "memory");
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -240,8 +252,8 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
                 }
         }
         pair_bar();  // (3) the 19 x 96 output tile is complete; V is no longer read
-        for (int idx = lane64; idx < kTokens * (kHeadDim / 4); idx += 64) {
-            const int row = idx / (kHeadDim / 4), c4 = idx - row * (kHeadDim / 4);
+        for (int row = st_slot; row < kTokens && st_slot < 2; row += 2) {
+            const int c4 = st_c4;
             const float4 v = *(const float4*)(sO + row * AS_OUT_PITCH + 4 * c4);
             const size_t o = ((size_t)seq * kTokens + row) * kDim + h * kHeadDim + 4 * c4;
             if (out_f32) *(float4*)(out_f32 + o) = v;

@@ -156,9 +156,10 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 constexpr float kC8ActRes = 256.f, kC8ActVal = 0.125f, kC8WScale = 2048.f, kC8WVal = 8.f, kC8WRes = 8.f;
 constexpr float kC8AccScale = 1.f / 2048.f;
 
-__device__ __forceinline__ uint32_t f16x2_sat(float x0, float x1) {
-    const __half2 h = __floats2half2_rn(fminf(fmaxf(x0, -65504.f), 65504.f), fminf(fmaxf(x1, -65504.f), 65504.f));
-    return *reinterpret_cast<const uint32_t*>(&h);
+__device__ __forceinline__ uint32_t f16x2_sat(float x0, float x1) {   // x0 in the low half; saturating (one F2FP.SATFINITE)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    return r;
 }
 __device__ __forceinline__ float2 f16x2_to_float(uint32_t h) {
     return __half22float2(*reinterpret_cast<const __half2*>(&h));
@@ -195,7 +196,8 @@ __device__ __forceinline__ void store_act4_f16c8(__nv_bfloat16* hi, __nv_bfloat1
     }
 }
 __device__ __forceinline__ void store_act1_f16c8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, float x) {
-    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    const uint32_t hp = f16x2_sat(x, 0.f);
+    const __half h = __ushort_as_half((unsigned short)(hp & 0xffffu));
     *((__half*)hi + off) = h;
     if (lo) {
         uint8_t* p = (uint8_t*)lo + c8_byte(off);

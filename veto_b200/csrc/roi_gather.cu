@@ -112,11 +112,15 @@ __device__ __forceinline__ void axis_taps_to_offsets(int4* ty, int4* tx, int ny,
 }
 // One bin of one channel from a [position][stride] staging buffer (`win` already offset by the lane's channel): samples in
 // the reference's order (iy outer, ix inner), acc += w1*v1 + w2*v2 + w3*v3 + w4*v4, one division by the sample count.
-__device__ __forceinline__ float pool_bin(const int4* ty, const int4* tx, const float* win, int bh, int bw, int sr, float count) {
+template <int SR>
+__device__ __forceinline__ float pool_bin(const int4* ty, const int4* tx, const float* win, int bh, int bw, int sr_rt, float count) {
+    const int sr = SR > 0 ? SR : sr_rt;          // compile-time sampling ratio: both loops unroll
     float acc = 0.f;
+#pragma unroll
     for (int iy = 0; iy < sr; ++iy) {
         const int4 ye = ty[bh * sr + iy];
         const float ly = __int_as_float(ye.z), hy = __int_as_float(ye.w);
+#pragma unroll
         for (int ix = 0; ix < sr; ++ix) {
             const int4 xe = tx[bw * sr + ix];
             const float lx = __int_as_float(xe.z), hx = __int_as_float(xe.w);
@@ -188,8 +192,10 @@ __device__ __forceinline__ void compute_taps(int4* tp, float4* tw, int* bounds, 
 }
 
 // One (roi, channel block) tile of the window kernel: channels [c0, c0 + nch) of the roi pooled into dst[(c0 + c) * bins + bin].
-__device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph, int pw, int sr, int c0, int nch,
+template <int POOL, int SR>
+__device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph_rt, int pw_rt, int sr_rt, int c0, int nch,
                                             float* __restrict__ dst, uint8_t* smem) {
+    const int ph = POOL > 0 ? POOL : ph_rt, pw = POOL > 0 ? POOL : pw_rt, sr = SR > 0 ? SR : sr_rt;   // 8 x 8, ratio 2: compile time
     const int bins = ph * pw, ny = ph * sr, nx = pw * sr;
     int4* ty = reinterpret_cast<int4*>(smem);
     int4* tx = ty + ny;
@@ -222,7 +228,7 @@ __device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph
         __syncthreads();
         for (int e = tid; e < nch * bins; e += kThreads) {
             const int cl = e / bins, bin = e - cl * bins;
-            dst[(size_t)(c0 + cl) * bins + bin] = pool_bin(ty, tx, g.src + (size_t)(c0 + cl) * plane, bin / pw, bin % pw, sr, count);
+            dst[(size_t)(c0 + cl) * bins + bin] = pool_bin<0>(ty, tx, g.src + (size_t)(c0 + cl) * plane, bin / pw, bin % pw, sr, count);
         }
         return;
     }
@@ -248,7 +254,7 @@ __device__ __forceinline__ void gather_tile(const RoiGeom& g, float4 box, int ph
         for (int b0 = warp * bins_per_iter; b0 < bins; b0 += kWarps * bins_per_iter) {
             const int bin = b0 + bsub;
             if (bin < bins && cl < nc)
-                tile[(sub * cb + cl) * (bins + 1) + bin] = pool_bin(ty, tx, win + cl, bin / pw, bin % pw, sr, count);
+                tile[(sub * cb + cl) * (bins + 1) + bin] = pool_bin<SR>(ty, tx, win + cl, bin / pw, bin % pw, sr, count);
         }
         __syncthreads();
     }
@@ -269,8 +275,8 @@ roi_align_fwd_kernel(const float* __restrict__ input, int channels, int height, 
     const int b = (int)r[0];
     RoiGeom g{input + (size_t)b * channels * height * width, height, width, scale};
     const int c0 = blockIdx.y * kChanBlock;
-    gather_tile(g, make_float4(r[1], r[2], r[3], r[4]), ph, pw, sr, c0, min(kChanBlock, channels - c0),
-                out + (size_t)n * channels * ph * pw, smem_raw);
+    gather_tile<0, 0>(g, make_float4(r[1], r[2], r[3], r[4]), ph, pw, sr, c0, min(kChanBlock, channels - c0),
+                      out + (size_t)n * channels * ph * pw, smem_raw);
 }
 
 struct GatherLevels {
@@ -295,6 +301,7 @@ __device__ __forceinline__ int map_level(float x1, float y1, float x2, float y2,
 
 // Window kernel, grid (N, channel blocks): the RGB features of the boxes whose FPN level is not map-resident
 // (and, when the depth map is too large for the resident kernel, grid.z = 2: z = 1 pools the depth features).
+template <int POOL, int SR>
 __global__ void __launch_bounds__(kThreads, 2)
 roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                   int channels, const float* __restrict__ boxes, const int32_t* __restrict__ box_off, int n_images,
@@ -326,7 +333,7 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
         dst = out_depth + (size_t)n * channels * pool * pool;
     }
     const int c0 = blockIdx.y * kChanBlock;
-    gather_tile(g, bx, pool, pool, sr, c0, min(kChanBlock, channels - c0), dst, smem_raw);
+    gather_tile<POOL, SR>(g, bx, pool, pool, sr, c0, min(kChanBlock, channels - c0), dst, smem_raw);
 }
 
 // Map-resident kernel, grid (n_images, maps, channels / 8): map 0 = the depth map, map 1 + l = FPN level l (resident ones).
@@ -334,12 +341,14 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
 // image's boxes round-robin, computes the 16 + 16 axis entries of a box (one per lane), pools its 8 channels x 64 bins
 // (lane = (bin slot, channel)) into a private tile and stores the tile as contiguous rows — no block barrier per box.
 constexpr int kResWarpBytes = 2 * 64 * (int)sizeof(int4);     // axis entries of one box: ph*sr + pw*sr <= 128 (checked on the host)
+template <int POOL, int SR>
 __global__ void __launch_bounds__(kThreads, 2)
 roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                            int depth_resident, int channels, const float* __restrict__ boxes,
-                           const int32_t* __restrict__ box_off, int pool, int sr, float* __restrict__ out_rgb,
+                           const int32_t* __restrict__ box_off, int pool_rt, int sr_rt, float* __restrict__ out_rgb,
                            float* __restrict__ out_depth) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const int pool = POOL > 0 ? POOL : pool_rt, sr = SR > 0 ? SR : sr_rt;
     const int img = blockIdx.x, m = blockIdx.y;
     const int l = m - 1;
     if (m == 0 ? !depth_resident : !lv.resident[l]) return;
@@ -391,7 +400,7 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
         __syncwarp();
         for (int b0 = 0; b0 < bins; b0 += kBinsPerIter) {
             const int bin = b0 + bsub;
-            if (cl < nc) tile[cl * (bins + 1) + bin] = pool_bin(ty, tx, map + cl, bin / pool, bin % pool, sr, count);
+            if (cl < nc) tile[cl * (bins + 1) + bin] = pool_bin<SR>(ty, tx, map + cl, bin / pool, bin % pool, sr, count);
         }
         __syncwarp();
         float* dst = out + ((size_t)n * channels + c0) * bins;
@@ -581,9 +590,11 @@ DeviceOnce g_attr_set;
 int ensure_attrs() {
     if (!g_attr_set.pending()) return VETO_OK;
     VETO_CUDA(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     VETO_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    VETO_CUDA(cudaFuncSetAttribute(roi_gather_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_resident_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    VETO_CUDA(cudaFuncSetAttribute(roi_gather_resident_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     VETO_CUDA(cudaFuncSetAttribute(roi_align_bwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     g_attr_set.done();
     return VETO_OK;
@@ -682,17 +693,18 @@ extern "C" int veto_roi_gather_forward(const float* const* feats_dev, const int3
     cudaStream_t s = (cudaStream_t)stream;
     if (any_resident || depth_resident) {
         dim3 rgrid(n_images, 1 + n_levels, (channels + kMapChan - 1) / kMapChan);
-        roi_gather_resident_kernel<<<rgrid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale,
-                                                                      depth_resident, channels, boxes_dev, box_offsets_dev, pool,
-                                                                      sampling_ratio, out_rgb_dev, out_depth_dev);
+        // the reference's pooling (8 x 8 bins, sampling ratio 2) has its loop bounds at compile time
+        auto* kern = (pool == 8 && sampling_ratio == 2) ? roi_gather_resident_kernel<8, 2> : roi_gather_resident_kernel<0, 0>;
+        kern<<<rgrid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, depth_resident, channels, boxes_dev,
+                                                box_offsets_dev, pool, sampling_ratio, out_rgb_dev, out_depth_dev);
         VETO_LAUNCH_CHECK();
     }
     if (!all_resident || !depth_resident || levels_out_dev) {
         // grid.y = 1 with every level resident only writes levels_out (the CTAs return at once)
         dim3 grid(n_boxes, all_resident && depth_resident ? 1 : (channels + kChanBlock - 1) / kChanBlock, depth_resident ? 1 : 2);
-        roi_gather_kernel<<<grid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, channels, boxes_dev,
-                                                            box_offsets_dev, n_images, pool, sampling_ratio, out_rgb_dev,
-                                                            out_depth_dev, levels_out_dev);
+        auto* kern = (pool == 8 && sampling_ratio == 2) ? roi_gather_kernel<8, 2> : roi_gather_kernel<0, 0>;
+        kern<<<grid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, channels, boxes_dev, box_offsets_dev,
+                                               n_images, pool, sampling_ratio, out_rgb_dev, out_depth_dev, levels_out_dev);
         VETO_LAUNCH_CHECK();
     }
     return VETO_OK;
