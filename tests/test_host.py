@@ -101,7 +101,7 @@ def test_config_defaults_follow_veto_final_yaml():
     assert vcfg.num_classes(cfg) == (151, 51)
     cfg.GLOBAL_SETTING.DATASET_CHOICE = "GQA"
     assert vcfg.num_classes(cfg) == (201, 101)
-    assert vcfg.get(cfg, "VETO_B200.PRECISION") == "bf16x3" and vcfg.get(cfg, "NOT.THERE", 7) == 7
+    assert vcfg.get(cfg, "VETO_B200.PRECISION") == "f16c8" and vcfg.get(cfg, "NOT.THERE", 7) == 7
     with pytest.raises(KeyError):
         cfg.merge_from_list(["MODEL.NOPE", 1])
     assert vcfg.GROUP_SPLITS[("VG", "divide4")] == synth.GROUP_SPLITS[("VG", "divide4")]

@@ -83,7 +83,7 @@ _DEFAULTS = {
     "GLOVE_DIR": "",
     "OUTPUT_DIR": "",
     # extension (not a reference key): arithmetic of the encoder GEMMs, see include/veto_b200.h
-    "VETO_B200": {"PRECISION": "bf16x3", "CHUNK_PAIRS": 0, "FREQ_BIAS": False, "PRED_COUNTS": "",
+    "VETO_B200": {"PRECISION": "f16c8", "CHUNK_PAIRS": 0, "FREQ_BIAS": False, "PRED_COUNTS": "",
                   "MEET_REFERENCE_DRAWS": False},
 }
 

@@ -85,6 +85,19 @@ bool split_attention_enabled() {
     return on != 0;
 }
 
+// VETO_RESIDUAL_OPERAND=1: drop the fp32 copy of the residual stream and read the residual from the operand-format one
+// (EPI_RESOP_*).  Measured (profiles/r2_modes_residual_ab.jsonl): 4.6 KB / row / layer less HBM traffic, logits unchanged
+// (8.4e-5 -> 8.8e-5), but NOT faster — to_out 51.0 -> 57.9 ms, FF2 61.7 -> 63.9 ms per step: the decode of the residual
+// costs the epilogue more than the bytes save at the clocks the power cap allows.  Off by default.
+bool resop_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VETO_RESIDUAL_OPERAND");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on != 0;
+}
+
 // VETO_LN_FUSION=0 keeps the LayerNorm kernels everywhere (A/B measurements, diagnosis)
 bool ln_fusion_enabled() {
     static int on = -1;
@@ -294,12 +307,20 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
         float2* ln_parts = fuse_ln ? (float2*)(B + W.ln_parts) : nullptr;
         float2* ln_stats = fuse_ln ? (float2*)(B + W.ln_stats) : nullptr;
         bool x_ops_ready = false;     // xo / ln_stats hold the current x
-        auto emit_x = [&](GemmEpilogue& e) {   // an epilogue that writes x: also its operand copy + statistics partials
+        // an epilogue that produces x.  Un-fused: x = acc + bias + x in fp32.  Fused: the result goes out in operand
+        // format with its statistics partials; once xo holds x (after layer 0's to_out) the residual is read from xo too and
+        // the fp32 copy is not written any more — the residual stream lives in operand format only.
+        auto emit_x = [&](GemmEpilogue& e) {
             if (!fuse_ln) return;
             e.out.hi = xo.hi;
             e.out.lo = xo.lo;
             e.out.fmt = xo.fmt;
             e.stats_partials = ln_parts;
+            if (x_ops_ready && resop_enabled()) {
+                e.residual = nullptr;
+                e.out.f32 = nullptr;
+                e.res_op = xo.out();
+            }
         };
         auto finish_x = [&]() -> int {
             if (!fuse_ln) return VETO_OK;
@@ -426,7 +447,8 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             if ((rc = attention_cls(q_cls, qkv, rc_pairs, ao.out(), s))) return rc;
             GemmEpilogue e2;
             e2.bias = w->out_b[l];
-            e2.residual = x;
+            if (x_ops_ready && resop_enabled()) e2.res_op = xo.out();     // the residual stream is in operand format (see emit_x)
+            else e2.residual = x;
             e2.ldr = kTokens * kDim;
             e2.out.f32 = x_cls;
             e2.ldc = kDim;

@@ -116,14 +116,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // order as erff's own), one exp and one reciprocal, no branches — the exact-erff version made the FF1 epilogue
 // ALU-bound (it costs about as many issue slots per tile as the MMAs take cycles).
 __device__ __forceinline__ float gelu_fast(float v) {
-    const float z = fabsf(v) * 0.70710678118654752440f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    // z = |v| / sqrt2; t = 1 / (1 + 0.3275911 z); exp(-z^2) = 2^(-v^2 * log2(e) / 2): the two MUFU ops as plain .approx.ftz
+    // instructions (no range fix-ups: t is in (0, 1], the exponent is <= 0) and the constants folded — 14 instructions
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(v), 1.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(v * v * -0.72134752044448170368f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = 1.f - p * t * __expf(-z * z);          // erf(|v|/sqrt2)
-    return 0.5f * v * (1.f + copysignf(e, v));
+    const float e = fmaf(-(p * t), ex, 1.f);               // erf(|v|/sqrt2)
+    const float hv = 0.5f * v;
+    return fmaf(hv, copysignf(e, v), hv);
 }
 __device__ __forceinline__ float apply_act_tc(float v, int act) {
     if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -279,6 +283,7 @@ struct GemmEpilogue {
     int ln_row_stride = 1;            //   the epilogue applies rstd * (acc - mean * ln_c1[n]) + bias[n] (bias = c2);
     const float* ln_c1 = nullptr;     //   row r's statistics sit at ln_stats[r * ln_row_stride]
     float2* stats_partials = nullptr; // [N / 64][M] partial (sum, sum of squares) of the OUTPUT rows (ln_stats_finalize)
+    ActOut res_op;                    // residual given in OPERAND format (hi / lo / fmt; row stride ldr) instead of `residual`
 };
 // (mean, rstd) of LayerNorm (eps 1e-5) over rows of kDim from the partial sums a gemm_tc2 epilogue wrote
 int ln_stats_finalize(const float2* partials, int n_parts, int64_t rows, float2* stats, cudaStream_t s);

@@ -31,8 +31,11 @@ namespace {
 using namespace tc;
 
 constexpr int BLOCK_M = 128;      // rows per CTA (256 per pair)
-constexpr int BLOCK_N = 192;      // columns per pair tile; each CTA stages BLOCK_N / 2 rows of W
-constexpr int HALF_N = BLOCK_N / 2;
+// Columns per pair tile: template parameter BN = 192 or 256 (each CTA stages BN / 2 rows of W).  192 divides every width of
+// the encoder (576, 1152, 1728); 256 (+ one narrower last tile: 1728 = 6 x 256 + 192, 1152 = 4 x 256 + 128) re-reads the A
+// tile 7 / 5 times instead of 9 / 6 — the kernel is bound by TMA operand delivery (L2 -> SM at ~10 TB/s,
+// profiles/r2_layer_f16c8_ncu.txt), not by the tensor pipe.  W travels in 32-row boxes so that one tensor map serves all widths.
+constexpr int W_BOX_ROWS = 32;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 12;  // three per TMEM lane quarter, interleaved over the 12 column chunks
@@ -40,13 +43,19 @@ constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 constexpr int EPI_COLS = 16;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;
 constexpr int BYTES_A = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int BYTES_B = HALF_N * BLOCK_K * 2;    // 12 KB
-constexpr int PIPE_BYTES = 168 * 1024;           // 3 stages of 56 KB (3-pass) or 6 stages of 28 KB (1-pass)
 constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
 constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = PIPE_BYTES + EPI_BYTES + 1024 + 256;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+template <int BN>
+struct TileN {
+    static constexpr int kHalf = BN / 2;                         // W rows per CTA of a full-width tile
+    static constexpr int kBytesB = kHalf * BLOCK_K * 2;          // 12 KB / 16 KB
+    // 3 stages of two-array operands (56 KB / 64 KB each) or 6 stages of single-array operands
+    static constexpr int kPipe = 3 * 2 * (BYTES_A + kBytesB);
+    static constexpr int kSmem = kPipe + EPI_BYTES + 1024 + 256;
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+    static_assert(2 * BN <= TMEM_COLS, "two accumulator buffers");
+};
 
 // arrive on the barrier at the same offset in CTA `rank` of the cluster
 // TMA load whose completion bytes go to the LEADER CTA's barrier (peer bit of the shared::cluster address cleared)
@@ -67,6 +76,9 @@ struct EpiParams {
     float* pre_f32;
     int res_mode;
     DropSpec drop;
+    const __nv_bfloat16* res_hi;   // residual in OPERAND format (hi / lo arrays, res_fmt) instead of fp32: the residual stream of
+    const __nv_bfloat16* res_lo;   //   the LayerNorm-fused inference path lives in operand format only
+    int res_fmt;
     const float2* ln_stats;  // fused LayerNorm on the A operand: (mean, rstd) of row r at ln_stats[r * ln_row_stride]
     const float* ln_c1;      //   and c1[n] = sum_k gamma_k W[n,k]; `bias` then holds c2[n] = sum_k beta_k W[n,k] (+ bias)
     int ln_row_stride;
@@ -91,16 +103,50 @@ struct EpiParams {
 // LayerNorm weight folded into W (veto_pack_weights), the row statistics come from the epilogue that produced x.
 //   EPI_OP / EPI_OP_LN   operand(acc) / operand(rstd * (acc - mean * c1) + c2)  (to_qkv for attention_split.cu: q, k, v as
 //                        bf16 hi + lo arrays instead of fp32)
-enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_COUNT };
+//   EPI_RESOP_OPS  acc + bias + residual with the residual READ from operand format and the result written in operand
+//                  format only (+ row statistics): x never exists in fp32 between the layers (4.6 KB / row / layer less HBM
+//                  traffic for the HBM-bound to_out / FF2 launches; measured effect on the logits: 8.4e-5 -> 8.8e-5)
+//   EPI_RESOP_F32  the same residual source, fp32 result (the CLS rows of the last layer)
+enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_RESOP_OPS,
+       EPI_RESOP_F32, EPI_COUNT };
 
-template <int EPI>
+// four consecutive residual values from the operand format (flat element offset off, off % 4 == 0)
+__device__ __forceinline__ float4 load_res_operand(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int fmt, size_t off) {
+    const uint2 h = *reinterpret_cast<const uint2*>(hi + off);
+    if (fmt == FMT_F16C8) {
+        const float2 a = f16x2_to_float(h.x), b = f16x2_to_float(h.y);
+        float4 v = make_float4(a.x, a.y, b.x, b.y);
+        if (lo) {   // + e4m3(256 r) / 256: the first byte stream of the 64-element block
+            const uint32_t rb = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(lo) + c8_byte(off));
+            uint32_t r01, r23;
+            asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r01) : "h"((unsigned short)(rb & 0xffffu)));
+            asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r23) : "h"((unsigned short)(rb >> 16)));
+            const float2 ra = f16x2_to_float(r01), rb2 = f16x2_to_float(r23);
+            constexpr float inv = 1.f / kC8ActRes;
+            v.x = fmaf(ra.x, inv, v.x); v.y = fmaf(ra.y, inv, v.y); v.z = fmaf(rb2.x, inv, v.z); v.w = fmaf(rb2.y, inv, v.w);
+        }
+        return v;
+    }
+    float4 v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                           __uint_as_float(h.y & 0xffff0000u));
+    if (lo) {
+        const uint2 l = *reinterpret_cast<const uint2*>(lo + off);
+        v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xffff0000u);
+        v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xffff0000u);
+    }
+    return v;
+}
+
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 int M, int N, int K, int passes, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_epi = smem + PIPE_BYTES;
+    using TN = TileN<BN>;
+    constexpr int BYTES_B = TN::kBytesB;
+    uint8_t* smem_epi = smem + TN::kPipe;
     uint64_t* bars = (uint64_t*)(smem_epi + EPI_BYTES);
     uint64_t* full_bar = bars;                   // [MAX_STAGES]
     uint64_t* empty_bar = bars + MAX_STAGES;     // [MAX_STAGES]
@@ -115,9 +161,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     const bool split = passes == TC_BF16X3 || passes == TC_F16C8;   // a stage holds hi and lo tiles of both operands
     const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
-    const int num_stages = PIPE_BYTES / stage_bytes;  // 3 or 6
+    const int num_stages = TN::kPipe / stage_bytes;  // 3 or 6
     const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-    const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_n = (N + BN - 1) / BN;
     const int mn_tiles = num_m * num_n;
     const int num_tiles = mn_tiles * ep.ksplit;
     const int num_kb = K / BLOCK_K;
@@ -174,17 +220,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 int tm, tn, kb0, kb1;
                 kb_range(tile_mn(tile, tm, tn), kb0, kb1);
                 const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M;
-                const int n0 = tn * BLOCK_N + rank * HALF_N;
+                const int halfw = min(BN, N - tn * BN) >> 1;      // W rows of this CTA (the last column tile may be narrower)
+                const int n0 = tn * BN + rank * halfw;
+                const int tx_bytes = (split ? 2 : 1) * (BYTES_A + halfw * BLOCK_K * 2);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const int k0 = kb * BLOCK_K;
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * tx_bytes);
                     uint8_t* sp = stage_ptr(stage);
                     tma_load_2d_pair(sp, &tm_a_hi, &full_bar[stage], k0, m0);
-                    tma_load_2d_pair(sp + off_w_hi, &tm_w_hi, &full_bar[stage], k0, n0);
+                    for (int r = 0; r < halfw; r += W_BOX_ROWS)
+                        tma_load_2d_pair(sp + off_w_hi + r * (BLOCK_K * 2), &tm_w_hi, &full_bar[stage], k0, n0 + r);
                     if (split) {
                         tma_load_2d_pair(sp + off_a_lo, &tm_a_lo, &full_bar[stage], k0, m0);
-                        tma_load_2d_pair(sp + off_w_lo, &tm_w_lo, &full_bar[stage], k0, n0);
+                        for (int r = 0; r < halfw; r += W_BOX_ROWS)
+                            tma_load_2d_pair(sp + off_w_lo + r * (BLOCK_K * 2), &tm_w_lo, &full_bar[stage], k0, n0 + r);
                     }
                     if (++stage == num_stages) {
                         stage = 0;
@@ -197,10 +247,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc_bf16 = make_idesc(2 * BLOCK_M, BLOCK_N);
-            constexpr uint32_t idesc_fmt0 = make_idesc_fmt0(2 * BLOCK_M, BLOCK_N);   // fp16 (kind::f16) / e4m3 (kind::f8f6f4)
             const bool fp16_ops = passes == TC_F16C8 || passes == TC_F16;
-            const uint32_t idesc = fp16_ops ? idesc_fmt0 : idesc_bf16;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -209,9 +256,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_base + acc * BN;
                 int tm, tn, kb0, kb1;
                 kb_range(tile_mn(tile, tm, tn), kb0, kb1);
+                const int width = min(BN, N - tn * BN);
+                const uint32_t idesc_fmt0 = make_idesc_fmt0(2 * BLOCK_M, width);   // fp16 (kind::f16) / e4m3 (kind::f8f6f4)
+                const uint32_t idesc = fp16_ops ? idesc_fmt0 : make_idesc(2 * BLOCK_M, width);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
@@ -247,15 +297,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         constexpr int kStride = NUM_EPI_WARPS / 4;  // chunks c = half, half + 3, ...
         float4* stage4 = reinterpret_cast<float4*>(smem_epi + (warp - 4) * EPI_STAGE_BYTES);
         const int rsub = lane >> 2, cg = lane & 3;
-        constexpr int kChunks = BLOCK_N / EPI_COLS;
         int it = 0;
         if constexpr (EPI != EPI_GENERIC) {
             constexpr bool kLnIn = EPI == EPI_F32_LN || EPI == EPI_GELU_OP_LN || EPI == EPI_OP_LN;
-            constexpr bool kResid = EPI == EPI_RES || EPI == EPI_RES_OPS;
+            constexpr bool kResOp = EPI == EPI_RESOP_OPS || EPI == EPI_RESOP_F32;       // residual read from operand format
+            constexpr bool kResid = EPI == EPI_RES || EPI == EPI_RES_OPS || kResOp;
             constexpr bool kGelu = EPI == EPI_GELU_OP || EPI == EPI_GELU_OP_LN;
-            constexpr bool kOutF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || kResid;
-            constexpr bool kOutOp = kGelu || EPI == EPI_RES_OPS || EPI == EPI_OP || EPI == EPI_OP_LN;
-            constexpr bool kStats = EPI == EPI_RES_OPS;
+            constexpr bool kOutF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_RES || EPI == EPI_RES_OPS || EPI == EPI_RESOP_F32;
+            constexpr bool kOutOp = kGelu || EPI == EPI_RES_OPS || EPI == EPI_OP || EPI == EPI_OP_LN || EPI == EPI_RESOP_OPS;
+            constexpr bool kStats = EPI == EPI_RES_OPS || EPI == EPI_RESOP_OPS;
+            static_assert(!kStats || BN == 192, "the row-statistics partials are laid out for 192-wide tiles");
             constexpr bool kBias = kResid || kGelu || kLnIn;
             for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
                 const int acc = it & 1;
@@ -263,14 +314,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 int tm, tn;
                 tile_mn(tile, tm, tn);
                 const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
-                const int n0 = tn * BLOCK_N;
+                const int n0 = tn * BN;
+                const int kChunks = min(BN, N - n0) / EPI_COLS;
                 float4 res[4], res_next[4];
                 auto load_res = [&](int c, float4 (&dst)[4]) {
                     const int col = n0 + c * EPI_COLS + cg * 4;
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int row = m0 + rr * 8 + rsub;
-                        dst[rr] = row < M ? *(const float4*)(ep.residual + (size_t)row * ep.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if constexpr (kResOp)
+                            dst[rr] = row < M ? load_res_operand(ep.res_hi, ep.res_lo, ep.res_fmt, (size_t)row * ep.ldr + col)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                        else
+                            dst[rr] = row < M ? *(const float4*)(ep.residual + (size_t)row * ep.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 };
                 float2 st[4];
@@ -284,13 +340,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 }
                 if constexpr (kResid) {
                     load_res(half, res_next);
-                    if (tile + num_pairs < num_tiles) {   // the NEXT tile's residual lines of this warp into L2
+                    if (!kResOp && tile + num_pairs < num_tiles) {   // the NEXT tile's residual lines of this warp into L2
                         int ntm, ntn;
                         tile_mn(tile + num_pairs, ntm, ntn);
                         const int pr = ntm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
-                        const int pc = ntn * BLOCK_N;
+                        const int pc = ntn * BN;
                         if (pr < M) {
-#pragma unroll
                             for (int c = half; c < kChunks; c += kStride)
                                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
                         }
@@ -298,7 +353,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 }
                 mbar_wait(&tmem_full[acc], acc_phase, 4);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
                 for (int c = half; c < kChunks; c += kStride) {
                     if constexpr (kResid) {
@@ -384,7 +439,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             int tm, tn;
             const int ks = tile_mn(tile, tm, tn);
             const int m0 = tm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32;
-            const int n0 = tn * BLOCK_N;
+            const int n0 = tn * BN;
+            const int kChunks = min(BN, N - n0) / EPI_COLS;
             const size_t split_off = (size_t)ks * (size_t)ep.split_stride;
             float4 res[4], res_next[4];
             auto load_res = [&](int c, float4 (&dst)[4]) {
@@ -403,16 +459,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 int ntm, ntn;
                 tile_mn(tile + num_pairs, ntm, ntn);
                 const int pr = ntm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
-                const int pc = ntn * BLOCK_N;
+                const int pc = ntn * BN;
                 if (pr < M) {
-#pragma unroll
                     for (int c = half; c < kChunks; c += kStride)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
                 }
             }
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
             for (int c = half; c < kChunks; c += kStride) {
 #pragma unroll
@@ -539,22 +594,34 @@ int init2() {
     VETO_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VETO_ERR_CUDA,
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_F32_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES_OPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_OP_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define VETO_TC2_ATTR(E, B) \
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem))
+    VETO_TC2_ATTR(EPI_GENERIC, 192); VETO_TC2_ATTR(EPI_F32, 192); VETO_TC2_ATTR(EPI_F32_LN, 192); VETO_TC2_ATTR(EPI_RES, 192);
+    VETO_TC2_ATTR(EPI_RES_OPS, 192); VETO_TC2_ATTR(EPI_GELU_OP, 192); VETO_TC2_ATTR(EPI_GELU_OP_LN, 192); VETO_TC2_ATTR(EPI_OP, 192);
+    VETO_TC2_ATTR(EPI_OP_LN, 192); VETO_TC2_ATTR(EPI_RESOP_OPS, 192); VETO_TC2_ATTR(EPI_RESOP_F32, 192);
+    VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256); VETO_TC2_ATTR(EPI_GELU_OP, 256);
+    VETO_TC2_ATTR(EPI_GELU_OP_LN, 256); VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
+#undef VETO_TC2_ATTR
     g_inited.done();
     return VETO_OK;
 }
 
 }  // namespace
 
-bool gemm_tc2_supported(int N, int K) { return N % BLOCK_N == 0 && K % BLOCK_K == 0; }
+bool gemm_tc2_supported(int N, int K) { return N % 192 == 0 && K % BLOCK_K == 0; }
+
+// 256-wide column tiles (+ one narrower last tile) where that saves A re-reads: to_qkv, 1728 = 6 x 256 + 192 (7 tiles instead
+// of 9: 92.3 -> 87.1 ms per inference step, profiles/r2_modes_bn256_ab.jsonl).  576 stays 3 x 192 (256 + 256 + 64 would be
+// three tiles as well); FF1 (1152 = 4 x 256 + 128) is bound by its epilogue, not by operand delivery, and measured no gain.
+static int tile_width(int N, int ksplit) {
+    static int allow = -1;
+    if (allow < 0) {
+        const char* e = getenv("VETO_GEMM_BN256");
+        allow = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int rem = N % 256;
+    return (allow && ksplit == 1 && N >= 1728 && (rem == 0 || (rem >= 128 && rem % 64 == 0))) ? 256 : 192;
+}
 
 // number of K slices a split-K request really produces (every slice non-empty)
 int gemm_tc2_slices(int K, int split_k) {
@@ -571,7 +638,7 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     if (M <= 0 || N <= 0) return VETO_OK;
     VETO_REQUIRE(passes >= TC_BF16 && passes <= TC_F16, VETO_ERR_ARG, "gemm_tc2: passes must be 1 .. 4 (common.cuh TC_*)");
     VETO_REQUIRE(gemm_tc2_supported(N, K) && K > 0, VETO_ERR_UNSUPPORTED, "gemm_tc2: N=%d must be a multiple of %d, K=%d of %d",
-                 N, BLOCK_N, K, BLOCK_K);
+                 N, 192, K, BLOCK_K);
     VETO_REQUIRE(ep.ldc % 4 == 0 && ep.ldr % 4 == 0 && A.ld % 8 == 0 && W.ld % 8 == 0, VETO_ERR_UNSUPPORTED,
                  "gemm_tc2: unaligned strides");
     const bool two_arrays = passes == TC_BF16X3 || passes == TC_F16C8;
@@ -583,12 +650,12 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     const uint64_t lda = A.ld ? A.ld : K, ldw = W.ld ? W.ld : K;
     if ((rc = get_map(A.hi, M, K, lda, BLOCK_M, &ta_hi))) return rc;
-    if ((rc = get_map(W.hi, N, K, ldw, HALF_N, &tw_hi))) return rc;
+    if ((rc = get_map(W.hi, N, K, ldw, W_BOX_ROWS, &tw_hi))) return rc;
     ta_lo = ta_hi;
     tw_lo = tw_hi;
     if (two_arrays) {   // the e4m3 byte pairs of f16c8 are addressed as 2-byte elements: the same tensor maps
         if ((rc = get_map(A.lo, M, K, lda, BLOCK_M, &ta_lo))) return rc;
-        if ((rc = get_map(W.lo, N, K, ldw, HALF_N, &tw_lo))) return rc;
+        if ((rc = get_map(W.lo, N, K, ldw, W_BOX_ROWS, &tw_lo))) return rc;
     }
     const int num_kb = K / BLOCK_K;
     const int ksplit = gemm_tc2_slices(K, ep.split_k);
@@ -598,22 +665,29 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
                  VETO_ERR_ARG, "gemm_tc2: split-K writes plain fp32 partial products only");
     VETO_REQUIRE(ep.res_mode == RES_ADD || ep.residual, VETO_ERR_ARG, "gemm_tc2: RES_GELU_GRAD needs the pre-activation");
     VETO_REQUIRE(!ep.drop.thr16 || ep.ldc % 4 == 0, VETO_ERR_ARG, "gemm_tc2: dropout needs ldc % 4 == 0");
-    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (N / BLOCK_N) * ksplit;
+    // the residual epilogues (to_out / FF2: N = 576) are built for 192-wide tiles only
+    const int bn = (ep.residual || ep.res_op.hi || ep.stats_partials) ? 192 : tile_width(N, ksplit);
+    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + bn - 1) / bn) * ksplit;
     const int pairs_avail = num_sms() / 2;
     const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     const float acc_scale = (passes == TC_F16C8 || passes == TC_F16) ? kC8AccScale : 1.f;
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
-                ep.pre_f32, ep.res_mode, ep.drop, ep.ln_stats, ep.ln_c1, ep.ln_row_stride > 0 ? ep.ln_row_stride : 1,
+                ep.pre_f32, ep.res_mode, ep.drop, ep.res_op.hi, ep.res_op.lo, ep.res_op.fmt, ep.ln_stats, ep.ln_c1,
+                ep.ln_row_stride > 0 ? ep.ln_row_stride : 1,
                 ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride};
     // the compile-time epilogues of the inference encoder; anything else (training options, tests) is EPI_GENERIC
     const bool plain = !ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ksplit == 1;
     const bool ln_in = ep.ln_stats != nullptr;
     VETO_REQUIRE(!ln_in || (ep.ln_c1 && ep.bias), VETO_ERR_ARG, "gemm_tc2: fused LayerNorm needs ln_c1 and the c2 vector as bias");
     int epi = EPI_GENERIC;
-    if (plain && ep.act == ACT_NONE && !ep.residual && ep.out.f32 && !ep.out.hi && !ep.stats_partials) {
+    if (plain && ep.act == ACT_NONE && ep.res_op.hi && !ep.residual && ep.bias && !ln_in) {
+        VETO_REQUIRE((ep.ldr ? ep.ldr : ep.ldc) % 64 == 0, VETO_ERR_ARG, "gemm_tc2: operand-format residual needs ldr %% 64 == 0");
+        if (ep.out.hi && !ep.out.f32 && ep.stats_partials) epi = EPI_RESOP_OPS;
+        else if (ep.out.f32 && !ep.out.hi && !ep.stats_partials) epi = EPI_RESOP_F32;
+    } else if (plain && ep.act == ACT_NONE && !ep.residual && ep.out.f32 && !ep.out.hi && !ep.stats_partials) {
         if (ln_in) epi = EPI_F32_LN;
         else if (!ep.bias) epi = EPI_F32;
-    } else if (plain && ep.act == ACT_NONE && ep.residual && ep.bias && ep.out.f32 && !ln_in) {
+    } else if (plain && ep.act == ACT_NONE && ep.residual && ep.bias && ep.out.f32 && !ln_in && !ep.res_op.hi) {
         if (ep.out.hi && ep.stats_partials) epi = EPI_RES_OPS;
         else if (!ep.out.hi && !ep.stats_partials) epi = EPI_RES;
     } else if (plain && ep.act == ACT_GELU && !ep.residual && ep.bias && ep.out.hi && !ep.out.f32 && !ep.stats_partials) {
@@ -622,22 +696,37 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
         if (ln_in) epi = EPI_OP_LN;
         else if (!ep.bias) epi = EPI_OP;
     }
-    VETO_REQUIRE(epi != EPI_GENERIC || (!ln_in && !ep.stats_partials), VETO_ERR_UNSUPPORTED,
+    VETO_REQUIRE(epi != EPI_GENERIC || (!ln_in && !ep.stats_partials && !ep.res_op.hi), VETO_ERR_UNSUPPORTED,
                  "gemm_tc2: LayerNorm fusion / row statistics exist for the inference epilogues only");
     static int force_generic = -1;   // VETO_GEMM_GENERIC_EPI=1: diagnosis, every launch through the run-time epilogue
     if (force_generic < 0) force_generic = getenv("VETO_GEMM_GENERIC_EPI") ? 1 : 0;
-    if (force_generic && !ln_in && !ep.stats_partials) epi = EPI_GENERIC;
-#define VETO_TC2_LAUNCH(E) gemm_tc2_kernel<E><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
-    switch (epi) {
-        case EPI_F32: VETO_TC2_LAUNCH(EPI_F32); break;
-        case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN); break;
-        case EPI_RES: VETO_TC2_LAUNCH(EPI_RES); break;
-        case EPI_RES_OPS: VETO_TC2_LAUNCH(EPI_RES_OPS); break;
-        case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP); break;
-        case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN); break;
-        case EPI_OP: VETO_TC2_LAUNCH(EPI_OP); break;
-        case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN); break;
-        default: VETO_TC2_LAUNCH(EPI_GENERIC); break;
+    if (force_generic && !ln_in && !ep.stats_partials && !ep.res_op.hi) epi = EPI_GENERIC;
+#define VETO_TC2_LAUNCH(E, B) \
+    gemm_tc2_kernel<E, B><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    if (bn == 256) {
+        switch (epi) {
+            case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 256); break;
+            case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN, 256); break;
+            case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP, 256); break;
+            case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN, 256); break;
+            case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 256); break;
+            case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 256); break;
+            default: VETO_TC2_LAUNCH(EPI_GENERIC, 256); break;
+        }
+    } else {
+        switch (epi) {
+            case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 192); break;
+            case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN, 192); break;
+            case EPI_RES: VETO_TC2_LAUNCH(EPI_RES, 192); break;
+            case EPI_RES_OPS: VETO_TC2_LAUNCH(EPI_RES_OPS, 192); break;
+            case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP, 192); break;
+            case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN, 192); break;
+            case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 192); break;
+            case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 192); break;
+            case EPI_RESOP_OPS: VETO_TC2_LAUNCH(EPI_RESOP_OPS, 192); break;
+            case EPI_RESOP_F32: VETO_TC2_LAUNCH(EPI_RESOP_F32, 192); break;
+            default: VETO_TC2_LAUNCH(EPI_GENERIC, 192); break;
+        }
     }
 #undef VETO_TC2_LAUNCH
     VETO_LAUNCH_CHECK();

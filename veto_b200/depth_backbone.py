@@ -121,7 +121,7 @@ class ResNetDepth(nn.Module):
 @BACKBONES.register("R-18-C4")
 def build_resnet18_depth(cfg, depth_backbone=False):
     """backbone.py:83-93."""
-    body = ResNetDepth(C.get(cfg, "VETO_B200.PRECISION", "bf16x3"))
+    body = ResNetDepth(C.get(cfg, "VETO_B200.PRECISION", "f16c8"))
     model = nn.Sequential(OrderedDict([("body", body)]))
     model.out_channels = 256
     return model

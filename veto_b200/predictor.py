@@ -163,7 +163,7 @@ class _Trunk(nn.Module):
         self.location_projection = nn.Sequential(nn.Linear(256, dim), nn.ReLU(inplace=True))
         self.fusion_transformer = _VETOTransformer(config, in_channels=256)
         self.n_layers = t.ENC_LAYERS
-        self.precision = C.get(config, "VETO_B200.PRECISION", "bf16x3")
+        self.precision = C.get(config, "VETO_B200.PRECISION", "f16c8")
         self.chunk_pairs = int(C.get(config, "VETO_B200.CHUNK_PAIRS", 0) or 0)
         self._packed = None
         self._packed_key = None
