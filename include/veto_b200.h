@@ -170,7 +170,8 @@ int veto_roi_align_backward(const float* grad_dev, const float* rois_dev, int n_
  * level's map, depth always from `depth_dev` with `depth_scale` (poolers.py:144-153).
  * feats_dev: n_levels (<= 4) device pointers (host array), each [B,C,feat_h[l],feat_w[l]].
  * boxes_dev [N,4] fp32 xyxy; box_offsets_dev int32 [n_images+1].
- * Outputs out_rgb_dev / out_depth_dev [N,C,pool,pool] fp32; levels_out_dev int32 [N] or NULL. */
+ * Outputs out_rgb_dev / out_depth_dev [N,C,pool,pool] fp32; levels_out_dev int32 [N] or NULL (give it: the FPN level
+ * of a box is then computed once by a separate launch and read by the gather kernels, instead of once per CTA). */
 int veto_roi_gather_forward(const float* const* feats_dev, const int32_t* feat_h, const int32_t* feat_w,
                             const float* scales, int n_levels, int k_min, int k_max,
                             const float* depth_dev, int depth_h, int depth_w, float depth_scale,

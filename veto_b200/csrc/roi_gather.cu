@@ -30,7 +30,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChanBlock = 32;                 // channels per CTA of the window kernel
 constexpr int kMapChan = 8;                    // channels per CTA of the map-resident kernel
-constexpr int kSmemBytes = 100 * 1024;         // two CTAs per SM
+constexpr int kSmemBytes = 110 * 1024;         // two CTAs per SM (2 x (110 + 1) KB of the 228 KB)
 
 struct RoiGeom {
     const float* src;   // [C, H, W] planes of the roi's image
@@ -129,6 +129,11 @@ __device__ __forceinline__ float pool_bin(const int4* ty, const int4* tx, const 
             acc += w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
         }
     }
+    // one division by the sample count, as the reference; for the sampling ratios 1 / 2 / 4 the count is a power of two and
+    // the multiplication by its reciprocal is the same correctly rounded result (an IEEE division costs ~10 instructions)
+    if (SR == 1) return acc;
+    if (SR == 2) return acc * 0.25f;
+    if (SR == 4) return acc * 0.0625f;
     return acc / count;
 }
 
@@ -299,6 +304,14 @@ __device__ __forceinline__ int map_level(float x1, float y1, float x2, float y2,
     return (int)lvl - k_min;
 }
 
+// FPN level of every box, once (the double-precision log2 of map_level is ~300 instructions on this chip)
+__global__ void roi_levels_kernel(const float* __restrict__ boxes, int n_boxes, int k_min, int k_max, int32_t* __restrict__ levels) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_boxes) return;
+    const float4 bx = __ldg((const float4*)boxes + n);
+    levels[n] = map_level(bx.x, bx.y, bx.z, bx.w, k_min, k_max);
+}
+
 // Window kernel, grid (N, channel blocks): the RGB features of the boxes whose FPN level is not map-resident
 // (and, when the depth map is too large for the resident kernel, grid.z = 2: z = 1 pools the depth features).
 template <int POOL, int SR>
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                   int channels, const float* __restrict__ boxes, const int32_t* __restrict__ box_off, int n_images,
                   int pool, int sr, float* __restrict__ out_rgb, float* __restrict__ out_depth,
-                  int32_t* __restrict__ levels_out) {
+                  const int32_t* __restrict__ levels_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int n = blockIdx.x;
     const float4 bx = __ldg((const float4*)boxes + n);
@@ -314,8 +327,9 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
     float* dst;
     int l = -1;
     if (blockIdx.z == 0) {
-        l = map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max);
-        if (levels_out && blockIdx.y == 0 && threadIdx.x == 0) levels_out[n] = l;
+        // the level comes from roi_levels_kernel when the caller gave a levels buffer (one double-precision log2 per box
+        // instead of one per thread of every CTA of the box)
+        l = levels_out ? levels_out[n] : map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max);
         if (lv.resident[l]) return;
     }
     // image of box n (poolers.py:96-107: roi batch index)
@@ -340,13 +354,17 @@ roi_gather_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h,
 // The CTA stages its 8 channels of the whole map as [position][9]; after that every WARP works on its own: it takes the
 // image's boxes round-robin, computes the 16 + 16 axis entries of a box (one per lane), pools its 8 channels x 64 bins
 // (lane = (bin slot, channel)) into a private tile and stores the tile as contiguous rows — no block barrier per box.
-constexpr int kResWarpBytes = 2 * 64 * (int)sizeof(int4);     // axis entries of one box: ph*sr + pw*sr <= 128 (checked on the host)
+// 16 warps per CTA and compact per-warp areas (16 + 16 axis entries = 512 B, an [8][65] tile = 2080 B): with the 68 KB
+// map of a 38 x 50 level two CTAs = 32 warps share an SM.  The first version (8 warps, 2 CTAs) was latency-bound: 62 %
+// issue-active at 23 % occupancy (profiles/r2_gather_kernels.txt).
+constexpr int kResThreads = 512;
+constexpr int kResWarps = kResThreads / 32;
 template <int POOL, int SR>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kResThreads, 2)
 roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int depth_h, int depth_w, float depth_scale,
                            int depth_resident, int channels, const float* __restrict__ boxes,
                            const int32_t* __restrict__ box_off, int pool_rt, int sr_rt, float* __restrict__ out_rgb,
-                           float* __restrict__ out_depth) {
+                           float* __restrict__ out_depth, const int32_t* __restrict__ levels) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int pool = POOL > 0 ? POOL : pool_rt, sr = SR > 0 ? SR : sr_rt;
     const int img = blockIdx.x, m = blockIdx.y;
@@ -354,10 +372,11 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     if (m == 0 ? !depth_resident : !lv.resident[l]) return;
     const int bins = pool * pool, ny = pool * sr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int4* ty = reinterpret_cast<int4*>(smem + (size_t)warp * kResWarpBytes);
+    const int warp_tap_bytes = 2 * ny * (int)sizeof(int4);
+    int4* ty = reinterpret_cast<int4*>(smem + (size_t)warp * warp_tap_bytes);
     int4* tx = ty + ny;
-    float* tile = reinterpret_cast<float*>(smem + (size_t)kWarps * kResWarpBytes) + (size_t)warp * kMapChan * (bins + 1);
-    float* map = reinterpret_cast<float*>(smem + (size_t)kWarps * kResWarpBytes) + (size_t)kWarps * kMapChan * (bins + 1);
+    float* tile = reinterpret_cast<float*>(smem + (size_t)kResWarps * warp_tap_bytes) + (size_t)warp * kMapChan * (bins + 1);
+    float* map = reinterpret_cast<float*>(smem + (size_t)kResWarps * warp_tap_bytes) + (size_t)kResWarps * kMapChan * (bins + 1);
     const int H = m == 0 ? depth_h : lv.h[l], W = m == 0 ? depth_w : lv.w[l];
     const float scale = m == 0 ? depth_scale : lv.scale[l];
     const int c0 = blockIdx.z * kMapChan, nc = min(kMapChan, channels - c0);
@@ -365,9 +384,13 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     // does any box of the image read this map?  (depth: all of them)
     if (m > 0) {
         int any = 0;
-        for (int n = n0 + tid; n < n1; n += kThreads) {
-            const float4 bx = __ldg((const float4*)boxes + n);
-            any |= map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) == l;
+        for (int n = n0 + tid; n < n1; n += kResThreads) {
+            if (levels) {
+                any |= levels[n] == l;
+            } else {
+                const float4 bx = __ldg((const float4*)boxes + n);
+                any |= map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) == l;
+            }
         }
         if (!__syncthreads_or(any)) return;
     } else if (n1 <= n0) {
@@ -377,7 +400,7 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     constexpr int stride = kMapChan + 1;
     const int hw = H * W;
     // the nc planes are one contiguous range of nc * hw floats: consecutive threads copy consecutive elements
-    for (int e = tid; e < nc * hw; e += kThreads) {
+    for (int e = tid; e < nc * hw; e += kResThreads) {
         const int c = e / hw, pos = e - c * hw;
         __pipeline_memcpy_async(map + (size_t)pos * stride + c, src + e, sizeof(float));
     }
@@ -390,9 +413,10 @@ roi_gather_resident_kernel(GatherLevels lv, const float* __restrict__ depth, int
     const int cl = lane % kMapChan, bsub = lane / kMapChan;
     int slot = 0;                                          // boxes of this map are dealt to the warps round-robin
     for (int n = n0; n < n1; ++n) {
+        if (m > 0 && levels && levels[n] != l) continue;
         const float4 bx = __ldg((const float4*)boxes + n);
-        if (m > 0 && map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) != l) continue;
-        if ((slot++ % kWarps) != warp) continue;
+        if (m > 0 && !levels && map_level(bx.x, bx.y, bx.z, bx.w, lv.k_min, lv.k_max) != l) continue;
+        if ((slot++ % kResWarps) != warp) continue;
         int4 range;
         roi_axis_taps(ty, tx, bx, scale, H, W, pool, pool, sr, range);
         __syncwarp();
@@ -580,7 +604,7 @@ roi_align_bwd_resident_kernel(const float* __restrict__ grad, const float* __res
 // floats the resident kernels need next to the map: taps + one [8][bins + 1] tile
 __host__ inline bool map_fits_resident(int h, int w, int pool, int sr) {
     // forward: per-warp axis entries + per-warp [8][bins + 1] tiles; backward: the 2-D taps + one tile — the larger of the two
-    const size_t fwd = (size_t)kWarps * kResWarpBytes + (size_t)kWarps * kMapChan * (pool * pool + 1) * sizeof(float);
+    const size_t fwd = (size_t)kResWarps * 2 * pool * sr * sizeof(int4) + (size_t)kResWarps * kMapChan * (pool * pool + 1) * sizeof(float);
     const size_t bwd = (size_t)pool * pool * sr * sr * (sizeof(int4) + sizeof(float4)) + (size_t)kMapChan * (pool * pool + 1) * sizeof(float);
     const size_t fixed = fwd > bwd ? fwd : bwd;
     return pool * sr <= 64 && fixed + (size_t)h * w * (kMapChan + 1) * sizeof(float) <= (size_t)kSmemBytes;
@@ -691,17 +715,20 @@ extern "C" int veto_roi_gather_forward(const float* const* feats_dev, const int3
     }
     const int depth_resident = map_fits_resident(depth_h, depth_w, pool, sampling_ratio) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
+    if (levels_out_dev) {
+        roi_levels_kernel<<<(n_boxes + 127) / 128, 128, 0, s>>>(boxes_dev, n_boxes, k_min, k_max, levels_out_dev);
+        VETO_LAUNCH_CHECK();
+    }
     if (any_resident || depth_resident) {
         dim3 rgrid(n_images, 1 + n_levels, (channels + kMapChan - 1) / kMapChan);
         // the reference's pooling (8 x 8 bins, sampling ratio 2) has its loop bounds at compile time
         auto* kern = (pool == 8 && sampling_ratio == 2) ? roi_gather_resident_kernel<8, 2> : roi_gather_resident_kernel<0, 0>;
-        kern<<<rgrid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, depth_resident, channels, boxes_dev,
-                                                box_offsets_dev, pool, sampling_ratio, out_rgb_dev, out_depth_dev);
+        kern<<<rgrid, kResThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, depth_resident, channels, boxes_dev,
+                                                box_offsets_dev, pool, sampling_ratio, out_rgb_dev, out_depth_dev, levels_out_dev);
         VETO_LAUNCH_CHECK();
     }
-    if (!all_resident || !depth_resident || levels_out_dev) {
-        // grid.y = 1 with every level resident only writes levels_out (the CTAs return at once)
-        dim3 grid(n_boxes, all_resident && depth_resident ? 1 : (channels + kChanBlock - 1) / kChanBlock, depth_resident ? 1 : 2);
+    if (!all_resident || !depth_resident) {
+        dim3 grid(n_boxes, (channels + kChanBlock - 1) / kChanBlock, depth_resident ? 1 : 2);
         auto* kern = (pool == 8 && sampling_ratio == 2) ? roi_gather_kernel<8, 2> : roi_gather_kernel<0, 0>;
         kern<<<grid, kThreads, kSmemBytes, s>>>(lv, depth_dev, depth_h, depth_w, depth_scale, channels, boxes_dev, box_offsets_dev,
                                                n_images, pool, sampling_ratio, out_rgb_dev, out_depth_dev, levels_out_dev);

@@ -139,7 +139,7 @@ def roi_gather(feats: Sequence[torch.Tensor], depth: torch.Tensor, boxes: torch.
     dev = boxes.device
     x2d = torch.empty((N, C, pool, pool), dtype=torch.float32, device=dev)
     d2d = torch.empty((N, C, pool, pool), dtype=torch.float32, device=dev)
-    levels = torch.empty(N, dtype=torch.int32, device=dev) if return_levels else None
+    levels = torch.empty(N, dtype=torch.int32, device=dev)   # always: the library then computes the FPN level once per box
     if N:
         box_off = offsets_tensor(n_boxes, dev)
         fp = (ctypes.c_void_p * n_levels)(*[f.data_ptr() for f in feats])
