@@ -1019,3 +1019,28 @@ def test_attention_tcgen05_kernel(n_seq):
     ref = att.permute(0, 2, 1, 3).reshape(n_seq * 19, 576).numpy()
     assert rel_err(H.np_(ops.test_attention_tc(_t(qkv.numpy()), True)), ref) < 3e-5
     assert rel_err(H.np_(ops.test_attention_tc(_t(qkv.numpy()), False)), ref) < 1e-2
+
+
+def test_gemm_cluster4_multicast_path():
+    """The opt-in 4-CTA-cluster variant of the encoder GEMMs (W tile multicast between two row tiles,
+    VETO_GEMM_CLUSTER4) must give the same logits bit for bit as the pair kernels: same tiles, same K order.  The switch
+    is read once per process, so both arms run in child processes."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import numpy as np, sys; from tests import test_gpu_parity as T;"
+            "out = [r.detach().cpu().numpy().ravel() for n in ('cfg1_predcls_vg', 'sgdet_cap', 'ragged_predcls')"
+            " for p in ('f16c8', 'bf16x3') for r in T._run_predictor(n, p)[6][1]];"
+            "np.save(sys.argv[1], np.concatenate(out))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("0", "2"):
+        path = os.path.join("/tmp", "veto_cluster4_%s_%d.npy" % (mode, os.getpid()))
+        env = dict(os.environ, VETO_GEMM_CLUSTER4=mode, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+        os.remove(path)
+    assert outs[0].shape == outs[1].shape and outs[0].size > 0
+    assert np.array_equal(outs[0], outs[1])

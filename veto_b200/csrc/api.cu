@@ -85,15 +85,17 @@ bool split_attention_enabled() {
     return on != 0;
 }
 
-// VETO_RESIDUAL_OPERAND=1: drop the fp32 copy of the residual stream and read the residual from the operand-format one
-// (EPI_RESOP_*).  Measured (profiles/r2_modes_residual_ab.jsonl): 4.6 KB / row / layer less HBM traffic, logits unchanged
-// (8.4e-5 -> 8.8e-5), but NOT faster — to_out 51.0 -> 57.9 ms, FF2 61.7 -> 63.9 ms per step: the decode of the residual
-// costs the epilogue more than the bytes save at the clocks the power cap allows.  Off by default.
+// The residual stream between the layers lives in operand format only (EPI_RESOP_*): no fp32 copy of x is written or read
+// (2.3 KB / row less HBM traffic for each to_out / FF2 launch; logits 8.4e-5 -> 8.8e-5).  The first version read the
+// residual with one 12-byte load per four values one chunk ahead and was SLOWER (to_out 51.0 -> 57.9 ms,
+// profiles/r2_modes_residual_ab.jsonl); with the next tile's lines prefetched into L2 and the raw words two chunks ahead
+// it is faster: to_out 52.2 -> 46.6 ms, FF2 63.4 -> 60.9 ms per step (profiles/r2_modes_residual_ab2.jsonl).
+// VETO_RESIDUAL_OPERAND=0 keeps the fp32 residual stream (A/B measurements).
 bool resop_enabled() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("VETO_RESIDUAL_OPERAND");
-        on = (e && e[0] == '1') ? 1 : 0;
+        on = (e && e[0] == '0') ? 0 : 1;
     }
     return on != 0;
 }

@@ -88,6 +88,7 @@ struct EpiParams {
     int ksplit;              // K slices (wgrad: tiny output, huge K); tiles enumerate (slice, m, n)
     int kb_per;              // K blocks per slice
     long long split_stride;  // elements between the partial outputs of consecutive slices
+    int w_box;               // rows per TMA box of W (32; 16 for the 4-CTA clusters: a quarter of a 192-wide tile is 48 rows)
 };
 
 // Epilogue variants.  EPI_GENERIC evaluates every option of EpiParams at run time (training branch, tests); the others
@@ -137,8 +138,34 @@ __device__ __forceinline__ float4 load_res_operand(const __nv_bfloat16* hi, cons
     return v;
 }
 
-template <int EPI, int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// the same in two steps: raw words now (12 bytes per four values: small enough to keep two chunks in flight), decode at use
+struct RawRes {
+    uint2 h;
+    uint32_t l;
+};
+__device__ __forceinline__ RawRes load_res_raw(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int fmt, size_t off) {
+    RawRes r;
+    r.h = *reinterpret_cast<const uint2*>(hi + off);
+    r.l = 0u;
+    if (fmt == FMT_F16C8 && lo) r.l = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(lo) + c8_byte(off));
+    return r;
+}
+__device__ __forceinline__ float4 decode_res_f16c8(const RawRes& r) {
+    const float2 a = f16x2_to_float(r.h.x), b = f16x2_to_float(r.h.y);
+    uint32_t r01, r23;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r01) : "h"((unsigned short)(r.l & 0xffffu)));
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r23) : "h"((unsigned short)(r.l >> 16)));
+    const float2 ra = f16x2_to_float(r01), rb = f16x2_to_float(r23);
+    constexpr float inv = 1.f / kC8ActRes;
+    return make_float4(fmaf(ra.x, inv, a.x), fmaf(ra.y, inv, a.y), fmaf(rb.x, inv, b.x), fmaf(rb.y, inv, b.y));
+}
+
+// CL = CTAs per cluster.  2: one CTA pair.  4: two pairs on consecutive row tiles of the same column tile share the W
+// tile — every CTA fetches half of its pair-half of W and multicasts it to the CTA of the same rank parity in the other
+// pair, so the W bytes cross L2 -> SM once per two row tiles.  The encoder GEMMs run at the L2 throughput cap (~6000 B /
+// SM cycle over the chip), not at the tensor-pipe or HBM limit.
+template <int EPI, int BN, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 int M, int N, int K, int passes, EpiParams ep) {
@@ -156,7 +183,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    static_assert(CL == 2 || CL == 4, "one or two CTA pairs per cluster");
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;        // CTA inside its pair
+    const uint32_t prank = crank >> 1;       // pair inside the cluster
     const bool leader = rank == 0;
 
     const bool split = passes == TC_BF16X3 || passes == TC_F16C8;   // a stage holds hi and lo tiles of both operands
@@ -165,10 +195,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     const int num_n = (N + BN - 1) / BN;
     const int mn_tiles = num_m * num_n;
-    const int num_tiles = mn_tiles * ep.ksplit;
+    // CL == 4: a cluster walks (pair of row tiles, column tile); no split-K
+    const int num_tiles = CL == 4 ? ((num_m + 1) >> 1) * num_n : mn_tiles * ep.ksplit;
     const int num_kb = K / BLOCK_K;
     // tile -> (K slice, m tile, n tile) and the K-block range of the slice
     auto tile_mn = [&](int tile, int& tm, int& tn) {
+        if constexpr (CL == 4) {
+            const int tm2 = tile / num_n;
+            tn = tile - tm2 * num_n;
+            tm = 2 * tm2 + (int)prank;   // may be one past the last row tile: TMA zero-fills, nothing is stored
+            return 0;
+        }
         const int t2 = tile % mn_tiles;
         tm = t2 / num_n;
         tn = t2 - tm * num_n;
@@ -178,7 +215,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         kb0 = ks * ep.kb_per;
         kb1 = kb0 + ep.kb_per < num_kb ? kb0 + ep.kb_per : num_kb;
     };
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;   // scheduling unit: the cluster
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi);
@@ -191,7 +228,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], CL / 2);   // one commit per pair that reads the stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -229,12 +266,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * tx_bytes);
                     uint8_t* sp = stage_ptr(stage);
                     tma_load_2d_pair(sp, &tm_a_hi, &full_bar[stage], k0, m0);
-                    for (int r = 0; r < halfw; r += W_BOX_ROWS)
-                        tma_load_2d_pair(sp + off_w_hi + r * (BLOCK_K * 2), &tm_w_hi, &full_bar[stage], k0, n0 + r);
-                    if (split) {
-                        tma_load_2d_pair(sp + off_a_lo, &tm_a_lo, &full_bar[stage], k0, m0);
-                        for (int r = 0; r < halfw; r += W_BOX_ROWS)
-                            tma_load_2d_pair(sp + off_w_lo + r * (BLOCK_K * 2), &tm_w_lo, &full_bar[stage], k0, n0 + r);
+                    if (split) tma_load_2d_pair(sp + off_a_lo, &tm_a_lo, &full_bar[stage], k0, m0);
+                    if constexpr (CL == 4) {
+                        // this CTA's quarter of the column tile, to both CTAs of this rank parity
+                        const int qw = halfw >> 1, r0 = (int)prank * qw;
+                        const uint16_t mask = (uint16_t)(0x5u << rank);
+                        for (int r = r0; r < r0 + qw; r += ep.w_box) {
+                            tma_load_2d_pair_mc(sp + off_w_hi + r * (BLOCK_K * 2), &tm_w_hi, &full_bar[stage], k0, n0 + r, mask);
+                            if (split)
+                                tma_load_2d_pair_mc(sp + off_w_lo + r * (BLOCK_K * 2), &tm_w_lo, &full_bar[stage], k0, n0 + r, mask);
+                        }
+                    } else {
+                        for (int r = 0; r < halfw; r += ep.w_box) {
+                            tma_load_2d_pair(sp + off_w_hi + r * (BLOCK_K * 2), &tm_w_hi, &full_bar[stage], k0, n0 + r);
+                            if (split) tma_load_2d_pair(sp + off_w_lo + r * (BLOCK_K * 2), &tm_w_lo, &full_bar[stage], k0, n0 + r);
+                        }
                     }
                     if (++stage == num_stages) {
                         stage = 0;
@@ -280,13 +326,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             umma2_f8(tmem_d, make_smem_desc(sp + off_a_lo + ko), make_smem_desc(sp + off_w_lo + ko), idesc_fmt0, 1u);
                         }
                     }
-                    umma2_commit_both(&empty_bar[stage]);
+                    umma2_commit_mask(&empty_bar[stage], CL == 4 ? 0xFu : 0x3u);   // every CTA that writes into this stage
                     if (++stage == num_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma2_commit_both(&tmem_full[acc]);
+                umma2_commit_mask(&tmem_full[acc], 0x3u << (2 * prank));   // the epilogues of this pair
             }
         }
         __syncwarp();
@@ -338,29 +384,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         st[rr] = row < M ? __ldg(ep.ln_stats + (size_t)row * ep.ln_row_stride) : make_float2(0.f, 0.f);
                     }
                 }
+                RawRes raw_a[4], raw_b[4];
+                auto load_raw = [&](int c, RawRes (&dst)[4]) {
+                    const int col = n0 + c * EPI_COLS + cg * 4;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = min(m0 + rr * 8 + rsub, M - 1);   // rows beyond M are never stored
+                        dst[rr] = load_res_raw(ep.res_hi, ep.res_lo, ep.res_fmt, (size_t)row * ep.ldr + col);
+                    }
+                };
                 if constexpr (kResid) {
-                    load_res(half, res_next);
-                    if (!kResOp && tile + num_pairs < num_tiles) {   // the NEXT tile's residual lines of this warp into L2
+                    if constexpr (kResOp && BN == 192) {
+                        if (ep.res_fmt == FMT_F16C8 && ep.res_lo) {
+                            load_raw(half, raw_a);
+                            load_raw(half + kStride, raw_b);
+                        }
+                    } else {
+                        load_res(half, res_next);
+                    }
+                    if (tile + num_pairs < num_tiles) {   // the NEXT tile's residual lines of this warp into L2
                         int ntm, ntn;
                         tile_mn(tile + num_pairs, ntm, ntn);
                         const int pr = ntm * (2 * BLOCK_M) + rank * BLOCK_M + q * 32 + lane;
                         const int pc = ntn * BN;
                         if (pr < M) {
-                            for (int c = half; c < kChunks; c += kStride)
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
+                            if constexpr (kResOp) {
+                                // operand format: 128 B of hi and 128 B of lo per 64 columns; this warp third takes block `half`
+                                const size_t off = (size_t)pr * ep.ldr + pc + half * 64;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.res_hi + off));
+                                if (ep.res_lo) {
+                                    const size_t lo_b = ep.res_fmt == FMT_F16C8 ? c8_byte(off) : off * 2;
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(ep.res_lo) + lo_b));
+                                }
+                            } else {
+                                for (int c = half; c < kChunks; c += kStride)
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + (size_t)pr * ep.ldr + pc + c * EPI_COLS));
+                            }
                         }
                     }
                 }
                 mbar_wait(&tmem_full[acc], acc_phase, 4);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-                for (int c = half; c < kChunks; c += kStride) {
-                    if constexpr (kResid) {
-#pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) res[rr] = res_next[rr];
-                        if (c + kStride < kChunks) load_res(c + kStride, res_next);
-                    }
+                auto chunk_body = [&](int c) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c * EPI_COLS, r);
                     tmem_ld_wait();
@@ -416,10 +482,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         }
                     }
                     __syncwarp();
+                };
+                if constexpr (kResOp && BN == 192) {
+                    // f16c8 residual stream: the four chunks of this warp unrolled, raw words two chunks ahead
+                    if (ep.res_fmt == FMT_F16C8 && ep.res_lo) {
+#pragma unroll
+                        for (int i = 0; i < 12 / kStride; ++i) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) res[rr] = decode_res_f16c8((i & 1) ? raw_b[rr] : raw_a[rr]);
+                            if (i + 2 < 12 / kStride) load_raw(half + (i + 2) * kStride, (i & 1) ? raw_b : raw_a);
+                            chunk_body(half + i * kStride);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int c = half; c < kChunks; c += kStride) {
+                            load_res(c, res);
+                            chunk_body(c);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = half; c < kChunks; c += kStride) {
+                        if constexpr (kResid) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) res[rr] = res_next[rr];
+                            if (c + kStride < kChunks) load_res(c + kStride, res_next);
+                        }
+                        chunk_body(c);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], crank & ~1u);
                 if constexpr (kStats) {
                     // this warp covered 64 of the row's columns (4 chunks x 16): one partial per (column tile, warp third)
 #pragma unroll
@@ -525,7 +619,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA thread waits for both CTAs
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], crank & ~1u);  // the leader's MMA thread waits for both CTAs
         }
     }
 
@@ -585,6 +679,28 @@ int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, u
     return VETO_OK;
 }
 
+// co-resident 4-CTA clusters of a kernel (a GPC whose SM count is no multiple of 4 leaves SMs out): the persistent grid
+int g_clusters4[EPI_COUNT][2] = {};
+int max_clusters4(const void* fn, int smem) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / 4 * 4);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 4;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int init2() {
     if (!g_inited.pending()) return VETO_OK;
     std::lock_guard<std::mutex> lk(g_mu);
@@ -595,13 +711,23 @@ int init2() {
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
 #define VETO_TC2_ATTR(E, B) \
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem))
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem))
     VETO_TC2_ATTR(EPI_GENERIC, 192); VETO_TC2_ATTR(EPI_F32, 192); VETO_TC2_ATTR(EPI_F32_LN, 192); VETO_TC2_ATTR(EPI_RES, 192);
     VETO_TC2_ATTR(EPI_RES_OPS, 192); VETO_TC2_ATTR(EPI_GELU_OP, 192); VETO_TC2_ATTR(EPI_GELU_OP_LN, 192); VETO_TC2_ATTR(EPI_OP, 192);
     VETO_TC2_ATTR(EPI_OP_LN, 192); VETO_TC2_ATTR(EPI_RESOP_OPS, 192); VETO_TC2_ATTR(EPI_RESOP_F32, 192);
     VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256); VETO_TC2_ATTR(EPI_GELU_OP, 256);
     VETO_TC2_ATTR(EPI_GELU_OP_LN, 256); VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
 #undef VETO_TC2_ATTR
+    // the 4-CTA-cluster instances: the full-sequence launches of the inference encoder
+#define VETO_TC2_ATTR4(E, B)                                                                                              \
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem)); \
+    g_clusters4[E][B == 256] = max_clusters4((const void*)gemm_tc2_kernel<E, B, 4>, TileN<B>::kSmem)
+    VETO_TC2_ATTR4(EPI_OP, 256); VETO_TC2_ATTR4(EPI_OP_LN, 256); VETO_TC2_ATTR4(EPI_GELU_OP, 192); VETO_TC2_ATTR4(EPI_GELU_OP_LN, 192);
+    VETO_TC2_ATTR4(EPI_RES_OPS, 192); VETO_TC2_ATTR4(EPI_RESOP_OPS, 192);
+#undef VETO_TC2_ATTR4
+    if (getenv("VETO_GEMM_DEBUG"))
+        fprintf(stderr, "veto gemm_tc2: co-resident 4-CTA clusters: to_qkv %d, ff1 %d, to_out / ff2 %d (of %d SMs)\n",
+                g_clusters4[EPI_OP_LN][1], g_clusters4[EPI_GELU_OP_LN][0], g_clusters4[EPI_RESOP_OPS][0], num_sms());
     g_inited.done();
     return VETO_OK;
 }
@@ -667,14 +793,21 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     VETO_REQUIRE(!ep.drop.thr16 || ep.ldc % 4 == 0, VETO_ERR_ARG, "gemm_tc2: dropout needs ldc % 4 == 0");
     // the residual epilogues (to_out / FF2: N = 576) are built for 192-wide tiles only
     const int bn = (ep.residual || ep.res_op.hi || ep.stats_partials) ? 192 : tile_width(N, ksplit);
-    const int tiles = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + bn - 1) / bn) * ksplit;
-    const int pairs_avail = num_sms() / 2;
-    const int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
+    const int num_m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n_tiles = (N + bn - 1) / bn;
+    const int tiles = num_m_tiles * num_n_tiles * ksplit;
+    static int pair_cap = -1;   // VETO_GEMM_PAIRS=n: diagnosis, run the persistent loop on n CTA pairs only
+    if (pair_cap < 0) {
+        const char* e = getenv("VETO_GEMM_PAIRS");
+        pair_cap = e ? atoi(e) : 0;
+    }
+    int pairs_avail = num_sms() / 2;
+    if (pair_cap > 0 && pair_cap < pairs_avail) pairs_avail = pair_cap;
+    int grid = 2 * (tiles < pairs_avail ? tiles : pairs_avail);
     const float acc_scale = (passes == TC_F16C8 || passes == TC_F16) ? kC8AccScale : 1.f;
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
                 ep.pre_f32, ep.res_mode, ep.drop, ep.res_op.hi, ep.res_op.lo, ep.res_op.fmt, ep.ln_stats, ep.ln_c1,
                 ep.ln_row_stride > 0 ? ep.ln_row_stride : 1,
-                ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride};
+                ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride, W_BOX_ROWS};
     // the compile-time epilogues of the inference encoder; anything else (training options, tests) is EPI_GENERIC
     const bool plain = !ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ksplit == 1;
     const bool ln_in = ep.ln_stats != nullptr;
@@ -701,8 +834,42 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     static int force_generic = -1;   // VETO_GEMM_GENERIC_EPI=1: diagnosis, every launch through the run-time epilogue
     if (force_generic < 0) force_generic = getenv("VETO_GEMM_GENERIC_EPI") ? 1 : 0;
     if (force_generic && !ln_in && !ep.stats_partials && !ep.res_op.hi) epi = EPI_GENERIC;
+    // 4-CTA clusters (W multicast between two row tiles) for the big two-array launches of the inference encoder.
+    // Measured (profiles/r2_modes_cluster4_ab.jsonl): only 33 clusters of 4 are co-resident on the 148 SMs (132 SMs), the
+    // step is 1.5 - 2 % SLOWER (to_qkv 89.7 -> 93.2 ms) although every SM does 7 - 8 % more work per unit time: a quarter
+    // less L2 -> SM traffic buys little, the kernels are bound inside the SM (shared-memory pipe: TMA fill + UMMA operand
+    // reads + epilogue staging, 58 % busy in profiles/r2_gemm_f16c8_ncu.txt), not by the L2.  Opt-in:
+    // VETO_GEMM_CLUSTER4=1 (=2: also for small M, which is how the parity tests exercise the path).
+    static int allow4 = -1;
+    if (allow4 < 0) {
+        const char* e = getenv("VETO_GEMM_CLUSTER4");
+        allow4 = !e ? 0 : (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0));
+    }
+    const bool has4 = (bn == 256 && (epi == EPI_OP || epi == EPI_OP_LN)) ||
+                      (bn == 192 && (epi == EPI_GELU_OP || epi == EPI_GELU_OP_LN || epi == EPI_RES_OPS || epi == EPI_RESOP_OPS));
+    const int clusters4 = has4 ? g_clusters4[epi][bn == 256] : 0;
+    if (allow4 && two_arrays && has4 && pair_cap <= 0 && clusters4 >= 16 && (allow4 == 2 || num_m_tiles >= 4 * clusters4)) {
+        p.w_box = 16;
+        if ((rc = get_map(W.hi, N, K, ldw, 16, &tw_hi))) return rc;
+        if ((rc = get_map(W.lo, N, K, ldw, 16, &tw_lo))) return rc;
+        const int units = ((num_m_tiles + 1) / 2) * num_n_tiles;
+        grid = 4 * (units < clusters4 ? units : clusters4);
+#define VETO_TC2_LAUNCH4(E, B) \
+    gemm_tc2_kernel<E, B, 4><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+        switch (epi) {
+            case EPI_OP: VETO_TC2_LAUNCH4(EPI_OP, 256); break;
+            case EPI_OP_LN: VETO_TC2_LAUNCH4(EPI_OP_LN, 256); break;
+            case EPI_GELU_OP: VETO_TC2_LAUNCH4(EPI_GELU_OP, 192); break;
+            case EPI_GELU_OP_LN: VETO_TC2_LAUNCH4(EPI_GELU_OP_LN, 192); break;
+            case EPI_RES_OPS: VETO_TC2_LAUNCH4(EPI_RES_OPS, 192); break;
+            default: VETO_TC2_LAUNCH4(EPI_RESOP_OPS, 192); break;
+        }
+#undef VETO_TC2_LAUNCH4
+        VETO_LAUNCH_CHECK();
+        return VETO_OK;
+    }
 #define VETO_TC2_LAUNCH(E, B) \
-    gemm_tc2_kernel<E, B><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    gemm_tc2_kernel<E, B, 2><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
     if (bn == 256) {
         switch (epi) {
             case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 256); break;

@@ -83,6 +83,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* t
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same, delivered to every CTA of `mask` (cluster ranks) at this shared-memory offset; each destination's completion
+// bytes go to the barrier at this offset in the leader of ITS pair (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -164,6 +173,12 @@ __device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// arrive (once all MMAs issued so far have retired) on the barrier at this offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void umma2_commit_mask(uint64_t* bar, uint32_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)mask)
+                 : "memory");
 }
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
