@@ -292,16 +292,11 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
         const int M = (int)(rc_pairs * kTokens);
         ActBuf xn = enc_act_at(B, W.xn, prec, (size_t)M * kDim);
         ActBuf hb = enc_act_at(B, W.h, prec, (size_t)M * kMlp);
-        set_tag(TAG_TOKENS);
-        if ((rc = build_tokens(ts, in->subj + r0, in->obj + r0, rc_pairs, x, s))) return rc;
-        if (out->tokens)
-            VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
-                                      cudaMemcpyDeviceToDevice, s));
         const int R = (int)rc_pairs;
         // LayerNorm fusion (tensor-core modes): the epilogues that produce x (to_out, FF2) also write it in operand format
         // with its row statistics, and the next Linear (FF1, the next layer's to_qkv) runs on those raw rows with the
         // LayerNorm weight folded into its weight (gemm_tc2.cu EPI_*_LN) — the LayerNorm pass over x and its normalised
-        // copy never exist.  Layer 0's first LayerNorm (x comes from the token kernel) keeps the kernel.
+        // copy never exist.  The token kernel emits its rows the same way, so layer 0 is no exception.
         // Only in the modes that carry ~16 bits per operand (bf16x3, f16c8): on raw rows the products are rounded relative
         // to |x|, not |x - mean|, and the single-product modes (bf16, f16) have no headroom for that next to their tolerance.
         const bool fuse_ln = ln_fusion_enabled() && prec_two_arrays(prec);
@@ -330,6 +325,14 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             x_ops_ready = true;
             return ln_stats_finalize(ln_parts, kDim / 64, M, ln_stats, s);
         };
+        // the fp32 rows of the fresh tokens are only needed without the fusion, for the fp32 residual stream, or on request
+        const bool tok_f32 = !fuse_ln || !resop_enabled() || out->tokens != nullptr;
+        set_tag(TAG_TOKENS);
+        if ((rc = build_tokens(ts, in->subj + r0, in->obj + r0, rc_pairs, tok_f32 ? x : nullptr, xo.out(), ln_parts, s))) return rc;
+        if (out->tokens)
+            VETO_CUDA(cudaMemcpyAsync(out->tokens + (size_t)r0 * kTokens * kDim, x, sizeof(float) * (size_t)M * kDim,
+                                      cudaMemcpyDeviceToDevice, s));
+        if ((rc = finish_x())) return rc;
         for (int l = 0; l + 1 < cfg->layers; ++l) {
             // x = to_out(softmax(q k^T * scale) v) + x      (PreNorm + Attention, model_veto.py:18-19,86-96)
             GemmEpilogue e1;

@@ -48,8 +48,10 @@ struct TokenSources {
     const float* clspos;  // [576] cls_token + pos_embedding
     const float* pos;     // [576] pos_embedding
 };
-int build_tokens(const TokenSources& src, const int32_t* subj, const int32_t* obj, int64_t n_pairs, float* x,
-                 cudaStream_t s);
+// x (fp32, may be NULL when xo is given) and / or xo: the rows in operand format + their LayerNorm statistics partials
+// [kDim / 64][n_pairs * 19] for ln_stats_finalize
+int build_tokens(const TokenSources& src, const int32_t* subj, const int32_t* obj, int64_t n_pairs, float* x, ActOut xo,
+                 float2* stats_partials, cudaStream_t s);
 int add_freq_bias(float* logits, int num_out, const float* table, const int64_t* labels, int num_obj,
                   const int32_t* subj, const int32_t* obj, int64_t n_pairs, cudaStream_t s);
 

@@ -19,40 +19,77 @@ __device__ __forceinline__ float4 relu4(float4 a) {
 }
 
 constexpr int kTokThreads = kDim / 4;  // 144
+constexpr int kStatParts = kDim / 64;  // 9 partial (sum, sum of squares) per row, as the gemm_tc2 epilogues emit them
 
+// OPS: the rows also go out in operand format (bf16 hi + lo or f16c8) with their LayerNorm statistics partials, so that
+// layer 0's to_qkv runs LayerNorm-fused on them like every later Linear (api.cu) — the LayerNorm pass over the fresh
+// tokens and, with the residual stream in operand format, their fp32 copy disappear.  x may then be NULL.
+template <bool OPS>
 __global__ void __launch_bounds__(kTokThreads)
 tokens_kernel(TokenSources src, const int32_t* __restrict__ subj, const int32_t* __restrict__ obj, int64_t n_pairs,
-              float* __restrict__ x) {
+              float* __restrict__ x, ActOut xo, float2* __restrict__ parts) {
+    __shared__ float2 sq[OPS ? kTokens * kTokThreads : 1];
     const int t = threadIdx.x;
     const float4 pos = __ldg((const float4*)src.pos + t);
     const float4 clspos = __ldg((const float4*)src.clspos + t);
     const bool depth_part = t < kDimDepth / 4;
+    const int64_t M = n_pairs * kTokens;
     for (int64_t r = blockIdx.x; r < n_pairs; r += gridDim.x) {
         const int s = subj[r], o = obj[r];
-        float4* xr = (float4*)(x + (size_t)r * kTokens * kDim) + t;
-        xr[0] = clspos;
+        float4* xr = x ? (float4*)(x + (size_t)r * kTokens * kDim) + t : nullptr;
+        auto emit = [&](int row, float4 v) {
+            if (xr) xr[(size_t)row * kTokThreads] = v;
+            if constexpr (OPS) {
+                const size_t off = ((size_t)r * kTokens + row) * kDim + 4 * t;
+                if (xo.fmt == FMT_F16C8) {
+                    store_act4_f16c8(xo.hi, xo.lo, off, v);
+                } else {
+                    uint2 hh, ll;
+                    split_pair(v.x, v.y, hh.x, ll.x);
+                    split_pair(v.z, v.w, hh.y, ll.y);
+                    *(uint2*)(xo.hi + off) = hh;
+                    *(uint2*)(xo.lo + off) = ll;
+                }
+                sq[row * kTokThreads + t] = make_float2((v.x + v.y) + (v.z + v.w), (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+            }
+        };
+        emit(0, clspos);
         if (depth_part) {
             const float4* ps = (const float4*)(src.so_d + (size_t)s * kPatches * 2 * kDimDepth) + t;
             const float4* po = (const float4*)(src.so_d + (size_t)o * kPatches * 2 * kDimDepth + kDimDepth) + t;
 #pragma unroll 4
             for (int p = 0; p < kPatches; ++p)
-                xr[(size_t)(1 + p) * kTokThreads] =
-                    add4(add4(__ldg(ps + (size_t)p * (2 * kDimDepth / 4)), __ldg(po + (size_t)p * (2 * kDimDepth / 4))), pos);
+                emit(1 + p, add4(add4(__ldg(ps + (size_t)p * (2 * kDimDepth / 4)), __ldg(po + (size_t)p * (2 * kDimDepth / 4))), pos));
         } else {
             const int tv = t - kDimDepth / 4;
             const float4* ps = (const float4*)(src.so_v + (size_t)s * kPatches * 2 * kDimRgb) + tv;
             const float4* po = (const float4*)(src.so_v + (size_t)o * kPatches * 2 * kDimRgb + kDimRgb) + tv;
 #pragma unroll 4
             for (int p = 0; p < kPatches; ++p)
-                xr[(size_t)(1 + p) * kTokThreads] =
-                    add4(add4(__ldg(ps + (size_t)p * (2 * kDimRgb / 4)), __ldg(po + (size_t)p * (2 * kDimRgb / 4))), pos);
+                emit(1 + p, add4(add4(__ldg(ps + (size_t)p * (2 * kDimRgb / 4)), __ldg(po + (size_t)p * (2 * kDimRgb / 4))), pos));
         }
         const float4 ls = __ldg((const float4*)(src.lso + (size_t)s * 2 * kDim) + t);
         const float4 lo = __ldg((const float4*)(src.lso + (size_t)o * 2 * kDim + kDim) + t);
-        xr[(size_t)17 * kTokThreads] = add4(relu4(add4(ls, lo)), pos);
+        emit(17, add4(relu4(add4(ls, lo)), pos));
         const float4 cs = __ldg((const float4*)(src.cso + (size_t)s * 2 * kDim) + t);
         const float4 co = __ldg((const float4*)(src.cso + (size_t)o * 2 * kDim + kDim) + t);
-        xr[(size_t)18 * kTokThreads] = add4(relu4(add4(cs, co)), pos);
+        emit(18, add4(relu4(add4(cs, co)), pos));
+        if constexpr (OPS) {
+            // 19 rows x 9 partials, each the sum over 16 threads' (= 64 columns') contributions
+            __syncthreads();
+            for (int e = t; e < kTokens * kStatParts; e += kTokThreads) {
+                const int row = e / kStatParts, part = e - row * kStatParts;
+                const float2* q = sq + row * kTokThreads + part * 16;
+                float sv = 0.f, qv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    sv += q[i].x;
+                    qv += q[i].y;
+                }
+                parts[(size_t)part * M + (size_t)r * kTokens + row] = make_float2(sv, qv);
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -72,12 +109,18 @@ __global__ void freq_bias_kernel(float* __restrict__ logits, int num_out, const 
 
 }  // namespace
 
-int build_tokens(const TokenSources& src, const int32_t* subj, const int32_t* obj, int64_t n_pairs, float* x,
-                 cudaStream_t s) {
+int build_tokens(const TokenSources& src, const int32_t* subj, const int32_t* obj, int64_t n_pairs, float* x, ActOut xo,
+                 float2* stats_partials, cudaStream_t s) {
     if (n_pairs <= 0) return VETO_OK;
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid = (int)(n_pairs < cap ? n_pairs : cap);
-    tokens_kernel<<<grid, kTokThreads, 0, s>>>(src, subj, obj, n_pairs, x);
+    if (xo.hi) {
+        VETO_REQUIRE(xo.lo && stats_partials, VETO_ERR_ARG, "build_tokens: operand-format rows need both arrays and the statistics buffer");
+        tokens_kernel<true><<<grid, kTokThreads, 0, s>>>(src, subj, obj, n_pairs, x, xo, stats_partials);
+    } else {
+        VETO_REQUIRE(x != nullptr, VETO_ERR_ARG, "build_tokens: no output");
+        tokens_kernel<false><<<grid, kTokThreads, 0, s>>>(src, subj, obj, n_pairs, x, xo, nullptr);
+    }
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -336,7 +336,7 @@ extern "C" int veto_relation_train_step(const veto_config* cfg, const veto_weigh
     {
         TokenSources ts{so_d, so_v, lso, cso, (const float*)(P + L.clspos), w->pos_embedding};
         set_tag(TAG_TOKENS);
-        RC(build_tokens(ts, in->subj, in->obj, R, x_in[0], s));
+        RC(build_tokens(ts, in->subj, in->obj, R, x_in[0], ActOut(), nullptr, s));
         RC(dropout_inplace(x_in[0], (size_t)M * kDim, drop_emb, s));  // Transformer.pos_drop (model_veto.py:63)
     }
     for (int l = 0; l < NL; ++l) {
