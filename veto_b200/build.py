@@ -51,7 +51,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # VETO_NVCC_DEFINES: extra -D switches for compile-time experiments (e.g. -DVETO_TC2_RES_STAGES=2)
+        cmd = [nvcc] + ARCH + COMMON + EXTRA.get(src, []) + os.environ.get("VETO_NVCC_DEFINES", "").split() + \
+            ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -100,6 +100,16 @@ bool resop_enabled() {
     return on != 0;
 }
 
+// VETO_LN_STATS_EPILOGUE=1: (mean, rstd) of the LayerNorm-fused rows inside the consuming epilogues instead of by the
+// ln_stats_finalize launches (the same arithmetic, bit-identical results).  Measured SLOWER (profiles/
+// r2_modes_stats_epilogue_ab.jsonl): the 11 launches per chunk cost 3.1 ms per step, but the 36 extra loads per thread and
+// tile lengthen the to_qkv / FF1 epilogues by 7 and 10 ms — those epilogues are the critical path of their kernels.
+bool stats_in_epilogue() {
+    static int on = -1;
+    if (on < 0) on = getenv("VETO_LN_STATS_EPILOGUE") ? 1 : 0;
+    return on != 0;
+}
+
 // VETO_LN_FUSION=0 keeps the LayerNorm kernels everywhere (A/B measurements, diagnosis)
 bool ln_fusion_enabled() {
     static int on = -1;
@@ -319,11 +329,20 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
                 e.res_op = xo.out();
             }
         };
+        auto set_ln_in = [&](GemmEpilogue& e) {
+            if (stats_in_epilogue()) {
+                e.ln_parts = ln_parts;
+                e.ln_parts_rows = M;
+            } else {
+                e.ln_stats = ln_stats;
+            }
+        };
         auto finish_x = [&]() -> int {
             if (!fuse_ln) return VETO_OK;
             set_tag(TAG_LN);
             x_ops_ready = true;
-            return ln_stats_finalize(ln_parts, kDim / 64, M, ln_stats, s);
+            if (!stats_in_epilogue()) return ln_stats_finalize(ln_parts, kDim / 64, M, ln_stats, s);
+            return VETO_OK;   // the consuming epilogues reduce the partials themselves
         };
         // the fp32 rows of the fresh tokens are only needed without the fusion, for the fp32 residual stream, or on request
         const bool tok_f32 = !fuse_ln || !resop_enabled() || out->tokens != nullptr;
@@ -352,7 +371,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             set_tag(TAG_QKV);
             if (x_ops_ready) {
                 const float* cq = (const float*)(P + L.c_qkv[l]);
-                e1.ln_stats = ln_stats;
+                set_ln_in(e1);
                 e1.ln_c1 = cq;
                 e1.bias = cq + 3 * kDim;
                 WRef wq{nullptr, bf(P, L.qkvf_hi[l]), bf(P, L.qkvf_lo[l])};
@@ -385,7 +404,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             e3.ldc = kMlp;
             if (fuse_ln) {
                 const float* cf = (const float*)(P + L.c_ff1[l]);
-                e3.ln_stats = ln_stats;
+                set_ln_in(e3);
                 e3.ln_c1 = cf;
                 e3.bias = cf + kMlp;
                 WRef w1{nullptr, bf(P, L.ff1f_hi[l]), bf(P, L.ff1f_lo[l])};
@@ -426,7 +445,8 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             eq.ldc = kDim;
             if (x_ops_ready) {   // LayerNorm fused (see above): K, V of every row, the query of the CLS rows (row stride 19)
                 const float* cq = (const float*)(P + L.c_qkv[l]);
-                e1.ln_stats = eq.ln_stats = ln_stats;
+                set_ln_in(e1);
+                set_ln_in(eq);
                 e1.ln_c1 = cq + kDim;
                 e1.bias = cq + 3 * kDim + kDim;
                 eq.ln_c1 = cq;

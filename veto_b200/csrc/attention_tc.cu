@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const float* __restrict__ qkv, int64_t n_seq, float* out_f32, __nv_bfloat16* out_hi,
                     __nv_bfloat16* out_lo) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every
+    // access through the result a GENERIC load / store (LD.E / ST.E instead of LDS / STS — the epilogue staging paid for it)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bar_s = (uint64_t*)(smem + OFF_BARS);
     uint64_t* bar_p = bar_s + 1;
     uint64_t* bar_o = bar_s + 2;

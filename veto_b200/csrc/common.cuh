@@ -282,6 +282,8 @@ struct GemmEpilogue {
     const float2* ln_stats = nullptr; // (mean, rstd) per A row: the GEMM runs on the RAW rows with gamma folded into W and
     int ln_row_stride = 1;            //   the epilogue applies rstd * (acc - mean * ln_c1[n]) + bias[n] (bias = c2);
     const float* ln_c1 = nullptr;     //   row r's statistics sit at ln_stats[r * ln_row_stride]
+    const float2* ln_parts = nullptr; // instead of ln_stats: the kDim / 64 partial (sum, sum of squares) planes the producing
+    long long ln_parts_rows = 0;      //   epilogue wrote (plane stride in rows); the epilogue reduces them itself
     float2* stats_partials = nullptr; // [N / 64][M] partial (sum, sum of squares) of the OUTPUT rows (ln_stats_finalize)
     ActOut res_op;                    // residual given in OPERAND format (hi / lo / fmt; row stride ldr) instead of `residual`
 };

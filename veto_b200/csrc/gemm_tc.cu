@@ -99,7 +99,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     using C = TileCfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every
+    // access through the result a GENERIC load / store (LD.E / ST.E instead of LDS / STS — the epilogue staging paid for it)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::kStages * C::kBytesA;
     // per-epilogue-warp transpose buffers behind the pipeline (CONV: kConvStages stages of [A_hi][A_lo][W_hi][W_lo])

@@ -38,12 +38,18 @@ constexpr int BLOCK_M = 128;      // rows per CTA (256 per pair)
 constexpr int W_BOX_ROWS = 32;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 12;  // three per TMEM lane quarter, interleaved over the 12 column chunks
-constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+// Epilogue warps: three or four per TMEM lane quarter, interleaved over the 16-column chunks of the tile.  The epilogues are
+// the critical path of the inference kernels (profiles/r2_modes_epilogue_diag.jsonl: with the epilogue switched off the
+// mainloops run at the tensor peak), and each warp walks its chunks as one dependent chain — so the epilogues without a
+// residual or GELU (64 - 80 registers: to_qkv) run 16 warps (16 chunks of a 256-wide tile: 4 per warp instead of 6 / 5 / 5,
+// to_qkv 90 -> 86 ms per step); the residual ones need up to 128 registers per thread and stay at 12 warps (512 threads).
+constexpr int MAX_EPI_WARPS = 16;
+__host__ __device__ constexpr int epi_warps(int epi);   // defined after the EPI_* enum
+__host__ __device__ constexpr int num_threads(int ew) { return (4 + ew) * 32; }
 constexpr int EPI_COLS = 16;
 constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;
 constexpr int BYTES_A = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+__host__ __device__ constexpr int epi_bytes(int ew) { return ew * EPI_STAGE_BYTES; }
 constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 template <int BN>
@@ -51,9 +57,13 @@ struct TileN {
     static constexpr int kHalf = BN / 2;                         // W rows per CTA of a full-width tile
     static constexpr int kBytesB = kHalf * BLOCK_K * 2;          // 12 KB / 16 KB
     // 3 stages of two-array operands (56 KB / 64 KB each) or 6 stages of single-array operands
-    static constexpr int kPipe = 3 * 2 * (BYTES_A + kBytesB);
-    static constexpr int kSmem = kPipe + EPI_BYTES + 1024 + 256;
-    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+    static constexpr int kStageBytes = 2 * (BYTES_A + kBytesB);
+    __host__ __device__ static constexpr int pipe(int stages) { return stages * kStageBytes; }
+    static constexpr int kPipe = pipe(3);
+    // dynamic shared memory of an instance with ew epilogue warps (no more than needed: what is left of the 256 KB is L1,
+    // and the residual epilogues re-read their 128-byte lines from it chunk after chunk)
+    __host__ __device__ static constexpr int smem(int ew, int stages) { return pipe(stages) + epi_bytes(ew) + 1024 + 256; }
+    static_assert(kPipe + epi_bytes(MAX_EPI_WARPS) + 1024 + 256 <= 227 * 1024, "shared memory budget");
     static_assert(2 * BN <= TMEM_COLS, "two accumulator buffers");
 };
 
@@ -82,12 +92,15 @@ struct EpiParams {
     const float2* ln_stats;  // fused LayerNorm on the A operand: (mean, rstd) of row r at ln_stats[r * ln_row_stride]
     const float* ln_c1;      //   and c1[n] = sum_k gamma_k W[n,k]; `bias` then holds c2[n] = sum_k beta_k W[n,k] (+ bias)
     int ln_row_stride;
+    const float2* ln_parts;  // alternatively the 9 partial (sum, sum of squares) planes of the rows, reduced here (no finalize launch)
+    long long ln_parts_rows;
     float2* stats_partials;  // row statistics of the OUTPUT: partial (sum, sum of squares) [N / 64][M] for ln_stats_finalize
     int out_fmt;             // FMT_BF16 / FMT_F16C8: storage format of out_hi / out_lo
     float acc_scale;         // accumulator scale (f16c8 / f16: 2^-11, the weights are stored times 2048)
     int ksplit;              // K slices (wgrad: tiny output, huge K); tiles enumerate (slice, m, n)
     int kb_per;              // K blocks per slice
     long long split_stride;  // elements between the partial outputs of consecutive slices
+    int diag;                // VETO_GEMM_DIAG (measurement only, results invalid): 1 = the epilogue handles one chunk per warp and tile
     int w_box;               // rows per TMA box of W (32; 16 for the 4-CTA clusters: a quarter of a 192-wide tile is 48 rows)
 };
 
@@ -110,6 +123,12 @@ struct EpiParams {
 //   EPI_RESOP_F32  the same residual source, fp32 result (the CLS rows of the last layer)
 enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_RESOP_OPS,
        EPI_RESOP_F32, EPI_COUNT };
+__host__ __device__ constexpr int epi_warps(int epi) {
+    // to_qkv only (256-wide tiles: 225 KB of shared memory either way).  FF1's 192-wide tiles would cross from 193 KB to 201
+    // KB, i.e. into the next shared-memory configuration of the SM (60 -> 28 KB of L1), which costs it more than the fourth
+    // warp per lane quarter gains: 70.5 -> 72.3 ms per step.
+    return (epi == EPI_F32 || epi == EPI_F32_LN || epi == EPI_OP || epi == EPI_OP_LN) ? 16 : 12;
+}
 
 // four consecutive residual values from the operand format (flat element offset off, off % 4 == 0)
 __device__ __forceinline__ float4 load_res_operand(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int fmt, size_t off) {
@@ -164,17 +183,24 @@ __device__ __forceinline__ float4 decode_res_f16c8(const RawRes& r) {
 // tile — every CTA fetches half of its pair-half of W and multicasts it to the CTA of the same rank parity in the other
 // pair, so the W bytes cross L2 -> SM once per two row tiles.  The encoder GEMMs run at the L2 throughput cap (~6000 B /
 // SM cycle over the chip), not at the tensor-pipe or HBM limit.
-template <int EPI, int BN, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// ST = pipeline stages of two-array operands: 3; 2 for the residual epilogues on K = 576 (to_out) — their kernels are short
+// on L1 (what the 256 KB of an SM do not hold as shared memory serves the residual reads): to_out 43.6 -> 40.9 ms per step
+// with 137 KB instead of 193 KB of shared memory, while FF2 (K = 1152) needs the third stage (60 -> 74 ms without it).
+template <int EPI, int BN, int CL, int ST = 3>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(num_threads(epi_warps(EPI)), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 int M, int N, int K, int passes, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every
+    // access through the result a GENERIC load / store (LD.E / ST.E instead of LDS / STS — the epilogue staging paid for it)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     using TN = TileN<BN>;
+    constexpr int NUM_EPI_WARPS = epi_warps(EPI);
     constexpr int BYTES_B = TN::kBytesB;
-    uint8_t* smem_epi = smem + TN::kPipe;
-    uint64_t* bars = (uint64_t*)(smem_epi + EPI_BYTES);
+    constexpr int kPipeBytes = TN::pipe(ST);
+    uint8_t* smem_epi = smem + kPipeBytes;
+    uint64_t* bars = (uint64_t*)(smem_epi + epi_bytes(NUM_EPI_WARPS));
     uint64_t* full_bar = bars;                   // [MAX_STAGES]
     uint64_t* empty_bar = bars + MAX_STAGES;     // [MAX_STAGES]
     uint64_t* tmem_full = bars + 2 * MAX_STAGES; // [2]
@@ -191,7 +217,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
     const bool split = passes == TC_BF16X3 || passes == TC_F16C8;   // a stage holds hi and lo tiles of both operands
     const int stage_bytes = split ? 2 * (BYTES_A + BYTES_B) : (BYTES_A + BYTES_B);
-    const int num_stages = TN::kPipe / stage_bytes;  // 3 or 6
+    const int num_stages = kPipeBytes / stage_bytes;  // 3 (2) stages of two-array operands or 6 (4) of single-array ones
     const int num_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     const int num_n = (N + BN - 1) / BN;
     const int mn_tiles = num_m * num_n;
@@ -381,7 +407,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int row = m0 + rr * 8 + rsub;
-                        st[rr] = row < M ? __ldg(ep.ln_stats + (size_t)row * ep.ln_row_stride) : make_float2(0.f, 0.f);
+                        st[rr] = make_float2(0.f, 0.f);
+                        if (row < M) {
+                            if (ep.ln_parts) {   // ln_stats_finalize_kernel's arithmetic, in its order
+                                const float2* pp = ep.ln_parts + (size_t)row * ep.ln_row_stride;
+                                float sv = 0.f, qv = 0.f;
+#pragma unroll
+                                for (int part = 0; part < kDim / 64; ++part) {
+                                    const float2 v = __ldg(pp + (size_t)part * ep.ln_parts_rows);
+                                    sv += v.x;
+                                    qv += v.y;
+                                }
+                                const float mean = sv * (1.f / kDim);
+                                const float var = fmaxf(qv * (1.f / kDim) - mean * mean, 0.f);
+                                st[rr] = make_float2(mean, 1.f / sqrtf(var + 1e-5f));
+                            } else {
+                                st[rr] = __ldg(ep.ln_stats + (size_t)row * ep.ln_row_stride);
+                            }
+                        }
                     }
                 }
                 RawRes raw_a[4], raw_b[4];
@@ -427,9 +470,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 auto chunk_body = [&](int c) {
+                    if (ep.diag == 4) return;
                     uint32_t r[16];
                     tmem_ld16(taddr + c * EPI_COLS, r);
                     tmem_ld_wait();
+                    if (ep.diag == 3 && r[0] != 0x12345678u) return;
                     const int sw = (lane >> 1) & 3;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -463,8 +508,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                                 v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
                             }
                             const size_t off = (size_t)row * ep.ldc + col;
-                            if constexpr (kOutF32) *(float4*)(ep.out_f32 + off) = v;
-                            if constexpr (kOutOp) {
+                            const bool st_ok = ep.diag != 2 || v.x == 1.2345678e-30f;
+                            if constexpr (kOutF32) if (st_ok) *(float4*)(ep.out_f32 + off) = v;
+                            if constexpr (kOutOp) if (st_ok) {
                                 if (ep.out_fmt == FMT_F16C8) {
                                     store_act4_f16c8(ep.out_hi, ep.out_lo, off, v);
                                 } else {
@@ -509,6 +555,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             if (c + kStride < kChunks) load_res(c + kStride, res_next);
                         }
                         chunk_body(c);
+                        if (ep.diag == 1) break;
                     }
                 }
                 tc_fence_before();
@@ -681,10 +728,10 @@ int get_map(const __nv_bfloat16* p, uint64_t rows, uint64_t cols, uint64_t ld, u
 
 // co-resident 4-CTA clusters of a kernel (a GPC whose SM count is no multiple of 4 leaves SMs out): the persistent grid
 int g_clusters4[EPI_COUNT][2] = {};
-int max_clusters4(const void* fn, int smem) {
+int max_clusters4(const void* fn, int smem, int threads) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms() / 4 * 4);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
@@ -711,17 +758,21 @@ int init2() {
                  "cuTensorMapEncodeTiled not available from the driver");
     g_encode = (EncodeTiledFn)fn;
 #define VETO_TC2_ATTR(E, B) \
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem))
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::smem(epi_warps(E), 3)))
     VETO_TC2_ATTR(EPI_GENERIC, 192); VETO_TC2_ATTR(EPI_F32, 192); VETO_TC2_ATTR(EPI_F32_LN, 192); VETO_TC2_ATTR(EPI_RES, 192);
     VETO_TC2_ATTR(EPI_RES_OPS, 192); VETO_TC2_ATTR(EPI_GELU_OP, 192); VETO_TC2_ATTR(EPI_GELU_OP_LN, 192); VETO_TC2_ATTR(EPI_OP, 192);
     VETO_TC2_ATTR(EPI_OP_LN, 192); VETO_TC2_ATTR(EPI_RESOP_OPS, 192); VETO_TC2_ATTR(EPI_RESOP_F32, 192);
     VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256); VETO_TC2_ATTR(EPI_GELU_OP, 256);
     VETO_TC2_ATTR(EPI_GELU_OP_LN, 256); VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
 #undef VETO_TC2_ATTR
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES_OPS, 192, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TileN<192>::smem(epi_warps(EPI_RES_OPS), 2)));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RESOP_OPS, 192, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TileN<192>::smem(epi_warps(EPI_RESOP_OPS), 2)));
     // the 4-CTA-cluster instances: the full-sequence launches of the inference encoder
 #define VETO_TC2_ATTR4(E, B)                                                                                              \
-    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::kSmem)); \
-    g_clusters4[E][B == 256] = max_clusters4((const void*)gemm_tc2_kernel<E, B, 4>, TileN<B>::kSmem)
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<B>::smem(epi_warps(E), 3))); \
+    g_clusters4[E][B == 256] = max_clusters4((const void*)gemm_tc2_kernel<E, B, 4>, TileN<B>::smem(epi_warps(E), 3), num_threads(epi_warps(E)))
     VETO_TC2_ATTR4(EPI_OP, 256); VETO_TC2_ATTR4(EPI_OP_LN, 256); VETO_TC2_ATTR4(EPI_GELU_OP, 192); VETO_TC2_ATTR4(EPI_GELU_OP_LN, 192);
     VETO_TC2_ATTR4(EPI_RES_OPS, 192); VETO_TC2_ATTR4(EPI_RESOP_OPS, 192);
 #undef VETO_TC2_ATTR4
@@ -747,6 +798,15 @@ static int tile_width(int N, int ksplit) {
     }
     const int rem = N % 256;
     return (allow && ksplit == 1 && N >= 1728 && (rem == 0 || (rem >= 128 && rem % 64 == 0))) ? 256 : 192;
+}
+
+static int diag_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VETO_GEMM_DIAG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
 }
 
 // number of K slices a split-K request really produces (every slice non-empty)
@@ -806,11 +866,12 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     const float acc_scale = (passes == TC_F16C8 || passes == TC_F16) ? kC8AccScale : 1.f;
     EpiParams p{ep.bias, ep.residual, ep.out.f32, ep.out.hi, ep.out.lo, ep.act, ep.ldc, ep.ldr ? ep.ldr : ep.ldc,
                 ep.pre_f32, ep.res_mode, ep.drop, ep.res_op.hi, ep.res_op.lo, ep.res_op.fmt, ep.ln_stats, ep.ln_c1,
-                ep.ln_row_stride > 0 ? ep.ln_row_stride : 1,
-                ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride, W_BOX_ROWS};
+                ep.ln_row_stride > 0 ? ep.ln_row_stride : 1, ep.ln_parts, ep.ln_parts_rows,
+                ep.stats_partials, ep.out.fmt, acc_scale, ksplit, kb_per, (long long)ep.split_stride, diag_mode(), W_BOX_ROWS};
     // the compile-time epilogues of the inference encoder; anything else (training options, tests) is EPI_GENERIC
     const bool plain = !ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ksplit == 1;
-    const bool ln_in = ep.ln_stats != nullptr;
+    const bool ln_in = ep.ln_stats != nullptr || ep.ln_parts != nullptr;
+    VETO_REQUIRE(!ep.ln_parts || (K == kDim && ep.ln_parts_rows > 0), VETO_ERR_ARG, "gemm_tc2: statistics partials are per 64 of 576 columns");
     VETO_REQUIRE(!ln_in || (ep.ln_c1 && ep.bias), VETO_ERR_ARG, "gemm_tc2: fused LayerNorm needs ln_c1 and the c2 vector as bias");
     int epi = EPI_GENERIC;
     if (plain && ep.act == ACT_NONE && ep.res_op.hi && !ep.residual && ep.bias && !ln_in) {
@@ -855,7 +916,7 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
         const int units = ((num_m_tiles + 1) / 2) * num_n_tiles;
         grid = 4 * (units < clusters4 ? units : clusters4);
 #define VETO_TC2_LAUNCH4(E, B) \
-    gemm_tc2_kernel<E, B, 4><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    gemm_tc2_kernel<E, B, 4><<<grid, num_threads(epi_warps(E)), TileN<B>::smem(epi_warps(E), 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
         switch (epi) {
             case EPI_OP: VETO_TC2_LAUNCH4(EPI_OP, 256); break;
             case EPI_OP_LN: VETO_TC2_LAUNCH4(EPI_OP_LN, 256); break;
@@ -869,7 +930,8 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
         return VETO_OK;
     }
 #define VETO_TC2_LAUNCH(E, B) \
-    gemm_tc2_kernel<E, B, 2><<<grid, NUM_THREADS, TileN<B>::kSmem, s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    gemm_tc2_kernel<E, B, 2><<<grid, num_threads(epi_warps(E)), TileN<B>::smem(epi_warps(E), 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
+    const bool shallow = two_arrays && K <= 576;   // residual epilogues: two pipeline stages, the rest of the SM's memory as L1
     if (bn == 256) {
         switch (epi) {
             case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 256); break;
@@ -885,12 +947,18 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
             case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 192); break;
             case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN, 192); break;
             case EPI_RES: VETO_TC2_LAUNCH(EPI_RES, 192); break;
-            case EPI_RES_OPS: VETO_TC2_LAUNCH(EPI_RES_OPS, 192); break;
+            case EPI_RES_OPS:
+                if (shallow) gemm_tc2_kernel<EPI_RES_OPS, 192, 2, 2><<<grid, num_threads(epi_warps(EPI_RES_OPS)), TileN<192>::smem(epi_warps(EPI_RES_OPS), 2), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+                else VETO_TC2_LAUNCH(EPI_RES_OPS, 192);
+                break;
             case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP, 192); break;
             case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN, 192); break;
             case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 192); break;
             case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 192); break;
-            case EPI_RESOP_OPS: VETO_TC2_LAUNCH(EPI_RESOP_OPS, 192); break;
+            case EPI_RESOP_OPS:
+                if (shallow) gemm_tc2_kernel<EPI_RESOP_OPS, 192, 2, 2><<<grid, num_threads(epi_warps(EPI_RESOP_OPS)), TileN<192>::smem(epi_warps(EPI_RESOP_OPS), 2), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
+                else VETO_TC2_LAUNCH(EPI_RESOP_OPS, 192);
+                break;
             case EPI_RESOP_F32: VETO_TC2_LAUNCH(EPI_RESOP_F32, 192); break;
             default: VETO_TC2_LAUNCH(EPI_GENERIC, 192); break;
         }

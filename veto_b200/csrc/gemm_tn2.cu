@@ -89,7 +89,9 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 int Nw, int Kw, int rows, int passes, TnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every
+    // access through the result a GENERIC load / store (LD.E / ST.E instead of LDS / STS — the epilogue staging paid for it)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_epi = smem + PIPE_BYTES;
     uint64_t* bars = (uint64_t*)(smem_epi + EPI_BYTES);
     uint64_t* full_bar = bars;

@@ -36,10 +36,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive on the barrier at this offset in CTA `rank` of the cluster.  Used for "accumulator drained" signals: what must be
+// ordered before the arrive are this warp's tcgen05.ld reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync), not
+// its global stores — so the plain form (cutlass ClusterBarrier::arrive(cta_id)), NOT .release.cluster: that one compiles
+// to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR and parks the epilogue warp until every store of the tile has landed (17 % of
+// the warp-stall samples of the to_qkv kernel, profiles/r2_layer_f16c8_ncu.txt source page).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
