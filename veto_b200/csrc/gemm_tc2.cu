@@ -186,8 +186,8 @@ __device__ __forceinline__ float4 decode_res_f16c8(const RawRes& r) {
 // ST = pipeline stages of two-array operands: 3; 2 for the residual epilogues on K = 576 (to_out) — their kernels are short
 // on L1 (what the 256 KB of an SM do not hold as shared memory serves the residual reads): to_out 43.6 -> 40.9 ms per step
 // with 137 KB instead of 193 KB of shared memory, while FF2 (K = 1152) needs the third stage (60 -> 74 ms without it).
-template <int EPI, int BN, int CL, int ST = 3>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(num_threads(epi_warps(EPI)), 1)
+template <int EPI, int BN, int CL, int ST = 3, int EW = epi_warps(EPI)>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(num_threads(EW), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 int M, int N, int K, int passes, EpiParams ep) {
@@ -196,7 +196,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // access through the result a GENERIC load / store (LD.E / ST.E instead of LDS / STS — the epilogue staging paid for it)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     using TN = TileN<BN>;
-    constexpr int NUM_EPI_WARPS = epi_warps(EPI);
+    constexpr int NUM_EPI_WARPS = EW;
     constexpr int BYTES_B = TN::kBytesB;
     constexpr int kPipeBytes = TN::pipe(ST);
     uint8_t* smem_epi = smem + kPipeBytes;
