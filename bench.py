@@ -309,12 +309,34 @@ def run_reference(args):
         line["sweep96"] = {"value": (n_p + n_s) / total_s, "unit": UNIT, "config": {"workload": SWEEP_WORKLOAD},
                            "sample": "per-image times summed: 48 x (" + psample + ") + 48 x (headline sample)"}
     line["wall_s"] = time.perf_counter() - t0
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout
+    when NCCL_DEBUG is set in the environment), so keep a private handle on the real stdout for the line and point
+    file descriptor 1 at stderr for everything else."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _OUT
+
+
+_OUT = None
+
+
+def emit(line):
+    out = _json_only_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
+    _json_only_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -807,7 +829,7 @@ def main():
             "cpu_baseline": headline["cpu_baseline"],
             "train": train_leg, "meet_gqa": meet_leg, "sweep96": sweep_leg,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
