@@ -127,9 +127,10 @@ struct EpiParams {
 enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_RESOP_OPS,
        EPI_RESOP_F32, EPI_COUNT };
 __host__ __device__ constexpr int epi_warps(int epi) {
-    // to_qkv only (256-wide tiles: 225 KB of shared memory either way).  FF1's 192-wide tiles would cross from 193 KB to 201
-    // KB, i.e. into the next shared-memory configuration of the SM (60 -> 28 KB of L1), which costs it more than the fourth
-    // warp per lane quarter gains: 70.5 -> 72.3 ms per step.
+    // to_qkv (256-wide tiles: 225 KB of shared memory either way).  The GELU epilogues run 16 warps on their 256-wide
+    // instances only (explicit EW argument at the launch): on 192-wide tiles 16 warps cross from 193 KB to 201 KB, i.e. into
+    // the next shared-memory configuration of the SM (60 -> 28 KB of L1), which cost FF1 more than the fourth warp per lane
+    // quarter gained (70.5 -> 72.3 ms per step).
     return (epi == EPI_F32 || epi == EPI_F32_LN || epi == EPI_OP || epi == EPI_OP_LN) ? 16 : 12;
 }
 
@@ -551,8 +552,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     // output format fixed at compile time: a per-row `row < M` branch makes every row its own basic block
                     // (shared-memory load -> arithmetic -> conversion -> stores as one exposed chain, four times per chunk).
                     // to_qkv 89.4 -> 86.8 ms per step; NOT for the GELU epilogue (four interleaved GELUs cost FF1 registers
-                    // and 3 ms: 70.9 -> 74.0), which keeps the row-by-row form.
-                    if (rows_full && !kGelu) {
+                    // and 3 ms: 70.9 -> 74.0) nor the residual ones (f16c8: no change; bf16x3: to_out 54 -> 64 ms), which keep
+                    // the row-by-row form.
+                    if (rows_full && !kGelu && !kResid) {
                         if (fmt_c8) chunk_rows(c, std::false_type(), std::true_type());
                         else chunk_rows(c, std::false_type(), std::false_type());
                     } else {
@@ -796,8 +798,10 @@ int init2() {
     VETO_TC2_ATTR(EPI_GENERIC, 192); VETO_TC2_ATTR(EPI_F32, 192); VETO_TC2_ATTR(EPI_F32_LN, 192); VETO_TC2_ATTR(EPI_RES, 192);
     VETO_TC2_ATTR(EPI_RES_OPS, 192); VETO_TC2_ATTR(EPI_GELU_OP, 192); VETO_TC2_ATTR(EPI_GELU_OP_LN, 192); VETO_TC2_ATTR(EPI_OP, 192);
     VETO_TC2_ATTR(EPI_OP_LN, 192); VETO_TC2_ATTR(EPI_RESOP_OPS, 192); VETO_TC2_ATTR(EPI_RESOP_F32, 192);
-    VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256); VETO_TC2_ATTR(EPI_GELU_OP, 256);
-    VETO_TC2_ATTR(EPI_GELU_OP_LN, 256); VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
+    VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256);
+    VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP, 256, 2, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<256>::smem(16, 3)));
+    VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP_LN, 256, 2, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<256>::smem(16, 3)));
 #undef VETO_TC2_ATTR
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_RES_OPS, 192, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TileN<192>::smem(epi_warps(EPI_RES_OPS), 2)));
@@ -821,17 +825,18 @@ int init2() {
 
 bool gemm_tc2_supported(int N, int K) { return N % 192 == 0 && K % BLOCK_K == 0; }
 
-// 256-wide column tiles (+ one narrower last tile) where that saves A re-reads: to_qkv, 1728 = 6 x 256 + 192 (7 tiles instead
-// of 9: 92.3 -> 87.1 ms per inference step, profiles/r2_modes_bn256_ab.jsonl).  576 stays 3 x 192 (256 + 256 + 64 would be
-// three tiles as well); FF1 (1152 = 4 x 256 + 128) is bound by its epilogue, not by operand delivery, and measured no gain.
-static int tile_width(int N, int ksplit) {
+// 256-wide column tiles (+ one narrower last tile): to_qkv, 1728 = 6 x 256 + 192 (7 tiles instead of 9: 92.3 -> 87.1 ms per
+// inference step, profiles/r2_modes_bn256_ab.jsonl) and, with 16 epilogue warps, the inference FF1 (1152 = 4 x 256 + 128:
+// 72.3 -> 69.4 ms, profiles/r2_modes_ff1_bn256_ab.jsonl; with 12 warps — 6 / 5 / 5 chunks per warp — it had gained nothing).
+// 576 stays 3 x 192 (256 + 256 + 64 would be three tiles as well).
+static int tile_width(int N, int ksplit, bool gelu_op_epilogue) {
     static int allow = -1;
     if (allow < 0) {
         const char* e = getenv("VETO_GEMM_BN256");
         allow = (e && e[0] == '0') ? 0 : 1;
     }
     const int rem = N % 256;
-    return (allow && ksplit == 1 && N >= 1728 && (rem == 0 || (rem >= 128 && rem % 64 == 0))) ? 256 : 192;
+    return (allow && ksplit == 1 && N >= (gelu_op_epilogue ? 1152 : 1728) && (rem == 0 || (rem >= 128 && rem % 64 == 0))) ? 256 : 192;
 }
 
 static int diag_mode() {
@@ -842,6 +847,8 @@ static int diag_mode() {
     }
     return v;
 }
+
+static bool shallow_residual(int K, int passes) { return passes == TC_F16C8 && K <= 576; }
 
 // number of K slices a split-K request really produces (every slice non-empty)
 int gemm_tc2_slices(int K, int split_k) {
@@ -886,7 +893,9 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     VETO_REQUIRE(ep.res_mode == RES_ADD || ep.residual, VETO_ERR_ARG, "gemm_tc2: RES_GELU_GRAD needs the pre-activation");
     VETO_REQUIRE(!ep.drop.thr16 || ep.ldc % 4 == 0, VETO_ERR_ARG, "gemm_tc2: dropout needs ldc % 4 == 0");
     // the residual epilogues (to_out / FF2: N = 576) are built for 192-wide tiles only
-    const int bn = (ep.residual || ep.res_op.hi || ep.stats_partials) ? 192 : tile_width(N, ksplit);
+    const bool gelu_op = !ep.pre_f32 && ep.res_mode == RES_ADD && !ep.drop.thr16 && ksplit == 1 && ep.act == ACT_GELU &&
+                         !ep.residual && ep.bias && ep.out.hi && !ep.out.f32 && !ep.stats_partials;   // EPI_GELU_OP[_LN] below
+    const int bn = (ep.residual || ep.res_op.hi || ep.stats_partials) ? 192 : tile_width(N, ksplit, gelu_op);
     const int num_m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n_tiles = (N + bn - 1) / bn;
     const int tiles = num_m_tiles * num_n_tiles * ksplit;
     static int pair_cap = -1;   // VETO_GEMM_PAIRS=n: diagnosis, run the persistent loop on n CTA pairs only
@@ -965,13 +974,15 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     }
 #define VETO_TC2_LAUNCH(E, B) \
     gemm_tc2_kernel<E, B, 2><<<grid, num_threads(epi_warps(E)), TileN<B>::smem(epi_warps(E), 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p)
-    const bool shallow = two_arrays && K <= 576;   // residual epilogues: two pipeline stages, the rest of the SM's memory as L1
+    // residual epilogues on K <= 576 (to_out) in f16c8 mode: two pipeline stages, the rest of the SM's memory as L1 (16
+    // epilogue warps on top of that gained nothing; the bf16x3 products need the third stage)
+    const bool shallow = shallow_residual(K, passes);
     if (bn == 256) {
         switch (epi) {
             case EPI_F32: VETO_TC2_LAUNCH(EPI_F32, 256); break;
             case EPI_F32_LN: VETO_TC2_LAUNCH(EPI_F32_LN, 256); break;
-            case EPI_GELU_OP: VETO_TC2_LAUNCH(EPI_GELU_OP, 256); break;
-            case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN, 256); break;
+            case EPI_GELU_OP: gemm_tc2_kernel<EPI_GELU_OP, 256, 2, 3, 16><<<grid, num_threads(16), TileN<256>::smem(16, 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p); break;
+            case EPI_GELU_OP_LN: gemm_tc2_kernel<EPI_GELU_OP_LN, 256, 2, 3, 16><<<grid, num_threads(16), TileN<256>::smem(16, 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p); break;
             case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 256); break;
             case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 256); break;
             default: VETO_TC2_LAUNCH(EPI_GENERIC, 256); break;
