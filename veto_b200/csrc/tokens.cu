@@ -19,8 +19,7 @@ __device__ __forceinline__ float4 relu4(float4 a) {
 }
 
 constexpr int kTokThreads = kDim / 4;  // 144
-// the depth / rgb column split falls on a warp boundary: the 16-lane butterflies below run inside uniform branches
-static_assert((kDimDepth / 4) % 32 == 0 && kTokThreads == 144, "token kernel thread layout");
+constexpr int kStatParts = kDim / 64;  // 9 partial (sum, sum of squares) per row, as the gemm_tc2 epilogues emit them
 
 // OPS: the rows also go out in operand format (bf16 hi + lo or f16c8) with their LayerNorm statistics partials, so that
 // layer 0's to_qkv runs LayerNorm-fused on them like every later Linear (api.cu) — the LayerNorm pass over the fresh
@@ -29,12 +28,14 @@ template <bool OPS>
 __global__ void __launch_bounds__(kTokThreads)
 tokens_kernel(TokenSources src, const int32_t* __restrict__ subj, const int32_t* __restrict__ obj, int64_t n_pairs,
               float* __restrict__ x, ActOut xo, float2* __restrict__ parts) {
+    // per-thread (sum, sum of squares) of its four columns, reduced per 64 columns after the pair's rows are out: 4.5 ms per
+    // step; 16-lane butterflies per row (no shared memory, no block barriers) measured 5.6 ms
+    __shared__ float2 sq[OPS ? kTokens * kTokThreads : 1];
     const int t = threadIdx.x;
     const float4 pos = __ldg((const float4*)src.pos + t);
     const float4 clspos = __ldg((const float4*)src.clspos + t);
     const bool depth_part = t < kDimDepth / 4;
     const int64_t M = n_pairs * kTokens;
-    const unsigned lane_mask = t < 128 ? 0xffffffffu : 0x0000ffffu;
     for (int64_t r = blockIdx.x; r < n_pairs; r += gridDim.x) {
         const int s = subj[r], o = obj[r];
         float4* xr = x ? (float4*)(x + (size_t)r * kTokens * kDim) + t : nullptr;
@@ -51,14 +52,7 @@ tokens_kernel(TokenSources src, const int32_t* __restrict__ subj, const int32_t*
                     *(uint2*)(xo.hi + off) = hh;
                     *(uint2*)(xo.lo + off) = ll;
                 }
-                // one partial per 64 columns = 16 consecutive threads (half a warp; the fifth warp has 16 lanes): butterfly
-                float sv = (v.x + v.y) + (v.z + v.w), qv = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-#pragma unroll
-                for (int d = 8; d >= 1; d >>= 1) {
-                    sv += __shfl_xor_sync(lane_mask, sv, d);
-                    qv += __shfl_xor_sync(lane_mask, qv, d);
-                }
-                if ((t & 15) == 0) parts[(size_t)(t >> 4) * M + (size_t)r * kTokens + row] = make_float2(sv, qv);
+                sq[row * kTokThreads + t] = make_float2((v.x + v.y) + (v.z + v.w), (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
             }
         };
         emit(0, clspos);
@@ -82,6 +76,22 @@ tokens_kernel(TokenSources src, const int32_t* __restrict__ subj, const int32_t*
         const float4 cs = __ldg((const float4*)(src.cso + (size_t)s * 2 * kDim) + t);
         const float4 co = __ldg((const float4*)(src.cso + (size_t)o * 2 * kDim + kDim) + t);
         emit(18, add4(relu4(add4(cs, co)), pos));
+        if constexpr (OPS) {
+            // 19 rows x 9 partials, each the sum over 16 threads' (= 64 columns') contributions
+            __syncthreads();
+            for (int e = t; e < kTokens * kStatParts; e += kTokThreads) {
+                const int row = e / kStatParts, part = e - row * kStatParts;
+                const float2* q = sq + row * kTokThreads + part * 16;
+                float sv = 0.f, qv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    sv += q[i].x;
+                    qv += q[i].y;
+                }
+                parts[(size_t)part * M + (size_t)r * kTokens + row] = make_float2(sv, qv);
+            }
+            __syncthreads();
+        }
     }
 }
 
