@@ -1,9 +1,10 @@
 // Token-wise GEMM of the relation encoder, CTA-pair version (tcgen05 cta_group::2): the kernel the encoder layers
-// run on.  Same contract as gemm_tc.cu (C[M,N] = epilogue(A[M,K] @ W[N,K]^T), bf16 operands, fp32 TMEM accumulate,
-// passes = 1 or 3 for the bf16x3 split), different mapping:
+// run on.  Same contract as gemm_tc.cu (C[M,N] = epilogue(A[M,K] @ W[N,K]^T), fp32 TMEM accumulate; passes = TC_BF16 /
+// TC_BF16X3 / TC_F16C8 / TC_F16 of common.cuh: one bf16 product, the three-product bf16 split, the fp16 product + e4m3
+// corrections, one fp16 product), different mapping:
 //
-//   * a cluster of two CTAs (one SM pair) owns a 256 x 192 output tile; each CTA holds its own 128 rows of A and
-//     HALF of the W tile (96 rows) in shared memory, and one tcgen05.mma.cta_group::2 (M=256, N=192, K=16), issued
+//   * a cluster of two CTAs (one SM pair) owns a 256 x 192 (or 256 x 256) output tile; each CTA holds its own 128 rows of
+//     A and HALF of the W tile in shared memory, and one tcgen05.mma.cta_group::2 (M=256, N=192 / 256, K=16), issued
 //     by the leader CTA, feeds both tensor cores.  The single-CTA kernel is shared-memory-bandwidth bound (every
 //     operand byte is written once by TMA and read once per MMA: 2 x 40 KB per 384 tensor cycles > 128 B/clk,
 //     profiles/r1_v2_gemm_ncu.txt); the pair halves the W traffic per SM;
@@ -15,7 +16,9 @@
 //                         cleared, as SM100_TMA_2SM_LOAD does); the leader's producer arms it with 2 x stage bytes.
 //   empty[s]  (each CTA): tcgen05.commit.cta_group::2 ... multicast 0b11 — both producers see the slot freed.
 //   tfull[a]  (each CTA): the same multicast commit after the last K block: both epilogues may drain.
-//   tempty[a] (leader)  : 2 x 8 epilogue warps arrive (the peer's through mapa + remote mbarrier.arrive).
+//   tempty[a] (leader)  : 2 x EW epilogue warps arrive (mapa + plain remote mbarrier.arrive, tcgen05.cuh).
+// With CL = 4 (opt-in) two pairs share a cluster and the W tile: empty[s] then counts one commit per pair, multicast to all
+// four CTAs.  What bounds the kernels and what the template parameters <EPI, BN, CL, ST, EW> buy: DESIGN.md 4b.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -35,8 +38,8 @@ using namespace tc;
 constexpr int BLOCK_M = 128;      // rows per CTA (256 per pair)
 // Columns per pair tile: template parameter BN = 192 or 256 (each CTA stages BN / 2 rows of W).  192 divides every width of
 // the encoder (576, 1152, 1728); 256 (+ one narrower last tile: 1728 = 6 x 256 + 192, 1152 = 4 x 256 + 128) re-reads the A
-// tile 7 / 5 times instead of 9 / 6 — the kernel is bound by TMA operand delivery (L2 -> SM at ~10 TB/s,
-// profiles/r2_layer_f16c8_ncu.txt), not by the tensor pipe.  W travels in 32-row boxes so that one tensor map serves all widths.
+// tile 7 / 5 times instead of 9 / 6 and, with 16 epilogue warps, gives every warp 4 chunks instead of 6 / 5 / 5.  W travels in
+// 32-row boxes so that one tensor map serves all widths.
 constexpr int W_BOX_ROWS = 32;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
@@ -185,8 +188,7 @@ __device__ __forceinline__ float4 decode_res_f16c8(const RawRes& r) {
 
 // CL = CTAs per cluster.  2: one CTA pair.  4: two pairs on consecutive row tiles of the same column tile share the W
 // tile — every CTA fetches half of its pair-half of W and multicasts it to the CTA of the same rank parity in the other
-// pair, so the W bytes cross L2 -> SM once per two row tiles.  The encoder GEMMs run at the L2 throughput cap (~6000 B /
-// SM cycle over the chip), not at the tensor-pipe or HBM limit.
+// pair, so the W bytes cross L2 -> SM once per two row tiles (measured: no gain, the kernels are epilogue-bound; opt-in).
 // ST = pipeline stages of two-array operands: 3; 2 for the residual epilogues on K = 576 (to_out) — their kernels are short
 // on L1 (what the 256 KB of an SM do not hold as shared memory serves the residual reads): to_out 43.6 -> 40.9 ms per step
 // with 137 KB instead of 193 KB of shared memory, while FF2 (K = 1152) needs the third stage (60 -> 74 ms without it).
