@@ -74,17 +74,15 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
     const int st_slot = lane64 / 24, st_c4 = lane64 - st_slot * 24;         // output: row slot 0..1 (2 = idle), 4-column group 0..23
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
     const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
-    for (int64_t item = (int64_t)blockIdx.x * AS_PAIRS + pair; item < items; item += (int64_t)gridDim.x * AS_PAIRS) {
-        const int64_t seq = item / kHeads;
-        const int h = (int)(item - seq * kHeads);
-        const size_t gbase = (size_t)seq * kTokens * LD + h * kHeadDim;
-        // 6 arrays x 19 rows of 12 16-byte chunks: 60 of the pair's 64 lanes own (row slot, chunk) once and for all, so
-        // that every copy is two additions away from its addresses (the flat index -> (array, row, chunk) decode of the
-        // first version cost a quarter of the kernel's instructions)
+    // staging of arrays [a0, a1) of an item (0, 1 = q hi / lo; 2, 3 = k; 4, 5 = v): 6 arrays x 19 rows of 12 16-byte chunks,
+    // 60 of the pair's 64 lanes own (row slot, chunk) once and for all, so that every copy is two additions away from its
+    // addresses (the flat index -> (array, row, chunk) decode of the first version cost a quarter of the kernel's instructions)
+    auto stage = [&](int64_t it, int a0, int a1) {
+        const int64_t sq = it / kHeads;
+        const size_t gb = (size_t)sq * kTokens * LD + (int)(it - sq * kHeads) * kHeadDim;
         if (ld_slot < 5) {
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gbase + (a >> 1) * kDim + ld_chunk * 8;
+            for (int a = a0; a < a1; ++a) {
+                const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gb + (a >> 1) * kDim + ld_chunk * 8;
                 __nv_bfloat16* dst = arr + a * AS_ARR + ld_chunk * 8;
 #pragma unroll
                 for (int r0 = 0; r0 < 20; r0 += 5) {
@@ -96,6 +94,16 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t item_stride = (int64_t)gridDim.x * AS_PAIRS;
+    const int64_t first = (int64_t)blockIdx.x * AS_PAIRS + pair;
+    if (first < items) stage(first, 0, 6);
+    for (int64_t item = first; item < items; item += item_stride) {
+        const int64_t seq = item / kHeads;
+        const int h = (int)(item - seq * kHeads);
+        const int64_t next = item + item_stride;
+        // the NEXT item's K is fetched as soon as the scores exist, its V after P V, its Q once the output tile (which
+        // lives in the Q arrays) is stored: two thirds of an item's bytes arrive under the previous item's arithmetic
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         pair_bar();  // (1) staged operands visible to both warps
 
@@ -146,6 +154,7 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
                     if (row < kTokens && col < kTokens) myS[row * 20 + col] = S[mt][nt][e];
                 }
         pair_bar();  // (2) partial scores exchanged; Q and K are no longer read
+        if (next < items) stage(next, 2, 4);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -259,6 +268,7 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
                 }
         }
         pair_bar();  // (3) the 19 x 96 output tile is complete; V is no longer read
+        if (next < items) stage(next, 4, 6);
         for (int row = st_slot; row < kTokens && st_slot < 2; row += 2) {
             const int c4 = st_c4;
             const float4 v = *(const float4*)(sO + row * AS_OUT_PITCH + 4 * c4);
@@ -276,7 +286,8 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
                 }
             }
         }
-        pair_bar();  // (4) the tile is stored before the next item's cp.async overwrites it
+        pair_bar();  // (4) the tile is stored before the next item's Q overwrites it
+        if (next < items) stage(next, 0, 2);
     }
 }
 
