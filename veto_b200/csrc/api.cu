@@ -110,6 +110,17 @@ bool stats_in_epilogue() {
     return on != 0;
 }
 
+// q, k, v between to_qkv and attention_split in the (sequence, head) item layout (common.cuh qkv_item_offset);
+// VETO_QKV_ITEM_LAYOUT=0 keeps the row-major [rows, 1728] arrays (A/B measurements)
+bool qkv_item_layout_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("VETO_QKV_ITEM_LAYOUT");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 // VETO_LN_FUSION=0 keeps the LayerNorm kernels everywhere (A/B measurements, diagnosis)
 bool ln_fusion_enabled() {
     static int on = -1;
@@ -361,10 +372,12 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
             const bool split_qkv = split_attention_enabled() && prec != VETO_PREC_FP32 && prec != VETO_PREC_BF16;
             __nv_bfloat16* qkv_hi = (__nv_bfloat16*)qkv;
             __nv_bfloat16* qkv_lo = qkv_hi + (size_t)M * 3 * kDim;
+            const bool item_qkv = split_qkv && qkv_item_layout_enabled();
             if (split_qkv) {
                 e1.out.hi = qkv_hi;
                 e1.out.lo = qkv_lo;
                 e1.out.fmt = FMT_BF16;
+                e1.qkv_item_layout = item_qkv;
             } else {
                 e1.out.f32 = qkv;
             }
@@ -384,7 +397,7 @@ extern "C" int veto_relation_forward(const veto_config* cfg, const veto_weights*
                 if ((rc = linear(prec, xn, kDim, wq, M, 3 * kDim, kDim, e1, s))) return rc;
             }
             set_tag(TAG_ATT);
-            if (split_qkv) rc = attention_seq_split(qkv_hi, qkv_lo, rc_pairs, xn.out(), s);
+            if (split_qkv) rc = attention_seq_split(qkv_hi, qkv_lo, rc_pairs, xn.out(), item_qkv, s);
             else rc = attention_seq(qkv, rc_pairs, xn.out(), s);
             if (rc) return rc;
             GemmEpilogue e2;

@@ -51,7 +51,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 
 __global__ void __launch_bounds__(AS_THREADS, 1)
 attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo, int64_t n_seq,
-                       float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int fmt) {
+                       float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int fmt, int item_layout) {
     extern __shared__ __align__(16) uint8_t as_smem[];
     constexpr int LD = 3 * kDim;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -78,18 +78,23 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
     // 60 of the pair's 64 lanes own (row slot, chunk) once and for all, so that every copy is two additions away from its
     // addresses (the flat index -> (array, row, chunk) decode of the first version cost a quarter of the kernel's instructions)
     auto stage = [&](int64_t it, int a0, int a1) {
+        // item layout (common.cuh qkv_item_offset): the item's q, k, v are three contiguous 19 x 96 blocks — 3.6 KB runs
+        // per array instead of 192-byte segments 3456 bytes apart; row-major layout: [rows, 1728]
         const int64_t sq = it / kHeads;
-        const size_t gb = (size_t)sq * kTokens * LD + (int)(it - sq * kHeads) * kHeadDim;
+        const size_t gb = item_layout ? (size_t)it * 3 * (kTokens * kHeadDim)
+                                      : (size_t)sq * kTokens * LD + (int)(it - sq * kHeads) * kHeadDim;
+        const size_t arr_stride = item_layout ? (size_t)(kTokens * kHeadDim) : (size_t)kDim;
+        const size_t row_stride = item_layout ? (size_t)kHeadDim : (size_t)LD;
         if (ld_slot < 5) {
             for (int a = a0; a < a1; ++a) {
-                const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gb + (a >> 1) * kDim + ld_chunk * 8;
+                const __nv_bfloat16* src = ((a & 1) ? qkv_lo : qkv_hi) + gb + (a >> 1) * arr_stride + ld_chunk * 8;
                 __nv_bfloat16* dst = arr + a * AS_ARR + ld_chunk * 8;
 #pragma unroll
                 for (int r0 = 0; r0 < 20; r0 += 5) {
                     const int row = r0 + ld_slot;
                     if (row < kTokens)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + row * AS_PITCH)),
-                                     "l"(src + (size_t)row * LD) : "memory");
+                                     "l"(src + (size_t)row * row_stride) : "memory");
                 }
             }
         }
@@ -293,7 +298,8 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
 
 }  // namespace
 
-int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int64_t n_seq, const ActOut& out, cudaStream_t s) {
+int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int64_t n_seq, const ActOut& out, bool item_layout,
+                        cudaStream_t s) {
     if (n_seq <= 0) return VETO_OK;
     VETO_REQUIRE(qkv_hi && qkv_lo && (out.hi || out.f32), VETO_ERR_ARG, "attention_seq_split: missing argument");
     static DeviceOnce attr_set;
@@ -303,7 +309,7 @@ int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo
     }
     const int64_t blocks = (n_seq * kHeads + AS_PAIRS - 1) / AS_PAIRS;
     const int grid = (int)(blocks < (int64_t)num_sms() ? blocks : (int64_t)num_sms());
-    attention_split_kernel<<<grid, AS_THREADS, AS_SMEM, s>>>(qkv_hi, qkv_lo, n_seq, out.f32, out.hi, out.lo, out.fmt);
+    attention_split_kernel<<<grid, AS_THREADS, AS_SMEM, s>>>(qkv_hi, qkv_lo, n_seq, out.f32, out.hi, out.lo, out.fmt, item_layout ? 1 : 0);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -286,7 +286,15 @@ struct GemmEpilogue {
     long long ln_parts_rows = 0;      //   epilogue wrote (plane stride in rows); the epilogue reduces them itself
     float2* stats_partials = nullptr; // [N / 64][M] partial (sum, sum of squares) of the OUTPUT rows (ln_stats_finalize)
     ActOut res_op;                    // residual given in OPERAND format (hi / lo / fmt; row stride ldr) instead of `residual`
+    bool qkv_item_layout = false;     // to_qkv for attention_split.cu (N = 1728, hi / lo outputs, M = whole sequences): element
+                                      //   (seq * 19 + tok, which * 576 + head * 96 + d) goes to qkv_item_offset(...) — every
+                                      //   (sequence, head)'s q, k, v as three contiguous 19 x 96 blocks instead of 192-byte
+                                      //   segments strided by a 3456-byte row
 };
+// offset of (row, col) of the [rows, 1728] to_qkv output in the item layout (in elements of the hi / lo arrays)
+__host__ __device__ __forceinline__ size_t qkv_item_offset(int64_t seq, int tok, int which, int head, int d) {
+    return (((size_t)seq * kHeads + head) * 3 + which) * (size_t)(kTokens * kHeadDim) + (size_t)tok * kHeadDim + d;
+}
 // (mean, rstd) of LayerNorm (eps 1e-5) over rows of kDim from the partial sums a gemm_tc2 epilogue wrote
 int ln_stats_finalize(const float2* partials, int n_parts, int64_t rows, float2* stats, cudaStream_t s);
 
@@ -345,7 +353,8 @@ int layernorm_rows(const float* x, int64_t ldx, const float* w, const float* b, 
 int attention_seq(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
 // the same on q, k, v already split into bf16 hi + lo arrays [n_seq*19, 1728] (attention_split.cu; the to_qkv epilogue
 // of gemm_tc2 writes them): the inference path of the tensor-core modes with 16-bit-mantissa operands
-int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int64_t n_seq, const ActOut& out, cudaStream_t s);
+int attention_seq_split(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int64_t n_seq, const ActOut& out, bool item_layout,
+                        cudaStream_t s);
 // tcgen05 version (attention_tc.cu): six sequences per 128-row tile, bf16 hi/lo split when out.lo is given
 int attention_tc(const float* qkv, int64_t n_seq, const ActOut& out, cudaStream_t s);
 // the same for the CLS query row only (last encoder layer: only x[:,0] is consumed, model_veto.py:25):

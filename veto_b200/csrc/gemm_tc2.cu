@@ -127,14 +127,16 @@ struct EpiParams {
 //                  format only (+ row statistics): x never exists in fp32 between the layers (4.6 KB / row / layer less HBM
 //                  traffic for the HBM-bound to_out / FF2 launches; measured effect on the logits: 8.4e-5 -> 8.8e-5)
 //   EPI_RESOP_F32  the same residual source, fp32 result (the CLS rows of the last layer)
+//   EPI_QKV / EPI_QKV_LN  EPI_OP / EPI_OP_LN with the outputs in the (sequence, head) item layout of common.cuh
+//                  qkv_item_offset: q, k, v of an item as three contiguous 19 x 96 blocks for attention_split.cu
 enum { EPI_GENERIC = 0, EPI_F32, EPI_F32_LN, EPI_RES, EPI_RES_OPS, EPI_GELU_OP, EPI_GELU_OP_LN, EPI_OP, EPI_OP_LN, EPI_RESOP_OPS,
-       EPI_RESOP_F32, EPI_COUNT };
+       EPI_RESOP_F32, EPI_QKV, EPI_QKV_LN, EPI_COUNT };
 __host__ __device__ constexpr int epi_warps(int epi) {
     // to_qkv (256-wide tiles: 225 KB of shared memory either way).  The GELU epilogues run 16 warps on their 256-wide
     // instances only (explicit EW argument at the launch): on 192-wide tiles 16 warps cross from 193 KB to 201 KB, i.e. into
     // the next shared-memory configuration of the SM (60 -> 28 KB of L1), which cost FF1 more than the fourth warp per lane
     // quarter gained (70.5 -> 72.3 ms per step).
-    return (epi == EPI_F32 || epi == EPI_F32_LN || epi == EPI_OP || epi == EPI_OP_LN) ? 16 : 12;
+    return (epi == EPI_F32 || epi == EPI_F32_LN || epi == EPI_OP || epi == EPI_OP_LN || epi == EPI_QKV || epi == EPI_QKV_LN) ? 16 : 12;
 }
 
 // four consecutive residual values from the operand format (flat element offset off, off % 4 == 0)
@@ -377,12 +379,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int rsub = lane >> 2, cg = lane & 3;
         int it = 0;
         if constexpr (EPI != EPI_GENERIC) {
-            constexpr bool kLnIn = EPI == EPI_F32_LN || EPI == EPI_GELU_OP_LN || EPI == EPI_OP_LN;
+            constexpr bool kItems = EPI == EPI_QKV || EPI == EPI_QKV_LN;
+            constexpr bool kLnIn = EPI == EPI_F32_LN || EPI == EPI_GELU_OP_LN || EPI == EPI_OP_LN || EPI == EPI_QKV_LN;
             constexpr bool kResOp = EPI == EPI_RESOP_OPS || EPI == EPI_RESOP_F32;       // residual read from operand format
             constexpr bool kResid = EPI == EPI_RES || EPI == EPI_RES_OPS || kResOp;
             constexpr bool kGelu = EPI == EPI_GELU_OP || EPI == EPI_GELU_OP_LN;
             constexpr bool kOutF32 = EPI == EPI_F32 || EPI == EPI_F32_LN || EPI == EPI_RES || EPI == EPI_RES_OPS || EPI == EPI_RESOP_F32;
-            constexpr bool kOutOp = kGelu || EPI == EPI_RES_OPS || EPI == EPI_OP || EPI == EPI_OP_LN || EPI == EPI_RESOP_OPS;
+            constexpr bool kOutOp = kGelu || EPI == EPI_RES_OPS || EPI == EPI_OP || EPI == EPI_OP_LN || EPI == EPI_RESOP_OPS || kItems;
             constexpr bool kStats = EPI == EPI_RES_OPS || EPI == EPI_RESOP_OPS;
             static_assert(!kStats || BN == 192, "the row-statistics partials are laid out for 192-wide tiles");
             constexpr bool kBias = kResid || kGelu || kLnIn;
@@ -476,12 +479,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 const bool rows_full = m0 + 32 <= M, fmt_c8 = ep.out_fmt == FMT_F16C8;
+                size_t item_row[kItems ? 4 : 1];   // item layout: the row's part of the offset (its sequence and token)
+                if constexpr (kItems) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = m0 + rr * 8 + rsub;
+                        const int sq = row / kTokens;
+                        item_row[rr] = qkv_item_offset(sq, row - sq * kTokens, 0, 0, 0);
+                    }
+                }
                 auto chunk_rows = [&](int c, auto checked, auto c8fmt) {
                     constexpr bool kCheck = decltype(checked)::value, kC8 = decltype(c8fmt)::value;
                     const int col = n0 + c * EPI_COLS + cg * 4;
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if constexpr (kBias) bias4 = __ldg((const float4*)(ep.bias + col));
                     if constexpr (kLnIn) c1 = __ldg((const float4*)(ep.ln_c1 + col));
+                    size_t item_col = 0;   // item layout: the column's part (q / k / v block of its head, head dimension)
+                    if constexpr (kItems) {
+                        const int which = col / kDim, rem = col - which * kDim, hd = rem / kHeadDim;
+                        item_col = qkv_item_offset(0, 0, which, hd, rem - hd * kHeadDim);
+                    }
                     float4 vv[4];
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
@@ -509,7 +526,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                             if constexpr (kResid) {
                                 v.x += res[rr].x; v.y += res[rr].y; v.z += res[rr].z; v.w += res[rr].w;
                             }
-                            const size_t off = (size_t)row * ep.ldc + col;
+                            size_t off;
+                            if constexpr (kItems) off = item_row[rr] + item_col;
+                            else off = (size_t)row * ep.ldc + col;
 #ifdef VETO_TC2_DIAG
                             const bool st_ok = ep.diag != 2 || v.x == 1.2345678e-30f;
 #else
@@ -800,6 +819,7 @@ int init2() {
     VETO_TC2_ATTR(EPI_GENERIC, 192); VETO_TC2_ATTR(EPI_F32, 192); VETO_TC2_ATTR(EPI_F32_LN, 192); VETO_TC2_ATTR(EPI_RES, 192);
     VETO_TC2_ATTR(EPI_RES_OPS, 192); VETO_TC2_ATTR(EPI_GELU_OP, 192); VETO_TC2_ATTR(EPI_GELU_OP_LN, 192); VETO_TC2_ATTR(EPI_OP, 192);
     VETO_TC2_ATTR(EPI_OP_LN, 192); VETO_TC2_ATTR(EPI_RESOP_OPS, 192); VETO_TC2_ATTR(EPI_RESOP_F32, 192);
+    VETO_TC2_ATTR(EPI_QKV, 192); VETO_TC2_ATTR(EPI_QKV_LN, 192); VETO_TC2_ATTR(EPI_QKV, 256); VETO_TC2_ATTR(EPI_QKV_LN, 256);
     VETO_TC2_ATTR(EPI_GENERIC, 256); VETO_TC2_ATTR(EPI_F32, 256); VETO_TC2_ATTR(EPI_F32_LN, 256);
     VETO_TC2_ATTR(EPI_OP, 256); VETO_TC2_ATTR(EPI_OP_LN, 256);
     VETO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI_GELU_OP, 256, 2, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileN<256>::smem(16, 3)));
@@ -932,14 +952,16 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
     } else if (plain && ep.act == ACT_GELU && !ep.residual && ep.bias && ep.out.hi && !ep.out.f32 && !ep.stats_partials) {
         epi = ln_in ? EPI_GELU_OP_LN : EPI_GELU_OP;
     } else if (plain && ep.act == ACT_NONE && !ep.residual && ep.out.hi && !ep.out.f32 && !ep.stats_partials) {
-        if (ln_in) epi = EPI_OP_LN;
-        else if (!ep.bias) epi = EPI_OP;
+        if (ln_in) epi = ep.qkv_item_layout ? EPI_QKV_LN : EPI_OP_LN;
+        else if (!ep.bias) epi = ep.qkv_item_layout ? EPI_QKV : EPI_OP;
     }
+    VETO_REQUIRE(!ep.qkv_item_layout || ((epi == EPI_QKV || epi == EPI_QKV_LN) && N == 3 * kDim && M % kTokens == 0 && ep.out.fmt == FMT_BF16),
+                 VETO_ERR_ARG, "gemm_tc2: the item layout is for to_qkv's bf16 hi / lo outputs over whole sequences");
     VETO_REQUIRE(epi != EPI_GENERIC || (!ln_in && !ep.stats_partials && !ep.res_op.hi), VETO_ERR_UNSUPPORTED,
                  "gemm_tc2: LayerNorm fusion / row statistics exist for the inference epilogues only");
     static int force_generic = -1;   // VETO_GEMM_GENERIC_EPI=1: diagnosis, every launch through the run-time epilogue
     if (force_generic < 0) force_generic = getenv("VETO_GEMM_GENERIC_EPI") ? 1 : 0;
-    if (force_generic && !ln_in && !ep.stats_partials && !ep.res_op.hi) epi = EPI_GENERIC;
+    if (force_generic && !ln_in && !ep.stats_partials && !ep.res_op.hi && !ep.qkv_item_layout) epi = EPI_GENERIC;
     // 4-CTA clusters (W multicast between two row tiles) for the big two-array launches of the inference encoder.
     // Measured (profiles/r2_modes_cluster4_ab.jsonl): only 33 clusters of 4 are co-resident on the 148 SMs (132 SMs), the
     // step is 1.5 - 2 % SLOWER (to_qkv 89.7 -> 93.2 ms) although every SM does 7 - 8 % more work per unit time: a quarter
@@ -987,6 +1009,8 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
             case EPI_GELU_OP_LN: gemm_tc2_kernel<EPI_GELU_OP_LN, 256, 2, 3, 16><<<grid, num_threads(16), TileN<256>::smem(16, 3), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p); break;
             case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 256); break;
             case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 256); break;
+            case EPI_QKV: VETO_TC2_LAUNCH(EPI_QKV, 256); break;
+            case EPI_QKV_LN: VETO_TC2_LAUNCH(EPI_QKV_LN, 256); break;
             default: VETO_TC2_LAUNCH(EPI_GENERIC, 256); break;
         }
     } else {
@@ -1002,6 +1026,8 @@ int gemm_tc2(const GemmOperand& A, const GemmOperand& W, int M, int N, int K, in
             case EPI_GELU_OP_LN: VETO_TC2_LAUNCH(EPI_GELU_OP_LN, 192); break;
             case EPI_OP: VETO_TC2_LAUNCH(EPI_OP, 192); break;
             case EPI_OP_LN: VETO_TC2_LAUNCH(EPI_OP_LN, 192); break;
+            case EPI_QKV: VETO_TC2_LAUNCH(EPI_QKV, 192); break;
+            case EPI_QKV_LN: VETO_TC2_LAUNCH(EPI_QKV_LN, 192); break;
             case EPI_RESOP_OPS:
                 if (shallow) gemm_tc2_kernel<EPI_RESOP_OPS, 192, 2, 2><<<grid, num_threads(epi_warps(EPI_RESOP_OPS)), TileN<192>::smem(epi_warps(EPI_RESOP_OPS), 2), s>>>(ta_hi, ta_lo, tw_hi, tw_lo, M, N, K, passes, p);
                 else VETO_TC2_LAUNCH(EPI_RESOP_OPS, 192);
