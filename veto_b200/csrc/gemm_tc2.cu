@@ -1048,7 +1048,10 @@ int gemm_tc_auto(const GemmOperand& A, const GemmOperand& W, int M, int N, int K
         const char* e = getenv("VETO_GEMM_2CTA");
         use2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use2 && gemm_tc2_supported(N, K)) return gemm_tc2(A, W, M, N, K, passes, ep, s);  // any M: one K order
+    // what only the pair kernel implements (the fused inference epilogues, the fp16-based product schemes)
+    const bool pair_only = ep.ln_stats || ep.ln_parts || ep.stats_partials || ep.res_op.hi || ep.qkv_item_layout ||
+                           ep.out.fmt != FMT_BF16 || passes == TC_F16C8 || passes == TC_F16;
+    if ((use2 || pair_only) && gemm_tc2_supported(N, K)) return gemm_tc2(A, W, M, N, K, passes, ep, s);  // any M: one K order
     return gemm_tc(A, W, M, N, K, passes, ep, s);
 }
 
