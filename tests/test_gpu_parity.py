@@ -1021,10 +1021,11 @@ def test_attention_tcgen05_kernel(n_seq):
     assert rel_err(H.np_(ops.test_attention_tc(_t(qkv.numpy()), False)), ref) < 1e-2
 
 
-def test_gemm_cluster4_multicast_path():
-    """The opt-in 4-CTA-cluster variant of the encoder GEMMs (W tile multicast between two row tiles,
-    VETO_GEMM_CLUSTER4) must give the same logits bit for bit as the pair kernels: same tiles, same K order.  The switch
-    is read once per process, so both arms run in child processes."""
+def test_layout_and_schedule_switches_are_bit_identical():
+    """The switches of the library that only change WHERE or by WHICH CTA something is computed — the opt-in 4-CTA-cluster
+    variant of the encoder GEMMs (W tile multicast between two row tiles), the (sequence, head) item layout of q / k / v,
+    256-wide column tiles — must give the same logits bit for bit as the defaults: same products, same K order.  The switches are read once per process, so every arm runs in a
+    child process."""
     import os
     import subprocess
     import sys
@@ -1034,13 +1035,15 @@ def test_gemm_cluster4_multicast_path():
             " for p in ('f16c8', 'bf16x3') for r in T._run_predictor(n, p)[6][1]];"
             "np.save(sys.argv[1], np.concatenate(out))")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    arms = [{}, {"VETO_GEMM_CLUSTER4": "2"}, {"VETO_QKV_ITEM_LAYOUT": "0"}, {"VETO_GEMM_BN256": "0"}]
     outs = []
-    for mode in ("0", "2"):
-        path = os.path.join("/tmp", "veto_cluster4_%s_%d.npy" % (mode, os.getpid()))
-        env = dict(os.environ, VETO_GEMM_CLUSTER4=mode, PYTHONPATH=root)
+    for k, arm in enumerate(arms):
+        path = os.path.join("/tmp", "veto_switch_%d_%d.npy" % (k, os.getpid()))
+        env = dict(os.environ, PYTHONPATH=root, **arm)
         r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.returncode == 0, (arm, r.stderr[-2000:])
         outs.append(np.load(path))
         os.remove(path)
-    assert outs[0].shape == outs[1].shape and outs[0].size > 0
-    assert np.array_equal(outs[0], outs[1])
+    assert outs[0].size > 0
+    for arm, o in zip(arms[1:], outs[1:]):
+        assert o.shape == outs[0].shape and np.array_equal(o, outs[0]), arm

@@ -101,7 +101,8 @@ bool resop_enabled() {
 }
 
 // VETO_LN_STATS_EPILOGUE=1: (mean, rstd) of the LayerNorm-fused rows inside the consuming epilogues instead of by the
-// ln_stats_finalize launches (the same arithmetic, bit-identical results).  Measured SLOWER (profiles/
+// ln_stats_finalize launches (the same formula; the results agree to ~1e-4 of the logit range, not bit for bit — the
+// compiler contracts E[x^2] - mean^2 differently in the two places).  Measured SLOWER (profiles/
 // r2_modes_stats_epilogue_ab.jsonl): the 11 launches per chunk cost 3.1 ms per step, but the 36 extra loads per thread and
 // tile lengthen the to_qkv / FF1 epilogues by 7 and 10 ms — those epilogues are the critical path of their kernels.
 bool stats_in_epilogue() {
