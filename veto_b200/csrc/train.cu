@@ -261,9 +261,16 @@ dropout_kernel(float* __restrict__ x, size_t n4, DropSpec drop) {
 
 // fp32 -> activation storage format (no transpose), optionally through the dropout mask of element index e; 4 per thread
 __global__ void __launch_bounds__(256)
-convert_kernel(const float* __restrict__ src, size_t n4, DropSpec drop, float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+convert_kernel(const float* __restrict__ src, size_t n4, DropSpec drop, float* f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int act) {
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
         float4 v = __ldg((const float4*)src + g);
+        if (act != ACT_NONE) {   // the activation of the forward epilogue that produced the saved pre-activation: the
+            if (hi) {            // tensor-core GEMMs apply apply_act_tc, the fp32 SIMT GEMM apply_act (bit-identical re-computation)
+                v.x = apply_act_tc(v.x, act); v.y = apply_act_tc(v.y, act); v.z = apply_act_tc(v.z, act); v.w = apply_act_tc(v.w, act);
+            } else {
+                v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+            }
+        }
         if (drop.thr16) {
             const float4 d = drop_scale4(drop, g);
             v.x *= d.x; v.y *= d.y; v.z *= d.z; v.w *= d.w;
@@ -1255,10 +1262,10 @@ int dropout_inplace(float* x, size_t n, const DropSpec& drop, cudaStream_t s) {
     return VETO_OK;
 }
 
-int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s) {
+int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s, int act) {
     if (n == 0) return VETO_OK;
     VETO_REQUIRE(n % 4 == 0, VETO_ERR_ARG, "convert_act: element count must be a multiple of 4");
-    convert_kernel<<<grid_cap((n / 4 + 255) / 256, 8), 256, 0, s>>>(src, n / 4, drop, out.f32, out.hi, out.lo);
+    convert_kernel<<<grid_cap((n / 4 + 255) / 256, 8), 256, 0, s>>>(src, n / 4, drop, out.f32, out.hi, out.lo, act);
     VETO_LAUNCH_CHECK();
     return VETO_OK;
 }

@@ -39,7 +39,8 @@ int transpose_bf16(const __nv_bfloat16* src, int64_t ld_src, int64_t rows, int c
 int splitk_reduce(const float* partial, int slices, size_t n, size_t stride, float* out, cudaStream_t s);
 int dropout_inplace(float* x, size_t n, const DropSpec& drop, cudaStream_t s);
 // fp32 [n] -> activation storage format, optionally times the dropout keep-scale of element index e (n % 4 == 0)
-int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s);
+// fp32 -> activation storage format; act != ACT_NONE first applies the activation (re-computation of a saved pre-activation)
+int convert_act(const float* src, size_t n, const DropSpec& drop, const ActOut& out, cudaStream_t s, int act = ACT_NONE);
 
 // LayerNorm backward over rows of 576: dx = dres + dLN(dy) (dx may alias dres or dy), g_gamma / g_beta overwritten.
 // Optionally also writes op_out = dropout(dx) in the operand format of the next backward GEMMs and its column sums
