@@ -488,12 +488,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                         item_row[rr] = qkv_item_offset(sq, row - sq * kTokens, 0, 0, 0);
                     }
                 }
-                auto chunk_rows = [&](int c, auto checked, auto c8fmt) {
+                auto chunk_rows = [&](int c, const float4& bias4, const float4& c1, auto checked, auto c8fmt) {
                     constexpr bool kCheck = decltype(checked)::value, kC8 = decltype(c8fmt)::value;
                     const int col = n0 + c * EPI_COLS + cg * 4;
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (kBias) bias4 = __ldg((const float4*)(ep.bias + col));
-                    if constexpr (kLnIn) c1 = __ldg((const float4*)(ep.ln_c1 + col));
                     size_t item_col = 0;   // item layout: the column's part (q / k / v block of its head, head dimension)
                     if constexpr (kItems) {
                         const int which = col / kDim, rem = col - which * kDim, hd = rem / kHeadDim;
@@ -557,6 +554,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #ifdef VETO_TC2_DIAG
                     if (ep.diag == 4) return;
 #endif
+                    // the per-column constants first: their global-load latency then hides under the TMEM load and the staging
+                    // (issued where they are used they were the largest stall site of the to_qkv epilogue, profiles/
+                    // r2_gemm_stall_sites.txt)
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    {
+                        const int col = n0 + c * EPI_COLS + cg * 4;
+                        if constexpr (kBias) bias4 = __ldg((const float4*)(ep.bias + col));
+                        if constexpr (kLnIn) c1 = __ldg((const float4*)(ep.ln_c1 + col));
+                    }
                     uint32_t r[16];
                     tmem_ld16(taddr + c * EPI_COLS, r);
                     tmem_ld_wait();
@@ -576,11 +582,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     // and 3 ms: 70.9 -> 74.0) nor the residual ones (f16c8: no change; bf16x3: to_out 54 -> 64 ms), which keep
                     // the row-by-row form.
                     if (rows_full && !kGelu && !kResid) {
-                        if (fmt_c8) chunk_rows(c, std::false_type(), std::true_type());
-                        else chunk_rows(c, std::false_type(), std::false_type());
+                        if (fmt_c8) chunk_rows(c, bias4, c1, std::false_type(), std::true_type());
+                        else chunk_rows(c, bias4, c1, std::false_type(), std::false_type());
                     } else {
-                        if (fmt_c8) chunk_rows(c, std::true_type(), std::true_type());
-                        else chunk_rows(c, std::true_type(), std::false_type());
+                        if (fmt_c8) chunk_rows(c, bias4, c1, std::true_type(), std::true_type());
+                        else chunk_rows(c, bias4, c1, std::true_type(), std::false_type());
                     }
                     __syncwarp();
                 };
