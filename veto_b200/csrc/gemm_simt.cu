@@ -168,7 +168,7 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 // and for the lane-per-column reads), a warp owns a row of A at a time (staged in shared memory, read back as
 // broadcast float4), and lane j accumulates output columns j, j + 32, ...: every SM works, rows are independent and
 // the k order is fixed, so results do not depend on how the rows are chunked.
-constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32;
+constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32, SK_ROWS = 2;
 constexpr int SK_SMEM_FLOATS = 40960;  // 160 KB for the W^T tile
 
 template <int NCH>
@@ -178,16 +178,20 @@ gemm_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict
     extern __shared__ float sk_smem[];
     constexpr int NP = NCH * 32 + 1;
     float* sW = sk_smem;                         // [KT][NP]
-    float* sX = sk_smem + (size_t)KT * NP;       // [SK_WARPS][KT]
+    float* sX = sk_smem + (size_t)KT * NP;       // [SK_WARPS][SK_ROWS][KT]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* xs = sX + wid * KT;
-    const int rows_per_pass = gridDim.x * SK_WARPS;
+    float* xs = sX + wid * SK_ROWS * KT;
+    const int rows_per_pass = gridDim.x * SK_WARPS * SK_ROWS;
     const int passes = (M + rows_per_pass - 1) / rows_per_pass;
     for (int pass = 0; pass < passes; ++pass) {
-        const int row = pass * rows_per_pass + blockIdx.x * SK_WARPS + wid;
-        float acc[NCH];
+        // a warp owns SK_ROWS consecutive rows at a time: every W^T value read from shared memory feeds SK_ROWS FMAs (the
+        // one-row version was bound by its one shared-memory load per FMA)
+        const int row0 = pass * rows_per_pass + (blockIdx.x * SK_WARPS + wid) * SK_ROWS;
+        float acc[SK_ROWS][NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+        for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc[r][c] = 0.f;
         for (int k0 = 0; k0 < K; k0 += KT) {
             const int kt = (K - k0 < KT) ? K - k0 : KT;
             if (pass == 0 || K > KT) {           // the W^T tile stays resident when it holds all of K
@@ -198,33 +202,51 @@ gemm_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict
                 }
                 __syncthreads();
             }
-            if (row < M) {
-                for (int k = lane; k < kt; k += 32) xs[k] = __ldg(A + (size_t)row * lda + k0 + k);
+            if (row0 < M) {
+#pragma unroll
+                for (int r = 0; r < SK_ROWS; ++r) {
+                    const int row = min(row0 + r, M - 1);   // a row past the end repeats the last one; it is never stored
+                    for (int k = lane; k < kt; k += 32) xs[r * KT + k] = __ldg(A + (size_t)row * lda + k0 + k);
+                }
                 __syncwarp();
                 int k = 0;
                 for (; k + 3 < kt; k += 4) {
-                    const float4 x = *(const float4*)(xs + k);
+                    float4 x[SK_ROWS];
+#pragma unroll
+                    for (int r = 0; r < SK_ROWS; ++r) x[r] = *(const float4*)(xs + r * KT + k);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         const float* wp = sW + k * NP + lane + 32 * c;   // columns past N hold stale values: never stored
-                        acc[c] = fmaf(x.x, wp[0], acc[c]);
-                        acc[c] = fmaf(x.y, wp[NP], acc[c]);
-                        acc[c] = fmaf(x.z, wp[2 * NP], acc[c]);
-                        acc[c] = fmaf(x.w, wp[3 * NP], acc[c]);
+                        const float w0 = wp[0], w1 = wp[NP], w2 = wp[2 * NP], w3 = wp[3 * NP];
+#pragma unroll
+                        for (int r = 0; r < SK_ROWS; ++r) {
+                            acc[r][c] = fmaf(x[r].x, w0, acc[r][c]);
+                            acc[r][c] = fmaf(x[r].y, w1, acc[r][c]);
+                            acc[r][c] = fmaf(x[r].z, w2, acc[r][c]);
+                            acc[r][c] = fmaf(x[r].w, w3, acc[r][c]);
+                        }
                     }
                 }
                 for (; k < kt; ++k) {
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) acc[c] = fmaf(xs[k], sW[k * NP + lane + 32 * c], acc[c]);
+                    for (int c = 0; c < NCH; ++c) {
+                        const float wv = sW[k * NP + lane + 32 * c];
+#pragma unroll
+                        for (int r = 0; r < SK_ROWS; ++r) acc[r][c] = fmaf(xs[r * KT + k], wv, acc[r][c]);
+                    }
                 }
                 __syncwarp();
             }
         }
-        if (row < M) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int n = lane + 32 * c;
-                if (n < N) out[(size_t)row * ldc + n] = acc[c] + (bias ? bias[n] : 0.f);
+        for (int r = 0; r < SK_ROWS; ++r) {
+            const int row = row0 + r;
+            if (row < M) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int n = lane + 32 * c;
+                    if (n < N) out[(size_t)row * ldc + n] = acc[r][c] + (bias ? bias[n] : 0.f);
+                }
             }
         }
     }
@@ -236,13 +258,13 @@ int launch_skinny(const float* A, int lda, const float* W, int M, int N, int K, 
     constexpr int NP = NCH * 32 + 1;
     int KT = (SK_SMEM_FLOATS / NP) & ~3;
     if (KT > K) KT = (K + 3) & ~3;
-    const int smem = (KT * NP + SK_WARPS * KT) * (int)sizeof(float);
+    const int smem = (KT * NP + SK_WARPS * SK_ROWS * KT) * (int)sizeof(float);
     static DeviceOnce attr_set;
     if (attr_set.pending()) {
         VETO_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set.done();
     }
-    int grid = (M + SK_WARPS - 1) / SK_WARPS;
+    int grid = (M + SK_WARPS * SK_ROWS - 1) / (SK_WARPS * SK_ROWS);
     if (grid > num_sms()) grid = num_sms();
     gemm_skinny_kernel<NCH><<<grid, SK_THREADS, smem, s>>>(A, lda, W, M, N, K, KT, bias, out, ldc);
     VETO_LAUNCH_CHECK();
